@@ -1,0 +1,396 @@
+/* oracle (test infrastructure): scalar restatement of the MMseqs2 k-mer prefilter as Spacedust's
+ * clustersearch runs it (k=6 spaced 1101010011, VTML80 seeds, BLOSUM62 diagonal scoring).
+ * See orc_common.h for the rules that govern this directory. */
+#include "orc_common.h"
+#include <limits.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define KMER 6
+#define SPAN 10
+#define N3 8000          /* 20^3 */
+#define NK 64000000      /* 20^6 */
+static const int SEED_POS[KMER] = {0, 1, 3, 5, 8, 9};   /* Sequence.h:24 spaced_seed_6 */
+
+/* ---- extended 3-mer matrix: ExtendedSubstitutionMatrix::calcScoreMatrix (ExtendedSubstitutionMatrix.cpp:20-69).
+ * Row for 3-mer x: all 3-mers y sorted by score(x,y) descending; std::stable_sort over the cartesian
+ * product enumerated first-letter-major, so ties keep (y0,y1,y2) lexicographic order while the stored
+ * index is y0 + 20*y1 + 400*y2 (Indexer::int2index, Indexer.h:20-85). */
+typedef struct { short *score; unsigned short *index; } ext3_t;
+
+static void build_ext3(const short *sub /*21x21*/, ext3_t *e) {
+    e->score = (short *)malloc(sizeof(short) * (size_t)N3 * N3);
+    e->index = (unsigned short *)malloc(sizeof(unsigned short) * (size_t)N3 * N3);
+    short *tmpS = (short *)malloc(sizeof(short) * N3);
+    int cnt[512];
+    for (int x0 = 0; x0 < 20; x0++)
+        for (int x1 = 0; x1 < 20; x1++)
+            for (int x2 = 0; x2 < 20; x2++) {
+                int xi = x0 + 20 * x1 + 400 * x2;
+                /* counting sort by score (range -256..255), stable in enumeration order */
+                memset(cnt, 0, sizeof cnt);
+                int n = 0;
+                for (int y0 = 0; y0 < 20; y0++)
+                    for (int y1 = 0; y1 < 20; y1++)
+                        for (int y2 = 0; y2 < 20; y2++) {
+                            short s = (short)(sub[x0 * 21 + y0] + sub[x1 * 21 + y1] + sub[x2 * 21 + y2]);
+                            tmpS[n++] = s;
+                            cnt[255 - s]++;       /* bucket 0 = highest score */
+                        }
+                int start[512], acc = 0;
+                for (int b = 0; b < 512; b++) { start[b] = acc; acc += cnt[b]; }
+                n = 0;
+                short *rs = e->score + (size_t)xi * N3;
+                unsigned short *ri = e->index + (size_t)xi * N3;
+                for (int y0 = 0; y0 < 20; y0++)
+                    for (int y1 = 0; y1 < 20; y1++)
+                        for (int y2 = 0; y2 < 20; y2++) {
+                            short s = tmpS[n++];
+                            int p = start[255 - s]++;
+                            rs[p] = s;
+                            ri[p] = (unsigned short)(y0 + 20 * y1 + 400 * y2);
+                        }
+            }
+    free(tmpS);
+}
+
+/* ---- target index: IndexBuilder::fillDatabase (IndexBuilder.cpp:55-239), IndexTable::addKmerCount /
+ * addSequence (IndexTable.h:133-173, 348-401): k-mers without X whose self score >= kmerThr; each
+ * distinct k-mer of a sequence once, at its first position; buckets ordered by (seqId, pos). */
+typedef struct { uint32_t seq; uint16_t pos; } entry_t;
+typedef struct {
+    uint32_t *off;       /* NK + 1 */
+    entry_t *ent;
+    uint64_t nEnt;
+} index_t;
+
+typedef struct { uint32_t kmer; uint16_t pos; } kp_t;
+static int cmp_kp(const void *a, const void *b) {
+    const kp_t *x = (const kp_t *)a, *y = (const kp_t *)b;
+    if (x->kmer != y->kmer) return x->kmer < y->kmer ? -1 : 1;
+    if (x->pos != y->pos) return x->pos < y->pos ? -1 : 1;
+    return 0;
+}
+
+static uint32_t collect_kmers(const unsigned char *s, int L, const short *kmat, int thr, kp_t *buf) {
+    uint32_t n = 0;
+    for (int p = 0; p + SPAN <= L; p++) {
+        int hasX = 0, self = 0;
+        uint32_t idx = 0, mul = 1;
+        for (int k = 0; k < KMER; k++) {
+            unsigned char c = s[p + SEED_POS[k]];
+            if (c == ORC_X) { hasX = 1; break; }
+            self += (signed char)kmat[c * 21 + c];
+            idx += c * mul;
+            mul *= 20;
+        }
+        if (hasX) continue;
+        if (thr > 0 && self < thr) continue;
+        buf[n].kmer = idx;
+        buf[n].pos = (uint16_t)p;
+        n++;
+    }
+    if (n > 1) qsort(buf, n, sizeof(kp_t), cmp_kp);
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < n; i++)
+        if (i == 0 || buf[i].kmer != buf[i - 1].kmer) buf[m++] = buf[i];
+    return m;
+}
+
+static void build_index(const unsigned char *res, const uint64_t *off, uint32_t nT, const short *kmat,
+                        int thr, index_t *ix) {
+    ix->off = (uint32_t *)calloc((size_t)NK + 1, sizeof(uint32_t));
+    int maxL = 0;
+    for (uint32_t t = 0; t < nT; t++) {
+        int L = (int)(off[t + 1] - off[t]);
+        if (L > maxL) maxL = L;
+    }
+    kp_t *buf = (kp_t *)malloc(sizeof(kp_t) * (size_t)(maxL + 1));
+    for (uint32_t t = 0; t < nT; t++) {
+        uint32_t m = collect_kmers(res + off[t], (int)(off[t + 1] - off[t]), kmat, thr, buf);
+        for (uint32_t i = 0; i < m; i++) ix->off[buf[i].kmer + 1]++;
+    }
+    for (size_t k = 0; k < NK; k++) ix->off[k + 1] += ix->off[k];
+    ix->nEnt = ix->off[NK];
+    ix->ent = (entry_t *)malloc(sizeof(entry_t) * (size_t)(ix->nEnt + 1));
+    uint32_t *fill = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)NK);
+    memcpy(fill, ix->off, sizeof(uint32_t) * (size_t)NK);
+    for (uint32_t t = 0; t < nT; t++) {      /* ascending t => buckets already (seqId,pos)-sorted */
+        uint32_t m = collect_kmers(res + off[t], (int)(off[t + 1] - off[t]), kmat, thr, buf);
+        for (uint32_t i = 0; i < m; i++) {
+            entry_t *e = &ix->ent[fill[buf[i].kmer]++];
+            e->seq = t;
+            e->pos = buf[i].pos;
+        }
+    }
+    free(fill);
+    free(buf);
+}
+
+/* ---- ungapped diagonal score: UngappedAlignment::scalarDiagonalScoring / computeSingelSequenceScores
+ * (UngappedAlignment.cpp:30-43, 416-430).  profile[pos*21 + aa]; diag = i - j as a signed 16-bit value. */
+static int diag_score(const signed char *prof, int Lq, const unsigned char *t, int Lt, int diag,
+                      uint64_t *residues) {
+    int qs, ts, len;
+    if (diag >= 0) {
+        if (diag >= Lq) return 0;
+        qs = diag; ts = 0;
+        len = Lt < Lq - diag ? Lt : Lq - diag;
+    } else {
+        int d = -diag;
+        if (d >= Lt) return 0;
+        qs = 0; ts = d;
+        len = Lt - d < Lq ? Lt - d : Lq;
+    }
+    int best = 0, run = 0;
+    for (int p = 0; p < len; p++) {
+        run += prof[(qs + p) * 21 + t[ts + p]];
+        if (run < 0) run = 0;
+        if (run > best) best = run;
+    }
+    if (residues) *residues += (uint64_t)len;
+    return best;
+}
+
+typedef struct { uint32_t id; uint16_t diag; unsigned char count; } cand_t;
+typedef struct { uint32_t id; uint16_t diag; } hit_t;
+typedef struct { uint32_t seqId; int score; uint16_t diag; } res_t;
+
+static int cmp_res(const void *a, const void *b) {   /* hit_t::compareHitsByScoreAndId QueryMatcher.h:38-48 */
+    const res_t *x = (const res_t *)a, *y = (const res_t *)b;
+    int ax = abs(x->score), ay = abs(y->score);
+    if (ax != ay) return ax > ay ? -1 : 1;
+    if (x->seqId != y->seqId) return x->seqId < y->seqId ? -1 : 1;
+    return 0;
+}
+
+static int can_be_covered(float covThr, int covMode, float q, float t) {   /* Util.cpp:477-494 */
+    switch (covMode) {
+        case 0: return (q / t >= covThr) && (t / q >= covThr);
+        case 1: return (q / t) >= covThr;
+        case 2: return (t / q) >= covThr;
+        case 3: return ((t / q) >= covThr) && (t / q) <= 1.0;
+        case 4: return ((q / t) >= covThr) && (q / t) <= 1.0;
+        case 5: return ((t < q ? t : q) / (t > q ? t : q)) >= covThr;
+        default: return 1;
+    }
+}
+
+long orc_prefilter(const char *tSeq, const uint64_t *tOff, uint32_t nT,
+                   const char *qSeq, const uint64_t *qOff, uint32_t nQ,
+                   const orc_pref_params *par, orc_pref_hit *out, long outCap,
+                   orc_pref_stats *stats, unsigned char *maskedOut) {
+    orc_submat kmat, umat;
+    orc_build_submat(1, 8.0f, -0.2f, &kmat);      /* Prefiltering.cpp:68 seed matrix VTML80 x8  */
+    orc_build_submat(0, 2.0f, -0.2f, &umat);      /* Prefiltering.cpp:69 diagonal matrix BLOSUM62 x2 */
+    const int kmerThr = orc_kmer_threshold(par->sensitivity, KMER);
+    orc_pref_stats st;
+    memset(&st, 0, sizeof st);
+
+    /* target residues: map + mask (IndexBuilder.cpp:117-133) */
+    unsigned char *tres = (unsigned char *)malloc((size_t)tOff[nT] + 1);
+    orc_map_sequence(tSeq, (int)tOff[nT], tres);
+    if (par->mask)
+        for (uint32_t t = 0; t < nT; t++)
+            orc_tantan_mask(tres + tOff[t], (int)(tOff[t + 1] - tOff[t]), &kmat, (double)par->maskProb);
+    if (maskedOut) memcpy(maskedOut, tres, (size_t)tOff[nT]);
+
+    index_t ix;
+    build_index(tres, tOff, nT, kmat.sub, kmerThr, &ix);
+    ext3_t e3;
+    build_ext3(kmat.sub, &e3);
+
+    int maxLq = 0;
+    for (uint32_t q = 0; q < nQ; q++) {
+        int L = (int)(qOff[q + 1] - qOff[q]);
+        if (L > maxLq) maxLq = L;
+    }
+    unsigned char *qres = (unsigned char *)malloc((size_t)maxLq + 1);
+    float *bias = (float *)malloc(sizeof(float) * (size_t)(maxLq + 1));
+    signed char *prof = (signed char *)malloc((size_t)21 * (size_t)(maxLq + 1));
+    size_t hitCap = 1 << 20, nHit;
+    hit_t *hits = (hit_t *)malloc(sizeof(hit_t) * hitCap);
+    size_t candCap = 1 << 16, nCand;
+    cand_t *cand = (cand_t *)malloc(sizeof(cand_t) * candCap);
+    cand_t *tmp = (cand_t *)malloc(sizeof(cand_t) * candCap);
+    unsigned char *last = (unsigned char *)calloc((size_t)nT + 1, 1);
+    const size_t maxHits = (size_t)par->maxSeqs < (size_t)nT ? (size_t)par->maxSeqs : (size_t)nT;
+    res_t *res = (res_t *)malloc(sizeof(res_t) * (maxHits + 2));
+    const uint32_t binMask = (uint32_t)par->binSize - 1;
+    int binBits = 0;
+    while ((1u << binBits) < (uint32_t)par->binSize) binBits++;
+    long nOut = 0;
+
+    for (uint32_t q = 0; q < nQ; q++) {
+        const int L = (int)(qOff[q + 1] - qOff[q]);
+        orc_map_sequence(qSeq + qOff[q], L, qres);
+        st.queryResidues += (uint64_t)L;
+        /* QueryMatcher::matchQuery (QueryMatcher.cpp:85-107): bias from the SEED matrix */
+        if (par->compBias) orc_comp_bias(&kmat, qres, L, bias, 1.0f);
+        else memset(bias, 0, sizeof(float) * (size_t)L);
+        /* UngappedAlignment::createProfile (UngappedAlignment.cpp:385-414) */
+        for (int p = 0; p < L; p++) {
+            float b = bias[p];
+            b = (b < 0.0) ? b / 4 - 0.5 : b / 4 + 0.5;
+            signed char corr = (signed char)b;
+            for (int a = 0; a < 21; a++)
+                prof[p * 21 + a] = (signed char)(umat.sub[qres[p] * 21 + a] + corr);
+        }
+        /* QueryMatcher::match (QueryMatcher.cpp:213-346) + KmerGenerator (KmerGenerator.cpp:107-216) */
+        nHit = 0;
+        for (int p = 0; p + SPAN <= L; p++) {
+            unsigned char km[KMER];
+            int hasX = 0;
+            float bsum = 0;
+            for (int k = 0; k < KMER; k++) {
+                km[k] = qres[p + SEED_POS[k]];
+                if (km[k] == ORC_X) hasX = 1;
+                bsum += bias[p + SEED_POS[k]];
+            }
+            if (hasX) continue;
+            short b = (short)((bsum < 0.0) ? bsum - 0.5 : bsum + 0.5);
+            short thr = (short)(kmerThr - b > 0 ? kmerThr - b : 0);
+            uint32_t i1 = km[0] + 20u * km[1] + 400u * km[2];
+            uint32_t i2 = km[3] + 20u * km[4] + 400u * km[5];
+            const short *s1 = e3.score + (size_t)i1 * N3, *s2 = e3.score + (size_t)i2 * N3;
+            const unsigned short *x1 = e3.index + (size_t)i1 * N3, *x2 = e3.index + (size_t)i2 * N3;
+            short cutoff1 = (short)(thr - s2[0]);
+            for (int a = 0; a < N3 && s1[a] >= cutoff1; a++) {
+                short cutoff2 = (short)(thr - s1[a]);
+                for (int c = 0; c < N3 && s2[c] >= cutoff2; c++) {
+                    uint32_t kmer = x1[a] + (uint32_t)N3 * x2[c];
+                    st.probes++;
+                    uint32_t lo = ix.off[kmer], hi = ix.off[kmer + 1];
+                    if (nHit + (hi - lo) > hitCap) {
+                        while (nHit + (hi - lo) > hitCap) hitCap *= 2;
+                        hits = (hit_t *)realloc(hits, sizeof(hit_t) * hitCap);
+                    }
+                    for (uint32_t e = lo; e < hi; e++) {
+                        hits[nHit].id = ix.ent[e].seq;
+                        hits[nHit].diag = (uint16_t)(p - ix.ent[e].pos);
+                        nHit++;
+                    }
+                }
+            }
+        }
+        st.matches += nHit;
+        /* CacheFriendlyOperations::findDuplicates (CacheFriendlyOperations.cpp:185-274): per radix bin
+         * (id & mask), walk hits in arrival order; a hit is kept when its 8-bit diagonal equals the
+         * previous 8-bit diagonal seen for that target (table starts at 0); kept hits of one target
+         * with equal consecutive 8-bit diagonals collapse to the first. */
+        nCand = 0;
+        if (nHit + 1 > candCap) {
+            while (nHit + 1 > candCap) candCap *= 2;
+            cand = (cand_t *)realloc(cand, sizeof(cand_t) * candCap);
+            tmp = (cand_t *)realloc(tmp, sizeof(cand_t) * candCap);
+        }
+        for (uint32_t bin = 0; bin <= binMask; bin++) {
+            size_t nTmp = 0;
+            for (size_t h = 0; h < nHit; h++) {
+                if ((hits[h].id & binMask) != bin) continue;
+                uint32_t slot = hits[h].id >> binBits;
+                unsigned char d8 = (unsigned char)hits[h].diag;
+                if (d8 == last[slot]) { tmp[nTmp].id = hits[h].id; tmp[nTmp].diag = hits[h].diag; nTmp++; }
+                last[slot] = d8;
+            }
+            for (size_t n = nTmp; n-- > 0;) last[tmp[n].id >> binBits] = (unsigned char)((unsigned char)tmp[n].diag + 1);
+            for (size_t n = 0; n < nTmp; n++) {
+                uint32_t slot = tmp[n].id >> binBits;
+                unsigned char d8 = (unsigned char)tmp[n].diag;
+                if (last[slot] != d8) { cand[nCand].id = tmp[n].id; cand[nCand].diag = tmp[n].diag; cand[nCand].count = 0; nCand++; }
+                last[slot] = d8;
+            }
+            for (size_t h = 0; h < nHit; h++)
+                if ((hits[h].id & binMask) == bin) last[hits[h].id >> binBits] = 0;
+        }
+        st.candidates += nCand;
+        /* UngappedAlignment::align (UngappedAlignment.cpp:25-27, 331-362): score every candidate, cap 255 */
+        for (size_t c = 0; c < nCand; c++) {
+            uint32_t t = cand[c].id;
+            int s = diag_score(prof, L, tres + tOff[t], (int)(tOff[t + 1] - tOff[t]), (short)cand[c].diag,
+                               &st.diagResidues);
+            cand[c].count = (unsigned char)(s > 255 ? 255 : s);
+        }
+        /* keepMaxScoreElementOnly (CacheFriendlyOperations.cpp:350-380): per target the first element
+         * carrying the maximal score; output again bin-major, arrival order inside a bin. */
+        size_t nKeep = 0;
+        for (uint32_t bin = 0; bin <= binMask; bin++) {
+            for (size_t c = 0; c < nCand; c++) {
+                if ((cand[c].id & binMask) != bin) continue;
+                uint32_t slot = cand[c].id >> binBits;
+                if (cand[c].count > last[slot]) last[slot] = cand[c].count;
+            }
+            for (size_t c = 0; c < nCand; c++) {
+                if ((cand[c].id & binMask) != bin) continue;
+                uint32_t slot = cand[c].id >> binBits;
+                int found = (last[slot] == cand[c].count);
+                if (found) tmp[nKeep++] = cand[c];
+                last[slot] = (unsigned char)(last[slot] * (1 - found));
+            }
+            for (size_t c = 0; c < nCand; c++)
+                if ((cand[c].id & binMask) == bin) last[cand[c].id >> binBits] = 0;
+        }
+        /* score histogram -> threshold (QueryMatcher.h:206-216), stable order by score desc
+         * (radixSortByScoreSize QueryMatcher.cpp:498-523), getResult (QueryMatcher.cpp:363-420) */
+        unsigned int histo[256];
+        memset(histo, 0, sizeof histo);
+        for (size_t c = 0; c < nKeep; c++) histo[tmp[c].count]++;
+        size_t found = 0;
+        unsigned int thr;
+        for (thr = 255; thr > 0; thr--) {
+            found += histo[thr];
+            if (found >= maxHits) break;
+        }
+        if (thr < (unsigned int)par->minDiagScore) thr = (unsigned int)par->minDiagScore;
+        if (thr >= 255) {
+            fprintf(stderr, "orc_prefilter: query %u needs the truncated-score rescoring path (not restated)\n", q);
+            return -2;
+        }
+        size_t nAbove = 0;
+        for (int s = 255; s >= (int)thr; s--)
+            for (size_t c = 0; c < nKeep; c++)
+                if (tmp[c].count == s) cand[nAbove++] = tmp[c];
+        size_t nRes = 0;
+        uint32_t identity = par->sameDB ? q : UINT_MAX;
+        if (identity != UINT_MAX) { res[0].seqId = identity; res[0].score = 65535; res[0].diag = 0; nRes = 1; }
+        size_t eligible = 0;
+        for (size_t c = 0; c < nAbove; c++) {
+            if (cand[c].id == identity) continue;
+            eligible++;
+            if (nRes >= maxHits) continue;
+            res[nRes].seqId = cand[c].id;
+            res[nRes].score = cand[c].count;
+            res[nRes].diag = cand[c].diag;
+            if (cand[c].count >= 255) {
+                uint32_t t = cand[c].id;
+                res[nRes].score = diag_score(prof, L, tres + tOff[t], (int)(tOff[t + 1] - tOff[t]),
+                                             (short)cand[c].diag, NULL);
+            }
+            nRes++;
+        }
+        if (eligible + (identity != UINT_MAX ? 1 : 0) > nRes) st.truncated++;
+        if (nRes > 1) {
+            if (identity != UINT_MAX) qsort(res + 1, nRes - 1, sizeof(res_t), cmp_res);
+            else qsort(res, nRes, sizeof(res_t), cmp_res);
+        }
+        st.hits += nRes;
+        /* Prefiltering::runSplit (Prefiltering.cpp:845-869): coverage pre-filter, then write */
+        for (size_t r = 0; r < nRes; r++) {
+            uint32_t t = res[r].seqId;
+            if (par->covThr > 0.0 && (par->covMode == 0 || par->covMode == 2 || par->covMode == 5)) {
+                if (!can_be_covered(par->covThr, par->covMode, (float)L, (float)(tOff[t + 1] - tOff[t]))) continue;
+            }
+            if (nOut >= outCap) return -1;
+            out[nOut].query = q;
+            out[nOut].target = t;
+            out[nOut].score = res[r].score;
+            out[nOut].diag = (int16_t)res[r].diag;
+            nOut++;
+        }
+    }
+    if (stats) *stats = st;
+    free(tres); free(ix.off); free(ix.ent); free(e3.score); free(e3.index);
+    free(qres); free(bias); free(prof); free(hits); free(cand); free(tmp); free(last); free(res);
+    return nOut;
+}

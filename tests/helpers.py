@@ -1,0 +1,177 @@
+"""Shared test helpers: MMseqs2 flat-file DB access, the oracle (ctypes), the reference binary."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_BIN = os.path.join(ORACLE_DIR, "_ref", "spacedust")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+# ----------------------------------------------------------------------------- DB files
+def read_index(path):
+    """<db>.index -> list of (key, offset, length) in file order."""
+    out = []
+    with open(path + ".index") as f:
+        for line in f:
+            k, o, l = line.split("\t")
+            out.append((int(k), int(o), int(l)))
+    return out
+
+
+def read_db(path):
+    """Return {key: bytes-without-trailing-NUL}.  Accepts merged DBs and per-thread splits
+    (<db>.0 .. <db>.N-1 concatenated in order, as DBReader does)."""
+    if os.path.exists(path):
+        data = open(path, "rb").read()
+    else:
+        parts = []
+        i = 0
+        while os.path.exists("%s.%d" % (path, i)):
+            parts.append(open("%s.%d" % (path, i), "rb").read())
+            i += 1
+        data = b"".join(parts)
+    out = {}
+    for k, o, l in read_index(path):
+        out[k] = data[o:o + l - 1]
+    return out
+
+
+def read_db_entries(path):
+    """Entries in index order, keys may repeat (matches/clusters DBs)."""
+    if os.path.exists(path):
+        data = open(path, "rb").read()
+    else:
+        parts = []
+        i = 0
+        while os.path.exists("%s.%d" % (path, i)):
+            parts.append(open("%s.%d" % (path, i), "rb").read())
+            i += 1
+        data = b"".join(parts)
+    return [(k, data[o:o + l - 1]) for k, o, l in read_index(path)]
+
+
+def load_seqdb(path):
+    """Sequence DB -> (keys, concatenated ASCII residues (np.uint8), offsets (np.uint64, n+1)).
+    Order = ascending data offset (DBReader LINEAR_ACCCESS), residues exclude the trailing newline."""
+    idx = sorted(read_index(path), key=lambda e: e[1])
+    data = open(path, "rb").read()
+    keys = np.array([e[0] for e in idx], dtype=np.uint32)
+    lens = np.array([e[2] - 2 for e in idx], dtype=np.uint64)
+    off = np.zeros(len(idx) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    buf = np.empty(int(off[-1]), dtype=np.uint8)
+    raw = np.frombuffer(data, dtype=np.uint8)
+    for i, (k, o, l) in enumerate(idx):
+        buf[int(off[i]):int(off[i + 1])] = raw[o:o + l - 2]
+    return keys, buf, off
+
+
+def read_fasta(path):
+    names, seqs = [], []
+    cur = []
+    for line in open(path):
+        line = line.rstrip("\n")
+        if line.startswith(">"):
+            if names:
+                seqs.append("".join(cur))
+            names.append(line[1:])
+            cur = []
+        else:
+            cur.append(line)
+    if names:
+        seqs.append("".join(cur))
+    return names, seqs
+
+
+def pack_seqs(seqs):
+    lens = np.array([len(s) for s in seqs], dtype=np.uint64)
+    off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    buf = np.frombuffer("".join(seqs).encode(), dtype=np.uint8).copy()
+    return buf, off
+
+
+# ----------------------------------------------------------------------------- oracle
+class OrcPrefParams(ctypes.Structure):
+    _fields_ = [("sensitivity", ctypes.c_float), ("maxSeqs", ctypes.c_int), ("minDiagScore", ctypes.c_int),
+                ("covThr", ctypes.c_float), ("covMode", ctypes.c_int), ("mask", ctypes.c_int),
+                ("maskProb", ctypes.c_float), ("compBias", ctypes.c_int), ("binSize", ctypes.c_int),
+                ("sameDB", ctypes.c_int)]
+
+
+class OrcPrefStats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in
+                ("probes", "matches", "diagResidues", "queryResidues", "hits", "candidates", "truncated")]
+
+
+ORC_HIT_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("score", "<i4"), ("diag", "<i2")], align=True)
+
+_orc = None
+
+
+def build_oracle():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+    return os.path.join(ORACLE_DIR, "_build", "liborc.so")
+
+
+def oracle():
+    global _orc
+    if _orc is None:
+        path = os.path.join(ORACLE_DIR, "_build", "liborc.so")
+        if not os.path.exists(path):
+            build_oracle()
+        _orc = ctypes.CDLL(path)
+        _orc.orc_prefilter.restype = ctypes.c_long
+    return _orc
+
+
+def default_pref_params(**kw):
+    p = OrcPrefParams(sensitivity=5.7, maxSeqs=300, minDiagScore=15, covThr=0.8, covMode=2, mask=1,
+                      maskProb=0.9, compBias=1, binSize=2, sameDB=1)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def orc_prefilter(tbuf, toff, qbuf, qoff, params, want_masked=False):
+    lib = oracle()
+    nT, nQ = len(toff) - 1, len(qoff) - 1
+    cap = max(1024, nQ * (params.maxSeqs + 1))
+    out = np.zeros(cap, dtype=ORC_HIT_DTYPE)
+    stats = OrcPrefStats()
+    masked = np.zeros(len(tbuf), dtype=np.uint8) if want_masked else None
+    n = lib.orc_prefilter(tbuf.ctypes.data_as(ctypes.c_char_p), toff.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(nT),
+                          qbuf.ctypes.data_as(ctypes.c_char_p), qoff.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(nQ),
+                          ctypes.byref(params), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(cap),
+                          ctypes.byref(stats), masked.ctypes.data_as(ctypes.c_void_p) if want_masked else None)
+    if n < 0:
+        raise RuntimeError("orc_prefilter failed: %d" % n)
+    st = {f[0]: getattr(stats, f[0]) for f in OrcPrefStats._fields_}
+    return (out[:n], st, masked) if want_masked else (out[:n], st)
+
+
+def hits_to_lines(hits, qkeys, tkeys):
+    """-> {queryKey: [b'tKey\\tscore\\tdiag', ...]} in output order (prefilterHitToBuffer QueryMatcher.h:118-130)."""
+    d = {int(k): [] for k in qkeys}
+    for h in hits:
+        d[int(qkeys[h["query"]])].append(b"%d\t%d\t%d" % (int(tkeys[h["target"]]), int(h["score"]), int(h["diag"])))
+    return d
+
+
+# ----------------------------------------------------------------------------- reference binary
+def have_ref():
+    return os.path.exists(REF_BIN) and os.access(REF_BIN, os.X_OK)
+
+
+def run_ref(args, cwd=None, threads=None):
+    env = dict(os.environ)
+    env["MMSEQS_FORCE_MERGE"] = "1"
+    r = subprocess.run([REF_BIN] + [str(a) for a in args], cwd=cwd, env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT)
+    if r.returncode != 0:
+        raise RuntimeError("reference failed: %s\n%s" % (args, r.stdout.decode()[-2000:]))
+    return r.stdout.decode()
