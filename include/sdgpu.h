@@ -1,0 +1,110 @@
+/*
+ * sdgpu.h -- C ABI of libsdgpu.so, the B200 (sm_100a) implementation of the Spacedust
+ * `clustersearch --search-mode 0` hot path.
+ *
+ * The reference (soedinglab/spacedust) has no in-process plugin interface for this path: every
+ * stage is a module `int f(int argc, const char **argv, const Command&)`
+ * (lib/mmseqs/src/commons/Command.h:94-105) run as its own process by data/clustersearch.sh:112-151
+ * and lib/mmseqs/data/workflow/blastp.sh:70,85, talking through flat-file DBs.  The entry points below
+ * are therefore what a binding for that path has to offer: one call per reference module body, on
+ * plain host pointers, so that a maintainer can replace the body of
+ *   Prefiltering::runSplit      (lib/mmseqs/src/prefiltering/Prefiltering.cpp:725-951)  -> sd_prefilter_*
+ *   Alignment::run              (lib/mmseqs/src/alignment/Alignment.cpp:248-542)        -> sd_align_*
+ *   clusterhits() pair loop     (src/util/ClusterHits.cpp:294-490)                      -> sd_clusterhits_*
+ * with a call into this library (INTEGRATION.md shows the stubs).  No torch / C++ types cross the
+ * boundary.  All functions return 0 on success and a negative SD_E* code on failure;
+ * sd_last_error() returns a thread-local message (the reference prints via Debug(Debug::ERROR) and
+ * EXIT(EXIT_FAILURE), lib/mmseqs/src/commons/MMseqsMPI.h:28-36 -- the front-end does the same with
+ * this message).  There is no CPU fallback: without a CUDA device every compute entry point fails
+ * with SD_ENODEV.
+ */
+#ifndef SDGPU_H
+#define SDGPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD_OK 0
+#define SD_EINVAL (-1)   /* bad argument                                  */
+#define SD_ENODEV (-2)   /* no CUDA device / CUDA runtime error           */
+#define SD_ENOMEM (-3)   /* host or device allocation failed              */
+#define SD_ELIMIT (-4)   /* an implementation limit was hit (see message) */
+#define SD_ESMALL (-5)   /* caller's output buffer too small              */
+
+typedef struct sd_context sd_context;        /* one per process per GPU            */
+typedef struct sd_target_index sd_target_index; /* device-resident target DB + k-mer index */
+
+const char *sd_last_error(void);
+int sd_version(void);
+
+/* device < 0: use the current CUDA device. */
+int sd_context_create(int device, sd_context **out);
+void sd_context_destroy(sd_context *ctx);
+/* Number of CUDA kernels launched through this context since creation. */
+uint64_t sd_context_launches(const sd_context *ctx);
+
+/* ---- prefilter (reference flags of `prefilter`) ---------------------- */
+typedef struct {
+    float sensitivity;        /* -s                     (5.7)  */
+    int max_seqs;             /* --max-seqs             (300)  */
+    int min_ungapped_score;   /* --min-ungapped-score   (15)   */
+    float cov_thr;            /* -c                     (0.8)  */
+    int cov_mode;             /* --cov-mode             (2)    */
+    int mask;                 /* --mask                 (1)    */
+    float mask_prob;          /* --mask-prob            (0.9)  */
+    int comp_bias_corr;       /* --comp-bias-corr       (1)    */
+    int bin_size;             /* tie-order radix of the reference when --max-seqs truncates; 0 = derive it
+                                 like QueryMatcher::initDiagonalMatcher (QueryMatcher.cpp:422-449) from the
+                                 host L2 size and the number of targets */
+    int same_db;              /* query DB is the target DB: identity hit first with score 65535 */
+} sd_prefilter_params;
+
+void sd_prefilter_params_default(sd_prefilter_params *p);
+
+typedef struct {
+    uint32_t query;           /* index of the query in the call's query array   */
+    uint32_t target;          /* index of the target in the index's target array */
+    int32_t score;            /* ungapped diagonal score (65535 for identity)   */
+    int16_t diag;             /* i - j, printed as signed short by the reference */
+    int16_t pad;
+} sd_prefilter_hit;
+
+typedef struct {
+    uint64_t probes;          /* P: similar k-mers looked up                    */
+    uint64_t matches;         /* M: index entries returned                      */
+    uint64_t diag_residues;   /* R: residues read by the diagonal scorer        */
+    uint64_t query_residues;  /* sum of query lengths                           */
+    uint64_t hits;            /* H: hits before the coverage pre-filter         */
+    uint64_t candidates;      /* diagonal-scored (target, diagonal) candidates  */
+    uint64_t truncated;       /* queries cut by --max-seqs                      */
+    double kernel_ms;         /* device time of the main prefilter kernel(s), CUDA events */
+    double total_ms;          /* device time of the whole call incl. copies     */
+} sd_prefilter_stats;
+
+/* Build the device-resident target side: residue mapping, tantan masking, k-mer index
+ * (IndexBuilder::fillDatabase, lib/mmseqs/src/prefiltering/IndexBuilder.cpp:55-239).
+ * seqs: ASCII residues of all targets concatenated; off[n+1]: byte offsets. */
+int sd_target_index_build(sd_context *ctx, const char *seqs, const uint64_t *off, uint32_t n,
+                          const sd_prefilter_params *par, sd_target_index **out);
+void sd_target_index_destroy(sd_target_index *idx);
+/* Copy the masked numeric residues (sum of lengths bytes) back; test hook. */
+int sd_target_index_masked(const sd_target_index *idx, uint8_t *out, uint64_t cap);
+uint64_t sd_target_index_entries(const sd_target_index *idx);
+
+/* Run the prefilter for nq queries against the index (body of the query loop of
+ * Prefiltering::runSplit, Prefiltering.cpp:790-880).  Hits are grouped by query in query order;
+ * inside a query they are in the reference's output order.  query_first (optional) is the index of
+ * query 0 in the target array when same_db is set (identity = query_first + q).
+ * Returns SD_ESMALL (and *n_hits = required) when cap is too small. */
+int sd_prefilter_run(sd_context *ctx, const sd_target_index *idx, const char *qseqs,
+                     const uint64_t *qoff, uint32_t nq, uint32_t query_first,
+                     const sd_prefilter_params *par, sd_prefilter_hit *hits, uint64_t cap,
+                     uint64_t *n_hits, sd_prefilter_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

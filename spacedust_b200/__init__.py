@@ -1,0 +1,154 @@
+"""spacedust_b200 -- B200 (sm_100a) implementation of the Spacedust `clustersearch` hot path.
+
+This package is a thin ctypes view of ``libsdgpu.so`` (CUDA kernels + C ABI, ``include/sdgpu.h``) used
+by the tests and by ``bench.py``; the product itself is the shared library and the ``sdb200`` front-end
+binary built from ``spacedust_b200/csrc``.  There is no CPU fallback: every compute call raises
+``SdError`` when the library or a CUDA device is missing.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsdgpu.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+
+class SdError(RuntimeError):
+    pass
+
+
+class PrefilterParams(ctypes.Structure):
+    """Mirrors sd_prefilter_params (flags of the reference's `prefilter` module)."""
+    _fields_ = [("sensitivity", ctypes.c_float), ("max_seqs", ctypes.c_int), ("min_ungapped_score", ctypes.c_int),
+                ("cov_thr", ctypes.c_float), ("cov_mode", ctypes.c_int), ("mask", ctypes.c_int),
+                ("mask_prob", ctypes.c_float), ("comp_bias_corr", ctypes.c_int), ("bin_size", ctypes.c_int),
+                ("same_db", ctypes.c_int)]
+
+
+class PrefilterStats(ctypes.Structure):
+    _fields_ = [("probes", ctypes.c_uint64), ("matches", ctypes.c_uint64), ("diag_residues", ctypes.c_uint64),
+                ("query_residues", ctypes.c_uint64), ("hits", ctypes.c_uint64), ("candidates", ctypes.c_uint64),
+                ("truncated", ctypes.c_uint64), ("kernel_ms", ctypes.c_double), ("total_ms", ctypes.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+HIT_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("score", "<i4"), ("diag", "<i2"), ("pad", "<i2")])
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile libsdgpu.so in-tree (nvcc, sm_100a)."""
+    r = subprocess.run(["make", "-C", CSRC], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    if verbose or r.returncode != 0:
+        print(r.stdout.decode())
+    if r.returncode != 0:
+        raise SdError("building libsdgpu.so failed")
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SdError("libsdgpu.so is missing (%s); run `python -c 'import __graft_entry__ as g; g.build()'` -- "
+                          "there is no CPU fallback" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.sd_last_error.restype = ctypes.c_char_p
+        L.sd_context_launches.restype = ctypes.c_uint64
+        L.sd_target_index_entries.restype = ctypes.c_uint64
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise SdError("libsdgpu error %d: %s" % (rc, lib().sd_last_error().decode()))
+
+
+def default_prefilter_params(**kw):
+    p = PrefilterParams()
+    lib().sd_prefilter_params_default(ctypes.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class Context:
+    def __init__(self, device=-1):
+        self._h = ctypes.c_void_p()
+        _check(lib().sd_context_create(ctypes.c_int(device), ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().sd_context_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    @property
+    def launches(self):
+        return int(lib().sd_context_launches(self._h))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _seq_args(buf, off):
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    return buf, off
+
+
+class TargetIndex:
+    """Device-resident target DB + k-mer index (IndexBuilder::fillDatabase counterpart)."""
+
+    def __init__(self, ctx, seqs, off, params):
+        self.ctx = ctx
+        self.seqs, self.off = _seq_args(seqs, off)
+        self.n = len(self.off) - 1
+        self._h = ctypes.c_void_p()
+        _check(lib().sd_target_index_build(ctx._h, self.seqs.ctypes.data_as(ctypes.c_char_p),
+                                           self.off.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(self.n),
+                                           ctypes.byref(params), ctypes.byref(self._h)))
+
+    @property
+    def entries(self):
+        return int(lib().sd_target_index_entries(self._h))
+
+    def masked_residues(self):
+        out = np.zeros(int(self.off[-1]), dtype=np.uint8)
+        _check(lib().sd_target_index_masked(self._h, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(len(out))))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().sd_target_index_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def prefilter(ctx, index, qseqs, qoff, params, query_first=0):
+    """Body of the reference's prefilter query loop for a batch of queries -> (hits, stats)."""
+    qseqs, qoff = _seq_args(qseqs, qoff)
+    nq = len(qoff) - 1
+    cap = max(1, nq * min(max(params.max_seqs, 1), index.n))
+    hits = np.zeros(cap, dtype=HIT_DTYPE)
+    n = ctypes.c_uint64(0)
+    st = PrefilterStats()
+    _check(lib().sd_prefilter_run(ctx._h, index._h, qseqs.ctypes.data_as(ctypes.c_char_p),
+                                  qoff.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(nq), ctypes.c_uint32(query_first),
+                                  ctypes.byref(params), hits.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(cap),
+                                  ctypes.byref(n), ctypes.byref(st)))
+    return hits[:n.value], st.as_dict()

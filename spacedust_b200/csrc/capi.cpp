@@ -1,0 +1,52 @@
+// C ABI plumbing of libsdgpu.so: error slot, context life cycle.
+#include "sd_internal.h"
+
+#include <cstring>
+
+namespace sd {
+static thread_local char g_err[1024] = "";
+void setError(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+}  // namespace sd
+
+extern "C" const char *sd_last_error(void) { return sd::g_err; }
+extern "C" int sd_version(void) { return 100; }
+
+extern "C" int sd_context_create(int device, sd_context **out) {
+    if (!out) { sd::setError("sd_context_create: out is NULL"); return SD_EINVAL; }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        sd::setError("no CUDA device available (%s); libsdgpu has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "0 devices");
+        return SD_ENODEV;
+    }
+    if (device < 0) SD_CUDA(cudaGetDevice(&device));
+    if (device >= count) { sd::setError("device %d out of range (%d devices)", device, count); return SD_EINVAL; }
+    SD_CUDA(cudaSetDevice(device));
+    sd_context *ctx = new sd_context();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    SD_CUDA(cudaGetDeviceProperties(&prop, device));
+    ctx->smCount = prop.multiProcessorCount;
+    SD_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    sd::buildSubMat(sd::VTML80, 8.0f, -0.2f, ctx->seedMat);
+    sd::buildSubMat(sd::BLOSUM62, 2.0f, -0.2f, ctx->diagMat);
+    sd::buildSubMat(sd::BLOSUM62, 2.0f, 0.0f, ctx->alnMat);
+    *out = ctx;
+    return SD_OK;
+}
+
+extern "C" void sd_context_destroy(sd_context *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->e3score.release();
+    ctx->e3index.release();
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" uint64_t sd_context_launches(const sd_context *ctx) { return ctx ? ctx->launches : 0; }

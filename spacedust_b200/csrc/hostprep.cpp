@@ -1,0 +1,253 @@
+#include "hostprep.h"
+#include "matrix_data.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cctype>
+#include <cmath>
+#include <cstring>
+#include <thread>
+#include <unistd.h>
+
+namespace sd {
+
+void buildSubMat(MatrixId which, float bitFactor, float scoreBias, SubMat &out) {
+    const double (*S)[21] = which == BLOSUM62 ? sd_blosum62_scores : sd_vtml80_scores;
+    const double *bg = which == BLOSUM62 ? sd_blosum62_background : sd_vtml80_background;
+    const double lambda = which == BLOSUM62 ? sd_blosum62_lambda : sd_vtml80_lambda;
+    // readProbMatrix (SubstitutionMatrix.cpp:315-397): background of the 20 letters is scaled by
+    // (1 - p_X) because no X score is positive; joint P_ab = exp(lambda S_ab) p_a p_b
+    for (int a = 0; a < AA; a++) out.pBack[a] = bg[a];
+    for (int a = 0; a < AA - 1; a++) out.pBack[a] = out.pBack[a] * (1.0 - out.pBack[XCODE]);
+    for (int a = 0; a < AA; a++)
+        for (int b = 0; b < AA; b++)
+            out.prob[a * AA + b] = std::exp(lambda * S[a][b]) * out.pBack[a] * out.pBack[b];
+    // generateSubMatrix (BaseMatrix.cpp:110-159): marginals are re-derived as row sums (X pinned to
+    // 1e-5), scores = round-half-away(bitFactor*log2(P_ab/(r_a r_b)) + bias)
+    double marg[AA];
+    for (int a = 0; a < AA; a++) {
+        double s = 0;
+        for (int b = 0; b < AA; b++) s += out.prob[a * AA + b];
+        marg[a] = s;
+    }
+    marg[XCODE] = 1E-5;
+    const double bf = bitFactor, sb = scoreBias;
+    for (int a = 0; a < AA; a++)
+        for (int b = 0; b < AA; b++) {
+            const double v = bf * std::log2(out.prob[a * AA + b] / (marg[a] * marg[b])) + sb;
+            out.sub[a * AA + b] = static_cast<short>((v < 0.0) ? v - 0.5 : v + 0.5);
+        }
+}
+
+static uint8_t g_map[256];
+static std::atomic<bool> g_mapReady{false};
+
+const uint8_t *aa2num() {
+    if (!g_mapReady.load(std::memory_order_acquire)) {
+        uint8_t direct[256];
+        std::memset(direct, 0xFF, sizeof direct);
+        for (int i = 0; i < AA; i++) direct[static_cast<unsigned char>(sd_blosum62_letters[i])] = static_cast<uint8_t>(i);
+        uint8_t tmp[256];
+        for (int c = 0; c < 256; c++) {
+            const int u = std::toupper(c);
+            uint8_t code = XCODE;
+            if (u == 'J') code = direct['L'];
+            else if (u == 'B') code = direct['D'];
+            else if (u == 'Z') code = direct['E'];
+            else if (u >= 0 && u < 256 && direct[u] != 0xFF) code = direct[u];
+            tmp[c] = code;
+        }
+        std::memcpy(g_map, tmp, sizeof tmp);
+        g_mapReady.store(true, std::memory_order_release);
+    }
+    return g_map;
+}
+
+void mapSequence(const char *s, uint64_t len, uint8_t *out) {
+    const uint8_t *m = aa2num();
+    for (uint64_t i = 0; i < len; i++) out[i] = m[static_cast<unsigned char>(s[i])];
+}
+
+void likelihoodRatios(const SubMat &m, double *lr) {
+    // ProbabilityMatrix ctor (lib/mmseqs/src/commons/BaseMatrix.h:83-96)
+    for (int a = 0; a < AA; a++)
+        for (int b = 0; b < AA; b++) lr[a * AA + b] = m.prob[a * AA + b] / (m.pBack[a] * m.pBack[b]);
+}
+
+// Repeat-HMM posterior masking.  States: background + W repeat offsets, gap states disabled (MMseqs2
+// passes firstGapProb = otherGapProb = 0).  The reference build sums the foreground vector with four
+// interleaved AVX2 lanes, reduced as (l0+l2)+(l1+l3), followed by a scalar tail; the same association
+// is used here so the doubles agree.
+int tantanMask(uint8_t *seq, int L, const double *lr, double minMaskProb) {
+    constexpr int W = 50;
+    if (L <= 0) return 0;
+    const double pRepeat = 0.005, pEnd = 0.05, decay = 0.9;
+    const double bb = 1 - pRepeat, fb = pEnd, ff = 1 - pEnd;
+    double toFgProb[W], fg[W];
+    {
+        double p = pRepeat * ((1 - decay) / (1 - std::pow(decay, W)));
+        for (int i = 0; i < W; i++) { toFgProb[i] = p; p *= decay; }
+    }
+    std::vector<float> post(L);
+    std::vector<double> scale(L / 16 + 1);
+    double bg = 1.0;
+    std::fill(fg, fg + W, 0.0);
+    for (int p = 0; p < L; p++) {
+        const double *row = lr + seq[p] * AA;
+        const int reach = std::min(p, W);
+        const double b = bg;
+        double lane[4] = {0, 0, 0, 0};
+        int i = 0;
+        for (; i + 4 <= reach; i += 4) {
+            for (int k = 0; k < 4; k++) {
+                const double f = fg[i + k];
+                lane[k] = lane[k] + f;
+                fg[i + k] = (b * toFgProb[i + k] + f * ff) * row[seq[p - 1 - i - k]];
+            }
+        }
+        double fromFg = (lane[0] + lane[2]) + (lane[1] + lane[3]);
+        for (; i < reach; i++) {
+            const double f = fg[i];
+            fromFg += f;
+            fg[i] = (b * toFgProb[i] + f * ff) * row[seq[p - 1 - i]];
+        }
+        bg = b * bb + fromFg * fb;
+        if ((p & 15) == 15) {
+            const double s = 1 / bg;
+            scale[p >> 4] = s;
+            bg *= s;
+            for (int k = 0; k < W; k++) fg[k] *= s;
+        }
+        post[p] = static_cast<float>(bg);
+    }
+    double fgTotal = 0.0;
+    for (int i = 0; i < W; i++) fgTotal += fg[i];
+    const double z = bg * bb + fgTotal * fb;
+    bg = bb;
+    std::fill(fg, fg + W, fb);
+    for (int p = L - 1; p >= 0; p--) {
+        const double notRepeat = post[p] * bg / z;
+        post[p] = 1 - static_cast<float>(notRepeat);
+        if ((p & 15) == 15) {
+            const double s = scale[p >> 4];
+            bg *= s;
+            for (int k = 0; k < W; k++) fg[k] *= s;
+        }
+        const double *row = lr + seq[p] * AA;
+        const int reach = std::min(p, W);
+        const double toBg = fb * bg;
+        double lane[4] = {0, 0, 0, 0};
+        int i = 0;
+        for (; i + 4 <= reach; i += 4) {
+            for (int k = 0; k < 4; k++) {
+                const double f = fg[i + k] * row[seq[p - 1 - i - k]];
+                lane[k] = lane[k] + toFgProb[i + k] * f;
+                fg[i + k] = toBg + ff * f;
+            }
+        }
+        double toFg = (lane[0] + lane[2]) + (lane[1] + lane[3]);
+        for (; i < reach; i++) {
+            const double f = fg[i] * row[seq[p - 1 - i]];
+            toFg += toFgProb[i] * f;
+            fg[i] = toBg + ff * f;
+        }
+        bg = bb * bg + toFg;
+    }
+    int masked = 0;
+    for (int p = 0; p < L; p++)
+        if (post[p] >= minMaskProb) { seq[p] = XCODE; masked++; }
+    return masked;
+}
+
+uint64_t tantanMaskAll(uint8_t *res, const uint64_t *off, uint32_t n, const SubMat &seedMat, double minMaskProb) {
+    double lr[AA * AA];
+    likelihoodRatios(seedMat, lr);
+    unsigned nThreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    if (n < 64) nThreads = 1;
+    std::atomic<uint32_t> next{0};
+    std::atomic<uint64_t> total{0};
+    auto work = [&]() {
+        uint64_t mine = 0;
+        for (;;) {
+            const uint32_t lo = next.fetch_add(64);
+            if (lo >= n) break;
+            const uint32_t hi = std::min(n, lo + 64);
+            for (uint32_t s = lo; s < hi; s++) mine += tantanMask(res + off[s], static_cast<int>(off[s + 1] - off[s]), lr, minMaskProb);
+        }
+        total += mine;
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nThreads; t++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+    return total.load();
+}
+
+int kmerThreshold(float sensitivity, int kmerSize) {
+    float best;
+    if (kmerSize == 5) { float base = 160.75; best = base - (sensitivity * 12.75); }
+    else if (kmerSize == 6) { float base = 163.2; best = base - (sensitivity * 8.917); }
+    else { float base = 186.15; best = base - (sensitivity * 11.22); }
+    return static_cast<int>(best);
+}
+
+void buildExt3(const SubMat &seedMat, std::vector<int16_t> &score, std::vector<uint16_t> &index) {
+    constexpr int N3 = 8000;
+    score.resize(static_cast<size_t>(N3) * N3);
+    index.resize(static_cast<size_t>(N3) * N3);
+    // pair tables first: s2[x0,x1][y0,y1] would be 160k entries; the triple loop below is cheap enough
+    unsigned nThreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    std::atomic<int> nextRow{0};
+    auto work = [&]() {
+        std::vector<int16_t> rowScore(N3);
+        for (;;) {
+            const int x = nextRow.fetch_add(16);
+            if (x >= N3) break;
+            for (int xr = x; xr < std::min(N3, x + 16); xr++) {
+                const int x0 = xr % 20, x1 = (xr / 20) % 20, x2 = xr / 400;   // stored index = x0 + 20 x1 + 400 x2
+                const short *r0 = seedMat.sub + x0 * AA, *r1 = seedMat.sub + x1 * AA, *r2 = seedMat.sub + x2 * AA;
+                int histo[512] = {0};
+                int e = 0;
+                for (int y0 = 0; y0 < 20; y0++)
+                    for (int y1 = 0; y1 < 20; y1++) {
+                        const int s01 = r0[y0] + r1[y1];
+                        for (int y2 = 0; y2 < 20; y2++) {
+                            const int16_t s = static_cast<int16_t>(s01 + r2[y2]);
+                            rowScore[e++] = s;
+                            histo[255 - s]++;
+                        }
+                    }
+                int base = 0;
+                for (int h = 0; h < 512; h++) { const int c = histo[h]; histo[h] = base; base += c; }
+                int16_t *outS = score.data() + static_cast<size_t>(xr) * N3;
+                uint16_t *outI = index.data() + static_cast<size_t>(xr) * N3;
+                e = 0;
+                for (int y0 = 0; y0 < 20; y0++)
+                    for (int y1 = 0; y1 < 20; y1++)
+                        for (int y2 = 0; y2 < 20; y2++) {
+                            const int16_t s = rowScore[e++];
+                            const int slot = histo[255 - s]++;
+                            outS[slot] = s;
+                            outI[slot] = static_cast<uint16_t>(y0 + 20 * y1 + 400 * y2);
+                        }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nThreads; t++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+}
+
+int referenceBinSize(uint64_t nTargets) {
+    uint64_t l2 = 262144;
+#if defined(_SC_LEVEL2_CACHE_SIZE)
+    const long v = sysconf(_SC_LEVEL2_CACHE_SIZE);
+    if (v > 0) l2 = static_cast<uint64_t>(v);
+#endif
+    for (int b = 2; b <= 1024; b *= 2)
+        if (nTargets / b < l2) return b;
+    return 2048;
+}
+
+}  // namespace sd

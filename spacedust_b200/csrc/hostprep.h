@@ -1,0 +1,45 @@
+// Host-side preparation shared by the CUDA stages: substitution matrices, residue mapping,
+// tantan masking of targets, the sorted 3-mer neighbour table.  Small double-precision pieces the
+// reference also runs once per process; they stay on the host in the reference's operation order
+// (hard part 4).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace sd {
+
+constexpr int AA = 21;     // alphabet incl. X
+constexpr int XCODE = 20;
+
+struct SubMat {
+    short sub[AA * AA];
+    double pBack[AA];
+    double prob[AA * AA];
+};
+
+enum MatrixId { BLOSUM62 = 0, VTML80 = 1 };
+
+// SubstitutionMatrix ctor (lib/mmseqs/src/commons/SubstitutionMatrix.cpp:12-57) for the two shipped tables.
+void buildSubMat(MatrixId which, float bitFactor, float scoreBias, SubMat &out);
+
+// SubstitutionMatrix::setupLetterMapping (SubstitutionMatrix.cpp:257-298)
+const uint8_t *aa2num();
+void mapSequence(const char *s, uint64_t len, uint8_t *out);
+
+// Masker::maskSequence -> tantan::maskSequences (lib/mmseqs/src/commons/Masker.cpp:52-92)
+int tantanMask(uint8_t *seq, int L, const double *lr /*AA*AA likelihood ratios*/, double minMaskProb);
+void likelihoodRatios(const SubMat &m, double *lr);
+// mask all sequences in place with a pool of host threads; returns masked residue count
+uint64_t tantanMaskAll(uint8_t *res, const uint64_t *off, uint32_t n, const SubMat &seedMat, double minMaskProb);
+
+// Prefiltering::getKmerThreshold (Prefiltering.cpp:1005-1065), amino-acid sequence branch
+int kmerThreshold(float sensitivity, int kmerSize);
+
+// ExtendedSubstitutionMatrix::calcScoreMatrix for 3-mers (ExtendedSubstitutionMatrix.cpp:20-69):
+// row x = all 8000 3-mers ordered by score desc, ties in first-letter-major enumeration order.
+void buildExt3(const SubMat &seedMat, std::vector<int16_t> &score, std::vector<uint16_t> &index);
+
+// QueryMatcher::initDiagonalMatcher (QueryMatcher.cpp:422-449) + Util::getL2CacheSize (Util.cpp:317-332)
+int referenceBinSize(uint64_t nTargets);
+
+}  // namespace sd

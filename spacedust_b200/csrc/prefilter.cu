@@ -1,0 +1,925 @@
+// k-mer prefilter on B200 (sm_100a): target index build, query preparation, and the fused
+// similar-k-mer / index probe / double-diagonal-hit / ungapped-diagonal-score / top-N kernel.
+//
+// Reference behaviour restated here (all paths relative to /root/reference/lib/mmseqs/src):
+//   prefiltering/IndexBuilder.cpp:55-239, IndexTable.h:133-173,348-401   target index
+//   prefiltering/QueryMatcher.cpp:85-346                                  matchQuery / match
+//   prefiltering/KmerGenerator.cpp:107-216                                similar k-mer list (order!)
+//   prefiltering/CacheFriendlyOperations.cpp:185-274,350-380              double hit / best diagonal
+//   prefiltering/UngappedAlignment.cpp:30-43,385-430                      diagonal score
+//   prefiltering/QueryMatcher.cpp:363-420, QueryMatcher.h:38-48,206-216   threshold, top-N, sort
+//   prefiltering/Prefiltering.cpp:845-869                                 coverage pre-filter
+//
+// Design: one warp owns one query at a time and walks its similar-k-mer probes in the
+// reference's stream order, 32 probes / 32 index entries per step, so the order-dependent double-hit
+// rule ("same 8-bit diagonal as the previous hit of this target") is evaluated with __match_any_sync
+// inside the step and a per-warp last-diagonal table in HBM between steps.  No sort, no atomics on
+// the hit stream; the stream itself is never materialised.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <memory>
+#include <numeric>
+
+#include "sd_internal.h"
+
+namespace sd {
+
+__constant__ int c_seedPos[KMER] = {0, 1, 3, 5, 8, 9};
+
+// ------------------------------------------------------------------------------------------------
+// small warp helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t laneId() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ uint32_t warpExclusiveScan(uint32_t v, uint32_t &total) {
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (laneId() >= (uint32_t)d) x += y;
+    }
+    total = __shfl_sync(0xffffffffu, x, 31);
+    return x - v;
+}
+
+// largest lane j with excl[j] <= x  (x < total); every lane must call
+__device__ __forceinline__ uint32_t warpFindOwner(uint32_t excl, uint32_t x) {
+    uint32_t lo = 0, hi = 31;
+#pragma unroll
+    for (int it = 0; it < 5; it++) {
+        uint32_t mid = (lo + hi + 1) >> 1;
+        uint32_t v = __shfl_sync(0xffffffffu, excl, mid);
+        if (v <= x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// index build
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t seqOfPosition(const uint32_t *off, uint32_t n, uint32_t gp) {
+    uint32_t lo = 0, hi = n;   // find s with off[s] <= gp < off[s+1]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= gp) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// key = seq<<42 | kmer<<16 | pos for indexable k-mers, ~0 otherwise (IndexTable::addKmerCount)
+__global__ void extractTargetKmers(const uint8_t *__restrict__ res, const uint32_t *__restrict__ off, uint32_t nT,
+                                   uint32_t totalRes, const int8_t *__restrict__ selfScore, int kmerThr,
+                                   uint64_t *__restrict__ keys) {
+    uint32_t gp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gp >= totalRes) return;
+    uint32_t s = seqOfPosition(off, nT, gp);
+    uint32_t p = gp - off[s];
+    uint32_t L = off[s + 1] - off[s];
+    uint64_t key = ~0ull;
+    if (p + SPAN <= L && p < 65536u) {
+        uint32_t idx = 0, mul = 1;
+        int self = 0;
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < KMER; k++) {
+            uint8_t c = res[gp + c_seedPos[k]];
+            ok = ok && (c < 20);
+            self += selfScore[c];
+            idx += (uint32_t)c * mul;
+            mul *= 20;
+        }
+        if (ok && !(kmerThr > 0 && self < kmerThr)) key = ((uint64_t)s << 42) | ((uint64_t)idx << 16) | p;
+    }
+    keys[gp] = key;
+}
+
+// after sorting by (seq,kmer,pos): the first key of each (seq,kmer) run is the entry the reference keeps
+__global__ void firstOccurrence(const uint64_t *__restrict__ sorted, uint32_t n, uint32_t *__restrict__ kmerKey,
+                                uint64_t *__restrict__ payload, uint32_t *__restrict__ kCount) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = sorted[i];
+    bool keep = (k != ~0ull) && (i == 0 || (sorted[i - 1] >> 16) != (k >> 16));
+    uint32_t kmer = (uint32_t)((k >> 16) & 0x3ffffffu);
+    kmerKey[i] = keep ? kmer : 0xffffffffu;
+    payload[i] = ((k >> 42) << 16) | (k & 0xffffu);   // seq<<16 | pos
+    if (keep) atomicAdd(&kCount[kmer], 1u);
+}
+
+__global__ void splitEntries(const uint64_t *__restrict__ payload, uint64_t n, uint32_t *__restrict__ entSeq,
+                             uint16_t *__restrict__ entPos) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t v = payload[i];
+    entSeq[i] = (uint32_t)(v >> 16);
+    entPos[i] = (uint16_t)(v & 0xffffu);
+}
+
+// ------------------------------------------------------------------------------------------------
+// query preparation
+// ------------------------------------------------------------------------------------------------
+struct QueryBatchDev {
+    const uint8_t *code;     // residue codes, concatenated
+    const uint32_t *off;     // nQ+1
+    const int8_t *corr;      // per-position profile correction  (UngappedAlignment::createProfile)
+    const int16_t *thr;      // per-position similar-k-mer threshold, -1 = no k-mer here
+};
+
+__global__ void mapResidues(const char *__restrict__ ascii, uint64_t n, const uint8_t *__restrict__ lut,
+                            uint8_t *__restrict__ out) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = lut[(uint8_t)ascii[i]];
+}
+
+// SubstitutionMatrix::calcLocalAaBiasCorrection (commons/SubstitutionMatrix.cpp:79-109): the float
+// accumulator is updated through double intermediates; __dmul_rn/__dadd_rn keep nvcc from fusing.
+__global__ void compositionBias(const uint8_t *__restrict__ code, const uint32_t *__restrict__ off, uint32_t nQ,
+                                uint32_t totalRes, const int16_t *__restrict__ seedSub /*21x21*/,
+                                const double *__restrict__ pBack, int enabled, float *__restrict__ bias,
+                                int8_t *__restrict__ corr) {
+    uint32_t gp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gp >= totalRes) return;
+    float b = 0.0f;
+    if (enabled) {
+        uint32_t s = seqOfPosition(off, nQ, gp);
+        int i = (int)(gp - off[s]);
+        int L = (int)(off[s + 1] - off[s]);
+        int lo = max(0, i - 20), hi = min(L, i + 20);
+        const uint8_t *seq = code + off[s];
+        const int16_t *row = seedSub + seq[i] * AA;
+        int sum = 0;
+        for (int j = lo; j < hi; j++) sum += row[seq[j]];
+        sum -= row[seq[i]];
+        float d = (float)sum;
+        d = __double2float_rn(__ddiv_rn((double)d, __dmul_rn(-1.0, (double)(float)(hi - lo))));
+        for (int a = 0; a < AA; a++) d = __double2float_rn(__dadd_rn((double)d, __dmul_rn(pBack[a], (double)(float)row[a])));
+        b = __fmul_rn(1.0f, d);
+    }
+    bias[gp] = b;
+    // createProfile: aaCorrBias/4 -+ 0.5 evaluated in double, stored to float, truncated to char
+    float q = __fdiv_rn(b, 4.0f);
+    float r = (b < 0.0f) ? __double2float_rn(__dadd_rn((double)q, -0.5)) : __double2float_rn(__dadd_rn((double)q, 0.5));
+    corr[gp] = (int8_t)(int)r;
+}
+
+// QueryMatcher::match (QueryMatcher.cpp:226-244): per k-mer start, threshold = max(kmerThr - round(sum bias), 0)
+__global__ void kmerThresholds(const uint8_t *__restrict__ code, const uint32_t *__restrict__ off, uint32_t nQ,
+                               uint32_t totalRes, const float *__restrict__ bias, int kmerThr,
+                               int16_t *__restrict__ thr) {
+    uint32_t gp = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gp >= totalRes) return;
+    uint32_t s = seqOfPosition(off, nQ, gp);
+    uint32_t p = gp - off[s];
+    uint32_t L = off[s + 1] - off[s];
+    int16_t out = -1;
+    if (p + SPAN <= L) {
+        bool ok = true;
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < KMER; k++) {
+            ok = ok && (code[gp + c_seedPos[k]] < 20);
+            acc = __fadd_rn(acc, bias[gp + c_seedPos[k]]);
+        }
+        if (ok) {
+            double adj = (acc < 0.0f) ? __dadd_rn((double)acc, -0.5) : __dadd_rn((double)acc, 0.5);
+            short rb = (short)(int)adj;
+            int t = kmerThr - rb;
+            out = (int16_t)(t > 0 ? t : 0);
+        }
+    }
+    thr[gp] = out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the prefilter kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int PF_WARPS = 8;              // warps per CTA
+constexpr int PF_CAP2 = 1024;            // staged prefix of the second 3-mer's neighbour row
+
+struct PrefilterArgs {
+    // target side
+    const uint8_t *tRes;
+    const uint32_t *tOff;
+    uint32_t nT;
+    const uint32_t *kOff;
+    const uint32_t *entSeq;
+    const uint16_t *entPos;
+    const int16_t *e3score;
+    const uint16_t *e3index;
+    const int8_t *diagSub;     // 21x21 BLOSUM62 x2 (-0.2)
+    // query side
+    QueryBatchDev q;
+    uint32_t nQ;
+    const uint32_t *order;     // queries, longest first
+    uint32_t queryFirst;       // identity = queryFirst + q when sameDb
+    int sameDb;
+    // parameters
+    uint32_t maxHits;          // min(max_seqs, nT)
+    uint32_t minDiagScore;
+    float covThr;
+    int covMode;
+    uint32_t binMask;
+    // scratch
+    uint32_t *table;           // per warp: nT words
+    uint32_t candCap;
+    uint64_t *cand;            // per warp: candCap   (t<<32 | diag<<16 | score<<8)
+    uint64_t *keep;            // per warp: candCap   (t<<32 | diag<<16 | score<<8), emission order kept
+    uint32_t *resT;            // per warp: maxHits
+    int32_t *resScore;
+    uint16_t *resDiag;
+    // output
+    sd_prefilter_hit *out;     // nQ * maxHits
+    uint32_t *outCount;        // nQ
+    unsigned long long *stats; // [0]=probes [1]=matches [2]=diagResidues [3]=hits [4]=candidates [5]=truncated [6]=errors
+    uint32_t *nextQuery;
+    uint32_t *errQuery;
+};
+
+enum { ST_PROBES = 0, ST_MATCHES, ST_DIAGRES, ST_HITS, ST_CANDS, ST_TRUNC, ST_ERR_CAND, ST_ERR_RESCORE, ST_N };
+
+// UngappedAlignment::computeSingelSequenceScores + scalarDiagonalScoring (UngappedAlignment.cpp:30-43,416-430)
+__device__ int diagonalScore(const PrefilterArgs &a, const int8_t *sSub, uint32_t qBase, int Lq, uint32_t t, int diag,
+                             uint32_t &residues) {
+    const uint32_t tb = a.tOff[t];
+    const int Lt = (int)(a.tOff[t + 1] - tb);
+    int qs, ts, len;
+    if (diag >= 0) {
+        if (diag >= Lq) return 0;
+        qs = diag; ts = 0; len = min(Lt, Lq - diag);
+    } else {
+        if (-diag >= Lt) return 0;
+        qs = 0; ts = -diag; len = min(Lt + diag, Lq);
+    }
+    const uint8_t *qc = a.q.code + qBase + qs;
+    const int8_t *qk = a.q.corr + qBase + qs;
+    const uint8_t *tc = a.tRes + tb + ts;
+    int best = 0, run = 0;
+    for (int p = 0; p < len; p++) {
+        run += (int)sSub[qc[p] * AA + tc[p]] + (int)qk[p];
+        run = max(run, 0);
+        best = max(best, run);
+    }
+    residues += (uint32_t)len;
+    return best;
+}
+
+__global__ void __launch_bounds__(PF_WARPS * 32) prefilterKernel(PrefilterArgs a) {
+    __shared__ int16_t sS2[PF_WARPS][PF_CAP2];
+    __shared__ uint16_t sX2[PF_WARPS][PF_CAP2];
+    __shared__ uint32_t sHist[PF_WARPS][256];
+    __shared__ int8_t sSub[AA * AA];
+
+    for (int i = threadIdx.x; i < AA * AA; i += blockDim.x) sSub[i] = a.diagSub[i];
+    __syncthreads();
+
+    const uint32_t lane = laneId();
+    const uint32_t wInBlock = threadIdx.x >> 5;
+    const uint32_t warp = blockIdx.x * PF_WARPS + wInBlock;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    uint32_t *tab = a.table + (size_t)warp * a.nT;
+    uint64_t *cand = a.cand + (size_t)warp * a.candCap;
+    uint64_t *keep = a.keep + (size_t)warp * a.candCap;
+    uint32_t *resT = a.resT + (size_t)warp * a.maxHits;
+    int32_t *resScore = a.resScore + (size_t)warp * a.maxHits;
+    uint16_t *resDiag = a.resDiag + (size_t)warp * a.maxHits;
+    int16_t *S2 = sS2[wInBlock];
+    uint16_t *X2 = sX2[wInBlock];
+    uint32_t *hist = sHist[wInBlock];
+
+    unsigned long long stProbes = 0, stMatches = 0, stDiagRes = 0, stHits = 0, stCands = 0, stTrunc = 0;
+    uint32_t epoch = 0;   // table words start zeroed; live epochs are 1..255
+
+    for (;;) {
+        uint32_t qi = 0;
+        if (lane == 0) qi = atomicAdd(a.nextQuery, 1u);
+        qi = __shfl_sync(0xffffffffu, qi, 0);
+        if (qi >= a.nQ) break;
+        const uint32_t q = a.order[qi];
+        const uint32_t qBase = a.q.off[q];
+        const int Lq = (int)(a.q.off[q + 1] - qBase);
+        const uint32_t identity = a.sameDb ? (a.queryFirst + q) : 0xffffffffu;
+
+        // two epochs per query: E for the hit stream, E+1 for the best-diagonal pass
+        if (epoch + 2 > 255) {
+            for (uint32_t i = lane; i < a.nT; i += 32) __stcg(&tab[i], 0u);
+            __syncwarp();
+            epoch = 0;
+        }
+        const uint32_t E = epoch + 1;
+        epoch += 2;
+
+        uint32_t nCand = 0;
+        bool candOverflow = false;
+
+        // ---------------- hit stream: positions -> similar k-mers -> buckets -> double-hit rule
+        for (int p = 0; p + SPAN <= Lq; p++) {
+            const int thr = a.q.thr[qBase + p];
+            if (thr < 0) continue;
+            const uint8_t *qc = a.q.code + qBase + p;
+            const uint32_t i1 = qc[0] + 20u * qc[1] + 400u * qc[3];
+            const uint32_t i2 = qc[5] + 20u * qc[8] + 400u * qc[9];
+            const int16_t *s1 = a.e3score + (size_t)i1 * N3;
+            const uint16_t *x1 = a.e3index + (size_t)i1 * N3;
+            const int16_t *s2 = a.e3score + (size_t)i2 * N3;
+            const uint16_t *x2 = a.e3index + (size_t)i2 * N3;
+            const int cutoff1 = thr - (int)s2[0];          // KmerGenerator.cpp:129-137
+            const int cutoff2max = thr - (int)s1[0];
+            if ((int)s1[0] < cutoff1) continue;
+            // stage the prefix of row 2 that any first-row element can reach
+            uint32_t nb2 = 0;
+            for (uint32_t c0 = 0; c0 < N3; c0 += 32) {
+                const uint32_t c = c0 + lane;
+                const int v = (c < N3) ? (int)s2[c] : -32768;
+                const bool ok = v >= cutoff2max;
+                if (ok && c < PF_CAP2) { S2[c] = (int16_t)v; X2[c] = x2[c]; }
+                const uint32_t b = __ballot_sync(0xffffffffu, ok);
+                nb2 += __popc(b);
+                if (b != 0xffffffffu) break;
+            }
+            __syncwarp();
+            if (nb2 == 0) continue;
+
+            for (uint32_t a0 = 0; a0 < N3; a0 += 32) {
+                const uint32_t ai = a0 + lane;
+                const int sa = (ai < N3) ? (int)s1[ai] : -32768;
+                const bool okA = sa >= cutoff1;
+                const uint32_t okBallot = __ballot_sync(0xffffffffu, okA);
+                if (okBallot == 0) break;
+                uint32_t nb = 0;
+                uint32_t xa = 0;
+                if (okA) {
+                    xa = x1[ai];
+                    const int cut = thr - sa;                 // KmerGenerator.cpp:201
+                    uint32_t lo = 0, hi = nb2;                // first c with s2[c] < cut
+                    while (lo < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        const int v = (mid < PF_CAP2) ? (int)S2[mid] : (int)s2[mid];
+                        if (v >= cut) lo = mid + 1; else hi = mid;
+                    }
+                    nb = lo;
+                }
+                uint32_t totalProbes;
+                const uint32_t exclA = warpExclusiveScan(nb, totalProbes);
+                stProbes += (lane == 0) ? totalProbes : 0;
+
+                for (uint32_t pc = 0; pc < totalProbes; pc += 32) {
+                    const uint32_t pidx = pc + lane;
+                    const bool validP = pidx < totalProbes;
+                    const uint32_t ownerA = warpFindOwner(exclA, validP ? pidx : 0);
+                    const uint32_t ownerExcl = __shfl_sync(0xffffffffu, exclA, ownerA);
+                    const uint32_t ownerX = __shfl_sync(0xffffffffu, xa, ownerA);
+                    uint32_t bLo = 0, m = 0;
+                    if (validP) {
+                        const uint32_t c = pidx - ownerExcl;
+                        const uint32_t xc = (c < PF_CAP2) ? (uint32_t)X2[c] : (uint32_t)x2[c];
+                        const uint32_t kmer = ownerX + N3 * xc;            // KmerGenerator.cpp:207
+                        bLo = __ldg(&a.kOff[kmer]);
+                        m = __ldg(&a.kOff[kmer + 1]) - bLo;
+                    }
+                    uint32_t totalM;
+                    const uint32_t exclM = warpExclusiveScan(m, totalM);
+                    stMatches += (lane == 0) ? totalM : 0;
+
+                    for (uint32_t ec = 0; ec < totalM; ec += 32) {
+                        const uint32_t eidx = ec + lane;
+                        const bool validE = eidx < totalM;
+                        const uint32_t ownerM = warpFindOwner(exclM, validE ? eidx : 0);
+                        const uint32_t oExcl = __shfl_sync(0xffffffffu, exclM, ownerM);
+                        const uint32_t oLo = __shfl_sync(0xffffffffu, bLo, ownerM);
+                        uint32_t t = 0x80000000u | lane;     // unique dummy for idle lanes
+                        uint32_t diag16 = 0;
+                        if (validE) {
+                            const uint32_t e = oLo + (eidx - oExcl);
+                            t = __ldg(&a.entSeq[e]);
+                            diag16 = (uint32_t)(uint16_t)(p - (int)__ldg(&a.entPos[e]));
+                        }
+                        const uint32_t d8 = diag16 & 0xffu;
+                        // --- CacheFriendlyOperations::findDuplicates, restated per target in stream order
+                        const uint32_t grp = __match_any_sync(0xffffffffu, t);
+                        uint32_t old = 0;
+                        if (validE) old = __ldcg(&tab[t]);
+                        if ((old >> 24) != E) old = 0;
+                        const uint32_t lowerG = grp & ltMask;
+                        const int prevLane = lowerG ? (31 - __clz(lowerG)) : -1;
+                        uint32_t prevD8 = __shfl_sync(0xffffffffu, d8, prevLane >= 0 ? prevLane : (int)lane);
+                        if (prevLane < 0) prevD8 = (old >> 16) & 0xffu;
+                        const bool emit = validE && (d8 == prevD8);
+                        const uint32_t emitBallot = __ballot_sync(0xffffffffu, emit);
+                        const uint32_t grpE = grp & emitBallot;
+                        const uint32_t lowerE = grpE & ltMask;
+                        const int prevELane = lowerE ? (31 - __clz(lowerE)) : -1;
+                        uint32_t prevED8 = __shfl_sync(0xffffffffu, d8, prevELane >= 0 ? prevELane : (int)lane);
+                        bool prevEExists = true;
+                        if (prevELane < 0) { prevED8 = old & 0xffu; prevEExists = ((old >> 8) & 1u) != 0; }
+                        const bool isCand = emit && !(prevEExists && prevED8 == d8);
+                        const int lastELane = grpE ? (31 - __clz(grpE)) : -1;
+                        const uint32_t lastED8 = __shfl_sync(0xffffffffu, d8, lastELane >= 0 ? lastELane : (int)lane);
+                        if (validE && (grp >> lane) == 1u) {
+                            uint32_t w = (E << 24) | (d8 << 16);
+                            if (lastELane >= 0) w |= (1u << 8) | lastED8;
+                            else w |= old & 0x1ffu;
+                            __stcg(&tab[t], w);
+                        }
+                        const uint32_t candBallot = __ballot_sync(0xffffffffu, isCand);
+                        if (isCand) {
+                            const uint32_t pos = nCand + __popc(candBallot & ltMask);
+                            if (pos < a.candCap) cand[pos] = ((uint64_t)t << 32) | ((uint64_t)diag16 << 16);
+                        }
+                        nCand += __popc(candBallot);
+                        __syncwarp();
+                    }
+                }
+                if (okBallot != 0xffffffffu) break;
+            }
+        }
+        if (nCand > a.candCap) { candOverflow = true; nCand = a.candCap; }
+        stCands += (lane == 0) ? nCand : 0;
+        __syncwarp();
+
+        // ---------------- diagonal scores (UngappedAlignment::align), capped at 255
+        {
+            uint32_t resid = 0;
+            for (uint32_t c = lane; c < nCand; c += 32) {
+                const uint64_t v = cand[c];
+                const uint32_t t = (uint32_t)(v >> 32);
+                const int diag = (int)(int16_t)(uint16_t)(v >> 16);
+                int s = diagonalScore(a, sSub, qBase, Lq, t, diag, resid);
+                s = min(s, 255);
+                cand[c] = v | ((uint64_t)s << 8);
+                // best score per target: epoch E+1 words order above every epoch-E word
+                atomicMax(&tab[t], ((E + 1) << 24) | (uint32_t)s);
+            }
+            stDiagRes += resid;
+        }
+        __threadfence_block();
+        __syncwarp();
+
+        // ---------------- keepMaxScoreElementOnly: first candidate (stream order) carrying the target's max
+        for (uint32_t i = lane; i < 256; i += 32) hist[i] = 0;
+        __syncwarp();
+        uint32_t nKeep = 0;
+        for (uint32_t c0 = 0; c0 < nCand; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            const bool valid = c < nCand;
+            uint64_t v = 0;
+            uint32_t t = 0x80000000u | lane;
+            if (valid) { v = cand[c]; t = (uint32_t)(v >> 32); }
+            const uint32_t s = (uint32_t)(v >> 8) & 0xffu;
+            uint32_t w = 0;
+            if (valid) w = __ldcg(&tab[t]);
+            const bool isMax = valid && ((w & 0x100u) == 0) && ((w & 0xffu) == s);
+            const uint32_t grp = __match_any_sync(0xffffffffu, t);
+            const uint32_t maxBallot = __ballot_sync(0xffffffffu, isMax);
+            const uint32_t grpMax = grp & maxBallot;
+            const bool winner = isMax && ((grpMax & ltMask) == 0);
+            if (winner) __stcg(&tab[t], w | 0x100u);
+            const uint32_t winBallot = __ballot_sync(0xffffffffu, winner);
+            if (winner) {
+                keep[nKeep + __popc(winBallot & ltMask)] = v;
+                atomicAdd(&hist[s], 1u);
+            }
+            nKeep += __popc(winBallot);
+            __syncwarp();
+        }
+
+        // ---------------- score threshold (QueryMatcher::computeScoreThreshold) and selection
+        uint32_t thrScore = 0;
+        if (lane == 0) {
+            uint32_t found = 0, sc;
+            for (sc = 255; sc > 0; sc--) {
+                found += hist[sc];
+                if (found >= a.maxHits) break;
+            }
+            thrScore = max(sc, a.minDiagScore);
+        }
+        thrScore = __shfl_sync(0xffffffffu, thrScore, 0);
+        const bool needRescale = thrScore >= 255u;   // reference's rescoreHits path: not implemented
+        uint32_t nRes = 0;
+        if (identity != 0xffffffffu) {
+            if (lane == 0) { resT[0] = identity; resScore[0] = 65535; resDiag[0] = 0; }
+            nRes = 1;
+        }
+        // everything strictly above the threshold survives
+        for (uint32_t c0 = 0; c0 < nKeep; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            uint64_t v = 0;
+            bool sel = false;
+            if (c < nKeep) {
+                v = keep[c];
+                const uint32_t s = (uint32_t)(v >> 8) & 0xffu;
+                sel = s > thrScore && (uint32_t)(v >> 32) != identity;
+            }
+            const uint32_t b = __ballot_sync(0xffffffffu, sel);
+            if (sel) {
+                const uint32_t pos = nRes + __popc(b & ltMask);
+                if (pos < a.maxHits) {
+                    resT[pos] = (uint32_t)(v >> 32);
+                    resScore[pos] = (int)((v >> 8) & 0xffu);
+                    resDiag[pos] = (uint16_t)(v >> 16);
+                }
+            }
+            nRes += __popc(b);
+        }
+        nRes = min(nRes, a.maxHits);
+        // the threshold class fills what is left, in (id & binMask, stream order) order
+        bool dropped = false;
+        for (uint32_t bin = 0; bin <= a.binMask; bin++) {
+            for (uint32_t c0 = 0; c0 < nKeep; c0 += 32) {
+                const uint32_t c = c0 + lane;
+                uint64_t v = 0;
+                bool sel = false;
+                if (c < nKeep) {
+                    v = keep[c];
+                    const uint32_t s = (uint32_t)(v >> 8) & 0xffu;
+                    const uint32_t t = (uint32_t)(v >> 32);
+                    sel = s == thrScore && t != identity && (t & a.binMask) == bin;
+                }
+                const uint32_t b = __ballot_sync(0xffffffffu, sel);
+                if (sel) {
+                    const uint32_t pos = nRes + __popc(b & ltMask);
+                    if (pos < a.maxHits) {
+                        resT[pos] = (uint32_t)(v >> 32);
+                        resScore[pos] = (int)((v >> 8) & 0xffu);
+                        resDiag[pos] = (uint16_t)(v >> 16);
+                    }
+                }
+                nRes += __popc(b);
+                if (nRes > a.maxHits) { dropped = true; nRes = a.maxHits; }
+            }
+        }
+        __syncwarp();
+        if (dropped) stTrunc += (lane == 0) ? 1 : 0;
+        // scores that hit the 8-bit cap are replaced by the uncapped diagonal score (QueryMatcher.cpp:410-413)
+        for (uint32_t r = lane; r < nRes; r += 32) {
+            if (resScore[r] >= 255 && resScore[r] != 65535) {
+                uint32_t dummy = 0;
+                resScore[r] = diagonalScore(a, sSub, qBase, Lq, resT[r], (int)(int16_t)resDiag[r], dummy);
+            }
+        }
+        __syncwarp();
+        stHits += (lane == 0) ? nRes : 0;
+
+        // ---------------- final order (score desc, id asc; identity stays first) + coverage pre-filter
+        const uint32_t first = (identity != 0xffffffffu) ? 1u : 0u;
+        sd_prefilter_hit *outQ = a.out + (size_t)q * a.maxHits;
+        uint32_t nOut = 0;
+        // rank sort: rank = number of elements that come before
+        for (uint32_t r0 = 0; r0 < nRes; r0 += 32) {
+            const uint32_t r = r0 + lane;
+            uint32_t rank = 0xffffffffu;
+            uint32_t t = 0;
+            int s = 0;
+            uint16_t dg = 0;
+            if (r < nRes) {
+                t = resT[r]; s = resScore[r]; dg = resDiag[r];
+                if (r < first) rank = 0;
+                else {
+                    rank = first;
+                    for (uint32_t j = first; j < nRes; j++) {
+                        const int sj = resScore[j];
+                        const uint32_t tj = resT[j];
+                        rank += (sj > s || (sj == s && tj < t)) ? 1u : 0u;
+                    }
+                }
+            }
+            // coverage pre-filter (Prefiltering.cpp:856-863, Util::canBeCovered Util.cpp:477-494)
+            bool pass = r < nRes;
+            if (pass && a.covThr > 0.0f && (a.covMode == 0 || a.covMode == 2 || a.covMode == 5)) {
+                const float ql = (float)Lq;
+                const float tl = (float)(a.tOff[t + 1] - a.tOff[t]);
+                if (a.covMode == 0) pass = (__fdiv_rn(ql, tl) >= a.covThr) && (__fdiv_rn(tl, ql) >= a.covThr);
+                else if (a.covMode == 2) pass = __fdiv_rn(tl, ql) >= a.covThr;
+                else pass = __fdiv_rn(fminf(tl, ql), fmaxf(tl, ql)) >= a.covThr;
+            }
+            if (r < nRes) {
+                // park (rank, pass) in the scratch result arrays' tail: write straight to the output slot by rank
+                outQ[rank].query = q;
+                outQ[rank].target = t;
+                outQ[rank].score = pass ? s : -1;      // -1 marks "filtered by coverage"; compacted below
+                outQ[rank].diag = (int16_t)dg;
+                outQ[rank].pad = 0;
+            }
+        }
+        __syncwarp();
+        __threadfence_block();
+        // compact the coverage-filtered entries in place, keeping order
+        for (uint32_t r0 = 0; r0 < nRes; r0 += 32) {
+            const uint32_t r = r0 + lane;
+            sd_prefilter_hit h;
+            bool ok = false;
+            if (r < nRes) { h = outQ[r]; ok = h.score >= 0; }
+            const uint32_t b = __ballot_sync(0xffffffffu, ok);
+            __syncwarp();
+            if (ok) outQ[nOut + __popc(b & ltMask)] = h;
+            nOut += __popc(b);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            a.outCount[q] = nOut;
+            if (candOverflow) { atomicAdd(&a.stats[ST_ERR_CAND], 1ull); atomicMin(a.errQuery, q); }
+            if (needRescale) { atomicAdd(&a.stats[ST_ERR_RESCORE], 1ull); atomicMin(a.errQuery, q); }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        atomicAdd(&a.stats[ST_PROBES], stProbes);
+        atomicAdd(&a.stats[ST_MATCHES], stMatches);
+        atomicAdd(&a.stats[ST_HITS], stHits);
+        atomicAdd(&a.stats[ST_CANDS], stCands);
+        atomicAdd(&a.stats[ST_TRUNC], stTrunc);
+    }
+    // diagResidues is accumulated per lane
+    for (int d = 16; d > 0; d >>= 1) stDiagRes += __shfl_down_sync(0xffffffffu, stDiagRes, d);
+    if (lane == 0) atomicAdd(&a.stats[ST_DIAGRES], stDiagRes);
+}
+
+// dense[offs[q] + i] = out[q*maxHits + i]; one warp per query
+__global__ void compactHits(const sd_prefilter_hit *__restrict__ out, const uint32_t *__restrict__ count,
+                            const uint32_t *__restrict__ offs, uint32_t nQ, uint32_t maxHits,
+                            sd_prefilter_hit *__restrict__ dense) {
+    const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nQ) return;
+    const uint32_t n = count[q];
+    const sd_prefilter_hit *src = out + (size_t)q * maxHits;
+    sd_prefilter_hit *dst = dense + offs[q];
+    for (uint32_t i = laneId(); i < n; i += 32) dst[i] = src[i];
+}
+
+}  // namespace sd
+
+// =================================================================================================
+// host side
+// =================================================================================================
+using namespace sd;
+
+static inline unsigned gridFor(uint64_t n, unsigned block) { return (unsigned)((n + block - 1) / block); }
+
+static int ensureExt3(sd_context *ctx) {
+    if (ctx->haveExt3) return SD_OK;
+    std::vector<int16_t> sc;
+    std::vector<uint16_t> ix;
+    buildExt3(ctx->seedMat, sc, ix);
+    int rc;
+    if ((rc = ctx->e3score.alloc(sc.size())) != SD_OK) return rc;
+    if ((rc = ctx->e3index.alloc(ix.size())) != SD_OK) return rc;
+    SD_CUDA(cudaMemcpyAsync(ctx->e3score.p, sc.data(), sc.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(cudaMemcpyAsync(ctx->e3index.p, ix.data(), ix.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->haveExt3 = true;
+    return SD_OK;
+}
+
+extern "C" void sd_prefilter_params_default(sd_prefilter_params *p) {
+    p->sensitivity = 5.7f;
+    p->max_seqs = 300;
+    p->min_ungapped_score = 15;
+    p->cov_thr = 0.8f;
+    p->cov_mode = 2;
+    p->mask = 1;
+    p->mask_prob = 0.9f;
+    p->comp_bias_corr = 1;
+    p->bin_size = 0;
+    p->same_db = 0;
+}
+
+extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const uint64_t *off, uint32_t n,
+                                     const sd_prefilter_params *par, sd_target_index **out) {
+    if (!ctx || !seqs || !off || !par || !out || n == 0) { setError("sd_target_index_build: bad argument"); return SD_EINVAL; }
+    const uint64_t total = off[n];
+    if (total >= 0xfff00000ull) { setError("target DB too large for 32-bit residue offsets (%llu residues)", (unsigned long long)total); return SD_ELIMIT; }
+    if (n >= (1u << 22)) { setError("more than 4M targets in one index shard (%u)", n); return SD_ELIMIT; }
+    for (uint32_t i = 0; i < n; i++)
+        if (off[i + 1] - off[i] >= 32768) { setError("target %u longer than 32767 residues: long-sequence path not implemented", i); return SD_ELIMIT; }
+    SD_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<sd_target_index> idx(new sd_target_index());
+    idx->ctx = ctx;
+    idx->nT = n;
+    idx->totalRes = total;
+    idx->kmerThr = kmerThreshold(par->sensitivity, KMER);
+    idx->hostOff.resize(n + 1);
+    for (uint32_t i = 0; i <= n; i++) idx->hostOff[i] = (uint32_t)off[i];
+
+    // residues: map on the host, mask with tantan on the host thread pool (double precision, see hostprep.cpp)
+    std::vector<uint8_t> codes(total + SPAN);
+    mapSequence(seqs, total, codes.data());
+    std::fill(codes.begin() + total, codes.end(), (uint8_t)XCODE);
+    if (par->mask) idx->masked = tantanMaskAll(codes.data(), off, n, ctx->seedMat, (double)par->mask_prob);
+
+    int rc;
+    if ((rc = idx->res.alloc(total + SPAN)) != SD_OK) return rc;
+    if ((rc = idx->off.alloc(n + 1)) != SD_OK) return rc;
+    if ((rc = idx->kOff.alloc((size_t)NKMER + 1)) != SD_OK) return rc;
+    cudaStream_t st = ctx->stream;
+    SD_CUDA(cudaMemcpyAsync(idx->res.p, codes.data(), total + SPAN, cudaMemcpyHostToDevice, st));
+    SD_CUDA(cudaMemcpyAsync(idx->off.p, idx->hostOff.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+
+    int8_t selfHost[AA];
+    for (int a = 0; a < AA; a++) selfHost[a] = (int8_t)ctx->seedMat.sub[a * AA + a];   // getScoreLookup IndexBuilder.cpp:10-22
+    DevBuf<int8_t> self;
+    if ((rc = self.alloc(AA)) != SD_OK) return rc;
+    SD_CUDA(cudaMemcpyAsync(self.p, selfHost, AA, cudaMemcpyHostToDevice, st));
+
+    const uint32_t nPos = (uint32_t)total;
+    DevBuf<uint64_t> keysA, keysB, payloadA, payloadB;
+    DevBuf<uint32_t> kmerA, kmerB;
+    if ((rc = keysA.alloc(nPos)) != SD_OK || (rc = keysB.alloc(nPos)) != SD_OK) return rc;
+    extractTargetKmers<<<gridFor(nPos, 256), 256, 0, st>>>(idx->res.p, idx->off.p, n, nPos, self.p, idx->kmerThr, keysA.p);
+    ctx->launches++;
+    SD_CUDA(cudaGetLastError());
+    // sort by (seq, kmer, pos)
+    {
+        size_t tmpBytes = 0;
+        SD_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmpBytes, keysA.p, keysB.p, (int64_t)nPos, 0, 64, st));
+        DevBuf<uint8_t> tmp;
+        if ((rc = tmp.alloc(tmpBytes)) != SD_OK) return rc;
+        SD_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmpBytes, keysA.p, keysB.p, (int64_t)nPos, 0, 64, st));
+        SD_CUDA(cudaStreamSynchronize(st));
+    }
+    keysA.release();
+    if ((rc = kmerA.alloc(nPos)) != SD_OK || (rc = kmerB.alloc(nPos)) != SD_OK) return rc;
+    if ((rc = payloadA.alloc(nPos)) != SD_OK || (rc = payloadB.alloc(nPos)) != SD_OK) return rc;
+    SD_CUDA(cudaMemsetAsync(idx->kOff.p, 0, ((size_t)NKMER + 1) * sizeof(uint32_t), st));
+    firstOccurrence<<<gridFor(nPos, 256), 256, 0, st>>>(keysB.p, nPos, kmerA.p, payloadA.p, idx->kOff.p);
+    ctx->launches++;
+    SD_CUDA(cudaGetLastError());
+    // stable sort by k-mer: buckets come out ordered by (seq, pos); dropped entries (0xffffffff) go last
+    {
+        size_t tmpBytes = 0;
+        SD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, kmerA.p, kmerB.p, payloadA.p, payloadB.p, (int64_t)nPos, 0, 32, st));
+        DevBuf<uint8_t> tmp;
+        if ((rc = tmp.alloc(tmpBytes)) != SD_OK) return rc;
+        SD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, kmerA.p, kmerB.p, payloadA.p, payloadB.p, (int64_t)nPos, 0, 32, st));
+        SD_CUDA(cudaStreamSynchronize(st));
+    }
+    // bucket starts = exclusive scan of the counts
+    {
+        size_t tmpBytes = 0;
+        SD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, idx->kOff.p, idx->kOff.p, (int64_t)NKMER + 1, st));
+        DevBuf<uint8_t> tmp;
+        if ((rc = tmp.alloc(tmpBytes)) != SD_OK) return rc;
+        SD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, idx->kOff.p, idx->kOff.p, (int64_t)NKMER + 1, st));
+    }
+    uint32_t nEnt = 0;
+    SD_CUDA(cudaMemcpyAsync(&nEnt, idx->kOff.p + NKMER, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SD_CUDA(cudaStreamSynchronize(st));
+    idx->nEntries = nEnt;
+    if ((rc = idx->entSeq.alloc(nEnt)) != SD_OK || (rc = idx->entPos.alloc(nEnt)) != SD_OK) return rc;
+    if (nEnt > 0) {
+        splitEntries<<<gridFor(nEnt, 256), 256, 0, st>>>(payloadB.p, nEnt, idx->entSeq.p, idx->entPos.p);
+        ctx->launches++;
+        SD_CUDA(cudaGetLastError());
+    }
+    SD_CUDA(cudaStreamSynchronize(st));
+    if ((rc = ensureExt3(ctx)) != SD_OK) return rc;
+    *out = idx.release();
+    return SD_OK;
+}
+
+extern "C" void sd_target_index_destroy(sd_target_index *idx) { delete idx; }
+
+extern "C" uint64_t sd_target_index_entries(const sd_target_index *idx) { return idx ? idx->nEntries : 0; }
+
+extern "C" int sd_target_index_masked(const sd_target_index *idx, uint8_t *out, uint64_t cap) {
+    if (!idx || !out || cap < idx->totalRes) { setError("sd_target_index_masked: bad argument"); return SD_EINVAL; }
+    SD_CUDA(cudaMemcpy(out, idx->res.p, idx->totalRes, cudaMemcpyDeviceToHost));
+    return SD_OK;
+}
+
+extern "C" int sd_prefilter_run(sd_context *ctx, const sd_target_index *idx, const char *qseqs, const uint64_t *qoff,
+                                uint32_t nq, uint32_t query_first, const sd_prefilter_params *par,
+                                sd_prefilter_hit *hits, uint64_t cap, uint64_t *n_hits, sd_prefilter_stats *stats) {
+    if (!ctx || !idx || !qseqs || !qoff || !par || !n_hits || (!hits && cap)) { setError("sd_prefilter_run: bad argument"); return SD_EINVAL; }
+    *n_hits = 0;
+    if (nq == 0) return SD_OK;
+    const uint64_t total = qoff[nq];
+    if (total >= 0xfff00000ull) { setError("query batch too large (%llu residues): split the call", (unsigned long long)total); return SD_ELIMIT; }
+    for (uint32_t i = 0; i < nq; i++)
+        if (qoff[i + 1] - qoff[i] >= 32768) { setError("query %u longer than 32767 residues: long-sequence path not implemented", i); return SD_ELIMIT; }
+    SD_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc;
+    cudaEvent_t ev0, ev1, evk0, evk1;
+    SD_CUDA(cudaEventCreate(&ev0)); SD_CUDA(cudaEventCreate(&ev1));
+    SD_CUDA(cudaEventCreate(&evk0)); SD_CUDA(cudaEventCreate(&evk1));
+    SD_CUDA(cudaEventRecord(ev0, st));
+
+    const uint32_t nPos = (uint32_t)total;
+    std::vector<uint32_t> hOff(nq + 1);
+    for (uint32_t i = 0; i <= nq; i++) hOff[i] = (uint32_t)qoff[i];
+    std::vector<uint32_t> order(nq);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return hOff[x + 1] - hOff[x] > hOff[y + 1] - hOff[y]; });
+
+    DevBuf<char> dAscii;
+    DevBuf<uint8_t> dLut, dCode;
+    DevBuf<uint32_t> dOff, dOrder;
+    DevBuf<float> dBias;
+    DevBuf<int8_t> dCorr, dDiagSub;
+    DevBuf<int16_t> dThr, dSeedSub;
+    DevBuf<double> dPBack;
+    if ((rc = dAscii.alloc(total)) || (rc = dLut.alloc(256)) || (rc = dCode.alloc(total + SPAN)) || (rc = dOff.alloc(nq + 1)) ||
+        (rc = dOrder.alloc(nq)) || (rc = dBias.alloc(total + SPAN)) || (rc = dCorr.alloc(total + SPAN)) || (rc = dThr.alloc(total + SPAN)) ||
+        (rc = dSeedSub.alloc(AA * AA)) || (rc = dDiagSub.alloc(AA * AA)) || (rc = dPBack.alloc(AA)))
+        return rc;
+    int16_t seedSub[AA * AA];
+    int8_t diagSub[AA * AA];
+    for (int i = 0; i < AA * AA; i++) { seedSub[i] = ctx->seedMat.sub[i]; diagSub[i] = (int8_t)ctx->diagMat.sub[i]; }
+    SD_CUDA(cudaMemcpyAsync(dAscii.p, qseqs, total, cudaMemcpyHostToDevice, st));
+    SD_CUDA(cudaMemcpyAsync(dLut.p, aa2num(), 256, cudaMemcpyHostToDevice, st));
+    SD_CUDA(cudaMemcpyAsync(dOff.p, hOff.data(), (nq + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    SD_CUDA(cudaMemcpyAsync(dOrder.p, order.data(), nq * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    SD_CUDA(cudaMemcpyAsync(dSeedSub.p, seedSub, sizeof seedSub, cudaMemcpyHostToDevice, st));
+    SD_CUDA(cudaMemcpyAsync(dDiagSub.p, diagSub, sizeof diagSub, cudaMemcpyHostToDevice, st));
+    SD_CUDA(cudaMemcpyAsync(dPBack.p, ctx->seedMat.pBack, AA * sizeof(double), cudaMemcpyHostToDevice, st));
+    SD_CUDA(cudaMemsetAsync(dCode.p + total, XCODE, SPAN, st));
+    SD_CUDA(cudaMemsetAsync(dBias.p + total, 0, SPAN * sizeof(float), st));
+    mapResidues<<<gridFor(total, 256), 256, 0, st>>>(dAscii.p, total, dLut.p, dCode.p);
+    compositionBias<<<gridFor(nPos, 128), 128, 0, st>>>(dCode.p, dOff.p, nq, nPos, dSeedSub.p, dPBack.p, par->comp_bias_corr, dBias.p, dCorr.p);
+    kmerThresholds<<<gridFor(nPos, 256), 256, 0, st>>>(dCode.p, dOff.p, nq, nPos, dBias.p, idx->kmerThr, dThr.p);
+    ctx->launches += 3;
+    SD_CUDA(cudaGetLastError());
+
+    const uint32_t maxHits = std::min<uint32_t>((uint32_t)std::max(par->max_seqs, 1), idx->nT);
+    const int binSize = par->bin_size > 0 ? par->bin_size : referenceBinSize(idx->nT);
+    const int ctasPerSm = 3;
+    const uint32_t nCta = std::max(1u, std::min<uint32_t>((uint32_t)(ctx->smCount * ctasPerSm), (nq + PF_WARPS - 1) / PF_WARPS));
+    const uint32_t nWarps = nCta * PF_WARPS;
+    const uint32_t candCap = 32768;
+
+    DevBuf<uint32_t> dTable, dResT, dOutCount, dNext;
+    DevBuf<uint64_t> dCand, dKeep;
+    DevBuf<int32_t> dResScore;
+    DevBuf<uint16_t> dResDiag;
+    DevBuf<sd_prefilter_hit> dOut;
+    DevBuf<unsigned long long> dStats;
+    if ((rc = dTable.alloc((size_t)nWarps * idx->nT)) || (rc = dCand.alloc((size_t)nWarps * candCap)) || (rc = dKeep.alloc((size_t)nWarps * candCap)) ||
+        (rc = dResT.alloc((size_t)nWarps * maxHits)) || (rc = dResScore.alloc((size_t)nWarps * maxHits)) || (rc = dResDiag.alloc((size_t)nWarps * maxHits)) ||
+        (rc = dOut.alloc((size_t)nq * maxHits)) || (rc = dOutCount.alloc(nq)) || (rc = dNext.alloc(2)) || (rc = dStats.alloc(ST_N)))
+        return rc;
+    SD_CUDA(cudaMemsetAsync(dTable.p, 0, (size_t)nWarps * idx->nT * sizeof(uint32_t), st));
+    SD_CUDA(cudaMemsetAsync(dOutCount.p, 0, nq * sizeof(uint32_t), st));
+    SD_CUDA(cudaMemsetAsync(dStats.p, 0, ST_N * sizeof(unsigned long long), st));
+    const uint32_t initNext[2] = {0u, 0xffffffffu};
+    SD_CUDA(cudaMemcpyAsync(dNext.p, initNext, sizeof initNext, cudaMemcpyHostToDevice, st));
+
+    PrefilterArgs a{};
+    a.tRes = idx->res.p; a.tOff = idx->off.p; a.nT = idx->nT;
+    a.kOff = idx->kOff.p; a.entSeq = idx->entSeq.p; a.entPos = idx->entPos.p;
+    a.e3score = ctx->e3score.p; a.e3index = ctx->e3index.p; a.diagSub = dDiagSub.p;
+    a.q.code = dCode.p; a.q.off = dOff.p; a.q.corr = dCorr.p; a.q.thr = dThr.p;
+    a.nQ = nq; a.order = dOrder.p; a.queryFirst = query_first; a.sameDb = par->same_db;
+    a.maxHits = maxHits; a.minDiagScore = (uint32_t)std::max(par->min_ungapped_score, 0);
+    a.covThr = par->cov_thr; a.covMode = par->cov_mode; a.binMask = (uint32_t)binSize - 1u;
+    a.table = dTable.p; a.candCap = candCap; a.cand = dCand.p; a.keep = dKeep.p;
+    a.resT = dResT.p; a.resScore = dResScore.p; a.resDiag = dResDiag.p;
+    a.out = dOut.p; a.outCount = dOutCount.p; a.stats = dStats.p; a.nextQuery = dNext.p; a.errQuery = dNext.p + 1;
+
+    SD_CUDA(cudaEventRecord(evk0, st));
+    prefilterKernel<<<nCta, PF_WARPS * 32, 0, st>>>(a);
+    ctx->launches++;
+    SD_CUDA(cudaGetLastError());
+    SD_CUDA(cudaEventRecord(evk1, st));
+
+    std::vector<uint32_t> hCount(nq);
+    unsigned long long hStats[ST_N];
+    uint32_t hNext[2];
+    SD_CUDA(cudaMemcpyAsync(hCount.data(), dOutCount.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SD_CUDA(cudaMemcpyAsync(hStats, dStats.p, sizeof hStats, cudaMemcpyDeviceToHost, st));
+    SD_CUDA(cudaMemcpyAsync(hNext, dNext.p, sizeof hNext, cudaMemcpyDeviceToHost, st));
+    SD_CUDA(cudaStreamSynchronize(st));
+    if (hStats[ST_ERR_CAND]) { setError("prefilter: %llu queries produced more than %u diagonal candidates (first: query %u)", hStats[ST_ERR_CAND], candCap, hNext[1]); return SD_ELIMIT; }
+    if (hStats[ST_ERR_RESCORE]) { setError("prefilter: %llu queries need the reference's truncated-score rescaling path (>= max-seqs hits at score 255; first: query %u): not implemented", hStats[ST_ERR_RESCORE], hNext[1]); return SD_ELIMIT; }
+    uint64_t totalHits = 0;
+    for (uint32_t i = 0; i < nq; i++) totalHits += hCount[i];
+    *n_hits = totalHits;
+    if (totalHits > cap) { setError("sd_prefilter_run: %llu hits, buffer holds %llu", (unsigned long long)totalHits, (unsigned long long)cap); return SD_ESMALL; }
+    // gather the per-query slices (strided device layout -> dense) and copy once
+    if (totalHits) {
+        DevBuf<uint32_t> dOffs;
+        DevBuf<sd_prefilter_hit> dDense;
+        DevBuf<uint8_t> tmp;
+        if ((rc = dOffs.alloc(nq)) || (rc = dDense.alloc(totalHits))) return rc;
+        size_t tmpBytes = 0;
+        SD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, dOutCount.p, dOffs.p, (int64_t)nq, st));
+        if ((rc = tmp.alloc(tmpBytes))) return rc;
+        SD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, dOutCount.p, dOffs.p, (int64_t)nq, st));
+        compactHits<<<gridFor((uint64_t)nq * 32, 256), 256, 0, st>>>(dOut.p, dOutCount.p, dOffs.p, nq, maxHits, dDense.p);
+        ctx->launches++;
+        SD_CUDA(cudaGetLastError());
+        SD_CUDA(cudaMemcpyAsync(hits, dDense.p, totalHits * sizeof(sd_prefilter_hit), cudaMemcpyDeviceToHost, st));
+        SD_CUDA(cudaStreamSynchronize(st));
+    }
+    SD_CUDA(cudaEventRecord(ev1, st));
+    SD_CUDA(cudaStreamSynchronize(st));
+    if (stats) {
+        float msK = 0, msT = 0;
+        cudaEventElapsedTime(&msK, evk0, evk1);
+        cudaEventElapsedTime(&msT, ev0, ev1);
+        stats->probes = hStats[ST_PROBES]; stats->matches = hStats[ST_MATCHES]; stats->diag_residues = hStats[ST_DIAGRES];
+        stats->query_residues = total; stats->hits = hStats[ST_HITS]; stats->candidates = hStats[ST_CANDS];
+        stats->truncated = hStats[ST_TRUNC]; stats->kernel_ms = msK; stats->total_ms = msT;
+    }
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evk0); cudaEventDestroy(evk1);
+    return SD_OK;
+}
