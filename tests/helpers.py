@@ -175,3 +175,85 @@ def run_ref(args, cwd=None, threads=None):
     if r.returncode != 0:
         raise RuntimeError("reference failed: %s\n%s" % (args, r.stdout.decode()[-2000:]))
     return r.stdout.decode()
+
+
+# ----------------------------------------------------------------------------- oracle: align
+class OrcAlignParams(ctypes.Structure):
+    _fields_ = [("evalThr", ctypes.c_double), ("seqIdThr", ctypes.c_double), ("covThr", ctypes.c_float),
+                ("covMode", ctypes.c_int), ("minAlnLen", ctypes.c_int), ("compBias", ctypes.c_int),
+                ("gapOpen", ctypes.c_int), ("gapExtend", ctypes.c_int), ("scoreBias", ctypes.c_float),
+                ("sameDB", ctypes.c_int)]
+
+
+class OrcAlignStats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in
+                ("alignments", "passed", "wordMode", "reversePasses", "tracebacks", "tracebackFailed", "scoreMismatch",
+                 "cellsForward", "cellsReverse", "cellsTraceback")]
+
+
+ORC_ALN_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("targetKey", "<u4"), ("score", "<i4"), ("bits", "<i4"),
+                          ("seqId", "<f4"), ("qcov", "<f4"), ("tcov", "<f4"), ("evalue", "<f8"),
+                          ("qStart", "<i4"), ("qEnd", "<i4"), ("qLen", "<i4"), ("tStart", "<i4"), ("tEnd", "<i4"),
+                          ("tLen", "<i4"), ("alnLen", "<i4"), ("btOff", "<u8"), ("btLen", "<u4")], align=True)
+
+
+def default_align_params(**kw):
+    p = OrcAlignParams(evalThr=10.0, seqIdThr=0.0, covThr=0.8, covMode=2, minAlnLen=30, compBias=1, gapOpen=11,
+                       gapExtend=1, scoreBias=0.0, sameDB=1)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def orc_align(tbuf, toff, tkeys, qbuf, qoff, qkeys, pair_q, pair_t, params, db_residues=None):
+    lib = oracle()
+    lib.orc_align.restype = ctypes.c_long
+    nT, nQ = len(toff) - 1, len(qoff) - 1
+    pair_q = np.ascontiguousarray(pair_q, dtype=np.uint32)
+    pair_t = np.ascontiguousarray(pair_t, dtype=np.uint32)
+    tkeys = np.ascontiguousarray(tkeys, dtype=np.uint32)
+    qkeys = np.ascontiguousarray(qkeys, dtype=np.uint32)
+    if db_residues is None:
+        db_residues = int(toff[-1])
+    cap = max(16, len(pair_q))
+    out = np.zeros(cap, dtype=ORC_ALN_DTYPE)
+    assert ORC_ALN_DTYPE.itemsize == 88, ORC_ALN_DTYPE.itemsize
+    lens_t = np.diff(toff).astype(np.int64)
+    lens_q = np.diff(qoff).astype(np.int64)
+    bt_cap = int((lens_t[pair_t] + lens_q[pair_q]).sum()) + 64
+    bt = np.zeros(bt_cap, dtype=np.uint8)
+    stats = OrcAlignStats()
+    n = lib.orc_align(tbuf.ctypes.data_as(ctypes.c_char_p), toff.ctypes.data_as(ctypes.c_void_p), tkeys.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(nT),
+                      qbuf.ctypes.data_as(ctypes.c_char_p), qoff.ctypes.data_as(ctypes.c_void_p), qkeys.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(nQ),
+                      pair_q.ctypes.data_as(ctypes.c_void_p), pair_t.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(len(pair_q)),
+                      ctypes.c_uint64(db_residues), ctypes.byref(params), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(cap),
+                      bt.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(bt_cap), ctypes.byref(stats))
+    if n < 0:
+        raise RuntimeError("orc_align failed: %d" % n)
+    st = {f[0]: getattr(stats, f[0]) for f in OrcAlignStats._fields_}
+    return out[:n], bt, st
+
+
+def format_alignments(alns, bt, qkeys):
+    """-> {queryKey: [line bytes (no newline), ...]} exactly as Matcher::resultToBuffer prints them."""
+    lib = oracle()
+    buf = ctypes.create_string_buffer(1 << 20)
+    d = {int(k): [] for k in qkeys}
+    for i in range(len(alns)):
+        rec = alns[i:i + 1]
+        n = lib.orc_format_alignment(rec.ctypes.data_as(ctypes.c_void_p), bt.ctypes.data_as(ctypes.c_char_p), buf, ctypes.c_int(1 << 20))
+        d[int(qkeys[alns[i]["query"]])].append(buf.raw[:n - 1])
+    return d
+
+
+def parse_pref_db(path, qkeys, tkeys):
+    """prefilter DB -> (pair_q, pair_t) index arrays in DB order of queries = order of qkeys."""
+    key2t = {int(k): i for i, k in enumerate(tkeys)}
+    db = read_db(path)
+    pq, pt = [], []
+    for qi, k in enumerate(qkeys):
+        for line in db.get(int(k), b"").split(b"\n"):
+            if line:
+                pq.append(qi)
+                pt.append(key2t[int(line.split(b"\t")[0])])
+    return np.array(pq, dtype=np.uint32), np.array(pt, dtype=np.uint32)
