@@ -104,6 +104,62 @@ int sd_prefilter_run(sd_context *ctx, const sd_target_index *idx, const char *qs
                      const sd_prefilter_params *par, sd_prefilter_hit *hits, uint64_t cap,
                      uint64_t *n_hits, sd_prefilter_stats *stats);
 
+/* ---- align (reference flags of `align`) -------------------------------- */
+typedef struct {
+    double evalue_thr;        /* -e                (10)   */
+    double min_seq_id;        /* --min-seq-id      (0)    */
+    float cov_thr;            /* -c                (0.8)  */
+    int cov_mode;             /* --cov-mode        (2)    */
+    int min_aln_len;          /* --min-aln-len     (30)   */
+    int comp_bias_corr;       /* --comp-bias-corr  (1)    */
+    int gap_open;             /* --gap-open        (11)   */
+    int gap_extend;           /* --gap-extend      (1)    */
+    float score_bias;         /* --score-bias      (0)    */
+    int same_db;              /* query DB is the target DB: identity pairs take the scoreIdentical shortcut */
+} sd_align_params;
+
+void sd_align_params_default(sd_align_params *p);
+
+typedef struct {
+    uint32_t query;           /* index into the call's query array                     */
+    uint32_t target;          /* index into the index's target array                   */
+    int32_t score;            /* raw Smith-Waterman score                              */
+    int32_t bits;             /* int(bit score + 0.5)                                  */
+    float seq_id;             /* identities / alignment length                         */
+    float qcov, tcov;
+    double evalue;
+    int32_t q_start, q_end, q_len, t_start, t_end, t_len, aln_len;
+    uint64_t bt_off;          /* offset of the M/I/D backtrace in the backtrace pool   */
+    uint32_t bt_len;
+    uint32_t pad;
+} sd_alignment;
+
+typedef struct {
+    uint64_t alignments;      /* pairs aligned (after the length pre-filter)            */
+    uint64_t passed;          /* alignments accepted by Alignment::checkCriteria        */
+    uint64_t word_mode;       /* pairs whose 8-bit pass overflowed (re-run in 16-bit semantics) */
+    uint64_t reverse_passes;
+    uint64_t tracebacks;
+    uint64_t cells_forward, cells_reverse, cells_traceback;
+    double sw_ms;             /* device time of the score/coordinate kernels, CUDA events */
+    double traceback_ms;
+    double total_ms;
+} sd_align_stats;
+
+/* Body of the query loop of Alignment::run (lib/mmseqs/src/alignment/Alignment.cpp:312-511) for the
+ * (query, target) pairs of a prefilter result: pairs must be grouped by query.  Accepted alignments come
+ * back grouped by query (ascending query index) and, inside a query, in Matcher::compareHits order
+ * (Matcher.h:157-168).  db_residues is the E-value search-space size (0: residues of the index).
+ * Returns SD_ESMALL with *n_out / *bt_used = required sizes when a buffer is too small. */
+int sd_align_run(sd_context *ctx, const sd_target_index *idx, const char *qseqs, const uint64_t *qoff, uint32_t nq,
+                 uint32_t query_first, const uint32_t *pair_q, const uint32_t *pair_t, uint64_t n_pairs,
+                 uint64_t db_residues, const sd_align_params *par, sd_alignment *out, uint64_t cap, uint64_t *n_out,
+                 char *bt_pool, uint64_t bt_cap, uint64_t *bt_used, sd_align_stats *stats);
+
+/* Matcher::resultToBuffer (Matcher.cpp:280-327): one text line "tKey bits seqId E qS qE qL tS tE tL cigar\n";
+ * returns the number of bytes written (0 if cap is too small). */
+int sd_format_alignment(const sd_alignment *a, uint32_t target_key, const char *bt_pool, char *buf, int cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -152,3 +152,71 @@ def prefilter(ctx, index, qseqs, qoff, params, query_first=0):
                                   ctypes.byref(params), hits.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(cap),
                                   ctypes.byref(n), ctypes.byref(st)))
     return hits[:n.value], st.as_dict()
+
+
+# ----------------------------------------------------------------------------- align
+class AlignParams(ctypes.Structure):
+    """Mirrors sd_align_params (flags of the reference's `align` module)."""
+    _fields_ = [("evalue_thr", ctypes.c_double), ("min_seq_id", ctypes.c_double), ("cov_thr", ctypes.c_float),
+                ("cov_mode", ctypes.c_int), ("min_aln_len", ctypes.c_int), ("comp_bias_corr", ctypes.c_int),
+                ("gap_open", ctypes.c_int), ("gap_extend", ctypes.c_int), ("score_bias", ctypes.c_float),
+                ("same_db", ctypes.c_int)]
+
+
+class AlignStats(ctypes.Structure):
+    _fields_ = [("alignments", ctypes.c_uint64), ("passed", ctypes.c_uint64), ("word_mode", ctypes.c_uint64),
+                ("reverse_passes", ctypes.c_uint64), ("tracebacks", ctypes.c_uint64), ("cells_forward", ctypes.c_uint64),
+                ("cells_reverse", ctypes.c_uint64), ("cells_traceback", ctypes.c_uint64), ("sw_ms", ctypes.c_double),
+                ("traceback_ms", ctypes.c_double), ("total_ms", ctypes.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+ALN_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("score", "<i4"), ("bits", "<i4"), ("seq_id", "<f4"),
+                      ("qcov", "<f4"), ("tcov", "<f4"), ("evalue", "<f8"), ("q_start", "<i4"), ("q_end", "<i4"),
+                      ("q_len", "<i4"), ("t_start", "<i4"), ("t_end", "<i4"), ("t_len", "<i4"), ("aln_len", "<i4"),
+                      ("bt_off", "<u8"), ("bt_len", "<u4"), ("pad", "<u4")], align=True)
+
+
+def default_align_params(**kw):
+    p = AlignParams()
+    lib().sd_align_params_default(ctypes.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def align(ctx, index, qseqs, qoff, pair_q, pair_t, params, query_first=0, db_residues=0):
+    """Body of the reference's align query loop for prefilter pairs -> (alignments, backtrace pool, stats)."""
+    assert ALN_DTYPE.itemsize == 88, ALN_DTYPE.itemsize
+    qseqs, qoff = _seq_args(qseqs, qoff)
+    nq = len(qoff) - 1
+    pair_q = np.ascontiguousarray(pair_q, dtype=np.uint32)
+    pair_t = np.ascontiguousarray(pair_t, dtype=np.uint32)
+    n_pairs = len(pair_q)
+    cap = max(1, n_pairs)
+    lens_t = np.diff(index.off).astype(np.int64)
+    lens_q = np.diff(qoff).astype(np.int64)
+    bt_cap = int((lens_t[pair_t] + lens_q[pair_q]).sum()) + 64 if n_pairs else 64
+    out = np.zeros(cap, dtype=ALN_DTYPE)
+    pool = np.zeros(bt_cap, dtype=np.uint8)
+    n = ctypes.c_uint64(0)
+    used = ctypes.c_uint64(0)
+    st = AlignStats()
+    _check(lib().sd_align_run(ctx._h, index._h, qseqs.ctypes.data_as(ctypes.c_char_p), qoff.ctypes.data_as(ctypes.c_void_p),
+                              ctypes.c_uint32(nq), ctypes.c_uint32(query_first), pair_q.ctypes.data_as(ctypes.c_void_p),
+                              pair_t.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(n_pairs), ctypes.c_uint64(db_residues),
+                              ctypes.byref(params), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(cap), ctypes.byref(n),
+                              pool.ctypes.data_as(ctypes.c_char_p), ctypes.c_uint64(bt_cap), ctypes.byref(used), ctypes.byref(st)))
+    return out[:n.value], pool[:used.value], st.as_dict()
+
+
+def format_alignment(aln, target_key, pool):
+    buf = ctypes.create_string_buffer(1 << 18)
+    rec = np.ascontiguousarray(aln.reshape(1))
+    n = lib().sd_format_alignment(rec.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(int(target_key)),
+                                  pool.ctypes.data_as(ctypes.c_char_p), buf, ctypes.c_int(1 << 18))
+    if n <= 0:
+        raise SdError("sd_format_alignment failed")
+    return buf.raw[:n]

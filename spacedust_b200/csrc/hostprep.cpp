@@ -250,4 +250,48 @@ int referenceBinSize(uint64_t nTargets) {
     return 2048;
 }
 
+Evaluer::Evaluer(double dbRes) : dbResidues(dbRes) {
+    // {lambda, K, a1, b1, a2, b2, alpha1, beta1, alpha2, beta2, sigma, tau} for blosum62.out, gap open 11, extend 1
+    lambda = 0.27359865037097330642; K = 0.044620920658722244834;
+    const double a1 = 1.5938724404943873658, b1 = -19.959867650284412122, a2 = 1.5938724404943873658, b2 = -19.959867650284412122;
+    const double alpha1 = 30.455610143099914211, beta1 = -622.28684628915891608, alpha2 = 30.455610143099914211, beta2 = -622.28684628915891608;
+    sigma = 29.602444874818868215; tau = -601.81087985041381216;
+    aI = a2; aJ = a1; bI = b2; bJ = b1; alphaI = alpha2; alphaJ = alpha1; betaI = beta2; betaJ = beta1;
+    viThr = std::max(2.0 * alphaI / lambda, 0.0);
+    vjThr = std::max(2.0 * alphaJ / lambda, 0.0);
+    cThr = std::max(2.0 * sigma / lambda, 0.0);
+    logK = std::log(K);
+}
+
+static inline double normalCdf(double x) { return 0.5 * std::erfc(-std::sqrt(0.5) * x); }
+
+double Evaluer::area(double y, double seqLen) const {
+    const double pi = 3.1415926535897932384626433832795;
+    const double invSqrt2Pi = 1 / std::sqrt(2.0 * pi);
+    const double m = dbResidues, n = seqLen;       // AlignmentEvaluer::area passes (seqlen2_, seqlen1_)
+    const double mLen = m - (aI * y + bI);
+    const double vi = std::max(viThr, alphaI * y + betaI);
+    const double sVi = std::sqrt(vi);
+    const double mF = (sVi == 0.0) ? 1e100 : mLen / sVi;
+    const double pM = normalCdf(mF);
+    const double eM = -invSqrt2Pi * std::exp(-0.5 * mF * mF);
+    const double p1 = mLen * pM - sVi * eM;
+    const double nLen = n - (aJ * y + bJ);
+    const double vj = std::max(vjThr, alphaJ * y + betaJ);
+    const double sVj = std::sqrt(vj);
+    const double nF = (sVj == 0.0) ? 1e100 : nLen / sVj;
+    const double pN = normalCdf(nF);
+    const double eN = -invSqrt2Pi * std::exp(-0.5 * nF * nF);
+    const double p2 = nLen * pN - sVj * eN;
+    const double c = std::max(cThr, sigma * y + tau);
+    return p1 * p2 + c * (pM * pN);
+}
+
+double Evaluer::evalue(double score, double seqLen) const {
+    const double perArea = K * std::exp(-lambda * score);
+    return perArea * area(score, seqLen);
+}
+
+int Evaluer::bitScore(double score) const { return static_cast<int>((lambda * score - logK) / std::log(2.0) + 0.5); }
+
 }  // namespace sd

@@ -42,4 +42,15 @@ void buildExt3(const SubMat &seedMat, std::vector<int16_t> &score, std::vector<u
 // QueryMatcher::initDiagonalMatcher (QueryMatcher.cpp:422-449) + Util::getL2CacheSize (Util.cpp:317-332)
 int referenceBinSize(uint64_t nTargets);
 
+// EvalueComputation (alignment/EvalueComputation.h) with the BLOSUM62 (11,1) Gumbel constants and ALP's
+// finite-size-corrected area (lib/alp/sls_pvalues.cpp:366-532)
+struct Evaluer {
+    double lambda, K, logK, aI, aJ, bI, bJ, alphaI, alphaJ, betaI, betaJ, sigma, tau, viThr, vjThr, cThr;
+    double dbResidues;
+    explicit Evaluer(double dbResidues);
+    double area(double score, double seqLen) const;
+    double evalue(double score, double seqLen) const;
+    int bitScore(double score) const;
+};
+
 }  // namespace sd

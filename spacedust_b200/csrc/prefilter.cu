@@ -22,6 +22,7 @@
 #include <numeric>
 
 #include "sd_internal.h"
+#include "prep.cuh"
 
 namespace sd {
 
@@ -58,15 +59,6 @@ __device__ __forceinline__ uint32_t warpFindOwner(uint32_t excl, uint32_t x) {
 // ------------------------------------------------------------------------------------------------
 // index build
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t seqOfPosition(const uint32_t *off, uint32_t n, uint32_t gp) {
-    uint32_t lo = 0, hi = n;   // find s with off[s] <= gp < off[s+1]
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (off[mid] <= gp) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
 // key = seq<<42 | kmer<<16 | pos for indexable k-mers, ~0 otherwise (IndexTable::addKmerCount)
 __global__ void extractTargetKmers(const uint8_t *__restrict__ res, const uint32_t *__restrict__ off, uint32_t nT,
                                    uint32_t totalRes, const int8_t *__restrict__ selfScore, int kmerThr,
@@ -126,40 +118,14 @@ struct QueryBatchDev {
     const int16_t *thr;      // per-position similar-k-mer threshold, -1 = no k-mer here
 };
 
-__global__ void mapResidues(const char *__restrict__ ascii, uint64_t n, const uint8_t *__restrict__ lut,
-                            uint8_t *__restrict__ out) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = lut[(uint8_t)ascii[i]];
-}
-
-// SubstitutionMatrix::calcLocalAaBiasCorrection (commons/SubstitutionMatrix.cpp:79-109): the float
-// accumulator is updated through double intermediates; __dmul_rn/__dadd_rn keep nvcc from fusing.
-__global__ void compositionBias(const uint8_t *__restrict__ code, const uint32_t *__restrict__ off, uint32_t nQ,
-                                uint32_t totalRes, const int16_t *__restrict__ seedSub /*21x21*/,
-                                const double *__restrict__ pBack, int enabled, float *__restrict__ bias,
-                                int8_t *__restrict__ corr) {
+// UngappedAlignment::createProfile (UngappedAlignment.cpp:393-396): aaCorrBias/4 -+ 0.5 evaluated in double,
+// stored to float, truncated to char
+__global__ void profileCorrection(const float *__restrict__ bias, uint32_t totalRes, int8_t *__restrict__ corr) {
     uint32_t gp = blockIdx.x * blockDim.x + threadIdx.x;
     if (gp >= totalRes) return;
-    float b = 0.0f;
-    if (enabled) {
-        uint32_t s = seqOfPosition(off, nQ, gp);
-        int i = (int)(gp - off[s]);
-        int L = (int)(off[s + 1] - off[s]);
-        int lo = max(0, i - 20), hi = min(L, i + 20);
-        const uint8_t *seq = code + off[s];
-        const int16_t *row = seedSub + seq[i] * AA;
-        int sum = 0;
-        for (int j = lo; j < hi; j++) sum += row[seq[j]];
-        sum -= row[seq[i]];
-        float d = (float)sum;
-        d = __double2float_rn(__ddiv_rn((double)d, __dmul_rn(-1.0, (double)(float)(hi - lo))));
-        for (int a = 0; a < AA; a++) d = __double2float_rn(__dadd_rn((double)d, __dmul_rn(pBack[a], (double)(float)row[a])));
-        b = __fmul_rn(1.0f, d);
-    }
-    bias[gp] = b;
-    // createProfile: aaCorrBias/4 -+ 0.5 evaluated in double, stored to float, truncated to char
-    float q = __fdiv_rn(b, 4.0f);
-    float r = (b < 0.0f) ? __double2float_rn(__dadd_rn((double)q, -0.5)) : __double2float_rn(__dadd_rn((double)q, 0.5));
+    const float b = bias[gp];
+    const float q = __fdiv_rn(b, 4.0f);
+    const float r = (b < 0.0f) ? __double2float_rn(__dadd_rn((double)q, -0.5)) : __double2float_rn(__dadd_rn((double)q, 0.5));
     corr[gp] = (int8_t)(int)r;
 }
 
@@ -704,9 +670,12 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
     std::vector<uint8_t> codes(total + SPAN);
     mapSequence(seqs, total, codes.data());
     std::fill(codes.begin() + total, codes.end(), (uint8_t)XCODE);
+    int rc;
+    if ((rc = idx->raw.alloc(total + SPAN)) != SD_OK) return rc;
+    SD_CUDA(cudaMemcpy(idx->raw.p, codes.data(), total + SPAN, cudaMemcpyHostToDevice));
+    for (uint32_t i = 0; i < n; i++) idx->maxLen = std::max<uint32_t>(idx->maxLen, (uint32_t)(off[i + 1] - off[i]));
     if (par->mask) idx->masked = tantanMaskAll(codes.data(), off, n, ctx->seedMat, (double)par->mask_prob);
 
-    int rc;
     if ((rc = idx->res.alloc(total + SPAN)) != SD_OK) return rc;
     if ((rc = idx->off.alloc(n + 1)) != SD_OK) return rc;
     if ((rc = idx->kOff.alloc((size_t)NKMER + 1)) != SD_OK) return rc;
@@ -835,9 +804,10 @@ extern "C" int sd_prefilter_run(sd_context *ctx, const sd_target_index *idx, con
     SD_CUDA(cudaMemsetAsync(dCode.p + total, XCODE, SPAN, st));
     SD_CUDA(cudaMemsetAsync(dBias.p + total, 0, SPAN * sizeof(float), st));
     mapResidues<<<gridFor(total, 256), 256, 0, st>>>(dAscii.p, total, dLut.p, dCode.p);
-    compositionBias<<<gridFor(nPos, 128), 128, 0, st>>>(dCode.p, dOff.p, nq, nPos, dSeedSub.p, dPBack.p, par->comp_bias_corr, dBias.p, dCorr.p);
+    compositionBias<<<gridFor(nPos, 128), 128, 0, st>>>(dCode.p, dOff.p, nq, nPos, dSeedSub.p, dPBack.p, par->comp_bias_corr, dBias.p);
+    profileCorrection<<<gridFor(nPos, 256), 256, 0, st>>>(dBias.p, nPos, dCorr.p);
     kmerThresholds<<<gridFor(nPos, 256), 256, 0, st>>>(dCode.p, dOff.p, nq, nPos, dBias.p, idx->kmerThr, dThr.p);
-    ctx->launches += 3;
+    ctx->launches += 4;
     SD_CUDA(cudaGetLastError());
 
     const uint32_t maxHits = std::min<uint32_t>((uint32_t)std::max(par->max_seqs, 1), idx->nT);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -10,6 +11,8 @@
 
 #include "../../include/sdgpu.h"
 #include "hostprep.h"
+
+struct sd_context;
 
 namespace sd {
 
@@ -56,6 +59,18 @@ struct DevBuf {
     DevBuf &operator=(const DevBuf &) = delete;
 };
 
+struct SwBatch;
+struct SwTask;
+struct SwResult;
+int launchSw(sd_context *ctx, const SwBatch &batch, const SwTask *dTasks, const uint32_t *dOrder, SwResult *dResults,
+             uint32_t nTasks, int *dBoundary, uint32_t boundaryStride, uint32_t nWarpsAllocated, uint32_t *dNext,
+             unsigned long long *dCells);
+int launchSwProfiles(sd_context *ctx, const uint8_t *code, const int8_t *cb, const uint32_t *qOff, uint32_t nQ,
+                     uint32_t totalRes, const int8_t *mat, const uint64_t *profOff, const uint32_t *profStride,
+                     int8_t *fwd, int8_t *rev);
+int launchAlignCompositionBias(sd_context *ctx, const float *bias, uint32_t totalRes, int8_t *cb);
+uint32_t swWarpsPerCta();
+
 }  // namespace sd
 
 struct sd_context {
@@ -80,7 +95,9 @@ struct sd_target_index {
     uint64_t masked = 0;
     int kmerThr = 0;
     std::vector<uint32_t> hostOff;     // nT+1
-    sd::DevBuf<uint8_t> res;           // masked residue codes, concatenated (+ SPAN pad)
+    sd::DevBuf<uint8_t> res;           // masked residue codes, concatenated (+ SPAN pad): prefilter side
+    sd::DevBuf<uint8_t> raw;           // unmasked residue codes: alignment side
+    uint32_t maxLen = 0;
     sd::DevBuf<uint32_t> off;          // nT+1
     sd::DevBuf<uint32_t> kOff;         // NKMER+1 bucket starts
     sd::DevBuf<uint32_t> entSeq;       // bucket entries: target id ...
