@@ -160,6 +160,56 @@ int sd_align_run(sd_context *ctx, const sd_target_index *idx, const char *qseqs,
  * returns the number of bytes written (0 if cap is too small). */
 int sd_format_alignment(const sd_alignment *a, uint32_t target_key, const char *bt_pool, char *buf, int cap);
 
+/* ---- besthitbyset + combinehits + clusterhits (reference flags) ------- */
+typedef struct {
+    float alpha;              /* --alpha             (1)    */
+    int filter_self_match;    /* --filter-self-match (0)    */
+    int max_gene_gap;         /* --max-gene-gap      (3)    */
+    int cluster_size;         /* --cluster-size      (2)    */
+    double cluster_pval;      /* --cluster-pval      (0.01) */
+    double multihit_pval;     /* --multihit-pval     (0.01) */
+} sd_cluster_params;
+
+void sd_cluster_params_default(sd_cluster_params *p);
+
+typedef struct {
+    uint32_t q_set, t_set;    /* dense set indices (= set keys of createsetdb)           */
+    double p_co;              /* clustering + ordering P-value, exp(-score)             */
+    double p_mh;              /* multihit P-value of the cluster                        */
+    uint32_t n;               /* member hits                                            */
+    uint32_t first;           /* offset of the first member in the member array         */
+} sd_cluster;
+
+typedef struct {
+    uint32_t aln;             /* index into the alignment array given to sd_cluster_run */
+    uint32_t pad;
+    double pval;              /* per-hit P-value as the reference prints it in column 3 */
+} sd_cluster_member;
+
+typedef struct {
+    uint64_t best_hits;       /* (query gene, target set) best hits after besthitbyset  */
+    uint64_t genome_pairs;    /* (query set, target set) matches after combinehits      */
+    uint64_t pairs_clustered; /* matches with at least two hits                         */
+    uint64_t max_hits_per_pair;
+    uint64_t merges;          /* agglomeration steps executed on the device             */
+    uint64_t inexact_log;     /* cluster sizes beyond the host-precomputed log table (device log used) */
+    double kernel_ms;         /* device time of the clustering kernel, CUDA events      */
+    double total_ms;
+} sd_cluster_stats;
+
+/* Bodies of besthitbyset (src/util/besthitbyset.cpp:41-144), mergeresultsbyset, combinehits
+ * (src/util/combinehits.cpp:74-234) and clusterhits (src/util/ClusterHits.cpp:294-490) on the accepted
+ * alignments of sd_align_run (grouped by ascending query, reference order inside a query).
+ * q_set_of/q_pos/q_strand: per query gene its set, gene index in the set (3rd-last field of the lookup name) and
+ * strand (1: start < end); same for targets.  Sets are dense indices in ascending key order.
+ * Clusters come back in the reference's order: ascending (query set, target set), then node index. */
+int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_t n_alns,
+                   const uint32_t *q_set_of, const uint32_t *q_pos, const uint8_t *q_strand, uint32_t nq,
+                   const uint32_t *t_set_of, const uint32_t *t_pos, const uint8_t *t_strand, uint32_t nt,
+                   const uint32_t *q_set_size, uint32_t n_q_sets, const uint32_t *t_set_size, uint32_t n_t_sets,
+                   const sd_cluster_params *par, sd_cluster *clusters, uint64_t cap, uint64_t *n_clusters,
+                   sd_cluster_member *members, uint64_t mcap, uint64_t *n_members, sd_cluster_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -220,3 +220,56 @@ def format_alignment(aln, target_key, pool):
     if n <= 0:
         raise SdError("sd_format_alignment failed")
     return buf.raw[:n]
+
+
+# ----------------------------------------------------------------------------- besthitbyset / combinehits / clusterhits
+class ClusterParams(ctypes.Structure):
+    """Mirrors sd_cluster_params (flags of combinehits / clusterhits)."""
+    _fields_ = [("alpha", ctypes.c_float), ("filter_self_match", ctypes.c_int), ("max_gene_gap", ctypes.c_int),
+                ("cluster_size", ctypes.c_int), ("cluster_pval", ctypes.c_double), ("multihit_pval", ctypes.c_double)]
+
+
+class ClusterStats(ctypes.Structure):
+    _fields_ = [("best_hits", ctypes.c_uint64), ("genome_pairs", ctypes.c_uint64), ("pairs_clustered", ctypes.c_uint64),
+                ("max_hits_per_pair", ctypes.c_uint64), ("merges", ctypes.c_uint64), ("inexact_log", ctypes.c_uint64),
+                ("kernel_ms", ctypes.c_double), ("total_ms", ctypes.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+CLUSTER_DTYPE = np.dtype([("q_set", "<u4"), ("t_set", "<u4"), ("p_co", "<f8"), ("p_mh", "<f8"), ("n", "<u4"), ("first", "<u4")],
+                         align=True)
+MEMBER_DTYPE = np.dtype([("aln", "<u4"), ("pad", "<u4"), ("pval", "<f8")], align=True)
+
+
+def default_cluster_params(**kw):
+    p = ClusterParams()
+    lib().sd_cluster_params_default(ctypes.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def cluster(ctx, alns, q_meta, t_meta, params):
+    """besthitbyset + combinehits + clusterhits on accepted alignments.
+    q_meta / t_meta: dict(set_of=uint32[n], pos=uint32[n], strand=uint8[n], set_size=uint32[nSets])."""
+    alns = np.ascontiguousarray(alns, dtype=ALN_DTYPE)
+
+    def arr(x, dt):
+        return np.ascontiguousarray(x, dtype=dt)
+    qs, qp, qst, qsz = arr(q_meta["set_of"], np.uint32), arr(q_meta["pos"], np.uint32), arr(q_meta["strand"], np.uint8), arr(q_meta["set_size"], np.uint32)
+    ts, tp, tst, tsz = arr(t_meta["set_of"], np.uint32), arr(t_meta["pos"], np.uint32), arr(t_meta["strand"], np.uint8), arr(t_meta["set_size"], np.uint32)
+    cap = max(1, len(alns))
+    clusters = np.zeros(cap, dtype=CLUSTER_DTYPE)
+    members = np.zeros(cap, dtype=MEMBER_DTYPE)
+    nc, nm = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    st = ClusterStats()
+    p = ctypes.c_void_p
+    _check(lib().sd_cluster_run(ctx._h, alns.ctypes.data_as(p), ctypes.c_uint64(len(alns)),
+                                qs.ctypes.data_as(p), qp.ctypes.data_as(p), qst.ctypes.data_as(p), ctypes.c_uint32(len(qs)),
+                                ts.ctypes.data_as(p), tp.ctypes.data_as(p), tst.ctypes.data_as(p), ctypes.c_uint32(len(ts)),
+                                qsz.ctypes.data_as(p), ctypes.c_uint32(len(qsz)), tsz.ctypes.data_as(p), ctypes.c_uint32(len(tsz)),
+                                ctypes.byref(params), clusters.ctypes.data_as(p), ctypes.c_uint64(cap), ctypes.byref(nc),
+                                members.ctypes.data_as(p), ctypes.c_uint64(cap), ctypes.byref(nm), ctypes.byref(st)))
+    return clusters[:nc.value], members[:nm.value], st.as_dict()

@@ -111,3 +111,20 @@ def pack(proteomes):
     np.cumsum(lens, out=off[1:])
     buf = np.frombuffer(b"".join(seqs), dtype=np.uint8).copy()
     return buf, off, sets
+
+
+def set_metadata(proteomes):
+    """Per protein (file order): set index, gene index inside the set, strand (1: start < end), plus the lookup
+    names `<id>_<geneIdx>_<start>_<end>` createsetdb writes (data/createsetdb.sh:121-135; start > end on the minus strand)."""
+    set_of, pos, strand, names = [], [], [], []
+    for si, p in enumerate(proteomes):
+        for gi, header in enumerate(p["names"]):
+            f = header.split(" # ")
+            start, end, st = int(f[1]), int(f[2]), int(f[3])
+            set_of.append(si)
+            pos.append(gi)
+            strand.append(1 if st > 0 else 0)
+            names.append("%s_%d_%d_%d" % (f[0], gi, start, end) if st > 0 else "%s_%d_%d_%d" % (f[0], gi, end, start))
+    return {"set_of": np.array(set_of, dtype=np.uint32), "pos": np.array(pos, dtype=np.uint32),
+            "strand": np.array(strand, dtype=np.uint8),
+            "set_size": np.array([len(p["names"]) for p in proteomes], dtype=np.uint32), "names": names}

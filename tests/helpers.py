@@ -257,3 +257,61 @@ def parse_pref_db(path, qkeys, tkeys):
                 pq.append(qi)
                 pt.append(key2t[int(line.split(b"\t")[0])])
     return np.array(pq, dtype=np.uint32), np.array(pt, dtype=np.uint32)
+
+
+# ----------------------------------------------------------------------------- oracle: whole clustersearch path
+def oracle_clustersearch(proteomes, filter_self_match=True, max_gene_gap=3, cluster_size=2, cluster_pval=0.01,
+                         multihit_pval=0.01, alpha=1.0, alns_override=None):
+    """prefilter -> align -> prefixid -> besthitbyset -> mergeresultsbyset -> combinehits -> clusterhits with the
+    oracle restatements; -> dict(alns, bt, result, matches, clusters) (text records as the reference exchanges them)."""
+    import sys
+    sys.path.insert(0, ORACLE_DIR)
+    import orc_cluster as oc
+    from spacedust_b200 import synth
+    buf, off, _ = synth.pack(proteomes)
+    meta = synth.set_metadata(proteomes)
+    n = len(off) - 1
+    keys = np.arange(n, dtype=np.uint32)
+    if alns_override is None:
+        hits, _ = orc_prefilter(buf, off, buf, off, default_pref_params())
+        alns, bt, _ = orc_align(buf, off, keys, buf, off, keys, hits["query"], hits["target"], default_align_params())
+    else:
+        alns, bt = alns_override
+    result = {k: [l.decode() for l in v] for k, v in format_alignments(alns, bt, keys).items()}
+    m2s = {i: int(meta["set_of"][i]) for i in range(n)}
+    s2m = {}
+    for i in range(n):
+        s2m.setdefault(int(meta["set_of"][i]), []).append(i)
+    ssz = {i: int(s) for i, s in enumerate(meta["set_size"])}
+    lookup = {i: meta["names"][i] for i in range(n)}
+    agg = oc.besthitbyset(oc.prefixid(result), m2s)
+    merged = oc.mergeresultsbyset(s2m, agg)
+    matches = oc.combinehits(merged, m2s, ssz, ssz, alpha, filter_self_match)
+    clusters = oc.clusterhits(matches, lookup, lookup, max(ssz.values()), d=max_gene_gap, cls=cluster_size,
+                              p_clu_thr=cluster_pval, p_mh_thr=multihit_pval, alpha=alpha)
+    return {"alns": alns, "bt": bt, "result": result, "matches": matches, "clusters": clusters, "meta": meta, "lookup": lookup}
+
+
+def canonical_clusters(clusters):
+    """[(header, [lines])] -> sorted list of (qSet, tSet, pCO, pMH, n, tuple(lines)) (cluster keys/order are not deterministic)."""
+    out = []
+    for hdr, lines in clusters:
+        h = hdr.split("\t")
+        out.append((int(h[0]), int(h[1]), h[2], h[3], int(h[4]), tuple(lines)))
+    return sorted(out)
+
+
+def parse_result_tsv(path, source_to_set, name_to_key):
+    """Final clustersearch TSV -> canonical clusters in the (header, lines) convention of clusterhits, with
+    names mapped back to keys so that it can be compared with canonical_clusters()."""
+    out, cur = [], None
+    for line in open(path):
+        line = line.rstrip("\n")
+        if line.startswith("#"):
+            f = line.split("\t")
+            cur = [source_to_set[f[1]], source_to_set[f[2]], f[3], f[4], int(f[5]), []]
+            out.append(cur)
+        elif line.startswith(">"):
+            f = line[1:].split("\t")
+            cur[5].append("\t".join([str(name_to_key[f[0]]), str(name_to_key[f[1]])] + f[2:]))
+    return sorted((a, b, c, d, e, tuple(l)) for a, b, c, d, e, l in out)

@@ -51,3 +51,45 @@ def test_oracle_prefilter_golden():
     assert np.array_equal(hits["target"], z["target"])
     assert np.array_equal(hits["score"], z["score"])
     assert np.array_equal(hits["diag"], z["diag"])
+
+
+def test_oracle_align_vs_reference(ref_setdb, synth_small):
+    """oracle align on the reference's own prefilter DB == reference result DB (text identical)."""
+    d = ref_setdb
+    db = os.path.join(d, "setDB")
+    if not os.path.exists(os.path.join(d, "pref.index")):
+        helpers.run_ref(["prefilter", db, db, os.path.join(d, "pref"), "-s", "5.7", "--max-seqs", "300", "-c", "0.8",
+                         "--cov-mode", "2", "--min-ungapped-score", "15", "--threads", "2", "-v", "1"])
+    helpers.run_ref(["align", db, db, os.path.join(d, "pref"), os.path.join(d, "result"), "-a", "1", "--alignment-mode", "2",
+                     "-e", "10", "--min-aln-len", "30", "-c", "0.8", "--cov-mode", "2", "--threads", "2", "-v", "1"])
+    keys, buf, off = helpers.load_seqdb(db)
+    pq, pt = helpers.parse_pref_db(os.path.join(d, "pref"), keys, keys)
+    alns, bt, st = helpers.orc_align(buf, off, keys, buf, off, keys, pq, pt, helpers.default_align_params())
+    mine = helpers.format_alignments(alns, bt, keys)
+    ref = helpers.read_db(os.path.join(d, "result"))
+    for k in keys:
+        assert [l for l in ref[int(k)].split(b"\n") if l] == mine[int(k)], "query %d" % k
+    assert st["passed"] > 0 and st["wordMode"] > 0
+
+
+def test_oracle_clustersearch_vs_reference(ref_setdb, synth_small):
+    """Whole path: reference `clustersearch --filter-self-match 1` final TSV == oracle pipeline (canonical order)."""
+    d = ref_setdb
+    db = os.path.join(d, "setDB")
+    out = os.path.join(d, "res.tsv")
+    helpers.run_ref(["clustersearch", db, db, out, os.path.join(d, "tmpcs"), "--filter-self-match", "1", "--threads", "2", "-v", "1"])
+    o = helpers.oracle_clustersearch(synth_small, filter_self_match=True)
+    # the reference's lookup must be what synth.set_metadata predicts
+    lookup = {}
+    for line in open(db + ".lookup"):
+        a = line.rstrip("\n").split("\t")
+        lookup[int(a[0])] = a[1]
+    assert lookup == o["lookup"]
+    src = {}
+    for line in open(db + ".source"):
+        a = line.rstrip("\n").split("\t")
+        src[a[1]] = int(a[0])
+    name_to_key = {v: k for k, v in lookup.items()}
+    ref = helpers.parse_result_tsv(out, src, name_to_key)
+    assert ref == helpers.canonical_clusters(o["clusters"])
+    assert len(ref) > 5
