@@ -1,0 +1,390 @@
+#!/usr/bin/env python3
+"""bench.py -- `spacedust clustersearch --search-mode 0` hot path on B200 vs the reference's AVX2 CPU path.
+
+Metric (BASELINE.json): query-genes/s of the clustersearch hot path (prefilter -> align -> besthitbyset/combinehits ->
+clusterhits) on synthetic proteomes.  Workload at N=1 is BASELINE config[1]: 20 synthetic 3k-gene prokaryote
+proteomes all-vs-all (60 000 query genes, 19.5 M residues), generator spacedust_b200/synth.py, seed 20261017.
+
+One step = one pass of the hot path over the whole query batch.
+  value  : target DB + k-mer index and the query batch already resident in HBM when the timed region starts
+  e2e    : same step through the C ABI from pinned HOST buffers: target index build (upload, masking, index),
+           query upload, all stages, results read back -- what `clustersearch` does after `createsetdb`
+Multi-GPU (--gpus N via torchrun): the target index is replicated, query SETS are split across ranks (no
+data-path collective; one NCCL all_gather of the per-rank result counts), total work fixed => "strong".
+
+`--impl reference` times the unmodified reference binary (oracle/_ref/spacedust, built by oracle/build_ref.py)
+on the host cores on a bounded sample of the same workload (S query proteomes against the same 20-proteome
+target setDB).
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PROTEOMES = 20
+GENES = 3000
+SEED = 20261017
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "spacedust")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--proteomes", type=int, default=N_PROTEOMES)
+    ap.add_argument("--genes", type=int, default=GENES)
+    ap.add_argument("--ref-sample", type=int, default=2, help="query proteomes in the reference / cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons every 200 ms while the timed region runs."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=5).stdout.decode().strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def parse_stage_times(log):
+    """`Time for processing: 0h 0m 5s 798ms` after each module banner (lib/mmseqs/src/commons/Application.cpp:45-48)."""
+    stages, cur = {}, None
+    for line in log.split("\n"):
+        w = line.split(" ")
+        if w and w[0] in ("prefilter", "align", "prefixid", "besthitbyset", "mergeresultsbyset", "combinehits", "clusterhits",
+                          "summarizeresults"):
+            cur = w[0]
+        if line.startswith("Time for processing:") and cur:
+            f = line.replace("Time for processing:", "").split()
+            sec = 0.0
+            for tok in f:
+                if tok.endswith("ms"):
+                    sec += float(tok[:-2]) / 1e3
+                elif tok.endswith("h"):
+                    sec += float(tok[:-1]) * 3600
+                elif tok.endswith("m"):
+                    sec += float(tok[:-1]) * 60
+                elif tok.endswith("s"):
+                    sec += float(tok[:-1])
+            stages[cur] = stages.get(cur, 0.0) + sec
+            cur = None
+        if line.startswith("Time for index table init:"):
+            f = line.replace("Time for index table init:", "").split()
+            sec = 0.0
+            for tok in f:
+                if tok.endswith("ms"):
+                    sec += float(tok[:-2]) / 1e3
+                elif tok.endswith("h"):
+                    sec += float(tok[:-1]) * 3600
+                elif tok.endswith("m"):
+                    sec += float(tok[:-1]) * 60
+                elif tok.endswith("s"):
+                    sec += float(tok[:-1])
+            stages["index_table_init"] = sec
+    return stages
+
+
+class ReferenceRunner:
+    """createsetdb once (excluded from the timing), then clustersearch per step."""
+
+    def __init__(self, proteomes, n_query_sets):
+        from spacedust_b200 import synth
+        if not (os.path.exists(REF_BIN) and os.access(REF_BIN, os.X_OK)):
+            raise RuntimeError("oracle/_ref/spacedust is missing: run `python oracle/build_ref.py` in the build container")
+        self.dir = tempfile.mkdtemp(prefix="sdbench_ref_")
+        self.threads = os.cpu_count() or 1
+        self.env = dict(os.environ, MMSEQS_FORCE_MERGE="1")
+        paths = synth.write_fasta(proteomes, os.path.join(self.dir, "faa"))
+        self._run(["createsetdb"] + paths + [os.path.join(self.dir, "tDB"), os.path.join(self.dir, "tmp_t"), "-v", "1"])
+        self._run(["createsetdb"] + paths[:n_query_sets] + [os.path.join(self.dir, "qDB"), os.path.join(self.dir, "tmp_q"), "-v", "1"])
+        self.n_queries = sum(len(p["seqs"]) for p in proteomes[:n_query_sets])
+        self.step_no = 0
+
+    def _run(self, args):
+        r = subprocess.run([REF_BIN] + args, env=self.env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+        if r.returncode != 0:
+            raise RuntimeError("reference failed: %s\n%s" % (" ".join(args[:3]), r.stdout.decode()[-1500:]))
+        return r.stdout.decode()
+
+    def step(self):
+        self.step_no += 1
+        tmp = os.path.join(self.dir, "tmp_cs%d" % self.step_no)
+        out = os.path.join(self.dir, "out%d.tsv" % self.step_no)
+        t0 = time.perf_counter()
+        log = self._run(["clustersearch", os.path.join(self.dir, "qDB"), os.path.join(self.dir, "tDB"), out, tmp,
+                         "--filter-self-match", "1", "--threads", str(self.threads), "-v", "3"])
+        dt = time.perf_counter() - t0
+        n_clusters = sum(1 for l in open(out) if l.startswith("#"))
+        shutil.rmtree(tmp, ignore_errors=True)
+        return dt, parse_stage_times(log), n_clusters
+
+    def close(self):
+        shutil.rmtree(self.dir, ignore_errors=True)
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args, proteomes, rank, world):
+    if rank != 0:
+        return
+    runner = ReferenceRunner(proteomes, args.ref_sample)
+    try:
+        for _ in range(args.warmup):
+            runner.step()
+        times, stages = [], {}
+        for _ in range(args.steps):
+            dt, stages, n_clu = runner.step()
+            times.append(dt)
+        total = sum(times)
+        value = runner.n_queries * args.steps / total
+        sample = ("%d of %d query proteomes (%d query genes) against the full %d-proteome target setDB, "
+                  "clustersearch --filter-self-match 1 --threads %d; createsetdb excluded"
+                  % (args.ref_sample, args.proteomes, runner.n_queries, args.proteomes, runner.threads))
+        line = {"impl": "reference", "metric": "clustersearch query-genes/s", "value": value, "unit": "query-genes/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
+                "config": workload_config(args),
+                "cpu_baseline": {"value": value, "unit": "query-genes/s", "cores": runner.threads, "kind": "reference",
+                                 "sample": sample, "cpu": cpu_model(), "stage_seconds": stages},
+                "e2e": {"value": value, "unit": "query-genes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+    finally:
+        runner.close()
+
+
+def workload_config(args):
+    return {"workload": "%d synthetic %d-gene prokaryote proteomes all-vs-all (BASELINE config[1]), seed %d, "
+                        "clustersearch --search-mode 0 --filter-self-match 1, defaults -s 5.7 --max-seqs 300 -e 10 -c 0.8 --cov-mode 2"
+                        % (args.proteomes, args.genes, SEED),
+            "query_genes": args.proteomes * args.genes, "proteomes": args.proteomes, "genes_per_proteome": args.genes,
+            "l2": "inputs larger than L2 (k-mer index + neighbour tables + per-warp state > 1 GB vs 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args, proteomes, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import spacedust_b200 as sd
+    from spacedust_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    buf, off, _ = synth.pack(proteomes)
+    meta = synth.set_metadata(proteomes)
+    n_total = len(off) - 1
+    # this rank's query sets: contiguous block of proteomes
+    sets = np.array_split(np.arange(args.proteomes), world)[rank]
+    sel = np.nonzero(np.isin(meta["set_of"], sets))[0]
+    q_first = int(sel[0]) if len(sel) else 0
+    q_lo, q_hi = (int(off[sel[0]]), int(off[sel[-1] + 1])) if len(sel) else (0, 0)
+    qbuf = buf[q_lo:q_hi]
+    qoff = (off[sel[0]:sel[-1] + 2] - off[sel[0]]).astype(np.uint64) if len(sel) else np.zeros(1, dtype=np.uint64)
+    q_meta = {"set_of": meta["set_of"][sel], "pos": meta["pos"][sel], "strand": meta["strand"][sel], "set_size": meta["set_size"]}
+    nq_local = len(sel)
+
+    # pinned host staging for the end-to-end arm
+    t_pin = torch.from_numpy(buf.copy()).pin_memory()
+    q_pin = torch.from_numpy(qbuf.copy()).pin_memory()
+    tbuf_h, qbuf_h = t_pin.numpy(), q_pin.numpy()
+
+    ctx = sd.Context(local_rank)
+    pp = sd.default_prefilter_params(same_db=1)
+    ap = sd.default_align_params(same_db=1)
+    cp = sd.default_cluster_params(filter_self_match=1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- resident arm
+    idx = sd.TargetIndex(ctx, tbuf_h, off, pp)
+    batch = sd.QueryBatch(ctx, qbuf_h, qoff)
+    res = None
+    for _ in range(args.warmup):
+        res = sd.clustersearch(ctx, idx, batch, q_meta, meta, pp, ap, cp, q_first)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = ctx.launches
+    t0 = time.perf_counter()
+    stage = {"prefilter_ms": 0.0, "prefilter_kernel_ms": 0.0, "align_ms": 0.0, "sw_kernel_ms": 0.0, "traceback_ms": 0.0,
+             "cluster_ms": 0.0, "cluster_kernel_ms": 0.0}
+    for _ in range(args.steps):
+        res = sd.clustersearch(ctx, idx, batch, q_meta, meta, pp, ap, cp, q_first)
+        stage["prefilter_ms"] += res["prefilter_stats"]["total_ms"]
+        stage["prefilter_kernel_ms"] += res["prefilter_stats"]["kernel_ms"]
+        stage["align_ms"] += res["align_stats"]["total_ms"]
+        stage["sw_kernel_ms"] += res["align_stats"]["sw_ms"]
+        stage["traceback_ms"] += res["align_stats"]["traceback_ms"]
+        stage["cluster_ms"] += res["cluster_stats"]["total_ms"]
+        stage["cluster_kernel_ms"] += res["cluster_stats"]["kernel_ms"]
+    barrier()
+    dt = time.perf_counter() - t0
+    launches = ctx.launches - launches0
+    clocks = sampler.stop() if sampler else None
+    # ---------------- end-to-end arm: host buffers in, results out, every step
+    batch.close()
+    idx.close()
+    e2e_h2d = int(len(tbuf_h) + len(qbuf_h) + 8 * (len(off) + len(qoff)))
+    e2e_d2h = 0
+    for it in range(1 + args.steps):      # one untimed pass, then K timed
+        if it == 1:
+            barrier()
+            t1 = time.perf_counter()
+        idx2 = sd.TargetIndex(ctx, tbuf_h, off, pp)
+        b2 = sd.QueryBatch(ctx, qbuf_h, qoff)
+        r2 = sd.clustersearch(ctx, idx2, b2, q_meta, meta, pp, ap, cp, q_first)
+        e2e_d2h = int(r2["hits"].nbytes + r2["alns"].nbytes + r2["pool"].nbytes + r2["clusters"].nbytes + r2["members"].nbytes)
+        b2.close()
+        idx2.close()
+    barrier()
+    dt_e2e = time.perf_counter() - t1
+
+    # max over ranks
+    t_all = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
+    counts = torch.tensor([len(res["hits"]), len(res["alns"]), len(res["clusters"]), nq_local], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        gathered = [torch.zeros_like(counts) for _ in range(world)]
+        dist.all_gather(gathered, counts)          # the one collective of the path: per-rank result sizes
+        counts = torch.stack(gathered).sum(0)
+    dt, dt_e2e = float(t_all[0]), float(t_all[1])
+    if rank == 0:
+        pst, ast, cst = res["prefilter_stats"], res["align_stats"], res["cluster_stats"]
+        peak, peak_src = peaks()
+        algo = 8 * pst["probes"] + 6 * pst["matches"] + pst["diag_residues"] + 21 * pst["query_residues"] + 10 * pst["hits"]
+        k_ms = pst["kernel_ms"]
+        achieved = algo / 1e9 / (k_ms / 1e3) if k_ms > 0 else 0.0
+        cells = ast["cells_forward"] + ast["cells_reverse"]
+        line = {"metric": "clustersearch query-genes/s", "value": n_total * args.steps / dt, "unit": "query-genes/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32 (u8/i16 scores)/f64",
+                "data": "synthetic", "config": workload_config(args),
+                "e2e": {"value": n_total * args.steps / dt_e2e, "unit": "query-genes/s", "h2d_bytes_per_step": e2e_h2d,
+                        "d2h_bytes_per_step": e2e_d2h, "ms_per_step": 1e3 * dt_e2e / args.steps,
+                        "includes": "target index build from host residues (tantan masking on host threads), query upload, "
+                                    "prefilter, align, besthitbyset/combinehits, clusterhits, results to host"},
+                "gpu_launches": int(launches),
+                "roofline": {"kernel": "prefilterKernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": int(algo),
+                             "bytes_formula": "8*P + 6*M + R + 21*Lq + 10*H (SURVEY.md 8d), P/M/R/H counted by the kernel and "
+                                              "equal to the oracle's counts (tests/test_prefilter_gpu.py)",
+                             "kernel_ms": k_ms},
+                "sw": {"gcups": cells / 1e9 / (ast["sw_ms"] / 1e3) if ast["sw_ms"] > 0 else 0.0, "cells": int(cells),
+                       "kernel_ms": ast["sw_ms"], "pairs": int(ast["alignments"]), "hbm_gbs_algorithmic":
+                       (int(ast["alignments"]) * 380.0) / 1e9 / (ast["sw_ms"] / 1e3) if ast["sw_ms"] > 0 else 0.0},
+                "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+                "results": {"prefilter_hits": int(counts[0]), "alignments": int(counts[1]), "clusters": int(counts[2]),
+                            "query_genes": int(counts[3])},
+                "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(args, proteomes)
+            except Exception as e:      # the baseline is reporting only; never lose the GPU line
+                line["cpu_baseline"] = {"error": str(e)[:300]}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, proteomes):
+    """oracle/_ref (the unmodified reference, AVX2) on this box's host cores, one bounded sample of the workload."""
+    runner = ReferenceRunner(proteomes, args.ref_sample)
+    try:
+        dt, stages, n_clu = runner.step()
+        return {"value": runner.n_queries / dt, "unit": "query-genes/s", "cores": runner.threads, "kind": "reference",
+                "sample": "%d of %d query proteomes (%d query genes) against the full %d-proteome target setDB, one clustersearch run, "
+                          "%.1f s wall; createsetdb excluded" % (args.ref_sample, args.proteomes, runner.n_queries, args.proteomes, dt),
+                "cpu": cpu_model(), "stage_seconds": stages, "clusters_in_sample": n_clu}
+    finally:
+        runner.close()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference" and rank != 0:
+        return 0
+    from spacedust_b200 import synth
+    proteomes = synth.generate(args.proteomes, args.genes, seed=SEED)
+    if args.impl == "reference":
+        run_reference(args, proteomes, rank, world)
+    else:
+        run_ours(args, proteomes, rank, world, local_rank)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

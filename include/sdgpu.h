@@ -46,6 +46,11 @@ void sd_context_destroy(sd_context *ctx);
 /* Number of CUDA kernels launched through this context since creation. */
 uint64_t sd_context_launches(const sd_context *ctx);
 
+/* ---- query batches: residues uploaded and mapped once, reusable by the prefilter and align calls ---- */
+typedef struct sd_query_batch sd_query_batch;
+int sd_query_batch_create(sd_context *ctx, const char *seqs, const uint64_t *off, uint32_t n, sd_query_batch **out);
+void sd_query_batch_destroy(sd_query_batch *b);
+
 /* ---- prefilter (reference flags of `prefilter`) ---------------------- */
 typedef struct {
     float sensitivity;        /* -s                     (5.7)  */
@@ -104,6 +109,11 @@ int sd_prefilter_run(sd_context *ctx, const sd_target_index *idx, const char *qs
                      const sd_prefilter_params *par, sd_prefilter_hit *hits, uint64_t cap,
                      uint64_t *n_hits, sd_prefilter_stats *stats);
 
+/* Same with a device-resident query batch (no host->device copy of query residues in the call). */
+int sd_prefilter_run_batch(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                           const sd_prefilter_params *par, sd_prefilter_hit *hits, uint64_t cap, uint64_t *n_hits,
+                           sd_prefilter_stats *stats);
+
 /* ---- align (reference flags of `align`) -------------------------------- */
 typedef struct {
     double evalue_thr;        /* -e                (10)   */
@@ -155,6 +165,11 @@ int sd_align_run(sd_context *ctx, const sd_target_index *idx, const char *qseqs,
                  uint32_t query_first, const uint32_t *pair_q, const uint32_t *pair_t, uint64_t n_pairs,
                  uint64_t db_residues, const sd_align_params *par, sd_alignment *out, uint64_t cap, uint64_t *n_out,
                  char *bt_pool, uint64_t bt_cap, uint64_t *bt_used, sd_align_stats *stats);
+
+int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                       const uint32_t *pair_q, const uint32_t *pair_t, uint64_t n_pairs, uint64_t db_residues,
+                       const sd_align_params *par, sd_alignment *out, uint64_t cap, uint64_t *n_out, char *bt_pool,
+                       uint64_t bt_cap, uint64_t *bt_used, sd_align_stats *stats);
 
 /* Matcher::resultToBuffer (Matcher.cpp:280-327): one text line "tKey bits seqId E qS qE qL tS tE tL cigar\n";
  * returns the number of bytes written (0 if cap is too small). */

@@ -273,3 +273,75 @@ def cluster(ctx, alns, q_meta, t_meta, params):
                                 ctypes.byref(params), clusters.ctypes.data_as(p), ctypes.c_uint64(cap), ctypes.byref(nc),
                                 members.ctypes.data_as(p), ctypes.c_uint64(cap), ctypes.byref(nm), ctypes.byref(st)))
     return clusters[:nc.value], members[:nm.value], st.as_dict()
+
+
+# ----------------------------------------------------------------------------- device-resident query batches
+class QueryBatch:
+    """Query residues uploaded and mapped once (sd_query_batch); reusable by prefilter_batch / align_batch."""
+
+    def __init__(self, ctx, seqs, off):
+        self.ctx = ctx
+        self.seqs, self.off = _seq_args(seqs, off)
+        self.n = len(self.off) - 1
+        self._h = ctypes.c_void_p()
+        _check(lib().sd_query_batch_create(ctx._h, self.seqs.ctypes.data_as(ctypes.c_char_p),
+                                           self.off.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(self.n), ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().sd_query_batch_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def prefilter_batch(ctx, index, batch, params, query_first=0, out=None):
+    cap = max(1, batch.n * min(max(params.max_seqs, 1), index.n))
+    hits = out if out is not None and len(out) >= cap else np.zeros(cap, dtype=HIT_DTYPE)
+    n = ctypes.c_uint64(0)
+    st = PrefilterStats()
+    _check(lib().sd_prefilter_run_batch(ctx._h, index._h, batch._h, ctypes.c_uint32(query_first), ctypes.byref(params),
+                                        hits.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(len(hits)), ctypes.byref(n), ctypes.byref(st)))
+    return hits[:n.value], st.as_dict()
+
+
+def align_batch(ctx, index, batch, pair_q, pair_t, params, query_first=0, db_residues=0):
+    pair_q = np.ascontiguousarray(pair_q, dtype=np.uint32)
+    pair_t = np.ascontiguousarray(pair_t, dtype=np.uint32)
+    n_pairs = len(pair_q)
+    # accepted alignments are a small fraction of the pairs: start small, grow on SD_ESMALL
+    cap = max(1024, n_pairs // 8)
+    bt_cap = max(1 << 16, cap * 512)
+    n = ctypes.c_uint64(0)
+    used = ctypes.c_uint64(0)
+    st = AlignStats()
+    for _ in range(2):
+        out = np.zeros(cap, dtype=ALN_DTYPE)
+        pool = np.zeros(bt_cap, dtype=np.uint8)
+        rc = lib().sd_align_run_batch(ctx._h, index._h, batch._h, ctypes.c_uint32(query_first), pair_q.ctypes.data_as(ctypes.c_void_p),
+                                      pair_t.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(n_pairs), ctypes.c_uint64(db_residues),
+                                      ctypes.byref(params), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(cap), ctypes.byref(n),
+                                      pool.ctypes.data_as(ctypes.c_char_p), ctypes.c_uint64(bt_cap), ctypes.byref(used), ctypes.byref(st))
+        if rc == -5:     # SD_ESMALL: sizes are reported back
+            cap, bt_cap = int(n.value) + 16, int(used.value) + 64
+            continue
+        _check(rc)
+        return out[:n.value], pool[:used.value], st.as_dict()
+    raise SdError("sd_align_run_batch: output buffers too small twice")
+
+
+def clustersearch(ctx, index, batch, q_meta, t_meta, pref_params=None, aln_params=None, clu_params=None, query_first=0):
+    """The hot path of `spacedust clustersearch` after createsetdb for one query batch:
+    prefilter -> align -> besthitbyset/combinehits -> clusterhits.  -> dict of stage outputs and stats."""
+    pp = pref_params or default_prefilter_params(same_db=1)
+    ap = aln_params or default_align_params(same_db=pp.same_db)
+    cp = clu_params or default_cluster_params(filter_self_match=1)
+    hits, pst = prefilter_batch(ctx, index, batch, pp, query_first)
+    alns, pool, ast = align_batch(ctx, index, batch, hits["query"], hits["target"], ap, query_first)
+    clusters, members, cst = cluster(ctx, alns, q_meta, t_meta, cp)
+    return {"hits": hits, "alns": alns, "pool": pool, "clusters": clusters, "members": members,
+            "prefilter_stats": pst, "align_stats": ast, "cluster_stats": cst}

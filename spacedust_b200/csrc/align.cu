@@ -290,16 +290,30 @@ extern "C" int sd_align_run(sd_context *ctx, const sd_target_index *idx, const c
                             uint32_t query_first, const uint32_t *pair_q, const uint32_t *pair_t, uint64_t n_pairs,
                             uint64_t db_residues, const sd_align_params *par, sd_alignment *out, uint64_t cap, uint64_t *n_out,
                             char *bt_pool, uint64_t bt_cap, uint64_t *bt_used, sd_align_stats *stats) {
-    if (!ctx || !idx || !qseqs || !qoff || !par || !n_out || !bt_used || (n_pairs && (!pair_q || !pair_t))) { setError("sd_align_run: bad argument"); return SD_EINVAL; }
+    if (!ctx || !idx || !qseqs || !qoff || !par || !n_out || !bt_used) { setError("sd_align_run: bad argument"); return SD_EINVAL; }
     *n_out = 0; *bt_used = 0;
     if (stats) memset(stats, 0, sizeof *stats);
     if (nq == 0 || n_pairs == 0) return SD_OK;
+    sd_query_batch *b = nullptr;
+    int rc = sd_query_batch_create(ctx, qseqs, qoff, nq, &b);
+    if (rc) return rc;
+    rc = sd_align_run_batch(ctx, idx, b, query_first, pair_q, pair_t, n_pairs, db_residues, par, out, cap, n_out, bt_pool, bt_cap, bt_used, stats);
+    sd_query_batch_destroy(b);
+    return rc;
+}
+
+extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                                  const uint32_t *pair_q, const uint32_t *pair_t, uint64_t n_pairs, uint64_t db_residues,
+                                  const sd_align_params *par, sd_alignment *out, uint64_t cap, uint64_t *n_out, char *bt_pool,
+                                  uint64_t bt_cap, uint64_t *bt_used, sd_align_stats *stats) {
+    if (!ctx || !idx || !queries || !par || !n_out || !bt_used || (n_pairs && (!pair_q || !pair_t))) { setError("sd_align_run_batch: bad argument"); return SD_EINVAL; }
+    *n_out = 0; *bt_used = 0;
+    if (stats) memset(stats, 0, sizeof *stats);
+    const uint32_t nq = queries->nq;
+    if (nq == 0 || n_pairs == 0) return SD_OK;
     if (par->gap_open < par->gap_extend) { setError("sd_align_run: gap open < gap extend is not supported"); return SD_ELIMIT; }
     if (n_pairs >= 0xffffffffull) { setError("sd_align_run: too many pairs in one call (%llu)", (unsigned long long)n_pairs); return SD_ELIMIT; }
-    const uint64_t total = qoff[nq];
-    if (total >= 0xfff00000ull) { setError("query batch too large (%llu residues): split the call", (unsigned long long)total); return SD_ELIMIT; }
-    for (uint32_t i = 0; i < nq; i++)
-        if (qoff[i + 1] - qoff[i] >= 32768) { setError("query %u longer than 32767 residues: not supported", i); return SD_ELIMIT; }
+    const uint64_t total = queries->total;
     for (uint64_t k = 0; k < n_pairs; k++) {
         if (pair_q[k] >= nq || pair_t[k] >= idx->nT) { setError("sd_align_run: pair %llu out of range", (unsigned long long)k); return SD_EINVAL; }
         if (k && pair_q[k] < pair_q[k - 1]) { setError("sd_align_run: pairs must be grouped by ascending query"); return SD_EINVAL; }
@@ -329,33 +343,29 @@ extern "C" int sd_align_run(sd_context *ctx, const sd_target_index *idx, const c
 
     // ---- query side on the device
     const uint32_t nPos = (uint32_t)total;
-    std::vector<uint32_t> hOff(nq + 1), hStride(nq), hLen(nq);
+    const std::vector<uint32_t> &hOff = queries->hostOff;
+    std::vector<uint32_t> hStride(nq), hLen(nq);
     std::vector<uint64_t> hProfOff(nq + 1);
     hProfOff[0] = 0;
-    for (uint32_t i = 0; i <= nq; i++) hOff[i] = (uint32_t)qoff[i];
     for (uint32_t i = 0; i < nq; i++) {
         hLen[i] = hOff[i + 1] - hOff[i];
         hStride[i] = ((hLen[i] + 3u) & ~3u) + 4u;
         hProfOff[i + 1] = hProfOff[i] + (uint64_t)AA * hStride[i];
     }
     const uint64_t profBytes = hProfOff[nq] + 8192;
-    DevBuf<char> dAscii;
-    DevBuf<uint8_t> dLut, dCode;
-    DevBuf<uint32_t> dOff, dStride, dLen, dNext;
+    struct { const uint8_t *p; } dCode{queries->code.p};
+    struct { const uint32_t *p; } dOff{queries->off.p};
+    DevBuf<uint32_t> dStride, dLen, dNext;
     DevBuf<uint64_t> dProfOff;
     DevBuf<float> dBias;
     DevBuf<int8_t> dCb, dMat8, dProfF, dProfR;
     DevBuf<int16_t> dSub;
     DevBuf<double> dPBack;
     DevBuf<unsigned long long> dCells;
-    if ((rc = dAscii.alloc(total)) || (rc = dLut.alloc(256)) || (rc = dCode.alloc(total + 16)) || (rc = dOff.alloc(nq + 1)) ||
-        (rc = dStride.alloc(nq)) || (rc = dLen.alloc(nq)) || (rc = dProfOff.alloc(nq + 1)) || (rc = dBias.alloc(total + 16)) ||
+    if ((rc = dStride.alloc(nq)) || (rc = dLen.alloc(nq)) || (rc = dProfOff.alloc(nq + 1)) || (rc = dBias.alloc(total + 16)) ||
         (rc = dCb.alloc(total + 16)) || (rc = dMat8.alloc(AA * AA)) || (rc = dSub.alloc(AA * AA)) || (rc = dPBack.alloc(AA)) ||
         (rc = dProfF.alloc(profBytes)) || (rc = dProfR.alloc(profBytes)) || (rc = dNext.alloc(4)) || (rc = dCells.alloc(4)))
         return rc;
-    SD_CUDA(cudaMemcpyAsync(dAscii.p, qseqs, total, cudaMemcpyHostToDevice, st));
-    SD_CUDA(cudaMemcpyAsync(dLut.p, aa2num(), 256, cudaMemcpyHostToDevice, st));
-    SD_CUDA(cudaMemcpyAsync(dOff.p, hOff.data(), (nq + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     SD_CUDA(cudaMemcpyAsync(dStride.p, hStride.data(), nq * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     SD_CUDA(cudaMemcpyAsync(dLen.p, hLen.data(), nq * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     SD_CUDA(cudaMemcpyAsync(dProfOff.p, hProfOff.data(), (nq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -365,16 +375,14 @@ extern "C" int sd_align_run(sd_context *ctx, const sd_target_index *idx, const c
     SD_CUDA(cudaMemsetAsync(dCells.p, 0, 4 * sizeof(unsigned long long), st));
     SD_CUDA(cudaMemsetAsync(dProfF.p, 0, profBytes, st));
     SD_CUDA(cudaMemsetAsync(dProfR.p, 0, profBytes, st));
-    mapResidues<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dAscii.p, total, dLut.p, dCode.p);
     compositionBias<<<(nPos + 127) / 128, 128, 0, st>>>(dCode.p, dOff.p, nq, nPos, dSub.p, dPBack.p, par->comp_bias_corr, dBias.p);
-    ctx->launches += 2;
+    ctx->launches += 1;
     SD_CUDA(cudaGetLastError());
     if ((rc = launchAlignCompositionBias(ctx, dBias.p, nPos, dCb.p))) return rc;
     if ((rc = launchSwProfiles(ctx, dCode.p, dCb.p, dOff.p, nq, nPos, dMat8.p, dProfOff.p, dStride.p, dProfF.p, dProfR.p))) return rc;
     std::vector<int8_t> hCb(total);
-    std::vector<uint8_t> hCode(total);
+    const std::vector<uint8_t> &hCode = queries->hostCode;
     SD_CUDA(cudaMemcpyAsync(hCb.data(), dCb.p, total, cudaMemcpyDeviceToHost, st));
-    SD_CUDA(cudaMemcpyAsync(hCode.data(), dCode.p, total, cudaMemcpyDeviceToHost, st));
     SD_CUDA(cudaStreamSynchronize(st));
     // 8-bit bias per query (ssw_init :1283-1291): |min matrix entry| + |min composition bias|
     std::vector<int> limit8(nq);

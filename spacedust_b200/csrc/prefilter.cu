@@ -755,16 +755,52 @@ extern "C" int sd_target_index_masked(const sd_target_index *idx, uint8_t *out, 
     return SD_OK;
 }
 
+extern "C" int sd_query_batch_create(sd_context *ctx, const char *seqs, const uint64_t *off, uint32_t n, sd_query_batch **out) {
+    if (!ctx || !seqs || !off || !out) { setError("sd_query_batch_create: bad argument"); return SD_EINVAL; }
+    const uint64_t total = off[n];
+    if (total >= 0xfff00000ull) { setError("query batch too large (%llu residues): split the call", (unsigned long long)total); return SD_ELIMIT; }
+    for (uint32_t i = 0; i < n; i++)
+        if (off[i + 1] - off[i] >= 32768) { setError("query %u longer than 32767 residues: long-sequence path not implemented", i); return SD_ELIMIT; }
+    SD_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<sd_query_batch> b(new sd_query_batch());
+    b->ctx = ctx; b->nq = n; b->total = total;
+    b->hostOff.resize(n + 1);
+    for (uint32_t i = 0; i <= n; i++) b->hostOff[i] = (uint32_t)off[i];
+    b->hostCode.resize(total + 16, (uint8_t)XCODE);
+    mapSequence(seqs, total, b->hostCode.data());
+    int rc;
+    if ((rc = b->code.alloc(total + 16)) || (rc = b->off.alloc(n + 1))) return rc;
+    SD_CUDA(cudaMemcpyAsync(b->code.p, b->hostCode.data(), total + 16, cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(cudaMemcpyAsync(b->off.p, b->hostOff.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = b.release();
+    return SD_OK;
+}
+
+extern "C" void sd_query_batch_destroy(sd_query_batch *b) { delete b; }
+
 extern "C" int sd_prefilter_run(sd_context *ctx, const sd_target_index *idx, const char *qseqs, const uint64_t *qoff,
                                 uint32_t nq, uint32_t query_first, const sd_prefilter_params *par,
                                 sd_prefilter_hit *hits, uint64_t cap, uint64_t *n_hits, sd_prefilter_stats *stats) {
     if (!ctx || !idx || !qseqs || !qoff || !par || !n_hits || (!hits && cap)) { setError("sd_prefilter_run: bad argument"); return SD_EINVAL; }
     *n_hits = 0;
     if (nq == 0) return SD_OK;
-    const uint64_t total = qoff[nq];
-    if (total >= 0xfff00000ull) { setError("query batch too large (%llu residues): split the call", (unsigned long long)total); return SD_ELIMIT; }
-    for (uint32_t i = 0; i < nq; i++)
-        if (qoff[i + 1] - qoff[i] >= 32768) { setError("query %u longer than 32767 residues: long-sequence path not implemented", i); return SD_ELIMIT; }
+    sd_query_batch *b = nullptr;
+    int rc = sd_query_batch_create(ctx, qseqs, qoff, nq, &b);
+    if (rc) return rc;
+    rc = sd_prefilter_run_batch(ctx, idx, b, query_first, par, hits, cap, n_hits, stats);
+    sd_query_batch_destroy(b);
+    return rc;
+}
+
+extern "C" int sd_prefilter_run_batch(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                                      const sd_prefilter_params *par, sd_prefilter_hit *hits, uint64_t cap, uint64_t *n_hits,
+                                      sd_prefilter_stats *stats) {
+    if (!ctx || !idx || !queries || !par || !n_hits || (!hits && cap)) { setError("sd_prefilter_run_batch: bad argument"); return SD_EINVAL; }
+    *n_hits = 0;
+    const uint32_t nq = queries->nq;
+    if (nq == 0) return SD_OK;
+    const uint64_t total = queries->total;
     SD_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int rc;
@@ -774,40 +810,33 @@ extern "C" int sd_prefilter_run(sd_context *ctx, const sd_target_index *idx, con
     SD_CUDA(cudaEventRecord(ev0, st));
 
     const uint32_t nPos = (uint32_t)total;
-    std::vector<uint32_t> hOff(nq + 1);
-    for (uint32_t i = 0; i <= nq; i++) hOff[i] = (uint32_t)qoff[i];
+    const std::vector<uint32_t> &hOff = queries->hostOff;
     std::vector<uint32_t> order(nq);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return hOff[x + 1] - hOff[x] > hOff[y + 1] - hOff[y]; });
 
-    DevBuf<char> dAscii;
-    DevBuf<uint8_t> dLut, dCode;
-    DevBuf<uint32_t> dOff, dOrder;
+    struct { const uint8_t *p; } dCode{queries->code.p};
+    struct { const uint32_t *p; } dOff{queries->off.p};
+    DevBuf<uint32_t> dOrder;
     DevBuf<float> dBias;
     DevBuf<int8_t> dCorr, dDiagSub;
     DevBuf<int16_t> dThr, dSeedSub;
     DevBuf<double> dPBack;
-    if ((rc = dAscii.alloc(total)) || (rc = dLut.alloc(256)) || (rc = dCode.alloc(total + SPAN)) || (rc = dOff.alloc(nq + 1)) ||
-        (rc = dOrder.alloc(nq)) || (rc = dBias.alloc(total + SPAN)) || (rc = dCorr.alloc(total + SPAN)) || (rc = dThr.alloc(total + SPAN)) ||
+    if ((rc = dOrder.alloc(nq)) || (rc = dBias.alloc(total + SPAN)) || (rc = dCorr.alloc(total + SPAN)) || (rc = dThr.alloc(total + SPAN)) ||
         (rc = dSeedSub.alloc(AA * AA)) || (rc = dDiagSub.alloc(AA * AA)) || (rc = dPBack.alloc(AA)))
         return rc;
     int16_t seedSub[AA * AA];
     int8_t diagSub[AA * AA];
     for (int i = 0; i < AA * AA; i++) { seedSub[i] = ctx->seedMat.sub[i]; diagSub[i] = (int8_t)ctx->diagMat.sub[i]; }
-    SD_CUDA(cudaMemcpyAsync(dAscii.p, qseqs, total, cudaMemcpyHostToDevice, st));
-    SD_CUDA(cudaMemcpyAsync(dLut.p, aa2num(), 256, cudaMemcpyHostToDevice, st));
-    SD_CUDA(cudaMemcpyAsync(dOff.p, hOff.data(), (nq + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     SD_CUDA(cudaMemcpyAsync(dOrder.p, order.data(), nq * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     SD_CUDA(cudaMemcpyAsync(dSeedSub.p, seedSub, sizeof seedSub, cudaMemcpyHostToDevice, st));
     SD_CUDA(cudaMemcpyAsync(dDiagSub.p, diagSub, sizeof diagSub, cudaMemcpyHostToDevice, st));
     SD_CUDA(cudaMemcpyAsync(dPBack.p, ctx->seedMat.pBack, AA * sizeof(double), cudaMemcpyHostToDevice, st));
-    SD_CUDA(cudaMemsetAsync(dCode.p + total, XCODE, SPAN, st));
     SD_CUDA(cudaMemsetAsync(dBias.p + total, 0, SPAN * sizeof(float), st));
-    mapResidues<<<gridFor(total, 256), 256, 0, st>>>(dAscii.p, total, dLut.p, dCode.p);
     compositionBias<<<gridFor(nPos, 128), 128, 0, st>>>(dCode.p, dOff.p, nq, nPos, dSeedSub.p, dPBack.p, par->comp_bias_corr, dBias.p);
     profileCorrection<<<gridFor(nPos, 256), 256, 0, st>>>(dBias.p, nPos, dCorr.p);
     kmerThresholds<<<gridFor(nPos, 256), 256, 0, st>>>(dCode.p, dOff.p, nq, nPos, dBias.p, idx->kmerThr, dThr.p);
-    ctx->launches += 4;
+    ctx->launches += 3;
     SD_CUDA(cudaGetLastError());
 
     const uint32_t maxHits = std::min<uint32_t>((uint32_t)std::max(par->max_seqs, 1), idx->nT);

@@ -87,6 +87,16 @@ struct sd_context {
     bool haveExt3 = false;
 };
 
+struct sd_query_batch {
+    sd_context *ctx = nullptr;
+    uint32_t nq = 0;
+    uint64_t total = 0;
+    std::vector<uint32_t> hostOff;     // nq+1
+    std::vector<uint8_t> hostCode;     // residue codes on the host (identity shortcut of align)
+    sd::DevBuf<uint8_t> code;          // residue codes, concatenated (+16 pad)
+    sd::DevBuf<uint32_t> off;          // nq+1
+};
+
 struct sd_target_index {
     sd_context *ctx = nullptr;
     uint32_t nT = 0;
