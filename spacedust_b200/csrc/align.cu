@@ -349,8 +349,8 @@ extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, c
     hProfOff[0] = 0;
     for (uint32_t i = 0; i < nq; i++) {
         hLen[i] = hOff[i + 1] - hOff[i];
-        hStride[i] = ((hLen[i] + 3u) & ~3u) + 4u;
-        hProfOff[i + 1] = hProfOff[i] + (uint64_t)AA * hStride[i];
+        hStride[i] = ((hLen[i] + 3u) & ~3u) + 72u;          // >= 68 bytes of -128 after every row
+        hProfOff[i + 1] = hProfOff[i] + (uint64_t)(AA + 1) * hStride[i];   // + dummy-letter row
     }
     const uint64_t profBytes = hProfOff[nq] + 8192;
     struct { const uint8_t *p; } dCode{queries->code.p};
@@ -373,8 +373,8 @@ extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, c
     SD_CUDA(cudaMemcpyAsync(dSub.p, sub16, sizeof sub16, cudaMemcpyHostToDevice, st));
     SD_CUDA(cudaMemcpyAsync(dPBack.p, alnMat.pBack, AA * sizeof(double), cudaMemcpyHostToDevice, st));
     SD_CUDA(cudaMemsetAsync(dCells.p, 0, 4 * sizeof(unsigned long long), st));
-    SD_CUDA(cudaMemsetAsync(dProfF.p, 0, profBytes, st));
-    SD_CUDA(cudaMemsetAsync(dProfR.p, 0, profBytes, st));
+    SD_CUDA(cudaMemsetAsync(dProfF.p, 0x80, profBytes, st));
+    SD_CUDA(cudaMemsetAsync(dProfR.p, 0x80, profBytes, st));
     compositionBias<<<(nPos + 127) / 128, 128, 0, st>>>(dCode.p, dOff.p, nq, nPos, dSub.p, dPBack.p, par->comp_bias_corr, dBias.p);
     ctx->launches += 1;
     SD_CUDA(cudaGetLastError());
@@ -419,16 +419,29 @@ extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, c
     DevBuf<int> dBoundary;
     if ((rc = dBoundary.alloc((size_t)swWarps * 6 * bndStride))) return rc;
 
-    auto runSw = [&](std::vector<SwTask> &tasks, std::vector<SwResult> &results, unsigned long long *cellSlot) -> int {
+    auto runSw = [&](std::vector<SwTask> &tasks, std::vector<SwResult> &results, unsigned long long *cellSlot, int packed16) -> int {
         results.resize(tasks.size());
         if (tasks.empty()) return SD_OK;
         DevBuf<SwTask> dTasks;
         DevBuf<SwResult> dRes;
+        DevBuf<uint32_t> dOrd;
         int r2;
-        if ((r2 = dTasks.alloc(tasks.size())) || (r2 = dRes.alloc(tasks.size()))) return r2;
+        if ((r2 = dTasks.alloc(tasks.size())) || (r2 = dRes.alloc(tasks.size())) || (r2 = dOrd.alloc(tasks.size()))) return r2;
+        // group tasks by rows-per-stage class, largest class first: warps that share an SM then run the same
+        // template instance (instruction-cache locality) and the long tasks start early
+        std::vector<uint32_t> ord(tasks.size());
+        {
+            uint32_t cnt[18] = {0};
+            auto cls = [](const SwTask &t) { const int rp = (t.nRows + 63) / 64; return (uint32_t)(rp > 16 ? 17 : rp); };
+            for (const SwTask &t : tasks) cnt[17 - cls(t)]++;
+            uint32_t start[18], acc = 0;
+            for (int c = 0; c < 18; c++) { start[c] = acc; acc += cnt[c]; }
+            for (uint32_t i = 0; i < tasks.size(); i++) ord[start[17 - cls(tasks[i])]++] = i;
+        }
+        SD_CUDA(cudaMemcpyAsync(dOrd.p, ord.data(), ord.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         SD_CUDA(cudaMemcpyAsync(dTasks.p, tasks.data(), tasks.size() * sizeof(SwTask), cudaMemcpyHostToDevice, st));
         SD_CUDA(cudaEventRecord(evA, st));
-        if ((r2 = launchSw(ctx, batch, dTasks.p, nullptr, dRes.p, (uint32_t)tasks.size(), dBoundary.p, bndStride, swWarps, dNext.p, cellSlot))) return r2;
+        if ((r2 = launchSw(ctx, batch, dTasks.p, dOrd.p, dRes.p, (uint32_t)tasks.size(), dBoundary.p, bndStride, swWarps, dNext.p, cellSlot, packed16))) return r2;
         SD_CUDA(cudaEventRecord(evB, st));
         SD_CUDA(cudaMemcpyAsync(results.data(), dRes.p, tasks.size() * sizeof(SwResult), cudaMemcpyDeviceToHost, st));
         SD_CUDA(cudaStreamSynchronize(st));
@@ -447,7 +460,7 @@ extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, c
         tk.limit = limit8[ps[k].q]; tk.width = 32; tk.reverse = 0; tk.pad = 0;
         tasks.push_back(tk); taskPair.push_back(k);
     }
-    if ((rc = runSw(tasks, results, dCells.p))) return rc;
+    if ((rc = runSw(tasks, results, dCells.p, 1))) return rc;
     // ---- forward pass again in 16-bit semantics where the 8-bit pass saturated
     std::vector<SwTask> wtasks;
     std::vector<uint32_t> wPair;
@@ -461,7 +474,16 @@ extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, c
         } else { s.score = results[i].score; s.tEnd = results[i].col; s.qEnd = results[i].row; }
     }
     std::vector<SwResult> wres;
-    if ((rc = runSw(wtasks, wres, dCells.p))) return rc;
+    if ((rc = runSw(wtasks, wres, dCells.p, 1))) return rc;
+    {   // scores close to 2^15 leave the packed 16-bit lanes: redo those pairs with the 32-bit pass
+        std::vector<SwTask> big;
+        std::vector<size_t> bigIdx;
+        for (size_t i = 0; i < wtasks.size(); i++)
+            if (wres[i].overflow) { big.push_back(wtasks[i]); bigIdx.push_back(i); }
+        std::vector<SwResult> bres;
+        if ((rc = runSw(big, bres, dCells.p, 0))) return rc;
+        for (size_t i = 0; i < big.size(); i++) wres[bigIdx[i]] = bres[i];
+    }
     for (size_t i = 0; i < wtasks.size(); i++) {
         PairState &s = ps[wPair[i]];
         s.score = wres[i].score; s.tEnd = wres[i].col; s.qEnd = wres[i].row;
@@ -504,7 +526,16 @@ extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, c
         rtasks.push_back(tk); rPair.push_back(k);
     }
     std::vector<SwResult> rres;
-    if ((rc = runSw(rtasks, rres, dCells.p + 1))) return rc;
+    if ((rc = runSw(rtasks, rres, dCells.p + 1, 1))) return rc;
+    {
+        std::vector<SwTask> big;
+        std::vector<size_t> bigIdx;
+        for (size_t i = 0; i < rtasks.size(); i++)
+            if (rres[i].overflow == 2) { big.push_back(rtasks[i]); bigIdx.push_back(i); }
+        std::vector<SwResult> bres;
+        if ((rc = runSw(big, bres, dCells.p + 1, 0))) return rc;
+        for (size_t i = 0; i < big.size(); i++) rres[bigIdx[i]] = bres[i];
+    }
     uint64_t scoreMismatch = 0;
     for (size_t i = 0; i < rtasks.size(); i++) {
         PairState &s = ps[rPair[i]];

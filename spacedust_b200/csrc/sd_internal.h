@@ -64,7 +64,7 @@ struct SwTask;
 struct SwResult;
 int launchSw(sd_context *ctx, const SwBatch &batch, const SwTask *dTasks, const uint32_t *dOrder, SwResult *dResults,
              uint32_t nTasks, int *dBoundary, uint32_t boundaryStride, uint32_t nWarpsAllocated, uint32_t *dNext,
-             unsigned long long *dCells);
+             unsigned long long *dCells, int packed16);
 int launchSwProfiles(sd_context *ctx, const uint8_t *code, const int8_t *cb, const uint32_t *qOff, uint32_t nQ,
                      uint32_t totalRes, const int8_t *mat, const uint64_t *profOff, const uint32_t *profStride,
                      int8_t *fwd, int8_t *rev);
