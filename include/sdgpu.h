@@ -225,6 +225,21 @@ int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_t n_alns,
                    const sd_cluster_params *par, sd_cluster *clusters, uint64_t cap, uint64_t *n_clusters,
                    sd_cluster_member *members, uint64_t mcap, uint64_t *n_members, sd_cluster_stats *stats);
 
+/* ---- fused hot path: prefilter -> align -> besthitbyset/combinehits -> clusterhits (data/clustersearch.sh:112-146) ----
+ * Same results as calling the three stages one after the other, but the prefilter hit list stays in HBM.  The result
+ * object owns host copies of the accepted alignments (+ backtraces) and the clusters. */
+typedef struct sd_search_result sd_search_result;
+int sd_clustersearch_run(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                         const sd_prefilter_params *ppar, const sd_align_params *apar, const sd_cluster_params *cpar,
+                         const uint32_t *q_set_of, const uint32_t *q_pos, const uint8_t *q_strand,
+                         const uint32_t *t_set_of, const uint32_t *t_pos, const uint8_t *t_strand, uint32_t nt,
+                         const uint32_t *q_set_size, uint32_t n_q_sets, const uint32_t *t_set_size, uint32_t n_t_sets,
+                         uint64_t db_residues, sd_search_result **out, sd_prefilter_stats *pst, sd_align_stats *ast,
+                         sd_cluster_stats *cst);
+void sd_search_result_sizes(const sd_search_result *r, uint64_t *n_alns, uint64_t *pool_bytes, uint64_t *n_clusters, uint64_t *n_members);
+int sd_search_result_copy(const sd_search_result *r, sd_alignment *alns, char *pool, sd_cluster *clusters, sd_cluster_member *members);
+void sd_search_result_destroy(sd_search_result *r);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,8 @@ def lib():
         L.sd_last_error.restype = ctypes.c_char_p
         L.sd_context_launches.restype = ctypes.c_uint64
         L.sd_target_index_entries.restype = ctypes.c_uint64
+        L.sd_search_result_sizes.restype = None
+        L.sd_search_result_destroy.restype = None
         _lib = L
     return _lib
 
@@ -334,9 +336,8 @@ def align_batch(ctx, index, batch, pair_q, pair_t, params, query_first=0, db_res
     raise SdError("sd_align_run_batch: output buffers too small twice")
 
 
-def clustersearch(ctx, index, batch, q_meta, t_meta, pref_params=None, aln_params=None, clu_params=None, query_first=0):
-    """The hot path of `spacedust clustersearch` after createsetdb for one query batch:
-    prefilter -> align -> besthitbyset/combinehits -> clusterhits.  -> dict of stage outputs and stats."""
+def clustersearch_staged(ctx, index, batch, q_meta, t_meta, pref_params=None, aln_params=None, clu_params=None, query_first=0):
+    """The hot path stage by stage through the three C-ABI calls (hit lists travel through the host)."""
     pp = pref_params or default_prefilter_params(same_db=1)
     ap = aln_params or default_align_params(same_db=pp.same_db)
     cp = clu_params or default_cluster_params(filter_self_match=1)
@@ -345,3 +346,41 @@ def clustersearch(ctx, index, batch, q_meta, t_meta, pref_params=None, aln_param
     clusters, members, cst = cluster(ctx, alns, q_meta, t_meta, cp)
     return {"hits": hits, "alns": alns, "pool": pool, "clusters": clusters, "members": members,
             "prefilter_stats": pst, "align_stats": ast, "cluster_stats": cst}
+
+
+def clustersearch(ctx, index, batch, q_meta, t_meta, pref_params=None, aln_params=None, clu_params=None, query_first=0,
+                  db_residues=0):
+    """The hot path of `spacedust clustersearch` after createsetdb for one query batch, fused (sd_clustersearch_run):
+    prefilter -> align -> besthitbyset/combinehits -> clusterhits with the prefilter hit list kept in HBM."""
+    pp = pref_params or default_prefilter_params(same_db=1)
+    ap = aln_params or default_align_params(same_db=pp.same_db)
+    cp = clu_params or default_cluster_params(filter_self_match=1)
+
+    def arr(x, dt):
+        return np.ascontiguousarray(x, dtype=dt)
+    qs, qp, qst, qsz = arr(q_meta["set_of"], np.uint32), arr(q_meta["pos"], np.uint32), arr(q_meta["strand"], np.uint8), arr(q_meta["set_size"], np.uint32)
+    ts, tp, tst, tsz = arr(t_meta["set_of"], np.uint32), arr(t_meta["pos"], np.uint32), arr(t_meta["strand"], np.uint8), arr(t_meta["set_size"], np.uint32)
+    assert len(qs) == batch.n and len(ts) == index.n
+    res = ctypes.c_void_p()
+    pst, ast, cst = PrefilterStats(), AlignStats(), ClusterStats()
+    p = ctypes.c_void_p
+    L = lib()
+    _check(L.sd_clustersearch_run(ctx._h, index._h, batch._h, ctypes.c_uint32(query_first), ctypes.byref(pp), ctypes.byref(ap),
+                                  ctypes.byref(cp), qs.ctypes.data_as(p), qp.ctypes.data_as(p), qst.ctypes.data_as(p),
+                                  ts.ctypes.data_as(p), tp.ctypes.data_as(p), tst.ctypes.data_as(p), ctypes.c_uint32(len(ts)),
+                                  qsz.ctypes.data_as(p), ctypes.c_uint32(len(qsz)), tsz.ctypes.data_as(p), ctypes.c_uint32(len(tsz)),
+                                  ctypes.c_uint64(db_residues), ctypes.byref(res), ctypes.byref(pst), ctypes.byref(ast), ctypes.byref(cst)))
+    try:
+        na, nb, nc, nm = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        L.sd_search_result_sizes(res, ctypes.byref(na), ctypes.byref(nb), ctypes.byref(nc), ctypes.byref(nm))
+        alns = np.zeros(max(1, na.value), dtype=ALN_DTYPE)
+        pool = np.zeros(max(1, nb.value), dtype=np.uint8)
+        clusters = np.zeros(max(1, nc.value), dtype=CLUSTER_DTYPE)
+        members = np.zeros(max(1, nm.value), dtype=MEMBER_DTYPE)
+        _check(L.sd_search_result_copy(res, alns.ctypes.data_as(p), pool.ctypes.data_as(ctypes.c_char_p), clusters.ctypes.data_as(p),
+                                       members.ctypes.data_as(p)))
+    finally:
+        L.sd_search_result_destroy(res)
+    pst_d = pst.as_dict()
+    return {"alns": alns[:na.value], "pool": pool[:nb.value], "clusters": clusters[:nc.value], "members": members[:nm.value],
+            "n_prefilter_hits": None, "prefilter_stats": pst_d, "align_stats": ast.as_dict(), "cluster_stats": cst.as_dict()}

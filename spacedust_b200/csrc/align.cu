@@ -272,19 +272,6 @@ extern "C" void sd_align_params_default(sd_align_params *p) {
     p->same_db = 0;
 }
 
-namespace {
-struct PairState {
-    uint32_t q, t;
-    int score = 0, qEnd = -1, tEnd = -1, qStart = -1, tStart = -1;
-    int word = 0;
-    double evalue = 0;
-    float qcov = 0, tcov = 0;
-    int stage = 0;      // 0 dropped, 1 needs reverse, 2 needs traceback, 3 accepted
-    int btLen = 0, ids = 0;
-    uint64_t btOff = 0;
-    bool identity = false;
-};
-}  // namespace
 
 extern "C" int sd_align_run(sd_context *ctx, const sd_target_index *idx, const char *qseqs, const uint64_t *qoff, uint32_t nq,
                             uint32_t query_first, const uint32_t *pair_q, const uint32_t *pair_t, uint64_t n_pairs,
@@ -302,22 +289,177 @@ extern "C" int sd_align_run(sd_context *ctx, const sd_target_index *idx, const c
     return rc;
 }
 
-extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
-                                  const uint32_t *pair_q, const uint32_t *pair_t, uint64_t n_pairs, uint64_t db_residues,
-                                  const sd_align_params *par, sd_alignment *out, uint64_t cap, uint64_t *n_out, char *bt_pool,
-                                  uint64_t bt_cap, uint64_t *bt_used, sd_align_stats *stats) {
-    if (!ctx || !idx || !queries || !par || !n_out || !bt_used || (n_pairs && (!pair_q || !pair_t))) { setError("sd_align_run_batch: bad argument"); return SD_EINVAL; }
-    *n_out = 0; *bt_used = 0;
+// ================================================================================================
+// device-side filter chain of align: forward 8-bit -> (overflow) forward 16-bit -> E-value score threshold +
+// end-point coverage -> reverse pass -> start coverage -> traceback.  Only survivors come back to the host.
+// ================================================================================================
+namespace {
+
+struct PairHit {            // one record per pair that reaches the reverse pass
+    uint32_t q, t;
+    int32_t score, qEnd, tEnd, qStart, tStart;
+    int32_t word;           // 16-bit semantics were needed
+    int32_t stage;          // 1 waits for reverse, 2 waits for traceback, 0 dropped
+    uint32_t tb;            // index of its traceback task
+};
+
+struct ChainArgs {
+    const uint32_t *pairQ, *pairT;
+    uint64_t nPairs;
+    const uint32_t *qLen;         // per query
+    const uint32_t *tOff;         // per target
+    const int32_t *limit8;        // per query: 255 - bias
+    const int32_t *minScore;      // per query: smallest score with E-value <= threshold
+    uint32_t queryFirst;
+    int sameDb;
+    float covThr;
+    int covMode;
+    // lists
+    SwTask *fwdTasks; uint32_t *nFwd;
+    SwTask *wordTasks; uint32_t *nWord;
+    SwTask *bigTasks; uint32_t *nBig;
+    SwTask *revTasks; uint32_t *nRev;
+    PairHit *hits; uint32_t *nHits;
+    uint32_t *identity; uint32_t *nIdentity;     // queries whose identity pair takes the scoreIdentical shortcut
+    TbTask *tbTasks; uint32_t *nTb;
+    unsigned long long *poolCursor;
+    uint32_t *classCount;                        // 18 counters per list, used by orderByClass
+    unsigned long long *counters;                // [0] aligned pairs, [1] score mismatches
+};
+
+__device__ __forceinline__ float devCov(unsigned start, unsigned end, unsigned len) {
+    return __fdiv_rn((float)(min(len, max(start, end)) - min(start, end) + 1), (float)len);
+}
+__device__ __forceinline__ bool devHasCoverage(float thr, int mode, float q, float t) {
+    switch (mode) {
+        case 0: return (q >= thr) && (t >= thr);
+        case 2: return q >= thr;
+        case 1: return t >= thr;
+        default: return true;
+    }
+}
+__device__ __forceinline__ bool devCanBeCovered(float thr, int mode, float q, float t) {
+    switch (mode) {
+        case 0: return (__fdiv_rn(q, t) >= thr) && (__fdiv_rn(t, q) >= thr);
+        case 1: return __fdiv_rn(q, t) >= thr;
+        case 2: return __fdiv_rn(t, q) >= thr;
+        case 3: return (__fdiv_rn(t, q) >= thr) && ((double)__fdiv_rn(t, q) <= 1.0);
+        case 4: return (__fdiv_rn(q, t) >= thr) && ((double)__fdiv_rn(q, t) <= 1.0);
+        case 5: return __fdiv_rn(fminf(t, q), fmaxf(t, q)) >= thr;
+        default: return true;
+    }
+}
+__device__ __forceinline__ uint32_t swClass(int nRows) { const int rp = (nRows + 63) / 64; return (uint32_t)(rp > 16 ? 17 : rp); }
+
+// Alignment.cpp:370 length pre-filter, identity shortcut, forward task per remaining pair
+__global__ void chainBuildForward(ChainArgs A) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.nPairs) return;
+    const uint32_t q = A.pairQ[k], t = A.pairT[k];
+    const int Lq = (int)A.qLen[q], Lt = (int)(A.tOff[t + 1] - A.tOff[t]);
+    if (!devCanBeCovered(A.covThr, A.covMode, (float)Lq, (float)Lt)) return;
+    atomicAdd(&A.counters[0], 1ull);
+    if (A.sameDb && A.queryFirst + q == t) { A.identity[atomicAdd(A.nIdentity, 1u)] = q; return; }
+    SwTask tk;
+    tk.q = q; tk.t = t; tk.nRows = Lq; tk.nCols = Lt; tk.limit = A.limit8[q]; tk.width = 32; tk.reverse = 0; tk.pad = 0;
+    A.fwdTasks[atomicAdd(A.nFwd, 1u)] = tk;
+    atomicAdd(&A.classCount[17 - swClass(Lq)], 1u);
+}
+
+// largest class first; order inside a class is arbitrary (results are keyed by task)
+__global__ void chainOrderByClass(const SwTask *tasks, uint32_t n, uint32_t *classCursor /*18, pre-scanned*/, uint32_t *order) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    order[atomicAdd(&classCursor[17 - swClass(tasks[i].nRows)], 1u)] = i;
+}
+
+__global__ void chainCountClasses(const SwTask *tasks, uint32_t n, uint32_t *classCount) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    atomicAdd(&classCount[17 - swClass(tasks[i].nRows)], 1u);
+}
+
+__global__ void chainScanClasses(uint32_t *classCount /*18*/) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int c = 0; c < 18; c++) { const uint32_t v = classCount[c]; classCount[c] = acc; acc += v; }
+    }
+}
+
+// ssw_align_private :383-398 after a forward pass: overflow -> next width; E-value / end-point coverage early outs
+__global__ void chainAfterForward(ChainArgs A, const SwTask *tasks, const SwResult *res, uint32_t n, int wordPass) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SwTask tk = tasks[i];
+    const SwResult r = res[i];
+    if (r.overflow) {
+        SwTask nt = tk;
+        nt.limit = INT_MAX; nt.width = 16;
+        if (!wordPass && r.overflow == 1) A.wordTasks[atomicAdd(A.nWord, 1u)] = nt;
+        else A.bigTasks[atomicAdd(A.nBig, 1u)] = nt;          // 16-bit lanes exhausted: 32-bit pass
+        return;
+    }
+    if (r.col < 0) return;                                     // no residue could be aligned
+    const int Lq = tk.nRows, Lt = tk.nCols;
+    if (r.score < A.minScore[tk.q]) return;                    // evalue > evalThr
+    const float qcov = devCov(0u, (unsigned)r.row, (unsigned)Lq), tcov = devCov(0u, (unsigned)r.col, (unsigned)Lt);
+    if (!devHasCoverage(A.covThr, A.covMode, qcov, tcov)) return;
+    const uint32_t h = atomicAdd(A.nHits, 1u);
+    PairHit ph;
+    ph.q = tk.q; ph.t = tk.t; ph.score = r.score; ph.qEnd = r.row; ph.tEnd = r.col; ph.qStart = -1; ph.tStart = -1;
+    ph.word = tk.width == 16; ph.stage = 1; ph.tb = 0;
+    A.hits[h] = ph;
+    SwTask rt;
+    rt.q = tk.q; rt.t = tk.t; rt.nRows = r.row + 1; rt.nCols = r.col + 1;
+    rt.limit = ph.word ? INT_MAX : A.limit8[tk.q]; rt.width = ph.word ? 16 : 32; rt.reverse = 1; rt.pad = (int32_t)h;
+    A.revTasks[atomicAdd(A.nRev, 1u)] = rt;
+}
+
+// ssw_align_private :456-480 after the reverse pass: start coordinates, coverage, traceback task
+__global__ void chainAfterReverse(ChainArgs A, const SwTask *tasks, const SwResult *res, uint32_t n, int bigPass) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const SwTask tk = tasks[i];
+    const SwResult r = res[i];
+    PairHit &ph = A.hits[tk.pad];
+    if (r.overflow == 2 && !bigPass) { A.bigTasks[atomicAdd(A.nBig, 1u)] = tk; return; }
+    if (r.overflow || r.score != ph.score) { atomicAdd(&A.counters[1], 1ull); ph.stage = 0; return; }
+    const int Lq = (int)A.qLen[ph.q], Lt = (int)(A.tOff[ph.t + 1] - A.tOff[ph.t]);
+    ph.tStart = ph.tEnd - r.col;
+    ph.qStart = ph.qEnd - r.row;
+    const float qcov = devCov((unsigned)ph.qStart, (unsigned)ph.qEnd, (unsigned)Lq), tcov = devCov((unsigned)ph.tStart, (unsigned)ph.tEnd, (unsigned)Lt);
+    if (!devHasCoverage(A.covThr, A.covMode, qcov, tcov)) { ph.stage = 0; return; }
+    ph.stage = 2;
+    TbTask tb;
+    tb.q = ph.q; tb.t = ph.t; tb.qStart = ph.qStart; tb.qEnd = ph.qEnd; tb.tStart = ph.tStart; tb.tEnd = ph.tEnd; tb.score = ph.score; tb.pad = (uint32_t)tk.pad;
+    tb.btOff = atomicAdd(A.poolCursor, (unsigned long long)((ph.qEnd - ph.qStart + 1) + (ph.tEnd - ph.tStart + 1) + 2));
+    const uint32_t ti = atomicAdd(A.nTb, 1u);
+    ph.tb = ti;
+    A.tbTasks[ti] = tb;
+}
+
+__global__ void splitPrefilterHits(const sd_prefilter_hit *hits, uint64_t n, uint32_t *q, uint32_t *t) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { q[i] = hits[i].query; t[i] = hits[i].target; }
+}
+
+inline unsigned gridOf(uint64_t n, unsigned b) { return (unsigned)std::max<uint64_t>(1, (n + b - 1) / b); }
+
+}  // namespace
+
+// Device pair arrays in, accepted alignments out.  dPairQ/dPairT live on the device (grouped or not: the order of
+// the output is defined by (query, Matcher::compareHits)).
+int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                          const uint32_t *dPairQ, const uint32_t *dPairT, uint64_t n_pairs, uint64_t db_residues,
+                          const sd_align_params *par, std::vector<sd_alignment> &acc, std::vector<char> &pool,
+                          sd_align_stats *stats) {
+    acc.clear(); pool.clear();
     if (stats) memset(stats, 0, sizeof *stats);
     const uint32_t nq = queries->nq;
     if (nq == 0 || n_pairs == 0) return SD_OK;
     if (par->gap_open < par->gap_extend) { setError("sd_align_run: gap open < gap extend is not supported"); return SD_ELIMIT; }
     if (n_pairs >= 0xffffffffull) { setError("sd_align_run: too many pairs in one call (%llu)", (unsigned long long)n_pairs); return SD_ELIMIT; }
     const uint64_t total = queries->total;
-    for (uint64_t k = 0; k < n_pairs; k++) {
-        if (pair_q[k] >= nq || pair_t[k] >= idx->nT) { setError("sd_align_run: pair %llu out of range", (unsigned long long)k); return SD_EINVAL; }
-        if (k && pair_q[k] < pair_q[k - 1]) { setError("sd_align_run: pairs must be grouped by ascending query"); return SD_EINVAL; }
-    }
     SD_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int rc;
@@ -325,11 +467,11 @@ extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, c
     SD_CUDA(cudaEventCreate(&ev0)); SD_CUDA(cudaEventCreate(&ev1)); SD_CUDA(cudaEventCreate(&evA)); SD_CUDA(cudaEventCreate(&evB));
     SD_CUDA(cudaEventRecord(ev0, st));
     double swMs = 0, tbMs = 0;
-    auto lap = [&](double &acc) -> int {
+    auto lap = [&](double &accMs) -> int {
         float ms = 0;
         SD_CUDA(cudaEventSynchronize(evB));
         cudaEventElapsedTime(&ms, evA, evB);
-        acc += ms;
+        accMs += ms;
         return SD_OK;
     };
 
@@ -341,20 +483,20 @@ extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, c
     int minMat = 0;
     for (int i = 0; i < AA * AA; i++) { sub16[i] = alnMat.sub[i]; mat8[i] = (int8_t)alnMat.sub[i]; minMat = std::min(minMat, (int)mat8[i]); }
 
-    // ---- query side on the device
+    // ---- query side on the device: composition bias, profiles
     const uint32_t nPos = (uint32_t)total;
     const std::vector<uint32_t> &hOff = queries->hostOff;
     std::vector<uint32_t> hStride(nq), hLen(nq);
     std::vector<uint64_t> hProfOff(nq + 1);
     hProfOff[0] = 0;
+    uint32_t maxQ = 1;
     for (uint32_t i = 0; i < nq; i++) {
         hLen[i] = hOff[i + 1] - hOff[i];
+        maxQ = std::max(maxQ, hLen[i]);
         hStride[i] = ((hLen[i] + 3u) & ~3u) + 72u;          // >= 68 bytes of -128 after every row
         hProfOff[i + 1] = hProfOff[i] + (uint64_t)(AA + 1) * hStride[i];   // + dummy-letter row
     }
     const uint64_t profBytes = hProfOff[nq] + 8192;
-    struct { const uint8_t *p; } dCode{queries->code.p};
-    struct { const uint32_t *p; } dOff{queries->off.p};
     DevBuf<uint32_t> dStride, dLen, dNext;
     DevBuf<uint64_t> dProfOff;
     DevBuf<float> dBias;
@@ -375,227 +517,171 @@ extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, c
     SD_CUDA(cudaMemsetAsync(dCells.p, 0, 4 * sizeof(unsigned long long), st));
     SD_CUDA(cudaMemsetAsync(dProfF.p, 0x80, profBytes, st));
     SD_CUDA(cudaMemsetAsync(dProfR.p, 0x80, profBytes, st));
-    compositionBias<<<(nPos + 127) / 128, 128, 0, st>>>(dCode.p, dOff.p, nq, nPos, dSub.p, dPBack.p, par->comp_bias_corr, dBias.p);
+    compositionBias<<<(nPos + 127) / 128, 128, 0, st>>>(queries->code.p, queries->off.p, nq, nPos, dSub.p, dPBack.p, par->comp_bias_corr, dBias.p);
     ctx->launches += 1;
     SD_CUDA(cudaGetLastError());
     if ((rc = launchAlignCompositionBias(ctx, dBias.p, nPos, dCb.p))) return rc;
-    if ((rc = launchSwProfiles(ctx, dCode.p, dCb.p, dOff.p, nq, nPos, dMat8.p, dProfOff.p, dStride.p, dProfF.p, dProfR.p))) return rc;
+    if ((rc = launchSwProfiles(ctx, queries->code.p, dCb.p, queries->off.p, nq, nPos, dMat8.p, dProfOff.p, dStride.p, dProfF.p, dProfR.p))) return rc;
     std::vector<int8_t> hCb(total);
     const std::vector<uint8_t> &hCode = queries->hostCode;
     SD_CUDA(cudaMemcpyAsync(hCb.data(), dCb.p, total, cudaMemcpyDeviceToHost, st));
     SD_CUDA(cudaStreamSynchronize(st));
-    // 8-bit bias per query (ssw_init :1283-1291): |min matrix entry| + |min composition bias|
-    std::vector<int> limit8(nq);
-    for (uint32_t q = 0; q < nq; q++) {
-        int mn = 0;
-        for (uint32_t i = hOff[q]; i < hOff[q + 1]; i++) mn = std::min(mn, (int)hCb[i]);
-        limit8[q] = 255 - (std::abs(minMat) + std::abs(mn));
-    }
 
-    // ---- pair states, length pre-filter (Alignment.cpp:370), identity shortcut
+    // per query: 8-bit limit (ssw_init :1283-1291) and the smallest raw score whose E-value passes -e
     const std::vector<uint32_t> &tOff = idx->hostOff;
     const Evaluer evaluer((double)(db_residues ? db_residues : idx->totalRes));
-    std::vector<PairState> ps;
-    ps.reserve(n_pairs);
-    uint64_t nAligned = 0;
-    for (uint64_t k = 0; k < n_pairs; k++) {
-        const uint32_t q = pair_q[k], t = pair_t[k];
-        const float ql = (float)hLen[q], tl = (float)(tOff[t + 1] - tOff[t]);
-        if (!canBeCovered(par->cov_thr, par->cov_mode, ql, tl)) continue;
-        PairState s;
-        s.q = q; s.t = t;
-        s.identity = par->same_db && (query_first + q == t);
-        ps.push_back(s);
-        nAligned++;
+    std::vector<int32_t> limit8(nq), minScore(nq);
+    {
+        std::vector<int32_t> byLen(maxQ + 1, -1);
+        for (uint32_t q = 0; q < nq; q++) byLen[hLen[q]] = 0;
+        parallelFor(maxQ + 1, [&](uint64_t L) {
+            if (byLen[L] < 0 || L == 0) return;
+            // E(s) falls monotonically in s (checked below); the first s with E <= thr is the pass mark
+            int s = 1;
+            while (s < 100000 && evaluer.evalue((double)s, (double)L) > par->evalue_thr) s++;
+            bool mono = true;
+            double prev = evaluer.evalue((double)s, (double)L);
+            for (int k = 1; k <= 64; k++) {
+                const double e = evaluer.evalue((double)(s + k), (double)L);
+                if (e > prev || e > par->evalue_thr) mono = false;
+                prev = e;
+            }
+            byLen[L] = mono ? s : -2;
+        });
+        for (uint32_t q = 0; q < nq; q++) {
+            int mn = 0;
+            for (uint32_t i = hOff[q]; i < hOff[q + 1]; i++) mn = std::min(mn, (int)hCb[i]);
+            limit8[q] = 255 - (std::abs(minMat) + std::abs(mn));
+            minScore[q] = hLen[q] ? byLen[hLen[q]] : 1;
+            if (minScore[q] == -2) { setError("sd_align_run: E-value is not monotone in the score for query length %u", hLen[q]); return SD_ELIMIT; }
+        }
     }
-    const uint32_t nP = (uint32_t)ps.size();
+
+    // ---- device lists
+    const uint32_t nP = (uint32_t)n_pairs;
+    DevBuf<SwTask> dFwd, dWord, dBig, dRev;
+    DevBuf<SwResult> dRes;
+    DevBuf<PairHit> dHits;
+    DevBuf<TbTask> dTb;
+    DevBuf<TbResult> dTbRes;
+    DevBuf<uint32_t> dIdent, dOrder, dCnt, dClass;
+    DevBuf<int32_t> dLimit8, dMinScore;
+    DevBuf<unsigned long long> dCounters;
+    if ((rc = dFwd.alloc(nP)) || (rc = dWord.alloc(nP)) || (rc = dBig.alloc(nP)) || (rc = dRev.alloc(nP)) || (rc = dRes.alloc(nP)) ||
+        (rc = dHits.alloc(nP)) || (rc = dTb.alloc(nP)) || (rc = dIdent.alloc(nP)) || (rc = dOrder.alloc(nP)) ||
+        (rc = dCnt.alloc(16)) || (rc = dClass.alloc(18)) || (rc = dLimit8.alloc(nq)) || (rc = dMinScore.alloc(nq)) || (rc = dCounters.alloc(4)))
+        return rc;
+    SD_CUDA(cudaMemcpyAsync(dLimit8.p, limit8.data(), nq * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    SD_CUDA(cudaMemcpyAsync(dMinScore.p, minScore.data(), nq * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    SD_CUDA(cudaMemsetAsync(dCnt.p, 0, 16 * sizeof(uint32_t), st));
+    SD_CUDA(cudaMemsetAsync(dClass.p, 0, 18 * sizeof(uint32_t), st));
+    SD_CUDA(cudaMemsetAsync(dCounters.p, 0, 4 * sizeof(unsigned long long), st));
+    enum { C_FWD = 0, C_WORD, C_BIG, C_REV, C_HITS, C_IDENT, C_TB };
+    ChainArgs C;
+    C.pairQ = dPairQ; C.pairT = dPairT; C.nPairs = n_pairs; C.qLen = dLen.p; C.tOff = idx->off.p; C.limit8 = dLimit8.p; C.minScore = dMinScore.p;
+    C.queryFirst = query_first; C.sameDb = par->same_db; C.covThr = par->cov_thr; C.covMode = par->cov_mode;
+    C.fwdTasks = dFwd.p; C.nFwd = dCnt.p + C_FWD; C.wordTasks = dWord.p; C.nWord = dCnt.p + C_WORD; C.bigTasks = dBig.p; C.nBig = dCnt.p + C_BIG;
+    C.revTasks = dRev.p; C.nRev = dCnt.p + C_REV; C.hits = dHits.p; C.nHits = dCnt.p + C_HITS; C.identity = dIdent.p; C.nIdentity = dCnt.p + C_IDENT;
+    C.tbTasks = dTb.p; C.nTb = dCnt.p + C_TB; C.poolCursor = dCounters.p + 2; C.classCount = dClass.p; C.counters = dCounters.p;
 
     SwBatch batch;
     batch.profFwd = dProfF.p; batch.profRev = dProfR.p; batch.profOff = dProfOff.p; batch.profStride = dStride.p; batch.qLen = dLen.p;
     batch.tRes = idx->raw.p; batch.tOff = idx->off.p; batch.gapOpen = par->gap_open; batch.gapExtend = par->gap_extend;
-
     const uint32_t swWarps = (uint32_t)ctx->smCount * 4u * swWarpsPerCta();
     const uint32_t bndStride = std::max<uint32_t>(idx->maxLen, 32u) + 32u;
     DevBuf<int> dBoundary;
     if ((rc = dBoundary.alloc((size_t)swWarps * 6 * bndStride))) return rc;
 
-    auto runSw = [&](std::vector<SwTask> &tasks, std::vector<SwResult> &results, unsigned long long *cellSlot, int packed16) -> int {
-        results.resize(tasks.size());
-        if (tasks.empty()) return SD_OK;
-        DevBuf<SwTask> dTasks;
-        DevBuf<SwResult> dRes;
-        DevBuf<uint32_t> dOrd;
-        int r2;
-        if ((r2 = dTasks.alloc(tasks.size())) || (r2 = dRes.alloc(tasks.size())) || (r2 = dOrd.alloc(tasks.size()))) return r2;
-        // group tasks by rows-per-stage class, largest class first: warps that share an SM then run the same
-        // template instance (instruction-cache locality) and the long tasks start early
-        std::vector<uint32_t> ord(tasks.size());
-        {
-            uint32_t cnt[18] = {0};
-            auto cls = [](const SwTask &t) { const int rp = (t.nRows + 63) / 64; return (uint32_t)(rp > 16 ? 17 : rp); };
-            for (const SwTask &t : tasks) cnt[17 - cls(t)]++;
-            uint32_t start[18], acc = 0;
-            for (int c = 0; c < 18; c++) { start[c] = acc; acc += cnt[c]; }
-            for (uint32_t i = 0; i < tasks.size(); i++) ord[start[17 - cls(tasks[i])]++] = i;
-        }
-        SD_CUDA(cudaMemcpyAsync(dOrd.p, ord.data(), ord.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        SD_CUDA(cudaMemcpyAsync(dTasks.p, tasks.data(), tasks.size() * sizeof(SwTask), cudaMemcpyHostToDevice, st));
-        SD_CUDA(cudaEventRecord(evA, st));
-        if ((r2 = launchSw(ctx, batch, dTasks.p, dOrd.p, dRes.p, (uint32_t)tasks.size(), dBoundary.p, bndStride, swWarps, dNext.p, cellSlot, packed16))) return r2;
-        SD_CUDA(cudaEventRecord(evB, st));
-        SD_CUDA(cudaMemcpyAsync(results.data(), dRes.p, tasks.size() * sizeof(SwResult), cudaMemcpyDeviceToHost, st));
+    uint32_t hCnt[16];
+    auto readCounts = [&]() -> int {
+        SD_CUDA(cudaMemcpyAsync(hCnt, dCnt.p, sizeof hCnt, cudaMemcpyDeviceToHost, st));
         SD_CUDA(cudaStreamSynchronize(st));
+        return SD_OK;
+    };
+    // one Smith-Waterman launch over a device task list, grouped by template class
+    auto runList = [&](SwTask *tasks, uint32_t n, bool classesCounted, int packed16, unsigned long long *cellSlot) -> int {
+        if (n == 0) return SD_OK;
+        if (!classesCounted) {
+            SD_CUDA(cudaMemsetAsync(dClass.p, 0, 18 * sizeof(uint32_t), st));
+            chainCountClasses<<<gridOf(n, 256), 256, 0, st>>>(tasks, n, dClass.p);
+            ctx->launches++;
+        }
+        chainScanClasses<<<1, 32, 0, st>>>(dClass.p);
+        chainOrderByClass<<<gridOf(n, 256), 256, 0, st>>>(tasks, n, dClass.p, dOrder.p);
+        ctx->launches += 2;
+        SD_CUDA(cudaGetLastError());
+        SD_CUDA(cudaEventRecord(evA, st));
+        int r2 = launchSw(ctx, batch, tasks, dOrder.p, dRes.p, n, dBoundary.p, bndStride, swWarps, dNext.p, cellSlot, packed16);
+        if (r2) return r2;
+        SD_CUDA(cudaEventRecord(evB, st));
         return lap(swMs);
     };
 
-    // ---- forward pass, 8-bit semantics
-    std::vector<uint32_t> taskPair;
-    std::vector<SwTask> tasks;
-    std::vector<SwResult> results;
-    tasks.reserve(nP); taskPair.reserve(nP);
-    for (uint32_t k = 0; k < nP; k++) {
-        if (ps[k].identity) continue;
-        SwTask tk;
-        tk.q = ps[k].q; tk.t = ps[k].t; tk.nRows = (int)hLen[ps[k].q]; tk.nCols = (int)(tOff[ps[k].t + 1] - tOff[ps[k].t]);
-        tk.limit = limit8[ps[k].q]; tk.width = 32; tk.reverse = 0; tk.pad = 0;
-        tasks.push_back(tk); taskPair.push_back(k);
+    chainBuildForward<<<gridOf(n_pairs, 256), 256, 0, st>>>(C);
+    ctx->launches++;
+    SD_CUDA(cudaGetLastError());
+    if ((rc = readCounts())) return rc;
+    const uint32_t nFwd = hCnt[C_FWD];
+    if ((rc = runList(dFwd.p, nFwd, true, 1, dCells.p))) return rc;
+    if (nFwd) { chainAfterForward<<<gridOf(nFwd, 256), 256, 0, st>>>(C, dFwd.p, dRes.p, nFwd, 0); ctx->launches++; }
+    if ((rc = readCounts())) return rc;
+    const uint32_t nWord = hCnt[C_WORD];
+    if ((rc = runList(dWord.p, nWord, false, 1, dCells.p))) return rc;
+    if (nWord) { chainAfterForward<<<gridOf(nWord, 256), 256, 0, st>>>(C, dWord.p, dRes.p, nWord, 1); ctx->launches++; }
+    if ((rc = readCounts())) return rc;
+    uint32_t nBig = hCnt[C_BIG];
+    if (nBig) {     // scores near 2^15: 32-bit pass
+        if ((rc = runList(dBig.p, nBig, false, 0, dCells.p))) return rc;
+        chainAfterForward<<<gridOf(nBig, 256), 256, 0, st>>>(C, dBig.p, dRes.p, nBig, 1);
+        ctx->launches++;
+        SD_CUDA(cudaMemsetAsync(dCnt.p + C_BIG, 0, sizeof(uint32_t), st));
+        if ((rc = readCounts())) return rc;
     }
-    if ((rc = runSw(tasks, results, dCells.p, 1))) return rc;
-    // ---- forward pass again in 16-bit semantics where the 8-bit pass saturated
-    std::vector<SwTask> wtasks;
-    std::vector<uint32_t> wPair;
-    for (size_t i = 0; i < tasks.size(); i++) {
-        PairState &s = ps[taskPair[i]];
-        if (results[i].overflow) {
-            SwTask tk = tasks[i];
-            tk.limit = INT_MAX; tk.width = 16;
-            wtasks.push_back(tk); wPair.push_back(taskPair[i]);
-            s.word = 1;
-        } else { s.score = results[i].score; s.tEnd = results[i].col; s.qEnd = results[i].row; }
+    const uint32_t nRev = hCnt[C_REV];
+    if ((rc = runList(dRev.p, nRev, false, 1, dCells.p + 1))) return rc;
+    if (nRev) { chainAfterReverse<<<gridOf(nRev, 256), 256, 0, st>>>(C, dRev.p, dRes.p, nRev, 0); ctx->launches++; }
+    if ((rc = readCounts())) return rc;
+    nBig = hCnt[C_BIG];
+    if (nBig) {
+        if ((rc = runList(dBig.p, nBig, false, 0, dCells.p + 1))) return rc;
+        chainAfterReverse<<<gridOf(nBig, 256), 256, 0, st>>>(C, dBig.p, dRes.p, nBig, 1);
+        ctx->launches++;
+        if ((rc = readCounts())) return rc;
     }
-    std::vector<SwResult> wres;
-    if ((rc = runSw(wtasks, wres, dCells.p, 1))) return rc;
-    {   // scores close to 2^15 leave the packed 16-bit lanes: redo those pairs with the 32-bit pass
-        std::vector<SwTask> big;
-        std::vector<size_t> bigIdx;
-        for (size_t i = 0; i < wtasks.size(); i++)
-            if (wres[i].overflow) { big.push_back(wtasks[i]); bigIdx.push_back(i); }
-        std::vector<SwResult> bres;
-        if ((rc = runSw(big, bres, dCells.p, 0))) return rc;
-        for (size_t i = 0; i < big.size(); i++) wres[bigIdx[i]] = bres[i];
-    }
-    for (size_t i = 0; i < wtasks.size(); i++) {
-        PairState &s = ps[wPair[i]];
-        s.score = wres[i].score; s.tEnd = wres[i].col; s.qEnd = wres[i].row;
-    }
-    const uint64_t nWord = wtasks.size();
-
-    // ---- E-value and end-point coverage (ssw_align_private :383-398), identity shortcut (scoreIdentical)
-    parallelFor(nP, [&](uint64_t k) {
-        PairState &s = ps[k];
-        const int Lq = (int)hLen[s.q], Lt = (int)(tOff[s.t + 1] - tOff[s.t]);
-        if (s.identity) {
-            short sc = 0;
-            const uint8_t *c = hCode.data() + hOff[s.q];
-            const int8_t *b = hCb.data() + hOff[s.q];
-            for (int i = 0; i < Lq && i < Lt; i++) sc = (short)(sc + mat8[c[i] * AA + c[i]] + b[i]);
-            s.score = sc;
-            s.evalue = evaluer.evalue(s.score, Lq);
-            s.qStart = 0; s.tStart = 0; s.qEnd = Lt - 1; s.tEnd = Lt - 1;
-            s.qcov = 1.0f; s.tcov = 1.0f;
-            s.btLen = Lt; s.ids = Lt;
-            s.stage = 3;
-            return;
-        }
-        if (s.tEnd < 0) { s.stage = 0; return; }
-        s.evalue = evaluer.evalue(s.score, Lq);
-        s.qcov = covOf(0, (unsigned)s.qEnd, (unsigned)Lq);
-        s.tcov = covOf(0, (unsigned)s.tEnd, (unsigned)Lt);
-        if (s.evalue > par->evalue_thr || !hasCoverage(par->cov_thr, par->cov_mode, s.qcov, s.tcov)) { s.stage = 0; return; }
-        s.stage = 1;
-    });
-
-    // ---- reverse pass on the prefixes: alignment start (ssw_align_private :400-480)
-    std::vector<SwTask> rtasks;
-    std::vector<uint32_t> rPair;
-    for (uint32_t k = 0; k < nP; k++) {
-        if (ps[k].stage != 1) continue;
-        SwTask tk;
-        tk.q = ps[k].q; tk.t = ps[k].t; tk.nRows = ps[k].qEnd + 1; tk.nCols = ps[k].tEnd + 1;
-        tk.limit = ps[k].word ? INT_MAX : limit8[ps[k].q]; tk.width = ps[k].word ? 16 : 32; tk.reverse = 1; tk.pad = 0;
-        rtasks.push_back(tk); rPair.push_back(k);
-    }
-    std::vector<SwResult> rres;
-    if ((rc = runSw(rtasks, rres, dCells.p + 1, 1))) return rc;
-    {
-        std::vector<SwTask> big;
-        std::vector<size_t> bigIdx;
-        for (size_t i = 0; i < rtasks.size(); i++)
-            if (rres[i].overflow == 2) { big.push_back(rtasks[i]); bigIdx.push_back(i); }
-        std::vector<SwResult> bres;
-        if ((rc = runSw(big, bres, dCells.p + 1, 0))) return rc;
-        for (size_t i = 0; i < big.size(); i++) rres[bigIdx[i]] = bres[i];
-    }
-    uint64_t scoreMismatch = 0;
-    for (size_t i = 0; i < rtasks.size(); i++) {
-        PairState &s = ps[rPair[i]];
-        if (rres[i].overflow || rres[i].score != s.score) { scoreMismatch++; s.stage = 0; continue; }
-        const int Lq = (int)hLen[s.q], Lt = (int)(tOff[s.t + 1] - tOff[s.t]);
-        s.tStart = s.tEnd - rres[i].col;
-        s.qStart = s.qEnd - rres[i].row;
-        s.qcov = covOf((unsigned)s.qStart, (unsigned)s.qEnd, (unsigned)Lq);
-        s.tcov = covOf((unsigned)s.tStart, (unsigned)s.tEnd, (unsigned)Lt);
-        s.stage = hasCoverage(par->cov_thr, par->cov_mode, s.qcov, s.tcov) ? 2 : 0;
-    }
-    if (scoreMismatch) {
+    const uint32_t nHit = hCnt[C_HITS], nIdent = hCnt[C_IDENT], nTb = hCnt[C_TB];
+    unsigned long long hCounters[4];
+    SD_CUDA(cudaMemcpyAsync(hCounters, dCounters.p, sizeof hCounters, cudaMemcpyDeviceToHost, st));
+    SD_CUDA(cudaStreamSynchronize(st));
+    if (hCounters[1]) {
         // the reference aborts in this situation ("Score of forward/backward SW differ")
-        setError("sd_align_run: forward and reverse Smith-Waterman scores differ for %llu pairs", (unsigned long long)scoreMismatch);
+        setError("sd_align_run: forward and reverse Smith-Waterman scores differ for %llu pairs", hCounters[1]);
         return SD_ELIMIT;
     }
+    const uint64_t poolNeed = hCounters[2];
 
-    // ---- banded traceback
-    std::vector<TbTask> ttasks;
-    std::vector<uint32_t> tPair;
-    uint64_t poolNeed = 0;
-    for (uint32_t k = 0; k < nP; k++) {
-        PairState &s = ps[k];
-        if (s.stage == 3) { s.btOff = poolNeed; poolNeed += (uint64_t)s.btLen; continue; }
-        if (s.stage != 2) continue;
-        TbTask tk;
-        tk.q = s.q; tk.t = s.t; tk.qStart = s.qStart; tk.qEnd = s.qEnd; tk.tStart = s.tStart; tk.tEnd = s.tEnd; tk.score = s.score; tk.pad = 0;
-        tk.btOff = poolNeed;
-        s.btOff = poolNeed;
-        poolNeed += (uint64_t)(s.qEnd - s.qStart + 1) + (uint64_t)(s.tEnd - s.tStart + 1) + 2;
-        ttasks.push_back(tk); tPair.push_back(k);
-    }
-    std::vector<char> hostPool(poolNeed + 1);
-    std::vector<TbResult> tres(ttasks.size());
-    if (!ttasks.empty()) {
-        DevBuf<TbTask> dT;
-        DevBuf<TbResult> dR;
-        DevBuf<char> dPool, dRev;
+    // ---- banded traceback on the survivors
+    std::vector<TbResult> tres(nTb);
+    std::vector<char> devPool(poolNeed + 1);
+    if (nTb) {
+        DevBuf<char> dPool, dRev2;
         DevBuf<int8_t> dDir;
         DevBuf<int> dRows;
-        DevBuf<uint32_t> dOrder;
-        if ((rc = dT.alloc(ttasks.size())) || (rc = dR.alloc(ttasks.size())) || (rc = dPool.alloc(poolNeed + 1))) return rc;
-        SD_CUDA(cudaMemcpyAsync(dT.p, ttasks.data(), ttasks.size() * sizeof(TbTask), cudaMemcpyHostToDevice, st));
-        uint32_t maxQ = 1;
-        for (uint32_t q = 0; q < nq; q++) maxQ = std::max(maxQ, hLen[q]);
+        DevBuf<uint32_t> dPend;
+        if ((rc = dTbRes.alloc(nTb)) || (rc = dPool.alloc(poolNeed + 1))) return rc;
         const uint32_t maxL = std::max(maxQ, idx->maxLen);
         TbArgs A;
-        A.qCode = dCode.p; A.qCb = dCb.p; A.qOff = dOff.p; A.tRes = idx->raw.p; A.tOff = idx->off.p; A.mat = dMat8.p;
-        A.gapOpen = par->gap_open; A.gapExtend = par->gap_extend; A.tasks = dT.p; A.results = dR.p; A.next = dNext.p;
+        A.qCode = queries->code.p; A.qCb = dCb.p; A.qOff = queries->off.p; A.tRes = idx->raw.p; A.tOff = idx->off.p; A.mat = dMat8.p;
+        A.gapOpen = par->gap_open; A.gapExtend = par->gap_extend; A.tasks = dTb.p; A.results = dTbRes.p; A.next = dNext.p;
         A.btPool = dPool.p; A.cells = dCells.p + 2;
-        // pass 1: every task with a modest scratch slot; pass 2: the few that need a wide band
         std::vector<uint32_t> pending;
         for (int pass = 0; pass < 2; pass++) {
-            uint32_t nTasks = pass == 0 ? (uint32_t)ttasks.size() : (uint32_t)pending.size();
+            const uint32_t nTasks = pass == 0 ? nTb : (uint32_t)pending.size();
             if (nTasks == 0) break;
             uint32_t nWarps;
             uint64_t dirCap;
             uint32_t rowCap;
             if (pass == 0) {
-                nWarps = std::min<uint32_t>((uint32_t)ctx->smCount * 4u * TB_WARPS, (nTasks + 0u));
+                nWarps = std::min<uint32_t>((uint32_t)ctx->smCount * 4u * TB_WARPS, nTasks);
                 dirCap = 1ull << 20;
                 rowCap = 4096;
             } else {
@@ -605,14 +691,14 @@ extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, c
                 rowCap = (uint32_t)std::min<uint64_t>(2 * worstBand + 8, 1u << 20);
             }
             nWarps = ((nWarps + TB_WARPS - 1) / TB_WARPS) * TB_WARPS;
-            if ((rc = dDir.alloc((size_t)nWarps * dirCap)) || (rc = dRows.alloc((size_t)nWarps * 3 * rowCap)) || (rc = dRev.alloc((size_t)nWarps * (2 * maxL + 8)))) return rc;
-            A.dir = dDir.p; A.dirCap = dirCap; A.rows = dRows.p; A.rowCap = rowCap; A.rev = dRev.p; A.revCap = 2 * maxL + 8;
+            if ((rc = dDir.alloc((size_t)nWarps * dirCap)) || (rc = dRows.alloc((size_t)nWarps * 3 * rowCap)) || (rc = dRev2.alloc((size_t)nWarps * (2 * maxL + 8)))) return rc;
+            A.dir = dDir.p; A.dirCap = dirCap; A.rows = dRows.p; A.rowCap = rowCap; A.rev = dRev2.p; A.revCap = 2 * maxL + 8;
             A.nTasks = nTasks;
             if (pass == 0) A.order = nullptr;
             else {
-                if ((rc = dOrder.alloc(pending.size()))) return rc;
-                SD_CUDA(cudaMemcpyAsync(dOrder.p, pending.data(), pending.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-                A.order = dOrder.p;
+                if ((rc = dPend.alloc(pending.size()))) return rc;
+                SD_CUDA(cudaMemcpyAsync(dPend.p, pending.data(), pending.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+                A.order = dPend.p;
             }
             SD_CUDA(cudaMemsetAsync(dNext.p, 0, sizeof(uint32_t), st));
             SD_CUDA(cudaEventRecord(evA, st));
@@ -620,78 +706,102 @@ extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, c
             ctx->launches++;
             SD_CUDA(cudaGetLastError());
             SD_CUDA(cudaEventRecord(evB, st));
-            SD_CUDA(cudaMemcpyAsync(tres.data(), dR.p, ttasks.size() * sizeof(TbResult), cudaMemcpyDeviceToHost, st));
+            SD_CUDA(cudaMemcpyAsync(tres.data(), dTbRes.p, (size_t)nTb * sizeof(TbResult), cudaMemcpyDeviceToHost, st));
             SD_CUDA(cudaStreamSynchronize(st));
             if ((rc = lap(tbMs))) return rc;
             pending.clear();
-            for (uint32_t i = 0; i < ttasks.size(); i++)
+            for (uint32_t i = 0; i < nTb; i++)
                 if (tres[i].status == 1) pending.push_back(i);
             if (pass == 1 && !pending.empty()) { setError("sd_align_run: %zu tracebacks exceed the scratch limit", pending.size()); return SD_ELIMIT; }
         }
-        SD_CUDA(cudaMemcpyAsync(hostPool.data(), dPool.p, poolNeed, cudaMemcpyDeviceToHost, st));
+        SD_CUDA(cudaMemcpyAsync(devPool.data(), dPool.p, poolNeed, cudaMemcpyDeviceToHost, st));
         SD_CUDA(cudaStreamSynchronize(st));
-        uint64_t tbErr = 0;
-        for (uint32_t i = 0; i < ttasks.size(); i++) {
-            PairState &s = ps[tPair[i]];
-            if (tres[i].status != 0) { tbErr++; s.stage = 0; continue; }
-            s.btLen = tres[i].btLen; s.ids = tres[i].ids; s.stage = 3;
-        }
-        if (tbErr) { setError("sd_align_run: %llu tracebacks left the band (inconsistent start/end)", (unsigned long long)tbErr); return SD_ELIMIT; }
+        for (uint32_t i = 0; i < nTb; i++)
+            if (tres[i].status != 0) { setError("sd_align_run: a traceback left the band (inconsistent start/end)"); return SD_ELIMIT; }
     }
-    for (uint32_t k = 0; k < nP; k++)
-        if (ps[k].identity && ps[k].stage == 3) memset(hostPool.data() + ps[k].btOff, 'M', (size_t)ps[k].btLen);
+    // ---- survivors and identity pairs to the host: E-values, criteria, order
+    std::vector<PairHit> hHits(nHit);
+    std::vector<uint32_t> hIdent(nIdent);
+    if (nHit) SD_CUDA(cudaMemcpyAsync(hHits.data(), dHits.p, (size_t)nHit * sizeof(PairHit), cudaMemcpyDeviceToHost, st));
+    if (nIdent) SD_CUDA(cudaMemcpyAsync(hIdent.data(), dIdent.p, (size_t)nIdent * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SD_CUDA(cudaStreamSynchronize(st));
+    const std::vector<uint32_t> &identQ = hIdent;
 
-    // ---- acceptance (Alignment::checkCriteria), order (Matcher::compareHits), output
-    std::vector<sd_alignment> acc;
-    acc.reserve(nP / 4 + 16);
-    for (uint32_t k = 0; k < nP; k++) {
-        const PairState &s = ps[k];
-        if (s.stage != 3) continue;
+    acc.reserve(nTb + nIdent);
+    uint64_t poolBytes = 0;
+    for (uint32_t i = 0; i < nHit; i++) {
+        const PairHit &h = hHits[i];
+        if (h.stage != 2) continue;
+        const TbResult &tr = tres[h.tb];
         sd_alignment a;
         memset(&a, 0, sizeof a);
-        a.query = s.q; a.target = s.t; a.score = s.score; a.evalue = s.evalue;
-        a.q_start = s.qStart; a.q_end = s.qEnd; a.q_len = (int)hLen[s.q];
-        a.t_start = s.tStart; a.t_end = s.tEnd; a.t_len = (int)(tOff[s.t + 1] - tOff[s.t]);
-        a.qcov = s.qcov; a.tcov = s.tcov;
-        a.aln_len = s.btLen;
-        a.seq_id = s.identity ? 1.0f : (float)s.ids / (float)s.btLen;
-        a.bt_off = s.btOff; a.bt_len = (uint32_t)s.btLen;
-        const bool ok = s.identity || ((a.evalue <= par->evalue_thr) && (a.seq_id >= par->min_seq_id) &&
-                                       hasCoverage(par->cov_thr, par->cov_mode, a.qcov, a.tcov) && (a.aln_len >= par->min_aln_len));
-        if (!ok) continue;
-        a.bits = evaluer.bitScore(a.score);
+        a.query = h.q; a.target = h.t; a.score = h.score;
+        a.q_start = h.qStart; a.q_end = h.qEnd; a.q_len = (int)hLen[h.q];
+        a.t_start = h.tStart; a.t_end = h.tEnd; a.t_len = (int)(tOff[h.t + 1] - tOff[h.t]);
+        a.qcov = covOf((unsigned)h.qStart, (unsigned)h.qEnd, (unsigned)a.q_len);
+        a.tcov = covOf((unsigned)h.tStart, (unsigned)h.tEnd, (unsigned)a.t_len);
+        a.aln_len = tr.btLen;
+        a.seq_id = (float)tr.ids / (float)tr.btLen;
+        a.bt_len = (uint32_t)tr.btLen;
+        a.bt_off = 0;
+        a.pad = h.tb;                   // remember the task: its backtrace is fetched below
         acc.push_back(a);
     }
-    // pairs are grouped by query already; sort each group
+    parallelFor(acc.size(), [&](uint64_t i) {
+        sd_alignment &a = acc[i];
+        a.evalue = evaluer.evalue(a.score, a.q_len);
+        a.bits = evaluer.bitScore(a.score);
+    });
+    // checkCriteria (Alignment.cpp:548-567)
     {
-        size_t i = 0;
-        while (i < acc.size()) {
-            size_t j = i;
-            while (j < acc.size() && acc[j].query == acc[i].query) j++;
-            std::sort(acc.begin() + i, acc.begin() + j, [](const sd_alignment &x, const sd_alignment &y) {
-                if (x.evalue != y.evalue) return x.evalue < y.evalue;
-                if (x.bits != y.bits) return x.bits > y.bits;
-                if (x.t_len != y.t_len) return x.t_len < y.t_len;
-                return x.target < y.target;      // keys ascend with the target index
-            });
-            i = j;
+        size_t w = 0;
+        for (size_t i = 0; i < acc.size(); i++) {
+            const sd_alignment &a = acc[i];
+            const bool ok = (a.evalue <= par->evalue_thr) && (a.seq_id >= par->min_seq_id) && hasCoverage(par->cov_thr, par->cov_mode, a.qcov, a.tcov) &&
+                            (a.aln_len >= par->min_aln_len);
+            if (ok) acc[w++] = a;
         }
+        acc.resize(w);
     }
-    // compact the backtraces of accepted alignments into the caller's pool
-    uint64_t used = 0;
-    for (const sd_alignment &a : acc) used += a.bt_len;
-    *n_out = acc.size();
-    *bt_used = used;
-    if (acc.size() > cap || used > bt_cap || (acc.size() && (!out || !bt_pool))) {
-        setError("sd_align_run: needs %zu alignments / %llu backtrace bytes", acc.size(), (unsigned long long)used);
-        return SD_ESMALL;
+    // identity shortcut (scoreIdentical StripedSmithWaterman.cpp:1675-1710; note the 16-bit accumulator)
+    const size_t nTraced = acc.size();
+    for (uint32_t i = 0; i < nIdent; i++) {
+        const uint32_t q = identQ[i], t = query_first + q;
+        const int Lq = (int)hLen[q], Lt = (int)(tOff[t + 1] - tOff[t]);
+        short sc = 0;
+        const uint8_t *c = hCode.data() + hOff[q];
+        const int8_t *b = hCb.data() + hOff[q];
+        for (int k = 0; k < Lq && k < Lt; k++) sc = (short)(sc + mat8[c[k] * AA + c[k]] + b[k]);
+        sd_alignment a;
+        memset(&a, 0, sizeof a);
+        a.query = q; a.target = t; a.score = sc; a.evalue = evaluer.evalue(sc, Lq); a.bits = evaluer.bitScore(sc);
+        a.q_start = 0; a.t_start = 0; a.q_end = Lt - 1; a.t_end = Lt - 1; a.q_len = Lq; a.t_len = Lt;
+        a.qcov = 1.0f; a.tcov = 1.0f; a.seq_id = 1.0f; a.aln_len = Lt; a.bt_len = (uint32_t)Lt; a.pad = 0xffffffffu;
+        acc.push_back(a);
     }
-    uint64_t w = 0;
-    for (size_t i = 0; i < acc.size(); i++) {
-        memcpy(bt_pool + w, hostPool.data() + acc[i].bt_off, acc[i].bt_len);
-        acc[i].bt_off = w;
-        w += acc[i].bt_len;
-        out[i] = acc[i];
+    (void)nTraced;
+    std::sort(acc.begin(), acc.end(), [](const sd_alignment &x, const sd_alignment &y) {
+        if (x.query != y.query) return x.query < y.query;
+        if (x.evalue != y.evalue) return x.evalue < y.evalue;          // Matcher::compareHits
+        if (x.bits != y.bits) return x.bits > y.bits;
+        if (x.t_len != y.t_len) return x.t_len < y.t_len;
+        return x.target < y.target;
+    });
+    for (const sd_alignment &a : acc) poolBytes += a.bt_len;
+    pool.resize(poolBytes + 1);
+    {
+        // task offsets in the device pool
+        std::vector<TbTask> hTb(nTb);
+        if (nTb) SD_CUDA(cudaMemcpy(hTb.data(), dTb.p, (size_t)nTb * sizeof(TbTask), cudaMemcpyDeviceToHost));
+        uint64_t w = 0;
+        for (sd_alignment &a : acc) {
+            if (a.pad == 0xffffffffu) memset(pool.data() + w, 'M', a.bt_len);
+            else memcpy(pool.data() + w, devPool.data() + hTb[a.pad].btOff, a.bt_len);
+            a.bt_off = w;
+            a.pad = 0;
+            w += a.bt_len;
+        }
+        pool.resize(poolBytes);
     }
     SD_CUDA(cudaEventRecord(ev1, st));
     SD_CUDA(cudaStreamSynchronize(st));
@@ -700,13 +810,61 @@ extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, c
         SD_CUDA(cudaMemcpy(hc, dCells.p, sizeof hc, cudaMemcpyDeviceToHost));
         float ms = 0;
         cudaEventElapsedTime(&ms, ev0, ev1);
-        stats->alignments = nAligned; stats->passed = acc.size(); stats->word_mode = nWord;
-        stats->reverse_passes = rtasks.size(); stats->tracebacks = ttasks.size();
+        stats->alignments = hCounters[0]; stats->passed = acc.size(); stats->word_mode = nWord;
+        stats->reverse_passes = nRev; stats->tracebacks = nTb;
         stats->cells_forward = hc[0]; stats->cells_reverse = hc[1]; stats->cells_traceback = hc[2];
         stats->sw_ms = swMs; stats->traceback_ms = tbMs; stats->total_ms = ms;
     }
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evA); cudaEventDestroy(evB);
     return SD_OK;
+}
+
+extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                                  const uint32_t *pair_q, const uint32_t *pair_t, uint64_t n_pairs, uint64_t db_residues,
+                                  const sd_align_params *par, sd_alignment *out, uint64_t cap, uint64_t *n_out, char *bt_pool,
+                                  uint64_t bt_cap, uint64_t *bt_used, sd_align_stats *stats) {
+    if (!ctx || !idx || !queries || !par || !n_out || !bt_used || (n_pairs && (!pair_q || !pair_t))) { setError("sd_align_run_batch: bad argument"); return SD_EINVAL; }
+    *n_out = 0; *bt_used = 0;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (queries->nq == 0 || n_pairs == 0) return SD_OK;
+    for (uint64_t k = 0; k < n_pairs; k++)
+        if (pair_q[k] >= queries->nq || pair_t[k] >= idx->nT) { setError("sd_align_run: pair %llu out of range", (unsigned long long)k); return SD_EINVAL; }
+    SD_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<uint32_t> dQ, dT;
+    int rc;
+    if ((rc = dQ.alloc(n_pairs)) || (rc = dT.alloc(n_pairs))) return rc;
+    SD_CUDA(cudaMemcpyAsync(dQ.p, pair_q, n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(cudaMemcpyAsync(dT.p, pair_t, n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<sd_alignment> acc;
+    std::vector<char> pool;
+    if ((rc = sd_align_device_pairs(ctx, idx, queries, query_first, dQ.p, dT.p, n_pairs, db_residues, par, acc, pool, stats))) return rc;
+    uint64_t used = 0;
+    for (const sd_alignment &a : acc) used += a.bt_len;
+    *n_out = acc.size();
+    *bt_used = used;
+    if (acc.size() > cap || used > bt_cap || (acc.size() && (!out || !bt_pool))) {
+        setError("sd_align_run: needs %zu alignments / %llu backtrace bytes", acc.size(), (unsigned long long)used);
+        return SD_ESMALL;
+    }
+    if (!acc.empty()) memcpy(out, acc.data(), acc.size() * sizeof(sd_alignment));
+    if (used) memcpy(bt_pool, pool.data(), used);
+    return SD_OK;
+}
+
+int sd_align_device_hits(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                         const sd_prefilter_hit *dHits, uint64_t n_hits, uint64_t db_residues, const sd_align_params *par,
+                         std::vector<sd_alignment> &acc, std::vector<char> &pool, sd_align_stats *stats) {
+    acc.clear(); pool.clear();
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (n_hits == 0) return SD_OK;
+    SD_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<uint32_t> dQ, dT;
+    int rc;
+    if ((rc = dQ.alloc(n_hits)) || (rc = dT.alloc(n_hits))) return rc;
+    splitPrefilterHits<<<gridOf(n_hits, 256), 256, 0, ctx->stream>>>(dHits, n_hits, dQ.p, dT.p);
+    ctx->launches++;
+    SD_CUDA(cudaGetLastError());
+    return sd_align_device_pairs(ctx, idx, queries, query_first, dQ.p, dT.p, n_hits, db_residues, par, acc, pool, stats);
 }
 
 extern "C" int sd_format_alignment(const sd_alignment *a, uint32_t target_key, const char *bt_pool, char *buf, int cap) {

@@ -793,10 +793,11 @@ extern "C" int sd_prefilter_run(sd_context *ctx, const sd_target_index *idx, con
     return rc;
 }
 
-extern "C" int sd_prefilter_run_batch(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
-                                      const sd_prefilter_params *par, sd_prefilter_hit *hits, uint64_t cap, uint64_t *n_hits,
-                                      sd_prefilter_stats *stats) {
-    if (!ctx || !idx || !queries || !par || !n_hits || (!hits && cap)) { setError("sd_prefilter_run_batch: bad argument"); return SD_EINVAL; }
+// keepOnDevice != nullptr: the dense hit array stays in HBM (fused clustersearch path), nothing is copied to `hits`
+int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                      const sd_prefilter_params *par, sd_prefilter_hit *hits, uint64_t cap, uint64_t *n_hits,
+                      sd_prefilter_stats *stats, sd::DevBuf<sd_prefilter_hit> *keepOnDevice) {
+    if (!ctx || !idx || !queries || !par || !n_hits || (!hits && cap && !keepOnDevice)) { setError("sd_prefilter_run_batch: bad argument"); return SD_EINVAL; }
     *n_hits = 0;
     const uint32_t nq = queries->nq;
     if (nq == 0) return SD_OK;
@@ -892,11 +893,12 @@ extern "C" int sd_prefilter_run_batch(sd_context *ctx, const sd_target_index *id
     uint64_t totalHits = 0;
     for (uint32_t i = 0; i < nq; i++) totalHits += hCount[i];
     *n_hits = totalHits;
-    if (totalHits > cap) { setError("sd_prefilter_run: %llu hits, buffer holds %llu", (unsigned long long)totalHits, (unsigned long long)cap); return SD_ESMALL; }
+    if (!keepOnDevice && totalHits > cap) { setError("sd_prefilter_run: %llu hits, buffer holds %llu", (unsigned long long)totalHits, (unsigned long long)cap); return SD_ESMALL; }
     // gather the per-query slices (strided device layout -> dense) and copy once
     if (totalHits) {
         DevBuf<uint32_t> dOffs;
-        DevBuf<sd_prefilter_hit> dDense;
+        DevBuf<sd_prefilter_hit> dDenseLocal;
+        DevBuf<sd_prefilter_hit> &dDense = keepOnDevice ? *keepOnDevice : dDenseLocal;
         DevBuf<uint8_t> tmp;
         if ((rc = dOffs.alloc(nq)) || (rc = dDense.alloc(totalHits))) return rc;
         size_t tmpBytes = 0;
@@ -906,7 +908,7 @@ extern "C" int sd_prefilter_run_batch(sd_context *ctx, const sd_target_index *id
         compactHits<<<gridFor((uint64_t)nq * 32, 256), 256, 0, st>>>(dOut.p, dOutCount.p, dOffs.p, nq, maxHits, dDense.p);
         ctx->launches++;
         SD_CUDA(cudaGetLastError());
-        SD_CUDA(cudaMemcpyAsync(hits, dDense.p, totalHits * sizeof(sd_prefilter_hit), cudaMemcpyDeviceToHost, st));
+        if (!keepOnDevice) SD_CUDA(cudaMemcpyAsync(hits, dDense.p, totalHits * sizeof(sd_prefilter_hit), cudaMemcpyDeviceToHost, st));
         SD_CUDA(cudaStreamSynchronize(st));
     }
     SD_CUDA(cudaEventRecord(ev1, st));
@@ -921,4 +923,10 @@ extern "C" int sd_prefilter_run_batch(sd_context *ctx, const sd_target_index *id
     }
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evk0); cudaEventDestroy(evk1);
     return SD_OK;
+}
+
+extern "C" int sd_prefilter_run_batch(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                                      const sd_prefilter_params *par, sd_prefilter_hit *hits, uint64_t cap, uint64_t *n_hits,
+                                      sd_prefilter_stats *stats) {
+    return sd_prefilter_core(ctx, idx, queries, query_first, par, hits, cap, n_hits, stats, nullptr);
 }

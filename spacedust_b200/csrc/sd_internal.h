@@ -13,6 +13,8 @@
 #include "hostprep.h"
 
 struct sd_context;
+struct sd_target_index;
+struct sd_query_batch;
 
 namespace sd {
 
@@ -96,6 +98,17 @@ struct sd_query_batch {
     sd::DevBuf<uint8_t> code;          // residue codes, concatenated (+16 pad)
     sd::DevBuf<uint32_t> off;          // nq+1
 };
+
+int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                      const sd_prefilter_params *par, sd_prefilter_hit *hits, uint64_t cap, uint64_t *n_hits,
+                      sd_prefilter_stats *stats, sd::DevBuf<sd_prefilter_hit> *keepOnDevice);
+int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                          const uint32_t *dPairQ, const uint32_t *dPairT, uint64_t n_pairs, uint64_t db_residues,
+                          const sd_align_params *par, std::vector<sd_alignment> &acc, std::vector<char> &pool,
+                          sd_align_stats *stats);
+int sd_align_device_hits(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                         const sd_prefilter_hit *dHits, uint64_t n_hits, uint64_t db_residues, const sd_align_params *par,
+                         std::vector<sd_alignment> &acc, std::vector<char> &pool, sd_align_stats *stats);
 
 struct sd_target_index {
     sd_context *ctx = nullptr;
