@@ -9,6 +9,7 @@
 //   alignment/StripedSmithWaterman.cpp:1348-1600 banded_sw (band doubling, direction bytes, tie rules)
 //   alignment/StripedSmithWaterman.cpp:1675-1710 scoreIdentical
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -235,26 +236,6 @@ static inline bool canBeCovered(float covThr, int covMode, float q, float t) {  
     }
 }
 
-template <typename F>
-static void parallelFor(uint64_t n, F fn) {
-    unsigned nThreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
-    if (n < 4096) nThreads = 1;
-    std::atomic<uint64_t> next{0};
-    const uint64_t chunk = 2048;
-    auto work = [&]() {
-        for (;;) {
-            const uint64_t lo = next.fetch_add(chunk);
-            if (lo >= n) break;
-            const uint64_t hi = std::min(n, lo + chunk);
-            for (uint64_t i = lo; i < hi; i++) fn(i);
-        }
-    };
-    std::vector<std::thread> pool;
-    for (unsigned t = 1; t < nThreads; t++) pool.emplace_back(work);
-    work();
-    for (auto &t : pool) t.join();
-}
-
 }  // namespace sd
 
 using namespace sd;
@@ -461,11 +442,24 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     if (n_pairs >= 0xffffffffull) { setError("sd_align_run: too many pairs in one call (%llu)", (unsigned long long)n_pairs); return SD_ELIMIT; }
     const uint64_t total = queries->total;
     SD_CUDA(cudaSetDevice(ctx->device));
+    sd::StreamScope allocScope(ctx->stream);
     cudaStream_t st = ctx->stream;
     int rc;
     cudaEvent_t ev0, ev1, evA, evB;
     SD_CUDA(cudaEventCreate(&ev0)); SD_CUDA(cudaEventCreate(&ev1)); SD_CUDA(cudaEventCreate(&evA)); SD_CUDA(cudaEventCreate(&evB));
     SD_CUDA(cudaEventRecord(ev0, st));
+    const bool timing = getenv("SD_TIMING") != nullptr;
+    auto tPrev = std::chrono::steady_clock::now();
+    std::string tLog;
+    auto tick = [&](const char *name) {
+        if (!timing) return;
+        cudaStreamSynchronize(st);
+        auto now = std::chrono::steady_clock::now();
+        char b[96];
+        snprintf(b, sizeof b, " %s=%.1f", name, std::chrono::duration<double, std::milli>(now - tPrev).count());
+        tLog += b;
+        tPrev = now;
+    };
     double swMs = 0, tbMs = 0;
     auto lap = [&](double &accMs) -> int {
         float ms = 0;
@@ -500,7 +494,8 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     DevBuf<uint32_t> dStride, dLen, dNext;
     DevBuf<uint64_t> dProfOff;
     DevBuf<float> dBias;
-    DevBuf<int8_t> dCb, dMat8, dProfF, dProfR;
+    DevBuf<int8_t> dCb, dMat8;
+    ScratchBuf<int8_t> dProfF(ctx, SL_AL_PROFF), dProfR(ctx, SL_AL_PROFR);
     DevBuf<int16_t> dSub;
     DevBuf<double> dPBack;
     DevBuf<unsigned long long> dCells;
@@ -527,6 +522,7 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     SD_CUDA(cudaMemcpyAsync(hCb.data(), dCb.p, total, cudaMemcpyDeviceToHost, st));
     SD_CUDA(cudaStreamSynchronize(st));
 
+    tick("profiles");
     // per query: 8-bit limit (ssw_init :1283-1291) and the smallest raw score whose E-value passes -e
     const std::vector<uint32_t> &tOff = idx->hostOff;
     const Evaluer evaluer((double)(db_residues ? db_residues : idx->totalRes));
@@ -557,14 +553,16 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
         }
     }
 
+    tick("minScore");
     // ---- device lists
     const uint32_t nP = (uint32_t)n_pairs;
-    DevBuf<SwTask> dFwd, dWord, dBig, dRev;
-    DevBuf<SwResult> dRes;
-    DevBuf<PairHit> dHits;
-    DevBuf<TbTask> dTb;
-    DevBuf<TbResult> dTbRes;
-    DevBuf<uint32_t> dIdent, dOrder, dCnt, dClass;
+    ScratchBuf<SwTask> dFwd(ctx, SL_AL_FWD), dWord(ctx, SL_AL_WORD), dBig(ctx, SL_AL_BIG), dRev(ctx, SL_AL_REV);
+    ScratchBuf<SwResult> dRes(ctx, SL_AL_RES);
+    ScratchBuf<PairHit> dHits(ctx, SL_AL_HITS);
+    ScratchBuf<TbTask> dTb(ctx, SL_AL_TB);
+    ScratchBuf<TbResult> dTbRes(ctx, SL_AL_TBRES);
+    ScratchBuf<uint32_t> dIdent(ctx, SL_AL_IDENT), dOrder(ctx, SL_AL_ORDER);
+    DevBuf<uint32_t> dCnt, dClass;
     DevBuf<int32_t> dLimit8, dMinScore;
     DevBuf<unsigned long long> dCounters;
     if ((rc = dFwd.alloc(nP)) || (rc = dWord.alloc(nP)) || (rc = dBig.alloc(nP)) || (rc = dRev.alloc(nP)) || (rc = dRes.alloc(nP)) ||
@@ -589,7 +587,7 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     batch.tRes = idx->raw.p; batch.tOff = idx->off.p; batch.gapOpen = par->gap_open; batch.gapExtend = par->gap_extend;
     const uint32_t swWarps = (uint32_t)ctx->smCount * 4u * swWarpsPerCta();
     const uint32_t bndStride = std::max<uint32_t>(idx->maxLen, 32u) + 32u;
-    DevBuf<int> dBoundary;
+    ScratchBuf<int> dBoundary(ctx, SL_AL_BOUND);
     if ((rc = dBoundary.alloc((size_t)swWarps * 6 * bndStride))) return rc;
 
     uint32_t hCnt[16];
@@ -617,14 +615,17 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
         return lap(swMs);
     };
 
+    tick("alloc");
     chainBuildForward<<<gridOf(n_pairs, 256), 256, 0, st>>>(C);
     ctx->launches++;
     SD_CUDA(cudaGetLastError());
     if ((rc = readCounts())) return rc;
+    tick("build");
     const uint32_t nFwd = hCnt[C_FWD];
     if ((rc = runList(dFwd.p, nFwd, true, 1, dCells.p))) return rc;
     if (nFwd) { chainAfterForward<<<gridOf(nFwd, 256), 256, 0, st>>>(C, dFwd.p, dRes.p, nFwd, 0); ctx->launches++; }
     if ((rc = readCounts())) return rc;
+    tick("fwd8");
     const uint32_t nWord = hCnt[C_WORD];
     if ((rc = runList(dWord.p, nWord, false, 1, dCells.p))) return rc;
     if (nWord) { chainAfterForward<<<gridOf(nWord, 256), 256, 0, st>>>(C, dWord.p, dRes.p, nWord, 1); ctx->launches++; }
@@ -637,6 +638,7 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
         SD_CUDA(cudaMemsetAsync(dCnt.p + C_BIG, 0, sizeof(uint32_t), st));
         if ((rc = readCounts())) return rc;
     }
+    tick("fwd16");
     const uint32_t nRev = hCnt[C_REV];
     if ((rc = runList(dRev.p, nRev, false, 1, dCells.p + 1))) return rc;
     if (nRev) { chainAfterReverse<<<gridOf(nRev, 256), 256, 0, st>>>(C, dRev.p, dRes.p, nRev, 0); ctx->launches++; }
@@ -648,6 +650,7 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
         ctx->launches++;
         if ((rc = readCounts())) return rc;
     }
+    tick("rev");
     const uint32_t nHit = hCnt[C_HITS], nIdent = hCnt[C_IDENT], nTb = hCnt[C_TB];
     unsigned long long hCounters[4];
     SD_CUDA(cudaMemcpyAsync(hCounters, dCounters.p, sizeof hCounters, cudaMemcpyDeviceToHost, st));
@@ -661,11 +664,12 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
 
     // ---- banded traceback on the survivors
     std::vector<TbResult> tres(nTb);
-    std::vector<char> devPool(poolNeed + 1);
+    char *devPool = static_cast<char *>(ctxPinnedScratch(ctx, 0, poolNeed + 1));
+    if (!devPool) return SD_ENOMEM;
     if (nTb) {
-        DevBuf<char> dPool, dRev2;
-        DevBuf<int8_t> dDir;
-        DevBuf<int> dRows;
+        ScratchBuf<char> dPool(ctx, SL_TB_POOL), dRev2(ctx, SL_TB_REV);
+        ScratchBuf<int8_t> dDir(ctx, SL_TB_DIR);
+        ScratchBuf<int> dRows(ctx, SL_TB_ROWS);
         DevBuf<uint32_t> dPend;
         if ((rc = dTbRes.alloc(nTb)) || (rc = dPool.alloc(poolNeed + 1))) return rc;
         const uint32_t maxL = std::max(maxQ, idx->maxLen);
@@ -714,11 +718,12 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
                 if (tres[i].status == 1) pending.push_back(i);
             if (pass == 1 && !pending.empty()) { setError("sd_align_run: %zu tracebacks exceed the scratch limit", pending.size()); return SD_ELIMIT; }
         }
-        SD_CUDA(cudaMemcpyAsync(devPool.data(), dPool.p, poolNeed, cudaMemcpyDeviceToHost, st));
+        SD_CUDA(cudaMemcpyAsync(devPool, dPool.p, poolNeed, cudaMemcpyDeviceToHost, st));
         SD_CUDA(cudaStreamSynchronize(st));
         for (uint32_t i = 0; i < nTb; i++)
             if (tres[i].status != 0) { setError("sd_align_run: a traceback left the band (inconsistent start/end)"); return SD_ELIMIT; }
     }
+    tick("traceback");
     // ---- survivors and identity pairs to the host: E-values, criteria, order
     std::vector<PairHit> hHits(nHit);
     std::vector<uint32_t> hIdent(nIdent);
@@ -747,6 +752,7 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
         a.pad = h.tb;                   // remember the task: its backtrace is fetched below
         acc.push_back(a);
     }
+    tick("gather");
     parallelFor(acc.size(), [&](uint64_t i) {
         sd_alignment &a = acc[i];
         a.evalue = evaluer.evalue(a.score, a.q_len);
@@ -780,6 +786,7 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
         acc.push_back(a);
     }
     (void)nTraced;
+    tick("evalue");
     std::sort(acc.begin(), acc.end(), [](const sd_alignment &x, const sd_alignment &y) {
         if (x.query != y.query) return x.query < y.query;
         if (x.evalue != y.evalue) return x.evalue < y.evalue;          // Matcher::compareHits
@@ -792,22 +799,28 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     {
         // task offsets in the device pool
         std::vector<TbTask> hTb(nTb);
-        if (nTb) SD_CUDA(cudaMemcpy(hTb.data(), dTb.p, (size_t)nTb * sizeof(TbTask), cudaMemcpyDeviceToHost));
-        uint64_t w = 0;
-        for (sd_alignment &a : acc) {
-            if (a.pad == 0xffffffffu) memset(pool.data() + w, 'M', a.bt_len);
-            else memcpy(pool.data() + w, devPool.data() + hTb[a.pad].btOff, a.bt_len);
-            a.bt_off = w;
-            a.pad = 0;
-            w += a.bt_len;
+        if (nTb) {
+            SD_CUDA(cudaMemcpyAsync(hTb.data(), dTb.p, (size_t)nTb * sizeof(TbTask), cudaMemcpyDeviceToHost, st));
+            SD_CUDA(cudaStreamSynchronize(st));
         }
+        uint64_t w = 0;
+        for (sd_alignment &a : acc) { a.bt_off = w; w += a.bt_len; }
+        parallelFor(acc.size(), [&](uint64_t i) {
+            sd_alignment &a = acc[i];
+            if (a.pad == 0xffffffffu) memset(pool.data() + a.bt_off, 'M', a.bt_len);
+            else memcpy(pool.data() + a.bt_off, devPool + hTb[a.pad].btOff, a.bt_len);
+            a.pad = 0;
+        });
         pool.resize(poolBytes);
     }
+    tick("sort+pool");
+    if (timing) fprintf(stderr, "[sd_align]%s\n", tLog.c_str());
     SD_CUDA(cudaEventRecord(ev1, st));
     SD_CUDA(cudaStreamSynchronize(st));
     if (stats) {
         unsigned long long hc[4];
-        SD_CUDA(cudaMemcpy(hc, dCells.p, sizeof hc, cudaMemcpyDeviceToHost));
+        SD_CUDA(cudaMemcpyAsync(hc, dCells.p, sizeof hc, cudaMemcpyDeviceToHost, st));
+        SD_CUDA(cudaStreamSynchronize(st));
         float ms = 0;
         cudaEventElapsedTime(&ms, ev0, ev1);
         stats->alignments = hCounters[0]; stats->passed = acc.size(); stats->word_mode = nWord;
@@ -830,7 +843,8 @@ extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, c
     for (uint64_t k = 0; k < n_pairs; k++)
         if (pair_q[k] >= queries->nq || pair_t[k] >= idx->nT) { setError("sd_align_run: pair %llu out of range", (unsigned long long)k); return SD_EINVAL; }
     SD_CUDA(cudaSetDevice(ctx->device));
-    DevBuf<uint32_t> dQ, dT;
+    sd::StreamScope allocScope(ctx->stream);
+    ScratchBuf<uint32_t> dQ(ctx, SL_AL_PAIRQ), dT(ctx, SL_AL_PAIRT);
     int rc;
     if ((rc = dQ.alloc(n_pairs)) || (rc = dT.alloc(n_pairs))) return rc;
     SD_CUDA(cudaMemcpyAsync(dQ.p, pair_q, n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -858,7 +872,8 @@ int sd_align_device_hits(sd_context *ctx, const sd_target_index *idx, const sd_q
     if (stats) memset(stats, 0, sizeof *stats);
     if (n_hits == 0) return SD_OK;
     SD_CUDA(cudaSetDevice(ctx->device));
-    DevBuf<uint32_t> dQ, dT;
+    sd::StreamScope allocScope(ctx->stream);
+    ScratchBuf<uint32_t> dQ(ctx, SL_AL_PAIRQ), dT(ctx, SL_AL_PAIRT);
     int rc;
     if ((rc = dQ.alloc(n_hits)) || (rc = dT.alloc(n_hits))) return rc;
     splitPrefilterHits<<<gridOf(n_hits, 256), 256, 0, ctx->stream>>>(dHits, n_hits, dQ.p, dT.p);

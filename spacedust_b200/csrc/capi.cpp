@@ -11,6 +11,32 @@ void setError(const char *fmt, ...) {
     vsnprintf(g_err, sizeof g_err, fmt, ap);
     va_end(ap);
 }
+void *ctxDeviceScratch(sd_context *ctx, int slot, size_t bytes) {
+    sd_context::Slot &s = ctx->devSlot[slot];
+    if (s.cap >= bytes && s.p) return s.p;
+    if (s.p) { cudaStreamSynchronize(ctx->stream); cudaFree(s.p); s.p = nullptr; s.cap = 0; }
+    const size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaMalloc(&s.p, want);
+    if (e != cudaSuccess) { s.p = nullptr; setError("device scratch allocation of %zu bytes failed: %s", want, cudaGetErrorString(e)); return nullptr; }
+    s.cap = want;
+    return s.p;
+}
+
+void *ctxPinnedScratch(sd_context *ctx, int slot, size_t bytes) {
+    sd_context::Slot &s = ctx->pinSlot[slot];
+    if (s.cap >= bytes && s.p) return s.p;
+    if (s.p) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(s.p); s.p = nullptr; s.cap = 0; }
+    const size_t want = bytes + bytes / 8 + 4096;
+    cudaError_t e = cudaHostAlloc(&s.p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) { s.p = nullptr; setError("pinned host allocation of %zu bytes failed: %s", want, cudaGetErrorString(e)); return nullptr; }
+    s.cap = want;
+    return s.p;
+}
+
+cudaStream_t &tlsAllocStream() {
+    static thread_local cudaStream_t s = nullptr;
+    return s;
+}
 }  // namespace sd
 
 extern "C" const char *sd_last_error(void) { return sd::g_err; }
@@ -33,6 +59,13 @@ extern "C" int sd_context_create(int device, sd_context **out) {
     SD_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->smCount = prop.multiProcessorCount;
     SD_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {   // keep freed device blocks in the pool instead of returning them to the driver at every synchronisation
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     sd::buildSubMat(sd::VTML80, 8.0f, -0.2f, ctx->seedMat);
     sd::buildSubMat(sd::BLOSUM62, 2.0f, -0.2f, ctx->diagMat);
     sd::buildSubMat(sd::BLOSUM62, 2.0f, 0.0f, ctx->alnMat);
@@ -43,6 +76,8 @@ extern "C" int sd_context_create(int device, sd_context **out) {
 extern "C" void sd_context_destroy(sd_context *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    for (auto &sl : ctx->devSlot) if (sl.p) cudaFree(sl.p);
+    for (auto &sl : ctx->pinSlot) if (sl.p) cudaFreeHost(sl.p);
     ctx->e3score.release();
     ctx->e3index.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -287,6 +287,7 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
     if (n_alns == 0) return SD_OK;
     if (n_alns >= 0xffffffffull) { setError("sd_cluster_run: too many alignments in one call"); return SD_ELIMIT; }
     SD_CUDA(cudaSetDevice(ctx->device));
+    sd::StreamScope allocScope(ctx->stream);
     cudaStream_t st = ctx->stream;
     cudaEvent_t ev0, ev1, evA, evB;
     SD_CUDA(cudaEventCreate(&ev0)); SD_CUDA(cudaEventCreate(&ev1)); SD_CUDA(cudaEventCreate(&evA)); SD_CUDA(cudaEventCreate(&evB));
@@ -295,6 +296,8 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
     // ---- besthitbyset: per query gene and target set the first alignment with the smallest printed E-value
     std::vector<BestHit> best;
     best.reserve(n_alns);
+    std::vector<double> evPrinted(n_alns);        // align prints %.3E, besthitbyset parses it
+    parallelFor(n_alns, [&](uint64_t i) { evPrinted[i] = roundTrip3E(alns[i].evalue); });
     {
         std::vector<std::pair<uint32_t, uint32_t>> grp;   // (target set, alignment index)
         uint64_t i = 0;
@@ -316,14 +319,14 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
                 double bestEval = DBL_MAX;
                 int64_t bestIdx = -1;
                 while (h < grp.size() && grp[h].first == grp[g].first) {
-                    const double ev = roundTrip3E(alns[grp[h].second].evalue);    // align prints %.3E, besthitbyset parses it
+                    const double ev = evPrinted[grp[h].second];
                     if (ev < bestEval) { bestEval = ev; bestIdx = grp[h].second; }
                     h++;
                 }
                 if (bestIdx >= 0) {
                     BestHit bh;
                     bh.aln = (uint32_t)bestIdx; bh.q = q; bh.qSet = q_set_of[q]; bh.tSet = grp[g].first;
-                    bh.logP = roundTrip3E(computeLogPval(bestEval));
+                    bh.logP = bestEval;      // turned into the printed log P-value below (parallel)
                     if (bh.qSet >= n_q_sets || bh.tSet >= n_t_sets) { setError("sd_cluster_run: set index out of range"); return SD_EINVAL; }
                     best.push_back(bh);
                 }
@@ -332,6 +335,7 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
             i = j;
         }
     }
+    parallelFor(best.size(), [&](uint64_t i) { best[i].logP = roundTrip3E(computeLogPval(best[i].logP)); });
     // ---- mergeresultsbyset + combinehits: group by (query set, target set), members in gene order
     std::stable_sort(best.begin(), best.end(), [](const BestHit &a, const BestHit &b) {
         if (a.qSet != b.qSet) return a.qSet < b.qSet;
@@ -356,7 +360,7 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
                         k++;
                         r -= best[h].logP - logPvalThr;
                         mAln.push_back(best[h].aln);
-                        mPval.push_back(roundTrip3E(std::exp(best[h].logP)));
+                        mPval.push_back(best[h].logP);     // exp + %.3E round trip below (parallel)
                     }
                 }
                 if (r == 0 || k == 0) { mAln.resize(first); mPval.resize(first); }
@@ -365,6 +369,7 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
             i = j;
         }
     }
+    parallelFor(mPval.size(), [&](uint64_t i) { mPval[i] = roundTrip3E(std::exp(mPval[i])); });
     // ---- clusterhits: genome pairs with at least two hits go to the device
     uint32_t maxOrf = 0;
     for (uint32_t s = 0; s < n_q_sets; s++) maxOrf = std::max(maxOrf, q_set_size[s]);
@@ -457,9 +462,12 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
     }
     // ---- clusters of each genome pair in node order; thresholds (ClusterHits.cpp:456-485)
     const uint32_t cls = (uint32_t)std::max(par->cluster_size, 0);
-    std::vector<sd_cluster> outC;
-    std::vector<sd_cluster_member> outM;
-    for (uint32_t di = 0; di < nDev; di++) {
+    std::vector<std::vector<sd_cluster>> partC(nDev);
+    std::vector<std::vector<sd_cluster_member>> partM(nDev);
+    parallelFor(nDev, [&](uint64_t di64) {
+        const uint32_t di = (uint32_t)di64;
+        std::vector<sd_cluster> &outC = partC[di];
+        std::vector<sd_cluster_member> &outM = partM[di];
         const Match &m = matches[devMatch[di]];
         const uint32_t base = dMatchOff[di];
         std::map<uint32_t, std::vector<uint32_t>> byRoot;
@@ -514,6 +522,12 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
             }
             outC.push_back(c);
         }
+    });
+    std::vector<sd_cluster> outC;
+    std::vector<sd_cluster_member> outM;
+    for (uint32_t di = 0; di < nDev; di++) {
+        for (sd_cluster c : partC[di]) { c.first += (uint32_t)outM.size(); outC.push_back(c); }
+        outM.insert(outM.end(), partM[di].begin(), partM[di].end());
     }
     *n_clusters = outC.size();
     *n_members = outM.size();

@@ -658,6 +658,7 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
     for (uint32_t i = 0; i < n; i++)
         if (off[i + 1] - off[i] >= 32768) { setError("target %u longer than 32767 residues: long-sequence path not implemented", i); return SD_ELIMIT; }
     SD_CUDA(cudaSetDevice(ctx->device));
+    sd::StreamScope allocScope(ctx->stream);
     std::unique_ptr<sd_target_index> idx(new sd_target_index());
     idx->ctx = ctx;
     idx->nT = n;
@@ -672,7 +673,8 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
     std::fill(codes.begin() + total, codes.end(), (uint8_t)XCODE);
     int rc;
     if ((rc = idx->raw.alloc(total + SPAN)) != SD_OK) return rc;
-    SD_CUDA(cudaMemcpy(idx->raw.p, codes.data(), total + SPAN, cudaMemcpyHostToDevice));
+    SD_CUDA(cudaMemcpyAsync(idx->raw.p, codes.data(), total + SPAN, cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(cudaStreamSynchronize(ctx->stream));
     for (uint32_t i = 0; i < n; i++) idx->maxLen = std::max<uint32_t>(idx->maxLen, (uint32_t)(off[i + 1] - off[i]));
     if (par->mask) idx->masked = tantanMaskAll(codes.data(), off, n, ctx->seedMat, (double)par->mask_prob);
 
@@ -751,7 +753,8 @@ extern "C" uint64_t sd_target_index_entries(const sd_target_index *idx) { return
 
 extern "C" int sd_target_index_masked(const sd_target_index *idx, uint8_t *out, uint64_t cap) {
     if (!idx || !out || cap < idx->totalRes) { setError("sd_target_index_masked: bad argument"); return SD_EINVAL; }
-    SD_CUDA(cudaMemcpy(out, idx->res.p, idx->totalRes, cudaMemcpyDeviceToHost));
+    SD_CUDA(cudaMemcpyAsync(out, idx->res.p, idx->totalRes, cudaMemcpyDeviceToHost, idx->ctx->stream));
+    SD_CUDA(cudaStreamSynchronize(idx->ctx->stream));
     return SD_OK;
 }
 
@@ -762,6 +765,7 @@ extern "C" int sd_query_batch_create(sd_context *ctx, const char *seqs, const ui
     for (uint32_t i = 0; i < n; i++)
         if (off[i + 1] - off[i] >= 32768) { setError("query %u longer than 32767 residues: long-sequence path not implemented", i); return SD_ELIMIT; }
     SD_CUDA(cudaSetDevice(ctx->device));
+    sd::StreamScope allocScope(ctx->stream);
     std::unique_ptr<sd_query_batch> b(new sd_query_batch());
     b->ctx = ctx; b->nq = n; b->total = total;
     b->hostOff.resize(n + 1);
@@ -803,6 +807,7 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     if (nq == 0) return SD_OK;
     const uint64_t total = queries->total;
     SD_CUDA(cudaSetDevice(ctx->device));
+    sd::StreamScope allocScope(ctx->stream);
     cudaStream_t st = ctx->stream;
     int rc;
     cudaEvent_t ev0, ev1, evk0, evk1;
@@ -847,11 +852,12 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     const uint32_t nWarps = nCta * PF_WARPS;
     const uint32_t candCap = 32768;
 
-    DevBuf<uint32_t> dTable, dResT, dOutCount, dNext;
-    DevBuf<uint64_t> dCand, dKeep;
-    DevBuf<int32_t> dResScore;
-    DevBuf<uint16_t> dResDiag;
-    DevBuf<sd_prefilter_hit> dOut;
+    ScratchBuf<uint32_t> dTable(ctx, SL_PF_TABLE), dResT(ctx, SL_PF_REST);
+    DevBuf<uint32_t> dOutCount, dNext;
+    ScratchBuf<uint64_t> dCand(ctx, SL_PF_CAND), dKeep(ctx, SL_PF_KEEP);
+    ScratchBuf<int32_t> dResScore(ctx, SL_PF_RESS);
+    ScratchBuf<uint16_t> dResDiag(ctx, SL_PF_RESD);
+    ScratchBuf<sd_prefilter_hit> dOut(ctx, SL_PF_OUT);
     DevBuf<unsigned long long> dStats;
     if ((rc = dTable.alloc((size_t)nWarps * idx->nT)) || (rc = dCand.alloc((size_t)nWarps * candCap)) || (rc = dKeep.alloc((size_t)nWarps * candCap)) ||
         (rc = dResT.alloc((size_t)nWarps * maxHits)) || (rc = dResScore.alloc((size_t)nWarps * maxHits)) || (rc = dResDiag.alloc((size_t)nWarps * maxHits)) ||

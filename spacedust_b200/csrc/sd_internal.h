@@ -6,7 +6,9 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sdgpu.h"
@@ -34,24 +36,39 @@ constexpr int SPAN = 10;                 // spaced seed 1101010011 (Sequence.h:2
 constexpr uint32_t N3 = 8000;            // 20^3
 constexpr uint32_t NKMER = 64000000;     // 20^6
 
+// Stream-ordered allocations: entry points set the calling context's stream (StreamScope); buffers then come from
+// the device's default memory pool (cudaMallocAsync), which keeps freed blocks for reuse -- no cudaMalloc/cudaFree
+// round trips in steady state.
+cudaStream_t &tlsAllocStream();
+struct StreamScope {
+    cudaStream_t prev;
+    explicit StreamScope(cudaStream_t s) : prev(tlsAllocStream()) { tlsAllocStream() = s; }
+    ~StreamScope() { tlsAllocStream() = prev; }
+};
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    cudaStream_t owner = nullptr;
+    bool async = false;
     int alloc(size_t count) {
         release();
         if (count == 0) count = 1;
-        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T));
+        cudaStream_t s = tlsAllocStream();
+        cudaError_t e;
+        if (s) { e = cudaMallocAsync(reinterpret_cast<void **>(&p), count * sizeof(T), s); async = true; owner = s; }
+        else { e = cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T)); async = false; }
         if (e != cudaSuccess) {
             p = nullptr;
-            setError("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            setError("device allocation of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
             return SD_ENOMEM;
         }
         n = count;
         return SD_OK;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) { if (async) cudaFreeAsync(p, owner); else cudaFree(p); }
         p = nullptr;
         n = 0;
     }
@@ -60,6 +77,54 @@ struct DevBuf {
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
 };
+
+enum ScratchSlot {
+    SL_PF_TABLE = 0, SL_PF_CAND, SL_PF_KEEP, SL_PF_REST, SL_PF_RESS, SL_PF_RESD, SL_PF_OUT, SL_PF_DENSE,
+    SL_AL_FWD, SL_AL_WORD, SL_AL_BIG, SL_AL_REV, SL_AL_RES, SL_AL_HITS, SL_AL_TB, SL_AL_TBRES, SL_AL_IDENT, SL_AL_ORDER,
+    SL_AL_PROFF, SL_AL_PROFR, SL_AL_BOUND, SL_AL_PAIRQ, SL_AL_PAIRT,
+    SL_TB_DIR, SL_TB_ROWS, SL_TB_REV, SL_TB_POOL, SL_COUNT
+};
+void *ctxDeviceScratch(sd_context *ctx, int slot, size_t bytes);     // nullptr + error message on failure
+void *ctxPinnedScratch(sd_context *ctx, int slot, size_t bytes);
+
+// DevBuf look-alike backed by a context slot (not freed when it goes out of scope)
+template <typename T>
+struct ScratchBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    sd_context *ctx;
+    int slot;
+    ScratchBuf(sd_context *c, int s) : ctx(c), slot(s) {}
+    int alloc(size_t count) {
+        if (count == 0) count = 1;
+        p = static_cast<T *>(ctxDeviceScratch(ctx, slot, count * sizeof(T)));
+        n = p ? count : 0;
+        return p ? SD_OK : SD_ENOMEM;
+    }
+    void release() {}
+};
+
+// run fn(i) for i in [0,n) on a pool of host threads (small per-item work, chunked)
+template <typename F>
+inline void parallelFor(uint64_t n, F fn) {
+    unsigned nThreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    if (n < 4096) nThreads = 1;
+    std::atomic<uint64_t> next{0};
+    const uint64_t chunk = 2048;
+    auto work = [&]() {
+        for (;;) {
+            const uint64_t lo = next.fetch_add(chunk);
+            if (lo >= n) break;
+            const uint64_t hi = std::min(n, lo + chunk);
+            for (uint64_t i = lo; i < hi; i++) fn(i);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nThreads; t++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+}
+
 
 struct SwBatch;
 struct SwTask;
@@ -76,6 +141,11 @@ uint32_t swWarpsPerCta();
 }  // namespace sd
 
 struct sd_context {
+    // persistent scratch: large per-call work buffers are kept between calls (slot = fixed purpose), so the steady
+    // state has no multi-GB allocations; released with the context
+    struct Slot { void *p = nullptr; size_t cap = 0; };
+    Slot devSlot[48];
+    Slot pinSlot[8];
     int device = 0;
     int smCount = 148;
     cudaStream_t stream = nullptr;
