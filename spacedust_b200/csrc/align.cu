@@ -344,7 +344,6 @@ __global__ void chainBuildForward(ChainArgs A) {
     SwTask tk;
     tk.q = q; tk.t = t; tk.nRows = Lq; tk.nCols = Lt; tk.limit = A.limit8[q]; tk.width = 32; tk.reverse = 0; tk.pad = 0;
     A.fwdTasks[atomicAdd(A.nFwd, 1u)] = tk;
-    atomicAdd(&A.classCount[17 - swClass(Lq)], 1u);
 }
 
 // largest class first; order inside a class is arbitrary (results are keyed by task)
@@ -596,43 +595,33 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
         SD_CUDA(cudaStreamSynchronize(st));
         return SD_OK;
     };
-    // one Smith-Waterman launch over a device task list, grouped by template class
-    auto runList = [&](SwTask *tasks, uint32_t n, bool classesCounted, int packed16, unsigned long long *cellSlot) -> int {
+    // one Smith-Waterman launch over a device task list (scheduling by class happens inside launchSw)
+    auto runList = [&](SwTask *tasks, uint32_t n, int packed16, int keyed, unsigned long long *cellSlot) -> int {
         if (n == 0) return SD_OK;
-        if (!classesCounted) {
-            SD_CUDA(cudaMemsetAsync(dClass.p, 0, 18 * sizeof(uint32_t), st));
-            chainCountClasses<<<gridOf(n, 256), 256, 0, st>>>(tasks, n, dClass.p);
-            ctx->launches++;
-        }
-        chainScanClasses<<<1, 32, 0, st>>>(dClass.p);
-        chainOrderByClass<<<gridOf(n, 256), 256, 0, st>>>(tasks, n, dClass.p, dOrder.p);
-        ctx->launches += 2;
-        SD_CUDA(cudaGetLastError());
         SD_CUDA(cudaEventRecord(evA, st));
-        int r2 = launchSw(ctx, batch, tasks, dOrder.p, dRes.p, n, dBoundary.p, bndStride, swWarps, dNext.p, cellSlot, packed16);
+        int r2 = launchSw(ctx, batch, tasks, dRes.p, n, dBoundary.p, bndStride, swWarps, dNext.p, cellSlot, packed16, keyed);
         if (r2) return r2;
         SD_CUDA(cudaEventRecord(evB, st));
         return lap(swMs);
     };
 
-    tick("alloc");
     chainBuildForward<<<gridOf(n_pairs, 256), 256, 0, st>>>(C);
     ctx->launches++;
     SD_CUDA(cudaGetLastError());
     if ((rc = readCounts())) return rc;
     tick("build");
     const uint32_t nFwd = hCnt[C_FWD];
-    if ((rc = runList(dFwd.p, nFwd, true, 1, dCells.p))) return rc;
+    if ((rc = runList(dFwd.p, nFwd, 1, 1, dCells.p))) return rc;
     if (nFwd) { chainAfterForward<<<gridOf(nFwd, 256), 256, 0, st>>>(C, dFwd.p, dRes.p, nFwd, 0); ctx->launches++; }
     if ((rc = readCounts())) return rc;
     tick("fwd8");
     const uint32_t nWord = hCnt[C_WORD];
-    if ((rc = runList(dWord.p, nWord, false, 1, dCells.p))) return rc;
+    if ((rc = runList(dWord.p, nWord, 1, 0, dCells.p))) return rc;
     if (nWord) { chainAfterForward<<<gridOf(nWord, 256), 256, 0, st>>>(C, dWord.p, dRes.p, nWord, 1); ctx->launches++; }
     if ((rc = readCounts())) return rc;
     uint32_t nBig = hCnt[C_BIG];
     if (nBig) {     // scores near 2^15: 32-bit pass
-        if ((rc = runList(dBig.p, nBig, false, 0, dCells.p))) return rc;
+        if ((rc = runList(dBig.p, nBig, 0, 0, dCells.p))) return rc;
         chainAfterForward<<<gridOf(nBig, 256), 256, 0, st>>>(C, dBig.p, dRes.p, nBig, 1);
         ctx->launches++;
         SD_CUDA(cudaMemsetAsync(dCnt.p + C_BIG, 0, sizeof(uint32_t), st));
@@ -640,12 +629,12 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     }
     tick("fwd16");
     const uint32_t nRev = hCnt[C_REV];
-    if ((rc = runList(dRev.p, nRev, false, 1, dCells.p + 1))) return rc;
+    if ((rc = runList(dRev.p, nRev, 1, 0, dCells.p + 1))) return rc;
     if (nRev) { chainAfterReverse<<<gridOf(nRev, 256), 256, 0, st>>>(C, dRev.p, dRes.p, nRev, 0); ctx->launches++; }
     if ((rc = readCounts())) return rc;
     nBig = hCnt[C_BIG];
     if (nBig) {
-        if ((rc = runList(dBig.p, nBig, false, 0, dCells.p + 1))) return rc;
+        if ((rc = runList(dBig.p, nBig, 0, 0, dCells.p + 1))) return rc;
         chainAfterReverse<<<gridOf(nBig, 256), 256, 0, st>>>(C, dBig.p, dRes.p, nBig, 1);
         ctx->launches++;
         if ((rc = readCounts())) return rc;

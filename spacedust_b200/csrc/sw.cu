@@ -12,6 +12,8 @@
 //   Ft / H   exact vertical-gap chain          -> what the reference ends up storing in H
 //   Fm / H1  chain reset at every segment start -> what feeds E
 // so scores, end points and the 8-bit overflow decision are bit-identical to the AVX2 build.
+#include <cub/cub.cuh>
+
 #include <climits>
 
 #include "sd_internal.h"
@@ -32,6 +34,7 @@ struct SwKernelArgs {
     uint32_t boundaryStride;
     unsigned long long *cells; // total DP cells computed
     int packed16;              // 1: packed 16-bit pass, 0: 32-bit pass (fallback for scores near 2^15)
+    const uint32_t *nRounds;   // packed pass: number of rounds in order[]
 };
 
 __device__ __forceinline__ uint32_t swLane() { return threadIdx.x & 31; }
@@ -207,31 +210,56 @@ __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)l
 __device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t v) { return (int)(short)(v >> 16); }
 
-template <int RP, bool KEYED>
-__device__ void swPass16(const SwKernelArgs &A, const SwTask &tk, int *bnd, SwResult &res, unsigned long long &cellCount) {
+// Scheduling classes of the packed pass: (lanes per pair, packed rows per stage).  Short queries use 8 lanes per pair
+// (4 pairs per warp, 16 wavefront stages), so every lane still owns enough rows to amortise the per-step work
+// (shuffles, profile fetch, maxima) and the pipeline fill is 15 columns instead of 63.
+__host__ __device__ inline int swClassOf(int nRows) {
+    if (nRows <= 320) { int rp = (nRows + 15) / 16; rp = (rp + 1) & ~1; if (rp < 2) rp = 2; return rp / 2 - 1; }       // 0..9 : 8 lanes, RP 2..20
+    if (nRows <= 640) { int rp = (nRows + 31) / 32; rp = (rp + 1) & ~1; return 10 + (rp - 12) / 2; }                     // 10..14: 16 lanes, RP 12..20
+    if (nRows <= 1280) { int rp = (nRows + 63) / 64; rp = (rp + 1) & ~1; return 15 + (rp - 12) / 2; }                   // 15..19: 32 lanes, RP 12..20
+    return 20;                                                                                                         // stripes of 1280 rows
+}
+__host__ __device__ inline int swClassTasksPerRound(int cls) { return cls < 10 ? 4 : (cls < 15 ? 2 : 1); }
+constexpr int SW_NCLASS = 21;
+
+template <int LANES, int RP, bool KEYED>
+__device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, unsigned long long &cellCount) {
     constexpr int NWA = (RP + 3) / 4;          // aligned words holding RP bytes
+    constexpr bool STRIPED = (LANES == 32);    // only whole-warp pairs may need more than one stripe
     const uint32_t lane = swLane();
+    const uint32_t gl = lane % LANES, grp = lane / LANES;
+    const uint32_t gmask = (LANES == 32) ? 0xffffffffu : (((1u << LANES) - 1u) << (grp * LANES));
+    const uint32_t id = A.order[(size_t)round * 4 + grp];
+    const bool have = id != 0xffffffffu;
+    SwTask tk;
+    if (have) tk = A.tasks[id];
+    else { tk.q = 0; tk.t = 0; tk.nRows = 0; tk.nCols = 0; tk.limit = INT_MAX; tk.width = 32; tk.reverse = 0; tk.pad = 0; }
     const int nRows = tk.nRows, nCols = tk.nCols;
-    const int segLen = (nRows + tk.width - 1) / tk.width;
+    const int segLen = have ? (nRows + tk.width - 1) / tk.width : 1;
     const uint32_t negGo = pack16(-A.b.gapOpen, -A.b.gapOpen), negGe = pack16(-A.b.gapExtend, -A.b.gapExtend);
-    const uint32_t Lq = A.b.qLen[tk.q];
-    const uint32_t stride = A.b.profStride[tk.q];
-    const int8_t *prof = (tk.reverse ? A.b.profRev : A.b.profFwd) + A.b.profOff[tk.q];
+    const uint32_t Lq = have ? A.b.qLen[tk.q] : 0u;
+    const uint32_t stride = have ? A.b.profStride[tk.q] : 0u;
+    const int8_t *prof = (tk.reverse ? A.b.profRev : A.b.profFwd) + (have ? A.b.profOff[tk.q] : 0ull);
     const uint32_t rowOffset = tk.reverse ? (Lq - (uint32_t)nRows) : 0u;
-    const uint8_t *T = A.b.tRes + A.b.tOff[tk.t];
+    const uint8_t *T = A.b.tRes + (have ? A.b.tOff[tk.t] : 0u);
+    const int lim = tk.limit != INT_MAX ? tk.limit : SW16_GUARD;
 
     int bestA = 0, bestB = 0, colA = INT_MAX, colB = INT_MAX, rowA = INT_MAX, rowB = INT_MAX;
     bool overflow = false;
     int pingpong = 0;
+    // every group runs the longest group's step count (shuffles are warp-wide)
+    const int mySteps = have ? nCols + 2 * LANES - 1 : 0;
+    const int warpSteps = (int)__reduce_max_sync(0xffffffffu, (unsigned)mySteps);
+    const int nStripes = STRIPED ? (int)__reduce_max_sync(0xffffffffu, (unsigned)((nRows + 64 * RP - 1) / (64 * RP))) : 1;
 
-    for (int stripe0 = 0; stripe0 < nRows && !overflow; stripe0 += 64 * RP) {
-        const bool hasPrev = stripe0 > 0;
-        const bool hasNext = stripe0 + 64 * RP < nRows;
-        const int i0 = stripe0 + (int)lane * 2 * RP;          // stage A rows [i0, i0+RP), stage B rows [i0+RP, i0+2RP)
-        const bool laneHasRows = i0 < nRows;
+    for (int stripe = 0; stripe < nStripes; stripe++) {
+        const int stripe0 = stripe * 64 * RP;
+        const bool hasPrev = STRIPED && stripe0 > 0;
+        const bool hasNext = STRIPED && stripe0 + 64 * RP < nRows;
+        const int i0 = stripe0 + (int)gl * 2 * RP;             // stage A rows [i0, i0+RP), stage B rows [i0+RP, i0+2RP)
+        const bool laneHasRows = have && i0 < nRows && !overflow;
         const int *bndIn = bnd + (size_t)pingpong * 3 * A.boundaryStride;
         int *bndOut = bnd + (size_t)(pingpong ^ 1) * 3 * A.boundaryStride;
-        // per packed row: 0xffff where the segment-local chain continues, 0 where a new segment starts
         uint32_t segKeep[RP];
 #pragma unroll
         for (int k = 0; k < RP; k++) {
@@ -246,40 +274,39 @@ __device__ void swPass16(const SwKernelArgs &A, const SwTask &tk, int *bnd, SwRe
         uint32_t H[RP], E[RP];
 #pragma unroll
         for (int k = 0; k < RP; k++) { H[k] = 0; E[k] = 0; }
-        uint32_t prevHup = 0;                                  // packed H of the row above, previous column
+        uint32_t prevHup = 0;
         uint32_t outL = pack16(SW_DUMMY_LETTER, SW_DUMMY_LETTER), outH = 0, outFt = 0, outFm = 0;
-        int tChunk = 0, bH = 0, bFt = 0, bFm = 0;
-        const int nSteps = nCols + 63;
+        int tChunk = SW_DUMMY_LETTER, bH = 0, bFt = 0, bFm = 0;
 
-        for (int s = 0; s < nSteps; s++) {
-            if ((s & 31) == 0) {
-                const int c = s + (int)lane;
-                tChunk = (c < nCols) ? (int)T[tk.reverse ? (nCols - 1 - c) : c] : SW_DUMMY_LETTER;
+        for (int s = 0; s < warpSteps; s++) {
+            if ((s % LANES) == 0) {
+                const int c = s + (int)gl;
+                tChunk = (have && c < nCols) ? (int)T[tk.reverse ? (nCols - 1 - c) : c] : SW_DUMMY_LETTER;
                 if (hasPrev) {
                     bH = (c < nCols) ? bndIn[c] : 0;
                     bFt = (c < nCols) ? bndIn[A.boundaryStride + c] : 0;
                     bFm = (c < nCols) ? bndIn[2 * A.boundaryStride + c] : 0;
                 }
             }
-            // stage A takes what the previous lane's stage B produced, stage B what this lane's stage A produced
-            uint32_t upL = __shfl_up_sync(0xffffffffu, outL, 1) >> 16;
-            uint32_t upH = __shfl_up_sync(0xffffffffu, outH, 1) >> 16;
-            uint32_t upFt = __shfl_up_sync(0xffffffffu, outFt, 1) >> 16;
-            uint32_t upFm = __shfl_up_sync(0xffffffffu, outFm, 1) >> 16;
-            const int a0 = __shfl_sync(0xffffffffu, tChunk, s & 31);
+            uint32_t upL = __shfl_up_sync(0xffffffffu, outL, 1, LANES) >> 16;
+            uint32_t upH = __shfl_up_sync(0xffffffffu, outH, 1, LANES) >> 16;
+            uint32_t upFt = __shfl_up_sync(0xffffffffu, outFt, 1, LANES) >> 16;
+            uint32_t upFm = __shfl_up_sync(0xffffffffu, outFm, 1, LANES) >> 16;
+            const int a0 = __shfl_sync(0xffffffffu, tChunk, s % LANES, LANES);
             int h0 = 0, ft0 = 0, fm0 = 0;
-            if (hasPrev) {
-                h0 = __shfl_sync(0xffffffffu, bH, s & 31);
-                ft0 = __shfl_sync(0xffffffffu, bFt, s & 31);
-                fm0 = __shfl_sync(0xffffffffu, bFm, s & 31);
+            if (STRIPED && nStripes > 1) {
+                h0 = __shfl_sync(0xffffffffu, bH, s % LANES, LANES);
+                ft0 = __shfl_sync(0xffffffffu, bFt, s % LANES, LANES);
+                fm0 = __shfl_sync(0xffffffffu, bFm, s % LANES, LANES);
+                if (!hasPrev) { h0 = 0; ft0 = 0; fm0 = 0; }
             }
-            if (lane == 0) { upL = (uint32_t)a0; upH = (uint32_t)h0 & 0xffffu; upFt = (uint32_t)ft0 & 0xffffu; upFm = (uint32_t)fm0 & 0xffffu; }
+            if (gl == 0) { upL = (uint32_t)a0; upH = (uint32_t)h0 & 0xffffu; upFt = (uint32_t)ft0 & 0xffffu; upFm = (uint32_t)fm0 & 0xffffu; }
             const uint32_t inL = upL | (outL << 16);
             const uint32_t inH = upH | (outH << 16);
             const uint32_t inFt = upFt | (outFt << 16);
             const uint32_t inFm = upFm | (outFm << 16);
-            const int cA = s - 2 * (int)lane;
-            if (cA >= 0 && cA <= nCols && laneHasRows) {        // stage A in [0,nCols), stage B = cA-1 in [-1,nCols)
+            const int cA = s - 2 * (int)gl;
+            if (cA >= 0 && cA <= nCols && laneHasRows && !overflow) {   // stage A column cA in [0,nCols), stage B column cA-1
                 const uint32_t letA = inL & 0xffffu, letB = inL >> 16;
                 const uint32_t *wa = (const uint32_t *)((addrA + (uintptr_t)letA * stride) & ~(uintptr_t)3);
                 const uint32_t *wb = (const uint32_t *)((addrB + (uintptr_t)letB * stride) & ~(uintptr_t)3);
@@ -297,7 +324,6 @@ __device__ void swPass16(const SwKernelArgs &A, const SwTask &tk, int *bnd, SwRe
                 uint32_t colMax = 0;
 #pragma unroll
                 for (int k = 0; k < RP; k++) {
-                    // sign-extended score bytes of both stages -> s16x2 (one PRMT)
                     const uint32_t sel = (uint32_t)(k & 3) | ((uint32_t)((k & 3) | 8) << 4) | ((uint32_t)(4 + (k & 3)) << 8) | ((uint32_t)((4 + (k & 3)) | 8) << 12);
                     const uint32_t sv = prmtSext(sa[k >> 2], sb[k >> 2], sel);
                     const uint32_t e = E[k];
@@ -307,8 +333,8 @@ __device__ void swPass16(const SwKernelArgs &A, const SwTask &tk, int *bnd, SwRe
                     const uint32_t hs = max16x2(h, ft);
                     diag = H[k];
                     H[k] = hs;
-                    // KEYED (8-bit semantics, H < 2^11): the key H*16 + (15-k) orders by score, then by smallest row
-                    colMax = max16x2(colMax, KEYED ? (hs * 16u + (uint32_t)((15 - k) * 0x10001)) : hs);
+                    // KEYED (8-bit semantics, H < 2^10): key H*32 + (31-k) orders by score, then by smallest row
+                    colMax = max16x2(colMax, KEYED ? (hs * 32u + (uint32_t)((31 - k) * 0x10001)) : hs);
                     const uint32_t open1 = __viaddmax_s16x2_relu(h1, negGo, 0u);
                     E[k] = __viaddmax_s16x2(e, negGe, open1);
                     fm = __viaddmax_s16x2(fm, negGe, open1);
@@ -318,13 +344,12 @@ __device__ void swPass16(const SwKernelArgs &A, const SwTask &tk, int *bnd, SwRe
                 outL = inL; outH = H[RP - 1]; outFt = ft; outFm = fm;
                 prevHup = inH;
                 if (KEYED) {
-                    // branch-free: (score, column, row) per stage; columns only grow inside a stripe and KEYED tasks have one stripe
                     const int kA = lo16(colMax), kB = hi16(colMax);
-                    const int mA = kA >> 4, mB = kB >> 4;
+                    const int mA = kA >> 5, mB = kB >> 5;
                     const bool upA = mA > bestA && cA < nCols;
                     const bool upB = mB > bestB && cA >= 1;
-                    bestA = upA ? mA : bestA; colA = upA ? cA : colA; rowA = upA ? i0 + 15 - (kA & 15) : rowA;
-                    bestB = upB ? mB : bestB; colB = upB ? cA - 1 : colB; rowB = upB ? i0 + RP + 15 - (kB & 15) : rowB;
+                    bestA = upA ? mA : bestA; colA = upA ? cA : colA; rowA = upA ? i0 + 31 - (kA & 31) : rowA;
+                    bestB = upB ? mB : bestB; colB = upB ? cA - 1 : colB; rowB = upB ? i0 + RP + 31 - (kB & 31) : rowB;
                 } else {
                     const int mA = lo16(colMax), mB = hi16(colMax);
                     if (mA >= bestA && mA > 0 && cA < nCols) {
@@ -344,40 +369,105 @@ __device__ void swPass16(const SwKernelArgs &A, const SwTask &tk, int *bnd, SwRe
                         }
                     }
                 }
-                if (hasNext && lane == 31 && cA >= 1) {
+                if (hasNext && gl == LANES - 1 && cA >= 1) {
                     bndOut[cA - 1] = hi16(outH);
                     bndOut[A.boundaryStride + cA - 1] = hi16(outFt);
                     bndOut[2 * A.boundaryStride + cA - 1] = hi16(outFm);
                 }
             }
             if ((s & 31) == 31) {
-                const int lim = tk.limit != INT_MAX ? tk.limit : SW16_GUARD;
-                if (__any_sync(0xffffffffu, max(bestA, bestB) >= lim)) { overflow = true; break; }
+                const uint32_t hit = __ballot_sync(0xffffffffu, max(bestA, bestB) >= lim);
+                if (hit & gmask) overflow = true;      // this pair is decided; its lanes idle until the round ends
+                if (__all_sync(0xffffffffu, overflow || !have)) break;
             }
         }
-        cellCount += (lane == 0) ? (unsigned long long)min(nRows - stripe0, 64 * RP) * (unsigned long long)nCols : 0ull;
+        cellCount += (have && gl == 0 && stripe0 < nRows) ? (unsigned long long)min(nRows - stripe0, 64 * RP) * (unsigned long long)nCols : 0ull;
         pingpong ^= 1;
         __syncwarp();
     }
-    // stage B rows lie below stage A rows: merge the two stages, then the lanes
     int best = bestA, bestCol = colA, bestRow = rowA;
     if (bestB > best || (bestB == best && (colB < bestCol || (colB == bestCol && rowB < bestRow)))) { best = bestB; bestCol = colB; bestRow = rowB; }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        const int b2 = __shfl_down_sync(0xffffffffu, best, d);
-        const int c2 = __shfl_down_sync(0xffffffffu, bestCol, d);
-        const int r2 = __shfl_down_sync(0xffffffffu, bestRow, d);
+    for (int d = LANES / 2; d > 0; d >>= 1) {
+        const int b2 = __shfl_down_sync(0xffffffffu, best, d, LANES);
+        const int c2 = __shfl_down_sync(0xffffffffu, bestCol, d, LANES);
+        const int r2 = __shfl_down_sync(0xffffffffu, bestRow, d, LANES);
         if (b2 > best || (b2 == best && (c2 < bestCol || (c2 == bestCol && r2 < bestRow)))) { best = b2; bestCol = c2; bestRow = r2; }
     }
-    best = __shfl_sync(0xffffffffu, best, 0);
-    const int lim = tk.limit != INT_MAX ? tk.limit : SW16_GUARD;
+    best = __shfl_sync(0xffffffffu, best, 0, LANES);
     if (!overflow && best >= lim) overflow = true;
-    if (lane == 0) {
+    if (have && gl == 0) {
+        SwResult res;
         res.score = best;
         res.col = best > 0 ? bestCol : -1;
         res.row = best > 0 ? bestRow : -1;
         res.overflow = overflow ? (tk.limit != INT_MAX ? 1 : 2) : 0;     // 2: needs the 32-bit pass
+        A.results[id] = res;
     }
+}
+
+// packed pass: one round = up to four pairs of the same scheduling class (order[] is laid out in rounds of 4 slots)
+template <bool KEYED>
+__global__ void __launch_bounds__(SW_WARPS * 32) swKernel16(SwKernelArgs A) {
+    const uint32_t lane = swLane();
+    const uint32_t warp = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
+    int *bnd = A.boundary + (size_t)warp * 6 * A.boundaryStride;
+    unsigned long long cells = 0;
+    const uint32_t nRounds = *A.nRounds;
+    for (;;) {
+        uint32_t round = 0;
+        if (lane == 0) round = atomicAdd(A.next, 1u);
+        round = __shfl_sync(0xffffffffu, round, 0);
+        if (round >= nRounds) break;
+        const uint32_t id0 = A.order[(size_t)round * 4];      // slot 0 of a round is always a real task
+        const int cls = swClassOf(A.tasks[id0].nRows);
+#define SD_G(L, N) swGroupPass<L, N, KEYED>(A, round, bnd, cells); break;
+        switch (cls) {
+            case 0: SD_G(8, 2) case 1: SD_G(8, 4) case 2: SD_G(8, 6) case 3: SD_G(8, 8) case 4: SD_G(8, 10)
+            case 5: SD_G(8, 12) case 6: SD_G(8, 14) case 7: SD_G(8, 16) case 8: SD_G(8, 18) case 9: SD_G(8, 20)
+            case 10: SD_G(16, 12) case 11: SD_G(16, 14) case 12: SD_G(16, 16) case 13: SD_G(16, 18) case 14: SD_G(16, 20)
+            case 15: SD_G(32, 12) case 16: SD_G(32, 14) case 17: SD_G(32, 16) case 18: SD_G(32, 18)
+            default: SD_G(32, 20)
+        }
+#undef SD_G
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cells += __shfl_down_sync(0xffffffffu, cells, d);    // group leaders counted their pairs
+    if (lane == 0 && cells) atomicAdd(A.cells, cells);
+}
+
+// ---- scheduling: sort tasks by (class desc, columns), lay them out in class-pure rounds of 4 slots
+__global__ void swScheduleKeys(const SwTask *tasks, uint32_t n, uint32_t *keys, uint32_t *vals, uint32_t *classCount) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cls = swClassOf(tasks[i].nRows);
+    keys[i] = ((uint32_t)(SW_NCLASS - 1 - cls) << 16) | (uint32_t)min(tasks[i].nCols, 65535);
+    vals[i] = i;
+    atomicAdd(&classCount[SW_NCLASS - 1 - cls], 1u);
+}
+
+// classInfo: [0..20] counts (in), -> [0..20] first sorted position, [32..52] first round, [64] number of rounds
+__global__ void swScheduleBases(uint32_t *classInfo) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t pos = 0, round = 0;
+    for (int cc = 0; cc < SW_NCLASS; cc++) {
+        const uint32_t cnt = classInfo[cc];
+        const uint32_t tpr = (uint32_t)swClassTasksPerRound(SW_NCLASS - 1 - cc);
+        classInfo[cc] = pos;
+        classInfo[32 + cc] = round;
+        pos += cnt;
+        round += (cnt + tpr - 1) / tpr;
+    }
+    classInfo[64] = round;
+}
+
+__global__ void swScheduleFill(const uint32_t *sortedKeys, const uint32_t *sortedVals, uint32_t n, const uint32_t *classInfo, uint32_t *order) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t cc = sortedKeys[p] >> 16;
+    const uint32_t r = p - classInfo[cc];
+    const uint32_t tpr = (uint32_t)swClassTasksPerRound(SW_NCLASS - 1 - (int)cc);
+    order[(size_t)(classInfo[32 + cc] + r / tpr) * 4 + (r % tpr)] = sortedVals[p];
 }
 
 template <bool PACKED>
@@ -395,22 +485,7 @@ __global__ void __launch_bounds__(SW_WARPS * 32) swKernel(SwKernelArgs A) {
         const SwTask tk = A.tasks[id];
         SwResult r;
         if (PACKED) {
-            const int rp = (tk.nRows + 63) / 64;
-            // 8-bit semantics on a single stripe: branch-free keyed maxima; everything else: generic tracking
-            const bool keyed = tk.limit != INT_MAX && rp <= 16;
-#define SD_SW16(N) { if (keyed) swPass16<N, true>(A, tk, bnd, r, cells); else swPass16<N, false>(A, tk, bnd, r, cells); }
-            if (rp <= 1) SD_SW16(1)
-            else if (rp == 2) SD_SW16(2)
-            else if (rp == 3) SD_SW16(3)
-            else if (rp == 4) SD_SW16(4)
-            else if (rp == 5) SD_SW16(5)
-            else if (rp == 6) SD_SW16(6)
-            else if (rp == 7) SD_SW16(7)
-            else if (rp == 8) SD_SW16(8)
-            else if (rp <= 10) SD_SW16(10)
-            else if (rp <= 12) SD_SW16(12)
-            else SD_SW16(16)
-#undef SD_SW16
+            r.score = 0; r.col = -1; r.row = -1; r.overflow = 0;   // unused: the packed pass is swKernel16
         } else {
             const int rowsPerLane = (tk.nRows + 31) / 32;
             if (rowsPerLane <= 4) swPass<4>(A, tk, bnd, r, cells);
@@ -460,20 +535,50 @@ __global__ void alignCompositionBias(const float *__restrict__ bias, uint32_t to
     cb[gp] = (int8_t)(int)v;
 }
 
-int launchSw(sd_context *ctx, const SwBatch &batch, const SwTask *dTasks, const uint32_t *dOrder, SwResult *dResults,
-             uint32_t nTasks, int *dBoundary, uint32_t boundaryStride, uint32_t nWarpsAllocated, uint32_t *dNext,
-             unsigned long long *dCells, int packed16) {
+int launchSw(sd_context *ctx, const SwBatch &batch, const SwTask *dTasks, SwResult *dResults, uint32_t nTasks, int *dBoundary,
+             uint32_t boundaryStride, uint32_t nWarpsAllocated, uint32_t *dNext, unsigned long long *dCells, int packed16, int keyed) {
     if (nTasks == 0) return SD_OK;
+    cudaStream_t st = ctx->stream;
     SwKernelArgs A;
-    A.b = batch; A.tasks = dTasks; A.order = dOrder; A.results = dResults; A.nTasks = nTasks; A.next = dNext;
-    A.boundary = dBoundary; A.boundaryStride = boundaryStride; A.cells = dCells; A.packed16 = packed16;
-    SD_CUDA(cudaMemsetAsync(dNext, 0, sizeof(uint32_t), ctx->stream));
+    A.b = batch; A.tasks = dTasks; A.order = nullptr; A.results = dResults; A.nTasks = nTasks; A.next = dNext;
+    A.boundary = dBoundary; A.boundaryStride = boundaryStride; A.cells = dCells; A.packed16 = packed16; A.nRounds = nullptr;
+    SD_CUDA(cudaMemsetAsync(dNext, 0, sizeof(uint32_t), st));
     uint32_t nCta = std::min<uint32_t>(nWarpsAllocated / SW_WARPS, (nTasks + SW_WARPS - 1) / SW_WARPS);
     if (nCta == 0) nCta = 1;
-    if (packed16) swKernel<true><<<nCta, SW_WARPS * 32, 0, ctx->stream>>>(A);
-    else swKernel<false><<<nCta, SW_WARPS * 32, 0, ctx->stream>>>(A);
+    if (!packed16) {
+        swKernel<false><<<nCta, SW_WARPS * 32, 0, st>>>(A);
+        ctx->launches++;
+        SD_CUDA(cudaGetLastError());
+        return SD_OK;
+    }
+    // schedule: (class desc, columns) order, class-pure rounds of four slots
+    ScratchBuf<uint32_t> keysA(ctx, SL_SW_KEYA), keysB(ctx, SL_SW_KEYB), valsA(ctx, SL_SW_VALA), valsB(ctx, SL_SW_VALB), order(ctx, SL_SW_ORDER);
+    ScratchBuf<uint8_t> tmp(ctx, SL_SW_TMP);
+    DevBuf<uint32_t> info;
+    int rc;
+    const size_t orderSlots = (size_t)nTasks * 4 + 4 * SW_NCLASS + 16;
+    if ((rc = keysA.alloc(nTasks)) || (rc = keysB.alloc(nTasks)) || (rc = valsA.alloc(nTasks)) || (rc = valsB.alloc(nTasks)) ||
+        (rc = order.alloc(orderSlots)) || (rc = info.alloc(128)))
+        return rc;
+    SD_CUDA(cudaMemsetAsync(info.p, 0, 128 * sizeof(uint32_t), st));
+    SD_CUDA(cudaMemsetAsync(order.p, 0xff, orderSlots * sizeof(uint32_t), st));
+    swScheduleKeys<<<(nTasks + 255) / 256, 256, 0, st>>>(dTasks, nTasks, keysA.p, valsA.p, info.p);
+    size_t tmpBytes = 0;
+    SD_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keysA.p, keysB.p, valsA.p, valsB.p, (int64_t)nTasks, 0, 21, st));
+    if ((rc = tmp.alloc(tmpBytes))) return rc;
+    SD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, keysA.p, keysB.p, valsA.p, valsB.p, (int64_t)nTasks, 0, 21, st));
+    swScheduleBases<<<1, 32, 0, st>>>(info.p);
+    swScheduleFill<<<(nTasks + 255) / 256, 256, 0, st>>>(keysB.p, valsB.p, nTasks, info.p, order.p);
+    ctx->launches += 3;
+    SD_CUDA(cudaGetLastError());
+    A.order = order.p;
+    A.nRounds = info.p + 64;
+    nCta = std::max<uint32_t>(1u, nWarpsAllocated / SW_WARPS);
+    if (keyed) swKernel16<true><<<nCta, SW_WARPS * 32, 0, st>>>(A);
+    else swKernel16<false><<<nCta, SW_WARPS * 32, 0, st>>>(A);
     ctx->launches++;
     SD_CUDA(cudaGetLastError());
+    SD_CUDA(cudaStreamSynchronize(st));      // info (DevBuf) is released when this returns
     return SD_OK;
 }
 
