@@ -338,7 +338,10 @@ def run_ours(args, proteomes, rank, world, local_rank):
                              "algorithmic_bytes_per_launch": int(algo),
                              "bytes_formula": "8*P + 6*M + R + 21*Lq + 10*H (SURVEY.md 8d), P/M/R/H counted by the kernel and "
                                               "equal to the oracle's counts (tests/test_prefilter_gpu.py)",
-                             "kernel_ms": k_ms},
+                             "kernel_ms": k_ms,
+                             "counts": {"P_probes": int(pst["probes"]), "M_index_entries": int(pst["matches"]),
+                                        "R_diag_residues": int(pst["diag_residues"]), "Lq_residues": int(pst["query_residues"]),
+                                        "H_hits": int(pst["hits"]), "diag_candidates": int(pst["candidates"])}},
                 "sw": {"gcups": cells / 1e9 / (ast["sw_ms"] / 1e3) if ast["sw_ms"] > 0 else 0.0, "cells": int(cells),
                        "kernel_ms": ast["sw_ms"], "pairs": int(ast["alignments"]), "hbm_gbs_algorithmic":
                        (int(ast["alignments"]) * 380.0) / 1e9 / (ast["sw_ms"] / 1e3) if ast["sw_ms"] > 0 else 0.0},

@@ -80,6 +80,7 @@ extern "C" void sd_context_destroy(sd_context *ctx) {
     for (auto &sl : ctx->pinSlot) if (sl.p) cudaFreeHost(sl.p);
     ctx->e3score.release();
     ctx->e3index.release();
+    ctx->e3cnt.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

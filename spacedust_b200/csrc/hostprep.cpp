@@ -191,8 +191,9 @@ int kmerThreshold(float sensitivity, int kmerSize) {
     return static_cast<int>(best);
 }
 
-void buildExt3(const SubMat &seedMat, std::vector<int16_t> &score, std::vector<uint16_t> &index) {
+void buildExt3(const SubMat &seedMat, std::vector<int16_t> &score, std::vector<uint16_t> &index, std::vector<uint16_t> &cntGE) {
     constexpr int N3 = 8000;
+    cntGE.resize(static_cast<size_t>(N3) * 512);
     score.resize(static_cast<size_t>(N3) * N3);
     index.resize(static_cast<size_t>(N3) * N3);
     // pair tables first: s2[x0,x1][y0,y1] would be 160k entries; the triple loop below is cheap enough
@@ -218,7 +219,8 @@ void buildExt3(const SubMat &seedMat, std::vector<int16_t> &score, std::vector<u
                         }
                     }
                 int base = 0;
-                for (int h = 0; h < 512; h++) { const int c = histo[h]; histo[h] = base; base += c; }
+                uint16_t *outC = cntGE.data() + static_cast<size_t>(xr) * 512;    // outC[255 - v] = #neighbours with score >= v
+                for (int h = 0; h < 512; h++) { const int c = histo[h]; histo[h] = base; base += c; outC[h] = static_cast<uint16_t>(base); }
                 int16_t *outS = score.data() + static_cast<size_t>(xr) * N3;
                 uint16_t *outI = index.data() + static_cast<size_t>(xr) * N3;
                 e = 0;

@@ -37,7 +37,8 @@ int kmerThreshold(float sensitivity, int kmerSize);
 
 // ExtendedSubstitutionMatrix::calcScoreMatrix for 3-mers (ExtendedSubstitutionMatrix.cpp:20-69):
 // row x = all 8000 3-mers ordered by score desc, ties in first-letter-major enumeration order.
-void buildExt3(const SubMat &seedMat, std::vector<int16_t> &score, std::vector<uint16_t> &index);
+// cntGE[x*512 + 255 - v] = number of 3-mers whose score against x is >= v  (v in [-256,255])
+void buildExt3(const SubMat &seedMat, std::vector<int16_t> &score, std::vector<uint16_t> &index, std::vector<uint16_t> &cntGE);
 
 // QueryMatcher::initDiagonalMatcher (QueryMatcher.cpp:422-449) + Util::getL2CacheSize (Util.cpp:317-332)
 int referenceBinSize(uint64_t nTargets);

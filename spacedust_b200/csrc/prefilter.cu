@@ -56,6 +56,23 @@ __device__ __forceinline__ uint32_t warpFindOwner(uint32_t excl, uint32_t x) {
     return lo;
 }
 
+// Owner of slot (base + lane) in a warp-wide segmented range: lane j owns slots [excl[j], excl[j] + len[j]).
+// Requires the lanes with len != 0 to form a prefix of the warp (then rank among them == lane index): one ballot for
+// the segments that start at or before `base`, one warp OR-reduction (REDUX) for the heads inside the 32-slot window.
+__device__ __forceinline__ uint32_t warpOwnerOfSlot(uint32_t excl, bool nonEmpty, uint32_t base, uint32_t lane) {
+    const uint32_t before = __ballot_sync(0xffffffffu, nonEmpty && excl <= base);
+    const uint32_t rel = excl - base;
+    const uint32_t heads = __reduce_or_sync(0xffffffffu, (nonEmpty && rel - 1u < 31u) ? (1u << rel) : 0u);
+    return (uint32_t)__popc(before) - 1u + (uint32_t)__popc(heads & (0xffffffffu >> (31u - lane)));
+}
+
+// number of neighbours of 3-mer x with score >= v (cumulative table built with the sorted rows)
+__device__ __forceinline__ uint32_t countGE(const uint16_t *__restrict__ cnt, uint32_t x, int v) {
+    if (v > 255) return 0u;
+    if (v < -256) return N3;
+    return (uint32_t)__ldg(&cnt[(size_t)x * 512 + (uint32_t)(255 - v)]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // index build
 // ------------------------------------------------------------------------------------------------
@@ -99,13 +116,42 @@ __global__ void firstOccurrence(const uint64_t *__restrict__ sorted, uint32_t n,
     if (keep) atomicAdd(&kCount[kmer], 1u);
 }
 
-__global__ void splitEntries(const uint64_t *__restrict__ payload, uint64_t n, uint32_t *__restrict__ entSeq,
-                             uint16_t *__restrict__ entPos) {
+__global__ void packEntries(const uint64_t *__restrict__ payload, uint64_t n, uint2 *__restrict__ ent) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t v = payload[i];
-    entSeq[i] = (uint32_t)(v >> 16);
-    entPos[i] = (uint16_t)(v & 0xffffu);
+    ent[i] = make_uint2((uint32_t)(v >> 16), (uint32_t)(v & 0xffffu));
+}
+
+// Occupancy bitmap of the k-mer space: one warp turns 32x32 bucket sizes into 32 words (coalesced reads of kOff).
+// bm[w].x = bits of k-mers 32w..32w+31 with a non-empty bucket; .y (filled by the scan below) = number of non-empty
+// k-mers before 32w, i.e. the row of the compact offset table.  16 MB for 20^6 k-mers: stays in the 126 MB L2, so an
+// empty probe never reaches HBM.
+__global__ void occupancyBits(const uint32_t *__restrict__ kOff, uint32_t nWords, uint32_t *__restrict__ bits,
+                              uint32_t *__restrict__ cnt) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w0 = warp * 32;
+    if (w0 >= nWords) return;
+    uint32_t mine = 0;
+    for (uint32_t j = 0; j < 32 && w0 + j < nWords; j++) {
+        const uint32_t k = (w0 + j) * 32 + lane;
+        const bool full = (k < NKMER) && (kOff[k + 1] != kOff[k]);
+        const uint32_t b = __ballot_sync(0xffffffffu, full);
+        if (j == lane) mine = b;
+    }
+    if (w0 + lane < nWords) { bits[w0 + lane] = mine; cnt[w0 + lane] = __popc(mine); }
+}
+
+__global__ void compactOffsets(const uint32_t *__restrict__ kOff, const uint32_t *__restrict__ bits,
+                               const uint32_t *__restrict__ rank, uint32_t nWords, uint2 *__restrict__ bm,
+                               uint32_t *__restrict__ cOff) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t w = k >> 5;
+    if (w >= nWords) return;
+    const uint32_t b = bits[w], r = rank[w];
+    if ((k & 31) == 0) bm[w] = make_uint2(b, r);
+    if (k < NKMER && ((b >> (k & 31)) & 1u)) cOff[r + __popc(b & ((1u << (k & 31)) - 1u))] = kOff[k];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -162,17 +208,26 @@ __global__ void kmerThresholds(const uint8_t *__restrict__ code, const uint32_t 
 // ------------------------------------------------------------------------------------------------
 constexpr int PF_WARPS = 8;              // warps per CTA
 constexpr int PF_CAP2 = 1024;            // staged prefix of the second 3-mer's neighbour row
+constexpr int PF_UNROLL = 4;             // probe steps in flight per warp (independent bitmap loads)
+constexpr uint32_t PF_Q1CAP = 256;       // ring 1 (non-empty buckets): up to 32*PF_UNROLL pushes between drains
+constexpr uint32_t PF_Q2CAP = 128;       // ring 2 (index hits)
+constexpr uint32_t PF_QDRAIN = 96;       // a stage runs when its ring holds this many: popped items were prefetched >= 64 pushes ago
+constexpr size_t PF_DYN_SMEM = (size_t)PF_WARPS * (PF_Q1CAP + PF_Q2CAP) * (sizeof(uint32_t) + sizeof(uint16_t));
+static_assert(PF_QDRAIN - 1 + 32 * PF_UNROLL <= PF_Q1CAP && PF_QDRAIN - 1 + 32 <= PF_Q2CAP, "ring capacity");
+
+__device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 struct PrefilterArgs {
     // target side
     const uint8_t *tRes;
     const uint32_t *tOff;
     uint32_t nT;
-    const uint32_t *kOff;
-    const uint32_t *entSeq;
-    const uint16_t *entPos;
+    const uint2 *bm;           // per 32 k-mers: occupancy bits, rank of the first one (L2 resident)
+    const uint32_t *cOff;      // bucket starts of the non-empty k-mers (+ sentinel)
+    const uint2 *ent;          // bucket entries: (target id, first position of the k-mer in that target)
     const int16_t *e3score;
     const uint16_t *e3index;
+    const uint16_t *e3cnt;     // [8000][512] cumulative counts: e3cnt[x*512 + 255 - v] = #{y : score(x,y) >= v}
     const int8_t *diagSub;     // 21x21 BLOSUM62 x2 (-0.2)
     // query side
     QueryBatchDev q;
@@ -231,10 +286,10 @@ __device__ int diagonalScore(const PrefilterArgs &a, const int8_t *sSub, uint32_
 }
 
 __global__ void __launch_bounds__(PF_WARPS * 32) prefilterKernel(PrefilterArgs a) {
-    __shared__ int16_t sS2[PF_WARPS][PF_CAP2];
     __shared__ uint16_t sX2[PF_WARPS][PF_CAP2];
     __shared__ uint32_t sHist[PF_WARPS][256];
     __shared__ int8_t sSub[AA * AA];
+    extern __shared__ __align__(16) uint8_t sDyn[];    // stage rings: [warp][Q1c | Q2t | Q1p | Q2d]
 
     for (int i = threadIdx.x; i < AA * AA; i += blockDim.x) sSub[i] = a.diagSub[i];
     __syncthreads();
@@ -249,9 +304,12 @@ __global__ void __launch_bounds__(PF_WARPS * 32) prefilterKernel(PrefilterArgs a
     uint32_t *resT = a.resT + (size_t)warp * a.maxHits;
     int32_t *resScore = a.resScore + (size_t)warp * a.maxHits;
     uint16_t *resDiag = a.resDiag + (size_t)warp * a.maxHits;
-    int16_t *S2 = sS2[wInBlock];
     uint16_t *X2 = sX2[wInBlock];
     uint32_t *hist = sHist[wInBlock];
+    uint32_t *Q1c = reinterpret_cast<uint32_t *>(sDyn) + (size_t)wInBlock * (PF_Q1CAP + PF_Q2CAP);
+    uint32_t *Q2t = Q1c + PF_Q1CAP;
+    uint16_t *Q1p = reinterpret_cast<uint16_t *>(sDyn + (size_t)PF_WARPS * (PF_Q1CAP + PF_Q2CAP) * sizeof(uint32_t)) + (size_t)wInBlock * (PF_Q1CAP + PF_Q2CAP);
+    uint16_t *Q2d = Q1p + PF_Q1CAP;
 
     unsigned long long stProbes = 0, stMatches = 0, stDiagRes = 0, stHits = 0, stCands = 0, stTrunc = 0;
     uint32_t epoch = 0;   // table words start zeroed; live epochs are 1..255
@@ -279,126 +337,199 @@ __global__ void __launch_bounds__(PF_WARPS * 32) prefilterKernel(PrefilterArgs a
         bool candOverflow = false;
 
         // ---------------- hit stream: positions -> similar k-mers -> buckets -> double-hit rule
-        for (int p = 0; p + SPAN <= Lq; p++) {
-            const int thr = a.q.thr[qBase + p];
-            if (thr < 0) continue;
-            const uint8_t *qc = a.q.code + qBase + p;
-            const uint32_t i1 = qc[0] + 20u * qc[1] + 400u * qc[3];
-            const uint32_t i2 = qc[5] + 20u * qc[8] + 400u * qc[9];
-            const int16_t *s1 = a.e3score + (size_t)i1 * N3;
-            const uint16_t *x1 = a.e3index + (size_t)i1 * N3;
-            const int16_t *s2 = a.e3score + (size_t)i2 * N3;
-            const uint16_t *x2 = a.e3index + (size_t)i2 * N3;
-            const int cutoff1 = thr - (int)s2[0];          // KmerGenerator.cpp:129-137
-            const int cutoff2max = thr - (int)s1[0];
-            if ((int)s1[0] < cutoff1) continue;
-            // stage the prefix of row 2 that any first-row element can reach
-            uint32_t nb2 = 0;
-            for (uint32_t c0 = 0; c0 < N3; c0 += 32) {
-                const uint32_t c = c0 + lane;
-                const int v = (c < N3) ? (int)s2[c] : -32768;
-                const bool ok = v >= cutoff2max;
-                if (ok && c < PF_CAP2) { S2[c] = (int16_t)v; X2[c] = x2[c]; }
-                const uint32_t b = __ballot_sync(0xffffffffu, ok);
-                nb2 += __popc(b);
-                if (b != 0xffffffffu) break;
-            }
+        // Three stages, decoupled by two small per-warp FIFO rings in shared memory so that every stage runs with full
+        // lanes and every HBM access was prefetched into L2 one stage earlier (stream order is the FIFO order):
+        //   A  32 similar k-mers per step -> occupancy bitmap + rank (L2 resident) -> non-empty ones to ring 1
+        //   B  32 buckets per step: compact offset row (prefetched by A) -> entries -> (target, diagonal) to ring 2
+        //   C  32 index hits per step: double-diagonal rule on the per-warp table (prefetched by B)
+        uint32_t q1h = 0, q1n = 0, q2h = 0, q2n = 0;
+
+        auto stageC = [&](const uint32_t n) {
             __syncwarp();
-            if (nb2 == 0) continue;
+            const bool validE = lane < n;
+            uint32_t t = 0x80000000u | lane;     // unique dummy for idle lanes
+            uint32_t diag16 = 0;
+            if (validE) {
+                const uint32_t slot = (q2h + lane) & (PF_Q2CAP - 1);
+                t = Q2t[slot];
+                diag16 = Q2d[slot];
+            }
+            q2h += n;
+            q2n -= n;
+            const uint32_t d8 = diag16 & 0xffu;
+            // --- CacheFriendlyOperations::findDuplicates, restated per target in stream order
+            const uint32_t grp = __match_any_sync(0xffffffffu, t);
+            uint32_t old = 0;
+            if (validE) old = __ldcg(&tab[t]);
+            if ((old >> 24) != E) old = 0;
+            const uint32_t lowerG = grp & ltMask;
+            const int prevLane = lowerG ? (31 - __clz(lowerG)) : -1;
+            uint32_t prevD8 = __shfl_sync(0xffffffffu, d8, prevLane >= 0 ? prevLane : (int)lane);
+            if (prevLane < 0) prevD8 = (old >> 16) & 0xffu;
+            const bool emit = validE && (d8 == prevD8);
+            const uint32_t emitBallot = __ballot_sync(0xffffffffu, emit);
+            const uint32_t grpE = grp & emitBallot;
+            const uint32_t lowerE = grpE & ltMask;
+            const int prevELane = lowerE ? (31 - __clz(lowerE)) : -1;
+            uint32_t prevED8 = __shfl_sync(0xffffffffu, d8, prevELane >= 0 ? prevELane : (int)lane);
+            bool prevEExists = true;
+            if (prevELane < 0) { prevED8 = old & 0xffu; prevEExists = ((old >> 8) & 1u) != 0; }
+            const bool isCand = emit && !(prevEExists && prevED8 == d8);
+            const int lastELane = grpE ? (31 - __clz(grpE)) : -1;
+            const uint32_t lastED8 = __shfl_sync(0xffffffffu, d8, lastELane >= 0 ? lastELane : (int)lane);
+            if (validE && (grp >> lane) == 1u) {
+                uint32_t w = (E << 24) | (d8 << 16);
+                if (lastELane >= 0) w |= (1u << 8) | lastED8;
+                else w |= old & 0x1ffu;
+                __stcg(&tab[t], w);
+            }
+            const uint32_t candBallot = __ballot_sync(0xffffffffu, isCand);
+            if (isCand) {
+                const uint32_t pos = nCand + __popc(candBallot & ltMask);
+                if (pos < a.candCap) cand[pos] = ((uint64_t)t << 32) | ((uint64_t)diag16 << 16);
+            }
+            nCand += __popc(candBallot);
+        };
 
-            for (uint32_t a0 = 0; a0 < N3; a0 += 32) {
-                const uint32_t ai = a0 + lane;
-                const int sa = (ai < N3) ? (int)s1[ai] : -32768;
-                const bool okA = sa >= cutoff1;
-                const uint32_t okBallot = __ballot_sync(0xffffffffu, okA);
-                if (okBallot == 0) break;
-                uint32_t nb = 0;
-                uint32_t xa = 0;
-                if (okA) {
-                    xa = x1[ai];
-                    const int cut = thr - sa;                 // KmerGenerator.cpp:201
-                    uint32_t lo = 0, hi = nb2;                // first c with s2[c] < cut
-                    while (lo < hi) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        const int v = (mid < PF_CAP2) ? (int)S2[mid] : (int)s2[mid];
-                        if (v >= cut) lo = mid + 1; else hi = mid;
-                    }
-                    nb = lo;
+        auto stageB = [&](const uint32_t n) {
+            __syncwarp();
+            uint32_t bLo = 0, m = 0, pq = 0;
+            if (lane < n) {
+                const uint32_t slot = (q1h + lane) & (PF_Q1CAP - 1);
+                const uint32_t ci = Q1c[slot];
+                pq = Q1p[slot];
+                bLo = __ldg(&a.cOff[ci]);
+                m = __ldg(&a.cOff[ci + 1]) - bLo;       // >= 1: only non-empty buckets are queued
+            }
+            q1h += n;
+            q1n -= n;
+            uint32_t totalM;
+            const uint32_t exclM = warpExclusiveScan(m, totalM);
+            stMatches += (lane == 0) ? totalM : 0;
+            for (uint32_t ec = 0; ec < totalM; ec += 32) {
+                const uint32_t eidx = ec + lane;
+                const bool validE = eidx < totalM;
+                const uint32_t ownerM = warpOwnerOfSlot(exclM, m != 0, ec, lane);
+                const uint32_t oExcl = __shfl_sync(0xffffffffu, exclM, ownerM);
+                const uint32_t oLo = __shfl_sync(0xffffffffu, bLo, ownerM);
+                const uint32_t oP = __shfl_sync(0xffffffffu, pq, ownerM);
+                if (validE) {
+                    const uint2 en = __ldg(&a.ent[oLo + (eidx - oExcl)]);
+                    prefetchL2(&tab[en.x]);
+                    const uint32_t slot = (q2h + q2n + lane) & (PF_Q2CAP - 1);
+                    Q2t[slot] = en.x;
+                    Q2d[slot] = (uint16_t)(oP - en.y);
                 }
-                uint32_t totalProbes;
-                const uint32_t exclA = warpExclusiveScan(nb, totalProbes);
-                stProbes += (lane == 0) ? totalProbes : 0;
+                q2n += min(32u, totalM - ec);
+                while (q2n >= PF_QDRAIN) stageC(32u);
+            }
+        };
 
-                for (uint32_t pc = 0; pc < totalProbes; pc += 32) {
-                    const uint32_t pidx = pc + lane;
-                    const bool validP = pidx < totalProbes;
-                    const uint32_t ownerA = warpFindOwner(exclA, validP ? pidx : 0);
-                    const uint32_t ownerExcl = __shfl_sync(0xffffffffu, exclA, ownerA);
-                    const uint32_t ownerX = __shfl_sync(0xffffffffu, xa, ownerA);
-                    uint32_t bLo = 0, m = 0;
-                    if (validP) {
-                        const uint32_t c = pidx - ownerExcl;
-                        const uint32_t xc = (c < PF_CAP2) ? (uint32_t)X2[c] : (uint32_t)x2[c];
-                        const uint32_t kmer = ownerX + N3 * xc;            // KmerGenerator.cpp:207
-                        bLo = __ldg(&a.kOff[kmer]);
-                        m = __ldg(&a.kOff[kmer + 1]) - bLo;
-                    }
-                    uint32_t totalM;
-                    const uint32_t exclM = warpExclusiveScan(m, totalM);
-                    stMatches += (lane == 0) ? totalM : 0;
-
-                    for (uint32_t ec = 0; ec < totalM; ec += 32) {
-                        const uint32_t eidx = ec + lane;
-                        const bool validE = eidx < totalM;
-                        const uint32_t ownerM = warpFindOwner(exclM, validE ? eidx : 0);
-                        const uint32_t oExcl = __shfl_sync(0xffffffffu, exclM, ownerM);
-                        const uint32_t oLo = __shfl_sync(0xffffffffu, bLo, ownerM);
-                        uint32_t t = 0x80000000u | lane;     // unique dummy for idle lanes
-                        uint32_t diag16 = 0;
-                        if (validE) {
-                            const uint32_t e = oLo + (eidx - oExcl);
-                            t = __ldg(&a.entSeq[e]);
-                            diag16 = (uint32_t)(uint16_t)(p - (int)__ldg(&a.entPos[e]));
+        for (int p0 = 0; p0 + SPAN <= Lq; p0 += 32) {
+            // ---- set-up of 32 positions at once (one per lane): thresholds, 3-mer rows, reachable prefix of row 2
+            int thrL = -1, top2L = 0;
+            uint32_t i1L = 0, i2L = 0, nb2L = 0;
+            {
+                const int pl = p0 + (int)lane;
+                if (pl + SPAN <= Lq) thrL = a.q.thr[qBase + pl];
+                if (thrL >= 0) {
+                    const uint8_t *qc = a.q.code + qBase + pl;
+                    i1L = qc[0] + 20u * qc[1] + 400u * qc[3];
+                    i2L = qc[5] + 20u * qc[8] + 400u * qc[9];
+                    const int top1 = (int)__ldg(&a.e3score[(size_t)i1L * N3]);
+                    top2L = (int)__ldg(&a.e3score[(size_t)i2L * N3]);
+                    if (top1 < thrL - top2L) thrL = -1;           // KmerGenerator.cpp:129-137: nothing reaches the threshold
+                    else {
+                        nb2L = countGE(a.e3cnt, i2L, thrL - top1);
+                        if (nb2L == 0) thrL = -1;
+                        else {
+                            prefetchL2(&a.e3index[(size_t)i1L * N3]);
+                            const uint16_t *x2 = a.e3index + (size_t)i2L * N3;
+                            for (uint32_t c = 0; c < nb2L && c < (uint32_t)PF_CAP2; c += 64) prefetchL2(&x2[c]);
                         }
-                        const uint32_t d8 = diag16 & 0xffu;
-                        // --- CacheFriendlyOperations::findDuplicates, restated per target in stream order
-                        const uint32_t grp = __match_any_sync(0xffffffffu, t);
-                        uint32_t old = 0;
-                        if (validE) old = __ldcg(&tab[t]);
-                        if ((old >> 24) != E) old = 0;
-                        const uint32_t lowerG = grp & ltMask;
-                        const int prevLane = lowerG ? (31 - __clz(lowerG)) : -1;
-                        uint32_t prevD8 = __shfl_sync(0xffffffffu, d8, prevLane >= 0 ? prevLane : (int)lane);
-                        if (prevLane < 0) prevD8 = (old >> 16) & 0xffu;
-                        const bool emit = validE && (d8 == prevD8);
-                        const uint32_t emitBallot = __ballot_sync(0xffffffffu, emit);
-                        const uint32_t grpE = grp & emitBallot;
-                        const uint32_t lowerE = grpE & ltMask;
-                        const int prevELane = lowerE ? (31 - __clz(lowerE)) : -1;
-                        uint32_t prevED8 = __shfl_sync(0xffffffffu, d8, prevELane >= 0 ? prevELane : (int)lane);
-                        bool prevEExists = true;
-                        if (prevELane < 0) { prevED8 = old & 0xffu; prevEExists = ((old >> 8) & 1u) != 0; }
-                        const bool isCand = emit && !(prevEExists && prevED8 == d8);
-                        const int lastELane = grpE ? (31 - __clz(grpE)) : -1;
-                        const uint32_t lastED8 = __shfl_sync(0xffffffffu, d8, lastELane >= 0 ? lastELane : (int)lane);
-                        if (validE && (grp >> lane) == 1u) {
-                            uint32_t w = (E << 24) | (d8 << 16);
-                            if (lastELane >= 0) w |= (1u << 8) | lastED8;
-                            else w |= old & 0x1ffu;
-                            __stcg(&tab[t], w);
-                        }
-                        const uint32_t candBallot = __ballot_sync(0xffffffffu, isCand);
-                        if (isCand) {
-                            const uint32_t pos = nCand + __popc(candBallot & ltMask);
-                            if (pos < a.candCap) cand[pos] = ((uint64_t)t << 32) | ((uint64_t)diag16 << 16);
-                        }
-                        nCand += __popc(candBallot);
-                        __syncwarp();
                     }
                 }
-                if (okBallot != 0xffffffffu) break;
+            }
+            uint32_t active = __ballot_sync(0xffffffffu, thrL >= 0);
+            while (active) {
+                const int src = __ffs(active) - 1;
+                active &= active - 1;
+                const int p = p0 + src;
+                const int thr = __shfl_sync(0xffffffffu, thrL, src);
+                const uint32_t i1 = __shfl_sync(0xffffffffu, i1L, src);
+                const uint32_t i2 = __shfl_sync(0xffffffffu, i2L, src);
+                const uint32_t nb2 = __shfl_sync(0xffffffffu, nb2L, src);
+                const int cutoff1 = thr - __shfl_sync(0xffffffffu, top2L, src);
+                const int16_t *s1 = a.e3score + (size_t)i1 * N3;
+                const uint16_t *x1 = a.e3index + (size_t)i1 * N3;
+                const uint16_t *x2 = a.e3index + (size_t)i2 * N3;
+                // stage the prefix of row 2 that any first-row element can reach
+                __syncwarp();
+                for (uint32_t c = lane; c < nb2 && c < (uint32_t)PF_CAP2; c += 32) X2[c] = __ldg(&x2[c]);
+                __syncwarp();
+
+                for (uint32_t a0 = 0; a0 < N3; a0 += 32) {
+                    const uint32_t ai = a0 + lane;
+                    const int sa = (ai < N3) ? (int)__ldg(&s1[ai]) : -32768;
+                    const bool okA = sa >= cutoff1;
+                    const uint32_t okBallot = __ballot_sync(0xffffffffu, okA);
+                    if (okBallot == 0) break;
+                    uint32_t nb = 0;
+                    uint32_t xa = 0;
+                    if (okA) {
+                        xa = __ldg(&x1[ai]);
+                        nb = countGE(a.e3cnt, i2, thr - sa);      // KmerGenerator.cpp:201: second-row elements with s2 >= thr - s1
+                    }
+                    // nb is non-increasing over the lanes (row 1 is sorted), zeros only at the tail
+                    uint32_t totalProbes;
+                    const uint32_t exclA = warpExclusiveScan(nb, totalProbes);
+                    stProbes += (lane == 0) ? totalProbes : 0;
+
+                    for (uint32_t pc = 0; pc < totalProbes; pc += 32 * PF_UNROLL) {
+                        uint2 w[PF_UNROLL];
+                        uint32_t kmerBit[PF_UNROLL];
+#pragma unroll
+                        for (int j = 0; j < PF_UNROLL; j++) {
+                            const uint32_t base = pc + 32u * j;
+                            w[j] = make_uint2(0u, 0u);
+                            kmerBit[j] = 0;
+                            if (base < totalProbes) {
+                                const uint32_t ownerA = warpOwnerOfSlot(exclA, nb != 0, base, lane);
+                                const uint32_t ownerExcl = __shfl_sync(0xffffffffu, exclA, ownerA);
+                                const uint32_t ownerX = __shfl_sync(0xffffffffu, xa, ownerA);
+                                if (base + lane < totalProbes) {
+                                    const uint32_t c = base + lane - ownerExcl;
+                                    const uint32_t xc = (c < (uint32_t)PF_CAP2) ? (uint32_t)X2[c] : (uint32_t)__ldg(&x2[c]);
+                                    const uint32_t kmer = ownerX + N3 * xc;            // KmerGenerator.cpp:207
+                                    w[j] = __ldg(&a.bm[kmer >> 5]);
+                                    kmerBit[j] = kmer & 31u;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < PF_UNROLL; j++) {
+                            if (pc + 32u * j < totalProbes) {
+                                const bool has = ((w[j].x >> kmerBit[j]) & 1u) != 0;   // idle lanes carry w = 0
+                                const uint32_t ci = w[j].y + __popc(w[j].x & ((1u << kmerBit[j]) - 1u));
+                                if (has) prefetchL2(&a.cOff[ci]);
+                                const uint32_t hb = __ballot_sync(0xffffffffu, has);
+                                if (has) {
+                                    const uint32_t slot = (q1h + q1n + __popc(hb & ltMask)) & (PF_Q1CAP - 1);
+                                    Q1c[slot] = ci;
+                                    Q1p[slot] = (uint16_t)p;
+                                }
+                                q1n += __popc(hb);
+                            }
+                        }
+                        while (q1n >= PF_QDRAIN) stageB(32u);
+                    }
+                    if (okBallot != 0xffffffffu) break;
+                }
             }
         }
+        while (q1n > 0) stageB(min(q1n, 32u));
+        while (q2n > 0) stageC(min(q2n, 32u));
+        __syncwarp();
         if (nCand > a.candCap) { candOverflow = true; nCand = a.candCap; }
         stCands += (lane == 0) ? nCand : 0;
         __syncwarp();
@@ -624,11 +755,13 @@ static inline unsigned gridFor(uint64_t n, unsigned block) { return (unsigned)((
 static int ensureExt3(sd_context *ctx) {
     if (ctx->haveExt3) return SD_OK;
     std::vector<int16_t> sc;
-    std::vector<uint16_t> ix;
-    buildExt3(ctx->seedMat, sc, ix);
+    std::vector<uint16_t> ix, cn;
+    buildExt3(ctx->seedMat, sc, ix, cn);
     int rc;
     if ((rc = ctx->e3score.alloc(sc.size())) != SD_OK) return rc;
     if ((rc = ctx->e3index.alloc(ix.size())) != SD_OK) return rc;
+    if ((rc = ctx->e3cnt.alloc(cn.size())) != SD_OK) return rc;
+    SD_CUDA(cudaMemcpyAsync(ctx->e3cnt.p, cn.data(), cn.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
     SD_CUDA(cudaMemcpyAsync(ctx->e3score.p, sc.data(), sc.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
     SD_CUDA(cudaMemcpyAsync(ctx->e3index.p, ix.data(), ix.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
     SD_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -680,7 +813,8 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
 
     if ((rc = idx->res.alloc(total + SPAN)) != SD_OK) return rc;
     if ((rc = idx->off.alloc(n + 1)) != SD_OK) return rc;
-    if ((rc = idx->kOff.alloc((size_t)NKMER + 1)) != SD_OK) return rc;
+    DevBuf<uint32_t> kOff;                 // dense bucket starts: build-time only
+    if ((rc = kOff.alloc((size_t)NKMER + 1)) != SD_OK) return rc;
     cudaStream_t st = ctx->stream;
     SD_CUDA(cudaMemcpyAsync(idx->res.p, codes.data(), total + SPAN, cudaMemcpyHostToDevice, st));
     SD_CUDA(cudaMemcpyAsync(idx->off.p, idx->hostOff.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
@@ -710,8 +844,8 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
     keysA.release();
     if ((rc = kmerA.alloc(nPos)) != SD_OK || (rc = kmerB.alloc(nPos)) != SD_OK) return rc;
     if ((rc = payloadA.alloc(nPos)) != SD_OK || (rc = payloadB.alloc(nPos)) != SD_OK) return rc;
-    SD_CUDA(cudaMemsetAsync(idx->kOff.p, 0, ((size_t)NKMER + 1) * sizeof(uint32_t), st));
-    firstOccurrence<<<gridFor(nPos, 256), 256, 0, st>>>(keysB.p, nPos, kmerA.p, payloadA.p, idx->kOff.p);
+    SD_CUDA(cudaMemsetAsync(kOff.p, 0, ((size_t)NKMER + 1) * sizeof(uint32_t), st));
+    firstOccurrence<<<gridFor(nPos, 256), 256, 0, st>>>(keysB.p, nPos, kmerA.p, payloadA.p, kOff.p);
     ctx->launches++;
     SD_CUDA(cudaGetLastError());
     // stable sort by k-mer: buckets come out ordered by (seq, pos); dropped entries (0xffffffff) go last
@@ -726,20 +860,43 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
     // bucket starts = exclusive scan of the counts
     {
         size_t tmpBytes = 0;
-        SD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, idx->kOff.p, idx->kOff.p, (int64_t)NKMER + 1, st));
+        SD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, kOff.p, kOff.p, (int64_t)NKMER + 1, st));
         DevBuf<uint8_t> tmp;
         if ((rc = tmp.alloc(tmpBytes)) != SD_OK) return rc;
-        SD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, idx->kOff.p, idx->kOff.p, (int64_t)NKMER + 1, st));
+        SD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, kOff.p, kOff.p, (int64_t)NKMER + 1, st));
     }
     uint32_t nEnt = 0;
-    SD_CUDA(cudaMemcpyAsync(&nEnt, idx->kOff.p + NKMER, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SD_CUDA(cudaMemcpyAsync(&nEnt, kOff.p + NKMER, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     SD_CUDA(cudaStreamSynchronize(st));
     idx->nEntries = nEnt;
-    if ((rc = idx->entSeq.alloc(nEnt)) != SD_OK || (rc = idx->entPos.alloc(nEnt)) != SD_OK) return rc;
+    if ((rc = idx->ent.alloc(nEnt)) != SD_OK) return rc;
     if (nEnt > 0) {
-        splitEntries<<<gridFor(nEnt, 256), 256, 0, st>>>(payloadB.p, nEnt, idx->entSeq.p, idx->entPos.p);
+        packEntries<<<gridFor(nEnt, 256), 256, 0, st>>>(payloadB.p, nEnt, idx->ent.p);
         ctx->launches++;
         SD_CUDA(cudaGetLastError());
+    }
+    // occupancy bitmap + rank, compact bucket starts
+    {
+        const uint32_t nWords = (NKMER + 31) / 32;
+        DevBuf<uint32_t> bits, cnt, rank;
+        if ((rc = bits.alloc(nWords)) || (rc = cnt.alloc(nWords + 1)) || (rc = rank.alloc(nWords + 1)) || (rc = idx->bm.alloc(nWords))) return rc;
+        SD_CUDA(cudaMemsetAsync(cnt.p + nWords, 0, sizeof(uint32_t), st));
+        occupancyBits<<<gridFor((uint64_t)((nWords + 31) / 32) * 32, 256), 256, 0, st>>>(kOff.p, nWords, bits.p, cnt.p);
+        size_t tmpBytes = 0;
+        SD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, cnt.p, rank.p, (int64_t)nWords + 1, st));
+        DevBuf<uint8_t> tmp;
+        if ((rc = tmp.alloc(tmpBytes)) != SD_OK) return rc;
+        SD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, cnt.p, rank.p, (int64_t)nWords + 1, st));
+        uint32_t nDistinct = 0;
+        SD_CUDA(cudaMemcpyAsync(&nDistinct, rank.p + nWords, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SD_CUDA(cudaStreamSynchronize(st));
+        idx->nDistinct = nDistinct;
+        if ((rc = idx->cOff.alloc((size_t)nDistinct + 1)) != SD_OK) return rc;
+        compactOffsets<<<gridFor((uint64_t)nWords * 32, 256), 256, 0, st>>>(kOff.p, bits.p, rank.p, nWords, idx->bm.p, idx->cOff.p);
+        SD_CUDA(cudaMemcpyAsync(idx->cOff.p + nDistinct, &nEnt, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        ctx->launches += 2;
+        SD_CUDA(cudaGetLastError());
+        SD_CUDA(cudaStreamSynchronize(st));
     }
     SD_CUDA(cudaStreamSynchronize(st));
     if ((rc = ensureExt3(ctx)) != SD_OK) return rc;
@@ -871,8 +1028,8 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
 
     PrefilterArgs a{};
     a.tRes = idx->res.p; a.tOff = idx->off.p; a.nT = idx->nT;
-    a.kOff = idx->kOff.p; a.entSeq = idx->entSeq.p; a.entPos = idx->entPos.p;
-    a.e3score = ctx->e3score.p; a.e3index = ctx->e3index.p; a.diagSub = dDiagSub.p;
+    a.bm = idx->bm.p; a.cOff = idx->cOff.p; a.ent = idx->ent.p;
+    a.e3score = ctx->e3score.p; a.e3index = ctx->e3index.p; a.e3cnt = ctx->e3cnt.p; a.diagSub = dDiagSub.p;
     a.q.code = dCode.p; a.q.off = dOff.p; a.q.corr = dCorr.p; a.q.thr = dThr.p;
     a.nQ = nq; a.order = dOrder.p; a.queryFirst = query_first; a.sameDb = par->same_db;
     a.maxHits = maxHits; a.minDiagScore = (uint32_t)std::max(par->min_ungapped_score, 0);
@@ -882,7 +1039,8 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     a.out = dOut.p; a.outCount = dOutCount.p; a.stats = dStats.p; a.nextQuery = dNext.p; a.errQuery = dNext.p + 1;
 
     SD_CUDA(cudaEventRecord(evk0, st));
-    prefilterKernel<<<nCta, PF_WARPS * 32, 0, st>>>(a);
+    SD_CUDA(cudaFuncSetAttribute(prefilterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_DYN_SMEM));
+    prefilterKernel<<<nCta, PF_WARPS * 32, PF_DYN_SMEM, st>>>(a);
     ctx->launches++;
     SD_CUDA(cudaGetLastError());
     SD_CUDA(cudaEventRecord(evk1, st));

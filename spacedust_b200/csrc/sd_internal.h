@@ -155,6 +155,7 @@ struct sd_context {
     sd::SubMat alnMat;        // BLOSUM62 x2, bias 0    (Alignment.cpp:152)
     sd::DevBuf<int16_t> e3score;
     sd::DevBuf<uint16_t> e3index;
+    sd::DevBuf<uint16_t> e3cnt;      // 8000 x 512 cumulative score counts of the rows (8 MB, L2 resident)
     bool haveExt3 = false;
 };
 
@@ -191,7 +192,8 @@ struct sd_target_index {
     sd::DevBuf<uint8_t> raw;           // unmasked residue codes: alignment side
     uint32_t maxLen = 0;
     sd::DevBuf<uint32_t> off;          // nT+1
-    sd::DevBuf<uint32_t> kOff;         // NKMER+1 bucket starts
-    sd::DevBuf<uint32_t> entSeq;       // bucket entries: target id ...
-    sd::DevBuf<uint16_t> entPos;       // ... and first position of the k-mer in that target
+    uint32_t nDistinct = 0;            // k-mers with a non-empty bucket
+    sd::DevBuf<uint2> bm;              // per 32 k-mers: {occupancy bits, rank of the first} -- 16 MB, L2 resident
+    sd::DevBuf<uint32_t> cOff;         // nDistinct+1 bucket starts (compact rows)
+    sd::DevBuf<uint2> ent;             // bucket entries: {target id, first position of the k-mer in that target}
 };
