@@ -18,6 +18,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <cstdlib>
 #include <memory>
 #include <numeric>
 
@@ -124,9 +125,8 @@ __global__ void packEntries(const uint64_t *__restrict__ payload, uint64_t n, ui
 }
 
 // Occupancy bitmap of the k-mer space: one warp turns 32x32 bucket sizes into 32 words (coalesced reads of kOff).
-// bm[w].x = bits of k-mers 32w..32w+31 with a non-empty bucket; .y (filled by the scan below) = number of non-empty
-// k-mers before 32w, i.e. the row of the compact offset table.  16 MB for 20^6 k-mers: stays in the 126 MB L2, so an
-// empty probe never reaches HBM.
+// bits[w] = k-mers 32w..32w+31 with a non-empty bucket (8 MB for 20^6 k-mers: meant to stay in the 126 MB L2, so an
+// empty probe never reaches HBM); rank[w] (scan below) = number of non-empty k-mers before 32w = row of the first one.
 __global__ void occupancyBits(const uint32_t *__restrict__ kOff, uint32_t nWords, uint32_t *__restrict__ bits,
                               uint32_t *__restrict__ cnt) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -143,15 +143,20 @@ __global__ void occupancyBits(const uint32_t *__restrict__ kOff, uint32_t nWords
     if (w0 + lane < nWords) { bits[w0 + lane] = mine; cnt[w0 + lane] = __popc(mine); }
 }
 
-__global__ void compactOffsets(const uint32_t *__restrict__ kOff, const uint32_t *__restrict__ bits,
-                               const uint32_t *__restrict__ rank, uint32_t nWords, uint2 *__restrict__ bm,
-                               uint32_t *__restrict__ cOff) {
+// One 8-byte row per non-empty k-mer: a bucket with a single entry is stored inline {target, 1<<31 | pos} (no second
+// random access), longer buckets as {start, length} into ent[].
+__global__ void compactRows(const uint32_t *__restrict__ kOff, const uint32_t *__restrict__ bits,
+                            const uint32_t *__restrict__ rank, uint32_t nWords, const uint2 *__restrict__ ent,
+                            uint2 *__restrict__ rows) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t w = k >> 5;
-    if (w >= nWords) return;
-    const uint32_t b = bits[w], r = rank[w];
-    if ((k & 31) == 0) bm[w] = make_uint2(b, r);
-    if (k < NKMER && ((b >> (k & 31)) & 1u)) cOff[r + __popc(b & ((1u << (k & 31)) - 1u))] = kOff[k];
+    if (w >= nWords || k >= NKMER) return;
+    const uint32_t b = bits[w];
+    if (!((b >> (k & 31)) & 1u)) return;
+    const uint32_t start = kOff[k], len = kOff[k + 1] - start;
+    uint2 row = make_uint2(start, len);
+    if (len == 1) { const uint2 e = ent[start]; row = make_uint2(e.x, 0x80000000u | e.y); }
+    rows[rank[w] + __popc(b & ((1u << (k & 31)) - 1u))] = row;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -217,13 +222,46 @@ static_assert(PF_QDRAIN - 1 + 32 * PF_UNROLL <= PF_Q1CAP && PF_QDRAIN - 1 + 32 <
 
 __device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
+// L2 cache policies: the streamed, never re-used data (bucket rows, entries, the per-warp tables) is marked evict-first so
+// that it does not push the re-used data (occupancy bitmap, count table, target residues) out of the L2.
+__device__ __forceinline__ uint64_t l2Policy(int evictFirst) {
+    uint64_t pol;
+    if (evictFirst) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2PolicyKeep() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint32_t ldKeep(const uint32_t *p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldStream(const uint32_t *p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 ldStream2(const uint2 *p, uint64_t pol) {
+    uint2 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stStream(uint32_t *p, uint32_t v, uint64_t pol) {
+    asm volatile("st.global.cg.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+
 struct PrefilterArgs {
     // target side
     const uint8_t *tRes;
     const uint32_t *tOff;
     uint32_t nT;
-    const uint2 *bm;           // per 32 k-mers: occupancy bits, rank of the first one (L2 resident)
-    const uint32_t *cOff;      // bucket starts of the non-empty k-mers (+ sentinel)
+    const uint32_t *bmBits;    // per 32 k-mers: occupancy bits (8 MB, L2 resident)
+    const uint32_t *bmRank;    // per 32 k-mers: row of the first non-empty one
+    const uint2 *rows;         // per non-empty k-mer: {target, 1<<31 | pos} (single entry) or {start, length}
     const uint2 *ent;          // bucket entries: (target id, first position of the k-mer in that target)
     const int16_t *e3score;
     const uint16_t *e3index;
@@ -255,6 +293,7 @@ struct PrefilterArgs {
     unsigned long long *stats; // [0]=probes [1]=matches [2]=diagResidues [3]=hits [4]=candidates [5]=truncated [6]=errors
     uint32_t *nextQuery;
     uint32_t *errQuery;
+    int evictFirst;            // L2 evict-first policy for the streamed data
 };
 
 enum { ST_PROBES = 0, ST_MATCHES, ST_DIAGRES, ST_HITS, ST_CANDS, ST_TRUNC, ST_ERR_CAND, ST_ERR_RESCORE, ST_N };
@@ -285,7 +324,50 @@ __device__ int diagonalScore(const PrefilterArgs &a, const int8_t *sSub, uint32_
     return best;
 }
 
-__global__ void __launch_bounds__(PF_WARPS * 32) prefilterKernel(PrefilterArgs a) {
+// same score, computed by a whole warp: lane l takes residues l, l+32, ...; with S the prefix sums of the per-residue scores,
+// run_i = S_i - min(0, min_{j<=i} S_j) and the result is max_i run_i
+__device__ __forceinline__ int diagonalScoreWarp(const PrefilterArgs &a, const int8_t *sSub, uint32_t qBase, int Lq, uint32_t t,
+                                                 int diag, uint32_t lane, unsigned long long &residues) {
+    const uint32_t tb = __ldg(&a.tOff[t]);
+    const int Lt = (int)(__ldg(&a.tOff[t + 1]) - tb);
+    int qs, ts, len;
+    if (diag >= 0) {
+        if (diag >= Lq) return 0;
+        qs = diag; ts = 0; len = min(Lt, Lq - diag);
+    } else {
+        if (-diag >= Lt) return 0;
+        qs = 0; ts = -diag; len = min(Lt + diag, Lq);
+    }
+    const uint8_t *qc = a.q.code + qBase + qs;
+    const int8_t *qk = a.q.corr + qBase + qs;
+    const uint8_t *tc = a.tRes + tb + ts;
+    int best = 0, carrySum = 0, carryMin = 0;
+    for (int p0 = 0; p0 < len; p0 += 32) {
+        const int p = p0 + (int)lane;
+        int x = 0;
+        if (p < len) x = (int)sSub[__ldg(&qc[p]) * AA + __ldg(&tc[p])] + (int)__ldg(&qk[p]);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= (uint32_t)d) x += y;
+        }
+        x += carrySum;
+        int m = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, m, d);
+            if (lane >= (uint32_t)d) m = min(m, y);
+        }
+        m = min(m, carryMin);
+        best = max(best, x - m);
+        carrySum = __shfl_sync(0xffffffffu, x, 31);
+        carryMin = __shfl_sync(0xffffffffu, m, 31);
+    }
+    if (lane == 0) residues += (unsigned long long)len;
+    return __reduce_max_sync(0xffffffffu, best);
+}
+
+__global__ void __launch_bounds__(PF_WARPS * 32, 3) prefilterKernel(PrefilterArgs a) {
     __shared__ uint16_t sX2[PF_WARPS][PF_CAP2];
     __shared__ uint32_t sHist[PF_WARPS][256];
     __shared__ int8_t sSub[AA * AA];
@@ -311,6 +393,8 @@ __global__ void __launch_bounds__(PF_WARPS * 32) prefilterKernel(PrefilterArgs a
     uint16_t *Q1p = reinterpret_cast<uint16_t *>(sDyn + (size_t)PF_WARPS * (PF_Q1CAP + PF_Q2CAP) * sizeof(uint32_t)) + (size_t)wInBlock * (PF_Q1CAP + PF_Q2CAP);
     uint16_t *Q2d = Q1p + PF_Q1CAP;
 
+    const uint64_t pol = l2Policy(a.evictFirst);
+    const uint64_t polKeep = a.evictFirst ? l2PolicyKeep() : l2Policy(0);
     unsigned long long stProbes = 0, stMatches = 0, stDiagRes = 0, stHits = 0, stCands = 0, stTrunc = 0;
     uint32_t epoch = 0;   // table words start zeroed; live epochs are 1..255
 
@@ -360,7 +444,7 @@ __global__ void __launch_bounds__(PF_WARPS * 32) prefilterKernel(PrefilterArgs a
             // --- CacheFriendlyOperations::findDuplicates, restated per target in stream order
             const uint32_t grp = __match_any_sync(0xffffffffu, t);
             uint32_t old = 0;
-            if (validE) old = __ldcg(&tab[t]);
+            if (validE) old = ldStream(&tab[t], pol);
             if ((old >> 24) != E) old = 0;
             const uint32_t lowerG = grp & ltMask;
             const int prevLane = lowerG ? (31 - __clz(lowerG)) : -1;
@@ -381,7 +465,7 @@ __global__ void __launch_bounds__(PF_WARPS * 32) prefilterKernel(PrefilterArgs a
                 uint32_t w = (E << 24) | (d8 << 16);
                 if (lastELane >= 0) w |= (1u << 8) | lastED8;
                 else w |= old & 0x1ffu;
-                __stcg(&tab[t], w);
+                stStream(&tab[t], w, pol);
             }
             const uint32_t candBallot = __ballot_sync(0xffffffffu, isCand);
             if (isCand) {
@@ -393,13 +477,14 @@ __global__ void __launch_bounds__(PF_WARPS * 32) prefilterKernel(PrefilterArgs a
 
         auto stageB = [&](const uint32_t n) {
             __syncwarp();
-            uint32_t bLo = 0, m = 0, pq = 0;
+            uint32_t rx = 0, ry = 0, m = 0, pq = 0;
             if (lane < n) {
                 const uint32_t slot = (q1h + lane) & (PF_Q1CAP - 1);
-                const uint32_t ci = Q1c[slot];
+                const uint2 row = ldStream2(&a.rows[Q1c[slot]], pol);
                 pq = Q1p[slot];
-                bLo = __ldg(&a.cOff[ci]);
-                m = __ldg(&a.cOff[ci + 1]) - bLo;       // >= 1: only non-empty buckets are queued
+                rx = row.x;
+                ry = row.y;
+                m = (ry >> 31) ? 1u : ry;                // >= 1: only non-empty buckets are queued
             }
             q1h += n;
             q1n -= n;
@@ -411,10 +496,12 @@ __global__ void __launch_bounds__(PF_WARPS * 32) prefilterKernel(PrefilterArgs a
                 const bool validE = eidx < totalM;
                 const uint32_t ownerM = warpOwnerOfSlot(exclM, m != 0, ec, lane);
                 const uint32_t oExcl = __shfl_sync(0xffffffffu, exclM, ownerM);
-                const uint32_t oLo = __shfl_sync(0xffffffffu, bLo, ownerM);
+                const uint32_t oX = __shfl_sync(0xffffffffu, rx, ownerM);
+                const uint32_t oY = __shfl_sync(0xffffffffu, ry, ownerM);
                 const uint32_t oP = __shfl_sync(0xffffffffu, pq, ownerM);
                 if (validE) {
-                    const uint2 en = __ldg(&a.ent[oLo + (eidx - oExcl)]);
+                    uint2 en = make_uint2(oX, oY & 0xffffu);
+                    if (!(oY >> 31)) en = ldStream2(&a.ent[oX + (eidx - oExcl)], pol);
                     prefetchL2(&tab[en.x]);
                     const uint32_t slot = (q2h + q2n + lane) & (PF_Q2CAP - 1);
                     Q2t[slot] = en.x;
@@ -486,13 +573,12 @@ __global__ void __launch_bounds__(PF_WARPS * 32) prefilterKernel(PrefilterArgs a
                     stProbes += (lane == 0) ? totalProbes : 0;
 
                     for (uint32_t pc = 0; pc < totalProbes; pc += 32 * PF_UNROLL) {
-                        uint2 w[PF_UNROLL];
-                        uint32_t kmerBit[PF_UNROLL];
+                        uint32_t w[PF_UNROLL], kmerW[PF_UNROLL];
 #pragma unroll
                         for (int j = 0; j < PF_UNROLL; j++) {
                             const uint32_t base = pc + 32u * j;
-                            w[j] = make_uint2(0u, 0u);
-                            kmerBit[j] = 0;
+                            w[j] = 0;
+                            kmerW[j] = 0;
                             if (base < totalProbes) {
                                 const uint32_t ownerA = warpOwnerOfSlot(exclA, nb != 0, base, lane);
                                 const uint32_t ownerExcl = __shfl_sync(0xffffffffu, exclA, ownerA);
@@ -500,18 +586,24 @@ __global__ void __launch_bounds__(PF_WARPS * 32) prefilterKernel(PrefilterArgs a
                                 if (base + lane < totalProbes) {
                                     const uint32_t c = base + lane - ownerExcl;
                                     const uint32_t xc = (c < (uint32_t)PF_CAP2) ? (uint32_t)X2[c] : (uint32_t)__ldg(&x2[c]);
-                                    const uint32_t kmer = ownerX + N3 * xc;            // KmerGenerator.cpp:207
-                                    w[j] = __ldg(&a.bm[kmer >> 5]);
-                                    kmerBit[j] = kmer & 31u;
+                                    kmerW[j] = ownerX + N3 * xc;            // KmerGenerator.cpp:207
+                                    w[j] = ldKeep(&a.bmBits[kmerW[j] >> 5], polKeep);
                                 }
                             }
+                        }
+                        uint32_t rk[PF_UNROLL];
+#pragma unroll
+                        for (int j = 0; j < PF_UNROLL; j++) {
+                            rk[j] = 0;
+                            if ((w[j] >> (kmerW[j] & 31u)) & 1u) rk[j] = __ldg(&a.bmRank[kmerW[j] >> 5]);   // idle lanes carry w = 0
                         }
 #pragma unroll
                         for (int j = 0; j < PF_UNROLL; j++) {
                             if (pc + 32u * j < totalProbes) {
-                                const bool has = ((w[j].x >> kmerBit[j]) & 1u) != 0;   // idle lanes carry w = 0
-                                const uint32_t ci = w[j].y + __popc(w[j].x & ((1u << kmerBit[j]) - 1u));
-                                if (has) prefetchL2(&a.cOff[ci]);
+                                const uint32_t bit = kmerW[j] & 31u;
+                                const bool has = ((w[j] >> bit) & 1u) != 0;
+                                const uint32_t ci = rk[j] + __popc(w[j] & ((1u << bit) - 1u));
+                                if (has) prefetchL2(&a.rows[ci]);
                                 const uint32_t hb = __ballot_sync(0xffffffffu, has);
                                 if (has) {
                                     const uint32_t slot = (q1h + q1n + __popc(hb & ltMask)) & (PF_Q1CAP - 1);
@@ -535,19 +627,24 @@ __global__ void __launch_bounds__(PF_WARPS * 32) prefilterKernel(PrefilterArgs a
         __syncwarp();
 
         // ---------------- diagonal scores (UngappedAlignment::align), capped at 255
-        {
-            uint32_t resid = 0;
-            for (uint32_t c = lane; c < nCand; c += 32) {
-                const uint64_t v = cand[c];
-                const uint32_t t = (uint32_t)(v >> 32);
-                const int diag = (int)(int16_t)(uint16_t)(v >> 16);
-                int s = diagonalScore(a, sSub, qBase, Lq, t, diag, resid);
-                s = min(s, 255);
-                cand[c] = v | ((uint64_t)s << 8);
-                // best score per target: epoch E+1 words order above every epoch-E word
-                atomicMax(&tab[t], ((E + 1) << 24) | (uint32_t)s);
+        // The whole warp scores one diagonal at a time: lanes take consecutive residues (coalesced reads of query and
+        // target), the running max(0, run + s) becomes prefix sums minus their running minimum (warp scans).
+        for (uint32_t c0 = 0; c0 < nCand; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            const uint64_t v = (c < nCand) ? cand[c] : 0ull;
+            const uint32_t nHere = min(32u, nCand - c0);
+            int myScore = 0;
+            for (uint32_t j = 0; j < nHere; j++) {
+                const uint64_t vj = __shfl_sync(0xffffffffu, v, j);
+                const int sc = diagonalScoreWarp(a, sSub, qBase, Lq, (uint32_t)(vj >> 32), (int)(int16_t)(uint16_t)(vj >> 16), lane, stDiagRes);
+                if (lane == j) myScore = sc;
             }
-            stDiagRes += resid;
+            if (c < nCand) {
+                const int sc = min(myScore, 255);
+                cand[c] = v | ((uint64_t)sc << 8);
+                // best score per target: epoch E+1 words order above every epoch-E word
+                atomicMax(&tab[(uint32_t)(v >> 32)], ((E + 1) << 24) | (uint32_t)sc);
+            }
         }
         __threadfence_block();
         __syncwarp();
@@ -878,22 +975,21 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
     // occupancy bitmap + rank, compact bucket starts
     {
         const uint32_t nWords = (NKMER + 31) / 32;
-        DevBuf<uint32_t> bits, cnt, rank;
-        if ((rc = bits.alloc(nWords)) || (rc = cnt.alloc(nWords + 1)) || (rc = rank.alloc(nWords + 1)) || (rc = idx->bm.alloc(nWords))) return rc;
+        DevBuf<uint32_t> cnt;
+        if ((rc = idx->bmBits.alloc(nWords)) || (rc = cnt.alloc(nWords + 1)) || (rc = idx->bmRank.alloc(nWords + 1))) return rc;
         SD_CUDA(cudaMemsetAsync(cnt.p + nWords, 0, sizeof(uint32_t), st));
-        occupancyBits<<<gridFor((uint64_t)((nWords + 31) / 32) * 32, 256), 256, 0, st>>>(kOff.p, nWords, bits.p, cnt.p);
+        occupancyBits<<<gridFor((uint64_t)((nWords + 31) / 32) * 32, 256), 256, 0, st>>>(kOff.p, nWords, idx->bmBits.p, cnt.p);
         size_t tmpBytes = 0;
-        SD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, cnt.p, rank.p, (int64_t)nWords + 1, st));
+        SD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, cnt.p, idx->bmRank.p, (int64_t)nWords + 1, st));
         DevBuf<uint8_t> tmp;
         if ((rc = tmp.alloc(tmpBytes)) != SD_OK) return rc;
-        SD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, cnt.p, rank.p, (int64_t)nWords + 1, st));
+        SD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, cnt.p, idx->bmRank.p, (int64_t)nWords + 1, st));
         uint32_t nDistinct = 0;
-        SD_CUDA(cudaMemcpyAsync(&nDistinct, rank.p + nWords, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SD_CUDA(cudaMemcpyAsync(&nDistinct, idx->bmRank.p + nWords, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         SD_CUDA(cudaStreamSynchronize(st));
         idx->nDistinct = nDistinct;
-        if ((rc = idx->cOff.alloc((size_t)nDistinct + 1)) != SD_OK) return rc;
-        compactOffsets<<<gridFor((uint64_t)nWords * 32, 256), 256, 0, st>>>(kOff.p, bits.p, rank.p, nWords, idx->bm.p, idx->cOff.p);
-        SD_CUDA(cudaMemcpyAsync(idx->cOff.p + nDistinct, &nEnt, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        if ((rc = idx->rows.alloc((size_t)nDistinct + 1)) != SD_OK) return rc;
+        compactRows<<<gridFor((uint64_t)nWords * 32, 256), 256, 0, st>>>(kOff.p, idx->bmBits.p, idx->bmRank.p, nWords, idx->ent.p, idx->rows.p);
         ctx->launches += 2;
         SD_CUDA(cudaGetLastError());
         SD_CUDA(cudaStreamSynchronize(st));
@@ -1028,7 +1124,7 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
 
     PrefilterArgs a{};
     a.tRes = idx->res.p; a.tOff = idx->off.p; a.nT = idx->nT;
-    a.bm = idx->bm.p; a.cOff = idx->cOff.p; a.ent = idx->ent.p;
+    a.bmBits = idx->bmBits.p; a.bmRank = idx->bmRank.p; a.rows = idx->rows.p; a.ent = idx->ent.p;
     a.e3score = ctx->e3score.p; a.e3index = ctx->e3index.p; a.e3cnt = ctx->e3cnt.p; a.diagSub = dDiagSub.p;
     a.q.code = dCode.p; a.q.off = dOff.p; a.q.corr = dCorr.p; a.q.thr = dThr.p;
     a.nQ = nq; a.order = dOrder.p; a.queryFirst = query_first; a.sameDb = par->same_db;
@@ -1039,11 +1135,38 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     a.out = dOut.p; a.outCount = dOutCount.p; a.stats = dStats.p; a.nextQuery = dNext.p; a.errQuery = dNext.p + 1;
 
     SD_CUDA(cudaEventRecord(evk0, st));
+    static const int envEvict = getenv("SD_PF_EVICT") ? atoi(getenv("SD_PF_EVICT")) : 1;
+    static const int envPersist = getenv("SD_PF_PERSIST") ? atoi(getenv("SD_PF_PERSIST")) : 1;
+    static const int envGran = getenv("SD_PF_L2GRAN") ? atoi(getenv("SD_PF_L2GRAN")) : 0;
+    a.evictFirst = envEvict;
+    if (envGran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)envGran);
+    if (envPersist) {
+        // the occupancy bitmap is probed once per similar k-mer: keep it in the persisting part of the L2
+        int maxPersist = 0, maxWin = 0;
+        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+        cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+        const size_t bmBytes = idx->bmBits.n * sizeof(uint32_t);
+        if (maxPersist > 0 && maxWin > 0) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)maxPersist, bmBytes + (8u << 20)));
+            cudaStreamAttrValue av{};
+            av.accessPolicyWindow.base_ptr = (void *)idx->bmBits.p;
+            av.accessPolicyWindow.num_bytes = std::min<size_t>(bmBytes, (size_t)maxWin);
+            av.accessPolicyWindow.hitRatio = 1.0f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+        }
+    }
     SD_CUDA(cudaFuncSetAttribute(prefilterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_DYN_SMEM));
     prefilterKernel<<<nCta, PF_WARPS * 32, PF_DYN_SMEM, st>>>(a);
     ctx->launches++;
     SD_CUDA(cudaGetLastError());
     SD_CUDA(cudaEventRecord(evk1, st));
+    if (envPersist) {
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+    }
 
     std::vector<uint32_t> hCount(nq);
     unsigned long long hStats[ST_N];

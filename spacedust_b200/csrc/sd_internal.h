@@ -193,7 +193,8 @@ struct sd_target_index {
     uint32_t maxLen = 0;
     sd::DevBuf<uint32_t> off;          // nT+1
     uint32_t nDistinct = 0;            // k-mers with a non-empty bucket
-    sd::DevBuf<uint2> bm;              // per 32 k-mers: {occupancy bits, rank of the first} -- 16 MB, L2 resident
-    sd::DevBuf<uint32_t> cOff;         // nDistinct+1 bucket starts (compact rows)
+    sd::DevBuf<uint32_t> bmBits;       // per 32 k-mers: occupancy bits -- 8 MB, L2 resident
+    sd::DevBuf<uint32_t> bmRank;       // per 32 k-mers: row of the first non-empty k-mer
+    sd::DevBuf<uint2> rows;            // per non-empty k-mer: inline single entry or {start, length} into ent
     sd::DevBuf<uint2> ent;             // bucket entries: {target id, first position of the k-mer in that target}
 };
