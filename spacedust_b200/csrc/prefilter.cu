@@ -294,6 +294,8 @@ struct PrefilterArgs {
     uint32_t *nextQuery;
     uint32_t *errQuery;
     int evictFirst;            // L2 evict-first policy for the streamed data
+    int prefetch;              // bit 0: table words, bit 1: bucket rows
+    int debugSkip;             // profiling only (SD_PF_SKIP): bit 0 drops stage C, bit 1 drops stage B -- results are then wrong
 };
 
 enum { ST_PROBES = 0, ST_MATCHES, ST_DIAGRES, ST_HITS, ST_CANDS, ST_TRUNC, ST_ERR_CAND, ST_ERR_RESCORE, ST_N };
@@ -367,7 +369,7 @@ __device__ __forceinline__ int diagonalScoreWarp(const PrefilterArgs &a, const i
     return __reduce_max_sync(0xffffffffu, best);
 }
 
-__global__ void __launch_bounds__(PF_WARPS * 32, 3) prefilterKernel(PrefilterArgs a) {
+__global__ void __launch_bounds__(PF_WARPS * 32, 4) prefilterKernel(PrefilterArgs a) {
     __shared__ uint16_t sX2[PF_WARPS][PF_CAP2];
     __shared__ uint32_t sHist[PF_WARPS][256];
     __shared__ int8_t sSub[AA * AA];
@@ -440,6 +442,7 @@ __global__ void __launch_bounds__(PF_WARPS * 32, 3) prefilterKernel(PrefilterArg
             }
             q2h += n;
             q2n -= n;
+            if (a.debugSkip & 1) return;
             const uint32_t d8 = diag16 & 0xffu;
             // --- CacheFriendlyOperations::findDuplicates, restated per target in stream order
             const uint32_t grp = __match_any_sync(0xffffffffu, t);
@@ -478,6 +481,7 @@ __global__ void __launch_bounds__(PF_WARPS * 32, 3) prefilterKernel(PrefilterArg
         auto stageB = [&](const uint32_t n) {
             __syncwarp();
             uint32_t rx = 0, ry = 0, m = 0, pq = 0;
+            if (a.debugSkip & 2) { q1h += n; q1n -= n; return; }
             if (lane < n) {
                 const uint32_t slot = (q1h + lane) & (PF_Q1CAP - 1);
                 const uint2 row = ldStream2(&a.rows[Q1c[slot]], pol);
@@ -502,7 +506,7 @@ __global__ void __launch_bounds__(PF_WARPS * 32, 3) prefilterKernel(PrefilterArg
                 if (validE) {
                     uint2 en = make_uint2(oX, oY & 0xffffu);
                     if (!(oY >> 31)) en = ldStream2(&a.ent[oX + (eidx - oExcl)], pol);
-                    prefetchL2(&tab[en.x]);
+                    if (a.prefetch & 1) prefetchL2(&tab[en.x]);
                     const uint32_t slot = (q2h + q2n + lane) & (PF_Q2CAP - 1);
                     Q2t[slot] = en.x;
                     Q2d[slot] = (uint16_t)(oP - en.y);
@@ -603,7 +607,7 @@ __global__ void __launch_bounds__(PF_WARPS * 32, 3) prefilterKernel(PrefilterArg
                                 const uint32_t bit = kmerW[j] & 31u;
                                 const bool has = ((w[j] >> bit) & 1u) != 0;
                                 const uint32_t ci = rk[j] + __popc(w[j] & ((1u << bit) - 1u));
-                                if (has) prefetchL2(&a.rows[ci]);
+                                if (has && (a.prefetch & 2)) prefetchL2(&a.rows[ci]);
                                 const uint32_t hb = __ballot_sync(0xffffffffu, has);
                                 if (has) {
                                     const uint32_t slot = (q1h + q1n + __popc(hb & ltMask)) & (PF_Q1CAP - 1);
@@ -976,20 +980,21 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
     {
         const uint32_t nWords = (NKMER + 31) / 32;
         DevBuf<uint32_t> cnt;
-        if ((rc = idx->bmBits.alloc(nWords)) || (rc = cnt.alloc(nWords + 1)) || (rc = idx->bmRank.alloc(nWords + 1))) return rc;
+        if ((rc = idx->bmBits.alloc(2 * (size_t)nWords + 2)) || (rc = cnt.alloc(nWords + 1))) return rc;
+        idx->bmRank = idx->bmBits.p + nWords;      // bits and rank share one allocation: one persisting-L2 window covers both
         SD_CUDA(cudaMemsetAsync(cnt.p + nWords, 0, sizeof(uint32_t), st));
         occupancyBits<<<gridFor((uint64_t)((nWords + 31) / 32) * 32, 256), 256, 0, st>>>(kOff.p, nWords, idx->bmBits.p, cnt.p);
         size_t tmpBytes = 0;
-        SD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, cnt.p, idx->bmRank.p, (int64_t)nWords + 1, st));
+        SD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, cnt.p, idx->bmRank, (int64_t)nWords + 1, st));
         DevBuf<uint8_t> tmp;
         if ((rc = tmp.alloc(tmpBytes)) != SD_OK) return rc;
-        SD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, cnt.p, idx->bmRank.p, (int64_t)nWords + 1, st));
+        SD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, cnt.p, idx->bmRank, (int64_t)nWords + 1, st));
         uint32_t nDistinct = 0;
-        SD_CUDA(cudaMemcpyAsync(&nDistinct, idx->bmRank.p + nWords, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SD_CUDA(cudaMemcpyAsync(&nDistinct, idx->bmRank + nWords, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         SD_CUDA(cudaStreamSynchronize(st));
         idx->nDistinct = nDistinct;
         if ((rc = idx->rows.alloc((size_t)nDistinct + 1)) != SD_OK) return rc;
-        compactRows<<<gridFor((uint64_t)nWords * 32, 256), 256, 0, st>>>(kOff.p, idx->bmBits.p, idx->bmRank.p, nWords, idx->ent.p, idx->rows.p);
+        compactRows<<<gridFor((uint64_t)nWords * 32, 256), 256, 0, st>>>(kOff.p, idx->bmBits.p, idx->bmRank, nWords, idx->ent.p, idx->rows.p);
         ctx->launches += 2;
         SD_CUDA(cudaGetLastError());
         SD_CUDA(cudaStreamSynchronize(st));
@@ -1100,7 +1105,7 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
 
     const uint32_t maxHits = std::min<uint32_t>((uint32_t)std::max(par->max_seqs, 1), idx->nT);
     const int binSize = par->bin_size > 0 ? par->bin_size : referenceBinSize(idx->nT);
-    const int ctasPerSm = 3;
+    static const int ctasPerSm = getenv("SD_PF_CTAS") ? atoi(getenv("SD_PF_CTAS")) : 4;
     const uint32_t nCta = std::max(1u, std::min<uint32_t>((uint32_t)(ctx->smCount * ctasPerSm), (nq + PF_WARPS - 1) / PF_WARPS));
     const uint32_t nWarps = nCta * PF_WARPS;
     const uint32_t candCap = 32768;
@@ -1124,7 +1129,7 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
 
     PrefilterArgs a{};
     a.tRes = idx->res.p; a.tOff = idx->off.p; a.nT = idx->nT;
-    a.bmBits = idx->bmBits.p; a.bmRank = idx->bmRank.p; a.rows = idx->rows.p; a.ent = idx->ent.p;
+    a.bmBits = idx->bmBits.p; a.bmRank = idx->bmRank; a.rows = idx->rows.p; a.ent = idx->ent.p;
     a.e3score = ctx->e3score.p; a.e3index = ctx->e3index.p; a.e3cnt = ctx->e3cnt.p; a.diagSub = dDiagSub.p;
     a.q.code = dCode.p; a.q.off = dOff.p; a.q.corr = dCorr.p; a.q.thr = dThr.p;
     a.nQ = nq; a.order = dOrder.p; a.queryFirst = query_first; a.sameDb = par->same_db;
@@ -1135,10 +1140,13 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     a.out = dOut.p; a.outCount = dOutCount.p; a.stats = dStats.p; a.nextQuery = dNext.p; a.errQuery = dNext.p + 1;
 
     SD_CUDA(cudaEventRecord(evk0, st));
-    static const int envEvict = getenv("SD_PF_EVICT") ? atoi(getenv("SD_PF_EVICT")) : 1;
-    static const int envPersist = getenv("SD_PF_PERSIST") ? atoi(getenv("SD_PF_PERSIST")) : 1;
+    static const int envEvict = getenv("SD_PF_EVICT") ? atoi(getenv("SD_PF_EVICT")) : 0;
+    static const int envPersist = getenv("SD_PF_PERSIST") ? atoi(getenv("SD_PF_PERSIST")) : 0;
     static const int envGran = getenv("SD_PF_L2GRAN") ? atoi(getenv("SD_PF_L2GRAN")) : 0;
     a.evictFirst = envEvict;
+    static const int envPrefetch = getenv("SD_PF_PREFETCH") ? atoi(getenv("SD_PF_PREFETCH")) : 0;
+    a.prefetch = envPrefetch;
+    a.debugSkip = getenv("SD_PF_SKIP") ? atoi(getenv("SD_PF_SKIP")) : 0;
     if (envGran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)envGran);
     if (envPersist) {
         // the occupancy bitmap is probed once per similar k-mer: keep it in the persisting part of the L2
@@ -1147,15 +1155,16 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
         cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
         const size_t bmBytes = idx->bmBits.n * sizeof(uint32_t);
         if (maxPersist > 0 && maxWin > 0) {
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)maxPersist, bmBytes + (8u << 20)));
+            const cudaError_t e1 = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)maxPersist, bmBytes + (8u << 20)));
             cudaStreamAttrValue av{};
             av.accessPolicyWindow.base_ptr = (void *)idx->bmBits.p;
             av.accessPolicyWindow.num_bytes = std::min<size_t>(bmBytes, (size_t)maxWin);
             av.accessPolicyWindow.hitRatio = 1.0f;
             av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-            cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
-        }
+            const cudaError_t e2 = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+            if (getenv("SD_PF_DEBUG")) fprintf(stderr, "[sd] persisting L2: max %d B, window max %d B, bitmap %zu B, setLimit=%d setAttr=%d\n", maxPersist, maxWin, bmBytes, (int)e1, (int)e2);
+        } else if (getenv("SD_PF_DEBUG")) fprintf(stderr, "[sd] persisting L2 not available (max %d, window %d)\n", maxPersist, maxWin);
     }
     SD_CUDA(cudaFuncSetAttribute(prefilterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_DYN_SMEM));
     prefilterKernel<<<nCta, PF_WARPS * 32, PF_DYN_SMEM, st>>>(a);

@@ -193,8 +193,8 @@ struct sd_target_index {
     uint32_t maxLen = 0;
     sd::DevBuf<uint32_t> off;          // nT+1
     uint32_t nDistinct = 0;            // k-mers with a non-empty bucket
-    sd::DevBuf<uint32_t> bmBits;       // per 32 k-mers: occupancy bits -- 8 MB, L2 resident
-    sd::DevBuf<uint32_t> bmRank;       // per 32 k-mers: row of the first non-empty k-mer
+    sd::DevBuf<uint32_t> bmBits;       // per 32 k-mers: occupancy bits (8 MB), followed by ...
+    uint32_t *bmRank = nullptr;        // ... per 32 k-mers: row of the first non-empty k-mer (same allocation, 8 MB)
     sd::DevBuf<uint2> rows;            // per non-empty k-mer: inline single entry or {start, length} into ent
     sd::DevBuf<uint2> ent;             // bucket entries: {target id, first position of the k-mer in that target}
 };

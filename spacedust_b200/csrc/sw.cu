@@ -142,8 +142,8 @@ __device__ void swPass(const SwKernelArgs &A, const SwTask &tk, int *bnd, SwResu
                     const int open1 = __viaddmax_s32_relu(h1, -go, 0);
                     E[k] = __viaddmax_s32(e, -ge, open1);
                     fm = __viaddmax_s32(fm, -ge, open1);
-                    const int openS = __viaddmax_s32_relu(hs, -go, 0);
-                    ft = __viaddmax_s32(ft, -ge, openS);
+                    // Ft >= Fm and go >= ge: (Fm - go) <= (Ft - ge), so the gap opened from H1 also serves the exact chain
+                    ft = __viaddmax_s32(ft, -ge, open1);
                 }
                 outA = inA; outH = H[R - 1]; outFt = ft; outFm = fm;
                 prevHup = inH;
@@ -338,8 +338,8 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
                     const uint32_t open1 = __viaddmax_s16x2_relu(h1, negGo, 0u);
                     E[k] = __viaddmax_s16x2(e, negGe, open1);
                     fm = __viaddmax_s16x2(fm, negGe, open1);
-                    const uint32_t openS = __viaddmax_s16x2_relu(hs, negGo, 0u);
-                    ft = __viaddmax_s16x2(ft, negGe, openS);
+                    // Ft >= Fm and go >= ge: (Fm - go) <= (Ft - ge), so the gap opened from H1 also serves the exact chain
+                    ft = __viaddmax_s16x2(ft, negGe, open1);
                 }
                 outL = inL; outH = H[RP - 1]; outFt = ft; outFm = fm;
                 prevHup = inH;
