@@ -431,7 +431,7 @@ inline unsigned gridOf(uint64_t n, unsigned b) { return (unsigned)std::max<uint6
 // the output is defined by (query, Matcher::compareHits)).
 int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
                           const uint32_t *dPairQ, const uint32_t *dPairT, uint64_t n_pairs, uint64_t db_residues,
-                          const sd_align_params *par, std::vector<sd_alignment> &acc, std::vector<char> &pool,
+                          const sd_align_params *par, std::vector<sd_alignment> &acc, sd::CharPool &pool,
                           sd_align_stats *stats) {
     acc.clear(); pool.clear();
     if (stats) memset(stats, 0, sizeof *stats);
@@ -527,10 +527,18 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     const Evaluer evaluer((double)(db_residues ? db_residues : idx->totalRes));
     std::vector<int32_t> limit8(nq), minScore(nq);
     {
-        std::vector<int32_t> byLen(maxQ + 1, -1);
-        for (uint32_t q = 0; q < nq; q++) byLen[hLen[q]] = 0;
+        // pass marks depend only on (database size, -e, query length): kept with the context between calls
+        if (ctx->minScoreDb != (double)(db_residues ? db_residues : idx->totalRes) || ctx->minScoreThr != par->evalue_thr) {
+            ctx->minScoreByLen.clear();
+            ctx->minScoreDb = (double)(db_residues ? db_residues : idx->totalRes);
+            ctx->minScoreThr = par->evalue_thr;
+        }
+        std::vector<int32_t> &byLen = ctx->minScoreByLen;      // 0 = not computed yet, -2 = not monotone
+        if (byLen.size() < (size_t)maxQ + 1) byLen.resize(maxQ + 1, 0);
+        std::vector<uint8_t> need(maxQ + 1, 0);
+        for (uint32_t q = 0; q < nq; q++) if (byLen[hLen[q]] == 0) need[hLen[q]] = 1;
         parallelFor(maxQ + 1, [&](uint64_t L) {
-            if (byLen[L] < 0 || L == 0) return;
+            if (!need[L] || L == 0) return;
             // E(s) falls monotonically in s (checked below); the first s with E <= thr is the pass mark
             int s = 1;
             while (s < 100000 && evaluer.evalue((double)s, (double)L) > par->evalue_thr) s++;
@@ -543,13 +551,15 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
             }
             byLen[L] = mono ? s : -2;
         });
-        for (uint32_t q = 0; q < nq; q++) {
+        std::atomic<int> bad{-1};
+        parallelFor(nq, [&](uint64_t q) {
             int mn = 0;
             for (uint32_t i = hOff[q]; i < hOff[q + 1]; i++) mn = std::min(mn, (int)hCb[i]);
             limit8[q] = 255 - (std::abs(minMat) + std::abs(mn));
             minScore[q] = hLen[q] ? byLen[hLen[q]] : 1;
-            if (minScore[q] == -2) { setError("sd_align_run: E-value is not monotone in the score for query length %u", hLen[q]); return SD_ELIMIT; }
-        }
+            if (minScore[q] == -2) bad = (int)hLen[q];
+        });
+        if (bad >= 0) { setError("sd_align_run: E-value is not monotone in the score for query length %d", bad.load()); return SD_ELIMIT; }
     }
 
     tick("minScore");
@@ -721,11 +731,12 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     SD_CUDA(cudaStreamSynchronize(st));
     const std::vector<uint32_t> &identQ = hIdent;
 
-    acc.reserve(nTb + nIdent);
-    uint64_t poolBytes = 0;
-    for (uint32_t i = 0; i < nHit; i++) {
+    // every stage-2 hit owns one traceback task: slot = task index (order is fixed by the sort below)
+    std::vector<sd_alignment> traced(nTb);
+    std::vector<uint8_t> tracedOk(nTb, 0);
+    parallelFor(nHit, [&](uint64_t i) {
         const PairHit &h = hHits[i];
-        if (h.stage != 2) continue;
+        if (h.stage != 2 || h.tb >= nTb) return;
         const TbResult &tr = tres[h.tb];
         sd_alignment a;
         memset(&a, 0, sizeof a);
@@ -739,28 +750,17 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
         a.bt_len = (uint32_t)tr.btLen;
         a.bt_off = 0;
         a.pad = h.tb;                   // remember the task: its backtrace is fetched below
-        acc.push_back(a);
-    }
-    tick("gather");
-    parallelFor(acc.size(), [&](uint64_t i) {
-        sd_alignment &a = acc[i];
         a.evalue = evaluer.evalue(a.score, a.q_len);
         a.bits = evaluer.bitScore(a.score);
+        // checkCriteria (Alignment.cpp:548-567)
+        tracedOk[h.tb] = (a.evalue <= par->evalue_thr) && (a.seq_id >= par->min_seq_id) && hasCoverage(par->cov_thr, par->cov_mode, a.qcov, a.tcov) &&
+                         (a.aln_len >= par->min_aln_len);
+        traced[h.tb] = a;
     });
-    // checkCriteria (Alignment.cpp:548-567)
-    {
-        size_t w = 0;
-        for (size_t i = 0; i < acc.size(); i++) {
-            const sd_alignment &a = acc[i];
-            const bool ok = (a.evalue <= par->evalue_thr) && (a.seq_id >= par->min_seq_id) && hasCoverage(par->cov_thr, par->cov_mode, a.qcov, a.tcov) &&
-                            (a.aln_len >= par->min_aln_len);
-            if (ok) acc[w++] = a;
-        }
-        acc.resize(w);
-    }
+    tick("gather");
     // identity shortcut (scoreIdentical StripedSmithWaterman.cpp:1675-1710; note the 16-bit accumulator)
-    const size_t nTraced = acc.size();
-    for (uint32_t i = 0; i < nIdent; i++) {
+    std::vector<sd_alignment> ident(nIdent);
+    parallelFor(nIdent, [&](uint64_t i) {
         const uint32_t q = identQ[i], t = query_first + q;
         const int Lq = (int)hLen[q], Lt = (int)(tOff[t + 1] - tOff[t]);
         short sc = 0;
@@ -772,19 +772,31 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
         a.query = q; a.target = t; a.score = sc; a.evalue = evaluer.evalue(sc, Lq); a.bits = evaluer.bitScore(sc);
         a.q_start = 0; a.t_start = 0; a.q_end = Lt - 1; a.t_end = Lt - 1; a.q_len = Lq; a.t_len = Lt;
         a.qcov = 1.0f; a.tcov = 1.0f; a.seq_id = 1.0f; a.aln_len = Lt; a.bt_len = (uint32_t)Lt; a.pad = 0xffffffffu;
-        acc.push_back(a);
-    }
-    (void)nTraced;
-    tick("evalue");
-    std::sort(acc.begin(), acc.end(), [](const sd_alignment &x, const sd_alignment &y) {
-        if (x.query != y.query) return x.query < y.query;
-        if (x.evalue != y.evalue) return x.evalue < y.evalue;          // Matcher::compareHits
-        if (x.bits != y.bits) return x.bits > y.bits;
-        if (x.t_len != y.t_len) return x.t_len < y.t_len;
-        return x.target < y.target;
+        ident[i] = a;
     });
+    // bucket by query (counting sort), then order every query's list with Matcher::compareHits in parallel
+    {
+        std::vector<uint32_t> start(nq + 1, 0);
+        for (uint32_t i = 0; i < nTb; i++) if (tracedOk[i]) start[traced[i].query + 1]++;
+        for (uint32_t i = 0; i < nIdent; i++) start[ident[i].query + 1]++;
+        for (uint32_t q = 0; q < nq; q++) start[q + 1] += start[q];
+        acc.resize(start[nq]);
+        std::vector<uint32_t> cur(start.begin(), start.end() - 1);
+        for (uint32_t i = 0; i < nTb; i++) if (tracedOk[i]) acc[cur[traced[i].query]++] = traced[i];
+        for (uint32_t i = 0; i < nIdent; i++) acc[cur[ident[i].query]++] = ident[i];
+        parallelFor(nq, [&](uint64_t q) {
+            std::sort(acc.begin() + start[q], acc.begin() + start[q + 1], [](const sd_alignment &x, const sd_alignment &y) {
+                if (x.evalue != y.evalue) return x.evalue < y.evalue;          // Matcher::compareHits
+                if (x.bits != y.bits) return x.bits > y.bits;
+                if (x.t_len != y.t_len) return x.t_len < y.t_len;
+                return x.target < y.target;
+            });
+        });
+    }
+    tick("evalue+sort");
+    uint64_t poolBytes = 0;
     for (const sd_alignment &a : acc) poolBytes += a.bt_len;
-    pool.resize(poolBytes + 1);
+    pool.resize(poolBytes);
     {
         // task offsets in the device pool
         std::vector<TbTask> hTb(nTb);
@@ -800,9 +812,8 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
             else memcpy(pool.data() + a.bt_off, devPool + hTb[a.pad].btOff, a.bt_len);
             a.pad = 0;
         });
-        pool.resize(poolBytes);
     }
-    tick("sort+pool");
+    tick("pool");
     if (timing) fprintf(stderr, "[sd_align]%s\n", tLog.c_str());
     SD_CUDA(cudaEventRecord(ev1, st));
     SD_CUDA(cudaStreamSynchronize(st));
@@ -839,7 +850,7 @@ extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, c
     SD_CUDA(cudaMemcpyAsync(dQ.p, pair_q, n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     SD_CUDA(cudaMemcpyAsync(dT.p, pair_t, n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     std::vector<sd_alignment> acc;
-    std::vector<char> pool;
+    sd::CharPool pool;
     if ((rc = sd_align_device_pairs(ctx, idx, queries, query_first, dQ.p, dT.p, n_pairs, db_residues, par, acc, pool, stats))) return rc;
     uint64_t used = 0;
     for (const sd_alignment &a : acc) used += a.bt_len;
@@ -856,7 +867,7 @@ extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, c
 
 int sd_align_device_hits(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
                          const sd_prefilter_hit *dHits, uint64_t n_hits, uint64_t db_residues, const sd_align_params *par,
-                         std::vector<sd_alignment> &acc, std::vector<char> &pool, sd_align_stats *stats) {
+                         std::vector<sd_alignment> &acc, sd::CharPool &pool, sd_align_stats *stats) {
     acc.clear(); pool.clear();
     if (stats) memset(stats, 0, sizeof *stats);
     if (n_hits == 0) return SD_OK;

@@ -24,6 +24,10 @@
 #include <map>
 #include <memory>
 
+#include <chrono>
+#include <cstdlib>
+#include <string>
+
 #include "sd_internal.h"
 
 namespace sd {
@@ -293,54 +297,90 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
     SD_CUDA(cudaEventCreate(&ev0)); SD_CUDA(cudaEventCreate(&ev1)); SD_CUDA(cudaEventCreate(&evA)); SD_CUDA(cudaEventCreate(&evB));
     SD_CUDA(cudaEventRecord(ev0, st));
 
+    const bool timing = getenv("SD_TIMING") != nullptr;
+    auto tPrev = std::chrono::steady_clock::now();
+    std::string tLog;
+    auto tick = [&](const char *name) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        char b[96];
+        snprintf(b, sizeof b, " %s=%.1f", name, std::chrono::duration<double, std::milli>(now - tPrev).count());
+        tLog += b;
+        tPrev = now;
+    };
     // ---- besthitbyset: per query gene and target set the first alignment with the smallest printed E-value
     std::vector<BestHit> best;
     best.reserve(n_alns);
     std::vector<double> evPrinted(n_alns);        // align prints %.3E, besthitbyset parses it
     parallelFor(n_alns, [&](uint64_t i) { evPrinted[i] = roundTrip3E(alns[i].evalue); });
+    tick("evprint");
     {
-        std::vector<std::pair<uint32_t, uint32_t>> grp;   // (target set, alignment index)
-        uint64_t i = 0;
-        while (i < n_alns) {
-            uint64_t j = i;
-            const uint32_t q = alns[i].query;
-            if (q >= nq) { setError("sd_cluster_run: alignment %llu has query %u out of range", (unsigned long long)i, q); return SD_EINVAL; }
-            grp.clear();
-            while (j < n_alns && alns[j].query == q) {
-                if (alns[j].target >= nt) { setError("sd_cluster_run: alignment %llu has target out of range", (unsigned long long)j); return SD_EINVAL; }
-                grp.emplace_back(t_set_of[alns[j].target], (uint32_t)j);
-                j++;
+        // query groups (alignments arrive grouped by ascending query), validated once
+        std::vector<uint64_t> gStart;
+        gStart.reserve(nq + 1);
+        for (uint64_t i = 0; i < n_alns; i++) {
+            if (i == 0 || alns[i].query != alns[i - 1].query) {
+                if (i && alns[i].query < alns[i - 1].query) { setError("sd_cluster_run: alignments must be grouped by ascending query"); return SD_EINVAL; }
+                if (alns[i].query >= nq) { setError("sd_cluster_run: alignment %llu has query %u out of range", (unsigned long long)i, alns[i].query); return SD_EINVAL; }
+                gStart.push_back(i);
             }
-            if (j < n_alns && alns[j].query < q) { setError("sd_cluster_run: alignments must be grouped by ascending query"); return SD_EINVAL; }
-            std::stable_sort(grp.begin(), grp.end(), [](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) { return a.first < b.first; });
-            size_t g = 0;
-            while (g < grp.size()) {
-                size_t h = g;
-                double bestEval = DBL_MAX;
-                int64_t bestIdx = -1;
-                while (h < grp.size() && grp[h].first == grp[g].first) {
-                    const double ev = evPrinted[grp[h].second];
-                    if (ev < bestEval) { bestEval = ev; bestIdx = grp[h].second; }
-                    h++;
-                }
-                if (bestIdx >= 0) {
-                    BestHit bh;
-                    bh.aln = (uint32_t)bestIdx; bh.q = q; bh.qSet = q_set_of[q]; bh.tSet = grp[g].first;
-                    bh.logP = bestEval;      // turned into the printed log P-value below (parallel)
-                    if (bh.qSet >= n_q_sets || bh.tSet >= n_t_sets) { setError("sd_cluster_run: set index out of range"); return SD_EINVAL; }
-                    best.push_back(bh);
-                }
-                g = h;
-            }
-            i = j;
+            if (alns[i].target >= nt) { setError("sd_cluster_run: alignment %llu has target out of range", (unsigned long long)i); return SD_EINVAL; }
         }
+        const uint64_t nGroups = gStart.size();
+        gStart.push_back(n_alns);
+        const unsigned nChunks = 256;
+        std::vector<std::vector<BestHit>> part(nChunks);
+        std::atomic<int> badSet{0};
+        parallelChunks(nGroups, nChunks, [&](unsigned c, uint64_t lo, uint64_t hi) {
+            std::vector<std::pair<uint32_t, uint32_t>> grp;   // (target set, alignment index)
+            std::vector<BestHit> &out = part[c];
+            for (uint64_t gi = lo; gi < hi; gi++) {
+                const uint32_t q = alns[gStart[gi]].query;
+                grp.clear();
+                for (uint64_t j = gStart[gi]; j < gStart[gi + 1]; j++) grp.emplace_back(t_set_of[alns[j].target], (uint32_t)j);
+                std::stable_sort(grp.begin(), grp.end(), [](const std::pair<uint32_t, uint32_t> &a, const std::pair<uint32_t, uint32_t> &b) { return a.first < b.first; });
+                size_t g = 0;
+                while (g < grp.size()) {
+                    size_t h = g;
+                    double bestEval = DBL_MAX;
+                    int64_t bestIdx = -1;
+                    while (h < grp.size() && grp[h].first == grp[g].first) {
+                        const double ev = evPrinted[grp[h].second];
+                        if (ev < bestEval) { bestEval = ev; bestIdx = grp[h].second; }
+                        h++;
+                    }
+                    if (bestIdx >= 0) {
+                        BestHit bh;
+                        bh.aln = (uint32_t)bestIdx; bh.q = q; bh.qSet = q_set_of[q]; bh.tSet = grp[g].first;
+                        bh.logP = bestEval;      // turned into the printed log P-value below (parallel)
+                        if (bh.qSet >= n_q_sets || bh.tSet >= n_t_sets) badSet = 1;
+                        out.push_back(bh);
+                    }
+                    g = h;
+                }
+            }
+        });
+        if (badSet) { setError("sd_cluster_run: set index out of range"); return SD_EINVAL; }
+        for (unsigned c = 0; c < nChunks; c++) best.insert(best.end(), part[c].begin(), part[c].end());
     }
+    tick("besthit");
     parallelFor(best.size(), [&](uint64_t i) { best[i].logP = roundTrip3E(computeLogPval(best[i].logP)); });
     // ---- mergeresultsbyset + combinehits: group by (query set, target set), members in gene order
-    std::stable_sort(best.begin(), best.end(), [](const BestHit &a, const BestHit &b) {
-        if (a.qSet != b.qSet) return a.qSet < b.qSet;
-        return a.tSet < b.tSet;
-    });
+    if ((uint64_t)n_q_sets * n_t_sets <= (1ull << 24)) {
+        // stable counting sort on the genome pair
+        std::vector<uint32_t> start((size_t)n_q_sets * n_t_sets + 1, 0);
+        for (const BestHit &b : best) start[(size_t)b.qSet * n_t_sets + b.tSet + 1]++;
+        for (size_t i = 1; i < start.size(); i++) start[i] += start[i - 1];
+        std::vector<BestHit> sorted(best.size());
+        for (const BestHit &b : best) sorted[start[(size_t)b.qSet * n_t_sets + b.tSet]++] = b;
+        best.swap(sorted);
+    } else {
+        std::stable_sort(best.begin(), best.end(), [](const BestHit &a, const BestHit &b) {
+            if (a.qSet != b.qSet) return a.qSet < b.qSet;
+            return a.tSet < b.tSet;
+        });
+    }
+    tick("pairsort");
     struct Match { uint32_t qSet, tSet, first, n; };
     std::vector<Match> matches;
     std::vector<uint32_t> mAln;       // alignment index per kept hit
@@ -370,6 +410,7 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
         }
     }
     parallelFor(mPval.size(), [&](uint64_t i) { mPval[i] = roundTrip3E(std::exp(mPval[i])); });
+    tick("combine");
     // ---- clusterhits: genome pairs with at least two hits go to the device
     uint32_t maxOrf = 0;
     for (uint32_t s = 0; s < n_q_sets; s++) maxOrf = std::max(maxOrf, q_set_size[s]);
@@ -411,6 +452,7 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
         devMatch.push_back((uint32_t)mi);
         dMatchOff.push_back((uint32_t)hQ.size());
     }
+    tick("matches");
     const uint32_t nDev = (uint32_t)devMatch.size();
     std::vector<uint32_t> hRoot(hQ.size());
     unsigned long long hStat[2] = {0, 0};
@@ -460,11 +502,12 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
         cudaEventElapsedTime(&ms, evA, evB);
         kernelMs = ms;
     }
+    tick("kernel");
     // ---- clusters of each genome pair in node order; thresholds (ClusterHits.cpp:456-485)
     const uint32_t cls = (uint32_t)std::max(par->cluster_size, 0);
     std::vector<std::vector<sd_cluster>> partC(nDev);
     std::vector<std::vector<sd_cluster_member>> partM(nDev);
-    parallelFor(nDev, [&](uint64_t di64) {
+    parallelItems(nDev, [&](uint64_t di64) {
         const uint32_t di = (uint32_t)di64;
         std::vector<sd_cluster> &outC = partC[di];
         std::vector<sd_cluster_member> &outM = partM[di];
@@ -537,6 +580,8 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
     }
     if (!outC.empty()) memcpy(clusters, outC.data(), outC.size() * sizeof(sd_cluster));
     if (!outM.empty()) memcpy(members, outM.data(), outM.size() * sizeof(sd_cluster_member));
+    tick("assemble");
+    if (timing) fprintf(stderr, "[sd_cluster]%s\n", tLog.c_str());
     SD_CUDA(cudaEventRecord(ev1, st));
     SD_CUDA(cudaStreamSynchronize(st));
     if (stats) {

@@ -8,7 +8,7 @@
 
 struct sd_search_result {
     std::vector<sd_alignment> alns;
-    std::vector<char> pool;
+    sd::CharPool pool;
     std::vector<sd_cluster> clusters;
     std::vector<sd_cluster_member> members;
 };

@@ -9,6 +9,7 @@
 #include <atomic>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/sdgpu.h"
@@ -126,6 +127,59 @@ inline void parallelFor(uint64_t n, F fn) {
 }
 
 
+// few heavy items (genome pairs, ...): one item per grab, always threaded
+template <typename F>
+inline void parallelItems(uint64_t n, F fn) {
+    unsigned nThreads = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min(std::thread::hardware_concurrency(), 64u), n));
+    std::atomic<uint64_t> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const uint64_t i = next.fetch_add(1);
+            if (i >= n) break;
+            fn(i);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nThreads; t++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+}
+
+// byte vector whose resize() does not zero-fill (backtrace pools are ~100 MB and completely overwritten)
+template <typename T>
+struct NoInitAlloc {
+    using value_type = T;
+    NoInitAlloc() = default;
+    template <typename U> NoInitAlloc(const NoInitAlloc<U> &) {}
+    T *allocate(size_t n) { return static_cast<T *>(::operator new(n * sizeof(T))); }
+    void deallocate(T *p, size_t) { ::operator delete(p); }
+    template <typename U, typename... A> void construct(U *p, A &&...a) { if (sizeof...(A)) ::new ((void *)p) U(std::forward<A>(a)...); }
+    template <typename U> bool operator==(const NoInitAlloc<U> &) const { return true; }
+    template <typename U> bool operator!=(const NoInitAlloc<U> &) const { return false; }
+};
+using CharPool = std::vector<char, NoInitAlloc<char>>;
+
+// run fn(chunk, lo, hi) over [0,n) split into nChunks contiguous ranges (deterministic partition, any thread order)
+template <typename F>
+inline void parallelChunks(uint64_t n, unsigned nChunks, F fn) {
+    if (nChunks == 0) nChunks = 1;
+    unsigned nThreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    if (n < 4096) nThreads = 1;
+    std::atomic<unsigned> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const unsigned c = next.fetch_add(1);
+            if (c >= nChunks) break;
+            const uint64_t lo = n * c / nChunks, hi = n * (c + 1) / nChunks;
+            if (hi > lo) fn(c, lo, hi);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nThreads; t++) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+}
+
 struct SwBatch;
 struct SwTask;
 struct SwResult;
@@ -157,6 +211,9 @@ struct sd_context {
     sd::DevBuf<uint16_t> e3index;
     sd::DevBuf<uint16_t> e3cnt;      // 8000 x 512 cumulative score counts of the rows (8 MB, L2 resident)
     bool haveExt3 = false;
+    // align: smallest passing raw score per query length for (database residues, -e)
+    double minScoreDb = -1, minScoreThr = -1;
+    std::vector<int32_t> minScoreByLen;
 };
 
 struct sd_query_batch {
@@ -174,11 +231,11 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
                       sd_prefilter_stats *stats, sd::DevBuf<sd_prefilter_hit> *keepOnDevice);
 int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
                           const uint32_t *dPairQ, const uint32_t *dPairT, uint64_t n_pairs, uint64_t db_residues,
-                          const sd_align_params *par, std::vector<sd_alignment> &acc, std::vector<char> &pool,
+                          const sd_align_params *par, std::vector<sd_alignment> &acc, sd::CharPool &pool,
                           sd_align_stats *stats);
 int sd_align_device_hits(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
                          const sd_prefilter_hit *dHits, uint64_t n_hits, uint64_t db_residues, const sd_align_params *par,
-                         std::vector<sd_alignment> &acc, std::vector<char> &pool, sd_align_stats *stats);
+                         std::vector<sd_alignment> &acc, sd::CharPool &pool, sd_align_stats *stats);
 
 struct sd_target_index {
     sd_context *ctx = nullptr;
