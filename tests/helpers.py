@@ -177,6 +177,24 @@ def run_ref(args, cwd=None, threads=None):
     return r.stdout.decode()
 
 
+def read_lookup(db):
+    """<db>.lookup -> {key: name}."""
+    out = {}
+    for line in open(db + ".lookup"):
+        a = line.rstrip("\n").split("\t")
+        out[int(a[0])] = a[1]
+    return out
+
+
+def read_source(db):
+    """<db>.source -> {filename: set key}."""
+    out = {}
+    for line in open(db + ".source"):
+        a = line.rstrip("\n").split("\t")
+        out[a[1]] = int(a[0])
+    return out
+
+
 # ----------------------------------------------------------------------------- oracle: align
 class OrcAlignParams(ctypes.Structure):
     _fields_ = [("evalThr", ctypes.c_double), ("seqIdThr", ctypes.c_double), ("covThr", ctypes.c_float),

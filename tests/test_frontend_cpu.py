@@ -1,0 +1,109 @@
+"""CPU tests of the drop-in boundary: the C-ABI library exports every symbol include/sdgpu.h declares, the product fails
+loudly without a CUDA device (no CPU fallback), and the native `sdb200 createsetdb` writes the reference's set DB byte for byte."""
+import ctypes
+import hashlib
+import json
+import os
+import re
+import shutil
+import subprocess
+import tempfile
+
+import pytest
+
+import helpers
+import spacedust_b200 as sd
+from spacedust_b200 import synth
+
+SDB200 = os.path.join(helpers.ROOT, "spacedust_b200", "sdb200")
+
+
+def _declared_symbols():
+    text = open(os.path.join(helpers.ROOT, "include", "sdgpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sd_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_symbols()
+    assert len(names) >= 24 and "sd_clustersearch_run" in names and "sd_prefilter_run" in names
+    L = ctypes.CDLL(sd.LIB_PATH)
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+    assert sd.lib().sd_version() >= 100
+
+
+def _no_gpu():
+    import torch
+    return not torch.cuda.is_available()
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="only meaningful on a box without a CUDA device")
+def test_no_cpu_fallback():
+    """Without a device the context cannot be created (SD_ENODEV) and the front-end exits non-zero with the message."""
+    with pytest.raises(sd.SdError) as e:
+        sd.Context(0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+    d = tempfile.mkdtemp(prefix="sdfe_")
+    try:
+        paths = synth.write_fasta(synth.generate(2, 5, seed=3), os.path.join(d, "faa"))
+        subprocess.run([SDB200, "createsetdb"] + paths + [os.path.join(d, "setDB"), os.path.join(d, "tmp")], check=True)
+        r = subprocess.run([SDB200, "clustersearch", os.path.join(d, "setDB"), os.path.join(d, "setDB"), os.path.join(d, "out.tsv"),
+                            os.path.join(d, "tmp")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert r.returncode != 0 and b"Error" in r.stderr
+        assert not os.path.exists(os.path.join(d, "out.tsv"))
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def test_frontend_rejects_unimplemented_modes():
+    d = tempfile.mkdtemp(prefix="sdfe_")
+    try:
+        paths = synth.write_fasta(synth.generate(2, 5, seed=3), os.path.join(d, "faa"))
+        db = os.path.join(d, "setDB")
+        subprocess.run([SDB200, "createsetdb"] + paths + [db, os.path.join(d, "tmp")], check=True)
+        for flags in (["--search-mode", "1"], ["--num-iterations", "3"], ["--compressed", "1"]):
+            r = subprocess.run([SDB200, "clustersearch", db, db, os.path.join(d, "o.tsv"), os.path.join(d, "tmp")] + flags,
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            assert r.returncode != 0 and b"not implemented" in r.stderr, flags
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def _sha(dirname):
+    return {f: hashlib.sha256(open(os.path.join(dirname, f), "rb").read()).hexdigest()
+            for f in sorted(os.listdir(dirname)) if f.startswith("setDB")}
+
+
+def test_createsetdb_golden():
+    """Every file of the set DB equals what the reference's createsetdb wrote (committed sha256 fixture)."""
+    g = json.load(open(os.path.join(helpers.GOLDEN, "createsetdb_syn2x5.json")))
+    d = tempfile.mkdtemp(prefix="sdfe_")
+    try:
+        paths = synth.write_fasta(synth.generate(g["n_proteomes"], g["genes"], seed=g["seed"]), os.path.join(d, "faa"))
+        subprocess.run([SDB200, "createsetdb"] + paths + [os.path.join(d, "setDB"), os.path.join(d, "tmp"), "--threads", "2"], check=True)
+        assert _sha(d) == g["sha256"]
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+@pytest.mark.parametrize("case", ["synth", "examples"])
+def test_createsetdb_vs_reference(case, synth_small):
+    if not helpers.have_ref():
+        pytest.skip("oracle/_ref/spacedust not built")
+    d = tempfile.mkdtemp(prefix="sdfe_")
+    try:
+        if case == "synth":
+            paths = synth.write_fasta(synth_small, os.path.join(d, "faa"))
+        else:
+            paths = [os.path.join("/root/reference/examples", f) for f in ("NC_000913.faa", "NC_000915.faa")]
+            if not all(os.path.exists(p) for p in paths):
+                pytest.skip("reference examples not mounted")
+        os.makedirs(os.path.join(d, "a"))
+        os.makedirs(os.path.join(d, "b"))
+        helpers.run_ref(["createsetdb"] + paths + [os.path.join(d, "a", "setDB"), os.path.join(d, "a", "tmp"), "-v", "1"])
+        subprocess.run([SDB200, "createsetdb"] + paths + [os.path.join(d, "b", "setDB"), os.path.join(d, "b", "tmp")], check=True)
+        assert _sha(os.path.join(d, "a")) == _sha(os.path.join(d, "b"))
+        assert len(_sha(os.path.join(d, "a"))) == 19
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
