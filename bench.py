@@ -9,8 +9,10 @@ One step = one pass of the hot path over the whole query batch.
   value  : target DB + k-mer index and the query batch already resident in HBM when the timed region starts
   e2e    : same step through the C ABI from pinned HOST buffers: target index build (upload, masking, index),
            query upload, all stages, results read back -- what `clustersearch` does after `createsetdb`
-Multi-GPU (--gpus N via torchrun): the target index is replicated, query SETS are split across ranks (no
-data-path collective; one NCCL all_gather of the per-rank result counts), total work fixed => "strong".
+Multi-GPU (--gpus N via torchrun): the target index is replicated, query SETS are split across ranks in contiguous
+residue-balanced blocks (spacedust_b200/shard.py); no collective inside the data path, ONE NCCL all_gather of the
+per-rank result lists (alignments, backtraces, clusters) per step so that every rank ends with the whole job's
+result; total work fixed => "strong".
 
 `--impl reference` times the unmodified reference binary (oracle/_ref/spacedust, built by oracle/build_ref.py)
 on the host cores on a bounded sample of the same workload (S query proteomes against the same 20-proteome
@@ -226,7 +228,7 @@ def run_ours(args, proteomes, rank, world, local_rank):
     import torch.distributed as dist
 
     import spacedust_b200 as sd
-    from spacedust_b200 import synth
+    from spacedust_b200 import shard, synth
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
@@ -237,9 +239,10 @@ def run_ours(args, proteomes, rank, world, local_rank):
     buf, off, _ = synth.pack(proteomes)
     meta = synth.set_metadata(proteomes)
     n_total = len(off) - 1
-    # this rank's query sets: contiguous block of proteomes
-    sets = np.array_split(np.arange(args.proteomes), world)[rank]
-    sel = np.nonzero(np.isin(meta["set_of"], sets))[0]
+    # this rank's query sets: contiguous block of proteomes, balanced by residues
+    set_res = np.array([sum(len(s) for s in p["seqs"]) for p in proteomes])
+    s_lo, s_hi = shard.partition_sets(set_res, world)[rank]
+    sel = np.arange(*shard.query_block(meta["set_of"], s_lo, s_hi))
     q_first = int(sel[0]) if len(sel) else 0
     q_lo, q_hi = (int(off[sel[0]]), int(off[sel[-1] + 1])) if len(sel) else (0, 0)
     qbuf = buf[q_lo:q_hi]
@@ -263,12 +266,21 @@ def run_ours(args, proteomes, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    dev = torch.device("cuda", local_rank)
+
+    def step(index, queries):
+        """One pass of the hot path over this rank's query block; N>1: + the one all_gather of the result lists."""
+        r = sd.clustersearch(ctx, index, queries, q_meta, meta, pp, ap, cp, q_first)
+        if world > 1:
+            r["merged"] = shard.allgather_results(shard.rebase_result(r, q_first), device=dev)
+        return r
+
     # ---------------- resident arm
     idx = sd.TargetIndex(ctx, tbuf_h, off, pp)
     batch = sd.QueryBatch(ctx, qbuf_h, qoff)
     res = None
     for _ in range(args.warmup):
-        res = sd.clustersearch(ctx, idx, batch, q_meta, meta, pp, ap, cp, q_first)
+        res = step(idx, batch)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -278,7 +290,7 @@ def run_ours(args, proteomes, rank, world, local_rank):
     stage = {"prefilter_ms": 0.0, "prefilter_kernel_ms": 0.0, "align_ms": 0.0, "sw_kernel_ms": 0.0, "traceback_ms": 0.0,
              "cluster_ms": 0.0, "cluster_kernel_ms": 0.0}
     for _ in range(args.steps):
-        res = sd.clustersearch(ctx, idx, batch, q_meta, meta, pp, ap, cp, q_first)
+        res = step(idx, batch)
         stage["prefilter_ms"] += res["prefilter_stats"]["total_ms"]
         stage["prefilter_kernel_ms"] += res["prefilter_stats"]["kernel_ms"]
         stage["align_ms"] += res["align_stats"]["total_ms"]
@@ -301,7 +313,7 @@ def run_ours(args, proteomes, rank, world, local_rank):
             t1 = time.perf_counter()
         idx2 = sd.TargetIndex(ctx, tbuf_h, off, pp)
         b2 = sd.QueryBatch(ctx, qbuf_h, qoff)
-        r2 = sd.clustersearch(ctx, idx2, b2, q_meta, meta, pp, ap, cp, q_first)
+        r2 = step(idx2, b2)
         e2e_d2h = int(r2["alns"].nbytes + r2["pool"].nbytes + r2["clusters"].nbytes + r2["members"].nbytes)
         b2.close()
         idx2.close()
@@ -314,7 +326,7 @@ def run_ours(args, proteomes, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
         gathered = [torch.zeros_like(counts) for _ in range(world)]
-        dist.all_gather(gathered, counts)          # the one collective of the path: per-rank result sizes
+        dist.all_gather(gathered, counts)          # reporting only (outside the timed region)
         counts = torch.stack(gathered).sum(0)
     dt, dt_e2e = float(t_all[0]), float(t_all[1])
     if rank == 0:
@@ -349,6 +361,12 @@ def run_ours(args, proteomes, rank, world, local_rank):
                 "results": {"aligned_pairs": int(counts[0]), "alignments": int(counts[1]), "clusters": int(counts[2]),
                             "query_genes": int(counts[3])},
                 "clocks": clocks}
+        if world > 1:
+            m = res["merged"]
+            assert len(m["alns"]) == int(counts[1]) and len(m["clusters"]) == int(counts[2])
+            line["collective"] = {"op": "all_gather (sizes + padded payload) of per-rank alignment/backtrace/cluster lists, NCCL",
+                                  "bytes_gathered_per_step": int(m["alns"].nbytes + m["pool"].nbytes + m["clusters"].nbytes + m["members"].nbytes),
+                                  "sharding": "query sets in contiguous residue-balanced blocks; target index replicated"}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(args, proteomes)

@@ -279,7 +279,7 @@ def parse_pref_db(path, qkeys, tkeys):
 
 # ----------------------------------------------------------------------------- oracle: whole clustersearch path
 def oracle_clustersearch(proteomes, filter_self_match=True, max_gene_gap=3, cluster_size=2, cluster_pval=0.01,
-                         multihit_pval=0.01, alpha=1.0, alns_override=None):
+                         multihit_pval=0.01, alpha=1.0, alns_override=None, query_sets=None):
     """prefilter -> align -> prefixid -> besthitbyset -> mergeresultsbyset -> combinehits -> clusterhits with the
     oracle restatements; -> dict(alns, bt, result, matches, clusters) (text records as the reference exchanges them)."""
     import sys
@@ -296,10 +296,14 @@ def oracle_clustersearch(proteomes, filter_self_match=True, max_gene_gap=3, clus
     else:
         alns, bt = alns_override
     result = {k: [l.decode() for l in v] for k, v in format_alignments(alns, bt, keys).items()}
+    if query_sets is not None:      # a rank's shard: only the query genes of its sets (targets stay whole)
+        qs = set(int(x) for x in query_sets)
+        result = {k: v for k, v in result.items() if int(meta["set_of"][k]) in qs}
     m2s = {i: int(meta["set_of"][i]) for i in range(n)}
     s2m = {}
     for i in range(n):
-        s2m.setdefault(int(meta["set_of"][i]), []).append(i)
+        if query_sets is None or int(meta["set_of"][i]) in qs:
+            s2m.setdefault(int(meta["set_of"][i]), []).append(i)
     ssz = {i: int(s) for i, s in enumerate(meta["set_size"])}
     lookup = {i: meta["names"][i] for i in range(n)}
     agg = oc.besthitbyset(oc.prefixid(result), m2s)

@@ -1,0 +1,121 @@
+"""CPU tests of the N>1 layout (spacedust_b200/shard.py): set partitioning, and -- with world_size-2 gloo processes --
+that sharding the path by query set and exchanging the per-rank result lists with one all_gather reproduces the
+unsharded result exactly.  The per-rank "path" here is the ORACLE (checker) applied to the rank's query sets; the GPU
+counterpart is tests/test_shard_gpu.py / bench.py --gpus N."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import helpers
+import spacedust_b200 as sd
+from spacedust_b200 import shard, synth
+
+
+def test_partition_sets_covers_and_balances():
+    rng = np.random.default_rng(1)
+    for n_sets, world in ((20, 1), (20, 2), (20, 8), (200, 8), (3, 8), (1, 2), (0, 2)):
+        w = rng.integers(500_000, 1_500_000, size=n_sets)
+        blocks = shard.partition_sets(w, world)
+        assert len(blocks) == world
+        assert blocks[0][0] == 0 and blocks[-1][1] == n_sets
+        for (a, b), (c, d) in zip(blocks, blocks[1:]):
+            assert a <= b == c <= d
+        if n_sets >= 4 * world:
+            loads = [w[a:b].sum() for a, b in blocks]
+            assert max(loads) <= 1.35 * (w.sum() / world), (n_sets, world, loads)
+    assert shard.partition_sets([5, 5, 5, 5], 2) == [(0, 2), (2, 4)]
+
+
+def test_query_block():
+    set_of = np.array([0, 0, 1, 1, 1, 2, 3, 3])
+    assert shard.query_block(set_of, 1, 3) == (2, 6)
+    assert shard.query_block(set_of, 0, 4) == (0, 8)
+    assert shard.query_block(set_of, 4, 4) == (0, 0)
+    with pytest.raises(ValueError):
+        shard.query_block(np.array([0, 1, 0]), 0, 1)
+
+
+def _records(o, q_lo, q_hi):
+    """Oracle output restricted to query genes [q_lo, q_hi) in the product's record layout (query indices block-relative)."""
+    alns_o, bt = o["alns"], o["bt"]
+    sel = np.nonzero((alns_o["query"] >= q_lo) & (alns_o["query"] < q_hi))[0]
+    a = np.zeros(len(sel), dtype=sd.ALN_DTYPE)
+    for fo, fg in (("query", "query"), ("target", "target"), ("score", "score"), ("bits", "bits"), ("seqId", "seq_id"),
+                   ("qcov", "qcov"), ("tcov", "tcov"), ("evalue", "evalue"), ("qStart", "q_start"), ("qEnd", "q_end"),
+                   ("qLen", "q_len"), ("tStart", "t_start"), ("tEnd", "t_end"), ("tLen", "t_len"), ("alnLen", "aln_len"),
+                   ("btLen", "bt_len")):
+        a[fg] = alns_o[fo][sel]
+    a["query"] -= np.uint32(q_lo)
+    pool = []
+    p = 0
+    for i, j in enumerate(sel):
+        b = bt[int(alns_o["btOff"][j]):int(alns_o["btOff"][j]) + int(alns_o["btLen"][j])]
+        a["bt_off"][i] = p
+        pool.append(b)
+        p += len(b)
+    pool = np.concatenate(pool) if pool else np.zeros(0, dtype=np.uint8)
+    where = {(int(alns_o["query"][j]), int(alns_o["target"][j])): i for i, j in enumerate(sel)}
+    clusters, members = [], []
+    for hdr, lines in o["clusters"]:
+        h = hdr.split("\t")
+        ms = []
+        for l in lines:
+            f = l.split("\t")
+            if (int(f[0]), int(f[1])) not in where:
+                ms = None
+                break
+            ms.append((where[(int(f[0]), int(f[1]))], 0, float(f[2])))
+        if ms is None:
+            continue
+        clusters.append((int(h[0]), int(h[1]), float(h[2]), float(h[3]), len(ms), len(members)))
+        members.extend(ms)
+    return {"alns": a, "pool": pool, "clusters": np.array(clusters, dtype=sd.CLUSTER_DTYPE).reshape(-1),
+            "members": np.array(members, dtype=sd.MEMBER_DTYPE).reshape(-1)}
+
+
+def _worker(rank, world, port, tmpdir):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(helpers.ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        prot = synth.generate(3, 120, seed=7)
+        z = np.load(os.path.join(tmpdir, "alns.npz"))
+        alns, bt = z["alns"], z["bt"]
+        buf, off, _ = synth.pack(prot)
+        meta = synth.set_metadata(prot)
+        set_res = np.array([sum(len(s) for s in p["seqs"]) for p in prot])
+        lo, hi = shard.partition_sets(set_res, world)[rank]
+        q_lo, q_hi = shard.query_block(meta["set_of"], lo, hi)
+        # the rank's share of the path: all target sets, only its query sets
+        o = helpers.oracle_clustersearch(prot, filter_self_match=True, alns_override=(alns, bt), query_sets=range(lo, hi))
+        local = _records(o, q_lo, q_hi)
+        merged = shard.allgather_results(shard.rebase_result(local, q_lo))
+        np.savez(os.path.join(tmpdir, "merged_%d.npz" % rank), **merged)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_equals_unsharded_gloo(tmp_path, synth_small):
+    import torch.multiprocessing as mp
+    o = helpers.oracle_clustersearch(synth_small, filter_self_match=True)
+    np.savez(os.path.join(tmp_path, "alns.npz"), alns=o["alns"], bt=o["bt"])
+    whole = _records(o, 0, len(synth.set_metadata(synth_small)["set_of"]))
+    assert len(whole["clusters"]) == len(o["clusters"]) > 5
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    world = 2
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for rank in range(world):
+        m = np.load(os.path.join(tmp_path, "merged_%d.npz" % rank))
+        for k in ("alns", "clusters", "members"):
+            assert m[k].dtype == whole[k].dtype and len(m[k]) == len(whole[k]), k
+            for f in whole[k].dtype.names:
+                assert np.array_equal(m[k][f], whole[k][f]), (k, f)
+        assert np.array_equal(m["pool"], whole["pool"])

@@ -1,0 +1,69 @@
+"""GPU, 2 ranks (skipped on a 1-GPU box): one process per GPU over NCCL, query sets sharded (spacedust_b200/shard.py),
+the libsdgpu path per rank, one all_gather of the result lists -> identical to the single-GPU result."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, tmpdir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(helpers.ROOT, "tests"))
+    import spacedust_b200 as sd
+    from spacedust_b200 import shard, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        prot = synth.generate(4, 150, seed=31)
+        buf, off, _ = synth.pack(prot)
+        meta = synth.set_metadata(prot)
+        set_res = np.array([sum(len(s) for s in p["seqs"]) for p in prot])
+        lo, hi = shard.partition_sets(set_res, world)[rank]
+        q_lo, q_hi = shard.query_block(meta["set_of"], lo, hi)
+        qbuf = buf[int(off[q_lo]):int(off[q_hi])]
+        qoff = (off[q_lo:q_hi + 1] - off[q_lo]).astype(np.uint64)
+        q_meta = {k: (meta[k][q_lo:q_hi] if k != "set_size" else meta[k]) for k in ("set_of", "pos", "strand", "set_size")}
+        ctx = sd.Context(rank)
+        pp = sd.default_prefilter_params(same_db=1, bin_size=2)
+        idx = sd.TargetIndex(ctx, buf, off, pp)
+        batch = sd.QueryBatch(ctx, qbuf, qoff)
+        r = sd.clustersearch(ctx, idx, batch, q_meta, meta, pp, query_first=q_lo)
+        merged = shard.allgather_results(shard.rebase_result(r, q_lo), device=torch.device("cuda", rank))
+        np.savez(os.path.join(tmpdir, "merged_%d.npz" % rank), **merged)
+        if rank == 0:      # the unsharded run on one GPU
+            whole = sd.clustersearch(ctx, idx, sd.QueryBatch(ctx, buf, off), meta, meta, pp)
+            np.savez(os.path.join(tmpdir, "whole.npz"), **{k: whole[k] for k in ("alns", "pool", "clusters", "members")})
+        batch.close(); idx.close(); ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_equal_one(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    whole = np.load(os.path.join(tmp_path, "whole.npz"))
+    assert len(whole["clusters"]) > 10
+    for rank in range(2):
+        m = np.load(os.path.join(tmp_path, "merged_%d.npz" % rank))
+        for k in ("alns", "clusters", "members"):
+            assert len(m[k]) == len(whole[k]), k
+            for f in whole[k].dtype.names:
+                if f != "pad":
+                    assert np.array_equal(m[k][f], whole[k][f]), (k, f)
+        assert np.array_equal(m["pool"], whole["pool"])
