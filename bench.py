@@ -268,11 +268,14 @@ def run_ours(args, proteomes, rank, world, local_rank):
 
     dev = torch.device("cuda", local_rank)
 
+    exch = shard.ResultExchange(device=dev)      # persistent pinned result block (+ exchange buffers for N>1)
+
     def step(index, queries):
-        """One pass of the hot path over this rank's query block; N>1: + the one all_gather of the result lists."""
-        r = sd.clustersearch(ctx, index, queries, q_meta, meta, pp, ap, cp, q_first)
+        """One pass of the hot path over this rank's query block, results into pinned host memory; N>1: + the one
+        all_gather of the result lists (every rank ends with all ranks' parts in host memory)."""
+        r = sd.clustersearch(ctx, index, queries, q_meta, meta, pp, ap, cp, q_first, out=exch)
         if world > 1:
-            r["merged"] = shard.allgather_results(shard.rebase_result(r, q_first), device=dev)
+            r["parts"] = exch.exchange(q_first)
         return r
 
     # ---------------- resident arm
@@ -362,10 +365,10 @@ def run_ours(args, proteomes, rank, world, local_rank):
                             "query_genes": int(counts[3])},
                 "clocks": clocks}
         if world > 1:
-            m = res["merged"]
-            assert len(m["alns"]) == int(counts[1]) and len(m["clusters"]) == int(counts[2])
-            line["collective"] = {"op": "all_gather (sizes + padded payload) of per-rank alignment/backtrace/cluster lists, NCCL",
-                                  "bytes_gathered_per_step": int(m["alns"].nbytes + m["pool"].nbytes + m["clusters"].nbytes + m["members"].nbytes),
+            parts = res["parts"]
+            assert sum(len(x["alns"]) for x in parts) == int(counts[1]) and sum(len(x["clusters"]) for x in parts) == int(counts[2])
+            line["collective"] = {"op": "all_gather_into_tensor (sizes, then padded blocks) of per-rank alignment/backtrace/cluster lists, NCCL",
+                                  "bytes_gathered_per_step": int(sum(x[k].nbytes for x in parts for k in ("alns", "pool", "clusters", "members"))),
                                   "sharding": "query sets in contiguous residue-balanced blocks; target index replicated"}
         if world == 1 and not args.no_cpu_baseline:
             try:

@@ -349,9 +349,11 @@ def clustersearch_staged(ctx, index, batch, q_meta, t_meta, pref_params=None, al
 
 
 def clustersearch(ctx, index, batch, q_meta, t_meta, pref_params=None, aln_params=None, clu_params=None, query_first=0,
-                  db_residues=0):
+                  db_residues=0, out=None):
     """The hot path of `spacedust clustersearch` after createsetdb for one query batch, fused (sd_clustersearch_run):
-    prefilter -> align -> besthitbyset/combinehits -> clusterhits with the prefilter hit list kept in HBM."""
+    prefilter -> align -> besthitbyset/combinehits -> clusterhits with the prefilter hit list kept in HBM.
+    out: optional object with carve(n_alns, pool_bytes, n_clusters, n_members) -> (alns, pool, clusters, members) arrays to
+    receive the result (e.g. shard.ResultExchange: persistent pinned memory, no per-call allocation)."""
     pp = pref_params or default_prefilter_params(same_db=1)
     ap = aln_params or default_align_params(same_db=pp.same_db)
     cp = clu_params or default_cluster_params(filter_self_match=1)
@@ -373,10 +375,13 @@ def clustersearch(ctx, index, batch, q_meta, t_meta, pref_params=None, aln_param
     try:
         na, nb, nc, nm = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
         L.sd_search_result_sizes(res, ctypes.byref(na), ctypes.byref(nb), ctypes.byref(nc), ctypes.byref(nm))
-        alns = np.zeros(max(1, na.value), dtype=ALN_DTYPE)
-        pool = np.zeros(max(1, nb.value), dtype=np.uint8)
-        clusters = np.zeros(max(1, nc.value), dtype=CLUSTER_DTYPE)
-        members = np.zeros(max(1, nm.value), dtype=MEMBER_DTYPE)
+        if out is not None:
+            alns, pool, clusters, members = out.carve(na.value, nb.value, nc.value, nm.value)
+        else:
+            alns = np.empty(max(1, na.value), dtype=ALN_DTYPE)
+            pool = np.empty(max(1, nb.value), dtype=np.uint8)
+            clusters = np.empty(max(1, nc.value), dtype=CLUSTER_DTYPE)
+            members = np.empty(max(1, nm.value), dtype=MEMBER_DTYPE)
         _check(L.sd_search_result_copy(res, alns.ctypes.data_as(p), pool.ctypes.data_as(ctypes.c_char_p), clusters.ctypes.data_as(p),
                                        members.ctypes.data_as(p)))
     finally:

@@ -115,3 +115,103 @@ def allgather_results(res, group=None, device=None):
             o += int(nb)
         parts.append(d)
     return merge_results(parts)
+
+
+class ResultExchange:
+    """Persistent buffers for the result lists of one rank and for the one all_gather of the N>1 path.
+
+    carve() hands sd.clustersearch four array views into ONE pinned host block laid out as
+        [int64 n_alns, pool_bytes, n_clusters, n_members | alignments | backtrace pool | clusters | members]
+    (fields 16-byte aligned), so the C ABI writes the result straight into the send buffer.  exchange() rebases the
+    rank's query indices to global ones in place, all_gathers the block sizes, then moves every rank's block with one
+    all_gather_into_tensor (padded to the largest block) -- pinned host -> HBM -> NCCL over NVLink -> pinned host on
+    the GPU box, plain host tensors with gloo -- and returns the per-rank parts as views (merge_results() makes them
+    contiguous when a consumer needs that)."""
+
+    HEAD = 64
+
+    def __init__(self, device=None, group=None):
+        import torch
+        self.torch = torch
+        self.device = device
+        self.group = group
+        self.cuda = device is not None and torch.device(device).type == "cuda"
+        self.send_h = None        # pinned (cuda) or plain host block of this rank
+        self.recv_h = None
+        self.send_d = self.recv_d = None
+        self.used = 0
+        self.sizes = (0, 0, 0, 0)
+
+    def _host(self, nbytes):
+        t = self.torch.empty(nbytes, dtype=self.torch.uint8)
+        return t.pin_memory() if self.cuda else t
+
+    @staticmethod
+    def _layout(na, nb, nc, nm):
+        import spacedust_b200 as sd
+        al = lambda x: (x + 15) & ~15      # noqa: E731
+        o_a = ResultExchange.HEAD
+        o_p = al(o_a + na * sd.ALN_DTYPE.itemsize)
+        o_c = al(o_p + nb)
+        o_m = al(o_c + nc * sd.CLUSTER_DTYPE.itemsize)
+        end = al(o_m + nm * sd.MEMBER_DTYPE.itemsize)
+        return o_a, o_p, o_c, o_m, end
+
+    @staticmethod
+    def _views(block, na, nb, nc, nm):
+        import spacedust_b200 as sd
+        o_a, o_p, o_c, o_m, _ = ResultExchange._layout(na, nb, nc, nm)
+        return (block[o_a:o_a + na * sd.ALN_DTYPE.itemsize].view(sd.ALN_DTYPE), block[o_p:o_p + nb],
+                block[o_c:o_c + nc * sd.CLUSTER_DTYPE.itemsize].view(sd.CLUSTER_DTYPE),
+                block[o_m:o_m + nm * sd.MEMBER_DTYPE.itemsize].view(sd.MEMBER_DTYPE))
+
+    def carve(self, na, nb, nc, nm):
+        na, nb, nc, nm = int(na), int(nb), int(nc), int(nm)
+        end = self._layout(na, nb, nc, nm)[4]
+        if self.send_h is None or self.send_h.numel() < end:
+            self.send_h = self._host(end + end // 4 + 4096)
+        block = self.send_h.numpy()
+        block[:self.HEAD].view(np.int64)[:4] = (na, nb, nc, nm)
+        self.used = end
+        self.sizes = (na, nb, nc, nm)
+        return self._views(block, na, nb, nc, nm)
+
+    def local(self):
+        a, p, c, m = self._views(self.send_h.numpy(), *self.sizes)
+        return {"alns": a, "pool": p, "clusters": c, "members": m}
+
+    def exchange(self, query_first):
+        """-> list (rank order) of {"alns","pool","clusters","members"} views with global query indices."""
+        torch = self.torch
+        import torch.distributed as dist
+        world = dist.get_world_size(self.group)
+        self.local()["alns"]["query"] += np.uint32(query_first)
+        n = torch.tensor([self.used], dtype=torch.int64, device=self.device)
+        sizes = torch.empty(world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(sizes, n, group=self.group)
+        cap = (int(sizes.max().item()) + 4095) & ~4095
+        if self.recv_h is None or self.recv_h.numel() < cap * world:
+            self.recv_h = self._host(cap * world + cap // 4 * world)
+            if self.cuda:
+                self.recv_d = torch.empty(self.recv_h.numel(), dtype=torch.uint8, device=self.device)
+        if self.send_h.numel() < cap:          # the padded send must be readable up to cap
+            grown = self._host(cap + cap // 4)
+            grown[:self.used].copy_(self.send_h[:self.used])
+            self.send_h = grown
+        if self.cuda:
+            if self.send_d is None or self.send_d.numel() < cap:
+                self.send_d = torch.empty(cap + cap // 4, dtype=torch.uint8, device=self.device)
+            self.send_d[:self.used].copy_(self.send_h[:self.used], non_blocking=True)
+            dist.all_gather_into_tensor(self.recv_d[:cap * world], self.send_d[:cap], group=self.group)
+            self.recv_h[:cap * world].copy_(self.recv_d[:cap * world], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        else:
+            dist.all_gather_into_tensor(self.recv_h[:cap * world], self.send_h[:cap], group=self.group)
+        raw = self.recv_h.numpy()
+        parts = []
+        for r in range(world):
+            block = raw[r * cap:(r + 1) * cap]
+            na, nb, nc, nm = (int(x) for x in block[:self.HEAD].view(np.int64)[:4])
+            a, p, c, m = self._views(block, na, nb, nc, nm)
+            parts.append({"alns": a, "pool": p, "clusters": c, "members": m})
+        return parts

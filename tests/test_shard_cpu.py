@@ -96,6 +96,14 @@ def _worker(rank, world, port, tmpdir):
         local = _records(o, q_lo, q_hi)
         merged = shard.allgather_results(shard.rebase_result(local, q_lo))
         np.savez(os.path.join(tmpdir, "merged_%d.npz" % rank), **merged)
+        # the persistent-buffer exchange bench.py uses: result written into the send block, parts come back as views
+        ex = shard.ResultExchange()
+        for _ in range(2):          # second round reuses the buffers
+            views = ex.carve(len(local["alns"]), len(local["pool"]), len(local["clusters"]), len(local["members"]))
+            for v, k in zip(views, ("alns", "pool", "clusters", "members")):
+                v[...] = local[k]
+            merged2 = shard.merge_results(ex.exchange(q_lo))
+        np.savez(os.path.join(tmpdir, "merged2_%d.npz" % rank), **merged2)
     finally:
         dist.destroy_process_group()
 
@@ -112,8 +120,8 @@ def test_sharded_equals_unsharded_gloo(tmp_path, synth_small):
     s.close()
     world = 2
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
-    for rank in range(world):
-        m = np.load(os.path.join(tmp_path, "merged_%d.npz" % rank))
+    for rank, name in [(r, n) for r in range(world) for n in ("merged", "merged2")]:
+        m = np.load(os.path.join(tmp_path, "%s_%d.npz" % (name, rank)))
         for k in ("alns", "clusters", "members"):
             assert m[k].dtype == whole[k].dtype and len(m[k]) == len(whole[k]), k
             for f in whole[k].dtype.names:

@@ -38,6 +38,15 @@ def _worker(rank, world, port, tmpdir):
         batch = sd.QueryBatch(ctx, qbuf, qoff)
         r = sd.clustersearch(ctx, idx, batch, q_meta, meta, pp, query_first=q_lo)
         merged = shard.allgather_results(shard.rebase_result(r, q_lo), device=torch.device("cuda", rank))
+        ex = shard.ResultExchange(device=torch.device("cuda", rank))
+        for _ in range(2):
+            sd.clustersearch(ctx, idx, batch, q_meta, meta, pp, query_first=q_lo, out=ex)
+            merged2 = shard.merge_results(ex.exchange(q_lo))
+        for k in ("alns", "clusters", "members"):
+            for f in merged[k].dtype.names:
+                if f != "pad":
+                    assert np.array_equal(merged[k][f], merged2[k][f]), (k, f)
+        assert np.array_equal(merged["pool"], merged2["pool"])
         np.savez(os.path.join(tmpdir, "merged_%d.npz" % rank), **merged)
         if rank == 0:      # the unsharded run on one GPU
             whole = sd.clustersearch(ctx, idx, sd.QueryBatch(ctx, buf, off), meta, meta, pp)
