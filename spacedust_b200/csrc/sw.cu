@@ -35,6 +35,7 @@ struct SwKernelArgs {
     unsigned long long *cells; // total DP cells computed
     int packed16;              // 1: packed 16-bit pass, 0: 32-bit pass (fallback for scores near 2^15)
     const uint32_t *nRounds;   // packed pass: number of rounds in order[]
+    uint32_t zero;             // always 0; a kernel parameter so that ptxas cannot re-materialise the constant per cell
 };
 
 __device__ __forceinline__ uint32_t swLane() { return threadIdx.x & 31; }
@@ -212,17 +213,22 @@ __device__ __forceinline__ int hi16(uint32_t v) { return (int)(short)(v >> 16); 
 
 // Scheduling classes of the packed pass: (lanes per pair, packed rows per stage).  Short queries use 8 lanes per pair
 // (4 pairs per warp, 16 wavefront stages), so every lane still owns enough rows to amortise the per-step work
-// (shuffles, profile fetch, maxima) and the pipeline fill is 15 columns instead of 63.
+// (shuffles, profile fetch, maxima) and the pipeline fill is 15 columns instead of 63.  The stage height follows the
+// segment length of the 8-bit striped layout, segLen = ceil(nRows/32): 8 lanes -> RP = 2 segLen, 16 lanes -> RP = segLen,
+// so that in the forward 8-bit pass every segment starts at a compile-time row of a stage (SEGMODE below).
 __host__ __device__ inline int swClassOf(int nRows) {
-    if (nRows <= 320) { int rp = (nRows + 15) / 16; rp = (rp + 1) & ~1; if (rp < 2) rp = 2; return rp / 2 - 1; }       // 0..9 : 8 lanes, RP 2..20
-    if (nRows <= 640) { int rp = (nRows + 31) / 32; rp = (rp + 1) & ~1; return 10 + (rp - 12) / 2; }                     // 10..14: 16 lanes, RP 12..20
-    if (nRows <= 1280) { int rp = (nRows + 63) / 64; rp = (rp + 1) & ~1; return 15 + (rp - 12) / 2; }                   // 15..19: 32 lanes, RP 12..20
-    return 20;                                                                                                         // stripes of 1280 rows
+    if (nRows <= 320) { int rp = 2 * ((nRows + 31) / 32); if (rp < 2) rp = 2; return rp / 2 - 1; }                       // 0..9  : 8 lanes, RP 2,4..20
+    if (nRows <= 640) { const int rp = (nRows + 31) / 32; return 10 + (rp - 11); }                                       // 10..19: 16 lanes, RP 11..20
+    if (nRows <= 1280) { int rp = (nRows + 63) / 64; rp = (rp + 1) & ~1; return 20 + (rp - 12) / 2; }                   // 20..24: 32 lanes, RP 12..20
+    return 25;                                                                                                         // stripes of 1280 rows
 }
-__host__ __device__ inline int swClassTasksPerRound(int cls) { return cls < 10 ? 4 : (cls < 15 ? 2 : 1); }
-constexpr int SW_NCLASS = 21;
+__host__ __device__ inline int swClassTasksPerRound(int cls) { return cls < 10 ? 4 : (cls < 20 ? 2 : 1); }
+constexpr int SW_NCLASS = 26;
+constexpr int SW_KEYMUL = 33;      // column-maximum key = H * 33 + (31 - k): not a shift, so it is an IMAD (FMA pipe), not an LEA
 
-template <int LANES, int RP, bool KEYED>
+// SEGMODE: where the reference's segment starts (Fm resets) fall inside a stage
+//   0  anywhere (per-row runtime mask)      1  rows 0 and RP/2 of both stages (segLen = RP/2)      2  row 0 of both stages (segLen = RP)
+template <int LANES, int RP, bool KEYED, int SEGMODE>
 __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, unsigned long long &cellCount) {
     constexpr int NWA = (RP + 3) / 4;          // aligned words holding RP bytes
     constexpr bool STRIPED = (LANES == 32);    // only whole-warp pairs may need more than one stripe
@@ -245,8 +251,10 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
     const int lim = tk.limit != INT_MAX ? tk.limit : SW16_GUARD;
 
     int bestA = 0, bestB = 0, colA = INT_MAX, colB = INT_MAX, rowA = INT_MAX, rowB = INT_MAX;
+    int thrA = SW_KEYMUL, thrB = SW_KEYMUL;     // KEYED: smallest key that beats the current best score
     bool overflow = false;
     int pingpong = 0;
+    const uint32_t zero = A.zero;               // opaque 0 (see SwKernelArgs)
     // every group runs the longest group's step count (shuffles are warp-wide)
     const int mySteps = have ? nCols + 2 * LANES - 1 : 0;
     const int warpSteps = (int)__reduce_max_sync(0xffffffffu, (unsigned)mySteps);
@@ -260,12 +268,14 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
         const bool laneHasRows = have && i0 < nRows && !overflow;
         const int *bndIn = bnd + (size_t)pingpong * 3 * A.boundaryStride;
         int *bndOut = bnd + (size_t)(pingpong ^ 1) * 3 * A.boundaryStride;
-        uint32_t segKeep[RP];
+        uint32_t segKeep[SEGMODE == 0 ? RP : 1];
+        if (SEGMODE == 0) {
 #pragma unroll
-        for (int k = 0; k < RP; k++) {
-            const uint32_t a = ((i0 + k) % segLen) == 0 ? 0u : 0xffffu;
-            const uint32_t b = ((i0 + RP + k) % segLen) == 0 ? 0u : 0xffff0000u;
-            segKeep[k] = a | b;
+            for (int k = 0; k < RP; k++) {
+                const uint32_t a = ((i0 + k) % segLen) == 0 ? 0u : 0xffffu;
+                const uint32_t b = ((i0 + RP + k) % segLen) == 0 ? 0u : 0xffff0000u;
+                segKeep[SEGMODE == 0 ? k : 0] = a | b;
+            }
         }
         const uintptr_t addrA = (uintptr_t)(prof + rowOffset + (uint32_t)i0);
         const uintptr_t addrB = addrA + RP;
@@ -327,15 +337,18 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
                     const uint32_t sel = (uint32_t)(k & 3) | ((uint32_t)((k & 3) | 8) << 4) | ((uint32_t)(4 + (k & 3)) << 8) | ((uint32_t)((4 + (k & 3)) | 8) << 12);
                     const uint32_t sv = prmtSext(sa[k >> 2], sb[k >> 2], sel);
                     const uint32_t e = E[k];
-                    fm &= segKeep[k];
+                    // a segment starts at this row in both stages: Fm restarts from 0 and H1 = max(h, 0) = h (h >= E >= 0)
+                    const bool segStart = (SEGMODE != 0) && (k == 0 || (SEGMODE == 1 && k == RP / 2));
+                    if (SEGMODE == 0) fm &= segKeep[SEGMODE == 0 ? k : 0];
+                    if (segStart) fm = zero;
                     const uint32_t h = __viaddmax_s16x2(diag, sv, e);
-                    const uint32_t h1 = max16x2(h, fm);
+                    const uint32_t h1 = segStart ? h : max16x2(h, fm);
                     const uint32_t hs = max16x2(h, ft);
                     diag = H[k];
                     H[k] = hs;
-                    // KEYED (8-bit semantics, H < 2^10): key H*32 + (31-k) orders by score, then by smallest row
-                    colMax = max16x2(colMax, KEYED ? (hs * 32u + (uint32_t)((31 - k) * 0x10001)) : hs);
-                    const uint32_t open1 = __viaddmax_s16x2_relu(h1, negGo, 0u);
+                    // KEYED (8-bit semantics, H < 992): key H*33 + (31-k) orders by score, then by smallest row
+                    colMax = max16x2(colMax, KEYED ? (hs * (uint32_t)SW_KEYMUL + (uint32_t)((31 - k) * 0x10001)) : hs);
+                    const uint32_t open1 = __viaddmax_s16x2_relu(h1, negGo, zero);
                     E[k] = __viaddmax_s16x2(e, negGe, open1);
                     fm = __viaddmax_s16x2(fm, negGe, open1);
                     // Ft >= Fm and go >= ge: (Fm - go) <= (Ft - ge), so the gap opened from H1 also serves the exact chain
@@ -345,11 +358,13 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
                 prevHup = inH;
                 if (KEYED) {
                     const int kA = lo16(colMax), kB = hi16(colMax);
-                    const int mA = kA >> 5, mB = kB >> 5;
-                    const bool upA = mA > bestA && cA < nCols;
-                    const bool upB = mB > bestB && cA >= 1;
-                    bestA = upA ? mA : bestA; colA = upA ? cA : colA; rowA = upA ? i0 + 31 - (kA & 31) : rowA;
-                    bestB = upB ? mB : bestB; colB = upB ? cA - 1 : colB; rowB = upB ? i0 + RP + 31 - (kB & 31) : rowB;
+                    const bool upA = kA >= thrA && cA < nCols;
+                    const bool upB = kB >= thrB && cA >= 1;
+                    if (upA | upB) {            // rare after the first columns: decode score and row from the key
+                        const int mA = kA / SW_KEYMUL, mB = kB / SW_KEYMUL;
+                        if (upA) { bestA = mA; colA = cA; rowA = i0 + 31 - (kA - mA * SW_KEYMUL); thrA = (mA + 1) * SW_KEYMUL; }
+                        if (upB) { bestB = mB; colB = cA - 1; rowB = i0 + RP + 31 - (kB - mB * SW_KEYMUL); thrB = (mB + 1) * SW_KEYMUL; }
+                    }
                 } else {
                     const int mA = lo16(colMax), mB = hi16(colMax);
                     if (mA >= bestA && mA > 0 && cA < nCols) {
@@ -421,13 +436,29 @@ __global__ void __launch_bounds__(SW_WARPS * 32) swKernel16(SwKernelArgs A) {
         if (round >= nRounds) break;
         const uint32_t id0 = A.order[(size_t)round * 4];      // slot 0 of a round is always a real task
         const int cls = swClassOf(A.tasks[id0].nRows);
-#define SD_G(L, N) swGroupPass<L, N, KEYED>(A, round, bnd, cells); break;
+        // forward 8-bit pass (KEYED): width 32, so segLen = RP/2 (8 lanes) or RP (16 lanes) for every pair of the round and
+        // the segment starts sit at compile-time rows; anything else (checked, warp-uniform) takes the per-row mask
+        bool segAligned = false;
+        if (KEYED && cls < 20) {
+            const uint32_t idg = A.order[(size_t)round * 4 + (cls < 10 ? lane / 8 : lane / 16)];
+            bool ok = true;
+            if (idg != 0xffffffffu) {
+                const SwTask tg = A.tasks[idg];
+                const int sl = (tg.nRows + tg.width - 1) / tg.width;
+                const int rp = cls < 10 ? 2 * (cls + 1) : cls + 1;
+                ok = (cls < 10) ? (2 * sl == rp) : (sl == rp);
+            }
+            segAligned = __all_sync(0xffffffffu, ok);
+        }
+#define SD_G(L, N, M) if (KEYED && M != 0 && segAligned) swGroupPass<L, N, KEYED, KEYED ? M : 0>(A, round, bnd, cells); \
+                      else swGroupPass<L, N, KEYED, 0>(A, round, bnd, cells); break;
         switch (cls) {
-            case 0: SD_G(8, 2) case 1: SD_G(8, 4) case 2: SD_G(8, 6) case 3: SD_G(8, 8) case 4: SD_G(8, 10)
-            case 5: SD_G(8, 12) case 6: SD_G(8, 14) case 7: SD_G(8, 16) case 8: SD_G(8, 18) case 9: SD_G(8, 20)
-            case 10: SD_G(16, 12) case 11: SD_G(16, 14) case 12: SD_G(16, 16) case 13: SD_G(16, 18) case 14: SD_G(16, 20)
-            case 15: SD_G(32, 12) case 16: SD_G(32, 14) case 17: SD_G(32, 16) case 18: SD_G(32, 18)
-            default: SD_G(32, 20)
+            case 0: SD_G(8, 2, 1) case 1: SD_G(8, 4, 1) case 2: SD_G(8, 6, 1) case 3: SD_G(8, 8, 1) case 4: SD_G(8, 10, 1)
+            case 5: SD_G(8, 12, 1) case 6: SD_G(8, 14, 1) case 7: SD_G(8, 16, 1) case 8: SD_G(8, 18, 1) case 9: SD_G(8, 20, 1)
+            case 10: SD_G(16, 11, 2) case 11: SD_G(16, 12, 2) case 12: SD_G(16, 13, 2) case 13: SD_G(16, 14, 2) case 14: SD_G(16, 15, 2)
+            case 15: SD_G(16, 16, 2) case 16: SD_G(16, 17, 2) case 17: SD_G(16, 18, 2) case 18: SD_G(16, 19, 2) case 19: SD_G(16, 20, 2)
+            case 20: SD_G(32, 12, 0) case 21: SD_G(32, 14, 0) case 22: SD_G(32, 16, 0) case 23: SD_G(32, 18, 0)
+            default: SD_G(32, 20, 0)
         }
 #undef SD_G
     }
@@ -541,7 +572,7 @@ int launchSw(sd_context *ctx, const SwBatch &batch, const SwTask *dTasks, SwResu
     cudaStream_t st = ctx->stream;
     SwKernelArgs A;
     A.b = batch; A.tasks = dTasks; A.order = nullptr; A.results = dResults; A.nTasks = nTasks; A.next = dNext;
-    A.boundary = dBoundary; A.boundaryStride = boundaryStride; A.cells = dCells; A.packed16 = packed16; A.nRounds = nullptr;
+    A.boundary = dBoundary; A.boundaryStride = boundaryStride; A.cells = dCells; A.packed16 = packed16; A.nRounds = nullptr; A.zero = 0;
     SD_CUDA(cudaMemsetAsync(dNext, 0, sizeof(uint32_t), st));
     uint32_t nCta = std::min<uint32_t>(nWarpsAllocated / SW_WARPS, (nTasks + SW_WARPS - 1) / SW_WARPS);
     if (nCta == 0) nCta = 1;
