@@ -74,114 +74,6 @@ void likelihoodRatios(const SubMat &m, double *lr) {
         for (int b = 0; b < AA; b++) lr[a * AA + b] = m.prob[a * AA + b] / (m.pBack[a] * m.pBack[b]);
 }
 
-// Repeat-HMM posterior masking.  States: background + W repeat offsets, gap states disabled (MMseqs2
-// passes firstGapProb = otherGapProb = 0).  The reference build sums the foreground vector with four
-// interleaved AVX2 lanes, reduced as (l0+l2)+(l1+l3), followed by a scalar tail; the same association
-// is used here so the doubles agree.
-int tantanMask(uint8_t *seq, int L, const double *lr, double minMaskProb) {
-    constexpr int W = 50;
-    if (L <= 0) return 0;
-    const double pRepeat = 0.005, pEnd = 0.05, decay = 0.9;
-    const double bb = 1 - pRepeat, fb = pEnd, ff = 1 - pEnd;
-    double toFgProb[W], fg[W];
-    {
-        double p = pRepeat * ((1 - decay) / (1 - std::pow(decay, W)));
-        for (int i = 0; i < W; i++) { toFgProb[i] = p; p *= decay; }
-    }
-    std::vector<float> post(L);
-    std::vector<double> scale(L / 16 + 1);
-    double bg = 1.0;
-    std::fill(fg, fg + W, 0.0);
-    for (int p = 0; p < L; p++) {
-        const double *row = lr + seq[p] * AA;
-        const int reach = std::min(p, W);
-        const double b = bg;
-        double lane[4] = {0, 0, 0, 0};
-        int i = 0;
-        for (; i + 4 <= reach; i += 4) {
-            for (int k = 0; k < 4; k++) {
-                const double f = fg[i + k];
-                lane[k] = lane[k] + f;
-                fg[i + k] = (b * toFgProb[i + k] + f * ff) * row[seq[p - 1 - i - k]];
-            }
-        }
-        double fromFg = (lane[0] + lane[2]) + (lane[1] + lane[3]);
-        for (; i < reach; i++) {
-            const double f = fg[i];
-            fromFg += f;
-            fg[i] = (b * toFgProb[i] + f * ff) * row[seq[p - 1 - i]];
-        }
-        bg = b * bb + fromFg * fb;
-        if ((p & 15) == 15) {
-            const double s = 1 / bg;
-            scale[p >> 4] = s;
-            bg *= s;
-            for (int k = 0; k < W; k++) fg[k] *= s;
-        }
-        post[p] = static_cast<float>(bg);
-    }
-    double fgTotal = 0.0;
-    for (int i = 0; i < W; i++) fgTotal += fg[i];
-    const double z = bg * bb + fgTotal * fb;
-    bg = bb;
-    std::fill(fg, fg + W, fb);
-    for (int p = L - 1; p >= 0; p--) {
-        const double notRepeat = post[p] * bg / z;
-        post[p] = 1 - static_cast<float>(notRepeat);
-        if ((p & 15) == 15) {
-            const double s = scale[p >> 4];
-            bg *= s;
-            for (int k = 0; k < W; k++) fg[k] *= s;
-        }
-        const double *row = lr + seq[p] * AA;
-        const int reach = std::min(p, W);
-        const double toBg = fb * bg;
-        double lane[4] = {0, 0, 0, 0};
-        int i = 0;
-        for (; i + 4 <= reach; i += 4) {
-            for (int k = 0; k < 4; k++) {
-                const double f = fg[i + k] * row[seq[p - 1 - i - k]];
-                lane[k] = lane[k] + toFgProb[i + k] * f;
-                fg[i + k] = toBg + ff * f;
-            }
-        }
-        double toFg = (lane[0] + lane[2]) + (lane[1] + lane[3]);
-        for (; i < reach; i++) {
-            const double f = fg[i] * row[seq[p - 1 - i]];
-            toFg += toFgProb[i] * f;
-            fg[i] = toBg + ff * f;
-        }
-        bg = bb * bg + toFg;
-    }
-    int masked = 0;
-    for (int p = 0; p < L; p++)
-        if (post[p] >= minMaskProb) { seq[p] = XCODE; masked++; }
-    return masked;
-}
-
-uint64_t tantanMaskAll(uint8_t *res, const uint64_t *off, uint32_t n, const SubMat &seedMat, double minMaskProb) {
-    double lr[AA * AA];
-    likelihoodRatios(seedMat, lr);
-    unsigned nThreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
-    if (n < 64) nThreads = 1;
-    std::atomic<uint32_t> next{0};
-    std::atomic<uint64_t> total{0};
-    auto work = [&]() {
-        uint64_t mine = 0;
-        for (;;) {
-            const uint32_t lo = next.fetch_add(64);
-            if (lo >= n) break;
-            const uint32_t hi = std::min(n, lo + 64);
-            for (uint32_t s = lo; s < hi; s++) mine += tantanMask(res + off[s], static_cast<int>(off[s + 1] - off[s]), lr, minMaskProb);
-        }
-        total += mine;
-    };
-    std::vector<std::thread> pool;
-    for (unsigned t = 1; t < nThreads; t++) pool.emplace_back(work);
-    work();
-    for (auto &t : pool) t.join();
-    return total.load();
-}
 
 int kmerThreshold(float sensitivity, int kmerSize) {
     float best;

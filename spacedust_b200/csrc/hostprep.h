@@ -1,5 +1,5 @@
 // Host-side preparation shared by the CUDA stages: substitution matrices, residue mapping,
-// tantan masking of targets, the sorted 3-mer neighbour table.  Small double-precision pieces the
+// the sorted 3-mer neighbour table.  Small double-precision pieces the
 // reference also runs once per process; they stay on the host in the reference's operation order
 // (hard part 4).
 #pragma once
@@ -26,11 +26,9 @@ void buildSubMat(MatrixId which, float bitFactor, float scoreBias, SubMat &out);
 const uint8_t *aa2num();
 void mapSequence(const char *s, uint64_t len, uint8_t *out);
 
-// Masker::maskSequence -> tantan::maskSequences (lib/mmseqs/src/commons/Masker.cpp:52-92)
-int tantanMask(uint8_t *seq, int L, const double *lr /*AA*AA likelihood ratios*/, double minMaskProb);
+// likelihood ratios of the tantan repeat masker (ProbabilityMatrix, lib/mmseqs/src/commons/BaseMatrix.h:83-96); the masking
+// itself runs on the device (tantan.cu)
 void likelihoodRatios(const SubMat &m, double *lr);
-// mask all sequences in place with a pool of host threads; returns masked residue count
-uint64_t tantanMaskAll(uint8_t *res, const uint64_t *off, uint32_t n, const SubMat &seedMat, double minMaskProb);
 
 // Prefiltering::getKmerThreshold (Prefiltering.cpp:1005-1065), amino-acid sequence branch
 int kmerThreshold(float sensitivity, int kmerSize);

@@ -18,6 +18,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <memory>
 #include <numeric>
@@ -293,6 +294,8 @@ struct PrefilterArgs {
     unsigned long long *stats; // [0]=probes [1]=matches [2]=diagResidues [3]=hits [4]=candidates [5]=truncated [6]=errors
     uint32_t *nextQuery;
     uint32_t *errQuery;
+    uint32_t *failList;        // queries whose candidate list did not fit candCap (re-run with a larger list)
+    uint32_t *nFail;
     int evictFirst;            // L2 evict-first policy for the streamed data
     int prefetch;              // bit 0: table words, bit 1: bucket rows
     int debugSkip;             // profiling only (SD_PF_SKIP): bit 0 drops stage C, bit 1 drops stage B -- results are then wrong
@@ -397,7 +400,6 @@ __global__ void __launch_bounds__(PF_WARPS * 32, 4) prefilterKernel(PrefilterArg
 
     const uint64_t pol = l2Policy(a.evictFirst);
     const uint64_t polKeep = a.evictFirst ? l2PolicyKeep() : l2Policy(0);
-    unsigned long long stProbes = 0, stMatches = 0, stDiagRes = 0, stHits = 0, stCands = 0, stTrunc = 0;
     uint32_t epoch = 0;   // table words start zeroed; live epochs are 1..255
 
     for (;;) {
@@ -405,6 +407,9 @@ __global__ void __launch_bounds__(PF_WARPS * 32, 4) prefilterKernel(PrefilterArg
         if (lane == 0) qi = atomicAdd(a.nextQuery, 1u);
         qi = __shfl_sync(0xffffffffu, qi, 0);
         if (qi >= a.nQ) break;
+        // per-query counters: added to the global statistics only when the query completes (a query whose candidate
+        // list overflows is re-run by a second launch and counted there)
+        unsigned long long stProbes = 0, stMatches = 0, stDiagRes = 0, stHits = 0, stCands = 0, stTrunc = 0;
         const uint32_t q = a.order[qi];
         const uint32_t qBase = a.q.off[q];
         const int Lq = (int)(a.q.off[q + 1] - qBase);
@@ -813,23 +818,27 @@ __global__ void __launch_bounds__(PF_WARPS * 32, 4) prefilterKernel(PrefilterArg
             nOut += __popc(b);
             __syncwarp();
         }
+        // diagResidues is accumulated per lane
+        for (int d = 16; d > 0; d >>= 1) stDiagRes += __shfl_down_sync(0xffffffffu, stDiagRes, d);
         if (lane == 0) {
-            a.outCount[q] = nOut;
-            if (candOverflow) { atomicAdd(&a.stats[ST_ERR_CAND], 1ull); atomicMin(a.errQuery, q); }
-            if (needRescale) { atomicAdd(&a.stats[ST_ERR_RESCORE], 1ull); atomicMin(a.errQuery, q); }
+            if (candOverflow) {
+                a.outCount[q] = 0;
+                a.failList[atomicAdd(a.nFail, 1u)] = q;
+                atomicAdd(&a.stats[ST_ERR_CAND], 1ull);
+                atomicMin(a.errQuery, q);
+            } else {
+                a.outCount[q] = nOut;
+                if (needRescale) { atomicAdd(&a.stats[ST_ERR_RESCORE], 1ull); atomicMin(a.errQuery, q); }
+                atomicAdd(&a.stats[ST_PROBES], stProbes);
+                atomicAdd(&a.stats[ST_MATCHES], stMatches);
+                atomicAdd(&a.stats[ST_DIAGRES], stDiagRes);
+                atomicAdd(&a.stats[ST_HITS], stHits);
+                atomicAdd(&a.stats[ST_CANDS], stCands);
+                if (stTrunc) atomicAdd(&a.stats[ST_TRUNC], stTrunc);
+            }
         }
         __syncwarp();
     }
-    if (lane == 0) {
-        atomicAdd(&a.stats[ST_PROBES], stProbes);
-        atomicAdd(&a.stats[ST_MATCHES], stMatches);
-        atomicAdd(&a.stats[ST_HITS], stHits);
-        atomicAdd(&a.stats[ST_CANDS], stCands);
-        atomicAdd(&a.stats[ST_TRUNC], stTrunc);
-    }
-    // diagResidues is accumulated per lane
-    for (int d = 16; d > 0; d >>= 1) stDiagRes += __shfl_down_sync(0xffffffffu, stDiagRes, d);
-    if (lane == 0) atomicAdd(&a.stats[ST_DIAGRES], stDiagRes);
 }
 
 // dense[offs[q] + i] = out[q*maxHits + i]; one warp per query
@@ -893,6 +902,18 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
         if (off[i + 1] - off[i] >= 32768) { setError("target %u longer than 32767 residues: long-sequence path not implemented", i); return SD_ELIMIT; }
     SD_CUDA(cudaSetDevice(ctx->device));
     sd::StreamScope allocScope(ctx->stream);
+    const bool timing = getenv("SD_TIMING") != nullptr;
+    auto tPrev = std::chrono::steady_clock::now();
+    std::string tLog;
+    auto tick = [&](const char *name) {
+        if (!timing) return;
+        cudaStreamSynchronize(ctx->stream);
+        auto now = std::chrono::steady_clock::now();
+        char b[96];
+        snprintf(b, sizeof b, " %s=%.1f", name, std::chrono::duration<double, std::milli>(now - tPrev).count());
+        tLog += b;
+        tPrev = now;
+    };
     std::unique_ptr<sd_target_index> idx(new sd_target_index());
     idx->ctx = ctx;
     idx->nT = n;
@@ -901,24 +922,25 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
     idx->hostOff.resize(n + 1);
     for (uint32_t i = 0; i <= n; i++) idx->hostOff[i] = (uint32_t)off[i];
 
-    // residues: map on the host, mask with tantan on the host thread pool (double precision, see hostprep.cpp)
+    // residues: mapped on the host, uploaded once; the masked copy is made on the device (tantan.cu)
     std::vector<uint8_t> codes(total + SPAN);
     mapSequence(seqs, total, codes.data());
     std::fill(codes.begin() + total, codes.end(), (uint8_t)XCODE);
     int rc;
+    cudaStream_t st = ctx->stream;
     if ((rc = idx->raw.alloc(total + SPAN)) != SD_OK) return rc;
-    SD_CUDA(cudaMemcpyAsync(idx->raw.p, codes.data(), total + SPAN, cudaMemcpyHostToDevice, ctx->stream));
-    SD_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (uint32_t i = 0; i < n; i++) idx->maxLen = std::max<uint32_t>(idx->maxLen, (uint32_t)(off[i + 1] - off[i]));
-    if (par->mask) idx->masked = tantanMaskAll(codes.data(), off, n, ctx->seedMat, (double)par->mask_prob);
-
     if ((rc = idx->res.alloc(total + SPAN)) != SD_OK) return rc;
     if ((rc = idx->off.alloc(n + 1)) != SD_OK) return rc;
+    SD_CUDA(cudaMemcpyAsync(idx->raw.p, codes.data(), total + SPAN, cudaMemcpyHostToDevice, st));
+    SD_CUDA(cudaMemcpyAsync(idx->res.p, idx->raw.p, total + SPAN, cudaMemcpyDeviceToDevice, st));
+    SD_CUDA(cudaMemcpyAsync(idx->off.p, idx->hostOff.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    for (uint32_t i = 0; i < n; i++) idx->maxLen = std::max<uint32_t>(idx->maxLen, (uint32_t)(off[i + 1] - off[i]));
+    tick("map+upload");
+    if (par->mask && (rc = launchTantan(ctx, idx->res.p, idx->off.p, idx->hostOff, n, ctx->seedMat, (double)par->mask_prob, &idx->masked)) != SD_OK) return rc;
+    tick("tantan");
+
     DevBuf<uint32_t> kOff;                 // dense bucket starts: build-time only
     if ((rc = kOff.alloc((size_t)NKMER + 1)) != SD_OK) return rc;
-    cudaStream_t st = ctx->stream;
-    SD_CUDA(cudaMemcpyAsync(idx->res.p, codes.data(), total + SPAN, cudaMemcpyHostToDevice, st));
-    SD_CUDA(cudaMemcpyAsync(idx->off.p, idx->hostOff.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
 
     int8_t selfHost[AA];
     for (int a = 0; a < AA; a++) selfHost[a] = (int8_t)ctx->seedMat.sub[a * AA + a];   // getScoreLookup IndexBuilder.cpp:10-22
@@ -1000,7 +1022,10 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
         SD_CUDA(cudaStreamSynchronize(st));
     }
     SD_CUDA(cudaStreamSynchronize(st));
+    tick("index");
     if ((rc = ensureExt3(ctx)) != SD_OK) return rc;
+    tick("ext3");
+    if (timing) fprintf(stderr, "[sd_index]%s\n", tLog.c_str());
     *out = idx.release();
     return SD_OK;
 }
@@ -1108,10 +1133,11 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     static const int ctasPerSm = getenv("SD_PF_CTAS") ? atoi(getenv("SD_PF_CTAS")) : 4;
     const uint32_t nCta = std::max(1u, std::min<uint32_t>((uint32_t)(ctx->smCount * ctasPerSm), (nq + PF_WARPS - 1) / PF_WARPS));
     const uint32_t nWarps = nCta * PF_WARPS;
-    const uint32_t candCap = 32768;
+    // first-pass capacity of the per-warp candidate lists (SD_PF_CANDCAP: test hook that forces the second pass)
+    const uint32_t candCap = getenv("SD_PF_CANDCAP") ? (uint32_t)std::max(32, atoi(getenv("SD_PF_CANDCAP"))) : 32768u;
 
     ScratchBuf<uint32_t> dTable(ctx, SL_PF_TABLE), dResT(ctx, SL_PF_REST);
-    DevBuf<uint32_t> dOutCount, dNext;
+    DevBuf<uint32_t> dOutCount, dNext, dFail;
     ScratchBuf<uint64_t> dCand(ctx, SL_PF_CAND), dKeep(ctx, SL_PF_KEEP);
     ScratchBuf<int32_t> dResScore(ctx, SL_PF_RESS);
     ScratchBuf<uint16_t> dResDiag(ctx, SL_PF_RESD);
@@ -1119,12 +1145,13 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     DevBuf<unsigned long long> dStats;
     if ((rc = dTable.alloc((size_t)nWarps * idx->nT)) || (rc = dCand.alloc((size_t)nWarps * candCap)) || (rc = dKeep.alloc((size_t)nWarps * candCap)) ||
         (rc = dResT.alloc((size_t)nWarps * maxHits)) || (rc = dResScore.alloc((size_t)nWarps * maxHits)) || (rc = dResDiag.alloc((size_t)nWarps * maxHits)) ||
-        (rc = dOut.alloc((size_t)nq * maxHits)) || (rc = dOutCount.alloc(nq)) || (rc = dNext.alloc(2)) || (rc = dStats.alloc(ST_N)))
+        (rc = dOut.alloc((size_t)nq * maxHits)) || (rc = dOutCount.alloc(nq)) || (rc = dNext.alloc(4)) || (rc = dStats.alloc(ST_N)) ||
+        (rc = dFail.alloc(nq)))
         return rc;
     SD_CUDA(cudaMemsetAsync(dTable.p, 0, (size_t)nWarps * idx->nT * sizeof(uint32_t), st));
     SD_CUDA(cudaMemsetAsync(dOutCount.p, 0, nq * sizeof(uint32_t), st));
     SD_CUDA(cudaMemsetAsync(dStats.p, 0, ST_N * sizeof(unsigned long long), st));
-    const uint32_t initNext[2] = {0u, 0xffffffffu};
+    const uint32_t initNext[4] = {0u, 0xffffffffu, 0u, 0u};     // next query, first failing query, number of overflowed queries
     SD_CUDA(cudaMemcpyAsync(dNext.p, initNext, sizeof initNext, cudaMemcpyHostToDevice, st));
 
     PrefilterArgs a{};
@@ -1138,6 +1165,7 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     a.table = dTable.p; a.candCap = candCap; a.cand = dCand.p; a.keep = dKeep.p;
     a.resT = dResT.p; a.resScore = dResScore.p; a.resDiag = dResDiag.p;
     a.out = dOut.p; a.outCount = dOutCount.p; a.stats = dStats.p; a.nextQuery = dNext.p; a.errQuery = dNext.p + 1;
+    a.failList = dFail.p; a.nFail = dNext.p + 2;
 
     SD_CUDA(cudaEventRecord(evk0, st));
     static const int envEvict = getenv("SD_PF_EVICT") ? atoi(getenv("SD_PF_EVICT")) : 0;
@@ -1170,6 +1198,32 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     prefilterKernel<<<nCta, PF_WARPS * 32, PF_DYN_SMEM, st>>>(a);
     ctx->launches++;
     SD_CUDA(cudaGetLastError());
+    {   // queries with more than candCap double-hit candidates (long queries against very large target sets): second launch
+        // over just those, few warps with a 4 M entry list each
+        uint32_t hN[4];
+        SD_CUDA(cudaMemcpyAsync(hN, dNext.p, sizeof hN, cudaMemcpyDeviceToHost, st));
+        SD_CUDA(cudaStreamSynchronize(st));
+        const uint32_t nFail = hN[2];
+        if (nFail) {
+            const uint32_t bigCap = 1u << 22;
+            const uint32_t nCta2 = std::max(1u, std::min<uint32_t>((nFail + PF_WARPS - 1) / PF_WARPS, 16u));
+            const uint32_t nWarps2 = nCta2 * PF_WARPS;
+            DevBuf<uint64_t> dCand2, dKeep2;
+            DevBuf<uint32_t> dOrder2;
+            if ((rc = dCand2.alloc((size_t)nWarps2 * bigCap)) || (rc = dKeep2.alloc((size_t)nWarps2 * bigCap)) || (rc = dOrder2.alloc(nFail))) return rc;
+            SD_CUDA(cudaMemcpyAsync(dOrder2.p, dFail.p, nFail * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+            SD_CUDA(cudaMemsetAsync(dTable.p, 0, (size_t)nWarps2 * idx->nT * sizeof(uint32_t), st));      // epochs restart at 0
+            SD_CUDA(cudaMemsetAsync(dStats.p + ST_ERR_CAND, 0, sizeof(unsigned long long), st));
+            const uint32_t init2[4] = {0u, 0xffffffffu, 0u, 0u};
+            SD_CUDA(cudaMemcpyAsync(dNext.p, init2, sizeof init2, cudaMemcpyHostToDevice, st));
+            PrefilterArgs b = a;
+            b.order = dOrder2.p; b.nQ = nFail; b.candCap = bigCap; b.cand = dCand2.p; b.keep = dKeep2.p;
+            prefilterKernel<<<nCta2, PF_WARPS * 32, PF_DYN_SMEM, st>>>(b);
+            ctx->launches++;
+            SD_CUDA(cudaGetLastError());
+            SD_CUDA(cudaStreamSynchronize(st));     // init2 and the second-pass buffers go out of scope
+        }
+    }
     SD_CUDA(cudaEventRecord(evk1, st));
     if (envPersist) {
         cudaStreamAttrValue av{};
@@ -1179,12 +1233,12 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
 
     std::vector<uint32_t> hCount(nq);
     unsigned long long hStats[ST_N];
-    uint32_t hNext[2];
+    uint32_t hNext[4];
     SD_CUDA(cudaMemcpyAsync(hCount.data(), dOutCount.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     SD_CUDA(cudaMemcpyAsync(hStats, dStats.p, sizeof hStats, cudaMemcpyDeviceToHost, st));
     SD_CUDA(cudaMemcpyAsync(hNext, dNext.p, sizeof hNext, cudaMemcpyDeviceToHost, st));
     SD_CUDA(cudaStreamSynchronize(st));
-    if (hStats[ST_ERR_CAND]) { setError("prefilter: %llu queries produced more than %u diagonal candidates (first: query %u)", hStats[ST_ERR_CAND], candCap, hNext[1]); return SD_ELIMIT; }
+    if (hStats[ST_ERR_CAND]) { setError("prefilter: %llu queries produced more than %u diagonal candidates (first: query %u)", hStats[ST_ERR_CAND], 1u << 22, hNext[1]); return SD_ELIMIT; }
     if (hStats[ST_ERR_RESCORE]) { setError("prefilter: %llu queries need the reference's truncated-score rescaling path (>= max-seqs hits at score 255; first: query %u): not implemented", hStats[ST_ERR_RESCORE], hNext[1]); return SD_ELIMIT; }
     uint64_t totalHits = 0;
     for (uint32_t i = 0; i < nq; i++) totalHits += hCount[i];

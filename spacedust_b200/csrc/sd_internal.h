@@ -190,6 +190,8 @@ int launchSwProfiles(sd_context *ctx, const uint8_t *code, const int8_t *cb, con
                      int8_t *fwd, int8_t *rev);
 int launchAlignCompositionBias(sd_context *ctx, const float *bias, uint32_t totalRes, int8_t *cb);
 uint32_t swWarpsPerCta();
+int launchTantan(sd_context *ctx, uint8_t *dRes, const uint32_t *dOff, const std::vector<uint32_t> &hostOff, uint32_t n,
+                 const SubMat &seedMat, double minMaskProb, uint64_t *maskedOut);
 
 }  // namespace sd
 

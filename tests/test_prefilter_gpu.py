@@ -68,6 +68,17 @@ def test_prefilter_truncation_tie_order(gpu_ctx):
     _compare(gpu_ctx, buf, off, buf, off, True, maxSeqs=12, minDiagScore=0, binSize=8)
 
 
+def test_prefilter_candidate_overflow_second_pass(gpu_ctx, synth_small, monkeypatch):
+    """Queries whose double-hit candidate list exceeds the first-pass capacity are re-run by a second launch with a
+    larger list: hits AND the P/M/R/H counters must still equal the oracle's (SD_PF_CANDCAP forces the situation)."""
+    monkeypatch.setenv("SD_PF_CANDCAP", "32")
+    buf, off, _ = synth.pack(synth_small)
+    st = _compare(gpu_ctx, buf, off, buf, off, True)
+    assert st["candidates"] > 32 * 10
+    fbuf, foff = _weak_family_set()
+    _compare(gpu_ctx, fbuf, foff, fbuf, foff, True, maxSeqs=16)
+
+
 def test_prefilter_edge_sequences(gpu_ctx):
     """Short (< k-mer span), X-rich, low-complexity and duplicated sequences."""
     long_seq = ("MKTAYIAKQRQISFVKSHFSRQLEERLGLIEVQAPILSRVGDGTQDNLSGAEKAVQVKVKALPDAQFEVVHSLAKWKRQTLGQHDFSAGEGLYTHMKALRPDEDRLSPLHSVYV"
