@@ -480,18 +480,26 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     const uint32_t nPos = (uint32_t)total;
     const std::vector<uint32_t> &hOff = queries->hostOff;
     std::vector<uint32_t> hStride(nq), hLen(nq);
-    std::vector<uint64_t> hProfOff(nq + 1);
+    std::vector<uint64_t> hProfOff(nq + 1), hStgOff(nq + 1);
+    std::vector<uint32_t> hStgStride(nq);
     hProfOff[0] = 0;
+    hStgOff[0] = 0;
     uint32_t maxQ = 1;
     for (uint32_t i = 0; i < nq; i++) {
         hLen[i] = hOff[i + 1] - hOff[i];
         maxQ = std::max(maxQ, hLen[i]);
         hStride[i] = ((hLen[i] + 3u) & ~3u) + 72u;          // >= 68 bytes of -128 after every row
         hProfOff[i + 1] = hProfOff[i] + (uint64_t)(AA + 1) * hStride[i];   // + dummy-letter row
+        int rp, rpPad, nStages;
+        swStageLayout((int)hLen[i], rp, rpPad, nStages);
+        hStgStride[i] = (uint32_t)(nStages * rpPad);                       // 0: no staged profile (32-lane classes)
+        hStgOff[i + 1] = hStgOff[i] + (uint64_t)(AA + 1) * hStgStride[i];
     }
+    const uint64_t stgBytes = hStgOff[nq] + 8192;
     const uint64_t profBytes = hProfOff[nq] + 8192;
-    DevBuf<uint32_t> dStride, dLen, dNext;
-    DevBuf<uint64_t> dProfOff;
+    DevBuf<uint32_t> dStride, dLen, dNext, dStgStride;
+    DevBuf<uint64_t> dProfOff, dStgOff;
+    ScratchBuf<int8_t> dProfS(ctx, SL_AL_PROFS);
     DevBuf<float> dBias;
     DevBuf<int8_t> dCb, dMat8;
     ScratchBuf<int8_t> dProfF(ctx, SL_AL_PROFF), dProfR(ctx, SL_AL_PROFR);
@@ -500,8 +508,12 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     DevBuf<unsigned long long> dCells;
     if ((rc = dStride.alloc(nq)) || (rc = dLen.alloc(nq)) || (rc = dProfOff.alloc(nq + 1)) || (rc = dBias.alloc(total + 16)) ||
         (rc = dCb.alloc(total + 16)) || (rc = dMat8.alloc(AA * AA)) || (rc = dSub.alloc(AA * AA)) || (rc = dPBack.alloc(AA)) ||
-        (rc = dProfF.alloc(profBytes)) || (rc = dProfR.alloc(profBytes)) || (rc = dNext.alloc(4)) || (rc = dCells.alloc(4)))
+        (rc = dProfF.alloc(profBytes)) || (rc = dProfR.alloc(profBytes)) || (rc = dNext.alloc(4)) || (rc = dCells.alloc(4)) ||
+        (rc = dStgStride.alloc(nq)) || (rc = dStgOff.alloc(nq + 1)) || (rc = dProfS.alloc(stgBytes)))
         return rc;
+    SD_CUDA(cudaMemcpyAsync(dStgStride.p, hStgStride.data(), nq * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    SD_CUDA(cudaMemcpyAsync(dStgOff.p, hStgOff.data(), (nq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    SD_CUDA(cudaMemsetAsync(dProfS.p, 0x80, stgBytes, st));
     SD_CUDA(cudaMemcpyAsync(dStride.p, hStride.data(), nq * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     SD_CUDA(cudaMemcpyAsync(dLen.p, hLen.data(), nq * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     SD_CUDA(cudaMemcpyAsync(dProfOff.p, hProfOff.data(), (nq + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -515,7 +527,7 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     ctx->launches += 1;
     SD_CUDA(cudaGetLastError());
     if ((rc = launchAlignCompositionBias(ctx, dBias.p, nPos, dCb.p))) return rc;
-    if ((rc = launchSwProfiles(ctx, queries->code.p, dCb.p, queries->off.p, nq, nPos, dMat8.p, dProfOff.p, dStride.p, dProfF.p, dProfR.p))) return rc;
+    if ((rc = launchSwProfiles(ctx, queries->code.p, dCb.p, queries->off.p, nq, nPos, dMat8.p, dProfOff.p, dStride.p, dProfF.p, dProfR.p, dStgOff.p, dStgStride.p, dProfS.p))) return rc;
     std::vector<int8_t> hCb(total);
     const std::vector<uint8_t> &hCode = queries->hostCode;
     SD_CUDA(cudaMemcpyAsync(hCb.data(), dCb.p, total, cudaMemcpyDeviceToHost, st));
@@ -593,6 +605,7 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
 
     SwBatch batch;
     batch.profFwd = dProfF.p; batch.profRev = dProfR.p; batch.profOff = dProfOff.p; batch.profStride = dStride.p; batch.qLen = dLen.p;
+    batch.profStg = dProfS.p; batch.stgOff = dStgOff.p; batch.stgStride = dStgStride.p;
     batch.tRes = idx->raw.p; batch.tOff = idx->off.p; batch.gapOpen = par->gap_open; batch.gapExtend = par->gap_extend;
     const uint32_t swWarps = (uint32_t)ctx->smCount * 4u * swWarpsPerCta();
     const uint32_t bndStride = std::max<uint32_t>(idx->maxLen, 32u) + 32u;

@@ -964,6 +964,7 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
         SD_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmpBytes, keysA.p, keysB.p, (int64_t)nPos, 0, 64, st));
         SD_CUDA(cudaStreamSynchronize(st));
     }
+    tick("extract+sort64");
     keysA.release();
     if ((rc = kmerA.alloc(nPos)) != SD_OK || (rc = kmerB.alloc(nPos)) != SD_OK) return rc;
     if ((rc = payloadA.alloc(nPos)) != SD_OK || (rc = payloadB.alloc(nPos)) != SD_OK) return rc;
@@ -980,6 +981,7 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
         SD_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmpBytes, kmerA.p, kmerB.p, payloadA.p, payloadB.p, (int64_t)nPos, 0, 32, st));
         SD_CUDA(cudaStreamSynchronize(st));
     }
+    tick("first+sort32");
     // bucket starts = exclusive scan of the counts
     {
         size_t tmpBytes = 0;
@@ -992,12 +994,14 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
     SD_CUDA(cudaMemcpyAsync(&nEnt, kOff.p + NKMER, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     SD_CUDA(cudaStreamSynchronize(st));
     idx->nEntries = nEnt;
+    tick("scan");
     if ((rc = idx->ent.alloc(nEnt)) != SD_OK) return rc;
     if (nEnt > 0) {
         packEntries<<<gridFor(nEnt, 256), 256, 0, st>>>(payloadB.p, nEnt, idx->ent.p);
         ctx->launches++;
         SD_CUDA(cudaGetLastError());
     }
+    tick("pack");
     // occupancy bitmap + rank, compact bucket starts
     {
         const uint32_t nWords = (NKMER + 31) / 32;
@@ -1022,7 +1026,7 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
         SD_CUDA(cudaStreamSynchronize(st));
     }
     SD_CUDA(cudaStreamSynchronize(st));
-    tick("index");
+    tick("bitmap");
     if ((rc = ensureExt3(ctx)) != SD_OK) return rc;
     tick("ext3");
     if (timing) fprintf(stderr, "[sd_index]%s\n", tLog.c_str());

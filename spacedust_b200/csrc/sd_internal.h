@@ -82,7 +82,7 @@ struct DevBuf {
 enum ScratchSlot {
     SL_PF_TABLE = 0, SL_PF_CAND, SL_PF_KEEP, SL_PF_REST, SL_PF_RESS, SL_PF_RESD, SL_PF_OUT, SL_PF_DENSE,
     SL_AL_FWD, SL_AL_WORD, SL_AL_BIG, SL_AL_REV, SL_AL_RES, SL_AL_HITS, SL_AL_TB, SL_AL_TBRES, SL_AL_IDENT, SL_AL_ORDER,
-    SL_AL_PROFF, SL_AL_PROFR, SL_AL_BOUND, SL_AL_PAIRQ, SL_AL_PAIRT,
+    SL_AL_PROFF, SL_AL_PROFR, SL_AL_PROFS, SL_AL_BOUND, SL_AL_PAIRQ, SL_AL_PAIRT,
     SL_TB_DIR, SL_TB_ROWS, SL_TB_REV, SL_TB_POOL, SL_SW_KEYA, SL_SW_KEYB, SL_SW_VALA, SL_SW_VALB, SL_SW_ORDER, SL_SW_TMP, SL_COUNT
 };
 void *ctxDeviceScratch(sd_context *ctx, int slot, size_t bytes);     // nullptr + error message on failure
@@ -187,7 +187,7 @@ int launchSw(sd_context *ctx, const SwBatch &batch, const SwTask *dTasks, SwResu
              uint32_t boundaryStride, uint32_t nWarpsAllocated, uint32_t *dNext, unsigned long long *dCells, int packed16, int keyed);
 int launchSwProfiles(sd_context *ctx, const uint8_t *code, const int8_t *cb, const uint32_t *qOff, uint32_t nQ,
                      uint32_t totalRes, const int8_t *mat, const uint64_t *profOff, const uint32_t *profStride,
-                     int8_t *fwd, int8_t *rev);
+                     int8_t *fwd, int8_t *rev, const uint64_t *stgOff, const uint32_t *stgStride, int8_t *stg);
 int launchAlignCompositionBias(sd_context *ctx, const float *bias, uint32_t totalRes, int8_t *cb);
 uint32_t swWarpsPerCta();
 int launchTantan(sd_context *ctx, uint8_t *dRes, const uint32_t *dOff, const std::vector<uint32_t> &hostOff, uint32_t n,

@@ -211,19 +211,6 @@ __device__ __forceinline__ uint32_t pack16(int lo, int hi) { return ((uint32_t)l
 __device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xffffu); }
 __device__ __forceinline__ int hi16(uint32_t v) { return (int)(short)(v >> 16); }
 
-// Scheduling classes of the packed pass: (lanes per pair, packed rows per stage).  Short queries use 8 lanes per pair
-// (4 pairs per warp, 16 wavefront stages), so every lane still owns enough rows to amortise the per-step work
-// (shuffles, profile fetch, maxima) and the pipeline fill is 15 columns instead of 63.  The stage height follows the
-// segment length of the 8-bit striped layout, segLen = ceil(nRows/32): 8 lanes -> RP = 2 segLen, 16 lanes -> RP = segLen,
-// so that in the forward 8-bit pass every segment starts at a compile-time row of a stage (SEGMODE below).
-__host__ __device__ inline int swClassOf(int nRows) {
-    if (nRows <= 320) { int rp = 2 * ((nRows + 31) / 32); if (rp < 2) rp = 2; return rp / 2 - 1; }                       // 0..9  : 8 lanes, RP 2,4..20
-    if (nRows <= 640) { const int rp = (nRows + 31) / 32; return 10 + (rp - 11); }                                       // 10..19: 16 lanes, RP 11..20
-    if (nRows <= 1280) { int rp = (nRows + 63) / 64; rp = (rp + 1) & ~1; return 20 + (rp - 12) / 2; }                   // 20..24: 32 lanes, RP 12..20
-    return 25;                                                                                                         // stripes of 1280 rows
-}
-__host__ __device__ inline int swClassTasksPerRound(int cls) { return cls < 10 ? 4 : (cls < 20 ? 2 : 1); }
-constexpr int SW_NCLASS = 26;
 constexpr int SW_KEYMUL = 33;      // column-maximum key = H * 33 + (31 - k): not a shift, so it is an IMAD (FMA pipe), not an LEA
 
 // SEGMODE: where the reference's segment starts (Fm resets) fall inside a stage
@@ -277,8 +264,12 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
                 segKeep[SEGMODE == 0 ? k : 0] = a | b;
             }
         }
-        const uintptr_t addrA = (uintptr_t)(prof + rowOffset + (uint32_t)i0);
-        const uintptr_t addrB = addrA + RP;
+        // SEGMODE != 0 (forward 8-bit pass): staged profile, stage st starts at st * RPPAD on a 4-byte boundary
+        constexpr int RPPAD = (RP + 3) & ~3;
+        const uint32_t strideU = (SEGMODE != 0 && have) ? A.b.stgStride[tk.q] : stride;
+        const uintptr_t addrA = (SEGMODE != 0) ? (uintptr_t)(A.b.profStg + (have ? A.b.stgOff[tk.q] : 0ull) + (uint32_t)(2 * gl) * RPPAD)
+                                               : (uintptr_t)(prof + rowOffset + (uint32_t)i0);
+        const uintptr_t addrB = addrA + ((SEGMODE != 0) ? RPPAD : RP);
         const uint32_t shA = (uint32_t)(addrA & 3u) * 8u, shB = (uint32_t)(addrB & 3u) * 8u;
 
         uint32_t H[RP], E[RP];
@@ -318,16 +309,23 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
             const int cA = s - 2 * (int)gl;
             if (cA >= 0 && cA <= nCols && laneHasRows && !overflow) {   // stage A column cA in [0,nCols), stage B column cA-1
                 const uint32_t letA = inL & 0xffffu, letB = inL >> 16;
-                const uint32_t *wa = (const uint32_t *)((addrA + (uintptr_t)letA * stride) & ~(uintptr_t)3);
-                const uint32_t *wb = (const uint32_t *)((addrB + (uintptr_t)letB * stride) & ~(uintptr_t)3);
-                uint32_t ra[NWA + 1], rb[NWA + 1];
-#pragma unroll
-                for (int w = 0; w <= NWA; w++) { ra[w] = __ldg(wa + w); rb[w] = __ldg(wb + w); }
                 uint32_t sa[NWA], sb[NWA];
+                if (SEGMODE != 0) {
+                    const uint32_t *wa = (const uint32_t *)(addrA + (uintptr_t)letA * strideU);
+                    const uint32_t *wb = (const uint32_t *)(addrB + (uintptr_t)letB * strideU);
 #pragma unroll
-                for (int w = 0; w < NWA; w++) {
-                    sa[w] = __funnelshift_r(ra[w], ra[w + 1], shA);
-                    sb[w] = __funnelshift_r(rb[w], rb[w + 1], shB);
+                    for (int w = 0; w < NWA; w++) { sa[w] = __ldg(wa + w); sb[w] = __ldg(wb + w); }
+                } else {
+                    const uint32_t *wa = (const uint32_t *)((addrA + (uintptr_t)letA * stride) & ~(uintptr_t)3);
+                    const uint32_t *wb = (const uint32_t *)((addrB + (uintptr_t)letB * stride) & ~(uintptr_t)3);
+                    uint32_t ra[NWA + 1], rb[NWA + 1];
+#pragma unroll
+                    for (int w = 0; w <= NWA; w++) { ra[w] = __ldg(wa + w); rb[w] = __ldg(wb + w); }
+#pragma unroll
+                    for (int w = 0; w < NWA; w++) {
+                        sa[w] = __funnelshift_r(ra[w], ra[w + 1], shA);
+                        sb[w] = __funnelshift_r(rb[w], rb[w + 1], shB);
+                    }
                 }
                 uint32_t diag = prevHup;
                 uint32_t ft = inFt, fm = inFm;
@@ -446,7 +444,7 @@ __global__ void __launch_bounds__(SW_WARPS * 32) swKernel16(SwKernelArgs A) {
                 const SwTask tg = A.tasks[idg];
                 const int sl = (tg.nRows + tg.width - 1) / tg.width;
                 const int rp = cls < 10 ? 2 * (cls + 1) : cls + 1;
-                ok = (cls < 10) ? (2 * sl == rp) : (sl == rp);
+                ok = ((cls < 10) ? (2 * sl == rp) : (sl == rp)) && tg.reverse == 0 && tg.nRows == (int)A.b.qLen[tg.q] && A.b.stgStride[tg.q] != 0;
             }
             segAligned = __all_sync(0xffffffffu, ok);
         }
@@ -534,7 +532,8 @@ __global__ void __launch_bounds__(SW_WARPS * 32) swKernel(SwKernelArgs A) {
 __global__ void buildSwProfiles(const uint8_t *__restrict__ code, const int8_t *__restrict__ cb,
                                 const uint32_t *__restrict__ qOff, uint32_t nQ, uint32_t totalRes,
                                 const int8_t *__restrict__ mat /*21x21*/, const uint64_t *__restrict__ profOff,
-                                const uint32_t *__restrict__ profStride, int8_t *__restrict__ fwd, int8_t *__restrict__ rev) {
+                                const uint32_t *__restrict__ profStride, int8_t *__restrict__ fwd, int8_t *__restrict__ rev,
+                                const uint64_t *__restrict__ stgOff, const uint32_t *__restrict__ stgStride, int8_t *__restrict__ stg) {
     const uint32_t gp = blockIdx.x * blockDim.x + threadIdx.x;
     if (gp >= totalRes) return;
     // binary search of the owning query
@@ -548,11 +547,16 @@ __global__ void buildSwProfiles(const uint8_t *__restrict__ code, const int8_t *
     const int c = code[gp];
     const int b = cb[gp];
     int8_t *f = fwd + profOff[q], *r = rev + profOff[q];
+    const uint32_t sStride = stgStride[q];
+    int rp, rpPad, nStages;
+    swStageLayout((int)L, rp, rpPad, nStages);
+    int8_t *g = stg + stgOff[q] + (sStride ? (i / (uint32_t)rp) * (uint32_t)rpPad + i % (uint32_t)rp : 0u);
 #pragma unroll
     for (int a = 0; a < AA; a++) {
         const int8_t v = (int8_t)(mat[a * AA + c] + b);
         f[(size_t)a * stride + i] = v;
         r[(size_t)a * stride + (L - 1 - i)] = v;
+        if (sStride) g[(size_t)a * sStride] = v;
     }
     // row AA (dummy letter) and all padding stay at the memset value -128
 }
@@ -615,9 +619,10 @@ int launchSw(sd_context *ctx, const SwBatch &batch, const SwTask *dTasks, SwResu
 
 int launchSwProfiles(sd_context *ctx, const uint8_t *code, const int8_t *cb, const uint32_t *qOff, uint32_t nQ,
                      uint32_t totalRes, const int8_t *mat, const uint64_t *profOff, const uint32_t *profStride,
-                     int8_t *fwd, int8_t *rev) {
+                     int8_t *fwd, int8_t *rev, const uint64_t *stgOff, const uint32_t *stgStride, int8_t *stg) {
     if (totalRes == 0) return SD_OK;
-    buildSwProfiles<<<(totalRes + 127) / 128, 128, 0, ctx->stream>>>(code, cb, qOff, nQ, totalRes, mat, profOff, profStride, fwd, rev);
+    buildSwProfiles<<<(totalRes + 127) / 128, 128, 0, ctx->stream>>>(code, cb, qOff, nQ, totalRes, mat, profOff, profStride, fwd, rev,
+                                                                      stgOff, stgStride, stg);
     ctx->launches++;
     SD_CUDA(cudaGetLastError());
     return SD_OK;
