@@ -139,9 +139,11 @@ typedef struct {
     float qcov, tcov;
     double evalue;
     int32_t q_start, q_end, q_len, t_start, t_end, t_len, aln_len;
-    uint64_t bt_off;          /* offset of the M/I/D backtrace in the backtrace pool   */
-    uint32_t bt_len;
-    uint32_t pad;
+    uint64_t bt_off;          /* offset of the backtrace string in the backtrace pool  */
+    uint32_t bt_len;          /* its length in bytes                                   */
+    uint32_t bt_cigar;        /* 1: the string is the run-length CIGAR text ("35M2D20M", what the library returns --
+                                 Matcher::compressAlignment, Matcher.cpp:166-185, done on the device); 0: one M/I/D
+                                 byte per alignment column (accepted on input, e.g. by sd_format_alignment) */
 } sd_alignment;
 
 typedef struct {

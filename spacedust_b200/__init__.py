@@ -178,7 +178,7 @@ class AlignStats(ctypes.Structure):
 ALN_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("score", "<i4"), ("bits", "<i4"), ("seq_id", "<f4"),
                       ("qcov", "<f4"), ("tcov", "<f4"), ("evalue", "<f8"), ("q_start", "<i4"), ("q_end", "<i4"),
                       ("q_len", "<i4"), ("t_start", "<i4"), ("t_end", "<i4"), ("t_len", "<i4"), ("aln_len", "<i4"),
-                      ("bt_off", "<u8"), ("bt_len", "<u4"), ("pad", "<u4")], align=True)
+                      ("bt_off", "<u8"), ("bt_len", "<u4"), ("bt_cigar", "<u4")], align=True)
 
 
 def default_align_params(**kw):

@@ -16,6 +16,8 @@
 #include <memory>
 #include <thread>
 
+#include <cub/cub.cuh>
+
 #include "sd_internal.h"
 #include "prep.cuh"
 #include "sw.cuh"
@@ -23,20 +25,29 @@
 namespace sd {
 
 // ------------------------------------------------------------------------------------------------
-// banded traceback: one warp per alignment, lanes across the band of one query row
+// banded traceback (banded_sw + computerBacktrace, StripedSmithWaterman.cpp:1348-1600,548-581)
+//
+// A warp fills the direction matrices of up to 32 alignments one after the other into its scratch slot -- lanes across the
+// band of one query row, the horizontal gap chain F_j = max(H_{j-1} - go, F_{j-1} - ge) as a decayed max-scan, row buffers
+// in shared memory while the band fits, ONE direction byte per cell (bit 0: E came from H, bit 1: F came from H, bits 2-4:
+// the H source) -- and then walks the 32 paths in parallel, one lane per alignment, so the dependent loads of the walk
+// overlap.  The walk run-length encodes on the fly and writes the CIGAR text right-to-left at the end of the alignment's
+// pool slot (the path is found end to start), so only the compressed string ever leaves the device.
 // ------------------------------------------------------------------------------------------------
 struct TbTask {
     uint32_t q, t;
     int32_t qStart, qEnd, tStart, tEnd, score;
     uint32_t pad;
-    uint64_t btOff;
+    uint64_t btOff;       // pool slot of 2 * (rows + columns) + 2 bytes (worst case: every run has length 1)
 };
 
 struct TbResult {
-    int32_t btLen;
+    int32_t btLen;        // alignment columns (M/I/D operations)
     int32_t ids;
-    int32_t status;    // 0 ok, 1 scratch too small, 2 trace walked off the band
+    int32_t status;       // 0 ok, 1 scratch too small, 2 trace walked off the band
     int32_t band;
+    uint32_t cigLen;      // CIGAR text bytes
+    uint32_t cigStart;    // offset of the text inside the slot
 };
 
 struct TbArgs {
@@ -50,163 +61,231 @@ struct TbArgs {
     const TbTask *tasks;
     const uint32_t *order;   // optional subset
     TbResult *results;
+    uint32_t *cigLen;        // per task (scan input of the pool compaction)
     uint32_t nTasks;
     uint32_t *next;
     // per-warp scratch
     int8_t *dir;
     uint64_t dirCap;
-    int *rows;               // 3 x rowCap ints
+    int *rows;               // 3 x rowCap ints (bands too wide for shared memory)
     uint32_t rowCap;
-    char *rev;
-    uint32_t revCap;
     char *btPool;
     unsigned long long *cells;
 };
 
 constexpr int TB_WARPS = 4;
+constexpr int TB_BATCH = 32;
+constexpr int TB_SROW = 264;     // shared-memory row buffers: bands up to 129
 constexpr int TB_NEG = -(1 << 28);
+
+__device__ __forceinline__ uint32_t tbSlotBytes(const TbTask &tk) { return 2u * (uint32_t)((tk.qEnd - tk.qStart + 1) + (tk.tEnd - tk.tStart + 1)) + 2u; }
 
 __global__ void __launch_bounds__(TB_WARPS * 32) tracebackKernel(TbArgs A) {
     __shared__ int8_t sMat[AA * AA];
+    __shared__ int sRows[TB_WARPS][3 * TB_SROW];
+    __shared__ uint32_t sId[TB_WARPS][TB_BATCH];
+    __shared__ uint32_t sBase[TB_WARPS][TB_BATCH];
+    __shared__ int sBand[TB_WARPS][TB_BATCH];
     for (int i = threadIdx.x; i < AA * AA; i += blockDim.x) sMat[i] = A.mat[i];
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp = blockIdx.x * TB_WARPS + (threadIdx.x >> 5);
+    const uint32_t wIn = threadIdx.x >> 5;
+    const uint32_t warp = blockIdx.x * TB_WARPS + wIn;
     int8_t *dir = A.dir + (size_t)warp * A.dirCap;
-    int *hb = A.rows + (size_t)warp * 3 * A.rowCap;
-    int *eb = hb + A.rowCap;
-    int *hc = eb + A.rowCap;
-    char *rev = A.rev + (size_t)warp * A.revCap;
+    int *gRows = A.rows + (size_t)warp * 3 * A.rowCap;
     const int go = A.gapOpen, ge = A.gapExtend;
     unsigned long long cells = 0;
+    uint32_t carry = 0xffffffffu;
+    bool drained = false;
 
     for (;;) {
-        uint32_t ti = 0;
-        if (lane == 0) ti = atomicAdd(A.next, 1u);
-        ti = __shfl_sync(0xffffffffu, ti, 0);
-        if (ti >= A.nTasks) break;
-        const uint32_t id = A.order ? A.order[ti] : ti;
-        const TbTask tk = A.tasks[id];
-        const int qLen = tk.qEnd - tk.qStart + 1, dbLen = tk.tEnd - tk.tStart + 1;
-        const uint8_t *qc = A.qCode + A.qOff[tk.q] + tk.qStart;
-        const int8_t *qb = A.qCb + A.qOff[tk.q] + tk.qStart;
-        const uint8_t *tc = A.tRes + A.tOff[tk.t] + tk.tStart;
-        int band = abs(dbLen - qLen) + 1;
-        int maxH = 0;
-        int status = 0;
-        long widthD = 0;
-        for (;;) {
-            const long width = (long)band * 2 + 3;
-            widthD = (long)band * 2 + 1;
-            if ((unsigned long long)widthD * (unsigned long long)qLen * 3ull > A.dirCap || (unsigned long long)width + 2 > A.rowCap) { status = 1; break; }
-            for (long u = lane; u < width + 1; u += 32) { hb[u] = 0; eb[u] = 0; hc[u] = 0; }
-            __syncwarp();
-            for (int i = 0; i < qLen; i++) {
-                const int beg = max(0, i - band), end = min(dbLen - 1, i + band);
-                const int edge = (int)min((long)end + 1, width - 1);
-                const int xi = max(i - band, 0), xim = max(i - 1 - band, 0);
-                if (lane == 0) { hb[0] = 0; eb[0] = 0; hb[edge] = 0; eb[edge] = 0; hc[0] = 0; }
+        // ---------------- fill: direction bytes of up to TB_BATCH alignments behind each other in the scratch slot
+        int nb = 0;
+        uint64_t used = 0;
+        while (nb < TB_BATCH) {
+            uint32_t ti = carry;
+            carry = 0xffffffffu;
+            if (ti == 0xffffffffu) {
+                if (drained) break;
+                if (lane == 0) ti = atomicAdd(A.next, 1u);
+                ti = __shfl_sync(0xffffffffu, ti, 0);
+                if (ti >= A.nTasks) { drained = true; break; }
+            }
+            const uint32_t id = A.order ? A.order[ti] : ti;
+            const TbTask tk = A.tasks[id];
+            const int qLen = tk.qEnd - tk.qStart + 1, dbLen = tk.tEnd - tk.tStart + 1;
+            const uint8_t *qc = A.qCode + A.qOff[tk.q] + tk.qStart;
+            const int8_t *qb = A.qCb + A.qOff[tk.q] + tk.qStart;
+            const uint8_t *tc = A.tRes + A.tOff[tk.t] + tk.tStart;
+            int band = abs(dbLen - qLen) + 1;
+            int maxH = 0;
+            int status = 0;
+            long widthD = 0;
+            uint64_t need = 0;
+            for (;;) {
+                const long width = (long)band * 2 + 3;
+                widthD = (long)band * 2 + 1;
+                need = (uint64_t)widthD * (uint64_t)qLen;
+                if (need > A.dirCap) { status = 1; break; }                  // needs the large-slot pass
+                if (need > A.dirCap - used) { status = 3; break; }           // no room behind this batch: opens the next one
+                int *hb, *eb, *hc;
+                if (width + 2 <= TB_SROW) { hb = sRows[wIn]; eb = hb + TB_SROW; hc = eb + TB_SROW; }
+                else if ((unsigned long long)width + 2 <= A.rowCap) { hb = gRows; eb = hb + A.rowCap; hc = eb + A.rowCap; }
+                else { status = 1; break; }
+                int8_t *dBase = dir + used;
+                for (long u = lane; u < width + 1; u += 32) { hb[u] = 0; eb[u] = 0; hc[u] = 0; }
                 __syncwarp();
-                const int8_t *mrow = sMat + (int)qc[i] * AA;
-                const int cbv = qb[i];
-                int8_t *line = dir + widthD * (long)i * 3;
-                int carryH = 0, carryF = 0;
-                for (int j0 = beg; j0 <= end; j0 += 32) {
-                    const int j = j0 + (int)lane;
-                    const bool valid = j <= end;
-                    const int u = j - xi + 1, up = j - xim + 1, dg = j - xim;
-                    int hbu = 0, ebu = 0, hbd = 0, tj = 0;
-                    if (valid) { hbu = hb[up]; ebu = eb[up]; hbd = hb[dg]; tj = tc[j]; }
+                for (int i = 0; i < qLen; i++) {
+                    const int beg = max(0, i - band), end = min(dbLen - 1, i + band);
+                    const int edge = (int)min((long)end + 1, width - 1);
+                    const int xi = max(i - band, 0), xim = max(i - 1 - band, 0);
+                    if (lane == 0) { hb[0] = 0; eb[0] = 0; hb[edge] = 0; eb[edge] = 0; hc[0] = 0; }
                     __syncwarp();
-                    int t1 = (i == 0) ? -go : hbu - go;
-                    int t2 = (i == 0) ? -ge : ebu - ge;
-                    const int e = t1 > t2 ? t1 : t2;
-                    const int8_t de = t1 > t2 ? 3 : 2;
-                    const int e1 = e > 0 ? e : 0;
-                    const int diagv = hbd + (int)mrow[tj] + cbv;
-                    const int h0 = e1 > diagv ? e1 : diagv;
-                    // horizontal gap chain F_j = max(H_{j-1} - go, F_{j-1} - ge) as a decayed max-scan
-                    int y = valid ? h0 - go : TB_NEG;
+                    const int8_t *mrow = sMat + (int)qc[i] * AA;
+                    const int cbv = qb[i];
+                    int8_t *line = dBase + widthD * (long)i;
+                    int carryH = 0, carryF = 0;
+                    for (int j0 = beg; j0 <= end; j0 += 32) {
+                        const int j = j0 + (int)lane;
+                        const bool valid = j <= end;
+                        const int u = j - xi + 1, up = j - xim + 1, dg = j - xim;
+                        int hbu = 0, ebu = 0, hbd = 0, tj = 0;
+                        if (valid) { hbu = hb[up]; ebu = eb[up]; hbd = hb[dg]; tj = tc[j]; }
+                        __syncwarp();
+                        int t1 = (i == 0) ? -go : hbu - go;
+                        int t2 = (i == 0) ? -ge : ebu - ge;
+                        const int e = t1 > t2 ? t1 : t2;
+                        const int de = t1 > t2 ? 3 : 2;
+                        const int e1 = e > 0 ? e : 0;
+                        const int diagv = hbd + (int)mrow[tj] + cbv;
+                        const int h0 = e1 > diagv ? e1 : diagv;
+                        // horizontal gap chain F_j = max(H_{j-1} - go, F_{j-1} - ge) as a decayed max-scan
+                        int y = valid ? h0 - go : TB_NEG;
 #pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const int o = __shfl_up_sync(0xffffffffu, y, d);
-                        if (lane >= (uint32_t)d) y = max(y, o - d * ge);
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const int o = __shfl_up_sync(0xffffffffu, y, d);
+                            if (lane >= (uint32_t)d) y = max(y, o - d * ge);
+                        }
+                        const int yPrev = __shfl_up_sync(0xffffffffu, y, 1);
+                        const int f0 = max(carryH - go, carryF - ge);
+                        const int f = (lane == 0) ? f0 : max(yPrev, f0 - (int)lane * ge);
+                        const int f1 = f > 0 ? f : 0;
+                        const int g1 = e1 > f1 ? e1 : f1;
+                        const int h = g1 > diagv ? g1 : diagv;
+                        int hPrev = __shfl_up_sync(0xffffffffu, h, 1);
+                        int fPrev = __shfl_up_sync(0xffffffffu, f, 1);
+                        if (lane == 0) { hPrev = carryH; fPrev = carryF; }
+                        const int df = (hPrev - go > fPrev - ge) ? 5 : 4;
+                        const int dh = (g1 <= diagv) ? 1 : (e1 > f1 ? de : df);
+                        if (valid) {
+                            eb[u] = e;
+                            hc[u] = h;
+                            line[j - xi] = (int8_t)((de == 3 ? 1 : 0) | (df == 5 ? 2 : 0) | (dh << 2));
+                            maxH = max(maxH, h);
+                        }
+                        const int lastLane = min(31, end - j0);
+                        carryH = __shfl_sync(0xffffffffu, h, lastLane);
+                        carryF = __shfl_sync(0xffffffffu, f, lastLane);
+                        __syncwarp();
                     }
-                    const int yPrev = __shfl_up_sync(0xffffffffu, y, 1);
-                    const int f0 = max(carryH - go, carryF - ge);
-                    const int f = (lane == 0) ? f0 : max(yPrev, f0 - (int)lane * ge);
-                    const int f1 = f > 0 ? f : 0;
-                    const int g1 = e1 > f1 ? e1 : f1;
-                    const int h = g1 > diagv ? g1 : diagv;
-                    int hPrev = __shfl_up_sync(0xffffffffu, h, 1);
-                    int fPrev = __shfl_up_sync(0xffffffffu, f, 1);
-                    if (lane == 0) { hPrev = carryH; fPrev = carryF; }
-                    const int8_t df = (hPrev - go > fPrev - ge) ? 5 : 4;
-                    const int8_t dh = (g1 <= diagv) ? 1 : (e1 > f1 ? de : df);
-                    if (valid) {
-                        eb[u] = e;
-                        hc[u] = h;
-                        int8_t *cell = line + (long)(j - xi) * 3;
-                        cell[0] = de; cell[1] = df; cell[2] = dh;
-                        maxH = max(maxH, h);
-                    }
-                    const int lastLane = min(31, end - j0);
-                    carryH = __shfl_sync(0xffffffffu, h, lastLane);
-                    carryF = __shfl_sync(0xffffffffu, f, lastLane);
+                    const int uMax = end - xi + 1;
+                    for (int u = 1 + (int)lane; u <= uMax; u += 32) hb[u] = hc[u];
                     __syncwarp();
+                    cells += (lane == 0) ? (unsigned long long)(end - beg + 1) : 0ull;
                 }
-                const int uMax = end - xi + 1;
-                for (int u = 1 + (int)lane; u <= uMax; u += 32) hb[u] = hc[u];
-                __syncwarp();
-                cells += (lane == 0) ? (unsigned long long)(end - beg + 1) : 0ull;
-            }
-            int m = maxH;
+                int m = maxH;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-            maxH = m;
-            if (maxH >= tk.score) break;
-            band *= 2;
-            if (band > 4 * (qLen + dbLen) + 8) { status = 2; break; }
-        }
-        int n = 0, ids = 0;
-        if (status == 0) {
-            if (lane == 0) {
-                int i = qLen - 1, j = dbLen - 1, state = 2;
-                while (i > 0 || j > 0) {
-                    if (i < 0 || j < 0) { status = 2; break; }
-                    const int xi = max(i - band, 0);
-                    const long x = j - xi;
-                    if (x < 0 || x >= widthD) { status = 2; break; }
-                    const int8_t d = dir[widthD * (long)i * 3 + x * 3 + state];
-                    char op;
-                    if (d == 1) { ids += (qc[i] == tc[j]); --i; --j; state = 2; op = 'M'; }
-                    else if (d == 2) { --i; state = 0; op = 'I'; }
-                    else if (d == 3) { --i; state = 2; op = 'I'; }
-                    else if (d == 4) { --j; state = 1; op = 'D'; }
-                    else if (d == 5) { --j; state = 2; op = 'D'; }
-                    else { status = 2; break; }
-                    if ((uint32_t)n + 2 > A.revCap) { status = 2; break; }
-                    rev[n++] = op;
+                for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+                maxH = m;
+                if (maxH >= tk.score) break;
+                band *= 2;
+                if (band > 4 * (qLen + dbLen) + 8) { status = 2; break; }
+            }
+            if (status == 3) { carry = ti; break; }
+            if (status != 0) {
+                if (lane == 0) {
+                    TbResult r;
+                    r.btLen = 0; r.ids = 0; r.status = status; r.band = band; r.cigLen = 0; r.cigStart = 0;
+                    A.results[id] = r;
+                    A.cigLen[id] = 0;
                 }
-                if (status == 0) { ids += (qc[0] == tc[0]); rev[n++] = 'M'; }
+                continue;
             }
-            n = __shfl_sync(0xffffffffu, n, 0);
-            status = __shfl_sync(0xffffffffu, status, 0);
-            __syncwarp();
-            if (status == 0) {
-                char *out = A.btPool + tk.btOff;
-                for (int k = (int)lane; k < n; k += 32) out[k] = rev[n - 1 - k];
-            }
+            if (lane == 0) { sId[wIn][nb] = id; sBase[wIn][nb] = (uint32_t)used; sBand[wIn][nb] = band; }
+            used += (need + 15) & ~(uint64_t)15;
+            nb++;
         }
-        if (lane == 0) {
+        __syncwarp();
+        __threadfence_block();
+        if (nb == 0) {
+            if (drained && carry == 0xffffffffu) break;
+            continue;
+        }
+        // ---------------- walk: lane l follows the path of the batch's l-th alignment, CIGAR written right to left
+        if ((int)lane < nb) {
+            const uint32_t id = sId[wIn][lane];
+            const TbTask tk = A.tasks[id];
+            const int band = sBand[wIn][lane];
+            const long widthD = (long)band * 2 + 1;
+            const int8_t *d = dir + sBase[wIn][lane];
+            const int qLen = tk.qEnd - tk.qStart + 1, dbLen = tk.tEnd - tk.tStart + 1;
+            const uint8_t *qc = A.qCode + A.qOff[tk.q] + tk.qStart;
+            const uint8_t *tc = A.tRes + A.tOff[tk.t] + tk.tStart;
+            const uint32_t slot = tbSlotBytes(tk);
+            char *slotEnd = A.btPool + tk.btOff + slot;
+            int i = qLen - 1, j = dbLen - 1, state = 2, n = 0, ids = 0, status = 0;
+            uint32_t pos = 0, run = 0;
+            char cur = 0;
+            auto flush = [&]() {
+                if (!run) return;
+                slotEnd[-1 - (long)pos++] = cur;
+                uint32_t r = run;
+                do { slotEnd[-1 - (long)pos++] = (char)('0' + r % 10u); r /= 10u; } while (r);
+            };
+            auto emit = [&](char op) {
+                if (op == cur) run++;
+                else { flush(); cur = op; run = 1; }
+                n++;
+            };
+            while (i > 0 || j > 0) {
+                if (i < 0 || j < 0) { status = 2; break; }
+                const int xi = max(i - band, 0);
+                const long x = j - xi;
+                if (x < 0 || x >= widthD) { status = 2; break; }
+                const int c = (int)(uint8_t)d[widthD * (long)i + x];
+                const int dd = state == 0 ? ((c & 1) ? 3 : 2) : (state == 1 ? ((c & 2) ? 5 : 4) : (c >> 2));
+                if (dd == 1) { ids += (qc[i] == tc[j]); --i; --j; state = 2; emit('M'); }
+                else if (dd == 2) { --i; state = 0; emit('I'); }
+                else if (dd == 3) { --i; state = 2; emit('I'); }
+                else if (dd == 4) { --j; state = 1; emit('D'); }
+                else if (dd == 5) { --j; state = 2; emit('D'); }
+                else { status = 2; break; }
+                // (text <= 2 bytes per operation and every operation lowers i or j: the slot of 2*(rows+columns)+2 cannot overflow)
+            }
+            if (status == 0) { ids += (qc[0] == tc[0]); emit('M'); flush(); }
             TbResult r;
-            r.btLen = n; r.ids = ids; r.status = status; r.band = band;
+            r.btLen = n; r.ids = ids; r.status = status; r.band = band; r.cigLen = status == 0 ? pos : 0u; r.cigStart = slot - pos;
             A.results[id] = r;
+            A.cigLen[id] = r.cigLen;
         }
         __syncwarp();
     }
     if (lane == 0 && cells) atomicAdd(A.cells, cells);
 }
+
+// dense CIGAR pool: one warp copies one alignment's text from its slot to its scanned offset
+__global__ void gatherCigars(const TbTask *tasks, const TbResult *res, const unsigned long long *denseOff, uint32_t n, const char *pool, char *dense) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const TbResult r = res[w];
+    const char *src = pool + tasks[w].btOff + r.cigStart;
+    char *dst = dense + denseOff[w];
+    for (uint32_t k = lane; k < r.cigLen; k += 32) dst[k] = src[k];
+}
+
+struct U32ToU64 {
+    __host__ __device__ unsigned long long operator()(uint32_t v) const { return (unsigned long long)v; }
+};
 
 // ------------------------------------------------------------------------------------------------
 // host helpers
@@ -412,7 +491,7 @@ __global__ void chainAfterReverse(ChainArgs A, const SwTask *tasks, const SwResu
     ph.stage = 2;
     TbTask tb;
     tb.q = ph.q; tb.t = ph.t; tb.qStart = ph.qStart; tb.qEnd = ph.qEnd; tb.tStart = ph.tStart; tb.tEnd = ph.tEnd; tb.score = ph.score; tb.pad = (uint32_t)tk.pad;
-    tb.btOff = atomicAdd(A.poolCursor, (unsigned long long)((ph.qEnd - ph.qStart + 1) + (ph.tEnd - ph.tStart + 1) + 2));
+    tb.btOff = atomicAdd(A.poolCursor, (unsigned long long)tbSlotBytes(tb));
     const uint32_t ti = atomicAdd(A.nTb, 1u);
     ph.tb = ti;
     A.tbTasks[ti] = tb;
@@ -674,20 +753,22 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     }
     const uint64_t poolNeed = hCounters[2];
 
-    // ---- banded traceback on the survivors
+    // ---- banded traceback on the survivors: CIGAR strings, compacted on the device, one copy to the host
     std::vector<TbResult> tres(nTb);
-    char *devPool = static_cast<char *>(ctxPinnedScratch(ctx, 0, poolNeed + 1));
-    if (!devPool) return SD_ENOMEM;
+    std::vector<unsigned long long> cigOff(nTb + 1, 0);
+    char *devPool = nullptr;
     if (nTb) {
-        ScratchBuf<char> dPool(ctx, SL_TB_POOL), dRev2(ctx, SL_TB_REV);
+        ScratchBuf<char> dPool(ctx, SL_TB_POOL), dDense(ctx, SL_TB_REV);
         ScratchBuf<int8_t> dDir(ctx, SL_TB_DIR);
         ScratchBuf<int> dRows(ctx, SL_TB_ROWS);
-        DevBuf<uint32_t> dPend;
-        if ((rc = dTbRes.alloc(nTb)) || (rc = dPool.alloc(poolNeed + 1))) return rc;
+        DevBuf<uint32_t> dPend, dCigLen;
+        DevBuf<unsigned long long> dCigOff;
+        if ((rc = dTbRes.alloc(nTb)) || (rc = dPool.alloc(poolNeed + 1)) || (rc = dCigLen.alloc(nTb + 1)) || (rc = dCigOff.alloc(nTb + 1))) return rc;
+        SD_CUDA(cudaMemsetAsync(dCigLen.p, 0, ((size_t)nTb + 1) * sizeof(uint32_t), st));
         const uint32_t maxL = std::max(maxQ, idx->maxLen);
         TbArgs A;
         A.qCode = queries->code.p; A.qCb = dCb.p; A.qOff = queries->off.p; A.tRes = idx->raw.p; A.tOff = idx->off.p; A.mat = dMat8.p;
-        A.gapOpen = par->gap_open; A.gapExtend = par->gap_extend; A.tasks = dTb.p; A.results = dTbRes.p; A.next = dNext.p;
+        A.gapOpen = par->gap_open; A.gapExtend = par->gap_extend; A.tasks = dTb.p; A.results = dTbRes.p; A.cigLen = dCigLen.p; A.next = dNext.p;
         A.btPool = dPool.p; A.cells = dCells.p + 2;
         std::vector<uint32_t> pending;
         for (int pass = 0; pass < 2; pass++) {
@@ -697,18 +778,19 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
             uint64_t dirCap;
             uint32_t rowCap;
             if (pass == 0) {
-                nWarps = std::min<uint32_t>((uint32_t)ctx->smCount * 4u * TB_WARPS, nTasks);
+                nWarps = std::min<uint32_t>((uint32_t)ctx->smCount * 4u * TB_WARPS, (nTasks + 7) / 8);
+                nWarps = std::max<uint32_t>(nWarps, 1);
                 dirCap = 1ull << 20;
                 rowCap = 4096;
             } else {
                 nWarps = std::min<uint32_t>(64u, nTasks);
                 const uint64_t worstBand = 4ull * maxL + 8ull;
-                dirCap = std::min<uint64_t>((2 * worstBand + 1) * (uint64_t)maxL * 3ull, 1ull << 30);
+                dirCap = std::min<uint64_t>((2 * worstBand + 1) * (uint64_t)maxL, 1ull << 30);
                 rowCap = (uint32_t)std::min<uint64_t>(2 * worstBand + 8, 1u << 20);
             }
             nWarps = ((nWarps + TB_WARPS - 1) / TB_WARPS) * TB_WARPS;
-            if ((rc = dDir.alloc((size_t)nWarps * dirCap)) || (rc = dRows.alloc((size_t)nWarps * 3 * rowCap)) || (rc = dRev2.alloc((size_t)nWarps * (2 * maxL + 8)))) return rc;
-            A.dir = dDir.p; A.dirCap = dirCap; A.rows = dRows.p; A.rowCap = rowCap; A.rev = dRev2.p; A.revCap = 2 * maxL + 8;
+            if ((rc = dDir.alloc((size_t)nWarps * dirCap)) || (rc = dRows.alloc((size_t)nWarps * 3 * rowCap))) return rc;
+            A.dir = dDir.p; A.dirCap = dirCap; A.rows = dRows.p; A.rowCap = rowCap;
             A.nTasks = nTasks;
             if (pass == 0) A.order = nullptr;
             else {
@@ -730,10 +812,28 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
                 if (tres[i].status == 1) pending.push_back(i);
             if (pass == 1 && !pending.empty()) { setError("sd_align_run: %zu tracebacks exceed the scratch limit", pending.size()); return SD_ELIMIT; }
         }
-        SD_CUDA(cudaMemcpyAsync(devPool, dPool.p, poolNeed, cudaMemcpyDeviceToHost, st));
-        SD_CUDA(cudaStreamSynchronize(st));
         for (uint32_t i = 0; i < nTb; i++)
             if (tres[i].status != 0) { setError("sd_align_run: a traceback left the band (inconsistent start/end)"); return SD_ELIMIT; }
+        // dense pool: offsets = exclusive scan of the text lengths, one gather, one device->host copy
+        {
+            cub::TransformInputIterator<unsigned long long, U32ToU64, const uint32_t *> lenIt(dCigLen.p, U32ToU64());
+            size_t tmpBytes = 0;
+            SD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, lenIt, dCigOff.p, (int64_t)nTb + 1, st));
+            DevBuf<uint8_t> tmp;
+            if ((rc = tmp.alloc(tmpBytes))) return rc;
+            SD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, lenIt, dCigOff.p, (int64_t)nTb + 1, st));
+            SD_CUDA(cudaMemcpyAsync(cigOff.data(), dCigOff.p, ((size_t)nTb + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            SD_CUDA(cudaStreamSynchronize(st));
+            const unsigned long long denseBytes = cigOff[nTb];
+            if ((rc = dDense.alloc(denseBytes + 1))) return rc;
+            devPool = static_cast<char *>(ctxPinnedScratch(ctx, 0, denseBytes + 1));
+            if (!devPool) return SD_ENOMEM;
+            gatherCigars<<<gridOf((uint64_t)nTb * 32, 256), 256, 0, st>>>(dTb.p, dTbRes.p, dCigOff.p, nTb, dPool.p, dDense.p);
+            ctx->launches++;
+            SD_CUDA(cudaGetLastError());
+            SD_CUDA(cudaMemcpyAsync(devPool, dDense.p, denseBytes, cudaMemcpyDeviceToHost, st));
+            SD_CUDA(cudaStreamSynchronize(st));
+        }
     }
     tick("traceback");
     // ---- survivors and identity pairs to the host: E-values, criteria, order
@@ -760,9 +860,9 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
         a.tcov = covOf((unsigned)h.tStart, (unsigned)h.tEnd, (unsigned)a.t_len);
         a.aln_len = tr.btLen;
         a.seq_id = (float)tr.ids / (float)tr.btLen;
-        a.bt_len = (uint32_t)tr.btLen;
+        a.bt_len = tr.cigLen;           // the pool holds the run-length CIGAR text
         a.bt_off = 0;
-        a.pad = h.tb;                   // remember the task: its backtrace is fetched below
+        a.bt_cigar = h.tb;              // remember the task: its text is fetched below
         a.evalue = evaluer.evalue(a.score, a.q_len);
         a.bits = evaluer.bitScore(a.score);
         // checkCriteria (Alignment.cpp:548-567)
@@ -784,7 +884,9 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
         memset(&a, 0, sizeof a);
         a.query = q; a.target = t; a.score = sc; a.evalue = evaluer.evalue(sc, Lq); a.bits = evaluer.bitScore(sc);
         a.q_start = 0; a.t_start = 0; a.q_end = Lt - 1; a.t_end = Lt - 1; a.q_len = Lq; a.t_len = Lt;
-        a.qcov = 1.0f; a.tcov = 1.0f; a.seq_id = 1.0f; a.aln_len = Lt; a.bt_len = (uint32_t)Lt; a.pad = 0xffffffffu;
+        a.qcov = 1.0f; a.tcov = 1.0f; a.seq_id = 1.0f; a.aln_len = Lt; a.bt_cigar = 0xffffffffu;
+        char tmpCig[16];
+        a.bt_len = (uint32_t)snprintf(tmpCig, sizeof tmpCig, "%dM", Lt);
         ident[i] = a;
     });
     // bucket by query (counting sort), then order every query's list with Matcher::compareHits in parallel
@@ -811,19 +913,16 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     for (const sd_alignment &a : acc) poolBytes += a.bt_len;
     pool.resize(poolBytes);
     {
-        // task offsets in the device pool
-        std::vector<TbTask> hTb(nTb);
-        if (nTb) {
-            SD_CUDA(cudaMemcpyAsync(hTb.data(), dTb.p, (size_t)nTb * sizeof(TbTask), cudaMemcpyDeviceToHost, st));
-            SD_CUDA(cudaStreamSynchronize(st));
-        }
         uint64_t w = 0;
         for (sd_alignment &a : acc) { a.bt_off = w; w += a.bt_len; }
         parallelFor(acc.size(), [&](uint64_t i) {
             sd_alignment &a = acc[i];
-            if (a.pad == 0xffffffffu) memset(pool.data() + a.bt_off, 'M', a.bt_len);
-            else memcpy(pool.data() + a.bt_off, devPool + hTb[a.pad].btOff, a.bt_len);
-            a.pad = 0;
+            if (a.bt_cigar == 0xffffffffu) {          // identity shortcut: one run of matches
+                char tmpCig[16];
+                const int n = snprintf(tmpCig, sizeof tmpCig, "%dM", a.aln_len);
+                memcpy(pool.data() + a.bt_off, tmpCig, (size_t)n);
+            } else memcpy(pool.data() + a.bt_off, devPool + cigOff[a.bt_cigar], a.bt_len);
+            a.bt_cigar = 1;
         });
     }
     tick("pool");
@@ -908,8 +1007,16 @@ extern "C" int sd_format_alignment(const sd_alignment *a, uint32_t target_key, c
     }
     n += snprintf(buf + n, (size_t)(cap - n), "\t%.3E\t%d\t%d\t%d\t%d\t%d\t%d\t", a->evalue, a->q_start, a->q_end, a->q_len,
                   a->t_start, a->t_end, a->t_len);
-    // Matcher::compressAlignment (Matcher.cpp:166-185)
     const char *bt = bt_pool + a->bt_off;
+    if (a->bt_cigar) {            // already run-length encoded on the device
+        if (n + (int)a->bt_len + 2 > cap) return 0;
+        memcpy(buf + n, bt, a->bt_len);
+        n += (int)a->bt_len;
+        buf[n++] = '\n';
+        buf[n] = '\0';
+        return n;
+    }
+    // Matcher::compressAlignment (Matcher.cpp:166-185)
     char state = 'M';
     unsigned count = 0;
     for (uint32_t i = 0; i < a->bt_len; i++) {

@@ -1,4 +1,6 @@
 """GPU parity: CUDA align stage (Smith-Waterman passes + banded traceback, through the C ABI) vs the oracle."""
+import itertools
+
 import numpy as np
 import pytest
 
@@ -38,10 +40,13 @@ def _compare(gpu_ctx, tbuf, toff, qbuf, qoff, pq, pt, same_db, **kw):
                    ("qEnd", "q_end"), ("tStart", "t_start"), ("tEnd", "t_end"), ("alnLen", "aln_len"), ("qLen", "q_len"),
                    ("tLen", "t_len"), ("seqId", "seq_id"), ("evalue", "evalue"), ("qcov", "qcov"), ("tcov", "tcov")):
         assert np.array_equal(oal[fo], gal[fg]), "field %s differs" % fo
+    # the library returns the backtrace run-length encoded (CIGAR text, Matcher::compressAlignment done on the device)
+    assert np.all(gal["bt_cigar"] == 1)
     for i in range(len(oal)):
-        a = bytes(obt[int(oal[i]["btOff"]):int(oal[i]["btOff"]) + int(oal[i]["btLen"])])
-        b = bytes(gbt[int(gal[i]["bt_off"]):int(gal[i]["bt_off"]) + int(gal[i]["bt_len"])])
-        assert a == b, "backtrace %d differs" % i
+        raw = bytes(obt[int(oal[i]["btOff"]):int(oal[i]["btOff"]) + int(oal[i]["btLen"])]).decode()
+        cigar = "".join("%d%s" % (len(list(g)), k) for k, g in itertools.groupby(raw))
+        b = bytes(gbt[int(gal[i]["bt_off"]):int(gal[i]["bt_off"]) + int(gal[i]["bt_len"])]).decode()
+        assert cigar == b, "backtrace %d differs" % i
     # the text lines are what the reference writes to the result DB
     omine = helpers.format_alignments(oal, obt, qkeys)
     for i in range(min(len(gal), 50)):

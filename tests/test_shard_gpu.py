@@ -44,7 +44,7 @@ def _worker(rank, world, port, tmpdir):
             merged2 = shard.merge_results(ex.exchange(q_lo))
         for k in ("alns", "clusters", "members"):
             for f in merged[k].dtype.names:
-                if f != "pad":
+                if True:
                     assert np.array_equal(merged[k][f], merged2[k][f]), (k, f)
         assert np.array_equal(merged["pool"], merged2["pool"])
         np.savez(os.path.join(tmpdir, "merged_%d.npz" % rank), **merged)
@@ -73,6 +73,6 @@ def test_two_ranks_equal_one(tmp_path):
         for k in ("alns", "clusters", "members"):
             assert len(m[k]) == len(whole[k]), k
             for f in whole[k].dtype.names:
-                if f != "pad":
+                if True:
                     assert np.array_equal(m[k][f], whole[k][f]), (k, f)
         assert np.array_equal(m["pool"], whole["pool"])
