@@ -80,7 +80,7 @@ constexpr int TB_NEG = -(1 << 28);
 
 __device__ __forceinline__ uint32_t tbSlotBytes(const TbTask &tk) { return 2u * (uint32_t)((tk.qEnd - tk.qStart + 1) + (tk.tEnd - tk.tStart + 1)) + 2u; }
 
-__global__ void __launch_bounds__(TB_WARPS * 32) tracebackKernel(TbArgs A) {
+__global__ void __launch_bounds__(TB_WARPS * 32, 8) tracebackKernel(TbArgs A) {
     __shared__ int8_t sMat[AA * AA];
     __shared__ int sRows[TB_WARPS][3 * TB_SROW];
     __shared__ uint32_t sId[TB_WARPS][TB_BATCH];
@@ -522,6 +522,9 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     SD_CUDA(cudaSetDevice(ctx->device));
     sd::StreamScope allocScope(ctx->stream);
     cudaStream_t st = ctx->stream;
+    // chunked clustersearch: hold the GPU token from here to the end of the traceback (released for the host tail)
+    std::unique_lock<std::mutex> gpuTurn;
+    if (ctx->gpuToken) gpuTurn = std::unique_lock<std::mutex>(*ctx->gpuToken);
     int rc;
     cudaEvent_t ev0, ev1, evA, evB;
     SD_CUDA(cudaEventCreate(&ev0)); SD_CUDA(cudaEventCreate(&ev1)); SD_CUDA(cudaEventCreate(&evA)); SD_CUDA(cudaEventCreate(&evB));
@@ -778,7 +781,7 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
             uint64_t dirCap;
             uint32_t rowCap;
             if (pass == 0) {
-                nWarps = std::min<uint32_t>((uint32_t)ctx->smCount * 4u * TB_WARPS, (nTasks + 7) / 8);
+                nWarps = std::min<uint32_t>((uint32_t)ctx->smCount * 8u * TB_WARPS, (nTasks + 7) / 8);     // 8 CTAs per SM: the row loop is latency bound
                 nWarps = std::max<uint32_t>(nWarps, 1);
                 dirCap = 1ull << 20;
                 rowCap = 4096;
@@ -836,6 +839,7 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
         }
     }
     tick("traceback");
+    if (gpuTurn.owns_lock()) gpuTurn.unlock();
     // ---- survivors and identity pairs to the host: E-values, criteria, order
     std::vector<PairHit> hHits(nHit);
     std::vector<uint32_t> hIdent(nIdent);

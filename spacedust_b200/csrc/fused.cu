@@ -1,16 +1,35 @@
 // Fused `clustersearch` hot path: prefilter -> align -> besthitbyset/combinehits -> clusterhits in one call, the
 // prefilter hit list never leaves HBM (data/clustersearch.sh:112-146 runs these as separate processes that exchange
 // flat-file DBs; this is the same chain with the DBs kept on the device).
+//
+// After the prefilter the query batch is cut into chunks of whole query SETS (every stage after the prefilter is
+// independent per query set: alignments per pair, besthitbyset per gene and target set, combinehits / clusterhits per
+// (query set, target set)).  Two host threads, each with its own context (stream + scratch), take the chunks in turn; a
+// token serialises the GPU-heavy part of the align stage, so one chunk's host post-processing (E-values, sorting,
+// aggregation, clustering bookkeeping) runs under the other chunk's Smith-Waterman kernels.
 #include <cstring>
 #include <memory>
+#include <mutex>
 
 #include "sd_internal.h"
 
-struct sd_search_result {
+namespace {
+
+struct ChunkResult {
     std::vector<sd_alignment> alns;
     sd::CharPool pool;
     std::vector<sd_cluster> clusters;
     std::vector<sd_cluster_member> members;
+    sd_align_stats ast;
+    sd_cluster_stats cst;
+    int rc = SD_OK;
+    std::string err;
+};
+
+}  // namespace
+
+struct sd_search_result {
+    std::vector<ChunkResult> chunks;     // ascending query sets
 };
 
 extern "C" int sd_clustersearch_run(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
@@ -20,42 +39,147 @@ extern "C" int sd_clustersearch_run(sd_context *ctx, const sd_target_index *idx,
                                     const uint32_t *q_set_size, uint32_t n_q_sets, const uint32_t *t_set_size, uint32_t n_t_sets,
                                     uint64_t db_residues, sd_search_result **out, sd_prefilter_stats *pst, sd_align_stats *ast,
                                     sd_cluster_stats *cst) {
-    if (!ctx || !idx || !queries || !ppar || !apar || !cpar || !out) { sd::setError("sd_clustersearch_run: bad argument"); return SD_EINVAL; }
+    if (!ctx || !idx || !queries || !ppar || !apar || !cpar || !out || !q_set_of) { sd::setError("sd_clustersearch_run: bad argument"); return SD_EINVAL; }
     *out = nullptr;
+    if (ast) memset(ast, 0, sizeof *ast);
+    if (cst) memset(cst, 0, sizeof *cst);
     std::unique_ptr<sd_search_result> r(new sd_search_result());
     sd::DevBuf<sd_prefilter_hit> dHits;
     uint64_t nHits = 0;
-    int rc = sd_prefilter_core(ctx, idx, queries, query_first, ppar, nullptr, 0, &nHits, pst, &dHits);
+    std::vector<uint64_t> hitOff;
+    int rc = sd_prefilter_core(ctx, idx, queries, query_first, ppar, nullptr, 0, &nHits, pst, &dHits, &hitOff);
     if (rc) return rc;
-    rc = sd_align_device_hits(ctx, idx, queries, query_first, dHits.p, nHits, db_residues, apar, r->alns, r->pool, ast);
-    if (rc) return rc;
+    SD_CUDA(cudaStreamSynchronize(ctx->stream));      // the hit list is read from the helper context's stream too
+    const uint32_t nq = queries->nq;
+
+    // ---- chunks of whole query sets, about equal numbers of (query, target) pairs
+    std::vector<uint32_t> cut;        // query index where a chunk starts; last = nq
+    {
+        bool contiguous = true;
+        std::vector<uint32_t> setStart;                     // first query of every run of equal set ids
+        for (uint32_t q = 0; q < nq; q++)
+            if (q == 0 || q_set_of[q] != q_set_of[q - 1]) {
+                if (q > 0 && q_set_of[q] < q_set_of[q - 1]) contiguous = false;   // sets must come in ascending blocks
+                setStart.push_back(q);
+            }
+        const int envChunks = getenv("SD_CHUNKS") ? atoi(getenv("SD_CHUNKS")) : 0;      // test / tuning hook
+        uint64_t want = envChunks > 0 ? (uint64_t)envChunks : std::max<uint64_t>(4, (nHits + (20ull << 20) - 1) / (20ull << 20));
+        if (!contiguous || setStart.size() < 2 || (envChunks <= 0 && nHits < 4096)) want = 1;
+        want = std::min<uint64_t>(want, setStart.size());
+        cut.push_back(0);
+        for (uint64_t c = 1; c < want; c++) {
+            const uint64_t target = nHits * c / want;
+            // first set boundary whose hit offset reaches the target
+            uint32_t best = nq;
+            for (uint32_t sIdx = 0; sIdx < setStart.size(); sIdx++)
+                if (hitOff[setStart[sIdx]] >= target) { best = setStart[sIdx]; break; }
+            if (best > cut.back() && best < nq) cut.push_back(best);
+        }
+        cut.push_back(nq);
+    }
+    const size_t nChunks = cut.size() - 1;
+    r->chunks.resize(nChunks);
+
+    // ---- helper context for the second thread (created once, kept with the context)
+    const bool twoThreads = nChunks > 1;
+    if (twoThreads && !ctx->helper) {
+        sd_context *h = nullptr;
+        if ((rc = sd_context_create(ctx->device, &h))) return rc;
+        ctx->helper = h;
+    }
+    std::mutex token;
+    std::atomic<size_t> nextChunk{0};
+    auto worker = [&](sd_context *c) {
+        cudaSetDevice(c->device);
+        for (;;) {
+            const size_t k = nextChunk.fetch_add(1);
+            if (k >= nChunks) break;
+            ChunkResult &cr = r->chunks[k];
+            memset(&cr.ast, 0, sizeof cr.ast);
+            memset(&cr.cst, 0, sizeof cr.cst);
+            const uint64_t lo = hitOff[cut[k]], hi = hitOff[cut[k + 1]];
+            int rc2 = sd_align_device_hits(c, idx, queries, query_first, dHits.p + lo, hi - lo, db_residues, apar, cr.alns, cr.pool, &cr.ast);
+            if (rc2 == SD_OK) {
+                uint64_t nC = 0, nM = 0;
+                cr.clusters.resize(cr.alns.size() / 2 + 1);
+                cr.members.resize(cr.alns.size() + 1);
+                rc2 = sd_cluster_run(c, cr.alns.data(), cr.alns.size(), q_set_of, q_pos, q_strand, nq, t_set_of, t_pos, t_strand, nt,
+                                     q_set_size, n_q_sets, t_set_size, n_t_sets, cpar, cr.clusters.data(), cr.clusters.size(), &nC,
+                                     cr.members.data(), cr.members.size(), &nM, &cr.cst);
+                if (rc2 == SD_OK) { cr.clusters.resize(nC); cr.members.resize(nM); }
+            }
+            if (rc2 != SD_OK) { cr.rc = rc2; cr.err = sd_last_error(); nextChunk.store(nChunks); break; }
+        }
+    };
+    if (twoThreads) {
+        ctx->gpuToken = &token;
+        ctx->helper->gpuToken = &token;
+        const uint64_t l0 = ctx->helper->launches;
+        std::thread t(worker, ctx->helper);
+        worker(ctx);
+        t.join();
+        ctx->launches += ctx->helper->launches - l0;
+        ctx->gpuToken = nullptr;
+        ctx->helper->gpuToken = nullptr;
+    } else {
+        worker(ctx);
+    }
     dHits.release();
-    uint64_t nC = 0, nM = 0;
-    r->clusters.resize(r->alns.size() / 2 + 1);
-    r->members.resize(r->alns.size() + 1);
-    rc = sd_cluster_run(ctx, r->alns.data(), r->alns.size(), q_set_of, q_pos, q_strand, queries->nq, t_set_of, t_pos, t_strand, nt,
-                        q_set_size, n_q_sets, t_set_size, n_t_sets, cpar, r->clusters.data(), r->clusters.size(), &nC,
-                        r->members.data(), r->members.size(), &nM, cst);
-    if (rc) return rc;
-    r->clusters.resize(nC);
-    r->members.resize(nM);
+    for (const ChunkResult &cr : r->chunks)
+        if (cr.rc != SD_OK) { sd::setError("%s", cr.err.c_str()); return cr.rc; }
+    // ---- statistics: sums over the chunks (stage times are device times per chunk; chunks overlap in wall-clock)
+    for (const ChunkResult &cr : r->chunks) {
+        if (ast) {
+            ast->alignments += cr.ast.alignments; ast->passed += cr.ast.passed; ast->word_mode += cr.ast.word_mode;
+            ast->reverse_passes += cr.ast.reverse_passes; ast->tracebacks += cr.ast.tracebacks;
+            ast->cells_forward += cr.ast.cells_forward; ast->cells_reverse += cr.ast.cells_reverse; ast->cells_traceback += cr.ast.cells_traceback;
+            ast->sw_ms += cr.ast.sw_ms; ast->traceback_ms += cr.ast.traceback_ms; ast->total_ms += cr.ast.total_ms;
+        }
+        if (cst) {
+            cst->best_hits += cr.cst.best_hits; cst->genome_pairs += cr.cst.genome_pairs; cst->pairs_clustered += cr.cst.pairs_clustered;
+            cst->max_hits_per_pair = std::max(cst->max_hits_per_pair, cr.cst.max_hits_per_pair);
+            cst->merges += cr.cst.merges; cst->inexact_log += cr.cst.inexact_log;
+            cst->kernel_ms += cr.cst.kernel_ms; cst->total_ms += cr.cst.total_ms;
+        }
+    }
     *out = r.release();
     return SD_OK;
 }
 
 extern "C" void sd_search_result_sizes(const sd_search_result *r, uint64_t *n_alns, uint64_t *pool_bytes, uint64_t *n_clusters, uint64_t *n_members) {
-    if (n_alns) *n_alns = r ? r->alns.size() : 0;
-    if (pool_bytes) *pool_bytes = r ? r->pool.size() : 0;
-    if (n_clusters) *n_clusters = r ? r->clusters.size() : 0;
-    if (n_members) *n_members = r ? r->members.size() : 0;
+    uint64_t a = 0, p = 0, c = 0, m = 0;
+    if (r)
+        for (const ChunkResult &cr : r->chunks) { a += cr.alns.size(); p += cr.pool.size(); c += cr.clusters.size(); m += cr.members.size(); }
+    if (n_alns) *n_alns = a;
+    if (pool_bytes) *pool_bytes = p;
+    if (n_clusters) *n_clusters = c;
+    if (n_members) *n_members = m;
 }
 
+// Chunk results are concatenated in chunk (= ascending query set) order; the cross references are rebased on the way:
+// alignment.bt_off -> pool, member.aln -> alignment array, cluster.first -> member array.
 extern "C" int sd_search_result_copy(const sd_search_result *r, sd_alignment *alns, char *pool, sd_cluster *clusters, sd_cluster_member *members) {
     if (!r) { sd::setError("sd_search_result_copy: null result"); return SD_EINVAL; }
-    if (alns && !r->alns.empty()) memcpy(alns, r->alns.data(), r->alns.size() * sizeof(sd_alignment));
-    if (pool && !r->pool.empty()) memcpy(pool, r->pool.data(), r->pool.size());
-    if (clusters && !r->clusters.empty()) memcpy(clusters, r->clusters.data(), r->clusters.size() * sizeof(sd_cluster));
-    if (members && !r->members.empty()) memcpy(members, r->members.data(), r->members.size() * sizeof(sd_cluster_member));
+    uint64_t a0 = 0, p0 = 0, c0 = 0, m0 = 0;
+    for (const ChunkResult &cr : r->chunks) {
+        const uint64_t na = cr.alns.size(), np = cr.pool.size(), nc = cr.clusters.size(), nm = cr.members.size();
+        if (alns && na) {
+            sd_alignment *dst = alns + a0;
+            const sd_alignment *src = cr.alns.data();
+            sd::parallelFor(na, [&](uint64_t i) { dst[i] = src[i]; dst[i].bt_off += p0; });
+        }
+        if (pool && np) memcpy(pool + p0, cr.pool.data(), np);
+        if (clusters && nc) {
+            sd_cluster *dst = clusters + c0;
+            for (uint64_t i = 0; i < nc; i++) { dst[i] = cr.clusters[i]; dst[i].first += (uint32_t)m0; }
+        }
+        if (members && nm) {
+            sd_cluster_member *dst = members + m0;
+            const sd_cluster_member *src = cr.members.data();
+            sd::parallelFor(nm, [&](uint64_t i) { dst[i] = src[i]; dst[i].aln += (uint32_t)a0; });
+        }
+        a0 += na; p0 += np; c0 += nc; m0 += nm;
+    }
     return SD_OK;
 }
 

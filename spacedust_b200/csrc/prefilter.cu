@@ -1090,7 +1090,8 @@ extern "C" int sd_prefilter_run(sd_context *ctx, const sd_target_index *idx, con
 // keepOnDevice != nullptr: the dense hit array stays in HBM (fused clustersearch path), nothing is copied to `hits`
 int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
                       const sd_prefilter_params *par, sd_prefilter_hit *hits, uint64_t cap, uint64_t *n_hits,
-                      sd_prefilter_stats *stats, sd::DevBuf<sd_prefilter_hit> *keepOnDevice) {
+                      sd_prefilter_stats *stats, sd::DevBuf<sd_prefilter_hit> *keepOnDevice, std::vector<uint64_t> *hitOffsets) {
+    if (hitOffsets) hitOffsets->assign((size_t)(queries ? queries->nq : 0) + 1, 0);
     if (!ctx || !idx || !queries || !par || !n_hits || (!hits && cap && !keepOnDevice)) { setError("sd_prefilter_run_batch: bad argument"); return SD_EINVAL; }
     *n_hits = 0;
     const uint32_t nq = queries->nq;
@@ -1249,6 +1250,8 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     if (hStats[ST_ERR_RESCORE]) { setError("prefilter: %llu queries need the reference's truncated-score rescaling path (>= max-seqs hits at score 255; first: query %u): not implemented", hStats[ST_ERR_RESCORE], hNext[1]); return SD_ELIMIT; }
     uint64_t totalHits = 0;
     for (uint32_t i = 0; i < nq; i++) totalHits += hCount[i];
+    if (hitOffsets)
+        for (uint32_t i = 0; i < nq; i++) (*hitOffsets)[i + 1] = (*hitOffsets)[i] + hCount[i];
     *n_hits = totalHits;
     if (!keepOnDevice && totalHits > cap) { setError("sd_prefilter_run: %llu hits, buffer holds %llu", (unsigned long long)totalHits, (unsigned long long)cap); return SD_ESMALL; }
     // gather the per-query slices (strided device layout -> dense) and copy once

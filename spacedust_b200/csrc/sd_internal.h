@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <utility>
@@ -205,6 +206,10 @@ struct sd_context {
     int smCount = 148;
     cudaStream_t stream = nullptr;
     uint64_t launches = 0;
+    // fused clustersearch: a second context (own stream + scratch) runs alternate query chunks on a helper thread; the token
+    // serialises the GPU-heavy part of the align stage so that one chunk's host post-processing overlaps the other's kernels
+    sd_context *helper = nullptr;
+    std::mutex *gpuToken = nullptr;
     // seed / diagonal matrices and the sorted 3-mer neighbour table are per context (device resident)
     sd::SubMat seedMat;       // VTML80 x8, bias -0.2   (Prefiltering.cpp:68)
     sd::SubMat diagMat;       // BLOSUM62 x2, bias -0.2 (Prefiltering.cpp:69)
@@ -230,7 +235,7 @@ struct sd_query_batch {
 
 int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
                       const sd_prefilter_params *par, sd_prefilter_hit *hits, uint64_t cap, uint64_t *n_hits,
-                      sd_prefilter_stats *stats, sd::DevBuf<sd_prefilter_hit> *keepOnDevice);
+                      sd_prefilter_stats *stats, sd::DevBuf<sd_prefilter_hit> *keepOnDevice, std::vector<uint64_t> *hitOffsets = nullptr);
 int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
                           const uint32_t *dPairQ, const uint32_t *dPairT, uint64_t n_pairs, uint64_t db_residues,
                           const sd_align_params *par, std::vector<sd_alignment> &acc, sd::CharPool &pool,

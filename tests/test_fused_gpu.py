@@ -10,7 +10,10 @@ from spacedust_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def test_fused_equals_staged_and_oracle(gpu_ctx, synth_small):
+@pytest.mark.parametrize("chunks", ["1", "3"])
+def test_fused_equals_staged_and_oracle(gpu_ctx, synth_small, monkeypatch, chunks):
+    """chunks=3: the fused call cuts the batch into query-set chunks processed by two host threads / contexts."""
+    monkeypatch.setenv("SD_CHUNKS", chunks)
     buf, off, _ = synth.pack(synth_small)
     meta = synth.set_metadata(synth_small)
     pp = sd.default_prefilter_params(same_db=1, bin_size=2)
