@@ -218,6 +218,7 @@ constexpr int SW_KEYMUL = 33;      // column-maximum key = H * 33 + (31 - k): no
 template <int LANES, int RP, bool KEYED, int SEGMODE>
 __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, unsigned long long &cellCount) {
     constexpr int NWA = (RP + 3) / 4;          // aligned words holding RP bytes
+    constexpr uint32_t BIAS = (SEGMODE != 0) ? 32u : 0u;     // see the note at biasP
     constexpr bool STRIPED = (LANES == 32);    // only whole-warp pairs may need more than one stripe
     const uint32_t lane = swLane();
     const uint32_t gl = lane % LANES, grp = lane / LANES;
@@ -238,10 +239,17 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
     const int lim = tk.limit != INT_MAX ? tk.limit : SW16_GUARD;
 
     int bestA = 0, bestB = 0, colA = INT_MAX, colB = INT_MAX, rowA = INT_MAX, rowB = INT_MAX;
-    int thrA = SW_KEYMUL, thrB = SW_KEYMUL;     // KEYED: smallest key that beats the current best score
+    int thrA = ((int)BIAS + 1) * SW_KEYMUL, thrB = thrA;     // KEYED: smallest key that beats the current best score
     bool overflow = false;
     int pingpong = 0;
     const uint32_t zero = A.zero;               // opaque 0 (see SwKernelArgs)
+    // SEGMODE != 0: all H/E/F values carry +BIAS in both halves.  The exact vertical chain is then not carried row by row:
+    // inside a segment that starts at row kb with the exact F value X, F_true(k) = max(F_seg(k), X - (k-kb)*ge), and
+    // X - d*ge for both halves is ONE 32-bit subtraction of a constant (the low half never borrows: X_lo >= BIAS > d), which
+    // ptxas can place on the FMA pipe (IMAD) instead of one more DPX instruction per cell on the saturated ALU pipe.
+    const uint32_t biasP = zero + BIAS * 0x10001u;
+    const uint32_t one = zero + 1u;             // opaque 1: X * one + c stays an IMAD (FMA pipe)
+    const uint32_t goP = (uint32_t)A.b.gapOpen * 0x10001u, geP = (uint32_t)A.b.gapExtend * 0x10001u;
     // every group runs the longest group's step count (shuffles are warp-wide)
     const int mySteps = have ? nCols + 2 * LANES - 1 : 0;
     const int warpSteps = (int)__reduce_max_sync(0xffffffffu, (unsigned)mySteps);
@@ -264,8 +272,8 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
                 segKeep[SEGMODE == 0 ? k : 0] = a | b;
             }
         }
-        // SEGMODE != 0 (forward 8-bit pass): staged profile, stage st starts at st * RPPAD on a 4-byte boundary
-        constexpr int RPPAD = (RP + 3) & ~3;
+        // SEGMODE != 0 (forward 8-bit pass): staged profile, stage st starts at st * RPPAD on a 16-byte boundary
+        constexpr int RPPAD = (RP + 15) & ~15;
         const uint32_t strideU = (SEGMODE != 0 && have) ? A.b.stgStride[tk.q] : stride;
         const uintptr_t addrA = (SEGMODE != 0) ? (uintptr_t)(A.b.profStg + (have ? A.b.stgOff[tk.q] : 0ull) + (uint32_t)(2 * gl) * RPPAD)
                                                : (uintptr_t)(prof + rowOffset + (uint32_t)i0);
@@ -274,9 +282,9 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
 
         uint32_t H[RP], E[RP];
 #pragma unroll
-        for (int k = 0; k < RP; k++) { H[k] = 0; E[k] = 0; }
-        uint32_t prevHup = 0;
-        uint32_t outL = pack16(SW_DUMMY_LETTER, SW_DUMMY_LETTER), outH = 0, outFt = 0, outFm = 0;
+        for (int k = 0; k < RP; k++) { H[k] = biasP; E[k] = biasP; }
+        uint32_t prevHup = biasP;
+        uint32_t outL = pack16(SW_DUMMY_LETTER, SW_DUMMY_LETTER), outH = biasP, outFt = biasP, outFm = biasP;
         int tChunk = SW_DUMMY_LETTER, bH = 0, bFt = 0, bFm = 0;
 
         for (int s = 0; s < warpSteps; s++) {
@@ -301,7 +309,10 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
                 fm0 = __shfl_sync(0xffffffffu, bFm, s % LANES, LANES);
                 if (!hasPrev) { h0 = 0; ft0 = 0; fm0 = 0; }
             }
-            if (gl == 0) { upL = (uint32_t)a0; upH = (uint32_t)h0 & 0xffffu; upFt = (uint32_t)ft0 & 0xffffu; upFm = (uint32_t)fm0 & 0xffffu; }
+            if (gl == 0) {
+                upL = (uint32_t)a0;
+                upH = (uint32_t)(h0 + (int)BIAS) & 0xffffu; upFt = (uint32_t)(ft0 + (int)BIAS) & 0xffffu; upFm = (uint32_t)(fm0 + (int)BIAS) & 0xffffu;
+            }
             const uint32_t inL = upL | (outL << 16);
             const uint32_t inH = upH | (outH << 16);
             const uint32_t inFt = upFt | (outFt << 16);
@@ -311,10 +322,16 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
                 const uint32_t letA = inL & 0xffffu, letB = inL >> 16;
                 uint32_t sa[NWA], sb[NWA];
                 if (SEGMODE != 0) {
-                    const uint32_t *wa = (const uint32_t *)(addrA + (uintptr_t)letA * strideU);
-                    const uint32_t *wb = (const uint32_t *)(addrB + (uintptr_t)letB * strideU);
+                    const uint4 *wa = (const uint4 *)(addrA + (uintptr_t)letA * strideU);
+                    const uint4 *wb = (const uint4 *)(addrB + (uintptr_t)letB * strideU);
 #pragma unroll
-                    for (int w = 0; w < NWA; w++) { sa[w] = __ldg(wa + w); sb[w] = __ldg(wb + w); }
+                    for (int w = 0; w < RPPAD / 16; w++) {
+                        const uint4 va = __ldg(wa + w), vb = __ldg(wb + w);
+                        if (4 * w + 0 < NWA) { sa[4 * w + 0] = va.x; sb[4 * w + 0] = vb.x; }
+                        if (4 * w + 1 < NWA) { sa[4 * w + 1] = va.y; sb[4 * w + 1] = vb.y; }
+                        if (4 * w + 2 < NWA) { sa[4 * w + 2] = va.z; sb[4 * w + 2] = vb.z; }
+                        if (4 * w + 3 < NWA) { sa[4 * w + 3] = va.w; sb[4 * w + 3] = vb.w; }
+                    }
                 } else {
                     const uint32_t *wa = (const uint32_t *)((addrA + (uintptr_t)letA * stride) & ~(uintptr_t)3);
                     const uint32_t *wb = (const uint32_t *)((addrB + (uintptr_t)letB * stride) & ~(uintptr_t)3);
@@ -330,17 +347,48 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
                 uint32_t diag = prevHup;
                 uint32_t ft = inFt, fm = inFm;
                 uint32_t colMax = 0;
+                if (SEGMODE != 0) {
+                    // segment-aligned stages (forward 8-bit pass, ge == 1): see the BIAS note above
+                    uint32_t X = inFt;           // exact F entering the stage's first row (= a segment start)
+                    int kb = 0;
+                    fm = biasP;
+#pragma unroll
+                    for (int k = 0; k < RP; k++) {
+                        const uint32_t sel = (uint32_t)(k & 3) | ((uint32_t)((k & 3) | 8) << 4) | ((uint32_t)(4 + (k & 3)) << 8) | ((uint32_t)((4 + (k & 3)) | 8) << 12);
+                        const uint32_t sv = prmtSext(sa[k >> 2], sb[k >> 2], sel);
+                        const uint32_t e = E[k];
+                        const bool segStart = (k == 0) || (SEGMODE == 1 && k == RP / 2);
+                        if (segStart && k != 0) {      // second segment of the stage: its X is the exact F entering this row
+                            X = max16x2(fm, X * one - (uint32_t)(k - kb) * 0x10001u);
+                            kb = k;
+                            fm = biasP;
+                        }
+                        const int d = k - kb;
+                        // X - d in both halves with one 32-bit subtraction: X_lo >= BIAS > d, so the low half never borrows
+                        const uint32_t xk = d == 0 ? X : X * one - (uint32_t)d * 0x10001u;
+                        const uint32_t h = __viaddmax_s16x2(diag, sv, e);
+                        // the gap-open term without Fm: max(H1 - go, 0) = max(h - go, 0, Fm - go), so the Fm chain
+                        // Fm' = max(Fm - ge, h - go, 0) is ONE dependent instruction per row (Fm - go <= Fm - ge)
+                        const uint32_t hg = __viaddmax_s16x2(h, negGo, biasP);
+                        const uint32_t fmg = fm * one - goP;          // Fm - go, E - ge: borrow-free 32-bit subtractions (IMAD)
+                        const uint32_t eg = e * one - geP;
+                        const uint32_t hs = segStart ? max16x2(h, xk) : __vimax3_s16x2(h, fm, xk);   // max(H1, exact F)
+                        diag = H[k];
+                        H[k] = hs;
+                        colMax = max16x2(colMax, hs * (uint32_t)SW_KEYMUL + (uint32_t)((31 - k) * 0x10001));
+                        E[k] = __vimax3_s16x2(eg, hg, fmg);
+                        fm = __viaddmax_s16x2(fm, negGe, hg);
+                    }
+                    ft = max16x2(fm, X * one - (uint32_t)(RP - kb) * 0x10001u);     // exact F leaving the stage
+                } else {
 #pragma unroll
                 for (int k = 0; k < RP; k++) {
                     const uint32_t sel = (uint32_t)(k & 3) | ((uint32_t)((k & 3) | 8) << 4) | ((uint32_t)(4 + (k & 3)) << 8) | ((uint32_t)((4 + (k & 3)) | 8) << 12);
                     const uint32_t sv = prmtSext(sa[k >> 2], sb[k >> 2], sel);
                     const uint32_t e = E[k];
-                    // a segment starts at this row in both stages: Fm restarts from 0 and H1 = max(h, 0) = h (h >= E >= 0)
-                    const bool segStart = (SEGMODE != 0) && (k == 0 || (SEGMODE == 1 && k == RP / 2));
-                    if (SEGMODE == 0) fm &= segKeep[SEGMODE == 0 ? k : 0];
-                    if (segStart) fm = zero;
+                    fm &= segKeep[SEGMODE == 0 ? k : 0];
                     const uint32_t h = __viaddmax_s16x2(diag, sv, e);
-                    const uint32_t h1 = segStart ? h : max16x2(h, fm);
+                    const uint32_t h1 = max16x2(h, fm);
                     const uint32_t hs = max16x2(h, ft);
                     diag = H[k];
                     H[k] = hs;
@@ -352,6 +400,7 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
                     // Ft >= Fm and go >= ge: (Fm - go) <= (Ft - ge), so the gap opened from H1 also serves the exact chain
                     ft = __viaddmax_s16x2(ft, negGe, open1);
                 }
+                }
                 outL = inL; outH = H[RP - 1]; outFt = ft; outFm = fm;
                 prevHup = inH;
                 if (KEYED) {
@@ -360,8 +409,8 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
                     const bool upB = kB >= thrB && cA >= 1;
                     if (upA | upB) {            // rare after the first columns: decode score and row from the key
                         const int mA = kA / SW_KEYMUL, mB = kB / SW_KEYMUL;
-                        if (upA) { bestA = mA; colA = cA; rowA = i0 + 31 - (kA - mA * SW_KEYMUL); thrA = (mA + 1) * SW_KEYMUL; }
-                        if (upB) { bestB = mB; colB = cA - 1; rowB = i0 + RP + 31 - (kB - mB * SW_KEYMUL); thrB = (mB + 1) * SW_KEYMUL; }
+                        if (upA) { bestA = mA - (int)BIAS; colA = cA; rowA = i0 + 31 - (kA - mA * SW_KEYMUL); thrA = (mA + 1) * SW_KEYMUL; }
+                        if (upB) { bestB = mB - (int)BIAS; colB = cA - 1; rowB = i0 + RP + 31 - (kB - mB * SW_KEYMUL); thrB = (mB + 1) * SW_KEYMUL; }
                     }
                 } else {
                     const int mA = lo16(colMax), mB = hi16(colMax);
@@ -421,7 +470,7 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
 
 // packed pass: one round = up to four pairs of the same scheduling class (order[] is laid out in rounds of 4 slots)
 template <bool KEYED>
-__global__ void __launch_bounds__(SW_WARPS * 32) swKernel16(SwKernelArgs A) {
+__global__ void __launch_bounds__(SW_WARPS * 32, 4) swKernel16(SwKernelArgs A) {
     const uint32_t lane = swLane();
     const uint32_t warp = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
     int *bnd = A.boundary + (size_t)warp * 6 * A.boundaryStride;
@@ -437,7 +486,7 @@ __global__ void __launch_bounds__(SW_WARPS * 32) swKernel16(SwKernelArgs A) {
         // forward 8-bit pass (KEYED): width 32, so segLen = RP/2 (8 lanes) or RP (16 lanes) for every pair of the round and
         // the segment starts sit at compile-time rows; anything else (checked, warp-uniform) takes the per-row mask
         bool segAligned = false;
-        if (KEYED && cls < 20) {
+        if (KEYED && cls < 20 && A.b.gapExtend == 1 && A.b.gapOpen >= 1 && A.b.gapOpen < 32) {
             const uint32_t idg = A.order[(size_t)round * 4 + (cls < 10 ? lane / 8 : lane / 16)];
             bool ok = true;
             if (idg != 0xffffffffu) {
