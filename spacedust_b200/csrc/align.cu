@@ -689,7 +689,8 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     batch.profFwd = dProfF.p; batch.profRev = dProfR.p; batch.profOff = dProfOff.p; batch.profStride = dStride.p; batch.qLen = dLen.p;
     batch.profStg = dProfS.p; batch.stgOff = dStgOff.p; batch.stgStride = dStgStride.p;
     batch.tRes = idx->raw.p; batch.tOff = idx->off.p; batch.gapOpen = par->gap_open; batch.gapExtend = par->gap_extend;
-    const uint32_t swWarps = (uint32_t)ctx->smCount * 4u * swWarpsPerCta();
+    static const uint32_t swCtasPerSm = getenv("SD_SW_CTAS") ? (uint32_t)atoi(getenv("SD_SW_CTAS")) : 5u;     // = __launch_bounds__ of swKernel16
+    const uint32_t swWarps = (uint32_t)ctx->smCount * swCtasPerSm * swWarpsPerCta();
     const uint32_t bndStride = std::max<uint32_t>(idx->maxLen, 32u) + 32u;
     ScratchBuf<int> dBoundary(ctx, SL_AL_BOUND);
     if ((rc = dBoundary.alloc((size_t)swWarps * 6 * bndStride))) return rc;

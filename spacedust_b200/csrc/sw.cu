@@ -470,7 +470,7 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
 
 // packed pass: one round = up to four pairs of the same scheduling class (order[] is laid out in rounds of 4 slots)
 template <bool KEYED>
-__global__ void __launch_bounds__(SW_WARPS * 32, 4) swKernel16(SwKernelArgs A) {
+__global__ void __launch_bounds__(SW_WARPS * 32, 5) swKernel16(SwKernelArgs A) {
     const uint32_t lane = swLane();
     const uint32_t warp = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
     int *bnd = A.boundary + (size_t)warp * 6 * A.boundaryStride;
