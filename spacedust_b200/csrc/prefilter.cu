@@ -1142,7 +1142,11 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     const uint32_t nCta = std::max(1u, std::min<uint32_t>((uint32_t)(ctx->smCount * ctasPerSm), (nq + PF_WARPS - 1) / PF_WARPS));
     const uint32_t nWarps = nCta * PF_WARPS;
     // first-pass capacity of the per-warp candidate lists (SD_PF_CANDCAP: test hook that forces the second pass)
-    const uint32_t candCap = getenv("SD_PF_CANDCAP") ? (uint32_t)std::max(32, atoi(getenv("SD_PF_CANDCAP"))) : 32768u;
+    // grows with the number of targets (long queries against 800 k targets have > 32 k candidates; re-running them in the
+    // few-warp second pass costs seconds): 32 k up to 256 k targets, 128 k at 800 k targets
+    uint32_t candCap = 32768u;
+    while (candCap < 262144u && (uint64_t)candCap * 8u < idx->nT) candCap *= 2;
+    if (getenv("SD_PF_CANDCAP")) candCap = (uint32_t)std::max(32, atoi(getenv("SD_PF_CANDCAP")));
 
     ScratchBuf<uint32_t> dTable(ctx, SL_PF_TABLE), dResT(ctx, SL_PF_REST);
     DevBuf<uint32_t> dOutCount, dNext, dFail;
