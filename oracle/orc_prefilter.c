@@ -343,14 +343,42 @@ long orc_prefilter(const char *tSeq, const uint64_t *tOff, uint32_t nT,
             if (found >= maxHits) break;
         }
         if (thr < (unsigned int)par->minDiagScore) thr = (unsigned int)par->minDiagScore;
-        if (thr >= 255) {
-            fprintf(stderr, "orc_prefilter: query %u needs the truncated-score rescoring path (not restated)\n", q);
-            return -2;
-        }
         size_t nAbove = 0;
         for (int s = 255; s >= (int)thr; s--)
             for (size_t c = 0; c < nKeep; c++)
                 if (tmp[c].count == s) cand[nAbove++] = tmp[c];
+        /* scoreIsTruncated (QueryMatcher.cpp:157-171): at least --max-seqs elements sit at the 8-bit cap, so the cap no longer
+         * orders them.  rescoreHits (QueryMatcher.cpp:525-544) replaces the capped score by the uncapped diagonal score,
+         * rescaled to 0..255 relative to the query's self score, then the list is re-sorted (stable) by that value and
+         * getResult maps it back with rescaleScore = maxSelfScore - 255 (QueryMatcher.cpp:407-410). */
+        int rescale = 0;
+        if (thr >= 255) {
+            int maxSelf = diag_score(prof, L, qres, L, 0, NULL) - 255;              /* scoreSingleSequence(query, 0, 0) */
+            if (maxSelf < 1) maxSelf = 1;
+            if (maxSelf > 65535) maxSelf = 65535;
+            const float fltMaxSelf = (float)maxSelf;
+            unsigned int histo2[256];
+            memset(histo2, 0, sizeof histo2);
+            size_t nNew = 0;
+            for (size_t c = 0; c < nAbove && cand[c].count >= 255; c++) {
+                uint32_t t = cand[c].id;
+                unsigned int newScore = (unsigned int)diag_score(prof, L, tres + tOff[t], (int)(tOff[t + 1] - tOff[t]),
+                                                                 (short)cand[c].diag, NULL);
+                newScore -= 255u;
+                const float score = (float)(newScore < 65535u ? newScore : 65535u);
+                cand[c].count = (unsigned char)(int)((score / fltMaxSelf) * (float)255 + 0.5);
+                histo2[cand[c].count]++;
+                nNew++;
+            }
+            /* radixSortByScoreSize(threshold 0): stable, new score descending */
+            size_t w = 0;
+            for (int s = 255; s >= 0; s--)
+                for (size_t c = 0; c < nNew; c++)
+                    if (cand[c].count == s) tmp[w++] = cand[c];
+            memcpy(cand, tmp, nNew * sizeof(cand_t));
+            nAbove = nNew;
+            rescale = maxSelf;
+        }
         size_t nRes = 0;
         uint32_t identity = par->sameDB ? q : UINT_MAX;
         if (identity != UINT_MAX) { res[0].seqId = identity; res[0].score = 65535; res[0].diag = 0; nRes = 1; }
@@ -362,7 +390,9 @@ long orc_prefilter(const char *tSeq, const uint64_t *tOff, uint32_t nT,
             res[nRes].seqId = cand[c].id;
             res[nRes].score = cand[c].count;
             res[nRes].diag = cand[c].diag;
-            if (cand[c].count >= 255) {
+            if (rescale != 0) {
+                res[nRes].score = (int)(255u + ((unsigned int)cand[c].count * (unsigned int)rescale / 255u));
+            } else if (cand[c].count >= 255) {
                 uint32_t t = cand[c].id;
                 res[nRes].score = diag_score(prof, L, tres + tOff[t], (int)(tOff[t + 1] - tOff[t]),
                                              (short)cand[c].diag, NULL);

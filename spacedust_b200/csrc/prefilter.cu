@@ -697,12 +697,90 @@ __global__ void __launch_bounds__(PF_WARPS * 32, 4) prefilterKernel(PrefilterArg
             thrScore = max(sc, a.minDiagScore);
         }
         thrScore = __shfl_sync(0xffffffffu, thrScore, 0);
-        const bool needRescale = thrScore >= 255u;   // reference's rescoreHits path: not implemented
+        const bool needRescale = thrScore >= 255u;   // >= max-seqs elements at the 8-bit cap: rescoreHits path below
         uint32_t nRes = 0;
         if (identity != 0xffffffffu) {
             if (lane == 0) { resT[0] = identity; resScore[0] = 65535; resDiag[0] = 0; }
             nRes = 1;
         }
+        bool dropped = false;
+        if (needRescale) {
+            // scoreIsTruncated (QueryMatcher.cpp:157-171): the cap no longer orders the top class.  rescoreHits (:525-544):
+            // uncapped diagonal score minus 255, rescaled to 0..255 against the query's self score; stable re-sort by that
+            // value; getResult maps it back with rescaleScore = maxSelf (:407-410).  Rare, so plain lane-parallel code.
+            // 1. the capped class in the reference's order (bin-major, arrival order inside a bin) -> cand[] (free by now)
+            uint32_t nL = 0;
+            for (uint32_t bin = 0; bin <= a.binMask; bin++) {
+                for (uint32_t c0 = 0; c0 < nKeep; c0 += 32) {
+                    const uint32_t c = c0 + lane;
+                    uint64_t v = 0;
+                    bool sel = false;
+                    if (c < nKeep) {
+                        v = keep[c];
+                        sel = ((uint32_t)(v >> 8) & 0xffu) == 255u && ((uint32_t)(v >> 32) & a.binMask) == bin;
+                    }
+                    const uint32_t b = __ballot_sync(0xffffffffu, sel);
+                    if (sel) cand[nL + __popc(b & ltMask)] = v & ~0xffffull;      // (target, diagonal), score byte cleared
+                    nL += __popc(b);
+                }
+            }
+            __syncwarp();
+            // 2. self score of the query on the main diagonal (scoreSingleSequence(query, 0, 0)), uncapped
+            int maxSelf = 0;
+            if (lane == 0) {
+                const uint8_t *qc = a.q.code + qBase;
+                const int8_t *qk = a.q.corr + qBase;
+                int best = 0, run = 0;
+                for (int p = 0; p < Lq; p++) {
+                    run += (int)sSub[qc[p] * AA + qc[p]] + (int)qk[p];
+                    run = max(run, 0);
+                    best = max(best, run);
+                }
+                maxSelf = min(max(best - 255, 1), 65535);
+            }
+            maxSelf = __shfl_sync(0xffffffffu, maxSelf, 0);
+            const float fltMaxSelf = (float)maxSelf;
+            // 3. rescaled 8-bit scores + their histogram
+            for (uint32_t i = lane; i < 256; i += 32) hist[i] = 0;
+            __syncwarp();
+            for (uint32_t c = lane; c < nL; c += 32) {
+                const uint64_t v = cand[c];
+                uint32_t dummy = 0;
+                const uint32_t full = (uint32_t)diagonalScore(a, sSub, qBase, Lq, (uint32_t)(v >> 32), (int)(int16_t)(uint16_t)(v >> 16), dummy);
+                const uint32_t newScore = full - 255u;
+                const float sc = (float)min(newScore, 65535u);
+                const float scaled = __fmul_rn(__fdiv_rn(sc, fltMaxSelf), 255.0f);
+                const uint32_t cnt = (uint32_t)(int)__dadd_rn((double)scaled, 0.5) & 0xffu;
+                cand[c] = v | (uint64_t)cnt;
+                atomicAdd(&hist[cnt], 1u);
+            }
+            __syncwarp();
+            // 4. stable selection by rescaled score, highest first
+            for (int s2 = 255; s2 >= 0; s2--) {
+                if (hist[s2] == 0) continue;
+                for (uint32_t c0 = 0; c0 < nL; c0 += 32) {
+                    const uint32_t c = c0 + lane;
+                    uint64_t v = 0;
+                    bool sel = false;
+                    if (c < nL) {
+                        v = cand[c];
+                        sel = (uint32_t)(v & 0xffu) == (uint32_t)s2 && (uint32_t)(v >> 32) != identity;
+                    }
+                    const uint32_t b = __ballot_sync(0xffffffffu, sel);
+                    if (sel) {
+                        const uint32_t pos = nRes + __popc(b & ltMask);
+                        if (pos < a.maxHits) {
+                            resT[pos] = (uint32_t)(v >> 32);
+                            resScore[pos] = (int)(255u + ((uint32_t)s2 * (uint32_t)maxSelf) / 255u);
+                            resDiag[pos] = (uint16_t)(v >> 16);
+                        }
+                    }
+                    nRes += __popc(b);
+                    if (nRes > a.maxHits) { dropped = true; nRes = a.maxHits; }
+                }
+            }
+            __syncwarp();
+        } else {
         // everything strictly above the threshold survives
         for (uint32_t c0 = 0; c0 < nKeep; c0 += 32) {
             const uint32_t c = c0 + lane;
@@ -726,7 +804,6 @@ __global__ void __launch_bounds__(PF_WARPS * 32, 4) prefilterKernel(PrefilterArg
         }
         nRes = min(nRes, a.maxHits);
         // the threshold class fills what is left, in (id & binMask, stream order) order
-        bool dropped = false;
         for (uint32_t bin = 0; bin <= a.binMask; bin++) {
             for (uint32_t c0 = 0; c0 < nKeep; c0 += 32) {
                 const uint32_t c = c0 + lane;
@@ -751,10 +828,11 @@ __global__ void __launch_bounds__(PF_WARPS * 32, 4) prefilterKernel(PrefilterArg
                 if (nRes > a.maxHits) { dropped = true; nRes = a.maxHits; }
             }
         }
+        }
         __syncwarp();
         if (dropped) stTrunc += (lane == 0) ? 1 : 0;
         // scores that hit the 8-bit cap are replaced by the uncapped diagonal score (QueryMatcher.cpp:410-413)
-        for (uint32_t r = lane; r < nRes; r += 32) {
+        for (uint32_t r = lane; r < nRes && !needRescale; r += 32) {
             if (resScore[r] >= 255 && resScore[r] != 65535) {
                 uint32_t dummy = 0;
                 resScore[r] = diagonalScore(a, sSub, qBase, Lq, resT[r], (int)(int16_t)resDiag[r], dummy);
@@ -828,7 +906,6 @@ __global__ void __launch_bounds__(PF_WARPS * 32, 4) prefilterKernel(PrefilterArg
                 atomicMin(a.errQuery, q);
             } else {
                 a.outCount[q] = nOut;
-                if (needRescale) { atomicAdd(&a.stats[ST_ERR_RESCORE], 1ull); atomicMin(a.errQuery, q); }
                 atomicAdd(&a.stats[ST_PROBES], stProbes);
                 atomicAdd(&a.stats[ST_MATCHES], stMatches);
                 atomicAdd(&a.stats[ST_DIAGRES], stDiagRes);
@@ -1251,7 +1328,6 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     SD_CUDA(cudaMemcpyAsync(hNext, dNext.p, sizeof hNext, cudaMemcpyDeviceToHost, st));
     SD_CUDA(cudaStreamSynchronize(st));
     if (hStats[ST_ERR_CAND]) { setError("prefilter: %llu queries produced more than %u diagonal candidates (first: query %u)", hStats[ST_ERR_CAND], 1u << 22, hNext[1]); return SD_ELIMIT; }
-    if (hStats[ST_ERR_RESCORE]) { setError("prefilter: %llu queries need the reference's truncated-score rescaling path (>= max-seqs hits at score 255; first: query %u): not implemented", hStats[ST_ERR_RESCORE], hNext[1]); return SD_ELIMIT; }
     uint64_t totalHits = 0;
     for (uint32_t i = 0; i < nq; i++) totalHits += hCount[i];
     if (hitOffsets)

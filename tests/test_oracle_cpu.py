@@ -93,3 +93,45 @@ def test_oracle_clustersearch_vs_reference(ref_setdb, synth_small):
     ref = helpers.parse_result_tsv(out, src, name_to_key)
     assert ref == helpers.canonical_clusters(o["clusters"])
     assert len(ref) > 5
+
+
+def _saturated_family(n_copies=60, n_unrelated=20, length=300, seed=9):
+    """One ancestral protein in many close copies (88-97 % identity: every pair's diagonal score is far above the 8-bit
+    cap) plus unrelated proteins, as ONE proteome in Prodigal form."""
+    rng = np.random.default_rng(seed)
+    anc = rng.choice(20, size=length, p=synth.BACKGROUND).astype(np.uint8)
+    seqs = [synth.LETTERS[synth._mutate(rng, anc, rng.uniform(0.88, 0.97))].tobytes() + b"*" for _ in range(n_copies)]
+    seqs += [synth.LETTERS[rng.choice(20, size=int(rng.integers(80, 400)), p=synth.BACKGROUND)].tobytes() + b"*" for _ in range(n_unrelated)]
+    names, pos = [], 1
+    for i, sq in enumerate(seqs):
+        end = pos + 3 * len(sq) - 1
+        names.append("SAT00001.1_%d # %d # %d # 1 # ID=1_%d;partial=00" % (i + 1, pos, end, i + 1))
+        pos = end + 50
+    return [{"acc": "SAT00001.1", "names": names, "seqs": seqs}]
+
+
+def test_oracle_prefilter_truncated_scores_vs_reference():
+    """More than --max-seqs targets at the 8-bit cap: the reference rescales the uncapped scores (rescoreHits,
+    QueryMatcher.cpp:157-171,525-544); the oracle must follow, hit for hit."""
+    if not helpers.have_ref():
+        pytest.skip("oracle/_ref/spacedust not built")
+    prot = _saturated_family()
+    d = tempfile.mkdtemp(prefix="sdref_")
+    try:
+        paths = synth.write_fasta(prot, os.path.join(d, "faa"))
+        db = os.path.join(d, "setDB")
+        helpers.run_ref(["createsetdb"] + paths + [db, os.path.join(d, "tmp"), "-v", "1"])
+        helpers.run_ref(["prefilter", db, db, os.path.join(d, "pref"), "-s", "5.7", "--max-seqs", "16", "-c", "0.8", "--cov-mode", "2",
+                         "--min-ungapped-score", "15", "--threads", "2", "-v", "1"])
+        keys, buf, off = helpers.load_seqdb(db)
+        hits, st = helpers.orc_prefilter(buf, off, buf, off, helpers.default_pref_params(maxSeqs=16))
+        mine = helpers.hits_to_lines(hits, keys, keys)
+        ref = helpers.read_db(os.path.join(d, "pref"))
+        n_rescaled = 0
+        for k in keys:
+            r = [l for l in ref[int(k)].split(b"\n") if l]
+            assert r == mine[int(k)], "query %d" % k
+            n_rescaled += sum(1 for l in r[1:] if int(l.split(b"\t")[1]) > 255)
+        assert n_rescaled > 200          # the family members' lists really went through the rescaling
+    finally:
+        shutil.rmtree(d, ignore_errors=True)

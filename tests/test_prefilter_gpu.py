@@ -79,6 +79,20 @@ def test_prefilter_candidate_overflow_second_pass(gpu_ctx, synth_small, monkeypa
     _compare(gpu_ctx, fbuf, foff, fbuf, foff, True, maxSeqs=16)
 
 
+def test_prefilter_truncated_scores(gpu_ctx):
+    """More than --max-seqs targets at the 8-bit cap (close copies of one protein): the rescoreHits path
+    (QueryMatcher.cpp:157-171,525-544) -- uncapped scores rescaled against the query's self score -- must give the oracle's
+    hits (the oracle is pinned on the reference binary for this case by tests/test_oracle_cpu.py)."""
+    rng = np.random.default_rng(9)
+    anc = rng.choice(20, size=300, p=synth.BACKGROUND).astype(np.uint8)
+    seqs = [synth.LETTERS[synth._mutate(rng, anc, rng.uniform(0.88, 0.97))].tobytes().decode() for _ in range(60)]
+    seqs += [synth.LETTERS[rng.choice(20, size=int(rng.integers(80, 400)), p=synth.BACKGROUND)].tobytes().decode() for _ in range(20)]
+    buf, off = helpers.pack_seqs(seqs)
+    st = _compare(gpu_ctx, buf, off, buf, off, True, maxSeqs=16)
+    assert st["truncated"] >= 60
+    _compare(gpu_ctx, buf, off, buf, off, False, maxSeqs=24, binSize=4)
+
+
 def test_prefilter_edge_sequences(gpu_ctx):
     """Short (< k-mer span), X-rich, low-complexity and duplicated sequences."""
     long_seq = ("MKTAYIAKQRQISFVKSHFSRQLEERLGLIEVQAPILSRVGDGTQDNLSGAEKAVQVKVKALPDAQFEVVHSLAKWKRQTLGQHDFSAGEGLYTHMKALRPDEDRLSPLHSVYV"
