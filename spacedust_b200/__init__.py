@@ -200,7 +200,8 @@ def align(ctx, index, qseqs, qoff, pair_q, pair_t, params, query_first=0, db_res
     cap = max(1, n_pairs)
     lens_t = np.diff(index.off).astype(np.int64)
     lens_q = np.diff(qoff).astype(np.int64)
-    bt_cap = int((lens_t[pair_t] + lens_q[pair_q]).sum()) + 64 if n_pairs else 64
+    # (indices are clipped only for this size estimate: the library itself rejects out-of-range pairs)
+    bt_cap = int((lens_t[np.minimum(pair_t, len(lens_t) - 1)] + lens_q[np.minimum(pair_q, len(lens_q) - 1)]).sum()) + 64 if n_pairs else 64
     out = np.zeros(cap, dtype=ALN_DTYPE)
     pool = np.zeros(bt_cap, dtype=np.uint8)
     n = ctypes.c_uint64(0)
