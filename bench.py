@@ -354,6 +354,13 @@ def run_ours(args, proteomes, rank, world, local_rank):
         algo = 8 * pst["probes"] + 6 * pst["matches"] + pst["diag_residues"] + 21 * pst["query_residues"] + 10 * pst["hits"]
         k_ms = pst["kernel_ms"]
         achieved = algo / 1e9 / (k_ms / 1e3) if k_ms > 0 else 0.0
+        # DRAM bytes of this launch from ncu (dram__bytes_read.sum + dram__bytes_write.sum, profiles/prof_prefilter_traffic_c2_r01.csv);
+        # known only for the default workload on one GPU
+        traffic, traffic_src = None, None
+        if world == 1 and args.proteomes == N_PROTEOMES and args.genes == GENES:
+            traffic = 495320312064 + 70822895104
+            traffic_src = ("ncu dram__bytes_read.sum + dram__bytes_write.sum of the C2 prefilterKernel launch (157.5 ms under ncu): 566 GB = "
+                           "6.65 x algorithmic, 3.6 TB/s; profiles/prof_prefilter_traffic_c2_r01.csv")
         cells = ast["cells_forward"] + ast["cells_reverse"]
         line = {"metric": "clustersearch query-genes/s", "value": n_total * args.steps / dt, "unit": "query-genes/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -366,7 +373,7 @@ def run_ours(args, proteomes, rank, world, local_rank):
                                     "prefilter, align, besthitbyset/combinehits, clusterhits, results to host"},
                 "gpu_launches": int(launches),
                 "roofline": {"kernel": "prefilterKernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": int(algo),
                              "bytes_formula": "8*P + 6*M + R + 21*Lq + 10*H (SURVEY.md 8d), P/M/R/H counted by the kernel and "
                                               "equal to the oracle's counts (tests/test_prefilter_gpu.py)",
