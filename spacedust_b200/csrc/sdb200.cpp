@@ -7,7 +7,8 @@
 //   sdb200 align         <qDB> <tDB> <prefDB> <resultDB> [align flags]       Alignment::run           -> sd_align_run
 //   sdb200 clustersearch <qSetDB> <tSetDB> <out.tsv> <tmp> [all flags]       clustersearch.sh:112-151 -> sd_clustersearch_run
 //                        (writes <tmp>/clusters, <tmp>/clusters_h and, with --write-dbs 1, <tmp>/result; then the TSV of
-//                         summarizeresults, src/util/SummarizeResults.cpp:77-114)
+//                         summarizeresults, src/util/SummarizeResults.cpp:77-114, <tmp>/clu_to_seq and <out>_seq_to_clu)
+//   sdb200 summarizeresults / filterdb --trim-to-one-column / swapdb      host-only text modules (postmods.cpp)
 // Flags keep the reference's names and meaning; reference flags that do not change the result of this path are
 // accepted and ignored; flags that select a path this implementation does not have make the tool fail
 // (Debug(Debug::ERROR) + EXIT(EXIT_FAILURE) in the reference, "Error: ..." + exit 1 here).  No CPU fallback.
@@ -25,6 +26,10 @@
 
 #include "../../include/sdgpu.h"
 #include "dbio.h"
+
+// postmods.cpp
+int filterdbTrimToOneColumn(const std::string &in, const std::string &out);
+int swapOneColumnDb(const std::string &in, const std::string &out);
 
 namespace {
 
@@ -436,6 +441,9 @@ int modClustersearch(int argc, char **argv) {
     if (!tsvBuf.empty()) fwrite(tsvBuf.data(), 1, tsvBuf.size(), tsv);
     fclose(tsv);
     if (!wc.close(err) || !wh.close(err)) die("%s", err.c_str());
+    // post-processing of data/clustersearch.sh:153-165: clusters -> clu_to_seq (first column), swapped into <out>_seq_to_clu
+    filterdbTrimToOneColumn(tmp + "/clusters", tmp + "/clu_to_seq");
+    swapOneColumnDb(tmp + "/clu_to_seq", out + "_seq_to_clu");
     info("Wrote %llu clusters to %s, %.0f ms; total %.0f ms\n", (unsigned long long)nC, out.c_str(), nowMs() - t0, nowMs() - tAll);
     sd_query_batch_destroy(batch);
     sd_target_index_destroy(idx);
@@ -446,10 +454,13 @@ int modClustersearch(int argc, char **argv) {
 }  // namespace
 
 int modCreatesetdb(int argc, char **argv);
+int modSummarizeresults(int argc, char **argv);
+int modFilterdb(int argc, char **argv);
+int modSwapdb(int argc, char **argv);
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "sdb200 (libsdgpu %d): createsetdb | prefilter | align | clustersearch\n", sd_version());
+        fprintf(stderr, "sdb200 (libsdgpu %d): createsetdb | prefilter | align | clustersearch | summarizeresults | filterdb | swapdb\n", sd_version());
         return EXIT_FAILURE;
     }
     const std::string mod = argv[1];
@@ -457,5 +468,8 @@ int main(int argc, char **argv) {
     if (mod == "prefilter") return modPrefilter(argc, argv);
     if (mod == "align") return modAlign(argc, argv);
     if (mod == "clustersearch") return modClustersearch(argc, argv);
+    if (mod == "summarizeresults") return modSummarizeresults(argc, argv);
+    if (mod == "filterdb") return modFilterdb(argc, argv);
+    if (mod == "swapdb") return modSwapdb(argc, argv);
     die("unknown module '%s'", mod.c_str());
 }

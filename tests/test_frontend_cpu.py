@@ -107,3 +107,71 @@ def test_createsetdb_vs_reference(case, synth_small):
         assert len(_sha(os.path.join(d, "a"))) == 19
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def test_post_modules_vs_reference(synth_small):
+    """Host-only modules after the clustering step (data/clustersearch.sh:151-165) on the REFERENCE's own clusters DB:
+    summarizeresults TSV identical (cluster order is thread-scheduling dependent in the reference: compared as sorted blocks),
+    filterdb --trim-to-one-column identical entries, swapdb the same keys, lengths and key sets per entry."""
+    if not helpers.have_ref():
+        pytest.skip("oracle/_ref/spacedust not built")
+    d = tempfile.mkdtemp(prefix="sdfe_")
+    try:
+        paths = synth.write_fasta(synth_small, os.path.join(d, "faa"))
+        db = os.path.join(d, "setDB")
+        helpers.run_ref(["createsetdb"] + paths + [db, os.path.join(d, "tmp"), "-v", "1"])
+        helpers.run_ref(["clustersearch", db, db, os.path.join(d, "ref.tsv"), os.path.join(d, "tmpcs"), "--filter-self-match", "1",
+                         "--threads", "2", "-v", "1"])
+        latest = os.path.join(d, "tmpcs", "latest")
+        subprocess.run([SDB200, "summarizeresults", db, db, os.path.join(latest, "clusters"), os.path.join(d, "mine.tsv")], check=True)
+
+        def blocks(path):
+            out, cur = [], None
+            for line in open(path):
+                if line.startswith("#"):
+                    cur = [line, []]
+                    out.append(cur)
+                else:
+                    cur[1].append(line)
+            return sorted((a, tuple(b)) for a, b in out)
+        ref_blocks = blocks(os.path.join(d, "ref.tsv"))
+        assert blocks(os.path.join(d, "mine.tsv")) == ref_blocks and len(ref_blocks) > 5
+
+        subprocess.run([SDB200, "filterdb", os.path.join(latest, "clusters"), os.path.join(d, "c2s"), "--trim-to-one-column"], check=True)
+        # (the reference writes the entries in thread order; content per key, lengths and dbtype must agree)
+        assert helpers.read_db(os.path.join(d, "c2s")) == helpers.read_db(os.path.join(latest, "clu_to_seq"))
+        assert sorted((k, l) for k, _, l in helpers.read_index(os.path.join(d, "c2s"))) == \
+            sorted((k, l) for k, _, l in helpers.read_index(os.path.join(latest, "clu_to_seq")))
+        assert open(os.path.join(d, "c2s.dbtype"), "rb").read() == open(os.path.join(latest, "clu_to_seq.dbtype"), "rb").read()
+        subprocess.run([SDB200, "swapdb", os.path.join(d, "c2s"), os.path.join(d, "s2c")], check=True)
+        ref_s2c = os.path.join(d, "ref.tsv_seq_to_clu")
+        assert sorted((k, l) for k, _, l in helpers.read_index(os.path.join(d, "s2c"))) == sorted((k, l) for k, _, l in helpers.read_index(ref_s2c))
+        assert open(os.path.join(d, "s2c.dbtype"), "rb").read() == open(ref_s2c + ".dbtype", "rb").read()
+        mine = {k: sorted(v.split()) for k, v in helpers.read_db(os.path.join(d, "s2c")).items()}
+        ref = {k: sorted(v.split()) for k, v in helpers.read_db(ref_s2c).items()}
+        assert mine == ref
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def test_db_reader_accepts_split_data_files():
+    """Per-thread split files <db>.0 .. <db>.N-1 with one merged index (DBWriter.cpp:531-623) read like a merged DB."""
+    d = tempfile.mkdtemp(prefix="sdfe_")
+    try:
+        paths = synth.write_fasta(synth.generate(2, 5, seed=3), os.path.join(d, "faa"))
+        db = os.path.join(d, "setDB")
+        subprocess.run([SDB200, "createsetdb"] + paths + [db, os.path.join(d, "tmp")], check=True)
+        # a tiny "clusters" DB in two split files: entries "0\t1\tx\n" style lines
+        with open(os.path.join(d, "clu.0"), "wb") as f:
+            f.write(b"3\t4\tx\n5\t6\ty\n\0")
+        with open(os.path.join(d, "clu.1"), "wb") as f:
+            f.write(b"7\t8\tz\n\0")
+        with open(os.path.join(d, "clu.index"), "w") as f:
+            f.write("0\t0\t17\n1\t17\t9\n")
+        with open(os.path.join(d, "clu.dbtype"), "wb") as f:
+            f.write((5).to_bytes(4, "little"))
+        subprocess.run([SDB200, "filterdb", os.path.join(d, "clu"), os.path.join(d, "one"), "--trim-to-one-column"], check=True)
+        got = helpers.read_db(os.path.join(d, "one"))
+        assert got == {0: b"3\n5\n", 1: b"7\n"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
