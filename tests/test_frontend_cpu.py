@@ -167,7 +167,7 @@ def test_db_reader_accepts_split_data_files():
         with open(os.path.join(d, "clu.1"), "wb") as f:
             f.write(b"7\t8\tz\n\0")
         with open(os.path.join(d, "clu.index"), "w") as f:
-            f.write("0\t0\t17\n1\t17\t9\n")
+            f.write("0\t0\t13\n1\t13\t7\n")
         with open(os.path.join(d, "clu.dbtype"), "wb") as f:
             f.write((5).to_bytes(4, "little"))
         subprocess.run([SDB200, "filterdb", os.path.join(d, "clu"), os.path.join(d, "one"), "--trim-to-one-column"], check=True)
