@@ -89,7 +89,7 @@ typedef struct {
     double total_ms;          /* device time of the whole call incl. copies     */
 } sd_prefilter_stats;
 
-/* Build the device-resident target side: residue mapping, tantan masking, k-mer index
+/* Build the device-resident target side: residue mapping, tantan masking (on the device), k-mer index
  * (IndexBuilder::fillDatabase, lib/mmseqs/src/prefiltering/IndexBuilder.cpp:55-239).
  * seqs: ASCII residues of all targets concatenated; off[n+1]: byte offsets. */
 int sd_target_index_build(sd_context *ctx, const char *seqs, const uint64_t *off, uint32_t n,
@@ -229,7 +229,9 @@ int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_t n_alns,
 
 /* ---- fused hot path: prefilter -> align -> besthitbyset/combinehits -> clusterhits (data/clustersearch.sh:112-146) ----
  * Same results as calling the three stages one after the other, but the prefilter hit list stays in HBM.  The result
- * object owns host copies of the accepted alignments (+ backtraces) and the clusters. */
+ * object owns host copies of the accepted alignments (+ CIGAR strings) and the clusters.  Internally the query batch is cut
+ * into chunks of whole query sets that two host threads process in turn (host post-processing of one chunk under the kernels of
+ * the next); q_set_of must list the sets in ascending contiguous blocks for that, otherwise the call runs as one chunk. */
 typedef struct sd_search_result sd_search_result;
 int sd_clustersearch_run(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
                          const sd_prefilter_params *ppar, const sd_align_params *apar, const sd_cluster_params *cpar,

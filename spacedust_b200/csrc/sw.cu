@@ -548,7 +548,7 @@ __global__ void swScheduleFill(const uint32_t *sortedKeys, const uint32_t *sorte
     order[(size_t)(classInfo[32 + cc] + r / tpr) * 4 + (r % tpr)] = sortedVals[p];
 }
 
-template <bool PACKED>
+// 32-bit pass for the few pairs whose scores approach 2^15 (the packed pass flags them with overflow = 2)
 __global__ void __launch_bounds__(SW_WARPS * 32) swKernel(SwKernelArgs A) {
     const uint32_t lane = swLane();
     const uint32_t warp = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
@@ -562,15 +562,11 @@ __global__ void __launch_bounds__(SW_WARPS * 32) swKernel(SwKernelArgs A) {
         const uint32_t id = A.order ? A.order[ti] : ti;
         const SwTask tk = A.tasks[id];
         SwResult r;
-        if (PACKED) {
-            r.score = 0; r.col = -1; r.row = -1; r.overflow = 0;   // unused: the packed pass is swKernel16
-        } else {
-            const int rowsPerLane = (tk.nRows + 31) / 32;
-            if (rowsPerLane <= 4) swPass<4>(A, tk, bnd, r, cells);
-            else if (rowsPerLane <= 8) swPass<8>(A, tk, bnd, r, cells);
-            else if (rowsPerLane <= 16) swPass<16>(A, tk, bnd, r, cells);
-            else swPass<32>(A, tk, bnd, r, cells);
-        }
+        const int rowsPerLane = (tk.nRows + 31) / 32;
+        if (rowsPerLane <= 4) swPass<4>(A, tk, bnd, r, cells);
+        else if (rowsPerLane <= 8) swPass<8>(A, tk, bnd, r, cells);
+        else if (rowsPerLane <= 16) swPass<16>(A, tk, bnd, r, cells);
+        else swPass<32>(A, tk, bnd, r, cells);
         if (lane == 0) A.results[id] = r;
     }
     if (lane == 0 && cells) atomicAdd(A.cells, cells);
@@ -630,7 +626,7 @@ int launchSw(sd_context *ctx, const SwBatch &batch, const SwTask *dTasks, SwResu
     uint32_t nCta = std::min<uint32_t>(nWarpsAllocated / SW_WARPS, (nTasks + SW_WARPS - 1) / SW_WARPS);
     if (nCta == 0) nCta = 1;
     if (!packed16) {
-        swKernel<false><<<nCta, SW_WARPS * 32, 0, st>>>(A);
+        swKernel<<<nCta, SW_WARPS * 32, 0, st>>>(A);
         ctx->launches++;
         SD_CUDA(cudaGetLastError());
         return SD_OK;
