@@ -517,6 +517,14 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     const uint32_t nq = queries->nq;
     if (nq == 0 || n_pairs == 0) return SD_OK;
     if (par->gap_open < par->gap_extend) { setError("sd_align_run: gap open < gap extend is not supported"); return SD_ELIMIT; }
+    if (par->gap_open != 11 || par->gap_extend != 1) {
+        // EvalueComputation::init (alignment/EvalueComputation.h:56-110): only BLOSUM62 (11, 1) has tabulated Gumbel parameters; for
+        // any other gap costs the reference ESTIMATES them with ALP's simulation (lib/alp, seed 42, up to 60 s) -- E-values and bit
+        // scores would silently differ here, so the call is refused
+        setError("sd_align_run: --gap-open %d --gap-extend %d: the reference estimates the E-value parameters for non-default gap "
+                 "costs by simulation (ALP); only 11/1 is implemented", par->gap_open, par->gap_extend);
+        return SD_ELIMIT;
+    }
     if (n_pairs >= 0xffffffffull) { setError("sd_align_run: too many pairs in one call (%llu)", (unsigned long long)n_pairs); return SD_ELIMIT; }
     const uint64_t total = queries->total;
     SD_CUDA(cudaSetDevice(ctx->device));

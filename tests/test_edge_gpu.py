@@ -76,5 +76,9 @@ def test_bad_arguments_fail_loudly(gpu_ctx):
         ap2 = sd.default_align_params(same_db=1, gap_open=1, gap_extend=3)
         with pytest.raises(sd.SdError):      # gap open < gap extend is rejected, not silently mis-scored
             sd.align(gpu_ctx, idx, buf, off, np.array([0], dtype=np.uint32), np.array([1], dtype=np.uint32), ap2)
+        ap3 = sd.default_align_params(same_db=1, gap_open=9, gap_extend=2)
+        with pytest.raises(sd.SdError) as e:  # the reference simulates Gumbel parameters for other gap costs: refused
+            sd.align(gpu_ctx, idx, buf, off, np.array([0], dtype=np.uint32), np.array([1], dtype=np.uint32), ap3)
+        assert "gap" in str(e.value)
     finally:
         idx.close()

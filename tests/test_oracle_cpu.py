@@ -135,3 +135,60 @@ def test_oracle_prefilter_truncated_scores_vs_reference():
         assert n_rescaled > 200          # the family members' lists really went through the rescaling
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+PREF_VARIANTS = [
+    ("s4", ["-s", "4.0", "--max-seqs", "300", "-c", "0.8", "--cov-mode", "2", "--min-ungapped-score", "15"], dict(sensitivity=4.0)),
+    ("s7.5", ["-s", "7.5", "--max-seqs", "300", "-c", "0.8", "--cov-mode", "2", "--min-ungapped-score", "15"], dict(sensitivity=7.5)),
+    ("cov0", ["-s", "5.7", "--max-seqs", "300", "-c", "0.5", "--cov-mode", "0", "--min-ungapped-score", "15"], dict(covThr=0.5, covMode=0)),
+    ("cov1", ["-s", "5.7", "--max-seqs", "300", "-c", "0.8", "--cov-mode", "1", "--min-ungapped-score", "15"], dict(covMode=1)),
+    ("nomask", ["-s", "5.7", "--mask", "0", "--max-seqs", "300", "-c", "0.8", "--cov-mode", "2", "--min-ungapped-score", "15"], dict(mask=0)),
+    ("nocomp", ["-s", "5.7", "--comp-bias-corr", "0", "--max-seqs", "300", "-c", "0.8", "--cov-mode", "2", "--min-ungapped-score", "15"], dict(compBias=0)),
+    ("tight", ["-s", "5.7", "--max-seqs", "20", "-c", "0.8", "--cov-mode", "2", "--min-ungapped-score", "30"], dict(maxSeqs=20, minDiagScore=30)),
+]
+
+
+@pytest.mark.parametrize("tag,flags,kw", PREF_VARIANTS, ids=[v[0] for v in PREF_VARIANTS])
+def test_oracle_prefilter_parameter_sweep(ref_setdb, tag, flags, kw):
+    """The oracle follows the reference's `prefilter` flags (sensitivity, coverage modes, masking, composition bias, tight cuts)."""
+    d = ref_setdb
+    db = os.path.join(d, "setDB")
+    out = os.path.join(d, "pref_" + tag)
+    helpers.run_ref(["prefilter", db, db, out] + flags + ["--threads", "2", "-v", "1"])
+    keys, buf, off = helpers.load_seqdb(db)
+    hits, _ = helpers.orc_prefilter(buf, off, buf, off, helpers.default_pref_params(**kw))
+    mine = helpers.hits_to_lines(hits, keys, keys)
+    ref = helpers.read_db(out)
+    for k in keys:
+        assert [l for l in ref[int(k)].split(b"\n") if l] == mine[int(k)], "query %d" % k
+
+
+ALIGN_VARIANTS = [
+    ("e1e-5", ["-e", "1e-5", "--min-aln-len", "30", "-c", "0.8", "--cov-mode", "2"], dict(evalThr=1e-5)),
+    ("cov0", ["-e", "10", "--min-aln-len", "0", "-c", "0.5", "--cov-mode", "0"], dict(covThr=0.5, covMode=0, minAlnLen=0)),
+    ("cov1", ["-e", "10", "--min-aln-len", "30", "-c", "0.7", "--cov-mode", "1"], dict(covThr=0.7, covMode=1)),
+    ("open", ["-e", "100", "--min-aln-len", "0", "-c", "0.0"], dict(covThr=0.0, evalThr=100.0, minAlnLen=0)),
+    ("minid", ["-e", "10", "--min-aln-len", "30", "-c", "0.8", "--cov-mode", "2", "--min-seq-id", "0.5"], dict(seqIdThr=0.5)),
+    ("nocomp", ["-e", "10", "--min-aln-len", "30", "-c", "0.8", "--cov-mode", "2", "--comp-bias-corr", "0"], dict(compBias=0)),
+]
+
+
+@pytest.mark.parametrize("tag,flags,kw", ALIGN_VARIANTS, ids=[v[0] for v in ALIGN_VARIANTS])
+def test_oracle_align_parameter_sweep(ref_setdb, tag, flags, kw):
+    """... and the `align` flags (E-value, coverage modes, identity, composition bias).  Gap costs other than 11/1 are NOT covered:
+    the reference estimates their Gumbel parameters by simulation (EvalueComputation.h:56-110); the product refuses them."""
+    d = ref_setdb
+    db = os.path.join(d, "setDB")
+    pref = os.path.join(d, "pref_all")
+    if not os.path.exists(pref + ".index"):
+        helpers.run_ref(["prefilter", db, db, pref, "-s", "5.7", "--max-seqs", "300", "-c", "0.0", "--min-ungapped-score", "15",
+                         "--threads", "2", "-v", "1"])
+    out = os.path.join(d, "res_" + tag)
+    helpers.run_ref(["align", db, db, pref, out, "-a", "1", "--alignment-mode", "2"] + flags + ["--threads", "2", "-v", "1"])
+    keys, buf, off = helpers.load_seqdb(db)
+    pq, pt = helpers.parse_pref_db(pref, keys, keys)
+    alns, bt, _ = helpers.orc_align(buf, off, keys, buf, off, keys, pq, pt, helpers.default_align_params(**kw))
+    mine = helpers.format_alignments(alns, bt, keys)
+    ref = helpers.read_db(out)
+    for k in keys:
+        assert [l for l in ref[int(k)].split(b"\n") if l] == mine[int(k)], "query %d" % k
