@@ -236,6 +236,8 @@ def run_ours(args, proteomes, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    if args.proteomes < world:
+        raise SystemExit("bench.py: %d query proteomes cannot be sharded over %d ranks (query sets are the sharding unit)" % (args.proteomes, world))
     buf, off, _ = synth.pack(proteomes)
     meta = synth.set_metadata(proteomes)
     n_total = len(off) - 1

@@ -13,8 +13,9 @@ import numpy as np
 
 
 def partition_sets(set_residues, world):
-    """Contiguous blocks of sets with ~equal residues: -> [(lo, hi)] * world (hi exclusive; blocks may be empty
-    when there are fewer sets than ranks).  Greedy split at the prefix-sum quantiles, every set in exactly one block."""
+    """Contiguous blocks of sets with ~equal residues: -> [(lo, hi)] * world (hi exclusive).  Split at the prefix-sum
+    quantiles; every set in exactly one block; no rank is left empty while another holds two sets (with fewer sets than
+    ranks the LAST ranks are empty, so rank 0 always has work)."""
     w = np.asarray(set_residues, dtype=np.float64)
     n = len(w)
     if world <= 0:
@@ -24,12 +25,14 @@ def partition_sets(set_residues, world):
     cuts = [0]
     for r in range(1, world):
         target = total * r / world
-        # first boundary whose prefix is >= target, but never before the previous cut
         c = int(np.searchsorted(pre, target, side="left"))
-        # choose the closer of c-1 / c
-        if c > 0 and c <= n and abs(pre[c - 1] - target) <= abs(pre[min(c, n)] - target):
+        # the closer of the two neighbouring boundaries
+        if 0 < c <= n and abs(pre[c - 1] - target) < abs(pre[c] - target):
             c -= 1
-        c = max(cuts[-1], min(c, n))
+        c = min(c, n)
+        lo_bound = min(cuts[-1] + 1, n)               # the previous rank gets at least one set while sets remain
+        hi_bound = max(n - (world - r), lo_bound)     # ... and so does every later rank, when there are enough sets
+        c = max(lo_bound, min(c, hi_bound))
         cuts.append(c)
     cuts.append(n)
     return [(cuts[i], cuts[i + 1]) for i in range(world)]

@@ -27,6 +27,12 @@ def test_partition_sets_covers_and_balances():
             loads = [w[a:b].sum() for a, b in blocks]
             assert max(loads) <= 1.35 * (w.sum() / world), (n_sets, world, loads)
     assert shard.partition_sets([5, 5, 5, 5], 2) == [(0, 2), (2, 4)]
+    # fewer sets than ranks: the first ranks get one set each, rank 0 is never empty
+    assert shard.partition_sets([100], 2) == [(0, 1), (1, 1)]
+    assert shard.partition_sets([1000, 1, 1], 3) == [(0, 1), (1, 2), (2, 3)]
+    assert shard.partition_sets([7, 7, 7], 8)[:4] == [(0, 1), (1, 2), (2, 3), (3, 3)]
+    for n_sets, world in ((20, 8), (9, 8), (8, 8)):
+        assert all(b > a for a, b in shard.partition_sets(np.ones(n_sets), world))
 
 
 def test_query_block():
@@ -127,3 +133,40 @@ def test_sharded_equals_unsharded_gloo(tmp_path, synth_small):
             for f in whole[k].dtype.names:
                 assert np.array_equal(m[k][f], whole[k][f]), (k, f)
         assert np.array_equal(m["pool"], whole["pool"])
+
+
+def _worker_empty(rank, world, port, tmpdir):
+    """Rank 1 owns no query set at all (fewer sets than ranks): its block is empty, the exchange must still work."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ex = shard.ResultExchange()
+        n = 5 if rank == 0 else 0
+        alns, pool, clusters, members = ex.carve(n, 3 * n, n // 2, n)
+        alns["query"] = np.arange(n)
+        alns["bt_off"] = 3 * np.arange(n)
+        alns["bt_len"] = 3
+        pool[...] = 77
+        clusters["first"] = 2 * np.arange(n // 2)
+        clusters["n"] = 2
+        members["aln"] = np.arange(n)
+        parts = ex.exchange(10 if rank == 0 else 0)
+        merged = shard.merge_results(parts)
+        assert [len(p["alns"]) for p in parts] == [5, 0]
+        assert list(merged["alns"]["query"]) == [10, 11, 12, 13, 14] and len(merged["pool"]) == 15
+        assert list(merged["clusters"]["first"]) == [0, 2] and list(merged["members"]["aln"]) == [0, 1, 2, 3, 4]
+        np.save(os.path.join(tmpdir, "ok_%d.npy" % rank), np.array([1]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exchange_with_an_empty_rank(tmp_path):
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_worker_empty, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert all(os.path.exists(os.path.join(tmp_path, "ok_%d.npy" % r)) for r in range(2))
