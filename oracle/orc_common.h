@@ -73,6 +73,11 @@ long orc_prefilter(const char *tSeq, const uint64_t *tOff, uint32_t nT,
                    const char *qSeq, const uint64_t *qOff, uint32_t nQ,
                    const orc_pref_params *par, orc_pref_hit *out, long outCap,
                    orc_pref_stats *stats, unsigned char *maskedOut /* optional, sum L_t bytes */);
+/* profile queries: profData = entries concatenated (25 bytes per column), qOff in columns; sameDB must be 0 */
+long orc_prefilter_profile(const char *tSeq, const uint64_t *tOff, uint32_t nT, const unsigned char *profData,
+                           const uint64_t *qOff, uint32_t nQ, const orc_pref_params *par, orc_pref_hit *out, long outCap,
+                           orc_pref_stats *stats);
+int orc_kmer_threshold_profile(float sensitivity, int kmerSize);
 
 #ifdef __cplusplus
 }

@@ -177,14 +177,119 @@ static int can_be_covered(float covThr, int covMode, float q, float t) {   /* Ut
     }
 }
 
+/* ---- profile queries (row a22 of SURVEY.md section 8: `prefilter <profileDB> <targetDB>` of the iterative search) ----
+ * A profile entry has 25 bytes per column (Sequence.h:458-471): 20 scores (x4 scaled), query letter, consensus, Neff, 2 gap
+ * bytes.  Sequence::mapProfile (Sequence.cpp:241-283) sorts every column's 20 scores descending with a fixed 20-input sorting
+ * network (Util::rankedDescSort20, Util.cpp:88-114; the comparator order decides ties, so it is kept as a table), the
+ * k-mer generator then combines the six columns of a spaced window list by list (KmerGenerator::setDivideStrategy(ScoreMatrix**)
+ * :30-39, generateKmerList :107-183, calculateArrayProduct :186-216), the diagonal scorer uses score/4 with X = 0, there is no
+ * composition bias (QueryMatcher.cpp:91-96), the k-mer threshold comes from the profile table (Prefiltering.cpp:1019-1048) and
+ * the target index keeps every k-mer (threshold 0, Prefiltering.cpp:525-527). */
+static const unsigned char SORT20[][2] = {
+    {0,16},{1,17},{2,18},{3,19},{4,12},{5,13},{6,14},{7,15},
+    {0,8},{1,9},{2,10},{3,11},
+    {8,16},{9,17},{10,18},{11,19},{0,4},{1,5},{2,6},{3,7},
+    {8,12},{9,13},{10,14},{11,15},{4,16},{5,17},{6,18},{7,19},{0,2},{1,3},
+    {4,8},{5,9},{6,10},{7,11},{12,16},{13,17},{14,18},{15,19},{0,1},
+    {4,6},{5,7},{8,10},{9,11},{12,14},{13,15},{16,18},{17,19},
+    {2,16},{3,17},{6,12},{7,13},{18,19},
+    {2,8},{3,9},{10,16},{11,17},
+    {2,4},{3,5},{6,8},{7,9},{10,12},{11,13},{14,16},{15,17},
+    {2,3},{4,5},{6,7},{8,9},{10,11},{12,13},{14,15},{16,17},
+    {1,16},{3,18},{5,12},{7,14},
+    {1,8},{3,10},{9,16},{11,18},
+    {1,4},{3,6},{5,8},{7,10},{9,12},{11,14},{13,16},{15,18},
+    {1,2},{3,4},{5,6},{7,8},{9,10},{11,12},{13,14},{15,16},{17,18}};
+
+static void ranked_desc_sort20(short *val, unsigned int *index) {
+    for (size_t c = 0; c < sizeof SORT20 / sizeof SORT20[0]; c++) {
+        const int x = SORT20[c][0], y = SORT20[c][1];
+        if (val[x] < val[y]) {
+            short t1 = val[x]; val[x] = val[y]; val[y] = t1;
+            unsigned int t2 = index[x]; index[x] = index[y]; index[y] = t2;
+        }
+    }
+}
+
+int orc_kmer_threshold_profile(float sensitivity, int kmerSize) {     /* Prefiltering.cpp:1033-1046, no context pseudo counts */
+    float thr;
+    if (kmerSize == 5) { float base = 108.8; thr = base - (sensitivity * 4.7); }
+    else if (kmerSize == 6) { float base = 134.35; thr = base - (sensitivity * 6.15); }
+    else { float base = 149.15; thr = base - (sensitivity * 6.85); }
+    return (int)thr;
+}
+
+#define ORC_MAX_KMER_RESULT ((size_t)262144 * 32)
+
+/* similar k-mers of one profile window: six sorted columns combined list by list; returns the list length, order as produced */
+static size_t profile_kmer_list(short sc[KMER][20], unsigned int ix[KMER][20], short thr, short **bufS, size_t **bufI,
+                                const size_t **result) {
+    static const size_t POW20[KMER] = {1, 20, 400, 8000, 160000, 3200000};
+    short rest[KMER];
+    rest[KMER - 1] = 0;
+    for (int i = KMER - 1; i >= 1; i--) rest[i - 1] = (short)(sc[i][0] + rest[i]);
+    short cutoff1 = (short)(thr - rest[0]);
+    for (int pos = 0; pos < 20 && sc[0][pos] >= cutoff1; pos++) bufI[1][pos] = ix[0][pos];
+    const short *inS = sc[0];
+    const size_t *inI = bufI[1];
+    size_t n = 20;
+    int i;
+    for (i = 0; i < KMER - 1; i++) {
+        short *outS = bufS[i % 2];
+        size_t *outI = bufI[i % 2];
+        size_t cnt = 0;
+        int full = 0;
+        for (size_t a = 0; a < n; a++) {
+            const short sa = inS[a];
+            if (sa < cutoff1) break;
+            const short cutoff2 = (short)(thr - sa - rest[i + 1]);
+            for (int j = 0; j < 20 && cnt + 1 < ORC_MAX_KMER_RESULT && sc[i + 1][j] >= cutoff2; j++) {
+                outS[cnt] = (short)(sa + sc[i + 1][j]);
+                outI[cnt] = inI[a] + (size_t)ix[i + 1][j] * POW20[i + 1];
+                cnt++;
+            }
+            if (cnt + 1 >= ORC_MAX_KMER_RESULT) { full = 1; break; }
+        }
+        (void)full;
+        inS = outS;
+        inI = outI;
+        cutoff1 = -1000;
+        n = cnt;
+    }
+    *result = bufI[(i - 1) % 2];
+    return n;
+}
+
+static long prefilter_core(const char *tSeq, const uint64_t *tOff, uint32_t nT,
+                           const char *qSeq, const uint64_t *qOff, uint32_t nQ,
+                           const orc_pref_params *par, orc_pref_hit *out, long outCap,
+                           orc_pref_stats *stats, unsigned char *maskedOut, const unsigned char *profData);
+
 long orc_prefilter(const char *tSeq, const uint64_t *tOff, uint32_t nT,
                    const char *qSeq, const uint64_t *qOff, uint32_t nQ,
                    const orc_pref_params *par, orc_pref_hit *out, long outCap,
                    orc_pref_stats *stats, unsigned char *maskedOut) {
+    return prefilter_core(tSeq, tOff, nT, qSeq, qOff, nQ, par, out, outCap, stats, maskedOut, NULL);
+}
+
+/* profData: the profile entries concatenated, 25 bytes per column; qOff in COLUMNS */
+long orc_prefilter_profile(const char *tSeq, const uint64_t *tOff, uint32_t nT,
+                           const unsigned char *profData, const uint64_t *qOff, uint32_t nQ,
+                           const orc_pref_params *par, orc_pref_hit *out, long outCap, orc_pref_stats *stats) {
+    return prefilter_core(tSeq, tOff, nT, NULL, qOff, nQ, par, out, outCap, stats, NULL, profData);
+}
+
+static long prefilter_core(const char *tSeq, const uint64_t *tOff, uint32_t nT,
+                           const char *qSeq, const uint64_t *qOff, uint32_t nQ,
+                           const orc_pref_params *par, orc_pref_hit *out, long outCap,
+                           orc_pref_stats *stats, unsigned char *maskedOut, const unsigned char *profData) {
     orc_submat kmat, umat;
-    orc_build_submat(1, 8.0f, -0.2f, &kmat);      /* Prefiltering.cpp:68 seed matrix VTML80 x8  */
+    const int isProfile = profData != NULL;
+    /* Prefiltering.cpp:67-77: sequence queries seed with VTML80 x8, profile queries take BLOSUM62 x8 (background distributions and
+     * the masker's likelihood ratios then come from BLOSUM62, so the masked target residues differ between the two modes) */
+    orc_build_submat(isProfile ? 0 : 1, 8.0f, -0.2f, &kmat);
     orc_build_submat(0, 2.0f, -0.2f, &umat);      /* Prefiltering.cpp:69 diagonal matrix BLOSUM62 x2 */
-    const int kmerThr = orc_kmer_threshold(par->sensitivity, KMER);
+    const int kmerThr = isProfile ? orc_kmer_threshold_profile(par->sensitivity, KMER) : orc_kmer_threshold(par->sensitivity, KMER);
     orc_pref_stats st;
     memset(&st, 0, sizeof st);
 
@@ -197,9 +302,17 @@ long orc_prefilter(const char *tSeq, const uint64_t *tOff, uint32_t nT,
     if (maskedOut) memcpy(maskedOut, tres, (size_t)tOff[nT]);
 
     index_t ix;
-    build_index(tres, tOff, nT, kmat.sub, kmerThr, &ix);
+    build_index(tres, tOff, nT, kmat.sub, isProfile ? 0 : kmerThr, &ix);
     ext3_t e3;
-    build_ext3(kmat.sub, &e3);
+    e3.score = NULL; e3.index = NULL;
+    if (!isProfile) build_ext3(kmat.sub, &e3);
+    short *pkS[2] = {NULL, NULL};
+    size_t *pkI[2] = {NULL, NULL};
+    if (isProfile)
+        for (int b = 0; b < 2; b++) {
+            pkS[b] = (short *)malloc(sizeof(short) * ORC_MAX_KMER_RESULT);
+            pkI[b] = (size_t *)malloc(sizeof(size_t) * ORC_MAX_KMER_RESULT);
+        }
 
     int maxLq = 0;
     for (uint32_t q = 0; q < nQ; q++) {
@@ -224,8 +337,18 @@ long orc_prefilter(const char *tSeq, const uint64_t *tOff, uint32_t nT,
 
     for (uint32_t q = 0; q < nQ; q++) {
         const int L = (int)(qOff[q + 1] - qOff[q]);
-        orc_map_sequence(qSeq + qOff[q], L, qres);
+        const unsigned char *pcol = isProfile ? profData + (size_t)qOff[q] * 25 : NULL;
         st.queryResidues += (uint64_t)L;
+        if (isProfile) {
+            /* Sequence::mapProfile: query letters, no composition bias; diagonal profile = score / 4, X column 0 */
+            for (int p = 0; p < L; p++) {
+                qres[p] = pcol[(size_t)p * 25 + 20];
+                bias[p] = 0.0f;
+                for (int a = 0; a < 20; a++) prof[p * 21 + a] = (signed char)((short)(signed char)pcol[(size_t)p * 25 + a] / 4);
+                prof[p * 21 + 20] = 0;
+            }
+        } else {
+        orc_map_sequence(qSeq + qOff[q], L, qres);
         /* QueryMatcher::matchQuery (QueryMatcher.cpp:85-107): bias from the SEED matrix */
         if (par->compBias) orc_comp_bias(&kmat, qres, L, bias, 1.0f);
         else memset(bias, 0, sizeof(float) * (size_t)L);
@@ -236,6 +359,7 @@ long orc_prefilter(const char *tSeq, const uint64_t *tOff, uint32_t nT,
             signed char corr = (signed char)b;
             for (int a = 0; a < 21; a++)
                 prof[p * 21 + a] = (signed char)(umat.sub[qres[p] * 21 + a] + corr);
+        }
         }
         /* QueryMatcher::match (QueryMatcher.cpp:213-346) + KmerGenerator (KmerGenerator.cpp:107-216) */
         nHit = 0;
@@ -251,6 +375,32 @@ long orc_prefilter(const char *tSeq, const uint64_t *tOff, uint32_t nT,
             if (hasX) continue;
             short b = (short)((bsum < 0.0) ? bsum - 0.5 : bsum + 0.5);
             short thr = (short)(kmerThr - b > 0 ? kmerThr - b : 0);
+            if (isProfile) {
+                short sc[KMER][20];
+                unsigned int ixs[KMER][20];
+                for (int k = 0; k < KMER; k++) {
+                    const unsigned char *col = pcol + (size_t)(p + SEED_POS[k]) * 25;
+                    for (int a = 0; a < 20; a++) { sc[k][a] = (short)(signed char)col[a]; ixs[k][a] = (unsigned int)a; }
+                    ranked_desc_sort20(sc[k], ixs[k]);
+                }
+                const size_t *list;
+                const size_t nList = profile_kmer_list(sc, ixs, thr, pkS, pkI, &list);
+                for (size_t c = 0; c < nList; c++) {
+                    const uint32_t kmer = (uint32_t)list[c];
+                    st.probes++;
+                    uint32_t lo = ix.off[kmer], hi = ix.off[kmer + 1];
+                    if (nHit + (hi - lo) > hitCap) {
+                        while (nHit + (hi - lo) > hitCap) hitCap *= 2;
+                        hits = (hit_t *)realloc(hits, sizeof(hit_t) * hitCap);
+                    }
+                    for (uint32_t e = lo; e < hi; e++) {
+                        hits[nHit].id = ix.ent[e].seq;
+                        hits[nHit].diag = (uint16_t)(p - ix.ent[e].pos);
+                        nHit++;
+                    }
+                }
+                continue;
+            }
             uint32_t i1 = km[0] + 20u * km[1] + 400u * km[2];
             uint32_t i2 = km[3] + 20u * km[4] + 400u * km[5];
             const short *s1 = e3.score + (size_t)i1 * N3, *s2 = e3.score + (size_t)i2 * N3;
@@ -422,5 +572,6 @@ long orc_prefilter(const char *tSeq, const uint64_t *tOff, uint32_t nT,
     if (stats) *stats = st;
     free(tres); free(ix.off); free(ix.ent); free(e3.score); free(e3.index);
     free(qres); free(bias); free(prof); free(hits); free(cand); free(tmp); free(last); free(res);
+    for (int b = 0; b < 2; b++) { free(pkS[b]); free(pkI[b]); }
     return nOut;
 }

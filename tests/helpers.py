@@ -154,6 +154,37 @@ def orc_prefilter(tbuf, toff, qbuf, qoff, params, want_masked=False):
     return (out[:n], st, masked) if want_masked else (out[:n], st)
 
 
+def load_profiledb(path):
+    """Profile DB (dbtype 2) -> (keys, profile bytes (np.uint8, 25 per column, entries concatenated), offsets in columns).
+    Entry = L * 25 bytes + terminator (Sequence.h:458-471); order = ascending data offset like load_seqdb."""
+    idx = sorted(read_index(path), key=lambda e: e[1])
+    raw = np.frombuffer(open(path, "rb").read(), dtype=np.uint8)
+    keys = np.array([e[0] for e in idx], dtype=np.uint32)
+    cols = np.array([(e[2] - 1) // 25 for e in idx], dtype=np.uint64)
+    off = np.zeros(len(idx) + 1, dtype=np.uint64)
+    np.cumsum(cols, out=off[1:])
+    buf = np.empty(int(off[-1]) * 25, dtype=np.uint8)
+    for i, (k, o, l) in enumerate(idx):
+        n = int(cols[i]) * 25
+        buf[int(off[i]) * 25:int(off[i]) * 25 + n] = raw[o:o + n]
+    return keys, buf, off
+
+
+def orc_prefilter_profile(tbuf, toff, pbuf, poff, params):
+    lib = oracle()
+    lib.orc_prefilter_profile.restype = ctypes.c_long
+    nT, nQ = len(toff) - 1, len(poff) - 1
+    cap = max(1024, nQ * (params.maxSeqs + 1))
+    out = np.zeros(cap, dtype=ORC_HIT_DTYPE)
+    stats = OrcPrefStats()
+    n = lib.orc_prefilter_profile(tbuf.ctypes.data_as(ctypes.c_char_p), toff.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(nT),
+                                  pbuf.ctypes.data_as(ctypes.c_void_p), poff.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(nQ),
+                                  ctypes.byref(params), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(cap), ctypes.byref(stats))
+    if n < 0:
+        raise RuntimeError("orc_prefilter_profile failed: %d" % n)
+    return out[:n], {f[0]: getattr(stats, f[0]) for f in OrcPrefStats._fields_}
+
+
 def hits_to_lines(hits, qkeys, tkeys):
     """-> {queryKey: [b'tKey\\tscore\\tdiag', ...]} in output order (prefilterHitToBuffer QueryMatcher.h:118-130)."""
     d = {int(k): [] for k in qkeys}

@@ -192,3 +192,33 @@ def test_oracle_align_parameter_sweep(ref_setdb, tag, flags, kw):
     ref = helpers.read_db(out)
     for k in keys:
         assert [l for l in ref[int(k)].split(b"\n") if l] == mine[int(k)], "query %d" % k
+
+
+@pytest.fixture(scope="module")
+def ref_profile_db(ref_setdb):
+    """Profile DB made by the reference itself (prefilter -> align -e 0.001 -> result2profile), as iteration 1 of
+    `search --num-iterations` does (lib/mmseqs/data/workflow/blastpgp.sh:73-133)."""
+    d = ref_setdb
+    db = os.path.join(d, "setDB")
+    if not os.path.exists(os.path.join(d, "prof0.index")):
+        helpers.run_ref(["prefilter", db, db, os.path.join(d, "it0_pref"), "-s", "5.7", "--max-seqs", "300", "--threads", "2", "-v", "1"])
+        helpers.run_ref(["align", db, db, os.path.join(d, "it0_pref"), os.path.join(d, "it0_aln"), "-a", "1", "-e", "0.001", "--threads", "2", "-v", "1"])
+        helpers.run_ref(["result2profile", db, db, os.path.join(d, "it0_aln"), os.path.join(d, "prof0"), "--threads", "2", "-v", "1"])
+    return os.path.join(d, "prof0")
+
+
+def test_oracle_profile_prefilter_vs_reference(ref_setdb, ref_profile_db):
+    """Row a22 groundwork: `prefilter <profileDB> <targetDB>` -- per-column sorted score lists combined into similar k-mers,
+    BLOSUM62-based masking, index threshold 0, profile/4 diagonal scores -- restated by the oracle, hit for hit."""
+    d = ref_setdb
+    db = os.path.join(d, "setDB")
+    assert open(ref_profile_db + ".dbtype", "rb").read() == b"\x02\x00\x00\x00"      # profile, no context pseudo counts
+    helpers.run_ref(["prefilter", ref_profile_db, db, os.path.join(d, "prof_pref"), "-s", "5.7", "--max-seqs", "300", "--threads", "2", "-v", "1"])
+    keys, buf, off = helpers.load_seqdb(db)
+    pkeys, pbuf, poff = helpers.load_profiledb(ref_profile_db)
+    hits, st = helpers.orc_prefilter_profile(buf, off, pbuf, poff, helpers.default_pref_params(sameDB=0, covThr=0.0))
+    mine = helpers.hits_to_lines(hits, pkeys, keys)
+    ref = helpers.read_db(os.path.join(d, "prof_pref"))
+    for k in pkeys:
+        assert [l for l in ref[int(k)].split(b"\n") if l] == mine[int(k)], "profile %d" % k
+    assert len(hits) > len(pkeys) and st["probes"] > 10 ** 6
