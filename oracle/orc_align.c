@@ -258,11 +258,39 @@ static int cmp_result(const void *a, const void *b) {   /* Matcher::compareHits 
     return 0;
 }
 
+static long align_core(const char *tSeq, const uint64_t *tOff, const uint32_t *tKeys, uint32_t nT,
+                       const char *qSeq, const uint64_t *qOff, const uint32_t *qKeys, uint32_t nQ,
+                       const uint32_t *pairQ, const uint32_t *pairT, uint64_t nPairs, uint64_t dbResidues,
+                       const orc_align_params *par, orc_aln *out, long outCap, char *btPool, uint64_t btCap,
+                       orc_align_stats *stats, const unsigned char *profData);
+
 long orc_align(const char *tSeq, const uint64_t *tOff, const uint32_t *tKeys, uint32_t nT,
                const char *qSeq, const uint64_t *qOff, const uint32_t *qKeys, uint32_t nQ,
                const uint32_t *pairQ, const uint32_t *pairT, uint64_t nPairs, uint64_t dbResidues,
                const orc_align_params *par, orc_aln *out, long outCap, char *btPool, uint64_t btCap,
                orc_align_stats *stats) {
+    return align_core(tSeq, tOff, tKeys, nT, qSeq, qOff, qKeys, nQ, pairQ, pairT, nPairs, dbResidues, par, out, outCap, btPool, btCap,
+                      stats, NULL);
+}
+
+/* Profile queries (row a22): profData = profile entries concatenated, 25 bytes per column (Sequence.h:458-471), qOff in columns.
+ * ssw_init for profiles (StripedSmithWaterman.cpp:1229-1282): score(row i, letter a) = profile score / 4 (Sequence.cpp:270-274),
+ * X scores 0, no composition bias, bias = |min over the 20 x L scores|; identities are counted against the profile's query
+ * letter (computerBacktrace :548-581). */
+long orc_align_profile(const char *tSeq, const uint64_t *tOff, const uint32_t *tKeys, uint32_t nT,
+                       const unsigned char *profData, const uint64_t *qOff, const uint32_t *qKeys, uint32_t nQ,
+                       const uint32_t *pairQ, const uint32_t *pairT, uint64_t nPairs, uint64_t dbResidues,
+                       const orc_align_params *par, orc_aln *out, long outCap, char *btPool, uint64_t btCap,
+                       orc_align_stats *stats) {
+    return align_core(tSeq, tOff, tKeys, nT, NULL, qOff, qKeys, nQ, pairQ, pairT, nPairs, dbResidues, par, out, outCap, btPool, btCap,
+                      stats, profData);
+}
+
+static long align_core(const char *tSeq, const uint64_t *tOff, const uint32_t *tKeys, uint32_t nT,
+                       const char *qSeq, const uint64_t *qOff, const uint32_t *qKeys, uint32_t nQ,
+                       const uint32_t *pairQ, const uint32_t *pairT, uint64_t nPairs, uint64_t dbResidues,
+                       const orc_align_params *par, orc_aln *out, long outCap, char *btPool, uint64_t btCap,
+                       orc_align_stats *stats, const unsigned char *profData) {
     orc_submat m;
     orc_build_submat(0, 2.0f, par->scoreBias, &m);      /* Alignment.cpp:152 */
     signed char mat[21 * 21];
@@ -288,6 +316,21 @@ long orc_align(const char *tSeq, const uint64_t *tOff, const uint32_t *tKeys, ui
         uint64_t pe = p;
         while (pe < nPairs && pairQ[pe] == q) pe++;
         const int Lq = (int)(qOff[q + 1] - qOff[q]);
+        int bias;
+        if (profData) {
+            const unsigned char *pcol = profData + (size_t)qOff[q] * 25;
+            int minProf = 0;
+            for (int i = 0; i < Lq; i++) {
+                qres[i] = pcol[(size_t)i * 25 + 20];
+                for (int a = 0; a < 20; a++) {
+                    const signed char v = (signed char)((short)(signed char)pcol[(size_t)i * 25 + a] / 4);
+                    rowScore[i * 21 + a] = v;
+                    if (v < minProf) minProf = v;
+                }
+                rowScore[i * 21 + 20] = 0;
+            }
+            bias = abs(minProf);
+        } else {
         orc_map_sequence(qSeq + qOff[q], Lq, qres);
         /* SmithWaterman::ssw_init (StripedSmithWaterman.cpp:1216-1345) */
         int minCb = 0;
@@ -298,9 +341,10 @@ long orc_align(const char *tSeq, const uint64_t *tOff, const uint32_t *tKeys, ui
                 if (cb[i] < minCb) minCb = cb[i];
             }
         } else memset(cb, 0, (size_t)Lq);
-        const int bias = abs(minMat) + abs(minCb);
+        bias = abs(minMat) + abs(minCb);
         for (int i = 0; i < Lq; i++)
             for (int a = 0; a < 21; a++) rowScore[i * 21 + a] = (signed char)(mat[a * 21 + qres[i]] + cb[i]);
+        }
         const long firstOut = nOut;
         for (uint64_t k = p; k < pe; k++) {
             const uint32_t t = pairT[k];

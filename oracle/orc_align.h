@@ -44,6 +44,11 @@ long orc_align(const char *tSeq, const uint64_t *tOff, const uint32_t *tKeys, ui
                const uint32_t *pairQ, const uint32_t *pairT, uint64_t nPairs, uint64_t dbResidues,
                const orc_align_params *par, orc_aln *out, long outCap, char *btPool, uint64_t btCap,
                orc_align_stats *stats);
+long orc_align_profile(const char *tSeq, const uint64_t *tOff, const uint32_t *tKeys, uint32_t nT,
+                       const unsigned char *profData, const uint64_t *qOff, const uint32_t *qKeys, uint32_t nQ,
+                       const uint32_t *pairQ, const uint32_t *pairT, uint64_t nPairs, uint64_t dbResidues,
+                       const orc_align_params *par, orc_aln *out, long outCap, char *btPool, uint64_t btCap,
+                       orc_align_stats *stats);
 int orc_format_alignment(const orc_aln *r, const char *btPool, char *buf, int cap);
 
 #ifdef __cplusplus

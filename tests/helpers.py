@@ -254,9 +254,11 @@ def default_align_params(**kw):
     return p
 
 
-def orc_align(tbuf, toff, tkeys, qbuf, qoff, qkeys, pair_q, pair_t, params, db_residues=None):
+def orc_align(tbuf, toff, tkeys, qbuf, qoff, qkeys, pair_q, pair_t, params, db_residues=None, profile=False):
+    """profile=True: qbuf holds profile entries (25 bytes per column), qoff counts columns (orc_align_profile)."""
     lib = oracle()
     lib.orc_align.restype = ctypes.c_long
+    lib.orc_align_profile.restype = ctypes.c_long
     nT, nQ = len(toff) - 1, len(qoff) - 1
     pair_q = np.ascontiguousarray(pair_q, dtype=np.uint32)
     pair_t = np.ascontiguousarray(pair_t, dtype=np.uint32)
@@ -272,7 +274,8 @@ def orc_align(tbuf, toff, tkeys, qbuf, qoff, qkeys, pair_q, pair_t, params, db_r
     bt_cap = int((lens_t[pair_t] + lens_q[pair_q]).sum()) + 64
     bt = np.zeros(bt_cap, dtype=np.uint8)
     stats = OrcAlignStats()
-    n = lib.orc_align(tbuf.ctypes.data_as(ctypes.c_char_p), toff.ctypes.data_as(ctypes.c_void_p), tkeys.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(nT),
+    fn = lib.orc_align_profile if profile else lib.orc_align
+    n = fn(tbuf.ctypes.data_as(ctypes.c_char_p), toff.ctypes.data_as(ctypes.c_void_p), tkeys.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(nT),
                       qbuf.ctypes.data_as(ctypes.c_char_p), qoff.ctypes.data_as(ctypes.c_void_p), qkeys.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(nQ),
                       pair_q.ctypes.data_as(ctypes.c_void_p), pair_t.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(len(pair_q)),
                       ctypes.c_uint64(db_residues), ctypes.byref(params), out.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(cap),

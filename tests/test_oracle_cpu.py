@@ -222,3 +222,24 @@ def test_oracle_profile_prefilter_vs_reference(ref_setdb, ref_profile_db):
     for k in pkeys:
         assert [l for l in ref[int(k)].split(b"\n") if l] == mine[int(k)], "profile %d" % k
     assert len(hits) > len(pkeys) and st["probes"] > 10 ** 6
+
+
+def test_oracle_profile_align_vs_reference(ref_setdb, ref_profile_db):
+    """Row a22 groundwork: `align <profileDB> <targetDB>` (profile/4 score rows, X = 0, no composition bias, striped-SW semantics,
+    traceback, identities against the profile's query letter) restated by the oracle: result lines identical."""
+    d = ref_setdb
+    db = os.path.join(d, "setDB")
+    pref = os.path.join(d, "prof_pref")
+    if not os.path.exists(pref + ".index"):
+        helpers.run_ref(["prefilter", ref_profile_db, db, pref, "-s", "5.7", "--max-seqs", "300", "--threads", "2", "-v", "1"])
+    helpers.run_ref(["align", ref_profile_db, db, pref, os.path.join(d, "prof_aln"), "-a", "1", "-e", "0.001", "--threads", "2", "-v", "1"])
+    keys, buf, off = helpers.load_seqdb(db)
+    pkeys, pbuf, poff = helpers.load_profiledb(ref_profile_db)
+    pq, pt = helpers.parse_pref_db(pref, pkeys, keys)
+    alns, bt, st = helpers.orc_align(buf, off, keys, pbuf, poff, pkeys, pq, pt,
+                                     helpers.default_align_params(evalThr=0.001, covThr=0.0, minAlnLen=0, sameDB=0), profile=True)
+    mine = helpers.format_alignments(alns, bt, pkeys)
+    ref = helpers.read_db(os.path.join(d, "prof_aln"))
+    for k in pkeys:
+        assert [l for l in ref[int(k)].split(b"\n") if l] == mine[int(k)], "profile %d" % k
+    assert st["passed"] > len(pkeys) and st["wordMode"] > 0
