@@ -3,10 +3,15 @@
 //   sdb200 summarizeresults <qSetDB> <tSetDB> <clustersDB> <out.tsv>     src/util/SummarizeResults.cpp:14-130
 //   sdb200 filterdb <inDB> <outDB> --trim-to-one-column                   first column of every line (clusters -> clu_to_seq)
 //   sdb200 swapdb <inDB> <outDB>                                          invert a one-column DB (clu_to_seq -> seq_to_clu)
+// and the two text modules of the iterative search glue (lib/mmseqs/data/workflow/blastpgp.sh:83-124; the profile search
+// itself is not built yet):
+//   sdb200 subtractdbs <leftDB> <rightDB> <outDB> [--e-profile X]         lib/mmseqs/src/util/subtractdbs.cpp:20-110
+//   sdb200 mergedbs <queryDB> <outDB> <db1> <db2> ...                     lib/mmseqs/src/util/mergedbs.cpp:8-69
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -194,5 +199,107 @@ int modSummarizeresults(int argc, char **argv) {
     }
     if (!out.empty()) fwrite(out.data(), 1, out.size(), f);
     fclose(f);
+    return EXIT_SUCCESS;
+}
+
+
+namespace {
+// key (first column) and, for alignment lines (>= 10 columns), the E-value (4th column) of one result line
+void lineKeyEvalue(const char *ls, const char *le, uint32_t &key, double &evalue) {
+    key = (uint32_t)strtoul(ls, nullptr, 10);
+    evalue = 0.0;
+    int columns = 0;
+    const char *col4 = nullptr;
+    const char *p = ls;
+    while (p < le) {
+        while (p < le && (*p == '\t' || *p == ' ')) p++;
+        if (p >= le) break;
+        columns++;
+        if (columns == 4) col4 = p;
+        while (p < le && *p != '\t' && *p != ' ') p++;
+    }
+    if (columns >= 10 && col4) evalue = strtod(col4, nullptr);
+}
+}  // namespace
+
+// lines of the left entry whose key does not occur in the right entry of the same DB key (both sides only count lines with
+// E-value <= threshold; prefilter lines have no E-value and always count)
+int modSubtractdbs(int argc, char **argv) {
+    std::map<std::string, std::string> flags;
+    std::vector<std::string> pos = positional(argc, argv, &flags);
+    if (pos.size() != 3) fail("usage: sdb200 subtractdbs <leftDB> <rightDB> <outDB> [--e-profile X]");
+    const double thr = flags.count("--e-profile") ? strtod(flags["--e-profile"].c_str(), nullptr) : 0.001;
+    sddb::Db left, right;
+    std::string err;
+    if (!left.open(pos[0], err)) fail(err);
+    if (!right.open(pos[1], err)) fail(err);
+    std::map<uint32_t, const sddb::Entry *> rightByKey;
+    for (const sddb::Entry &e : right.index) rightByKey[e.key] = &e;
+    sddb::DbWriter w(pos[2], left.dbtype >= 0 ? left.dbtype : sddb::DBTYPE_GENERIC_DB);
+    std::string buf;
+    auto forLines = [](const char *p, const char *end, const std::function<void(const char *, const char *)> &fn) {
+        while (p < end) {
+            const char *ls = p;
+            while (p < end && *p != '\n') p++;
+            const char *le = p;
+            if (p < end) p++;
+            fn(ls, le < end ? le + 1 : le);
+        }
+    };
+    for (const sddb::Entry &e : left.index) {
+        std::map<uint32_t, bool> keep;
+        const char *lp = left.ptr(e), *lend = lp + left.size(e);
+        forLines(lp, lend, [&](const char *ls, const char *le) {
+            uint32_t k; double ev;
+            lineKeyEvalue(ls, le, k, ev);
+            if (ev <= thr) keep[k] = true;
+        });
+        auto it = rightByKey.find(e.key);
+        if (it != rightByKey.end()) {
+            const char *rp = right.ptr(*it->second), *rend = rp + right.size(*it->second);
+            forLines(rp, rend, [&](const char *ls, const char *le) {
+                uint32_t k; double ev;
+                lineKeyEvalue(ls, le, k, ev);
+                if (ev <= thr) keep[k] = false;
+            });
+        }
+        buf.clear();
+        forLines(lp, lend, [&](const char *ls, const char *le) {
+            const uint32_t k = (uint32_t)strtoul(ls, nullptr, 10);
+            auto kt = keep.find(k);
+            if (kt != keep.end() && kt->second) buf.append(ls, (size_t)(le - ls));
+        });
+        w.add(e.key, buf);
+    }
+    if (!w.close(err)) fail(err);
+    return EXIT_SUCCESS;
+}
+
+// per key of the query DB: the entries of db1, db2, ... concatenated in that order
+int modMergedbs(int argc, char **argv) {
+    std::vector<std::string> pos = positional(argc, argv);
+    if (pos.size() < 4) fail("usage: sdb200 mergedbs <queryDB> <outDB> <db1> <db2> [...]");
+    sddb::Db q;
+    std::string err;
+    if (!q.open(pos[0], err)) fail(err);
+    const size_t n = pos.size() - 2;
+    std::vector<sddb::Db> dbs(n);
+    std::vector<std::map<uint32_t, const sddb::Entry *>> byKey(n);
+    for (size_t i = 0; i < n; i++) {
+        if (!dbs[i].open(pos[i + 2], err)) fail(err);
+        for (const sddb::Entry &e : dbs[i].index) byKey[i][e.key] = &e;
+    }
+    sddb::DbWriter w(pos[1], dbs[0].dbtype >= 0 ? dbs[0].dbtype : sddb::DBTYPE_GENERIC_DB);
+    std::string buf;
+    for (const sddb::Entry &qe : q.index) {
+        buf.clear();
+        for (size_t i = 0; i < n; i++) {
+            auto it = byKey[i].find(qe.key);
+            if (it == byKey[i].end()) continue;
+            buf.append(dbs[i].ptr(*it->second), dbs[i].size(*it->second));
+        }
+        w.add(qe.key, buf);
+    }
+    if (!w.close(err)) fail(err);
     return EXIT_SUCCESS;
 }

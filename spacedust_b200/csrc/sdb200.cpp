@@ -457,10 +457,12 @@ int modCreatesetdb(int argc, char **argv);
 int modSummarizeresults(int argc, char **argv);
 int modFilterdb(int argc, char **argv);
 int modSwapdb(int argc, char **argv);
+int modSubtractdbs(int argc, char **argv);
+int modMergedbs(int argc, char **argv);
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "sdb200 (libsdgpu %d): createsetdb | prefilter | align | clustersearch | summarizeresults | filterdb | swapdb\n", sd_version());
+        fprintf(stderr, "sdb200 (libsdgpu %d): createsetdb | prefilter | align | clustersearch | summarizeresults | filterdb | swapdb | subtractdbs | mergedbs\n", sd_version());
         return EXIT_FAILURE;
     }
     const std::string mod = argv[1];
@@ -471,5 +473,7 @@ int main(int argc, char **argv) {
     if (mod == "summarizeresults") return modSummarizeresults(argc, argv);
     if (mod == "filterdb") return modFilterdb(argc, argv);
     if (mod == "swapdb") return modSwapdb(argc, argv);
+    if (mod == "subtractdbs") return modSubtractdbs(argc, argv);
+    if (mod == "mergedbs") return modMergedbs(argc, argv);
     die("unknown module '%s'", mod.c_str());
 }

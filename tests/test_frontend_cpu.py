@@ -175,3 +175,29 @@ def test_db_reader_accepts_split_data_files():
         assert got == {0: b"3\n5\n", 1: b"7\n"}
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def test_iteration_glue_modules_vs_reference(synth_small):
+    """subtractdbs / mergedbs (text glue of the iterative search, blastpgp.sh:83-124) on the reference's own DBs."""
+    if not helpers.have_ref():
+        pytest.skip("oracle/_ref/spacedust not built")
+    d = tempfile.mkdtemp(prefix="sdfe_")
+    try:
+        paths = synth.write_fasta(synth_small, os.path.join(d, "faa"))
+        db = os.path.join(d, "setDB")
+        helpers.run_ref(["createsetdb"] + paths + [db, os.path.join(d, "tmp"), "-v", "1"])
+        helpers.run_ref(["prefilter", db, db, os.path.join(d, "pref"), "-s", "5.7", "--threads", "2", "-v", "1"])
+        helpers.run_ref(["align", db, db, os.path.join(d, "pref"), os.path.join(d, "aln"), "-a", "1", "-e", "0.001", "--threads", "2", "-v", "1"])
+        helpers.run_ref(["subtractdbs", os.path.join(d, "pref"), os.path.join(d, "aln"), os.path.join(d, "sub_ref"), "--e-profile", "0.001",
+                         "--threads", "2", "-v", "1"])
+        subprocess.run([SDB200, "subtractdbs", os.path.join(d, "pref"), os.path.join(d, "aln"), os.path.join(d, "sub_mine"), "--e-profile", "0.001"],
+                       check=True)
+        ref = helpers.read_db(os.path.join(d, "sub_ref"))
+        assert helpers.read_db(os.path.join(d, "sub_mine")) == ref
+        assert 0 < sum(len(v) for v in ref.values()) < sum(len(v) for v in helpers.read_db(os.path.join(d, "pref")).values())
+        helpers.run_ref(["mergedbs", db, os.path.join(d, "mrg_ref"), os.path.join(d, "aln"), os.path.join(d, "sub_ref"), "-v", "1"])
+        subprocess.run([SDB200, "mergedbs", db, os.path.join(d, "mrg_mine"), os.path.join(d, "aln"), os.path.join(d, "sub_mine")], check=True)
+        assert helpers.read_db(os.path.join(d, "mrg_mine")) == helpers.read_db(os.path.join(d, "mrg_ref"))
+        assert open(os.path.join(d, "mrg_mine.dbtype"), "rb").read() == open(os.path.join(d, "mrg_ref.dbtype"), "rb").read()
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
