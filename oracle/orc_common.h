@@ -47,6 +47,8 @@ typedef struct {
     int compBias;          /* --comp-bias-corr */
     int binSize;           /* radix bin count of the reference's CacheFriendlyOperations (host-L2 dependent) */
     int sameDB;            /* query DB == target DB: identity hit first */
+    uint64_t maxDbMatches;        /* test hook: size of the hit buffer (0 = reference: 2*max(10^6, nT), QueryMatcher.cpp:43) */
+    uint64_t foundDiagonalsSize;  /* test hook: size of the candidate array (0 = reference: max(10^6, nT), QueryMatcher.cpp:42) */
 } orc_pref_params;
 
 typedef struct {
@@ -57,6 +59,8 @@ typedef struct {
     uint64_t hits;         /* H: hits written (before the coverage filter)     */
     uint64_t candidates;   /* double-hit candidates that were diagonal-scored  */
     uint64_t truncated;    /* queries where the --max-seqs cut dropped hits    */
+    uint64_t overflowQueries;      /* queries whose index hits overflowed the hit buffer at least once (QueryMatcher.cpp:280) */
+    uint64_t multiOverflowQueries; /* ... at least twice (reversed merge + intermediate keepMax, :296-303) */
 } orc_pref_stats;
 
 typedef struct {

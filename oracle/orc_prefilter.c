@@ -260,6 +260,183 @@ static size_t profile_kmer_list(short sc[KMER][20], unsigned int ix[KMER][20], s
     return n;
 }
 
+
+/* ---- CacheFriendlyOperations, restated on flat arrays.  The reference first hashes the input into radix bins
+ * (id & binMask), stable inside a bin, and then walks bin by bin; `last` is its duplicateBitArray (index id >> binBits). */
+typedef struct {
+    unsigned char *last;       /* duplicateBitArray */
+    cand_t *tmp;               /* tmpElementBuffer / scratch copy */
+    size_t tmpCap;
+    uint32_t binMask;
+    int binBits;
+} cfo_t;
+
+static void cfo_reserve(cfo_t *c, size_t n) {
+    if (n + 1 > c->tmpCap) {
+        while (n + 1 > c->tmpCap) c->tmpCap *= 2;
+        c->tmp = (cand_t *)realloc(c->tmp, sizeof(cand_t) * c->tmpCap);
+    }
+}
+
+/* findDuplicates (CacheFriendlyOperations.cpp:185-274, diagonal-scoring branch): a hit is kept when its 8-bit diagonal equals the
+ * previous 8-bit diagonal seen for that target (table starts at 0); kept hits of one target with equal consecutive 8-bit
+ * diagonals collapse to the first.  Returns early when the output array would overflow (:208-211). */
+static size_t cfo_find_duplicates(cfo_t *c, const hit_t *hits, size_t nHit, cand_t *out, size_t outputSize) {
+    size_t nOut = 0;
+    cfo_reserve(c, nHit);
+    for (uint32_t bin = 0; bin <= c->binMask; bin++) {
+        size_t nTmp = 0, binCount = 0;
+        for (size_t h = 0; h < nHit; h++) {
+            if ((hits[h].id & c->binMask) != bin) continue;
+            binCount++;
+            uint32_t slot = hits[h].id >> c->binBits;
+            unsigned char d8 = (unsigned char)hits[h].diag;
+            if (d8 == c->last[slot]) { c->tmp[nTmp].id = hits[h].id; c->tmp[nTmp].diag = hits[h].diag; nTmp++; }
+            c->last[slot] = d8;
+        }
+        if (nOut + (nTmp < binCount / 2 ? nTmp : binCount / 2) >= outputSize) return nOut;
+        for (size_t n = nTmp; n-- > 0;) c->last[c->tmp[n].id >> c->binBits] = (unsigned char)((unsigned char)c->tmp[n].diag + 1);
+        for (size_t n = 0; n < nTmp; n++) {
+            uint32_t slot = c->tmp[n].id >> c->binBits;
+            unsigned char d8 = (unsigned char)c->tmp[n].diag;
+            out[nOut].id = c->tmp[n].id; out[nOut].diag = c->tmp[n].diag; out[nOut].count = 0;
+            if (c->last[slot] != d8) nOut++;
+            c->last[slot] = d8;
+        }
+        for (size_t h = 0; h < nHit; h++)
+            if ((hits[h].id & c->binMask) == bin) c->last[hits[h].id >> c->binBits] = 0;
+    }
+    return nOut;
+}
+
+/* mergeDiagonalDuplicates (CacheFriendlyOperations.cpp:84-113): per target, consecutive elements with the same 8-bit
+ * diagonal collapse to the first; output bin-major.  The table is NOT cleared afterwards (the caller's next use clears or
+ * overwrites it) -- cleared here, which is equivalent for every caller on this path. */
+static size_t cfo_merge_diagonal(cfo_t *c, cand_t *arr, size_t N) {
+    cfo_reserve(c, N);
+    memcpy(c->tmp, arr, N * sizeof(cand_t));
+    size_t nOut = 0;
+    for (uint32_t bin = 0; bin <= c->binMask; bin++) {
+        for (size_t n = N; n-- > 0;)
+            if ((c->tmp[n].id & c->binMask) == bin) c->last[c->tmp[n].id >> c->binBits] = (unsigned char)((unsigned char)c->tmp[n].diag + 1);
+        for (size_t n = 0; n < N; n++) {
+            if ((c->tmp[n].id & c->binMask) != bin) continue;
+            uint32_t slot = c->tmp[n].id >> c->binBits;
+            unsigned char d8 = (unsigned char)c->tmp[n].diag;
+            arr[nOut] = c->tmp[n];
+            if (c->last[slot] != d8) nOut++;
+            c->last[slot] = d8;
+        }
+        for (size_t n = 0; n < N; n++)
+            if ((c->tmp[n].id & c->binMask) == bin) c->last[c->tmp[n].id >> c->binBits] = 0;
+    }
+    return nOut;
+}
+
+/* mergeDiagonalKeepScoredHitsDuplicates (CacheFriendlyOperations.cpp:116-145): walks every bin BACKWARDS; an element survives
+ * when it already carries a score or its 8-bit diagonal differs from the element after it (same target); output order is the
+ * reversed walk. */
+static size_t cfo_merge_keep_scored(cfo_t *c, cand_t *arr, size_t N) {
+    cfo_reserve(c, N);
+    memcpy(c->tmp, arr, N * sizeof(cand_t));
+    size_t nOut = 0;
+    for (uint32_t bin = 0; bin <= c->binMask; bin++) {
+        for (size_t n = 0; n < N; n++)
+            if ((c->tmp[n].id & c->binMask) == bin) c->last[c->tmp[n].id >> c->binBits] = (unsigned char)((unsigned char)c->tmp[n].diag + 1);
+        for (size_t n = N; n-- > 0;) {
+            if ((c->tmp[n].id & c->binMask) != bin) continue;
+            uint32_t slot = c->tmp[n].id >> c->binBits;
+            unsigned char d8 = (unsigned char)c->tmp[n].diag;
+            arr[nOut] = c->tmp[n];
+            if (arr[nOut].count != 0 || c->last[slot] != d8) nOut++;
+            c->last[slot] = d8;
+        }
+        for (size_t n = 0; n < N; n++)
+            if ((c->tmp[n].id & c->binMask) == bin) c->last[c->tmp[n].id >> c->binBits] = 0;
+    }
+    return nOut;
+}
+
+/* keepMaxScoreElementOnly (CacheFriendlyOperations.cpp:350-380): per target the first element carrying the maximal score;
+ * output again bin-major, arrival order inside a bin. */
+static size_t cfo_keep_max(cfo_t *c, cand_t *arr, size_t N) {
+    cfo_reserve(c, N);
+    memcpy(c->tmp, arr, N * sizeof(cand_t));
+    size_t nKeep = 0;
+    for (uint32_t bin = 0; bin <= c->binMask; bin++) {
+        for (size_t i = 0; i < N; i++) {
+            if ((c->tmp[i].id & c->binMask) != bin) continue;
+            uint32_t slot = c->tmp[i].id >> c->binBits;
+            if (c->tmp[i].count > c->last[slot]) c->last[slot] = c->tmp[i].count;
+        }
+        for (size_t i = 0; i < N; i++) {
+            if ((c->tmp[i].id & c->binMask) != bin) continue;
+            uint32_t slot = c->tmp[i].id >> c->binBits;
+            int found = (c->last[slot] == c->tmp[i].count);
+            if (found) arr[nKeep++] = c->tmp[i];
+            c->last[slot] = (unsigned char)(c->last[slot] * (1 - found));
+        }
+        for (size_t i = 0; i < N; i++)
+            if ((c->tmp[i].id & c->binMask) == bin) c->last[c->tmp[i].id >> c->binBits] = 0;
+    }
+    return nKeep;
+}
+
+/* UngappedAlignment::align -> computeScores (UngappedAlignment.cpp:25-27, 331-362): elements that already carry a score are
+ * skipped; the others get min(255, diagonal score) */
+static void align_cands(cand_t *arr, size_t N, const signed char *prof, int L, const unsigned char *tres, const uint64_t *tOff,
+                        uint64_t *residues) {
+    for (size_t c = 0; c < N; c++) {
+        if (arr[c].count != 0) continue;
+        uint32_t t = arr[c].id;
+        int s = diag_score(prof, L, tres + tOff[t], (int)(tOff[t + 1] - tOff[t]), (short)arr[c].diag, residues);
+        arr[c].count = (unsigned char)(s > 255 ? 255 : s);
+    }
+}
+
+/* QueryMatcher::match (QueryMatcher.cpp:213-346): index entries are buffered in databaseHits (maxDbMatches entries).  When the
+ * next bucket would reach the end of the buffer (:280) the buffered part is reduced by findDuplicates (fresh table) into
+ * foundDiagonals behind the results of earlier overflows; from the second overflow on the list is merged with
+ * mergeDiagonalKeepScoredHitsDuplicates, scored and cut to the best diagonal per target (:296-303). */
+typedef struct {
+    hit_t *hits;
+    size_t nHit, maxDbMatches;
+    size_t overflowHitCount, overflowNumMatches, nOverflows;
+    cand_t *found;
+    size_t foundSize;
+    cfo_t *cfo;
+    const signed char *prof;
+    int L;
+    const unsigned char *tres;
+    const uint64_t *tOff;
+    uint64_t *residues;
+} match_t;
+
+/* returns 1 for the reference's `goto outer` (a single bucket as large as the whole buffer) */
+static int match_bucket(match_t *m, const index_t *ix, uint32_t kmer, int p) {
+    const uint32_t lo = ix->off[kmer], hi = ix->off[kmer + 1];
+    const size_t len = hi - lo;
+    if (m->nHit + len >= m->maxDbMatches) {
+        const size_t hitCount = cfo_find_duplicates(m->cfo, m->hits, m->nHit, m->found + m->overflowHitCount,
+                                                    m->foundSize - m->overflowHitCount);
+        if (m->overflowHitCount != 0) {
+            m->overflowHitCount = cfo_merge_keep_scored(m->cfo, m->found, hitCount + m->overflowHitCount);
+            align_cands(m->found, m->overflowHitCount, m->prof, m->L, m->tres, m->tOff, m->residues);
+            m->overflowHitCount = cfo_keep_max(m->cfo, m->found, m->overflowHitCount);
+        } else m->overflowHitCount = hitCount;
+        m->overflowNumMatches += m->nHit;
+        m->nHit = 0;
+        m->nOverflows++;
+        if (len >= m->maxDbMatches) return 1;
+    }
+    for (uint32_t e = lo; e < hi; e++) {
+        m->hits[m->nHit].id = ix->ent[e].seq;
+        m->hits[m->nHit].diag = (uint16_t)(p - ix->ent[e].pos);
+        m->nHit++;
+    }
+    return 0;
+}
+
 static long prefilter_core(const char *tSeq, const uint64_t *tOff, uint32_t nT,
                            const char *qSeq, const uint64_t *qOff, uint32_t nQ,
                            const orc_pref_params *par, orc_pref_hit *out, long outCap,
@@ -322,17 +499,25 @@ static long prefilter_core(const char *tSeq, const uint64_t *tOff, uint32_t nT,
     unsigned char *qres = (unsigned char *)malloc((size_t)maxLq + 1);
     float *bias = (float *)malloc(sizeof(float) * (size_t)(maxLq + 1));
     signed char *prof = (signed char *)malloc((size_t)21 * (size_t)(maxLq + 1));
-    size_t hitCap = 1 << 20, nHit;
-    hit_t *hits = (hit_t *)malloc(sizeof(hit_t) * hitCap);
-    size_t candCap = 1 << 16, nCand;
-    cand_t *cand = (cand_t *)malloc(sizeof(cand_t) * candCap);
-    cand_t *tmp = (cand_t *)malloc(sizeof(cand_t) * candCap);
-    unsigned char *last = (unsigned char *)calloc((size_t)nT + 1, 1);
+    /* QueryMatcher.cpp:42-43: hit buffer of maxDbMatches index entries, candidate array of foundDiagonalsSize elements
+     * (par->maxDbMatches / par->foundDiagonalsSize: test hooks that shrink them; 0 = the reference's values) */
+    const size_t refFound = (size_t)nT > 1000000 ? (size_t)nT : 1000000;
+    const size_t maxDbMatches = par->maxDbMatches ? (size_t)par->maxDbMatches : refFound * 2;
+    const size_t foundDiagonalsSize = par->foundDiagonalsSize ? (size_t)par->foundDiagonalsSize : refFound;
+    size_t nCand;
+    hit_t *hits = (hit_t *)malloc(sizeof(hit_t) * (maxDbMatches + 1));
+    cand_t *cand = (cand_t *)calloc(foundDiagonalsSize + 1, sizeof(cand_t));     /* foundDiagonals */
+    cfo_t cfo;
+    cfo.tmpCap = 1 << 16;
+    cfo.tmp = (cand_t *)malloc(sizeof(cand_t) * cfo.tmpCap);
+    cfo.last = (unsigned char *)calloc((size_t)nT + 1, 1);
     const size_t maxHits = (size_t)par->maxSeqs < (size_t)nT ? (size_t)par->maxSeqs : (size_t)nT;
     res_t *res = (res_t *)malloc(sizeof(res_t) * (maxHits + 2));
     const uint32_t binMask = (uint32_t)par->binSize - 1;
     int binBits = 0;
     while ((1u << binBits) < (uint32_t)par->binSize) binBits++;
+    cfo.binMask = binMask;
+    cfo.binBits = binBits;
     long nOut = 0;
 
     for (uint32_t q = 0; q < nQ; q++) {
@@ -362,8 +547,13 @@ static long prefilter_core(const char *tSeq, const uint64_t *tOff, uint32_t nT,
         }
         }
         /* QueryMatcher::match (QueryMatcher.cpp:213-346) + KmerGenerator (KmerGenerator.cpp:107-216) */
-        nHit = 0;
-        for (int p = 0; p + SPAN <= L; p++) {
+        match_t m;
+        m.hits = hits; m.nHit = 0; m.maxDbMatches = maxDbMatches;
+        m.overflowHitCount = 0; m.overflowNumMatches = 0; m.nOverflows = 0;
+        m.found = cand; m.foundSize = foundDiagonalsSize; m.cfo = &cfo;
+        m.prof = prof; m.L = L; m.tres = tres; m.tOff = tOff; m.residues = &st.diagResidues;
+        int stop = 0;
+        for (int p = 0; p + SPAN <= L && !stop; p++) {
             unsigned char km[KMER];
             int hasX = 0;
             float bsum = 0;
@@ -385,19 +575,9 @@ static long prefilter_core(const char *tSeq, const uint64_t *tOff, uint32_t nT,
                 }
                 const size_t *list;
                 const size_t nList = profile_kmer_list(sc, ixs, thr, pkS, pkI, &list);
-                for (size_t c = 0; c < nList; c++) {
-                    const uint32_t kmer = (uint32_t)list[c];
+                for (size_t c = 0; c < nList && !stop; c++) {
                     st.probes++;
-                    uint32_t lo = ix.off[kmer], hi = ix.off[kmer + 1];
-                    if (nHit + (hi - lo) > hitCap) {
-                        while (nHit + (hi - lo) > hitCap) hitCap *= 2;
-                        hits = (hit_t *)realloc(hits, sizeof(hit_t) * hitCap);
-                    }
-                    for (uint32_t e = lo; e < hi; e++) {
-                        hits[nHit].id = ix.ent[e].seq;
-                        hits[nHit].diag = (uint16_t)(p - ix.ent[e].pos);
-                        nHit++;
-                    }
+                    stop = match_bucket(&m, &ix, (uint32_t)list[c], p);
                 }
                 continue;
             }
@@ -406,81 +586,33 @@ static long prefilter_core(const char *tSeq, const uint64_t *tOff, uint32_t nT,
             const short *s1 = e3.score + (size_t)i1 * N3, *s2 = e3.score + (size_t)i2 * N3;
             const unsigned short *x1 = e3.index + (size_t)i1 * N3, *x2 = e3.index + (size_t)i2 * N3;
             short cutoff1 = (short)(thr - s2[0]);
-            for (int a = 0; a < N3 && s1[a] >= cutoff1; a++) {
+            for (int a = 0; a < N3 && s1[a] >= cutoff1 && !stop; a++) {
                 short cutoff2 = (short)(thr - s1[a]);
-                for (int c = 0; c < N3 && s2[c] >= cutoff2; c++) {
+                for (int c = 0; c < N3 && s2[c] >= cutoff2 && !stop; c++) {
                     uint32_t kmer = x1[a] + (uint32_t)N3 * x2[c];
                     st.probes++;
-                    uint32_t lo = ix.off[kmer], hi = ix.off[kmer + 1];
-                    if (nHit + (hi - lo) > hitCap) {
-                        while (nHit + (hi - lo) > hitCap) hitCap *= 2;
-                        hits = (hit_t *)realloc(hits, sizeof(hit_t) * hitCap);
-                    }
-                    for (uint32_t e = lo; e < hi; e++) {
-                        hits[nHit].id = ix.ent[e].seq;
-                        hits[nHit].diag = (uint16_t)(p - ix.ent[e].pos);
-                        nHit++;
-                    }
+                    stop = match_bucket(&m, &ix, kmer, p);
                 }
             }
         }
-        st.matches += nHit;
-        /* CacheFriendlyOperations::findDuplicates (CacheFriendlyOperations.cpp:185-274): per radix bin
-         * (id & mask), walk hits in arrival order; a hit is kept when its 8-bit diagonal equals the
-         * previous 8-bit diagonal seen for that target (table starts at 0); kept hits of one target
-         * with equal consecutive 8-bit diagonals collapse to the first. */
+        /* QueryMatcher.cpp:322-333: the last buffered part; after an overflow the lists are merged by mergeDiagonalDuplicates.
+         * An empty last part returns NO hits at all (hitCount stays 0) -- literal. */
         nCand = 0;
-        if (nHit + 1 > candCap) {
-            while (nHit + 1 > candCap) candCap *= 2;
-            cand = (cand_t *)realloc(cand, sizeof(cand_t) * candCap);
-            tmp = (cand_t *)realloc(tmp, sizeof(cand_t) * candCap);
+        if (m.nHit > 0) {
+            nCand = cfo_find_duplicates(&cfo, hits, m.nHit, cand + m.overflowHitCount, foundDiagonalsSize - m.overflowHitCount);
+            if (m.overflowHitCount != 0) nCand = cfo_merge_diagonal(&cfo, cand, m.overflowHitCount + nCand);
         }
-        for (uint32_t bin = 0; bin <= binMask; bin++) {
-            size_t nTmp = 0;
-            for (size_t h = 0; h < nHit; h++) {
-                if ((hits[h].id & binMask) != bin) continue;
-                uint32_t slot = hits[h].id >> binBits;
-                unsigned char d8 = (unsigned char)hits[h].diag;
-                if (d8 == last[slot]) { tmp[nTmp].id = hits[h].id; tmp[nTmp].diag = hits[h].diag; nTmp++; }
-                last[slot] = d8;
-            }
-            for (size_t n = nTmp; n-- > 0;) last[tmp[n].id >> binBits] = (unsigned char)((unsigned char)tmp[n].diag + 1);
-            for (size_t n = 0; n < nTmp; n++) {
-                uint32_t slot = tmp[n].id >> binBits;
-                unsigned char d8 = (unsigned char)tmp[n].diag;
-                if (last[slot] != d8) { cand[nCand].id = tmp[n].id; cand[nCand].diag = tmp[n].diag; cand[nCand].count = 0; nCand++; }
-                last[slot] = d8;
-            }
-            for (size_t h = 0; h < nHit; h++)
-                if ((hits[h].id & binMask) == bin) last[hits[h].id >> binBits] = 0;
-        }
+        st.matches += m.overflowNumMatches + m.nHit;
+        if (m.nOverflows) st.overflowQueries++;
+        if (m.nOverflows > 1) st.multiOverflowQueries++;
         st.candidates += nCand;
-        /* UngappedAlignment::align (UngappedAlignment.cpp:25-27, 331-362): score every candidate, cap 255 */
-        for (size_t c = 0; c < nCand; c++) {
-            uint32_t t = cand[c].id;
-            int s = diag_score(prof, L, tres + tOff[t], (int)(tOff[t + 1] - tOff[t]), (short)cand[c].diag,
-                               &st.diagResidues);
-            cand[c].count = (unsigned char)(s > 255 ? 255 : s);
-        }
-        /* keepMaxScoreElementOnly (CacheFriendlyOperations.cpp:350-380): per target the first element
-         * carrying the maximal score; output again bin-major, arrival order inside a bin. */
-        size_t nKeep = 0;
-        for (uint32_t bin = 0; bin <= binMask; bin++) {
-            for (size_t c = 0; c < nCand; c++) {
-                if ((cand[c].id & binMask) != bin) continue;
-                uint32_t slot = cand[c].id >> binBits;
-                if (cand[c].count > last[slot]) last[slot] = cand[c].count;
-            }
-            for (size_t c = 0; c < nCand; c++) {
-                if ((cand[c].id & binMask) != bin) continue;
-                uint32_t slot = cand[c].id >> binBits;
-                int found = (last[slot] == cand[c].count);
-                if (found) tmp[nKeep++] = cand[c];
-                last[slot] = (unsigned char)(last[slot] * (1 - found));
-            }
-            for (size_t c = 0; c < nCand; c++)
-                if ((cand[c].id & binMask) == bin) last[cand[c].id >> binBits] = 0;
-        }
+        /* UngappedAlignment::align (UngappedAlignment.cpp:25-27, 331-362): score every candidate that has no score yet, cap 255 */
+        align_cands(cand, nCand, prof, L, tres, tOff, &st.diagResidues);
+        /* keepMaxScoreElementOnly (CacheFriendlyOperations.cpp:350-380) */
+        size_t nKeep = cfo_keep_max(&cfo, cand, nCand);
+        cfo_reserve(&cfo, nCand > nKeep ? nCand : nKeep);
+        cand_t *tmp = cfo.tmp;
+        memcpy(tmp, cand, nKeep * sizeof(cand_t));
         /* score histogram -> threshold (QueryMatcher.h:206-216), stable order by score desc
          * (radixSortByScoreSize QueryMatcher.cpp:498-523), getResult (QueryMatcher.cpp:363-420) */
         unsigned int histo[256];
@@ -571,7 +703,7 @@ static long prefilter_core(const char *tSeq, const uint64_t *tOff, uint32_t nT,
     }
     if (stats) *stats = st;
     free(tres); free(ix.off); free(ix.ent); free(e3.score); free(e3.index);
-    free(qres); free(bias); free(prof); free(hits); free(cand); free(tmp); free(last); free(res);
+    free(qres); free(bias); free(prof); free(hits); free(cand); free(cfo.tmp); free(cfo.last); free(res);
     for (int b = 0; b < 2; b++) { free(pkS[b]); free(pkI[b]); }
     return nOut;
 }

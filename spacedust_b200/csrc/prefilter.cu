@@ -160,6 +160,13 @@ __global__ void compactRows(const uint32_t *__restrict__ kOff, const uint32_t *_
     rows[rank[w] + __popc(b & ((1u << (k & 31)) - 1u))] = row;
 }
 
+// {bits, rank} side by side: one 8-byte load answers a probe (empty or not) and gives the row of a non-empty k-mer
+__global__ void interleaveBitmap(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ rank, uint32_t nWords,
+                                 uint2 *__restrict__ bm) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nWords) bm[i] = make_uint2(bits[i], rank[i]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // query preparation
 // ------------------------------------------------------------------------------------------------
@@ -209,714 +216,7 @@ __global__ void kmerThresholds(const uint8_t *__restrict__ code, const uint32_t 
     thr[gp] = out;
 }
 
-// ------------------------------------------------------------------------------------------------
-// the prefilter kernel
-// ------------------------------------------------------------------------------------------------
-constexpr int PF_WARPS = 8;              // warps per CTA
-constexpr int PF_CAP2 = 1024;            // staged prefix of the second 3-mer's neighbour row
-constexpr int PF_UNROLL = 4;             // probe steps in flight per warp (independent bitmap loads)
-constexpr uint32_t PF_Q1CAP = 256;       // ring 1 (non-empty buckets): up to 32*PF_UNROLL pushes between drains
-constexpr uint32_t PF_Q2CAP = 128;       // ring 2 (index hits)
-constexpr uint32_t PF_QDRAIN = 96;       // a stage runs when its ring holds this many: popped items were prefetched >= 64 pushes ago
-constexpr size_t PF_DYN_SMEM = (size_t)PF_WARPS * (PF_Q1CAP + PF_Q2CAP) * (sizeof(uint32_t) + sizeof(uint16_t));
-static_assert(PF_QDRAIN - 1 + 32 * PF_UNROLL <= PF_Q1CAP && PF_QDRAIN - 1 + 32 <= PF_Q2CAP, "ring capacity");
-
-__device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// L2 cache policies: the streamed, never re-used data (bucket rows, entries, the per-warp tables) is marked evict-first so
-// that it does not push the re-used data (occupancy bitmap, count table, target residues) out of the L2.
-__device__ __forceinline__ uint64_t l2Policy(int evictFirst) {
-    uint64_t pol;
-    if (evictFirst) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint64_t l2PolicyKeep() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint32_t ldKeep(const uint32_t *p, uint64_t pol) {
-    uint32_t v;
-    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ uint32_t ldStream(const uint32_t *p, uint64_t pol) {
-    uint32_t v;
-    asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint2 ldStream2(const uint2 *p, uint64_t pol) {
-    uint2 v;
-    asm volatile("ld.global.cg.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol) : "memory");
-    return v;
-}
-__device__ __forceinline__ void stStream(uint32_t *p, uint32_t v, uint64_t pol) {
-    asm volatile("st.global.cg.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
-}
-
-struct PrefilterArgs {
-    // target side
-    const uint8_t *tRes;
-    const uint32_t *tOff;
-    uint32_t nT;
-    const uint32_t *bmBits;    // per 32 k-mers: occupancy bits (8 MB, L2 resident)
-    const uint32_t *bmRank;    // per 32 k-mers: row of the first non-empty one
-    const uint2 *rows;         // per non-empty k-mer: {target, 1<<31 | pos} (single entry) or {start, length}
-    const uint2 *ent;          // bucket entries: (target id, first position of the k-mer in that target)
-    const int16_t *e3score;
-    const uint16_t *e3index;
-    const uint16_t *e3cnt;     // [8000][512] cumulative counts: e3cnt[x*512 + 255 - v] = #{y : score(x,y) >= v}
-    const int8_t *diagSub;     // 21x21 BLOSUM62 x2 (-0.2)
-    // query side
-    QueryBatchDev q;
-    uint32_t nQ;
-    const uint32_t *order;     // queries, longest first
-    uint32_t queryFirst;       // identity = queryFirst + q when sameDb
-    int sameDb;
-    // parameters
-    uint32_t maxHits;          // min(max_seqs, nT)
-    uint32_t minDiagScore;
-    float covThr;
-    int covMode;
-    uint32_t binMask;
-    // scratch
-    uint32_t *table;           // per warp: nT words
-    uint32_t candCap;
-    uint64_t *cand;            // per warp: candCap   (t<<32 | diag<<16 | score<<8)
-    uint64_t *keep;            // per warp: candCap   (t<<32 | diag<<16 | score<<8), emission order kept
-    uint32_t *resT;            // per warp: maxHits
-    int32_t *resScore;
-    uint16_t *resDiag;
-    // output
-    sd_prefilter_hit *out;     // nQ * maxHits
-    uint32_t *outCount;        // nQ
-    unsigned long long *stats; // [0]=probes [1]=matches [2]=diagResidues [3]=hits [4]=candidates [5]=truncated [6]=errors
-    uint32_t *nextQuery;
-    uint32_t *errQuery;
-    uint32_t *failList;        // queries whose candidate list did not fit candCap (re-run with a larger list)
-    uint32_t *nFail;
-    int evictFirst;            // L2 evict-first policy for the streamed data
-    int prefetch;              // bit 0: table words, bit 1: bucket rows
-    int debugSkip;             // profiling only (SD_PF_SKIP): bit 0 drops stage C, bit 1 drops stage B -- results are then wrong
-};
-
-enum { ST_PROBES = 0, ST_MATCHES, ST_DIAGRES, ST_HITS, ST_CANDS, ST_TRUNC, ST_ERR_CAND, ST_ERR_RESCORE, ST_N };
-
-// UngappedAlignment::computeSingelSequenceScores + scalarDiagonalScoring (UngappedAlignment.cpp:30-43,416-430)
-__device__ int diagonalScore(const PrefilterArgs &a, const int8_t *sSub, uint32_t qBase, int Lq, uint32_t t, int diag,
-                             uint32_t &residues) {
-    const uint32_t tb = a.tOff[t];
-    const int Lt = (int)(a.tOff[t + 1] - tb);
-    int qs, ts, len;
-    if (diag >= 0) {
-        if (diag >= Lq) return 0;
-        qs = diag; ts = 0; len = min(Lt, Lq - diag);
-    } else {
-        if (-diag >= Lt) return 0;
-        qs = 0; ts = -diag; len = min(Lt + diag, Lq);
-    }
-    const uint8_t *qc = a.q.code + qBase + qs;
-    const int8_t *qk = a.q.corr + qBase + qs;
-    const uint8_t *tc = a.tRes + tb + ts;
-    int best = 0, run = 0;
-    for (int p = 0; p < len; p++) {
-        run += (int)sSub[qc[p] * AA + tc[p]] + (int)qk[p];
-        run = max(run, 0);
-        best = max(best, run);
-    }
-    residues += (uint32_t)len;
-    return best;
-}
-
-// same score, computed by a whole warp: lane l takes residues l, l+32, ...; with S the prefix sums of the per-residue scores,
-// run_i = S_i - min(0, min_{j<=i} S_j) and the result is max_i run_i
-__device__ __forceinline__ int diagonalScoreWarp(const PrefilterArgs &a, const int8_t *sSub, uint32_t qBase, int Lq, uint32_t t,
-                                                 int diag, uint32_t lane, unsigned long long &residues) {
-    const uint32_t tb = __ldg(&a.tOff[t]);
-    const int Lt = (int)(__ldg(&a.tOff[t + 1]) - tb);
-    int qs, ts, len;
-    if (diag >= 0) {
-        if (diag >= Lq) return 0;
-        qs = diag; ts = 0; len = min(Lt, Lq - diag);
-    } else {
-        if (-diag >= Lt) return 0;
-        qs = 0; ts = -diag; len = min(Lt + diag, Lq);
-    }
-    const uint8_t *qc = a.q.code + qBase + qs;
-    const int8_t *qk = a.q.corr + qBase + qs;
-    const uint8_t *tc = a.tRes + tb + ts;
-    int best = 0, carrySum = 0, carryMin = 0;
-    for (int p0 = 0; p0 < len; p0 += 32) {
-        const int p = p0 + (int)lane;
-        int x = 0;
-        if (p < len) x = (int)sSub[__ldg(&qc[p]) * AA + __ldg(&tc[p])] + (int)__ldg(&qk[p]);
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, x, d);
-            if (lane >= (uint32_t)d) x += y;
-        }
-        x += carrySum;
-        int m = x;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, m, d);
-            if (lane >= (uint32_t)d) m = min(m, y);
-        }
-        m = min(m, carryMin);
-        best = max(best, x - m);
-        carrySum = __shfl_sync(0xffffffffu, x, 31);
-        carryMin = __shfl_sync(0xffffffffu, m, 31);
-    }
-    if (lane == 0) residues += (unsigned long long)len;
-    return __reduce_max_sync(0xffffffffu, best);
-}
-
-__global__ void __launch_bounds__(PF_WARPS * 32, 4) prefilterKernel(PrefilterArgs a) {
-    __shared__ uint16_t sX2[PF_WARPS][PF_CAP2];
-    __shared__ uint32_t sHist[PF_WARPS][256];
-    __shared__ int8_t sSub[AA * AA];
-    extern __shared__ __align__(16) uint8_t sDyn[];    // stage rings: [warp][Q1c | Q2t | Q1p | Q2d]
-
-    for (int i = threadIdx.x; i < AA * AA; i += blockDim.x) sSub[i] = a.diagSub[i];
-    __syncthreads();
-
-    const uint32_t lane = laneId();
-    const uint32_t wInBlock = threadIdx.x >> 5;
-    const uint32_t warp = blockIdx.x * PF_WARPS + wInBlock;
-    const uint32_t ltMask = (1u << lane) - 1u;
-    uint32_t *tab = a.table + (size_t)warp * a.nT;
-    uint64_t *cand = a.cand + (size_t)warp * a.candCap;
-    uint64_t *keep = a.keep + (size_t)warp * a.candCap;
-    uint32_t *resT = a.resT + (size_t)warp * a.maxHits;
-    int32_t *resScore = a.resScore + (size_t)warp * a.maxHits;
-    uint16_t *resDiag = a.resDiag + (size_t)warp * a.maxHits;
-    uint16_t *X2 = sX2[wInBlock];
-    uint32_t *hist = sHist[wInBlock];
-    uint32_t *Q1c = reinterpret_cast<uint32_t *>(sDyn) + (size_t)wInBlock * (PF_Q1CAP + PF_Q2CAP);
-    uint32_t *Q2t = Q1c + PF_Q1CAP;
-    uint16_t *Q1p = reinterpret_cast<uint16_t *>(sDyn + (size_t)PF_WARPS * (PF_Q1CAP + PF_Q2CAP) * sizeof(uint32_t)) + (size_t)wInBlock * (PF_Q1CAP + PF_Q2CAP);
-    uint16_t *Q2d = Q1p + PF_Q1CAP;
-
-    const uint64_t pol = l2Policy(a.evictFirst);
-    const uint64_t polKeep = a.evictFirst ? l2PolicyKeep() : l2Policy(0);
-    uint32_t epoch = 0;   // table words start zeroed; live epochs are 1..255
-
-    for (;;) {
-        uint32_t qi = 0;
-        if (lane == 0) qi = atomicAdd(a.nextQuery, 1u);
-        qi = __shfl_sync(0xffffffffu, qi, 0);
-        if (qi >= a.nQ) break;
-        // per-query counters: added to the global statistics only when the query completes (a query whose candidate
-        // list overflows is re-run by a second launch and counted there)
-        unsigned long long stProbes = 0, stMatches = 0, stDiagRes = 0, stHits = 0, stCands = 0, stTrunc = 0;
-        const uint32_t q = a.order[qi];
-        const uint32_t qBase = a.q.off[q];
-        const int Lq = (int)(a.q.off[q + 1] - qBase);
-        const uint32_t identity = a.sameDb ? (a.queryFirst + q) : 0xffffffffu;
-
-        // two epochs per query: E for the hit stream, E+1 for the best-diagonal pass
-        if (epoch + 2 > 255) {
-            for (uint32_t i = lane; i < a.nT; i += 32) __stcg(&tab[i], 0u);
-            __syncwarp();
-            epoch = 0;
-        }
-        const uint32_t E = epoch + 1;
-        epoch += 2;
-
-        uint32_t nCand = 0;
-        bool candOverflow = false;
-
-        // ---------------- hit stream: positions -> similar k-mers -> buckets -> double-hit rule
-        // Three stages, decoupled by two small per-warp FIFO rings in shared memory so that every stage runs with full
-        // lanes and every HBM access was prefetched into L2 one stage earlier (stream order is the FIFO order):
-        //   A  32 similar k-mers per step -> occupancy bitmap + rank (L2 resident) -> non-empty ones to ring 1
-        //   B  32 buckets per step: compact offset row (prefetched by A) -> entries -> (target, diagonal) to ring 2
-        //   C  32 index hits per step: double-diagonal rule on the per-warp table (prefetched by B)
-        uint32_t q1h = 0, q1n = 0, q2h = 0, q2n = 0;
-
-        auto stageC = [&](const uint32_t n) {
-            __syncwarp();
-            const bool validE = lane < n;
-            uint32_t t = 0x80000000u | lane;     // unique dummy for idle lanes
-            uint32_t diag16 = 0;
-            if (validE) {
-                const uint32_t slot = (q2h + lane) & (PF_Q2CAP - 1);
-                t = Q2t[slot];
-                diag16 = Q2d[slot];
-            }
-            q2h += n;
-            q2n -= n;
-            if (a.debugSkip & 1) return;
-            const uint32_t d8 = diag16 & 0xffu;
-            // --- CacheFriendlyOperations::findDuplicates, restated per target in stream order
-            const uint32_t grp = __match_any_sync(0xffffffffu, t);
-            uint32_t old = 0;
-            if (validE) old = ldStream(&tab[t], pol);
-            if ((old >> 24) != E) old = 0;
-            const uint32_t lowerG = grp & ltMask;
-            const int prevLane = lowerG ? (31 - __clz(lowerG)) : -1;
-            uint32_t prevD8 = __shfl_sync(0xffffffffu, d8, prevLane >= 0 ? prevLane : (int)lane);
-            if (prevLane < 0) prevD8 = (old >> 16) & 0xffu;
-            const bool emit = validE && (d8 == prevD8);
-            const uint32_t emitBallot = __ballot_sync(0xffffffffu, emit);
-            const uint32_t grpE = grp & emitBallot;
-            const uint32_t lowerE = grpE & ltMask;
-            const int prevELane = lowerE ? (31 - __clz(lowerE)) : -1;
-            uint32_t prevED8 = __shfl_sync(0xffffffffu, d8, prevELane >= 0 ? prevELane : (int)lane);
-            bool prevEExists = true;
-            if (prevELane < 0) { prevED8 = old & 0xffu; prevEExists = ((old >> 8) & 1u) != 0; }
-            const bool isCand = emit && !(prevEExists && prevED8 == d8);
-            const int lastELane = grpE ? (31 - __clz(grpE)) : -1;
-            const uint32_t lastED8 = __shfl_sync(0xffffffffu, d8, lastELane >= 0 ? lastELane : (int)lane);
-            if (validE && (grp >> lane) == 1u) {
-                uint32_t w = (E << 24) | (d8 << 16);
-                if (lastELane >= 0) w |= (1u << 8) | lastED8;
-                else w |= old & 0x1ffu;
-                stStream(&tab[t], w, pol);
-            }
-            const uint32_t candBallot = __ballot_sync(0xffffffffu, isCand);
-            if (isCand) {
-                const uint32_t pos = nCand + __popc(candBallot & ltMask);
-                if (pos < a.candCap) cand[pos] = ((uint64_t)t << 32) | ((uint64_t)diag16 << 16);
-            }
-            nCand += __popc(candBallot);
-        };
-
-        auto stageB = [&](const uint32_t n) {
-            __syncwarp();
-            uint32_t rx = 0, ry = 0, m = 0, pq = 0;
-            if (a.debugSkip & 2) { q1h += n; q1n -= n; return; }
-            if (lane < n) {
-                const uint32_t slot = (q1h + lane) & (PF_Q1CAP - 1);
-                const uint2 row = ldStream2(&a.rows[Q1c[slot]], pol);
-                pq = Q1p[slot];
-                rx = row.x;
-                ry = row.y;
-                m = (ry >> 31) ? 1u : ry;                // >= 1: only non-empty buckets are queued
-            }
-            q1h += n;
-            q1n -= n;
-            uint32_t totalM;
-            const uint32_t exclM = warpExclusiveScan(m, totalM);
-            stMatches += (lane == 0) ? totalM : 0;
-            for (uint32_t ec = 0; ec < totalM; ec += 32) {
-                const uint32_t eidx = ec + lane;
-                const bool validE = eidx < totalM;
-                const uint32_t ownerM = warpOwnerOfSlot(exclM, m != 0, ec, lane);
-                const uint32_t oExcl = __shfl_sync(0xffffffffu, exclM, ownerM);
-                const uint32_t oX = __shfl_sync(0xffffffffu, rx, ownerM);
-                const uint32_t oY = __shfl_sync(0xffffffffu, ry, ownerM);
-                const uint32_t oP = __shfl_sync(0xffffffffu, pq, ownerM);
-                if (validE) {
-                    uint2 en = make_uint2(oX, oY & 0xffffu);
-                    if (!(oY >> 31)) en = ldStream2(&a.ent[oX + (eidx - oExcl)], pol);
-                    if (a.prefetch & 1) prefetchL2(&tab[en.x]);
-                    const uint32_t slot = (q2h + q2n + lane) & (PF_Q2CAP - 1);
-                    Q2t[slot] = en.x;
-                    Q2d[slot] = (uint16_t)(oP - en.y);
-                }
-                q2n += min(32u, totalM - ec);
-                while (q2n >= PF_QDRAIN) stageC(32u);
-            }
-        };
-
-        for (int p0 = 0; p0 + SPAN <= Lq; p0 += 32) {
-            // ---- set-up of 32 positions at once (one per lane): thresholds, 3-mer rows, reachable prefix of row 2
-            int thrL = -1, top2L = 0;
-            uint32_t i1L = 0, i2L = 0, nb2L = 0;
-            {
-                const int pl = p0 + (int)lane;
-                if (pl + SPAN <= Lq) thrL = a.q.thr[qBase + pl];
-                if (thrL >= 0) {
-                    const uint8_t *qc = a.q.code + qBase + pl;
-                    i1L = qc[0] + 20u * qc[1] + 400u * qc[3];
-                    i2L = qc[5] + 20u * qc[8] + 400u * qc[9];
-                    const int top1 = (int)__ldg(&a.e3score[(size_t)i1L * N3]);
-                    top2L = (int)__ldg(&a.e3score[(size_t)i2L * N3]);
-                    if (top1 < thrL - top2L) thrL = -1;           // KmerGenerator.cpp:129-137: nothing reaches the threshold
-                    else {
-                        nb2L = countGE(a.e3cnt, i2L, thrL - top1);
-                        if (nb2L == 0) thrL = -1;
-                        else {
-                            prefetchL2(&a.e3index[(size_t)i1L * N3]);
-                            const uint16_t *x2 = a.e3index + (size_t)i2L * N3;
-                            for (uint32_t c = 0; c < nb2L && c < (uint32_t)PF_CAP2; c += 64) prefetchL2(&x2[c]);
-                        }
-                    }
-                }
-            }
-            uint32_t active = __ballot_sync(0xffffffffu, thrL >= 0);
-            while (active) {
-                const int src = __ffs(active) - 1;
-                active &= active - 1;
-                const int p = p0 + src;
-                const int thr = __shfl_sync(0xffffffffu, thrL, src);
-                const uint32_t i1 = __shfl_sync(0xffffffffu, i1L, src);
-                const uint32_t i2 = __shfl_sync(0xffffffffu, i2L, src);
-                const uint32_t nb2 = __shfl_sync(0xffffffffu, nb2L, src);
-                const int cutoff1 = thr - __shfl_sync(0xffffffffu, top2L, src);
-                const int16_t *s1 = a.e3score + (size_t)i1 * N3;
-                const uint16_t *x1 = a.e3index + (size_t)i1 * N3;
-                const uint16_t *x2 = a.e3index + (size_t)i2 * N3;
-                // stage the prefix of row 2 that any first-row element can reach
-                __syncwarp();
-                for (uint32_t c = lane; c < nb2 && c < (uint32_t)PF_CAP2; c += 32) X2[c] = __ldg(&x2[c]);
-                __syncwarp();
-
-                for (uint32_t a0 = 0; a0 < N3; a0 += 32) {
-                    const uint32_t ai = a0 + lane;
-                    const int sa = (ai < N3) ? (int)__ldg(&s1[ai]) : -32768;
-                    const bool okA = sa >= cutoff1;
-                    const uint32_t okBallot = __ballot_sync(0xffffffffu, okA);
-                    if (okBallot == 0) break;
-                    uint32_t nb = 0;
-                    uint32_t xa = 0;
-                    if (okA) {
-                        xa = __ldg(&x1[ai]);
-                        nb = countGE(a.e3cnt, i2, thr - sa);      // KmerGenerator.cpp:201: second-row elements with s2 >= thr - s1
-                    }
-                    // nb is non-increasing over the lanes (row 1 is sorted), zeros only at the tail
-                    uint32_t totalProbes;
-                    const uint32_t exclA = warpExclusiveScan(nb, totalProbes);
-                    stProbes += (lane == 0) ? totalProbes : 0;
-
-                    for (uint32_t pc = 0; pc < totalProbes; pc += 32 * PF_UNROLL) {
-                        uint32_t w[PF_UNROLL], kmerW[PF_UNROLL];
-#pragma unroll
-                        for (int j = 0; j < PF_UNROLL; j++) {
-                            const uint32_t base = pc + 32u * j;
-                            w[j] = 0;
-                            kmerW[j] = 0;
-                            if (base < totalProbes) {
-                                const uint32_t ownerA = warpOwnerOfSlot(exclA, nb != 0, base, lane);
-                                const uint32_t ownerExcl = __shfl_sync(0xffffffffu, exclA, ownerA);
-                                const uint32_t ownerX = __shfl_sync(0xffffffffu, xa, ownerA);
-                                if (base + lane < totalProbes) {
-                                    const uint32_t c = base + lane - ownerExcl;
-                                    const uint32_t xc = (c < (uint32_t)PF_CAP2) ? (uint32_t)X2[c] : (uint32_t)__ldg(&x2[c]);
-                                    kmerW[j] = ownerX + N3 * xc;            // KmerGenerator.cpp:207
-                                    w[j] = ldKeep(&a.bmBits[kmerW[j] >> 5], polKeep);
-                                }
-                            }
-                        }
-                        uint32_t rk[PF_UNROLL];
-#pragma unroll
-                        for (int j = 0; j < PF_UNROLL; j++) {
-                            rk[j] = 0;
-                            if ((w[j] >> (kmerW[j] & 31u)) & 1u) rk[j] = __ldg(&a.bmRank[kmerW[j] >> 5]);   // idle lanes carry w = 0
-                        }
-#pragma unroll
-                        for (int j = 0; j < PF_UNROLL; j++) {
-                            if (pc + 32u * j < totalProbes) {
-                                const uint32_t bit = kmerW[j] & 31u;
-                                const bool has = ((w[j] >> bit) & 1u) != 0;
-                                const uint32_t ci = rk[j] + __popc(w[j] & ((1u << bit) - 1u));
-                                if (has && (a.prefetch & 2)) prefetchL2(&a.rows[ci]);
-                                const uint32_t hb = __ballot_sync(0xffffffffu, has);
-                                if (has) {
-                                    const uint32_t slot = (q1h + q1n + __popc(hb & ltMask)) & (PF_Q1CAP - 1);
-                                    Q1c[slot] = ci;
-                                    Q1p[slot] = (uint16_t)p;
-                                }
-                                q1n += __popc(hb);
-                            }
-                        }
-                        while (q1n >= PF_QDRAIN) stageB(32u);
-                    }
-                    if (okBallot != 0xffffffffu) break;
-                }
-            }
-        }
-        while (q1n > 0) stageB(min(q1n, 32u));
-        while (q2n > 0) stageC(min(q2n, 32u));
-        __syncwarp();
-        if (nCand > a.candCap) { candOverflow = true; nCand = a.candCap; }
-        stCands += (lane == 0) ? nCand : 0;
-        __syncwarp();
-
-        // ---------------- diagonal scores (UngappedAlignment::align), capped at 255
-        // The whole warp scores one diagonal at a time: lanes take consecutive residues (coalesced reads of query and
-        // target), the running max(0, run + s) becomes prefix sums minus their running minimum (warp scans).
-        for (uint32_t c0 = 0; c0 < nCand; c0 += 32) {
-            const uint32_t c = c0 + lane;
-            const uint64_t v = (c < nCand) ? cand[c] : 0ull;
-            const uint32_t nHere = min(32u, nCand - c0);
-            int myScore = 0;
-            for (uint32_t j = 0; j < nHere; j++) {
-                const uint64_t vj = __shfl_sync(0xffffffffu, v, j);
-                const int sc = diagonalScoreWarp(a, sSub, qBase, Lq, (uint32_t)(vj >> 32), (int)(int16_t)(uint16_t)(vj >> 16), lane, stDiagRes);
-                if (lane == j) myScore = sc;
-            }
-            if (c < nCand) {
-                const int sc = min(myScore, 255);
-                cand[c] = v | ((uint64_t)sc << 8);
-                // best score per target: epoch E+1 words order above every epoch-E word
-                atomicMax(&tab[(uint32_t)(v >> 32)], ((E + 1) << 24) | (uint32_t)sc);
-            }
-        }
-        __threadfence_block();
-        __syncwarp();
-
-        // ---------------- keepMaxScoreElementOnly: first candidate (stream order) carrying the target's max
-        for (uint32_t i = lane; i < 256; i += 32) hist[i] = 0;
-        __syncwarp();
-        uint32_t nKeep = 0;
-        for (uint32_t c0 = 0; c0 < nCand; c0 += 32) {
-            const uint32_t c = c0 + lane;
-            const bool valid = c < nCand;
-            uint64_t v = 0;
-            uint32_t t = 0x80000000u | lane;
-            if (valid) { v = cand[c]; t = (uint32_t)(v >> 32); }
-            const uint32_t s = (uint32_t)(v >> 8) & 0xffu;
-            uint32_t w = 0;
-            if (valid) w = __ldcg(&tab[t]);
-            const bool isMax = valid && ((w & 0x100u) == 0) && ((w & 0xffu) == s);
-            const uint32_t grp = __match_any_sync(0xffffffffu, t);
-            const uint32_t maxBallot = __ballot_sync(0xffffffffu, isMax);
-            const uint32_t grpMax = grp & maxBallot;
-            const bool winner = isMax && ((grpMax & ltMask) == 0);
-            if (winner) __stcg(&tab[t], w | 0x100u);
-            const uint32_t winBallot = __ballot_sync(0xffffffffu, winner);
-            if (winner) {
-                keep[nKeep + __popc(winBallot & ltMask)] = v;
-                atomicAdd(&hist[s], 1u);
-            }
-            nKeep += __popc(winBallot);
-            __syncwarp();
-        }
-
-        // ---------------- score threshold (QueryMatcher::computeScoreThreshold) and selection
-        uint32_t thrScore = 0;
-        if (lane == 0) {
-            uint32_t found = 0, sc;
-            for (sc = 255; sc > 0; sc--) {
-                found += hist[sc];
-                if (found >= a.maxHits) break;
-            }
-            thrScore = max(sc, a.minDiagScore);
-        }
-        thrScore = __shfl_sync(0xffffffffu, thrScore, 0);
-        const bool needRescale = thrScore >= 255u;   // >= max-seqs elements at the 8-bit cap: rescoreHits path below
-        uint32_t nRes = 0;
-        if (identity != 0xffffffffu) {
-            if (lane == 0) { resT[0] = identity; resScore[0] = 65535; resDiag[0] = 0; }
-            nRes = 1;
-        }
-        bool dropped = false;
-        if (needRescale) {
-            // scoreIsTruncated (QueryMatcher.cpp:157-171): the cap no longer orders the top class.  rescoreHits (:525-544):
-            // uncapped diagonal score minus 255, rescaled to 0..255 against the query's self score; stable re-sort by that
-            // value; getResult maps it back with rescaleScore = maxSelf (:407-410).  Rare, so plain lane-parallel code.
-            // 1. the capped class in the reference's order (bin-major, arrival order inside a bin) -> cand[] (free by now)
-            uint32_t nL = 0;
-            for (uint32_t bin = 0; bin <= a.binMask; bin++) {
-                for (uint32_t c0 = 0; c0 < nKeep; c0 += 32) {
-                    const uint32_t c = c0 + lane;
-                    uint64_t v = 0;
-                    bool sel = false;
-                    if (c < nKeep) {
-                        v = keep[c];
-                        sel = ((uint32_t)(v >> 8) & 0xffu) == 255u && ((uint32_t)(v >> 32) & a.binMask) == bin;
-                    }
-                    const uint32_t b = __ballot_sync(0xffffffffu, sel);
-                    if (sel) cand[nL + __popc(b & ltMask)] = v & ~0xffffull;      // (target, diagonal), score byte cleared
-                    nL += __popc(b);
-                }
-            }
-            __syncwarp();
-            // 2. self score of the query on the main diagonal (scoreSingleSequence(query, 0, 0)), uncapped
-            int maxSelf = 0;
-            if (lane == 0) {
-                const uint8_t *qc = a.q.code + qBase;
-                const int8_t *qk = a.q.corr + qBase;
-                int best = 0, run = 0;
-                for (int p = 0; p < Lq; p++) {
-                    run += (int)sSub[qc[p] * AA + qc[p]] + (int)qk[p];
-                    run = max(run, 0);
-                    best = max(best, run);
-                }
-                maxSelf = min(max(best - 255, 1), 65535);
-            }
-            maxSelf = __shfl_sync(0xffffffffu, maxSelf, 0);
-            const float fltMaxSelf = (float)maxSelf;
-            // 3. rescaled 8-bit scores + their histogram
-            for (uint32_t i = lane; i < 256; i += 32) hist[i] = 0;
-            __syncwarp();
-            for (uint32_t c = lane; c < nL; c += 32) {
-                const uint64_t v = cand[c];
-                uint32_t dummy = 0;
-                const uint32_t full = (uint32_t)diagonalScore(a, sSub, qBase, Lq, (uint32_t)(v >> 32), (int)(int16_t)(uint16_t)(v >> 16), dummy);
-                const uint32_t newScore = full - 255u;
-                const float sc = (float)min(newScore, 65535u);
-                const float scaled = __fmul_rn(__fdiv_rn(sc, fltMaxSelf), 255.0f);
-                const uint32_t cnt = (uint32_t)(int)__dadd_rn((double)scaled, 0.5) & 0xffu;
-                cand[c] = v | (uint64_t)cnt;
-                atomicAdd(&hist[cnt], 1u);
-            }
-            __syncwarp();
-            // 4. stable selection by rescaled score, highest first
-            for (int s2 = 255; s2 >= 0; s2--) {
-                if (hist[s2] == 0) continue;
-                for (uint32_t c0 = 0; c0 < nL; c0 += 32) {
-                    const uint32_t c = c0 + lane;
-                    uint64_t v = 0;
-                    bool sel = false;
-                    if (c < nL) {
-                        v = cand[c];
-                        sel = (uint32_t)(v & 0xffu) == (uint32_t)s2 && (uint32_t)(v >> 32) != identity;
-                    }
-                    const uint32_t b = __ballot_sync(0xffffffffu, sel);
-                    if (sel) {
-                        const uint32_t pos = nRes + __popc(b & ltMask);
-                        if (pos < a.maxHits) {
-                            resT[pos] = (uint32_t)(v >> 32);
-                            resScore[pos] = (int)(255u + ((uint32_t)s2 * (uint32_t)maxSelf) / 255u);
-                            resDiag[pos] = (uint16_t)(v >> 16);
-                        }
-                    }
-                    nRes += __popc(b);
-                    if (nRes > a.maxHits) { dropped = true; nRes = a.maxHits; }
-                }
-            }
-            __syncwarp();
-        } else {
-        // everything strictly above the threshold survives
-        for (uint32_t c0 = 0; c0 < nKeep; c0 += 32) {
-            const uint32_t c = c0 + lane;
-            uint64_t v = 0;
-            bool sel = false;
-            if (c < nKeep) {
-                v = keep[c];
-                const uint32_t s = (uint32_t)(v >> 8) & 0xffu;
-                sel = s > thrScore && (uint32_t)(v >> 32) != identity;
-            }
-            const uint32_t b = __ballot_sync(0xffffffffu, sel);
-            if (sel) {
-                const uint32_t pos = nRes + __popc(b & ltMask);
-                if (pos < a.maxHits) {
-                    resT[pos] = (uint32_t)(v >> 32);
-                    resScore[pos] = (int)((v >> 8) & 0xffu);
-                    resDiag[pos] = (uint16_t)(v >> 16);
-                }
-            }
-            nRes += __popc(b);
-        }
-        nRes = min(nRes, a.maxHits);
-        // the threshold class fills what is left, in (id & binMask, stream order) order
-        for (uint32_t bin = 0; bin <= a.binMask; bin++) {
-            for (uint32_t c0 = 0; c0 < nKeep; c0 += 32) {
-                const uint32_t c = c0 + lane;
-                uint64_t v = 0;
-                bool sel = false;
-                if (c < nKeep) {
-                    v = keep[c];
-                    const uint32_t s = (uint32_t)(v >> 8) & 0xffu;
-                    const uint32_t t = (uint32_t)(v >> 32);
-                    sel = s == thrScore && t != identity && (t & a.binMask) == bin;
-                }
-                const uint32_t b = __ballot_sync(0xffffffffu, sel);
-                if (sel) {
-                    const uint32_t pos = nRes + __popc(b & ltMask);
-                    if (pos < a.maxHits) {
-                        resT[pos] = (uint32_t)(v >> 32);
-                        resScore[pos] = (int)((v >> 8) & 0xffu);
-                        resDiag[pos] = (uint16_t)(v >> 16);
-                    }
-                }
-                nRes += __popc(b);
-                if (nRes > a.maxHits) { dropped = true; nRes = a.maxHits; }
-            }
-        }
-        }
-        __syncwarp();
-        if (dropped) stTrunc += (lane == 0) ? 1 : 0;
-        // scores that hit the 8-bit cap are replaced by the uncapped diagonal score (QueryMatcher.cpp:410-413)
-        for (uint32_t r = lane; r < nRes && !needRescale; r += 32) {
-            if (resScore[r] >= 255 && resScore[r] != 65535) {
-                uint32_t dummy = 0;
-                resScore[r] = diagonalScore(a, sSub, qBase, Lq, resT[r], (int)(int16_t)resDiag[r], dummy);
-            }
-        }
-        __syncwarp();
-        stHits += (lane == 0) ? nRes : 0;
-
-        // ---------------- final order (score desc, id asc; identity stays first) + coverage pre-filter
-        const uint32_t first = (identity != 0xffffffffu) ? 1u : 0u;
-        sd_prefilter_hit *outQ = a.out + (size_t)q * a.maxHits;
-        uint32_t nOut = 0;
-        // rank sort: rank = number of elements that come before
-        for (uint32_t r0 = 0; r0 < nRes; r0 += 32) {
-            const uint32_t r = r0 + lane;
-            uint32_t rank = 0xffffffffu;
-            uint32_t t = 0;
-            int s = 0;
-            uint16_t dg = 0;
-            if (r < nRes) {
-                t = resT[r]; s = resScore[r]; dg = resDiag[r];
-                if (r < first) rank = 0;
-                else {
-                    rank = first;
-                    for (uint32_t j = first; j < nRes; j++) {
-                        const int sj = resScore[j];
-                        const uint32_t tj = resT[j];
-                        rank += (sj > s || (sj == s && tj < t)) ? 1u : 0u;
-                    }
-                }
-            }
-            // coverage pre-filter (Prefiltering.cpp:856-863, Util::canBeCovered Util.cpp:477-494)
-            bool pass = r < nRes;
-            if (pass && a.covThr > 0.0f && (a.covMode == 0 || a.covMode == 2 || a.covMode == 5)) {
-                const float ql = (float)Lq;
-                const float tl = (float)(a.tOff[t + 1] - a.tOff[t]);
-                if (a.covMode == 0) pass = (__fdiv_rn(ql, tl) >= a.covThr) && (__fdiv_rn(tl, ql) >= a.covThr);
-                else if (a.covMode == 2) pass = __fdiv_rn(tl, ql) >= a.covThr;
-                else pass = __fdiv_rn(fminf(tl, ql), fmaxf(tl, ql)) >= a.covThr;
-            }
-            if (r < nRes) {
-                // park (rank, pass) in the scratch result arrays' tail: write straight to the output slot by rank
-                outQ[rank].query = q;
-                outQ[rank].target = t;
-                outQ[rank].score = pass ? s : -1;      // -1 marks "filtered by coverage"; compacted below
-                outQ[rank].diag = (int16_t)dg;
-                outQ[rank].pad = 0;
-            }
-        }
-        __syncwarp();
-        __threadfence_block();
-        // compact the coverage-filtered entries in place, keeping order
-        for (uint32_t r0 = 0; r0 < nRes; r0 += 32) {
-            const uint32_t r = r0 + lane;
-            sd_prefilter_hit h;
-            bool ok = false;
-            if (r < nRes) { h = outQ[r]; ok = h.score >= 0; }
-            const uint32_t b = __ballot_sync(0xffffffffu, ok);
-            __syncwarp();
-            if (ok) outQ[nOut + __popc(b & ltMask)] = h;
-            nOut += __popc(b);
-            __syncwarp();
-        }
-        // diagResidues is accumulated per lane
-        for (int d = 16; d > 0; d >>= 1) stDiagRes += __shfl_down_sync(0xffffffffu, stDiagRes, d);
-        if (lane == 0) {
-            if (candOverflow) {
-                a.outCount[q] = 0;
-                a.failList[atomicAdd(a.nFail, 1u)] = q;
-                atomicAdd(&a.stats[ST_ERR_CAND], 1ull);
-                atomicMin(a.errQuery, q);
-            } else {
-                a.outCount[q] = nOut;
-                atomicAdd(&a.stats[ST_PROBES], stProbes);
-                atomicAdd(&a.stats[ST_MATCHES], stMatches);
-                atomicAdd(&a.stats[ST_DIAGRES], stDiagRes);
-                atomicAdd(&a.stats[ST_HITS], stHits);
-                atomicAdd(&a.stats[ST_CANDS], stCands);
-                if (stTrunc) atomicAdd(&a.stats[ST_TRUNC], stTrunc);
-            }
-        }
-        __syncwarp();
-    }
-}
+#include "prefilter_kernel.cuh"
 
 // dense[offs[q] + i] = out[q*maxHits + i]; one warp per query
 __global__ void compactHits(const sd_prefilter_hit *__restrict__ out, const uint32_t *__restrict__ count,
@@ -1003,16 +303,16 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
     for (uint32_t i = 0; i <= n; i++) idx->hostOff[i] = (uint32_t)off[i];
 
     // residues: mapped on the host, uploaded once; the masked copy is made on the device (tantan.cu)
-    std::vector<uint8_t> codes(total + SPAN);
+    std::vector<uint8_t> codes(total + 32);
     mapSequence(seqs, total, codes.data());
     std::fill(codes.begin() + total, codes.end(), (uint8_t)XCODE);
     int rc;
     cudaStream_t st = ctx->stream;
-    if ((rc = idx->raw.alloc(total + SPAN)) != SD_OK) return rc;
-    if ((rc = idx->res.alloc(total + SPAN)) != SD_OK) return rc;
+    if ((rc = idx->raw.alloc(total + 32)) != SD_OK) return rc;
+    if ((rc = idx->res.alloc(total + 32)) != SD_OK) return rc;
     if ((rc = idx->off.alloc(n + 1)) != SD_OK) return rc;
-    SD_CUDA(cudaMemcpyAsync(idx->raw.p, codes.data(), total + SPAN, cudaMemcpyHostToDevice, st));
-    SD_CUDA(cudaMemcpyAsync(idx->res.p, idx->raw.p, total + SPAN, cudaMemcpyDeviceToDevice, st));
+    SD_CUDA(cudaMemcpyAsync(idx->raw.p, codes.data(), total + 32, cudaMemcpyHostToDevice, st));
+    SD_CUDA(cudaMemcpyAsync(idx->res.p, idx->raw.p, total + 32, cudaMemcpyDeviceToDevice, st));
     SD_CUDA(cudaMemcpyAsync(idx->off.p, idx->hostOff.data(), (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     for (uint32_t i = 0; i < n; i++) idx->maxLen = std::max<uint32_t>(idx->maxLen, (uint32_t)(off[i + 1] - off[i]));
     tick("map+upload");
@@ -1085,23 +385,23 @@ extern "C" int sd_target_index_build(sd_context *ctx, const char *seqs, const ui
     // occupancy bitmap + rank, compact bucket starts
     {
         const uint32_t nWords = (NKMER + 31) / 32;
-        DevBuf<uint32_t> cnt;
-        if ((rc = idx->bmBits.alloc(2 * (size_t)nWords + 2)) || (rc = cnt.alloc(nWords + 1))) return rc;
-        idx->bmRank = idx->bmBits.p + nWords;      // bits and rank share one allocation: one persisting-L2 window covers both
+        DevBuf<uint32_t> cnt, bits, rank;
+        if ((rc = bits.alloc((size_t)nWords + 1)) || (rc = rank.alloc((size_t)nWords + 1)) || (rc = cnt.alloc(nWords + 1)) || (rc = idx->bm.alloc((size_t)nWords + 1))) return rc;
         SD_CUDA(cudaMemsetAsync(cnt.p + nWords, 0, sizeof(uint32_t), st));
-        occupancyBits<<<gridFor((uint64_t)((nWords + 31) / 32) * 32, 256), 256, 0, st>>>(kOff.p, nWords, idx->bmBits.p, cnt.p);
+        occupancyBits<<<gridFor((uint64_t)((nWords + 31) / 32) * 32, 256), 256, 0, st>>>(kOff.p, nWords, bits.p, cnt.p);
         size_t tmpBytes = 0;
-        SD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, cnt.p, idx->bmRank, (int64_t)nWords + 1, st));
+        SD_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, cnt.p, rank.p, (int64_t)nWords + 1, st));
         DevBuf<uint8_t> tmp;
         if ((rc = tmp.alloc(tmpBytes)) != SD_OK) return rc;
-        SD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, cnt.p, idx->bmRank, (int64_t)nWords + 1, st));
+        SD_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmpBytes, cnt.p, rank.p, (int64_t)nWords + 1, st));
         uint32_t nDistinct = 0;
-        SD_CUDA(cudaMemcpyAsync(&nDistinct, idx->bmRank + nWords, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SD_CUDA(cudaMemcpyAsync(&nDistinct, rank.p + nWords, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         SD_CUDA(cudaStreamSynchronize(st));
         idx->nDistinct = nDistinct;
         if ((rc = idx->rows.alloc((size_t)nDistinct + 1)) != SD_OK) return rc;
-        compactRows<<<gridFor((uint64_t)nWords * 32, 256), 256, 0, st>>>(kOff.p, idx->bmBits.p, idx->bmRank, nWords, idx->ent.p, idx->rows.p);
-        ctx->launches += 2;
+        compactRows<<<gridFor((uint64_t)nWords * 32, 256), 256, 0, st>>>(kOff.p, bits.p, rank.p, nWords, idx->ent.p, idx->rows.p);
+        interleaveBitmap<<<gridFor(nWords, 256), 256, 0, st>>>(bits.p, rank.p, nWords, idx->bm.p);
+        ctx->launches += 3;
         SD_CUDA(cudaGetLastError());
         SD_CUDA(cudaStreamSynchronize(st));
     }
@@ -1215,29 +515,76 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
 
     const uint32_t maxHits = std::min<uint32_t>((uint32_t)std::max(par->max_seqs, 1), idx->nT);
     const int binSize = par->bin_size > 0 ? par->bin_size : referenceBinSize(idx->nT);
-    static const int ctasPerSm = getenv("SD_PF_CTAS") ? atoi(getenv("SD_PF_CTAS")) : 4;
-    const uint32_t nCta = std::max(1u, std::min<uint32_t>((uint32_t)(ctx->smCount * ctasPerSm), (nq + PF_WARPS - 1) / PF_WARPS));
-    const uint32_t nWarps = nCta * PF_WARPS;
-    // first-pass capacity of the per-warp candidate lists (SD_PF_CANDCAP: test hook that forces the second pass)
-    // grows with the number of targets (long queries against 800 k targets have > 32 k candidates; re-running them in the
-    // few-warp second pass costs seconds): 32 k up to 256 k targets, 128 k at 800 k targets
-    uint32_t candCap = 32768u;
-    while (candCap < 262144u && (uint64_t)candCap * 8u < idx->nT) candCap *= 2;
-    if (getenv("SD_PF_CANDCAP")) candCap = (uint32_t)std::max(32, atoi(getenv("SD_PF_CANDCAP")));
+    uint32_t maxLq = 1;
+    for (uint32_t i = 0; i < nq; i++) maxLq = std::max(maxLq, hOff[i + 1] - hOff[i]);
 
-    ScratchBuf<uint32_t> dTable(ctx, SL_PF_TABLE), dResT(ctx, SL_PF_REST);
-    DevBuf<uint32_t> dOutCount, dNext, dFail;
-    ScratchBuf<uint64_t> dCand(ctx, SL_PF_CAND), dKeep(ctx, SL_PF_KEEP);
+    // ---- launch geometry: two CTAs per SM when the shared-memory split allows it
+    cudaFuncAttributes fa{};
+    SD_CUDA(cudaFuncGetAttributes(&fa, prefilterKernel));
+    int smemPerSm = 0, smemOptin = 0;
+    SD_CUDA(cudaDeviceGetAttribute(&smemPerSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device));
+    SD_CUDA(cudaDeviceGetAttribute(&smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    static const int ctasPerSm = getenv("SD_PF_CTAS") ? std::max(1, atoi(getenv("SD_PF_CTAS"))) : 2;
+    const size_t dynBudget = std::min<size_t>((size_t)smemOptin, (size_t)smemPerSm / ctasPerSm - 1024) - fa.sharedSizeBytes;
+    // ---- target bins: id ranges whose table (2 bytes + 1 bit per target) fits a warp's share of the dynamic shared memory;
+    // nBins is a multiple of the warps so that every round of P2 keeps all warps busy
+    uint32_t nBins = 0, tBinSize = 0, tabBytes = 0;
+    for (uint32_t rounds = 1; rounds <= 4096; rounds++) {
+        const uint32_t nb = rounds * PF_WARPS;
+        const size_t cntBytes = ((size_t)PF_WARPS * nb * 4 + 15) & ~(size_t)15;
+        if (cntBytes + PF_WARPS * 256 > dynBudget) break;
+        const size_t perWarp = ((dynBudget - cntBytes) / PF_WARPS) & ~(size_t)15;
+        uint32_t bs = (idx->nT + nb - 1) / nb;
+        bs = std::max(bs, 512u);
+        const size_t need = (((size_t)bs * 2 + 15) & ~(size_t)15) + ((((size_t)bs + 31) / 32 * 4 + 15) & ~(size_t)15);
+        if (bs <= PF_MAXBINSIZE && need <= perWarp) { nBins = nb; tBinSize = bs; tabBytes = (uint32_t)need; break; }
+    }
+    if (!nBins) { setError("prefilter: %u targets do not fit the shared-memory bin tables", idx->nT); return SD_ELIMIT; }
+    const size_t dynSmem = (((size_t)PF_WARPS * nBins * 4 + 15) & ~(size_t)15) + (size_t)PF_WARPS * tabBytes;
+    SD_CUDA(cudaFuncSetAttribute(prefilterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynSmem));
+    int occ = 0;
+    SD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prefilterKernel, PF_THREADS, dynSmem));
+    if (occ < 1) { setError("prefilter kernel does not fit an SM (%zu bytes of shared memory)", dynSmem + fa.sharedSizeBytes); return SD_ELIMIT; }
+    const uint32_t nCta = std::max(1u, std::min<uint32_t>((uint32_t)(ctx->smCount * std::min(occ, ctasPerSm)), nq));
+
+    // ---- per-CTA scratch.  Expected index entries per query position: similar k-mers per position x entries per k-mer
+    // (measured on the synthetic proteomes: 425 x nEntries / 20^6); the regions of (slice, bin) get 4x the share of the
+    // longest query, queries that still overflow are re-run by a second launch with 16x the space
+    const double hitsPerPos = 425.0 * (double)std::max<uint64_t>(idx->nEntries, 1) / (double)NKMER;
+    const double mMax = std::max(4096.0, hitsPerPos * (double)maxLq);
+    auto roundUp = [](double x, uint32_t m) { return (uint32_t)(((uint64_t)x + m - 1) / m * m); };
+    uint32_t regionCap = std::max(256u, roundUp(4.0 * mMax / ((double)PF_WARPS * nBins), 32));
+    uint32_t candCap = std::max(2048u, roundUp(mMax / 16.0, 32));
+    if (getenv("SD_PF_REGIONCAP")) regionCap = (uint32_t)std::max(32, atoi(getenv("SD_PF_REGIONCAP")));     // test hooks: force the second pass
+    if (getenv("SD_PF_CANDCAP")) candCap = (uint32_t)std::max(32, atoi(getenv("SD_PF_CANDCAP")));
+    candCap = std::min(candCap, 1u << 23);
+    // QueryMatcher.cpp:43 (SD_PF_MAXDBMATCHES: test hook, the oracle has the same knob)
+    unsigned long long maxDbMatches = 2ull * std::max<unsigned long long>(1000000ull, idx->nT);
+    if (getenv("SD_PF_MAXDBMATCHES")) maxDbMatches = strtoull(getenv("SD_PF_MAXDBMATCHES"), nullptr, 10);
+
+    ScratchBuf<uint2> dPool(ctx, SL_PF_TABLE);
+    ScratchBuf<uint64_t> dCand(ctx, SL_PF_CAND);
+    ScratchBuf<uint32_t> dCandSeq(ctx, SL_PF_CSEQ), dResT(ctx, SL_PF_REST), dResAux(ctx, SL_PF_RESD);
+    ScratchBuf<uint4> dKeep(ctx, SL_PF_KEEP);
     ScratchBuf<int32_t> dResScore(ctx, SL_PF_RESS);
-    ScratchBuf<uint16_t> dResDiag(ctx, SL_PF_RESD);
+    ScratchBuf<uint16_t> dQpack(ctx, SL_PF_QPACK);
     ScratchBuf<sd_prefilter_hit> dOut(ctx, SL_PF_OUT);
+    DevBuf<uint32_t> dOutCount, dNext, dFail;
     DevBuf<unsigned long long> dStats;
-    if ((rc = dTable.alloc((size_t)nWarps * idx->nT)) || (rc = dCand.alloc((size_t)nWarps * candCap)) || (rc = dKeep.alloc((size_t)nWarps * candCap)) ||
-        (rc = dResT.alloc((size_t)nWarps * maxHits)) || (rc = dResScore.alloc((size_t)nWarps * maxHits)) || (rc = dResDiag.alloc((size_t)nWarps * maxHits)) ||
-        (rc = dOut.alloc((size_t)nq * maxHits)) || (rc = dOutCount.alloc(nq)) || (rc = dNext.alloc(4)) || (rc = dStats.alloc(ST_N)) ||
-        (rc = dFail.alloc(nq)))
+    auto allocScratch = [&](uint32_t ctas, uint32_t rCap, uint32_t cCap, uint32_t &kCap) -> int {
+        int r;
+        kCap = (uint32_t)std::min<uint64_t>(idx->nT, (uint64_t)PF_WARPS * cCap);
+        if ((r = dPool.alloc((size_t)ctas * PF_WARPS * nBins * rCap)) || (r = dCand.alloc((size_t)ctas * PF_WARPS * cCap)) ||
+            (r = dCandSeq.alloc((size_t)ctas * PF_WARPS * cCap)) || (r = dKeep.alloc((size_t)ctas * kCap)) ||
+            (r = dResT.alloc((size_t)ctas * maxHits)) || (r = dResScore.alloc((size_t)ctas * maxHits)) || (r = dResAux.alloc((size_t)ctas * maxHits)) ||
+            (r = dQpack.alloc((size_t)ctas * (maxLq + 16))))
+            return r;
+        return SD_OK;
+    };
+    uint32_t keepCap = 0;
+    if ((rc = allocScratch(nCta, regionCap, candCap, keepCap)) || (rc = dOut.alloc((size_t)nq * maxHits)) || (rc = dOutCount.alloc(nq)) ||
+        (rc = dNext.alloc(4)) || (rc = dStats.alloc(ST_N)) || (rc = dFail.alloc(nq)))
         return rc;
-    SD_CUDA(cudaMemsetAsync(dTable.p, 0, (size_t)nWarps * idx->nT * sizeof(uint32_t), st));
     SD_CUDA(cudaMemsetAsync(dOutCount.p, 0, nq * sizeof(uint32_t), st));
     SD_CUDA(cudaMemsetAsync(dStats.p, 0, ST_N * sizeof(unsigned long long), st));
     const uint32_t initNext[4] = {0u, 0xffffffffu, 0u, 0u};     // next query, first failing query, number of overflowed queries
@@ -1245,80 +592,54 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
 
     PrefilterArgs a{};
     a.tRes = idx->res.p; a.tOff = idx->off.p; a.nT = idx->nT;
-    a.bmBits = idx->bmBits.p; a.bmRank = idx->bmRank; a.rows = idx->rows.p; a.ent = idx->ent.p;
+    a.bm = idx->bm.p; a.rows = idx->rows.p; a.ent = idx->ent.p;
     a.e3score = ctx->e3score.p; a.e3index = ctx->e3index.p; a.e3cnt = ctx->e3cnt.p; a.diagSub = dDiagSub.p;
     a.q.code = dCode.p; a.q.off = dOff.p; a.q.corr = dCorr.p; a.q.thr = dThr.p;
     a.nQ = nq; a.order = dOrder.p; a.queryFirst = query_first; a.sameDb = par->same_db;
     a.maxHits = maxHits; a.minDiagScore = (uint32_t)std::max(par->min_ungapped_score, 0);
     a.covThr = par->cov_thr; a.covMode = par->cov_mode; a.binMask = (uint32_t)binSize - 1u;
-    a.table = dTable.p; a.candCap = candCap; a.cand = dCand.p; a.keep = dKeep.p;
-    a.resT = dResT.p; a.resScore = dResScore.p; a.resDiag = dResDiag.p;
+    a.maxDbMatches = maxDbMatches;
+    a.nBins = nBins; a.binSize = tBinSize; a.binMagic = ((1ull << 40) + tBinSize - 1) / tBinSize; a.tabBytes = tabBytes;
+    a.regionCap = regionCap; a.pool = dPool.p; a.candCap = candCap; a.cand = dCand.p; a.candSeq = dCandSeq.p;
+    a.keepCap = keepCap; a.keep = dKeep.p; a.resT = dResT.p; a.resScore = dResScore.p; a.resAux = dResAux.p;
+    a.qpackG = dQpack.p; a.maxLq = maxLq + 16;
     a.out = dOut.p; a.outCount = dOutCount.p; a.stats = dStats.p; a.nextQuery = dNext.p; a.errQuery = dNext.p + 1;
     a.failList = dFail.p; a.nFail = dNext.p + 2;
+    if (getenv("SD_PF_DEBUG"))
+        fprintf(stderr, "[sd] prefilter: %u CTAs x %d threads, %zu B dynamic + %zu B static smem, %u bins of %u targets, region %u, cand %u, keep %u, maxDbMatches %llu\n",
+                nCta, PF_THREADS, dynSmem, (size_t)fa.sharedSizeBytes, nBins, tBinSize, regionCap, candCap, keepCap, maxDbMatches);
 
     SD_CUDA(cudaEventRecord(evk0, st));
-    static const int envEvict = getenv("SD_PF_EVICT") ? atoi(getenv("SD_PF_EVICT")) : 0;
-    static const int envPersist = getenv("SD_PF_PERSIST") ? atoi(getenv("SD_PF_PERSIST")) : 0;
-    static const int envGran = getenv("SD_PF_L2GRAN") ? atoi(getenv("SD_PF_L2GRAN")) : 0;
-    a.evictFirst = envEvict;
-    static const int envPrefetch = getenv("SD_PF_PREFETCH") ? atoi(getenv("SD_PF_PREFETCH")) : 0;
-    a.prefetch = envPrefetch;
-    a.debugSkip = getenv("SD_PF_SKIP") ? atoi(getenv("SD_PF_SKIP")) : 0;
-    if (envGran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)envGran);
-    if (envPersist) {
-        // the occupancy bitmap is probed once per similar k-mer: keep it in the persisting part of the L2
-        int maxPersist = 0, maxWin = 0;
-        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
-        cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
-        const size_t bmBytes = idx->bmBits.n * sizeof(uint32_t);
-        if (maxPersist > 0 && maxWin > 0) {
-            const cudaError_t e1 = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)maxPersist, bmBytes + (8u << 20)));
-            cudaStreamAttrValue av{};
-            av.accessPolicyWindow.base_ptr = (void *)idx->bmBits.p;
-            av.accessPolicyWindow.num_bytes = std::min<size_t>(bmBytes, (size_t)maxWin);
-            av.accessPolicyWindow.hitRatio = 1.0f;
-            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-            const cudaError_t e2 = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
-            if (getenv("SD_PF_DEBUG")) fprintf(stderr, "[sd] persisting L2: max %d B, window max %d B, bitmap %zu B, setLimit=%d setAttr=%d\n", maxPersist, maxWin, bmBytes, (int)e1, (int)e2);
-        } else if (getenv("SD_PF_DEBUG")) fprintf(stderr, "[sd] persisting L2 not available (max %d, window %d)\n", maxPersist, maxWin);
-    }
-    SD_CUDA(cudaFuncSetAttribute(prefilterKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_DYN_SMEM));
-    prefilterKernel<<<nCta, PF_WARPS * 32, PF_DYN_SMEM, st>>>(a);
+    prefilterKernel<<<nCta, PF_THREADS, dynSmem, st>>>(a);
     ctx->launches++;
     SD_CUDA(cudaGetLastError());
-    {   // queries with more than candCap double-hit candidates (long queries against very large target sets): second launch
-        // over just those, few warps with a 4 M entry list each
+    {   // queries whose hit / candidate lists did not fit the per-CTA scratch: second launch over just those, few CTAs with
+        // 16x the space each
         uint32_t hN[4];
         SD_CUDA(cudaMemcpyAsync(hN, dNext.p, sizeof hN, cudaMemcpyDeviceToHost, st));
         SD_CUDA(cudaStreamSynchronize(st));
         const uint32_t nFail = hN[2];
         if (nFail) {
-            const uint32_t bigCap = 1u << 22;
-            const uint32_t nCta2 = std::max(1u, std::min<uint32_t>((nFail + PF_WARPS - 1) / PF_WARPS, 16u));
-            const uint32_t nWarps2 = nCta2 * PF_WARPS;
-            DevBuf<uint64_t> dCand2, dKeep2;
+            const uint32_t nCta2 = std::max(1u, std::min<uint32_t>(nFail, std::max(1u, nCta / 16)));
             DevBuf<uint32_t> dOrder2;
-            if ((rc = dCand2.alloc((size_t)nWarps2 * bigCap)) || (rc = dKeep2.alloc((size_t)nWarps2 * bigCap)) || (rc = dOrder2.alloc(nFail))) return rc;
+            if ((rc = dOrder2.alloc(nFail))) return rc;
             SD_CUDA(cudaMemcpyAsync(dOrder2.p, dFail.p, nFail * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-            SD_CUDA(cudaMemsetAsync(dTable.p, 0, (size_t)nWarps2 * idx->nT * sizeof(uint32_t), st));      // epochs restart at 0
-            SD_CUDA(cudaMemsetAsync(dStats.p + ST_ERR_CAND, 0, sizeof(unsigned long long), st));
-            const uint32_t init2[4] = {0u, 0xffffffffu, 0u, 0u};
+            SD_CUDA(cudaMemsetAsync(dStats.p + ST_ERR_CAP, 0, sizeof(unsigned long long), st));
+            const uint32_t init2[4] = {0u, hN[1], 0u, 0u};
             SD_CUDA(cudaMemcpyAsync(dNext.p, init2, sizeof init2, cudaMemcpyHostToDevice, st));
             PrefilterArgs b = a;
-            b.order = dOrder2.p; b.nQ = nFail; b.candCap = bigCap; b.cand = dCand2.p; b.keep = dKeep2.p;
-            prefilterKernel<<<nCta2, PF_WARPS * 32, PF_DYN_SMEM, st>>>(b);
+            b.regionCap = regionCap * 16; b.candCap = std::min(candCap * 16, 1u << 23);
+            if ((rc = allocScratch(nCta2, b.regionCap, b.candCap, b.keepCap))) return rc;
+            b.pool = dPool.p; b.cand = dCand.p; b.candSeq = dCandSeq.p; b.keep = dKeep.p; b.resT = dResT.p; b.resScore = dResScore.p;
+            b.resAux = dResAux.p; b.qpackG = dQpack.p;
+            b.order = dOrder2.p; b.nQ = nFail;
+            prefilterKernel<<<nCta2, PF_THREADS, dynSmem, st>>>(b);
             ctx->launches++;
             SD_CUDA(cudaGetLastError());
             SD_CUDA(cudaStreamSynchronize(st));     // init2 and the second-pass buffers go out of scope
         }
     }
     SD_CUDA(cudaEventRecord(evk1, st));
-    if (envPersist) {
-        cudaStreamAttrValue av{};
-        av.accessPolicyWindow.num_bytes = 0;
-        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
-    }
 
     std::vector<uint32_t> hCount(nq);
     unsigned long long hStats[ST_N];
@@ -1327,7 +648,12 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     SD_CUDA(cudaMemcpyAsync(hStats, dStats.p, sizeof hStats, cudaMemcpyDeviceToHost, st));
     SD_CUDA(cudaMemcpyAsync(hNext, dNext.p, sizeof hNext, cudaMemcpyDeviceToHost, st));
     SD_CUDA(cudaStreamSynchronize(st));
-    if (hStats[ST_ERR_CAND]) { setError("prefilter: %llu queries produced more than %u diagonal candidates (first: query %u)", hStats[ST_ERR_CAND], 1u << 22, hNext[1]); return SD_ELIMIT; }
+    if (hStats[ST_ERR_OVERFLOW]) {
+        setError("prefilter: %llu queries return at least twice maxDbMatches = %llu index entries (first: query %u): the reference's repeated "
+                 "hit-buffer overflow path (QueryMatcher.cpp:296-303) is not implemented", hStats[ST_ERR_OVERFLOW], maxDbMatches, hNext[1]);
+        return SD_ELIMIT;
+    }
+    if (hStats[ST_ERR_CAP]) { setError("prefilter: %llu queries overflow the enlarged hit / candidate scratch (region %u, candidates %u)", hStats[ST_ERR_CAP], regionCap * 16, candCap * 16); return SD_ELIMIT; }
     uint64_t totalHits = 0;
     for (uint32_t i = 0; i < nq; i++) totalHits += hCount[i];
     if (hitOffsets)

@@ -1,0 +1,764 @@
+// The prefilter kernel (included by prefilter.cu inside namespace sd).
+//
+// One CTA owns one query at a time (queries handed out longest first through an atomic counter, two CTAs per SM).
+// The reference's result depends on the ORDER of the index hits of a target (double-diagonal rule,
+// CacheFriendlyOperations.cpp:196-207) and, when --max-seqs cuts, on the arrival order of the kept candidates
+// (radix bin, then stream order).  The reference makes its per-target table cache resident by binning the hit stream
+// by target id (CacheFriendlyOperations::hashIndexEntry); the same idea, laid out for an SM:
+//
+//   P1  produce   every warp takes a contiguous slice of the query's k-mer positions and walks it in stream order:
+//                 similar k-mers (KmerGenerator order, rows of (first 3-mer neighbour a, count of second-row
+//                 neighbours) flattened over positions so that every probe step has 32 busy lanes) -> occupancy
+//                 bitmap {bits, rank} (16 MB, L2 resident) -> bucket rows -> index entries.  Every hit
+//                 (target, diagonal, running number) is appended to the region of (slice, target bin) in a per-CTA pool
+//                 (global memory, re-used by every query of the CTA: stays in the L2).  Target bins are id ranges
+//                 small enough that one bin's last-diagonal table fits a warp's share of shared memory.
+//   P2  consume   warp w takes bins w, w+W, ...: for a bin it reads the regions of slice 0, 1, ... in order = the
+//                 reference's stream order restricted to the bin, and applies the double-hit rule on a SHARED-MEMORY
+//                 table (16 bits + 1 flag bit per target).  No table traffic reaches L2/HBM.
+//   P3  score     the same warp scores the bin's candidates, one candidate per lane (16-byte loads of target residues,
+//                 query row in shared memory), capped at 255.
+//   P4  best      first candidate carrying the target's maximum (keepMaxElement) by atomicMax of
+//                 (score, -candidate index) keys in the now idle table; winners go to the CTA's kept list.
+//   P5  select    CTA-wide: score histogram -> threshold, the threshold class is cut in the reference's order
+//                 (id & binMask, stream order) by a radix select on (bin, running number) keys, uncapped rescoring,
+//                 final order, coverage pre-filter, output.
+//
+// Hit-buffer overflow of the reference (QueryMatcher.cpp:43,280-320: at most maxDbMatches index entries are buffered;
+// when the next bucket would reach the limit the buffered part goes through findDuplicates with a fresh table and the
+// candidate lists are merged later): the chunk boundary is found from the running numbers after P1 (the bucket that
+// holds hit number maxDbMatches-1), P2 restarts the last-diagonal bytes at the boundary and keeps the collapse state,
+// which is exactly what findDuplicates + mergeDiagonalDuplicates produce for ONE overflow.  Two or more overflows
+// (>= 2*maxDbMatches entries for one query) go through the reference's reversed merge + intermediate keepMax
+// (QueryMatcher.cpp:296-303) and are not implemented: the query is reported and the call fails with SD_ELIMIT.
+
+constexpr int PF_WARPS = 8;              // warps per CTA
+constexpr int PF_THREADS = PF_WARPS * 32;
+constexpr int PF_UNROLL = 4;             // probe steps in flight per warp (independent bitmap loads)
+constexpr uint32_t PF_RQCAP = 64;        // row ring: (position, first-row neighbour) rows waiting to be enumerated
+constexpr uint32_t PF_HQCAP = 256;       // hit-row ring: non-empty buckets waiting for their entries
+constexpr uint32_t PF_QCAP = 2048;       // query positions staged in shared memory for the diagonal scorer
+constexpr uint32_t PF_MAXBINSIZE = 8192; // 13 bits of target-in-bin in a pool entry
+constexpr uint32_t PF_SEQBITS = 28;      // running number inside a slice; slice index above
+static_assert(PF_WARPS <= 16, "slice index must fit above the running number");
+
+struct PrefilterArgs {
+    // target side
+    const uint8_t *tRes;
+    const uint32_t *tOff;
+    uint32_t nT;
+    const uint2 *bm;           // per 32 k-mers: {occupancy bits, row of the first non-empty k-mer}
+    const uint2 *rows;         // per non-empty k-mer: {target, 1<<31 | pos} (single entry) or {start, length}
+    const uint2 *ent;          // bucket entries: (target id, first position of the k-mer in that target)
+    const int16_t *e3score;
+    const uint16_t *e3index;
+    const uint16_t *e3cnt;     // [8000][512] cumulative counts: e3cnt[x*512 + 255 - v] = #{y : score(x,y) >= v}
+    const int8_t *diagSub;     // 21x21 BLOSUM62 x2 (-0.2)
+    // query side
+    QueryBatchDev q;
+    uint32_t nQ;
+    const uint32_t *order;     // queries, longest first
+    uint32_t queryFirst;       // identity = queryFirst + q when sameDb
+    int sameDb;
+    // parameters
+    uint32_t maxHits;          // min(max_seqs, nT)
+    uint32_t minDiagScore;
+    float covThr;
+    int covMode;
+    uint32_t binMask;          // reference radix (tie order of the --max-seqs cut)
+    unsigned long long maxDbMatches;   // QueryMatcher.cpp:43
+    // target bins
+    uint32_t nBins, binSize;
+    unsigned long long binMagic;       // ceil(2^40 / binSize)
+    uint32_t tabBytes;         // shared-memory table bytes per warp (>= binSize*2 + binSize/8, multiple of 16)
+    // per-CTA scratch in global memory
+    uint32_t regionCap;        // pool entries per (slice, bin)
+    uint2 *pool;               // [cta][PF_WARPS * nBins * regionCap]
+    uint32_t candCap;          // per warp
+    uint64_t *cand;            // [cta][PF_WARPS][candCap]  t<<32 | diag<<16 | score<<8
+    uint32_t *candSeq;         // [cta][PF_WARPS][candCap]  slice<<28 | running number
+    uint32_t keepCap;          // per CTA
+    uint4 *keep;               // [cta][keepCap]  {target, diag | score<<16, seq, rescaled score}
+    uint32_t *resT;            // [cta][maxHits]
+    int32_t *resScore;
+    uint32_t *resAux;          // diag | pass<<16 ...
+    uint16_t *qpackG;          // [cta][maxLq]: staged query rows of queries longer than PF_QCAP
+    uint32_t maxLq;
+    // output
+    sd_prefilter_hit *out;     // nQ * maxHits
+    uint32_t *outCount;        // nQ
+    unsigned long long *stats;
+    uint32_t *nextQuery;
+    uint32_t *errQuery;
+    uint32_t *failList;        // queries whose lists did not fit (re-run with larger scratch)
+    uint32_t *nFail;
+};
+
+enum { ST_PROBES = 0, ST_MATCHES, ST_DIAGRES, ST_HITS, ST_CANDS, ST_TRUNC, ST_ERR_CAP, ST_ERR_OVERFLOW, ST_CHUNKED, ST_N };
+
+__device__ __forceinline__ uint2 ldgU2(const uint2 *p) { return __ldg(p); }
+
+// UngappedAlignment::computeSingelSequenceScores + scalarDiagonalScoring (UngappedAlignment.cpp:30-43,416-430), one
+// candidate per lane.  qp[p] = query code | profile correction << 8; sub32[code*32 + targetCode].
+// Target residues are read in aligned 16-byte pieces (tRes is padded by 32 bytes).
+template <bool CAPPED>
+__device__ __forceinline__ int diagonalScoreLane(const uint8_t *__restrict__ tRes, const uint32_t *__restrict__ tOff,
+                                                 const int8_t *sub32, const uint16_t *qp, int Lq, uint32_t t, int diag,
+                                                 unsigned long long &residues) {
+    const uint32_t tb = __ldg(&tOff[t]);
+    const int Lt = (int)(__ldg(&tOff[t + 1]) - tb);
+    int qs, ts, len;
+    if (diag >= 0) {
+        if (diag >= Lq) return 0;
+        qs = diag; ts = 0; len = min(Lt, Lq - diag);
+    } else {
+        if (-diag >= Lt) return 0;
+        qs = 0; ts = -diag; len = min(Lt + diag, Lq);
+    }
+    residues += (unsigned long long)len;
+    const uint32_t start = tb + (uint32_t)ts;
+    const uint32_t base = start & ~15u;
+    const int lead = (int)(start - base);
+    const uint16_t *qrow = qp + qs - lead;       // qrow[off + k] is the query row of byte k of the piece at `off`
+    int best = 0, run = 0;
+    const int end = lead + len;
+    for (int off = 0; off < end; off += 16) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(tRes + base + off));
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int pos = off + k;
+            if (pos >= lead && pos < end) {
+                const uint32_t tc = (wv[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                const uint32_t qv = qrow[pos];
+                run += (int)sub32[(qv & 0xffu) * 32u + tc] + (int)(int8_t)(qv >> 8);
+                run = max(run, 0);
+                best = max(best, run);
+            }
+        }
+        if (CAPPED && best >= 255) break;
+    }
+    return best;
+}
+
+// Shared memory: static part below + dynamic [counters: PF_WARPS*nBins u32][tables: PF_WARPS * tabBytes]
+struct PfShared {
+    int8_t sub32[AA * 32];
+    uint32_t hist[256];
+    uint2 rq[PF_WARPS][PF_RQCAP];
+    uint32_t hqc[PF_WARPS][PF_HQCAP];
+    uint16_t hqp[PF_WARPS][PF_HQCAP];
+    uint16_t qpack[PF_QCAP];
+    uint32_t sliceTotal[PF_WARPS];
+    unsigned long long sliceBase[PF_WARPS + 1];
+    unsigned long long stat[8];
+    unsigned long long selPrefix;
+    uint32_t q, fail, nKeep, nRes, nAt, thrScore, selCount, selNeed, nOut;
+    uint32_t boundSlice, boundSeq, nBound, boundSearch;
+    int maxSelf;
+};
+
+__global__ void __launch_bounds__(PF_THREADS, 2) prefilterKernel(PrefilterArgs a) {
+    __shared__ PfShared S;
+    extern __shared__ __align__(16) uint8_t sDyn[];
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t lane = tid & 31;
+    const uint32_t w = tid >> 5;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    const uint32_t nBins = a.nBins;
+    uint32_t *cntAll = reinterpret_cast<uint32_t *>(sDyn);                    // [slice][bin]
+    uint32_t *cntW = cntAll + w * nBins;
+    uint8_t *tabW = sDyn + (((size_t)PF_WARPS * nBins * 4 + 15) & ~(size_t)15) + (size_t)w * a.tabBytes;
+    uint16_t *tab16 = reinterpret_cast<uint16_t *>(tabW);                     // [binSize]  last d8 | last emitted d8 << 8
+    uint32_t *tabFlag = reinterpret_cast<uint32_t *>(tabW + (((size_t)a.binSize * 2 + 15) & ~(size_t)15));   // emitted bits
+    uint32_t *tab32 = reinterpret_cast<uint32_t *>(tabW);                     // P4 view
+    const uint32_t tabWords = a.tabBytes / 4;
+
+    uint2 *poolC = a.pool + (size_t)blockIdx.x * PF_WARPS * nBins * a.regionCap;
+    uint64_t *candW = a.cand + ((size_t)blockIdx.x * PF_WARPS + w) * a.candCap;
+    uint32_t *candSeqW = a.candSeq + ((size_t)blockIdx.x * PF_WARPS + w) * a.candCap;
+    uint4 *keepC = a.keep + (size_t)blockIdx.x * a.keepCap;
+    uint32_t *resT = a.resT + (size_t)blockIdx.x * a.maxHits;
+    int32_t *resScore = a.resScore + (size_t)blockIdx.x * a.maxHits;
+    uint32_t *resAux = a.resAux + (size_t)blockIdx.x * a.maxHits;
+    uint16_t *qpackG = a.qpackG + (size_t)blockIdx.x * a.maxLq;
+
+    for (uint32_t i = tid; i < AA * 32; i += PF_THREADS) S.sub32[i] = ((i & 31) < AA) ? a.diagSub[(i >> 5) * AA + (i & 31)] : (int8_t)0;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t qi = atomicAdd(a.nextQuery, 1u);
+            S.q = (qi < a.nQ) ? a.order[qi] : 0xffffffffu;
+            S.fail = 0; S.nKeep = 0; S.nRes = 0; S.nAt = 0; S.nBound = 0; S.nOut = 0;
+            for (int i = 0; i < 8; i++) S.stat[i] = 0;
+        }
+        __syncthreads();
+        const uint32_t q = S.q;
+        if (q == 0xffffffffu) break;
+        const uint32_t qBase = a.q.off[q];
+        const int Lq = (int)(a.q.off[q + 1] - qBase);
+        const uint32_t identity = a.sameDb ? (a.queryFirst + q) : 0xffffffffu;
+        const uint16_t *qp = (Lq <= (int)PF_QCAP) ? S.qpack : qpackG;
+
+        // ---------------- P0: counters, histogram, staged query rows
+        for (uint32_t i = tid; i < PF_WARPS * nBins; i += PF_THREADS) cntAll[i] = 0;
+        for (uint32_t i = tid; i < 256; i += PF_THREADS) S.hist[i] = 0;
+        {
+            uint16_t *dst = (Lq <= (int)PF_QCAP) ? S.qpack : qpackG;
+            for (int p = (int)tid; p < Lq; p += PF_THREADS)
+                dst[p] = (uint16_t)((uint32_t)a.q.code[qBase + p] | ((uint32_t)(uint8_t)a.q.corr[qBase + p] << 8));
+        }
+        unsigned long long stProbes = 0, stDiagRes = 0;
+
+        // ---------------- P1: hit stream of this warp's slice of positions
+        {
+            uint2 *RQ = S.rq[w];
+            uint32_t *HQc = S.hqc[w];
+            uint16_t *HQp = S.hqp[w];
+            uint32_t rqH = 0, rqN = 0, hqH = 0, hqN = 0;
+            uint32_t seqBase = 0;
+            bool overflow = false;
+            uint2 *poolW = poolC + (size_t)w * nBins * a.regionCap;
+
+            auto stageB = [&](const uint32_t n) {
+                __syncwarp();
+                uint32_t rx = 0, ry = 0, m = 0, pq = 0;
+                if (lane < n) {
+                    const uint32_t slot = (hqH + lane) & (PF_HQCAP - 1);
+                    const uint2 row = ldgU2(&a.rows[HQc[slot]]);
+                    pq = HQp[slot];
+                    rx = row.x;
+                    ry = row.y;
+                    m = (ry >> 31) ? 1u : ry;                // >= 1: only non-empty buckets are queued
+                }
+                hqH += n;
+                hqN -= n;
+                uint32_t totalM;
+                const uint32_t exclM = warpExclusiveScan(m, totalM);
+                for (uint32_t ec = 0; ec < totalM; ec += 32) {
+                    const uint32_t eidx = ec + lane;
+                    const bool valid = eidx < totalM;
+                    const uint32_t owner = warpOwnerOfSlot(exclM, m != 0, ec, lane);
+                    const uint32_t oExcl = __shfl_sync(0xffffffffu, exclM, owner);
+                    const uint32_t oX = __shfl_sync(0xffffffffu, rx, owner);
+                    const uint32_t oY = __shfl_sync(0xffffffffu, ry, owner);
+                    const uint32_t oP = __shfl_sync(0xffffffffu, pq, owner);
+                    uint32_t t = 0, j = 0, k = 0;
+                    if (valid) {
+                        k = eidx - oExcl;
+                        if (oY >> 31) { t = oX; j = oY & 0xffffu; }
+                        else { const uint2 en = ldgU2(&a.ent[oX + k]); t = en.x; j = en.y; }
+                    }
+                    const uint32_t bin = (uint32_t)(((unsigned long long)t * a.binMagic) >> 40);
+                    const uint32_t grp = __match_any_sync(0xffffffffu, valid ? bin : (0x80000000u | lane));
+                    const uint32_t leader = (uint32_t)__ffs(grp) - 1u;
+                    uint32_t old = 0;
+                    if (valid && lane == leader) { old = cntW[bin]; cntW[bin] = old + (uint32_t)__popc(grp); }
+                    old = __shfl_sync(0xffffffffu, old, leader);
+                    if (valid) {
+                        const uint32_t slot = old + (uint32_t)__popc(grp & ltMask);
+                        const uint32_t tl = t - bin * a.binSize;
+                        const uint32_t diag16 = (oP - j) & 0xffffu;
+                        if (slot < a.regionCap)
+                            poolW[(size_t)bin * a.regionCap + slot] = make_uint2(tl | (diag16 << 13) | ((k == 0 ? 1u : 0u) << 29), seqBase + lane);
+                        else overflow = true;
+                    }
+                    seqBase += min(32u, totalM - ec);
+                    __syncwarp();
+                }
+            };
+
+            auto drainRows = [&](const uint32_t n) {
+                __syncwarp();
+                uint2 row = make_uint2(0u, 0u);
+                if (lane < n) row = RQ[(rqH + lane) & (PF_RQCAP - 1)];
+                rqH += n;
+                rqN -= n;
+                const uint32_t nb = row.y & 0xffffu;
+                uint32_t total;
+                const uint32_t excl = warpExclusiveScan(nb, total);
+                stProbes += (lane == 0) ? total : 0;
+                for (uint32_t pc = 0; pc < total; pc += 32 * PF_UNROLL) {
+                    uint2 wd[PF_UNROLL];
+                    uint32_t kmerW[PF_UNROLL], pp[PF_UNROLL];
+#pragma unroll
+                    for (int j = 0; j < PF_UNROLL; j++) {
+                        const uint32_t base = pc + 32u * j;
+                        wd[j] = make_uint2(0u, 0u);
+                        kmerW[j] = 0;
+                        pp[j] = 0;
+                        if (base < total) {
+                            const uint32_t owner = warpOwnerOfSlot(excl, nb != 0, base, lane);
+                            const uint32_t oExcl = __shfl_sync(0xffffffffu, excl, owner);
+                            const uint32_t oLo = __shfl_sync(0xffffffffu, row.x, owner);
+                            const uint32_t oHi = __shfl_sync(0xffffffffu, row.y, owner);
+                            if (base + lane < total) {
+                                const uint32_t c = base + lane - oExcl;
+                                const uint32_t xc = (uint32_t)__ldg(&a.e3index[(size_t)(oLo >> 16) * N3 + c]);
+                                kmerW[j] = (oLo & 0xffffu) + N3 * xc;            // KmerGenerator.cpp:207
+                                pp[j] = oHi >> 16;
+                                wd[j] = ldgU2(&a.bm[kmerW[j] >> 5]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < PF_UNROLL; j++) {
+                        if (pc + 32u * j < total) {
+                            const uint32_t bit = kmerW[j] & 31u;
+                            const bool has = ((wd[j].x >> bit) & 1u) != 0;       // idle lanes carry bits = 0
+                            const uint32_t hb = __ballot_sync(0xffffffffu, has);
+                            if (has) {
+                                const uint32_t slot = (hqH + hqN + __popc(hb & ltMask)) & (PF_HQCAP - 1);
+                                HQc[slot] = wd[j].y + __popc(wd[j].x & ((1u << bit) - 1u));
+                                HQp[slot] = (uint16_t)pp[j];
+                            }
+                            hqN += __popc(hb);
+                        }
+                    }
+                    while (hqN >= 32) stageB(32u);
+                }
+            };
+
+            const int nPos = max(Lq - SPAN + 1, 0);
+            const int pLo = (int)(((long long)nPos * w) / PF_WARPS), pHi = (int)(((long long)nPos * (w + 1)) / PF_WARPS);
+            for (int p0 = pLo; p0 < pHi; p0 += 32) {
+                // ---- set-up of 32 positions at once (one per lane): thresholds, 3-mer rows
+                int thrL = -1, top2L = 0;
+                uint32_t i1L = 0, i2L = 0;
+                {
+                    const int pl = p0 + (int)lane;
+                    if (pl < pHi) thrL = a.q.thr[qBase + pl];
+                    if (thrL >= 0) {
+                        const uint8_t *qc = a.q.code + qBase + pl;
+                        i1L = qc[0] + 20u * qc[1] + 400u * qc[3];
+                        i2L = qc[5] + 20u * qc[8] + 400u * qc[9];
+                        const int top1 = (int)__ldg(&a.e3score[(size_t)i1L * N3]);
+                        top2L = (int)__ldg(&a.e3score[(size_t)i2L * N3]);
+                        if (top1 < thrL - top2L) thrL = -1;           // KmerGenerator.cpp:129-137: nothing reaches the threshold
+                    }
+                }
+                uint32_t active = __ballot_sync(0xffffffffu, thrL >= 0);
+                while (active) {
+                    const int src = __ffs(active) - 1;
+                    active &= active - 1;
+                    const uint32_t p = (uint32_t)(p0 + src);
+                    const int thr = __shfl_sync(0xffffffffu, thrL, src);
+                    const uint32_t i1 = __shfl_sync(0xffffffffu, i1L, src);
+                    const uint32_t i2 = __shfl_sync(0xffffffffu, i2L, src);
+                    const int cutoff1 = thr - __shfl_sync(0xffffffffu, top2L, src);
+                    const int16_t *s1 = a.e3score + (size_t)i1 * N3;
+                    const uint16_t *x1 = a.e3index + (size_t)i1 * N3;
+                    for (uint32_t a0 = 0; a0 < N3; a0 += 32) {
+                        const uint32_t ai = a0 + lane;                // N3 is a multiple of 32
+                        const int sa = (int)__ldg(&s1[ai]);
+                        const bool okA = sa >= cutoff1;
+                        const uint32_t okBallot = __ballot_sync(0xffffffffu, okA);   // a prefix of the lanes: the row is sorted
+                        if (okBallot == 0) break;
+                        if (okA) {
+                            // KmerGenerator.cpp:201: second-row elements with s2 >= thr - s1 (>= 1 because sa >= cutoff1)
+                            const uint32_t nb = countGE(a.e3cnt, i2, thr - sa);
+                            RQ[(rqH + rqN + lane) & (PF_RQCAP - 1)] = make_uint2((uint32_t)__ldg(&x1[ai]) | (i2 << 16), nb | (p << 16));
+                        }
+                        rqN += __popc(okBallot);
+                        if (rqN >= 32) drainRows(32u);
+                        if (okBallot != 0xffffffffu) break;
+                    }
+                }
+            }
+            if (rqN > 0) drainRows(rqN);
+            while (hqN > 0) stageB(min(hqN, 32u));
+            __syncwarp();
+            if (lane == 0) {
+                S.sliceTotal[w] = seqBase;
+                if (seqBase >= (1u << PF_SEQBITS)) overflow = true;
+            }
+            if (__any_sync(0xffffffffu, overflow)) { if (lane == 0) atomicOr(&S.fail, 1u); }
+        }
+        __syncthreads();
+
+        // ---------------- chunk boundary of the reference's hit buffer (see the header comment)
+        if (tid == 0) {
+            unsigned long long acc = 0;
+            for (int s = 0; s < PF_WARPS; s++) { S.sliceBase[s] = acc; acc += S.sliceTotal[s]; }
+            S.sliceBase[PF_WARPS] = acc;
+            S.stat[ST_MATCHES] = acc;
+            S.boundSearch = 0;
+            if (acc >= a.maxDbMatches) {
+                if (acc >= 2ull * a.maxDbMatches - 1ull) S.fail |= 2u;      // at least two overflows for sure
+                else {
+                    const unsigned long long x = a.maxDbMatches - 1ull;     // the bucket holding hit x opens chunk 1
+                    int s = 0;
+                    while (S.sliceBase[s + 1] <= x) s++;
+                    S.boundSlice = (uint32_t)s;
+                    S.boundSeq = (uint32_t)(x - S.sliceBase[s]);            // turned into the bucket start below
+                    S.boundSearch = 1;
+                    S.selCount = 0;
+                }
+            }
+        }
+        __syncthreads();
+        if (S.boundSearch && !S.fail) {
+            // largest bucket start (first-entry flag) <= boundSeq in slice boundSlice, over all bins
+            const uint32_t bs = S.boundSlice, bx = S.boundSeq;
+            uint32_t best = 0;
+            for (uint32_t bin = w; bin < nBins; bin += PF_WARPS) {
+                const uint32_t n = min(cntAll[bs * nBins + bin], a.regionCap);
+                const uint2 *reg = poolC + ((size_t)bs * nBins + bin) * a.regionCap;
+                for (uint32_t i = lane; i < n; i += 32) {
+                    const uint2 e = reg[i];
+                    if (((e.x >> 29) & 1u) && e.y <= bx) best = max(best, e.y);
+                }
+            }
+            atomicMax(&S.selCount, best);
+            __syncthreads();
+            if (tid == 0) {
+                S.boundSeq = S.selCount;
+                S.nBound = 1;
+                // a second overflow inside chunk 1?
+                const unsigned long long g = S.sliceBase[bs] + S.boundSeq;
+                if (S.sliceBase[PF_WARPS] - g >= a.maxDbMatches) S.fail |= 2u;
+            }
+            __syncthreads();
+        }
+
+        // ---------------- P2-P4: per warp, bin by bin
+        if (!S.fail) {
+            const uint32_t nBound = S.nBound, boundSlice = S.boundSlice, boundSeq = S.boundSeq;
+            bool overflow = false;
+            unsigned long long stCands = 0;
+            for (uint32_t bin = w; bin < nBins; bin += PF_WARPS) {
+                const uint32_t binBase = bin * a.binSize;
+                for (uint32_t i = lane; i < tabWords; i += 32) tab32[i] = 0u;
+                __syncwarp();
+                uint32_t nC = 0;
+                // ---- P2: double-hit rule in stream order (CacheFriendlyOperations::findDuplicates restated per target)
+                auto rule = [&](const uint2 *reg, const uint32_t s, const uint32_t lo, const uint32_t hi) {
+                    for (uint32_t e0 = lo; e0 < hi; e0 += 32) {
+                        const bool validE = e0 + lane < hi;
+                        uint32_t ex = 0, ey = 0;
+                        if (validE) { const uint2 e = reg[e0 + lane]; ex = e.x; ey = e.y; }
+                        const uint32_t tl = validE ? (ex & 0x1fffu) : (0x80000000u | lane);     // unique dummy for idle lanes
+                        const uint32_t diag16 = (ex >> 13) & 0xffffu;
+                        const uint32_t d8 = diag16 & 0xffu;
+                        const uint32_t grp = __match_any_sync(0xffffffffu, tl);
+                        uint32_t old = 0, oldFlag = 0;
+                        if (validE) { old = tab16[tl]; oldFlag = (tabFlag[tl >> 5] >> (tl & 31u)) & 1u; }
+                        const uint32_t lowerG = grp & ltMask;
+                        const int prevLane = lowerG ? (31 - __clz(lowerG)) : -1;
+                        uint32_t prevD8 = __shfl_sync(0xffffffffu, d8, prevLane >= 0 ? prevLane : (int)lane);
+                        if (prevLane < 0) prevD8 = old & 0xffu;
+                        const bool emit = validE && (d8 == prevD8);
+                        const uint32_t emitBallot = __ballot_sync(0xffffffffu, emit);
+                        const uint32_t grpE = grp & emitBallot;
+                        const uint32_t lowerE = grpE & ltMask;
+                        const int prevELane = lowerE ? (31 - __clz(lowerE)) : -1;
+                        uint32_t prevED8 = __shfl_sync(0xffffffffu, d8, prevELane >= 0 ? prevELane : (int)lane);
+                        bool prevEExists = true;
+                        if (prevELane < 0) { prevED8 = old >> 8; prevEExists = oldFlag != 0; }
+                        const bool isCand = emit && !(prevEExists && prevED8 == d8);
+                        const int lastELane = grpE ? (31 - __clz(grpE)) : -1;
+                        const uint32_t lastED8 = __shfl_sync(0xffffffffu, d8, lastELane >= 0 ? lastELane : (int)lane);
+                        if (validE && (grp >> lane) == 1u) {        // last hit of this target in the step
+                            tab16[tl] = (uint16_t)(d8 | ((lastELane >= 0 ? lastED8 : (old >> 8)) << 8));
+                            if (lastELane >= 0 && !oldFlag) atomicOr(&tabFlag[tl >> 5], 1u << (tl & 31u));
+                        }
+                        const uint32_t candBallot = __ballot_sync(0xffffffffu, isCand);
+                        if (isCand) {
+                            const uint32_t pos = nC + __popc(candBallot & ltMask);
+                            if (pos < a.candCap) {
+                                candW[pos] = ((uint64_t)(binBase + tl) << 32) | ((uint64_t)diag16 << 16);
+                                candSeqW[pos] = (s << PF_SEQBITS) | ey;
+                            }
+                        }
+                        nC += __popc(candBallot);
+                        __syncwarp();
+                    }
+                };
+                bool resetPending = nBound != 0;
+                for (uint32_t s = 0; s < PF_WARPS; s++) {
+                    const uint32_t n = cntAll[s * nBins + bin];
+                    const uint2 *reg = poolC + ((size_t)s * nBins + bin) * a.regionCap;
+                    uint32_t split = n;
+                    if (resetPending && s >= boundSlice) {
+                        split = 0;
+                        if (s == boundSlice) {
+                            // entries are ordered by running number: count those before the boundary
+                            uint32_t c = 0;
+                            for (uint32_t i = lane; i < n; i += 32) c += (reg[i].y < boundSeq) ? 1u : 0u;
+                            for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+                            split = c;
+                        }
+                        rule(reg, s, 0u, split);
+                        // chunk 1 starts: the reference runs findDuplicates on a cleared table; the collapse state (last
+                        // emitted diagonal) lives on through mergeDiagonalDuplicates
+                        for (uint32_t i = lane; i < a.binSize; i += 32) tab16[i] &= 0xff00u;
+                        __syncwarp();
+                        resetPending = false;
+                        rule(reg, s, split, n);
+                    } else rule(reg, s, 0u, n);
+                }
+                if (nC > a.candCap) { overflow = true; nC = a.candCap; }
+                stCands += (lane == 0) ? nC : 0;
+                __syncwarp();
+                // ---- P3: diagonal scores, one candidate per lane, capped at 255 (UngappedAlignment::align)
+                for (uint32_t c0 = 0; c0 < nC; c0 += 32) {
+                    const uint32_t c = c0 + lane;
+                    if (c < nC) {
+                        const uint64_t v = candW[c];
+                        const int sc = diagonalScoreLane<true>(a.tRes, a.tOff, S.sub32, qp, Lq, (uint32_t)(v >> 32), (int)(int16_t)(uint16_t)(v >> 16), stDiagRes);
+                        candW[c] = v | ((uint64_t)min(sc, 255) << 8);
+                    }
+                }
+                __syncwarp();
+                // ---- P4: keepMaxScoreElementOnly: first candidate (stream order) carrying the target's maximum
+                for (uint32_t lo = 0; lo < a.binSize; lo += tabWords) {
+                    for (uint32_t i = lane; i < tabWords; i += 32) tab32[i] = 0u;
+                    __syncwarp();
+                    for (uint32_t c = lane; c < nC; c += 32) {
+                        const uint64_t v = candW[c];
+                        const uint32_t tl = (uint32_t)(v >> 32) - binBase - lo;
+                        if (tl < tabWords) atomicMax(&tab32[tl], ((uint32_t)((v >> 8) & 0xffu) << 24) | (0xffffffu - c));
+                    }
+                    __syncwarp();
+                    for (uint32_t c0 = 0; c0 < nC; c0 += 32) {
+                        const uint32_t c = c0 + lane;
+                        bool win = false;
+                        uint64_t v = 0;
+                        if (c < nC) {
+                            v = candW[c];
+                            const uint32_t tl = (uint32_t)(v >> 32) - binBase - lo;
+                            win = tl < tabWords && tab32[tl] == (((uint32_t)((v >> 8) & 0xffu) << 24) | (0xffffffu - c));
+                        }
+                        const uint32_t wb = __ballot_sync(0xffffffffu, win);
+                        uint32_t base = 0;
+                        if (lane == 0 && wb) base = atomicAdd(&S.nKeep, (uint32_t)__popc(wb));
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        if (win) {
+                            const uint32_t pos = base + __popc(wb & ltMask);
+                            const uint32_t sc = (uint32_t)(v >> 8) & 0xffu;
+                            if (pos < a.keepCap) keepC[pos] = make_uint4((uint32_t)(v >> 32), ((uint32_t)(v >> 16) & 0xffffu) | (sc << 16), candSeqW[c], 0u);
+                            atomicAdd(&S.hist[sc], 1u);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            if (__any_sync(0xffffffffu, overflow)) { if (lane == 0) atomicOr(&S.fail, 1u); }
+            for (int d = 16; d > 0; d >>= 1) stDiagRes += __shfl_down_sync(0xffffffffu, stDiagRes, d);
+            if (lane == 0) {
+                atomicAdd(&S.stat[ST_DIAGRES], stDiagRes);
+                atomicAdd(&S.stat[ST_CANDS], stCands);
+            }
+        }
+        if (lane == 0) atomicAdd(&S.stat[ST_PROBES], stProbes);
+        __syncthreads();
+        if (tid == 0 && S.nKeep > a.keepCap) S.fail |= 1u;
+        __syncthreads();
+        if (S.fail) {
+            if (tid == 0) {
+                a.outCount[q] = 0;
+                if (S.fail & 2u) { atomicAdd(&a.stats[ST_ERR_OVERFLOW], 1ull); atomicMin(a.errQuery, q); }
+                else { a.failList[atomicAdd(a.nFail, 1u)] = q; atomicAdd(&a.stats[ST_ERR_CAP], 1ull); }
+            }
+            continue;
+        }
+
+        // ---------------- P5: threshold (QueryMatcher::computeScoreThreshold), selection, final order, output
+        const uint32_t nKeep = S.nKeep;
+        if (tid == 0) {
+            uint32_t found = 0, sc;
+            for (sc = 255; sc > 0; sc--) {
+                found += S.hist[sc];
+                if (found >= a.maxHits) break;
+            }
+            S.thrScore = max(sc, a.minDiagScore);
+            const uint32_t first = (identity != 0xffffffffu) ? 1u : 0u;
+            if (first) { resT[0] = identity; resScore[0] = 65535; resAux[0] = 0; }
+            S.nRes = first;
+        }
+        __syncthreads();
+        const uint32_t thrScore = S.thrScore;
+        const bool needRescale = thrScore >= 255u;   // >= max-seqs elements at the 8-bit cap: rescoreHits path
+        int maxSelf = 0;
+        if (needRescale) {
+            // scoreIsTruncated (QueryMatcher.cpp:157-171): the cap no longer orders the top class.  rescoreHits (:525-544):
+            // uncapped diagonal score minus 255, rescaled to 0..255 against the query's self score; stable re-sort by that
+            // value; getResult maps it back with rescaleScore = maxSelf (:407-410).
+            if (tid == 0) {
+                int best = 0, run = 0;
+                for (int p = 0; p < Lq; p++) {
+                    const uint32_t qv = qp[p];
+                    run += (int)S.sub32[(qv & 0xffu) * 32u + (qv & 0xffu)] + (int)(int8_t)(qv >> 8);
+                    run = max(run, 0);
+                    best = max(best, run);
+                }
+                S.maxSelf = min(max(best - 255, 1), 65535);
+            }
+            __syncthreads();
+            maxSelf = S.maxSelf;
+            const float fltMaxSelf = (float)maxSelf;
+            for (uint32_t i = tid; i < nKeep; i += PF_THREADS) {
+                uint4 v = keepC[i];
+                if ((v.y >> 16) == 255u) {
+                    unsigned long long dummy = 0;
+                    const uint32_t full = (uint32_t)diagonalScoreLane<false>(a.tRes, a.tOff, S.sub32, qp, Lq, v.x, (int)(int16_t)(uint16_t)(v.y & 0xffffu), dummy);
+                    const uint32_t newScore = full - 255u;
+                    const float sc = (float)min(newScore, 65535u);
+                    const float scaled = __fmul_rn(__fdiv_rn(sc, fltMaxSelf), 255.0f);
+                    v.w = (uint32_t)(int)__dadd_rn((double)scaled, 0.5) & 0xffu;
+                    keepC[i] = v;
+                }
+            }
+            __syncthreads();
+        } else {
+            // everything strictly above the threshold survives (fewer than maxHits elements by construction)
+            for (uint32_t i0 = 0; i0 < nKeep; i0 += PF_THREADS) {
+                const uint32_t i = i0 + tid;
+                bool sel = false;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (i < nKeep) { v = keepC[i]; sel = (v.y >> 16) > thrScore && v.x != identity; }
+                if (sel) {
+                    const uint32_t pos = atomicAdd(&S.nRes, 1u);
+                    if (pos < a.maxHits) { resT[pos] = v.x; resScore[pos] = (int)(v.y >> 16); resAux[pos] = v.y & 0xffffu; }
+                }
+            }
+            __syncthreads();
+        }
+        // the threshold class fills what is left in the reference's order: (rescaled score desc,) id & binMask, stream order
+        const uint32_t classScore = needRescale ? 255u : thrScore;
+        {
+            uint32_t c = 0;
+            for (uint32_t i = tid; i < nKeep; i += PF_THREADS) {
+                const uint4 v = keepC[i];
+                c += ((v.y >> 16) == classScore && v.x != identity) ? 1u : 0u;
+            }
+            for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+            if (lane == 0 && c) atomicAdd(&S.nAt, c);
+        }
+        __syncthreads();
+        const uint32_t nResAbove = min(S.nRes, a.maxHits);
+        const uint32_t room = a.maxHits - nResAbove;
+        const uint32_t nAt = S.nAt;
+        unsigned long long selLimit = ~0ull;             // keys <= selLimit are taken
+        auto keyOf = [&](const uint4 &v) -> unsigned long long {
+            return ((unsigned long long)(255u - (needRescale ? v.w : 255u)) << 40) | ((unsigned long long)(v.x & a.binMask) << 32) | v.z;
+        };
+        if (nAt > room) {
+            // radix select of the room-th smallest key (keys are distinct: the running number is)
+            if (room == 0) selLimit = 0ull;              // nothing fits; key 0 cannot occur together with room == 0 ... guard below
+            else {
+                if (tid == 0) { S.selPrefix = 0ull; S.selNeed = room; }
+                __syncthreads();
+                for (int bit = needRescale ? 47 : 43; bit >= 0; bit--) {
+                    if (tid == 0) S.selCount = 0;
+                    __syncthreads();
+                    const unsigned long long prefix = S.selPrefix;
+                    uint32_t c = 0;
+                    for (uint32_t i = tid; i < nKeep; i += PF_THREADS) {
+                        const uint4 v = keepC[i];
+                        if ((v.y >> 16) == classScore && v.x != identity) {
+                            const unsigned long long k = keyOf(v);
+                            c += ((k >> bit) == (prefix >> bit)) ? 1u : 0u;      // matches the prefix with this bit 0
+                        }
+                    }
+                    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+                    if (lane == 0 && c) atomicAdd(&S.selCount, c);
+                    __syncthreads();
+                    if (tid == 0) {
+                        if (S.selNeed > S.selCount) { S.selNeed -= S.selCount; S.selPrefix = prefix | (1ull << bit); }
+                    }
+                    __syncthreads();
+                }
+                selLimit = S.selPrefix;
+            }
+        }
+        for (uint32_t i0 = 0; i0 < nKeep; i0 += PF_THREADS) {
+            const uint32_t i = i0 + tid;
+            bool sel = false;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (i < nKeep) {
+                v = keepC[i];
+                sel = (v.y >> 16) == classScore && v.x != identity && room > 0 && keyOf(v) <= selLimit;
+            }
+            if (sel) {
+                const uint32_t pos = atomicAdd(&S.nRes, 1u);
+                if (pos < a.maxHits) {
+                    resT[pos] = v.x;
+                    resScore[pos] = needRescale ? (int)(255u + (v.w * (uint32_t)maxSelf) / 255u) : (int)(v.y >> 16);
+                    resAux[pos] = v.y & 0xffffu;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t nRes = min(S.nRes, a.maxHits);
+        // scores that hit the 8-bit cap are replaced by the uncapped diagonal score (QueryMatcher.cpp:410-413)
+        if (!needRescale) {
+            for (uint32_t r = tid; r < nRes; r += PF_THREADS) {
+                if (resScore[r] >= 255 && resScore[r] != 65535) {
+                    unsigned long long dummy = 0;
+                    resScore[r] = diagonalScoreLane<false>(a.tRes, a.tOff, S.sub32, qp, Lq, resT[r], (int)(int16_t)(uint16_t)resAux[r], dummy);
+                }
+            }
+        }
+        __syncthreads();
+        // ---------------- final order (score desc, id asc; identity stays first) + coverage pre-filter
+        const uint32_t first = (identity != 0xffffffffu) ? 1u : 0u;
+        sd_prefilter_hit *outQ = a.out + (size_t)q * a.maxHits;
+        for (uint32_t r = tid; r < nRes; r += PF_THREADS) {
+            const uint32_t t = resT[r];
+            const int s = resScore[r];
+            uint32_t rank = 0;
+            if (r >= first) {
+                rank = first;
+                for (uint32_t j = first; j < nRes; j++) {
+                    const int sj = resScore[j];
+                    const uint32_t tj = resT[j];
+                    rank += (sj > s || (sj == s && tj < t)) ? 1u : 0u;
+                }
+            }
+            // coverage pre-filter (Prefiltering.cpp:856-863, Util::canBeCovered Util.cpp:477-494)
+            bool pass = true;
+            if (a.covThr > 0.0f && (a.covMode == 0 || a.covMode == 2 || a.covMode == 5)) {
+                const float ql = (float)Lq;
+                const float tl = (float)(a.tOff[t + 1] - a.tOff[t]);
+                if (a.covMode == 0) pass = (__fdiv_rn(ql, tl) >= a.covThr) && (__fdiv_rn(tl, ql) >= a.covThr);
+                else if (a.covMode == 2) pass = __fdiv_rn(tl, ql) >= a.covThr;
+                else pass = __fdiv_rn(fminf(tl, ql), fmaxf(tl, ql)) >= a.covThr;
+            }
+            outQ[rank].query = q;
+            outQ[rank].target = t;
+            outQ[rank].score = pass ? s : -1;      // -1 marks "filtered by coverage"; compacted below
+            outQ[rank].diag = (int16_t)(uint16_t)resAux[r];
+            outQ[rank].pad = 0;
+        }
+        __syncthreads();
+        // compact the coverage-filtered entries in place, keeping order (warp 0)
+        if (w == 0) {
+            uint32_t nOut = 0;
+            for (uint32_t r0 = 0; r0 < nRes; r0 += 32) {
+                const uint32_t r = r0 + lane;
+                sd_prefilter_hit h;
+                bool ok = false;
+                if (r < nRes) { h = outQ[r]; ok = h.score >= 0; }
+                const uint32_t b = __ballot_sync(0xffffffffu, ok);
+                __syncwarp();
+                if (ok) outQ[nOut + __popc(b & ltMask)] = h;
+                nOut += __popc(b);
+                __syncwarp();
+            }
+            if (lane == 0) {
+                a.outCount[q] = nOut;
+                const uint32_t eligible = (needRescale ? 0u : (nResAbove - first)) + nAt;
+                atomicAdd(&a.stats[ST_PROBES], S.stat[ST_PROBES]);
+                atomicAdd(&a.stats[ST_MATCHES], S.stat[ST_MATCHES]);
+                atomicAdd(&a.stats[ST_DIAGRES], S.stat[ST_DIAGRES]);
+                atomicAdd(&a.stats[ST_HITS], (unsigned long long)nRes);
+                atomicAdd(&a.stats[ST_CANDS], S.stat[ST_CANDS]);
+                if (eligible + first > nRes) atomicAdd(&a.stats[ST_TRUNC], 1ull);
+                if (S.nBound) atomicAdd(&a.stats[ST_CHUNKED], 1ull);
+            }
+        }
+    }
+}

@@ -100,12 +100,13 @@ class OrcPrefParams(ctypes.Structure):
     _fields_ = [("sensitivity", ctypes.c_float), ("maxSeqs", ctypes.c_int), ("minDiagScore", ctypes.c_int),
                 ("covThr", ctypes.c_float), ("covMode", ctypes.c_int), ("mask", ctypes.c_int),
                 ("maskProb", ctypes.c_float), ("compBias", ctypes.c_int), ("binSize", ctypes.c_int),
-                ("sameDB", ctypes.c_int)]
+                ("sameDB", ctypes.c_int), ("maxDbMatches", ctypes.c_uint64), ("foundDiagonalsSize", ctypes.c_uint64)]
 
 
 class OrcPrefStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in
-                ("probes", "matches", "diagResidues", "queryResidues", "hits", "candidates", "truncated")]
+                ("probes", "matches", "diagResidues", "queryResidues", "hits", "candidates", "truncated",
+                 "overflowQueries", "multiOverflowQueries")]
 
 
 ORC_HIT_DTYPE = np.dtype([("query", "<u4"), ("target", "<u4"), ("score", "<i4"), ("diag", "<i2")], align=True)
@@ -131,7 +132,7 @@ def oracle():
 
 def default_pref_params(**kw):
     p = OrcPrefParams(sensitivity=5.7, maxSeqs=300, minDiagScore=15, covThr=0.8, covMode=2, mask=1,
-                      maskProb=0.9, compBias=1, binSize=2, sameDB=1)
+                      maskProb=0.9, compBias=1, binSize=2, sameDB=1, maxDbMatches=0, foundDiagonalsSize=0)
     for k, v in kw.items():
         setattr(p, k, v)
     return p

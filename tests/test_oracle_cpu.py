@@ -243,3 +243,53 @@ def test_oracle_profile_align_vs_reference(ref_setdb, ref_profile_db):
     for k in pkeys:
         assert [l for l in ref[int(k)].split(b"\n") if l] == mine[int(k)], "profile %d" % k
     assert st["passed"] > len(pkeys) and st["wordMode"] > 0
+
+
+def _overflow_family(seed=11, n_a=6000, len_a=560, n_b=6000, len_b=1100, n_unrel=200):
+    """Two huge families (92-99 % identity) + unrelated proteins, shuffled: a query from family A returns > 2*10^6 index entries
+    (one overflow of the reference's hit buffer, QueryMatcher.cpp:43,280), one from family B > 4*10^6 (two overflows)."""
+    rng = np.random.default_rng(seed)
+    anc_a = rng.choice(20, size=len_a, p=synth.BACKGROUND).astype(np.uint8)
+    anc_b = rng.choice(20, size=len_b, p=synth.BACKGROUND).astype(np.uint8)
+    seqs = [synth.LETTERS[synth._mutate(rng, anc_a, rng.uniform(0.92, 0.99))].tobytes() for _ in range(n_a)]
+    seqs += [synth.LETTERS[synth._mutate(rng, anc_b, rng.uniform(0.92, 0.99))].tobytes() for _ in range(n_b)]
+    seqs += [synth.LETTERS[rng.choice(20, size=int(rng.integers(80, 400)), p=synth.BACKGROUND)].tobytes() for _ in range(n_unrel)]
+    perm = rng.permutation(len(seqs))
+    inv = np.argsort(perm)
+    targets = [seqs[i] for i in perm]
+    q_idx = [int(inv[i]) for i in (0, 1, 2, n_a, n_a + 1, n_a + 2, n_a + n_b, n_a + n_b + 1)]
+    return targets, [targets[i] for i in q_idx]
+
+
+def _write_plain_fasta(path, seqs, prefix):
+    with open(path, "wb") as f:
+        for i, s in enumerate(seqs):
+            f.write(b">%s%d\n%s\n" % (prefix.encode(), i, s))
+
+
+def test_oracle_prefilter_hit_buffer_overflow_vs_reference():
+    """Queries whose index hits overflow the reference's hit buffer (maxDbMatches = 2*max(10^6, dbSize), QueryMatcher.cpp:43): the
+    buffered part is reduced with a fresh double-hit table and merged later (:280-320, :322-333); from the second overflow on
+    the reversed merge + intermediate keepMax (:296-303) applies.  The oracle must follow the reference hit for hit."""
+    if not helpers.have_ref():
+        pytest.skip("oracle/_ref/spacedust not built")
+    targets, queries = _overflow_family()
+    d = tempfile.mkdtemp(prefix="sdref_")
+    try:
+        _write_plain_fasta(os.path.join(d, "t.faa"), targets, "t")
+        _write_plain_fasta(os.path.join(d, "q.faa"), queries, "q")
+        helpers.run_ref(["createdb", os.path.join(d, "t.faa"), os.path.join(d, "T"), "--shuffle", "0", "-v", "1"])
+        helpers.run_ref(["createdb", os.path.join(d, "q.faa"), os.path.join(d, "Q"), "--shuffle", "0", "-v", "1"])
+        helpers.run_ref(["prefilter", os.path.join(d, "Q"), os.path.join(d, "T"), os.path.join(d, "pref"), "-s", "5.7", "--max-seqs", "300",
+                         "-c", "0.8", "--cov-mode", "2", "--min-ungapped-score", "15", "--threads", "4", "-v", "1"])
+        tkeys, tbuf, toff = helpers.load_seqdb(os.path.join(d, "T"))
+        qkeys, qbuf, qoff = helpers.load_seqdb(os.path.join(d, "Q"))
+        hits, st = helpers.orc_prefilter(tbuf, toff, qbuf, qoff, helpers.default_pref_params(sameDB=0))
+        assert st["overflowQueries"] >= 2 and st["multiOverflowQueries"] >= 1 and st["overflowQueries"] > st["multiOverflowQueries"], st
+        mine = helpers.hits_to_lines(hits, qkeys, tkeys)
+        ref = helpers.read_db(os.path.join(d, "pref"))
+        for k in qkeys:
+            r = [l for l in ref[int(k)].split(b"\n") if l]
+            assert r == mine[int(k)], "query %d" % k
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
