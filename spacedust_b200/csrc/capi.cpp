@@ -79,8 +79,7 @@ extern "C" void sd_context_destroy(sd_context *ctx) {
     cudaSetDevice(ctx->device);
     for (auto &sl : ctx->devSlot) if (sl.p) cudaFree(sl.p);
     for (auto &sl : ctx->pinSlot) if (sl.p) cudaFreeHost(sl.p);
-    ctx->e3score.release();
-    ctx->e3index.release();
+    ctx->e3pair.release();
     ctx->e3cnt.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -227,8 +227,12 @@ void lineKeyEvalue(const char *ls, const char *le, uint32_t &key, double &evalue
 int modSubtractdbs(int argc, char **argv) {
     std::map<std::string, std::string> flags;
     std::vector<std::string> pos = positional(argc, argv, &flags);
-    if (pos.size() != 3) fail("usage: sdb200 subtractdbs <leftDB> <rightDB> <outDB> [--e-profile X]");
-    const double thr = flags.count("--e-profile") ? strtod(flags["--e-profile"].c_str(), nullptr) : 0.001;
+    if (pos.size() != 3) fail("usage: sdb200 subtractdbs <leftDB> <rightDB> <outDB> [-e X] [--e-profile X]");
+    // subtractdbs.cpp:17: the threshold is the smaller of -e (default 0.001) and --e-profile (default 0.001, Parameters.cpp)
+    const double evalThr = flags.count("-e") ? strtod(flags["-e"].c_str(), nullptr) : 0.001;
+    const double evalProfile = flags.count("--e-profile") ? strtod(flags["--e-profile"].c_str(), nullptr) : 0.001;
+    const double thr = std::min(evalThr, evalProfile);
+    if (flags.count("--compressed") && atoi(flags["--compressed"].c_str()) != 0) fail("--compressed 1 is not implemented");
     sddb::Db left, right;
     std::string err;
     if (!left.open(pos[0], err)) fail(err);

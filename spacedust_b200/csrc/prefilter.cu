@@ -160,6 +160,12 @@ __global__ void compactRows(const uint32_t *__restrict__ kOff, const uint32_t *_
     rows[rank[w] + __popc(b & ((1u << (k & 31)) - 1u))] = row;
 }
 
+// sorted neighbour rows as one word per element: score (low half) | 3-mer index (high half)
+__global__ void pairExt3(const int16_t *__restrict__ score, const uint16_t *__restrict__ index, uint64_t n, uint32_t *__restrict__ pair) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pair[i] = (uint32_t)(uint16_t)score[i] | ((uint32_t)index[i] << 16);
+}
+
 // {bits, rank} side by side: one 8-byte load answers a probe (empty or not) and gives the row of a non-empty k-mer
 __global__ void interleaveBitmap(const uint32_t *__restrict__ bits, const uint32_t *__restrict__ rank, uint32_t nWords,
                                  uint2 *__restrict__ bm) {
@@ -245,12 +251,18 @@ static int ensureExt3(sd_context *ctx) {
     std::vector<uint16_t> ix, cn;
     buildExt3(ctx->seedMat, sc, ix, cn);
     int rc;
-    if ((rc = ctx->e3score.alloc(sc.size())) != SD_OK) return rc;
-    if ((rc = ctx->e3index.alloc(ix.size())) != SD_OK) return rc;
+    DevBuf<int16_t> dScore;
+    DevBuf<uint16_t> dIndex;
+    if ((rc = dScore.alloc(sc.size())) != SD_OK) return rc;
+    if ((rc = dIndex.alloc(ix.size())) != SD_OK) return rc;
+    if ((rc = ctx->e3pair.alloc(sc.size())) != SD_OK) return rc;
     if ((rc = ctx->e3cnt.alloc(cn.size())) != SD_OK) return rc;
     SD_CUDA(cudaMemcpyAsync(ctx->e3cnt.p, cn.data(), cn.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
-    SD_CUDA(cudaMemcpyAsync(ctx->e3score.p, sc.data(), sc.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
-    SD_CUDA(cudaMemcpyAsync(ctx->e3index.p, ix.data(), ix.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(cudaMemcpyAsync(dScore.p, sc.data(), sc.size() * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(cudaMemcpyAsync(dIndex.p, ix.data(), ix.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->stream));
+    pairExt3<<<gridFor(sc.size(), 256), 256, 0, ctx->stream>>>(dScore.p, dIndex.p, sc.size(), ctx->e3pair.p);
+    ctx->launches++;
+    SD_CUDA(cudaGetLastError());
     SD_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->haveExt3 = true;
     return SD_OK;
@@ -568,6 +580,8 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     ScratchBuf<uint4> dKeep(ctx, SL_PF_KEEP);
     ScratchBuf<int32_t> dResScore(ctx, SL_PF_RESS);
     ScratchBuf<uint16_t> dQpack(ctx, SL_PF_QPACK);
+    ScratchBuf<uint4> dPosInfo(ctx, SL_PF_POSINFO);
+    ScratchBuf<uint32_t> dPosPrefix(ctx, SL_PF_POSPREFIX);
     ScratchBuf<sd_prefilter_hit> dOut(ctx, SL_PF_OUT);
     DevBuf<uint32_t> dOutCount, dNext, dFail;
     DevBuf<unsigned long long> dStats;
@@ -577,7 +591,8 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
         if ((r = dPool.alloc((size_t)ctas * PF_WARPS * nBins * rCap)) || (r = dCand.alloc((size_t)ctas * PF_WARPS * cCap)) ||
             (r = dCandSeq.alloc((size_t)ctas * PF_WARPS * cCap)) || (r = dKeep.alloc((size_t)ctas * kCap)) ||
             (r = dResT.alloc((size_t)ctas * maxHits)) || (r = dResScore.alloc((size_t)ctas * maxHits)) || (r = dResAux.alloc((size_t)ctas * maxHits)) ||
-            (r = dQpack.alloc((size_t)ctas * (maxLq + 16))))
+            (r = dQpack.alloc((size_t)ctas * (maxLq + 16))) || (r = dPosInfo.alloc((size_t)ctas * (maxLq + 16))) ||
+            (r = dPosPrefix.alloc((size_t)ctas * (maxLq + 16))))
             return r;
         return SD_OK;
     };
@@ -593,7 +608,7 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     PrefilterArgs a{};
     a.tRes = idx->res.p; a.tOff = idx->off.p; a.nT = idx->nT;
     a.bm = idx->bm.p; a.rows = idx->rows.p; a.ent = idx->ent.p;
-    a.e3score = ctx->e3score.p; a.e3index = ctx->e3index.p; a.e3cnt = ctx->e3cnt.p; a.diagSub = dDiagSub.p;
+    a.e3pair = ctx->e3pair.p; a.e3cnt = ctx->e3cnt.p; a.diagSub = dDiagSub.p;
     a.q.code = dCode.p; a.q.off = dOff.p; a.q.corr = dCorr.p; a.q.thr = dThr.p;
     a.nQ = nq; a.order = dOrder.p; a.queryFirst = query_first; a.sameDb = par->same_db;
     a.maxHits = maxHits; a.minDiagScore = (uint32_t)std::max(par->min_ungapped_score, 0);
@@ -602,14 +617,33 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     a.nBins = nBins; a.binSize = tBinSize; a.binMagic = ((1ull << 40) + tBinSize - 1) / tBinSize; a.tabBytes = tabBytes;
     a.regionCap = regionCap; a.pool = dPool.p; a.candCap = candCap; a.cand = dCand.p; a.candSeq = dCandSeq.p;
     a.keepCap = keepCap; a.keep = dKeep.p; a.resT = dResT.p; a.resScore = dResScore.p; a.resAux = dResAux.p;
-    a.qpackG = dQpack.p; a.maxLq = maxLq + 16;
+    a.qpackG = dQpack.p; a.posInfo = dPosInfo.p; a.posPrefix = dPosPrefix.p; a.maxLq = maxLq + 16;
     a.out = dOut.p; a.outCount = dOutCount.p; a.stats = dStats.p; a.nextQuery = dNext.p; a.errQuery = dNext.p + 1;
     a.failList = dFail.p; a.nFail = dNext.p + 2;
+    a.debugSkip = getenv("SD_PF_SKIP") ? atoi(getenv("SD_PF_SKIP")) : 0;
     if (getenv("SD_PF_DEBUG"))
         fprintf(stderr, "[sd] prefilter: %u CTAs x %d threads, %zu B dynamic + %zu B static smem, %u bins of %u targets, region %u, cand %u, keep %u, maxDbMatches %llu\n",
                 nCta, PF_THREADS, dynSmem, (size_t)fa.sharedSizeBytes, nBins, tBinSize, regionCap, candCap, keepCap, maxDbMatches);
 
     SD_CUDA(cudaEventRecord(evk0, st));
+    static const int envPersist = getenv("SD_PF_PERSIST") ? atoi(getenv("SD_PF_PERSIST")) : 0;
+    if (envPersist) {
+        // the occupancy bitmap is probed once per similar k-mer: keep it in the persisting part of the L2
+        int maxPersist = 0, maxWin = 0;
+        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+        cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+        const size_t bmBytes = idx->bm.n * sizeof(uint2);
+        if (maxPersist > 0 && maxWin > 0) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)maxPersist, bmBytes + (8u << 20)));
+            cudaStreamAttrValue av{};
+            av.accessPolicyWindow.base_ptr = (void *)idx->bm.p;
+            av.accessPolicyWindow.num_bytes = std::min<size_t>(bmBytes, (size_t)maxWin);
+            av.accessPolicyWindow.hitRatio = 1.0f;
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+        }
+    }
     prefilterKernel<<<nCta, PF_THREADS, dynSmem, st>>>(a);
     ctx->launches++;
     SD_CUDA(cudaGetLastError());
@@ -619,6 +653,7 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
         SD_CUDA(cudaMemcpyAsync(hN, dNext.p, sizeof hN, cudaMemcpyDeviceToHost, st));
         SD_CUDA(cudaStreamSynchronize(st));
         const uint32_t nFail = hN[2];
+        if (getenv("SD_PF_DEBUG")) fprintf(stderr, "[sd] prefilter: %u queries overflowed the first-pass scratch\n", nFail);
         if (nFail) {
             const uint32_t nCta2 = std::max(1u, std::min<uint32_t>(nFail, std::max(1u, nCta / 16)));
             DevBuf<uint32_t> dOrder2;
@@ -631,7 +666,7 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
             b.regionCap = regionCap * 16; b.candCap = std::min(candCap * 16, 1u << 23);
             if ((rc = allocScratch(nCta2, b.regionCap, b.candCap, b.keepCap))) return rc;
             b.pool = dPool.p; b.cand = dCand.p; b.candSeq = dCandSeq.p; b.keep = dKeep.p; b.resT = dResT.p; b.resScore = dResScore.p;
-            b.resAux = dResAux.p; b.qpackG = dQpack.p;
+            b.resAux = dResAux.p; b.qpackG = dQpack.p; b.posInfo = dPosInfo.p; b.posPrefix = dPosPrefix.p;
             b.order = dOrder2.p; b.nQ = nFail;
             prefilterKernel<<<nCta2, PF_THREADS, dynSmem, st>>>(b);
             ctx->launches++;
@@ -640,6 +675,11 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
         }
     }
     SD_CUDA(cudaEventRecord(evk1, st));
+    if (envPersist) {
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+    }
 
     std::vector<uint32_t> hCount(nq);
     unsigned long long hStats[ST_N];
@@ -679,6 +719,13 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     }
     SD_CUDA(cudaEventRecord(ev1, st));
     SD_CUDA(cudaStreamSynchronize(st));
+    if (getenv("SD_PF_DEBUG"))
+        fprintf(stderr, "[sd] prefilter phase cycles (sum over queries, M): P1 %.1f  P2-4 %.1f  P5 %.1f (select %.1f)  chunked queries %llu\n",
+                hStats[ST_CYC_P1] / 1e6, hStats[ST_CYC_P24] / 1e6, hStats[ST_CYC_P5] / 1e6, hStats[ST_CYC_SEL] / 1e6, hStats[ST_CHUNKED]);
+    if (getenv("SD_PF_DEBUG"))
+        fprintf(stderr, "[sd] prefilter P1, warp 0 (M cycles): set-up %.1f  stage B %.1f (%llu calls, %llu hit rows)  queued rows incl. stage B %.1f  big rows %.1f  tail %.1f\n",
+                hStats[ST_CYC_P0B] / 1e6, hStats[ST_CYC_STAGEB] / 1e6, hStats[ST_N_STAGEB], hStats[ST_N_HITROWS], hStats[ST_CYC_DRAIN] / 1e6,
+                hStats[ST_CYC_BIG] / 1e6, hStats[ST_CYC_TAIL] / 1e6);
     if (stats) {
         float msK = 0, msT = 0;
         cudaEventElapsedTime(&msK, evk0, evk1);

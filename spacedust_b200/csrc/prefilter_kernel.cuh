@@ -35,9 +35,10 @@
 constexpr int PF_WARPS = 8;              // warps per CTA
 constexpr int PF_THREADS = PF_WARPS * 32;
 constexpr int PF_UNROLL = 4;             // probe steps in flight per warp (independent bitmap loads)
-constexpr uint32_t PF_RQCAP = 64;        // row ring: (position, first-row neighbour) rows waiting to be enumerated
-constexpr uint32_t PF_HQCAP = 256;       // hit-row ring: non-empty buckets waiting for their entries
-constexpr uint32_t PF_QCAP = 2048;       // query positions staged in shared memory for the diagonal scorer
+constexpr uint32_t PF_RQCAP = 128;       // row ring: (position, first-row neighbour) rows waiting to be enumerated
+constexpr uint32_t PF_HQCAP = 256;       // hit-row ring: non-empty buckets {bucket row, position} waiting for their entries
+constexpr uint32_t PF_HQDRAIN = 128;     // stage B runs when the ring holds this many: its rows were prefetched >= 96 pushes ago
+constexpr uint32_t PF_PROFLEN = 1168;    // query positions whose 21-column diagonal profile is staged in shared memory
 constexpr uint32_t PF_MAXBINSIZE = 8192; // 13 bits of target-in-bin in a pool entry
 constexpr uint32_t PF_SEQBITS = 28;      // running number inside a slice; slice index above
 static_assert(PF_WARPS <= 16, "slice index must fit above the running number");
@@ -50,8 +51,7 @@ struct PrefilterArgs {
     const uint2 *bm;           // per 32 k-mers: {occupancy bits, row of the first non-empty k-mer}
     const uint2 *rows;         // per non-empty k-mer: {target, 1<<31 | pos} (single entry) or {start, length}
     const uint2 *ent;          // bucket entries: (target id, first position of the k-mer in that target)
-    const int16_t *e3score;
-    const uint16_t *e3index;
+    const uint32_t *e3pair;    // sorted 3-mer neighbour rows 8000 x 8000: score (low 16 bits) | 3-mer index << 16
     const uint16_t *e3cnt;     // [8000][512] cumulative counts: e3cnt[x*512 + 255 - v] = #{y : score(x,y) >= v}
     const int8_t *diagSub;     // 21x21 BLOSUM62 x2 (-0.2)
     // query side
@@ -83,6 +83,8 @@ struct PrefilterArgs {
     int32_t *resScore;
     uint32_t *resAux;          // diag | pass<<16 ...
     uint16_t *qpackG;          // [cta][maxLq]: staged query rows of queries longer than PF_QCAP
+    uint4 *posInfo;            // [cta][maxLq]: per k-mer position {i1 | i2<<16, thr | cutoff1<<16, cutMid | cutBig<<16, similar k-mers}
+    uint32_t *posPrefix;       // [cta][maxLq]: inclusive prefix of the position weights (slice balancing)
     uint32_t maxLq;
     // output
     sd_prefilter_hit *out;     // nQ * maxHits
@@ -92,19 +94,19 @@ struct PrefilterArgs {
     uint32_t *errQuery;
     uint32_t *failList;        // queries whose lists did not fit (re-run with larger scratch)
     uint32_t *nFail;
+    int debugSkip;             // profiling only (SD_PF_SKIP): 1 = drop stage B (index entries), 2 = drop the bitmap loads too; results are wrong
 };
 
-enum { ST_PROBES = 0, ST_MATCHES, ST_DIAGRES, ST_HITS, ST_CANDS, ST_TRUNC, ST_ERR_CAP, ST_ERR_OVERFLOW, ST_CHUNKED, ST_N };
+enum { ST_PROBES = 0, ST_MATCHES, ST_DIAGRES, ST_HITS, ST_CANDS, ST_TRUNC, ST_ERR_CAP, ST_ERR_OVERFLOW, ST_CHUNKED,
+       ST_CYC_P1, ST_CYC_P24, ST_CYC_P5, ST_CYC_SEL, ST_CYC_P0B, ST_CYC_STAGEB, ST_CYC_DRAIN, ST_CYC_BIG, ST_CYC_TAIL, ST_N_STAGEB, ST_N_HITROWS, ST_N };   // ST_CYC_*: SM cycles per phase summed over queries (thread 0's view)
 
 __device__ __forceinline__ uint2 ldgU2(const uint2 *p) { return __ldg(p); }
 
 // UngappedAlignment::computeSingelSequenceScores + scalarDiagonalScoring (UngappedAlignment.cpp:30-43,416-430), one
-// candidate per lane.  qp[p] = query code | profile correction << 8; sub32[code*32 + targetCode].
-// Target residues are read in aligned 16-byte pieces (tRes is padded by 32 bytes).
-template <bool CAPPED>
-__device__ __forceinline__ int diagonalScoreLane(const uint8_t *__restrict__ tRes, const uint32_t *__restrict__ tOff,
-                                                 const int8_t *sub32, const uint16_t *qp, int Lq, uint32_t t, int diag,
-                                                 unsigned long long &residues) {
+// candidate per lane.  Target residues are read in aligned 16-byte pieces (tRes is padded by 32 bytes).
+// Fast path (P3, queries up to PF_PROFLEN residues): prof[pos*21 + targetCode] in shared memory, capped at 255.
+__device__ __forceinline__ int diagonalScoreProf(const uint8_t *__restrict__ tRes, const uint32_t *__restrict__ tOff,
+                                                 const int8_t *prof, int Lq, uint32_t t, int diag, unsigned long long &residues) {
     const uint32_t tb = __ldg(&tOff[t]);
     const int Lt = (int)(__ldg(&tOff[t + 1]) - tb);
     int qs, ts, len;
@@ -119,37 +121,152 @@ __device__ __forceinline__ int diagonalScoreLane(const uint8_t *__restrict__ tRe
     const uint32_t start = tb + (uint32_t)ts;
     const uint32_t base = start & ~15u;
     const int lead = (int)(start - base);
-    const uint16_t *qrow = qp + qs - lead;       // qrow[off + k] is the query row of byte k of the piece at `off`
     int best = 0, run = 0;
     const int end = lead + len;
     for (int off = 0; off < end; off += 16) {
         const uint4 v = __ldg(reinterpret_cast<const uint4 *>(tRes + base + off));
         const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+        const int8_t *pr = prof + (qs + off - lead) * AA;      // profile row of byte 0 of this piece
+        if (off >= lead && off + 16 <= end) {                  // whole piece inside the diagonal
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            const int pos = off + k;
-            if (pos >= lead && pos < end) {
+            for (int k = 0; k < 16; k++) {
                 const uint32_t tc = (wv[k >> 2] >> (8 * (k & 3))) & 0xffu;
-                const uint32_t qv = qrow[pos];
-                run += (int)sub32[(qv & 0xffu) * 32u + tc] + (int)(int8_t)(qv >> 8);
-                run = max(run, 0);
+                run = max(run + (int)pr[k * AA + tc], 0);
                 best = max(best, run);
             }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int pos = off + k;
+                if (pos >= lead && pos < end) {
+                    const uint32_t tc = (wv[k >> 2] >> (8 * (k & 3))) & 0xffu;
+                    run = max(run + (int)pr[k * AA + tc], 0);
+                    best = max(best, run);
+                }
+            }
         }
-        if (CAPPED && best >= 255) break;
+        if (best >= 255) break;
     }
     return best;
+}
+
+// Same score on the rare paths (queries longer than PF_PROFLEN, uncapped rescoring): one out-of-line copy, generic pointers.
+// useProf: prof[pos*21 + targetCode]; otherwise qp[pos] = query code | profile correction << 8 and sub32[code*32 + targetCode].
+__device__ __noinline__ int diagonalScoreSlow(const uint8_t *__restrict__ tRes, const uint32_t *__restrict__ tOff, const int8_t *prof,
+                                              const int8_t *sub32, const uint16_t *qp, int useProf, int capped, int Lq, uint32_t t,
+                                              int diag, unsigned long long *residues) {
+    const uint32_t tb = __ldg(&tOff[t]);
+    const int Lt = (int)(__ldg(&tOff[t + 1]) - tb);
+    int qs, ts, len;
+    if (diag >= 0) {
+        if (diag >= Lq) return 0;
+        qs = diag; ts = 0; len = min(Lt, Lq - diag);
+    } else {
+        if (-diag >= Lt) return 0;
+        qs = 0; ts = -diag; len = min(Lt + diag, Lq);
+    }
+    *residues += (unsigned long long)len;
+    const uint8_t *tc = tRes + tb + ts;
+    int best = 0, run = 0;
+    for (int p = 0; p < len; p++) {
+        const uint32_t c = __ldg(&tc[p]);
+        int sc;
+        if (useProf) sc = (int)prof[(qs + p) * AA + c];
+        else { const uint32_t qv = qp[qs + p]; sc = (int)sub32[(qv & 0xffu) * 32u + c] + (int)(int8_t)(qv >> 8); }
+        run = max(run + sc, 0);
+        best = max(best, run);
+        if (capped && best >= 255) break;
+    }
+    return best;
+}
+
+__device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// P1, stage B: 32 (or the last n) non-empty buckets from the hit-row ring -> their index entries -> (target bin, running number)
+// appended to this warp's regions.  Out of line: it is large.  Latency is taken out of the dependent chain bucket row -> entries
+// by working one batch ahead: the rows of THIS batch were loaded by the previous call (rowBuf; their entry lists prefetched into
+// the L2 then), and this call loads the rows of the next batch (nAhead entries wait behind this one; their rows were prefetched
+// when they were pushed) before it appends.
+// Returns the new running number; bit 31 set = a region overflowed.
+__device__ __noinline__ uint32_t prefilterStageB(const uint2 *__restrict__ rows, const uint2 *__restrict__ ent, unsigned long long binMagic,
+                                                 uint32_t binSize, uint32_t regionCap, const uint2 *HQ, uint32_t hqH, uint32_t n, uint32_t nAhead,
+                                                 uint2 *rowBuf, uint32_t rowBufValid, uint32_t *cntW, uint2 *poolW, uint32_t seqBase) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    __syncwarp();
+    uint32_t rx = 0, ry = 0, m = 0, pq = 0;
+    bool overflow = false;
+    if (lane < n) {
+        const uint2 h = HQ[(hqH + lane) & (PF_HQCAP - 1)];      // {bucket row, position}
+        const uint2 row = (lane < rowBufValid) ? rowBuf[lane] : __ldg(&rows[h.x]);     // rowBufValid: rows loaded by the previous call
+        pq = h.y;
+        rx = row.x;
+        ry = row.y;
+        m = (ry >> 31) ? 1u : ry;                // >= 1: only non-empty buckets are queued
+    }
+    // rows of the next batch (in flight while this batch is appended)
+    uint2 nextRow = make_uint2(0u, 0x80000000u);
+    const bool haveNext = lane < min(nAhead, 32u);
+    if (haveNext) nextRow = __ldg(&rows[HQ[(hqH + 32u + lane) & (PF_HQCAP - 1)].x]);
+    uint32_t totalM;
+    const uint32_t exclM = warpExclusiveScan(m, totalM);
+    for (uint32_t ec = 0; ec < totalM; ec += 32) {
+        const uint32_t eidx = ec + lane;
+        const bool valid = eidx < totalM;
+        const uint32_t owner = warpOwnerOfSlot(exclM, m != 0, ec, lane);
+        const uint32_t oExcl = __shfl_sync(0xffffffffu, exclM, owner);
+        const uint32_t oX = __shfl_sync(0xffffffffu, rx, owner);
+        const uint32_t oY = __shfl_sync(0xffffffffu, ry, owner);
+        const uint32_t oP = __shfl_sync(0xffffffffu, pq, owner);
+        uint32_t t = 0, j = 0, k = 0;
+        if (valid) {
+            k = eidx - oExcl;
+            if (oY >> 31) { t = oX; j = oY & 0xffffu; }
+            else { const uint2 en = __ldg(&ent[oX + k]); t = en.x; j = en.y; }
+        }
+        const uint32_t bin = (uint32_t)(((unsigned long long)t * binMagic) >> 40);
+        const uint32_t grp = __match_any_sync(0xffffffffu, valid ? bin : (0x80000000u | lane));
+        const uint32_t leader = (uint32_t)__ffs(grp) - 1u;
+        uint32_t old = 0;
+        if (valid && lane == leader) { old = cntW[bin]; cntW[bin] = old + (uint32_t)__popc(grp); }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        if (valid) {
+            const uint32_t slot = old + (uint32_t)__popc(grp & ltMask);
+            const uint32_t tl = t - bin * binSize;
+            const uint32_t diag16 = (oP - j) & 0xffffu;
+            if (slot < regionCap)
+                poolW[(size_t)bin * regionCap + slot] = make_uint2(tl | (diag16 << 13) | ((k == 0 ? 1u : 0u) << 29), seqBase + lane);
+            else overflow = true;
+        }
+        seqBase += min(32u, totalM - ec);
+        __syncwarp();
+    }
+    // next batch: keep its rows, prefetch its entry lists (first 128 bytes; longer lists stream behind them)
+    if (haveNext) {
+        rowBuf[lane] = nextRow;
+        if (!(nextRow.y >> 31)) {
+            prefetchL2(&ent[nextRow.x]);
+            if (nextRow.y > 8u) prefetchL2(&ent[nextRow.x + 8u]);
+        }
+    }
+    __syncwarp();
+    if (__any_sync(0xffffffffu, overflow) || seqBase >= (1u << PF_SEQBITS)) seqBase |= 0x80000000u;
+    return seqBase;
 }
 
 // Shared memory: static part below + dynamic [counters: PF_WARPS*nBins u32][tables: PF_WARPS * tabBytes]
 struct PfShared {
     int8_t sub32[AA * 32];
     uint32_t hist[256];
-    uint2 rq[PF_WARPS][PF_RQCAP];
-    uint32_t hqc[PF_WARPS][PF_HQCAP];
-    uint16_t hqp[PF_WARPS][PF_HQCAP];
-    uint16_t qpack[PF_QCAP];
+    union {      // the rings live in P1, the diagonal profile from P2 on
+        struct { uint32_t rq[PF_WARPS][PF_RQCAP]; uint2 hq[PF_WARPS][PF_HQCAP]; uint2 rowBuf[PF_WARPS][32]; } ring;
+        int8_t prof[PF_PROFLEN * AA];
+    } u;
     uint32_t sliceTotal[PF_WARPS];
+    uint32_t scanTmp[PF_WARPS];
+    unsigned long long totalWeight;
+    long long prof1[6];
+    long long clkP0b;
     unsigned long long sliceBase[PF_WARPS + 1];
     unsigned long long stat[8];
     unsigned long long selPrefix;
@@ -158,7 +275,7 @@ struct PfShared {
     int maxSelf;
 };
 
-__global__ void __launch_bounds__(PF_THREADS, 2) prefilterKernel(PrefilterArgs a) {
+__global__ void __launch_bounds__(PF_THREADS, 3) prefilterKernel(PrefilterArgs a) {
     __shared__ PfShared S;
     extern __shared__ __align__(16) uint8_t sDyn[];
 
@@ -200,184 +317,302 @@ __global__ void __launch_bounds__(PF_THREADS, 2) prefilterKernel(PrefilterArgs a
         const uint32_t qBase = a.q.off[q];
         const int Lq = (int)(a.q.off[q + 1] - qBase);
         const uint32_t identity = a.sameDb ? (a.queryFirst + q) : 0xffffffffu;
-        const uint16_t *qp = (Lq <= (int)PF_QCAP) ? S.qpack : qpackG;
+        const bool useProf = Lq <= (int)PF_PROFLEN;
+        const uint16_t *qp = qpackG;
 
         // ---------------- P0: counters, histogram, staged query rows
         for (uint32_t i = tid; i < PF_WARPS * nBins; i += PF_THREADS) cntAll[i] = 0;
         for (uint32_t i = tid; i < 256; i += PF_THREADS) S.hist[i] = 0;
-        {
-            uint16_t *dst = (Lq <= (int)PF_QCAP) ? S.qpack : qpackG;
+        if (!useProf) {
             for (int p = (int)tid; p < Lq; p += PF_THREADS)
-                dst[p] = (uint16_t)((uint32_t)a.q.code[qBase + p] | ((uint32_t)(uint8_t)a.q.corr[qBase + p] << 8));
+                qpackG[p] = (uint16_t)((uint32_t)a.q.code[qBase + p] | ((uint32_t)(uint8_t)a.q.corr[qBase + p] << 8));
         }
         unsigned long long stProbes = 0, stDiagRes = 0;
+        const long long clk0 = clock64();
+
+        // ---------------- P0b: per-position set-up and EXACT similar-k-mer counts, balanced slices
+        // (KmerGenerator.cpp:129-137,186-216: the list of position p is {(a, c): s1[a] + s2[c] >= thr}; its size is
+        // sum over score levels v of #{a: s1[a] = v} * #{c: s2[c] >= thr - v}, read from the cumulative count table)
+        const int nPos = max(Lq - SPAN + 1, 0);
+        uint4 *posInfo = a.posInfo + (size_t)blockIdx.x * a.maxLq;
+        uint32_t *posPrefix = a.posPrefix + (size_t)blockIdx.x * a.maxLq;        // inclusive prefix of the slice weights
+        {
+            uint32_t carry = 0;
+            for (int p0 = 0; p0 < nPos; p0 += PF_THREADS) {
+                const int p = p0 + (int)tid;
+                uint32_t wgt = 0;
+                if (p < nPos) {
+                    uint4 info = make_uint4(0u, 0xffffu, 0u, 0u);               // threshold -1: no k-mer here
+                    const int thr = a.q.thr[qBase + p];
+                    if (thr >= 0) {
+                        const uint8_t *qc = a.q.code + qBase + p;
+                        const uint32_t i1 = qc[0] + 20u * qc[1] + 400u * qc[3];
+                        const uint32_t i2 = qc[5] + 20u * qc[8] + 400u * qc[9];
+                        const int top1 = (int)(int16_t)(__ldg(&a.e3pair[(size_t)i1 * N3]) & 0xffffu);
+                        const uint32_t *row2 = a.e3pair + (size_t)i2 * N3;
+                        const int top2 = (int)(int16_t)(__ldg(&row2[0]) & 0xffffu);
+                        if (top1 + top2 >= thr) {                                // else nothing reaches the threshold
+                            const int cutoff1 = thr - top2;                      // first-row elements with s1 >= cutoff1 have a partner
+                            const int cutMid = thr - (int)(int16_t)(__ldg(&row2[1]) & 0xffffu);     // ... at least 2 partners
+                            const int cutBig = thr - (int)(int16_t)(__ldg(&row2[31]) & 0xffffu);    // ... at least 32 partners
+                            uint32_t prevC = 0, probes = 0;
+                            for (int v = top1; v >= cutoff1; v--) {
+                                const uint32_t c1 = countGE(a.e3cnt, i1, v);
+                                if (c1 != prevC) probes += (c1 - prevC) * countGE(a.e3cnt, i2, thr - v);
+                                prevC = c1;
+                            }
+                            // the first row is sorted by score: rows [0, nBig) have >= 32 partners, [nBig, nHead) 2..31, [nHead, nRows) one
+                            const uint32_t nRows = prevC;
+                            const uint32_t nHead = countGE(a.e3cnt, i1, cutMid), nBig = countGE(a.e3cnt, i1, cutBig);
+                            info = make_uint4(i1 | (i2 << 16), ((uint32_t)thr & 0xffffu) | (nRows << 16), nBig | (nHead << 16), probes);
+                            wgt = probes + 64u;
+                        }
+                    }
+                    posInfo[p] = info;
+                }
+                // block-wide inclusive scan of wgt
+                uint32_t x = wgt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                    if (lane >= (uint32_t)d) x += y;
+                }
+                if (lane == 31) S.scanTmp[w] = x;
+                __syncthreads();
+                uint32_t add = carry;
+                for (uint32_t i = 0; i < w; i++) add += S.scanTmp[i];
+                uint32_t tot = 0;
+                for (uint32_t i = 0; i < PF_WARPS; i++) tot += S.scanTmp[i];
+                if (p < nPos) posPrefix[p] = x + add;
+                carry += tot;
+                __syncthreads();
+            }
+            if (tid == 0) { S.totalWeight = carry; S.clkP0b = clock64() - clk0; }
+        }
+        __syncthreads();
 
         // ---------------- P1: hit stream of this warp's slice of positions
         {
-            uint2 *RQ = S.rq[w];
-            uint32_t *HQc = S.hqc[w];
-            uint16_t *HQp = S.hqp[w];
+            uint32_t *RQ = S.u.ring.rq[w];                 // queued rows of the current position: first-row neighbour | partners << 16
+            uint2 *HQ = S.u.ring.hq[w];
+            uint2 *rowBuf = S.u.ring.rowBuf[w];
+            uint32_t rowBufValid = 0;               // rows of the ring's first 32 entries already loaded (and their entries prefetched)
             uint32_t rqH = 0, rqN = 0, hqH = 0, hqN = 0;
             uint32_t seqBase = 0;
             bool overflow = false;
             uint2 *poolW = poolC + (size_t)w * nBins * a.regionCap;
+            long long cycStageB = 0;
+            uint32_t nStageB = 0, nHitRows = 0;
 
-            auto stageB = [&](const uint32_t n) {
-                __syncwarp();
-                uint32_t rx = 0, ry = 0, m = 0, pq = 0;
-                if (lane < n) {
-                    const uint32_t slot = (hqH + lane) & (PF_HQCAP - 1);
-                    const uint2 row = ldgU2(&a.rows[HQc[slot]]);
-                    pq = HQp[slot];
-                    rx = row.x;
-                    ry = row.y;
-                    m = (ry >> 31) ? 1u : ry;                // >= 1: only non-empty buckets are queued
-                }
-                hqH += n;
-                hqN -= n;
-                uint32_t totalM;
-                const uint32_t exclM = warpExclusiveScan(m, totalM);
-                for (uint32_t ec = 0; ec < totalM; ec += 32) {
-                    const uint32_t eidx = ec + lane;
-                    const bool valid = eidx < totalM;
-                    const uint32_t owner = warpOwnerOfSlot(exclM, m != 0, ec, lane);
-                    const uint32_t oExcl = __shfl_sync(0xffffffffu, exclM, owner);
-                    const uint32_t oX = __shfl_sync(0xffffffffu, rx, owner);
-                    const uint32_t oY = __shfl_sync(0xffffffffu, ry, owner);
-                    const uint32_t oP = __shfl_sync(0xffffffffu, pq, owner);
-                    uint32_t t = 0, j = 0, k = 0;
-                    if (valid) {
-                        k = eidx - oExcl;
-                        if (oY >> 31) { t = oX; j = oY & 0xffffu; }
-                        else { const uint2 en = ldgU2(&a.ent[oX + k]); t = en.x; j = en.y; }
+            // slice of positions with 1/PF_WARPS of the query's similar k-mers
+            int pLo, pHi;
+            {
+                const unsigned long long tw = S.totalWeight;
+                auto bound = [&](const uint32_t k) -> int {      // first position whose exclusive prefix reaches tw*k/PF_WARPS
+                    if (k == 0) return 0;
+                    if (k >= PF_WARPS) return nPos;
+                    const uint32_t target = (uint32_t)(tw * k / PF_WARPS);
+                    int lo = 0, hi = nPos;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const uint32_t excl = mid == 0 ? 0u : posPrefix[mid - 1];
+                        if (excl >= target) hi = mid; else lo = mid + 1;
                     }
-                    const uint32_t bin = (uint32_t)(((unsigned long long)t * a.binMagic) >> 40);
-                    const uint32_t grp = __match_any_sync(0xffffffffu, valid ? bin : (0x80000000u | lane));
-                    const uint32_t leader = (uint32_t)__ffs(grp) - 1u;
-                    uint32_t old = 0;
-                    if (valid && lane == leader) { old = cntW[bin]; cntW[bin] = old + (uint32_t)__popc(grp); }
-                    old = __shfl_sync(0xffffffffu, old, leader);
-                    if (valid) {
-                        const uint32_t slot = old + (uint32_t)__popc(grp & ltMask);
-                        const uint32_t tl = t - bin * a.binSize;
-                        const uint32_t diag16 = (oP - j) & 0xffffu;
-                        if (slot < a.regionCap)
-                            poolW[(size_t)bin * a.regionCap + slot] = make_uint2(tl | (diag16 << 13) | ((k == 0 ? 1u : 0u) << 29), seqBase + lane);
-                        else overflow = true;
-                    }
-                    seqBase += min(32u, totalM - ec);
-                    __syncwarp();
-                }
-            };
+                    return lo;
+                };
+                pLo = bound(w);
+                pHi = bound(w + 1);
+            }
 
-            auto drainRows = [&](const uint32_t n) {
-                __syncwarp();
-                uint2 row = make_uint2(0u, 0u);
-                if (lane < n) row = RQ[(rqH + lane) & (PF_RQCAP - 1)];
-                rqH += n;
-                rqN -= n;
-                const uint32_t nb = row.y & 0xffffu;
-                uint32_t total;
-                const uint32_t excl = warpExclusiveScan(nb, total);
-                stProbes += (lane == 0) ? total : 0;
-                for (uint32_t pc = 0; pc < total; pc += 32 * PF_UNROLL) {
-                    uint2 wd[PF_UNROLL];
-                    uint32_t kmerW[PF_UNROLL], pp[PF_UNROLL];
+            // ONE loop produces the similar k-mers of the slice in stream order, 32*PF_UNROLL at a time, from four generators
+            // (a small state machine: the code of the occupancy test, the hit-row ring and stage B exists once):
+            //   HEAD   next chunk of 32 first-row neighbours with at least 2 partners: rows with >= 32 partners are handed to BIG,
+            //          rows with 2..31 partners are queued;
+            //   BIG    one first-row neighbour, lanes across its second-row partners;
+            //   DRAIN  the queued rows, flattened: lane-balanced 32 similar k-mers per step;
+            //   TAIL   first-row neighbours whose only partner is the best second-row neighbour, lanes across the first row.
+            // Positions are walked with a two-deep software pipeline: the set-up record of position p+2 and the first chunk of the
+            // first row (and the best second-row neighbour) of position p+1 are loaded while position p is processed.
+            enum { M_NEXTPOS, M_HEAD, M_BIG, M_DRAIN, M_TAIL };
+            int mode = M_NEXTPOS, afterBig = M_NEXTPOS, afterDrain = M_NEXTPOS;
+            uint4 infoB = make_uint4(0u, 0xffffu, 0u, 0u), infoC = infoB;      // p+1, p+2
+            uint32_t prB = 0, topB = 0;
+            int p = pLo - 1;
+            if (pLo < pHi) infoB = posInfo[pLo];
+            if (pLo + 1 < pHi) infoC = posInfo[pLo + 1];
+            if ((int16_t)(infoB.y & 0xffffu) >= 0) {
+                prB = __ldg(&a.e3pair[(size_t)(infoB.x & 0xffffu) * N3 + lane]);
+                topB = __ldg(&a.e3pair[(size_t)(infoB.x >> 16) * N3]);
+            }
+            int thr = 0;
+            uint32_t i2 = 0, nRows = 0, nBig = 0, nHead = 0, x2top = 0, pr0 = 0, a0 = 0;
+            const uint32_t *row1 = a.e3pair, *row2 = a.e3pair;
+            uint32_t xaL = 0, nbL = 0, bigMask = 0;                             // HEAD -> BIG
+            uint32_t xb = 0, nbb = 0, c0 = 0;                                   // BIG
+            uint32_t dRow = 0, dExcl = 0, dTotal = 0, pc = 0;                   // DRAIN
+            for (;;) {
+                uint32_t kmerW[PF_UNROLL];
+                uint32_t nSteps = 0;
+#pragma unroll
+                for (int j = 0; j < PF_UNROLL; j++) kmerW[j] = 0xffffffffu;
+                if (mode == M_NEXTPOS) {
+                    p++;
+                    if (p >= pHi) break;
+                    const uint4 info = infoB;
+                    pr0 = prB;
+                    const uint32_t top2w = topB;
+                    infoB = infoC;
+                    if (p + 2 < pHi) infoC = posInfo[p + 2];
+                    if (p + 1 < pHi && (int16_t)(infoB.y & 0xffffu) >= 0) {
+                        prB = __ldg(&a.e3pair[(size_t)(infoB.x & 0xffffu) * N3 + lane]);
+                        topB = __ldg(&a.e3pair[(size_t)(infoB.x >> 16) * N3]);
+                    }
+                    thr = (int)(int16_t)(info.y & 0xffffu);
+                    if (thr < 0) continue;
+                    stProbes += (lane == 0) ? info.w : 0;
+                    i2 = info.x >> 16;
+                    nRows = info.y >> 16; nBig = info.z & 0xffffu; nHead = info.z >> 16;
+                    row1 = a.e3pair + (size_t)(info.x & 0xffffu) * N3;
+                    row2 = a.e3pair + (size_t)i2 * N3;
+                    x2top = N3 * (top2w >> 16);
+                    a0 = 0;
+                    mode = nHead ? M_HEAD : M_TAIL;
+                    continue;
+                } else if (mode == M_HEAD) {
+                    const uint32_t ai = a0 + lane;
+                    const uint32_t pr = (a0 == 0) ? pr0 : __ldg(&row1[min(ai, N3 - 1)]);
+                    xaL = pr >> 16;
+                    const bool isBig = ai < nBig;
+                    const bool isMid = !isBig && ai < nHead;
+                    nbL = 1;
+                    // KmerGenerator.cpp:201: second-row elements with s2 >= thr - s1
+                    if (isBig || isMid) nbL = countGE(a.e3cnt, i2, thr - (int)(int16_t)(pr & 0xffffu));
+                    bigMask = __ballot_sync(0xffffffffu, isBig);
+                    const uint32_t midMask = __ballot_sync(0xffffffffu, isMid);
+                    if (isMid) RQ[(rqH + rqN + __popc(midMask & ltMask)) & (PF_RQCAP - 1)] = xaL | (nbL << 16);
+                    rqN += __popc(midMask);
+                    a0 = min(a0 + 32u, nHead);
+                    // stream order: the big rows of this chunk, then (when the head is complete or the queue is full) the queued rows
+                    int next = M_HEAD;
+                    if (a0 == nHead) { next = rqN ? M_DRAIN : M_TAIL; afterDrain = M_TAIL; }
+                    else if (rqN >= PF_RQCAP - 32) { next = M_DRAIN; afterDrain = M_HEAD; }
+                    afterBig = next;
+                    mode = bigMask ? M_BIG : next;
+                    c0 = 0; nbb = 0;
+                    pc = 0; dTotal = 0;
+                    continue;
+                } else if (mode == M_BIG) {
+                    if (c0 >= nbb) {
+                        if (!bigMask) { mode = afterBig; pc = 0; dTotal = 0; continue; }
+                        const int src = __ffs(bigMask) - 1;
+                        bigMask &= bigMask - 1;
+                        xb = __shfl_sync(0xffffffffu, xaL, src);
+                        nbb = __shfl_sync(0xffffffffu, nbL, src);
+                        c0 = 0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < PF_UNROLL; j++) {
+                        const uint32_t c = c0 + 32u * j + lane;
+                        if (c < nbb) kmerW[j] = xb + N3 * (__ldg(&row2[c]) >> 16);
+                    }
+                    nSteps = (min(nbb - c0, 32u * PF_UNROLL) + 31u) / 32u;
+                    c0 += 32 * PF_UNROLL;
+                } else if (mode == M_DRAIN) {
+                    if (pc >= dTotal) {
+                        if (rqN == 0) { mode = afterDrain; continue; }
+                        // calls of similar size (a 33-row queue is drained as 17 + 16, not 32 + 1)
+                        const uint32_t calls = (rqN + 31u) / 32u;
+                        const uint32_t n = (rqN + calls - 1u) / calls;
+                        __syncwarp();
+                        dRow = (lane < n) ? RQ[(rqH + lane) & (PF_RQCAP - 1)] : 0u;
+                        rqH += n;
+                        rqN -= n;
+                        dExcl = warpExclusiveScan(dRow >> 16, dTotal);
+                        pc = 0;
+                    }
+                    const uint32_t nb = dRow >> 16;
 #pragma unroll
                     for (int j = 0; j < PF_UNROLL; j++) {
                         const uint32_t base = pc + 32u * j;
-                        wd[j] = make_uint2(0u, 0u);
-                        kmerW[j] = 0;
-                        pp[j] = 0;
-                        if (base < total) {
-                            const uint32_t owner = warpOwnerOfSlot(excl, nb != 0, base, lane);
-                            const uint32_t oExcl = __shfl_sync(0xffffffffu, excl, owner);
-                            const uint32_t oLo = __shfl_sync(0xffffffffu, row.x, owner);
-                            const uint32_t oHi = __shfl_sync(0xffffffffu, row.y, owner);
-                            if (base + lane < total) {
-                                const uint32_t c = base + lane - oExcl;
-                                const uint32_t xc = (uint32_t)__ldg(&a.e3index[(size_t)(oLo >> 16) * N3 + c]);
-                                kmerW[j] = (oLo & 0xffffu) + N3 * xc;            // KmerGenerator.cpp:207
-                                pp[j] = oHi >> 16;
-                                wd[j] = ldgU2(&a.bm[kmerW[j] >> 5]);
-                            }
+                        if (base < dTotal) {
+                            const uint32_t owner = warpOwnerOfSlot(dExcl, nb != 0, base, lane);
+                            const uint32_t oExcl = __shfl_sync(0xffffffffu, dExcl, owner);
+                            const uint32_t oRow = __shfl_sync(0xffffffffu, dRow, owner);
+                            if (base + lane < dTotal) kmerW[j] = (oRow & 0xffffu) + N3 * (__ldg(&row2[base + lane - oExcl]) >> 16);   // KmerGenerator.cpp:207
                         }
                     }
+                    nSteps = (min(dTotal - pc, 32u * PF_UNROLL) + 31u) / 32u;
+                    pc += 32 * PF_UNROLL;
+                } else {    // M_TAIL
+                    if (a0 >= nRows) { mode = M_NEXTPOS; continue; }
 #pragma unroll
                     for (int j = 0; j < PF_UNROLL; j++) {
-                        if (pc + 32u * j < total) {
-                            const uint32_t bit = kmerW[j] & 31u;
-                            const bool has = ((wd[j].x >> bit) & 1u) != 0;       // idle lanes carry bits = 0
-                            const uint32_t hb = __ballot_sync(0xffffffffu, has);
-                            if (has) {
-                                const uint32_t slot = (hqH + hqN + __popc(hb & ltMask)) & (PF_HQCAP - 1);
-                                HQc[slot] = wd[j].y + __popc(wd[j].x & ((1u << bit) - 1u));
-                                HQp[slot] = (uint16_t)pp[j];
-                            }
-                            hqN += __popc(hb);
-                        }
+                        const uint32_t ai = a0 + 32u * j + lane;
+                        if (ai < nRows) kmerW[j] = (__ldg(&row1[ai]) >> 16) + x2top;
                     }
-                    while (hqN >= 32) stageB(32u);
+                    nSteps = (min(nRows - a0, 32u * PF_UNROLL) + 31u) / 32u;
+                    a0 += 32 * PF_UNROLL;
                 }
-            };
-
-            const int nPos = max(Lq - SPAN + 1, 0);
-            const int pLo = (int)(((long long)nPos * w) / PF_WARPS), pHi = (int)(((long long)nPos * (w + 1)) / PF_WARPS);
-            for (int p0 = pLo; p0 < pHi; p0 += 32) {
-                // ---- set-up of 32 positions at once (one per lane): thresholds, 3-mer rows
-                int thrL = -1, top2L = 0;
-                uint32_t i1L = 0, i2L = 0;
-                {
-                    const int pl = p0 + (int)lane;
-                    if (pl < pHi) thrL = a.q.thr[qBase + pl];
-                    if (thrL >= 0) {
-                        const uint8_t *qc = a.q.code + qBase + pl;
-                        i1L = qc[0] + 20u * qc[1] + 400u * qc[3];
-                        i2L = qc[5] + 20u * qc[8] + 400u * qc[9];
-                        const int top1 = (int)__ldg(&a.e3score[(size_t)i1L * N3]);
-                        top2L = (int)__ldg(&a.e3score[(size_t)i2L * N3]);
-                        if (top1 < thrL - top2L) thrL = -1;           // KmerGenerator.cpp:129-137: nothing reaches the threshold
+                // ---- common: occupancy words of up to 32*PF_UNROLL similar k-mers, non-empty buckets to the hit-row ring, stage B
+                uint2 wd[PF_UNROLL];
+#pragma unroll
+                for (int j = 0; j < PF_UNROLL; j++) {
+                    wd[j] = make_uint2(0u, 0u);
+                    if (kmerW[j] != 0xffffffffu) wd[j] = (a.debugSkip & 2) ? make_uint2(kmerW[j] * 2654435761u & 0x11111111u, 0u) : ldgU2(&a.bm[kmerW[j] >> 5]);
+                }
+#pragma unroll
+                for (int j = 0; j < PF_UNROLL; j++) {
+                    if ((uint32_t)j < nSteps) {
+                        const bool has = ((wd[j].x >> (kmerW[j] & 31u)) & 1u) != 0;       // idle lanes carry bits = 0
+                        const uint32_t hb = __ballot_sync(0xffffffffu, has);
+                        if (has) {
+                            const uint32_t ci = wd[j].y + __popc(wd[j].x & ((1u << (kmerW[j] & 31u)) - 1u));
+                            prefetchL2(&a.rows[ci]);
+                            HQ[(hqH + hqN + __popc(hb & ltMask)) & (PF_HQCAP - 1)] = make_uint2(ci, (uint32_t)p);
+                        }
+                        hqN += __popc(hb);
                     }
                 }
-                uint32_t active = __ballot_sync(0xffffffffu, thrL >= 0);
-                while (active) {
-                    const int src = __ffs(active) - 1;
-                    active &= active - 1;
-                    const uint32_t p = (uint32_t)(p0 + src);
-                    const int thr = __shfl_sync(0xffffffffu, thrL, src);
-                    const uint32_t i1 = __shfl_sync(0xffffffffu, i1L, src);
-                    const uint32_t i2 = __shfl_sync(0xffffffffu, i2L, src);
-                    const int cutoff1 = thr - __shfl_sync(0xffffffffu, top2L, src);
-                    const int16_t *s1 = a.e3score + (size_t)i1 * N3;
-                    const uint16_t *x1 = a.e3index + (size_t)i1 * N3;
-                    for (uint32_t a0 = 0; a0 < N3; a0 += 32) {
-                        const uint32_t ai = a0 + lane;                // N3 is a multiple of 32
-                        const int sa = (int)__ldg(&s1[ai]);
-                        const bool okA = sa >= cutoff1;
-                        const uint32_t okBallot = __ballot_sync(0xffffffffu, okA);   // a prefix of the lanes: the row is sorted
-                        if (okBallot == 0) break;
-                        if (okA) {
-                            // KmerGenerator.cpp:201: second-row elements with s2 >= thr - s1 (>= 1 because sa >= cutoff1)
-                            const uint32_t nb = countGE(a.e3cnt, i2, thr - sa);
-                            RQ[(rqH + rqN + lane) & (PF_RQCAP - 1)] = make_uint2((uint32_t)__ldg(&x1[ai]) | (i2 << 16), nb | (p << 16));
-                        }
-                        rqN += __popc(okBallot);
-                        if (rqN >= 32) drainRows(32u);
-                        if (okBallot != 0xffffffffu) break;
+                while (hqN >= PF_HQDRAIN) {
+                    const long long t0 = clock64();
+                    nStageB++; nHitRows += 32;
+                    if (!(a.debugSkip & 3)) {
+                        const uint32_t r = prefilterStageB(a.rows, a.ent, a.binMagic, a.binSize, a.regionCap, HQ, hqH, 32u, hqN - 32u, rowBuf, rowBufValid, cntW, poolW, seqBase);
+                        overflow = overflow || (r >> 31) != 0;
+                        seqBase = r & 0x7fffffffu;
+                        rowBufValid = 32;
                     }
+                    hqH += 32;
+                    hqN -= 32;
+                    cycStageB += clock64() - t0;
                 }
             }
-            if (rqN > 0) drainRows(rqN);
-            while (hqN > 0) stageB(min(hqN, 32u));
+            while (hqN > 0 && !(a.debugSkip & 3)) {
+                const uint32_t n = min(hqN, 32u);
+                const uint32_t r = prefilterStageB(a.rows, a.ent, a.binMagic, a.binSize, a.regionCap, HQ, hqH, n, hqN - n, rowBuf, rowBufValid, cntW, poolW, seqBase);
+                overflow = overflow || (r >> 31) != 0;
+                seqBase = r & 0x7fffffffu;
+                rowBufValid = min(hqN - n, 32u);
+                hqH += n;
+                hqN -= n;
+            }
             __syncwarp();
-            if (lane == 0) {
-                S.sliceTotal[w] = seqBase;
-                if (seqBase >= (1u << PF_SEQBITS)) overflow = true;
+            if (lane == 0) S.sliceTotal[w] = seqBase;
+            if (tid == 0) {      // warp 0's view of where P1's cycles go
+                S.prof1[0] = cycStageB; S.prof1[1] = 0; S.prof1[2] = 0; S.prof1[3] = 0; S.prof1[4] = nStageB; S.prof1[5] = nHitRows;
             }
             if (__any_sync(0xffffffffu, overflow)) { if (lane == 0) atomicOr(&S.fail, 1u); }
         }
         __syncthreads();
 
+        if (useProf) {
+            // UngappedAlignment::createProfile: BLOSUM62 x2 + per-position correction, one 21-column row per position
+            // (the rings of P1 are dead now: same shared memory)
+            for (int i = (int)tid; i < Lq * AA; i += PF_THREADS) {
+                const int p = i / AA, c = i - p * AA;
+                S.u.prof[i] = (int8_t)((int)S.sub32[(uint32_t)a.q.code[qBase + p] * 32u + c] + (int)a.q.corr[qBase + p]);
+            }
+        }
         // ---------------- chunk boundary of the reference's hit buffer (see the header comment)
         if (tid == 0) {
             unsigned long long acc = 0;
@@ -386,7 +621,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) prefilterKernel(PrefilterArgs a
             S.stat[ST_MATCHES] = acc;
             S.boundSearch = 0;
             if (acc >= a.maxDbMatches) {
-                if (acc >= 2ull * a.maxDbMatches - 1ull) S.fail |= 2u;      // at least two overflows for sure
+                if (acc >= 2ull * a.maxDbMatches - 1ull && !(a.debugSkip & 4)) S.fail |= 2u;      // at least two overflows for sure
                 else {
                     const unsigned long long x = a.maxDbMatches - 1ull;     // the bucket holding hit x opens chunk 1
                     int s = 0;
@@ -418,11 +653,12 @@ __global__ void __launch_bounds__(PF_THREADS, 2) prefilterKernel(PrefilterArgs a
                 S.nBound = 1;
                 // a second overflow inside chunk 1?
                 const unsigned long long g = S.sliceBase[bs] + S.boundSeq;
-                if (S.sliceBase[PF_WARPS] - g >= a.maxDbMatches) S.fail |= 2u;
+                if (S.sliceBase[PF_WARPS] - g >= a.maxDbMatches && !(a.debugSkip & 4)) S.fail |= 2u;
             }
             __syncthreads();
         }
 
+        const long long clk1 = clock64();
         // ---------------- P2-P4: per warp, bin by bin
         if (!S.fail) {
             const uint32_t nBound = S.nBound, boundSlice = S.boundSlice, boundSeq = S.boundSeq;
@@ -435,10 +671,12 @@ __global__ void __launch_bounds__(PF_THREADS, 2) prefilterKernel(PrefilterArgs a
                 uint32_t nC = 0;
                 // ---- P2: double-hit rule in stream order (CacheFriendlyOperations::findDuplicates restated per target)
                 auto rule = [&](const uint2 *reg, const uint32_t s, const uint32_t lo, const uint32_t hi) {
+                    uint2 nxt = make_uint2(0u, 0u);
+                    if (lo + lane < hi) nxt = reg[lo + lane];
                     for (uint32_t e0 = lo; e0 < hi; e0 += 32) {
                         const bool validE = e0 + lane < hi;
-                        uint32_t ex = 0, ey = 0;
-                        if (validE) { const uint2 e = reg[e0 + lane]; ex = e.x; ey = e.y; }
+                        const uint32_t ex = nxt.x, ey = nxt.y;
+                        if (e0 + 32 + lane < hi) nxt = reg[e0 + 32 + lane];       // next step's entries are in flight during this one
                         const uint32_t tl = validE ? (ex & 0x1fffu) : (0x80000000u | lane);     // unique dummy for idle lanes
                         const uint32_t diag16 = (ex >> 13) & 0xffffu;
                         const uint32_t d8 = diag16 & 0xffu;
@@ -481,7 +719,8 @@ __global__ void __launch_bounds__(PF_THREADS, 2) prefilterKernel(PrefilterArgs a
                     const uint32_t n = cntAll[s * nBins + bin];
                     const uint2 *reg = poolC + ((size_t)s * nBins + bin) * a.regionCap;
                     uint32_t split = n;
-                    if (resetPending && s >= boundSlice) {
+                    const bool resetHere = resetPending && s >= boundSlice;
+                    if (resetHere) {
                         split = 0;
                         if (s == boundSlice) {
                             // entries are ordered by running number: count those before the boundary
@@ -490,14 +729,17 @@ __global__ void __launch_bounds__(PF_THREADS, 2) prefilterKernel(PrefilterArgs a
                             for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
                             split = c;
                         }
-                        rule(reg, s, 0u, split);
-                        // chunk 1 starts: the reference runs findDuplicates on a cleared table; the collapse state (last
-                        // emitted diagonal) lives on through mergeDiagonalDuplicates
-                        for (uint32_t i = lane; i < a.binSize; i += 32) tab16[i] &= 0xff00u;
-                        __syncwarp();
                         resetPending = false;
-                        rule(reg, s, split, n);
-                    } else rule(reg, s, 0u, n);
+                    }
+                    for (int part = 0; part < 2; part++) {
+                        if (part == 1 && resetHere) {
+                            // chunk 1 starts: the reference runs findDuplicates on a cleared table; the collapse state (last
+                            // emitted diagonal) lives on through mergeDiagonalDuplicates
+                            for (uint32_t i = lane; i < a.binSize; i += 32) tab16[i] &= 0xff00u;
+                            __syncwarp();
+                        }
+                        rule(reg, s, part ? split : 0u, part ? n : split);
+                    }
                 }
                 if (nC > a.candCap) { overflow = true; nC = a.candCap; }
                 stCands += (lane == 0) ? nC : 0;
@@ -507,7 +749,10 @@ __global__ void __launch_bounds__(PF_THREADS, 2) prefilterKernel(PrefilterArgs a
                     const uint32_t c = c0 + lane;
                     if (c < nC) {
                         const uint64_t v = candW[c];
-                        const int sc = diagonalScoreLane<true>(a.tRes, a.tOff, S.sub32, qp, Lq, (uint32_t)(v >> 32), (int)(int16_t)(uint16_t)(v >> 16), stDiagRes);
+                        const uint32_t ct = (uint32_t)(v >> 32);
+                        const int cd = (int)(int16_t)(uint16_t)(v >> 16);
+                        const int sc = useProf ? diagonalScoreProf(a.tRes, a.tOff, S.u.prof, Lq, ct, cd, stDiagRes)
+                                               : diagonalScoreSlow(a.tRes, a.tOff, S.u.prof, S.sub32, qp, 0, 1, Lq, ct, cd, &stDiagRes);
                         candW[c] = v | ((uint64_t)min(sc, 255) << 8);
                     }
                 }
@@ -566,6 +811,11 @@ __global__ void __launch_bounds__(PF_THREADS, 2) prefilterKernel(PrefilterArgs a
         }
 
         // ---------------- P5: threshold (QueryMatcher::computeScoreThreshold), selection, final order, output
+        auto scoreUncapped = [&](const uint32_t t, const int diag, unsigned long long &res) -> int {
+            return diagonalScoreSlow(a.tRes, a.tOff, S.u.prof, S.sub32, qp, useProf ? 1 : 0, 0, Lq, t, diag, &res);
+        };
+        const long long clk2 = clock64();
+        long long clkSel = 0;
         const uint32_t nKeep = S.nKeep;
         if (tid == 0) {
             uint32_t found = 0, sc;
@@ -589,8 +839,8 @@ __global__ void __launch_bounds__(PF_THREADS, 2) prefilterKernel(PrefilterArgs a
             if (tid == 0) {
                 int best = 0, run = 0;
                 for (int p = 0; p < Lq; p++) {
-                    const uint32_t qv = qp[p];
-                    run += (int)S.sub32[(qv & 0xffu) * 32u + (qv & 0xffu)] + (int)(int8_t)(qv >> 8);
+                    const uint32_t qcode = a.q.code[qBase + p];
+                    run += (int)S.sub32[qcode * 32u + qcode] + (int)a.q.corr[qBase + p];
                     run = max(run, 0);
                     best = max(best, run);
                 }
@@ -603,7 +853,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) prefilterKernel(PrefilterArgs a
                 uint4 v = keepC[i];
                 if ((v.y >> 16) == 255u) {
                     unsigned long long dummy = 0;
-                    const uint32_t full = (uint32_t)diagonalScoreLane<false>(a.tRes, a.tOff, S.sub32, qp, Lq, v.x, (int)(int16_t)(uint16_t)(v.y & 0xffffu), dummy);
+                    const uint32_t full = (uint32_t)scoreUncapped(v.x, (int)(int16_t)(uint16_t)(v.y & 0xffffu), dummy);
                     const uint32_t newScore = full - 255u;
                     const float sc = (float)min(newScore, 65535u);
                     const float scaled = __fmul_rn(__fdiv_rn(sc, fltMaxSelf), 255.0f);
@@ -646,6 +896,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) prefilterKernel(PrefilterArgs a
             return ((unsigned long long)(255u - (needRescale ? v.w : 255u)) << 40) | ((unsigned long long)(v.x & a.binMask) << 32) | v.z;
         };
         if (nAt > room) {
+            clkSel = clock64();
             // radix select of the room-th smallest key (keys are distinct: the running number is)
             if (room == 0) selLimit = 0ull;              // nothing fits; key 0 cannot occur together with room == 0 ... guard below
             else {
@@ -673,6 +924,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) prefilterKernel(PrefilterArgs a
                 }
                 selLimit = S.selPrefix;
             }
+            clkSel = clock64() - clkSel;
         }
         for (uint32_t i0 = 0; i0 < nKeep; i0 += PF_THREADS) {
             const uint32_t i = i0 + tid;
@@ -698,7 +950,7 @@ __global__ void __launch_bounds__(PF_THREADS, 2) prefilterKernel(PrefilterArgs a
             for (uint32_t r = tid; r < nRes; r += PF_THREADS) {
                 if (resScore[r] >= 255 && resScore[r] != 65535) {
                     unsigned long long dummy = 0;
-                    resScore[r] = diagonalScoreLane<false>(a.tRes, a.tOff, S.sub32, qp, Lq, resT[r], (int)(int16_t)(uint16_t)resAux[r], dummy);
+                    resScore[r] = scoreUncapped(resT[r], (int)(int16_t)(uint16_t)resAux[r], dummy);
                 }
             }
         }
@@ -758,6 +1010,18 @@ __global__ void __launch_bounds__(PF_THREADS, 2) prefilterKernel(PrefilterArgs a
                 atomicAdd(&a.stats[ST_CANDS], S.stat[ST_CANDS]);
                 if (eligible + first > nRes) atomicAdd(&a.stats[ST_TRUNC], 1ull);
                 if (S.nBound) atomicAdd(&a.stats[ST_CHUNKED], 1ull);
+                const long long clk3 = clock64();
+                atomicAdd(&a.stats[ST_CYC_P1], (unsigned long long)(clk1 - clk0));
+                atomicAdd(&a.stats[ST_CYC_P24], (unsigned long long)(clk2 - clk1));
+                atomicAdd(&a.stats[ST_CYC_P5], (unsigned long long)(clk3 - clk2));
+                atomicAdd(&a.stats[ST_CYC_SEL], (unsigned long long)clkSel);
+                atomicAdd(&a.stats[ST_CYC_P0B], (unsigned long long)S.clkP0b);
+                atomicAdd(&a.stats[ST_CYC_STAGEB], (unsigned long long)S.prof1[0]);
+                atomicAdd(&a.stats[ST_CYC_DRAIN], (unsigned long long)S.prof1[1]);
+                atomicAdd(&a.stats[ST_CYC_BIG], (unsigned long long)S.prof1[2]);
+                atomicAdd(&a.stats[ST_CYC_TAIL], (unsigned long long)S.prof1[3]);
+                atomicAdd(&a.stats[ST_N_STAGEB], (unsigned long long)S.prof1[4]);
+                atomicAdd(&a.stats[ST_N_HITROWS], (unsigned long long)S.prof1[5]);
             }
         }
     }

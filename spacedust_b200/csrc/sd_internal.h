@@ -81,11 +81,12 @@ struct DevBuf {
 };
 
 enum ScratchSlot {
-    SL_PF_TABLE = 0, SL_PF_CAND, SL_PF_KEEP, SL_PF_REST, SL_PF_RESS, SL_PF_RESD, SL_PF_OUT, SL_PF_DENSE, SL_PF_CSEQ, SL_PF_QPACK,
+    SL_PF_TABLE = 0, SL_PF_CAND, SL_PF_KEEP, SL_PF_REST, SL_PF_RESS, SL_PF_RESD, SL_PF_OUT, SL_PF_DENSE, SL_PF_CSEQ, SL_PF_QPACK, SL_PF_POSINFO, SL_PF_POSPREFIX,
     SL_AL_FWD, SL_AL_WORD, SL_AL_BIG, SL_AL_REV, SL_AL_RES, SL_AL_HITS, SL_AL_TB, SL_AL_TBRES, SL_AL_IDENT, SL_AL_ORDER,
     SL_AL_PROFF, SL_AL_PROFR, SL_AL_PROFS, SL_AL_BOUND, SL_AL_PAIRQ, SL_AL_PAIRT,
     SL_TB_DIR, SL_TB_ROWS, SL_TB_REV, SL_TB_POOL, SL_SW_KEYA, SL_SW_KEYB, SL_SW_VALA, SL_SW_VALB, SL_SW_ORDER, SL_SW_TMP, SL_COUNT
 };
+static_assert(SL_COUNT <= 48, "sd_context::devSlot is too small");
 void *ctxDeviceScratch(sd_context *ctx, int slot, size_t bytes);     // nullptr + error message on failure
 void *ctxPinnedScratch(sd_context *ctx, int slot, size_t bytes);
 
@@ -214,8 +215,7 @@ struct sd_context {
     sd::SubMat seedMat;       // VTML80 x8, bias -0.2   (Prefiltering.cpp:68)
     sd::SubMat diagMat;       // BLOSUM62 x2, bias -0.2 (Prefiltering.cpp:69)
     sd::SubMat alnMat;        // BLOSUM62 x2, bias 0    (Alignment.cpp:152)
-    sd::DevBuf<int16_t> e3score;
-    sd::DevBuf<uint16_t> e3index;
+    sd::DevBuf<uint32_t> e3pair;     // sorted 3-mer neighbour rows 8000 x 8000: score | index << 16 (256 MB)
     sd::DevBuf<uint16_t> e3cnt;      // 8000 x 512 cumulative score counts of the rows (8 MB, L2 resident)
     bool haveExt3 = false;
     // align: smallest passing raw score per query length for (database residues, -e)

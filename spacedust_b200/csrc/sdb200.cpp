@@ -96,8 +96,57 @@ Args parseArgs(int argc, char **argv, int first) {
     return a;
 }
 
+// Every flag is classified: implemented (read somewhere below), inert for this path (host-runtime knobs and parameters of code
+// that `--search-mode 0` sequence search never reaches: nucleotide / ORF extraction, profile building, GPU server of the
+// reference, ...), or accepted only with the value the clustersearch workflow passes (data/clustersearch.sh, blastp.sh) because any
+// other value selects code that is not built here.  Anything else stops the program: a silently ignored flag would return a
+// different result with exit code 0.
+void checkKnownFlags(const Args &a) {
+    static const char *implemented[] = {
+        "-s", "-c", "-e", "-k", "-v", "-a", "--max-seqs", "--min-ungapped-score", "--cov-mode", "--mask", "--mask-prob", "--comp-bias-corr",
+        "--min-seq-id", "--min-aln-len", "--score-bias", "--gap-open", "--gap-extend", "--alignment-mode", "--filter-self-match",
+        "--max-gene-gap", "--cluster-size", "--cluster-pval", "--multihit-pval", "--alpha", "--gpu", "--gpus", "--write-dbs", "--search-mode",
+        "--num-iterations", "--exact-kmer-matching", "--diag-score", "--spaced-kmer-mode", "--realign", "--alt-ali", "--compressed",
+        "--split", "--add-self-matches", "--cluster-use-weight", "--aggregation-mode", "--sub-mat", "--seed-sub-mat", nullptr};
+    static const char *inert[] = {
+        "--threads", "--remove-tmp-files", "--force-reuse", "--db-load-mode", "--split-mode", "--split-memory-limit", "--disk-space-limit",
+        "--local-tmp", "--mpi-runner", "--gpu-server", "--gpu-server-wait-timeout", "--zdrop", "--pca", "--pcb", "--mask-profile", "--e-profile",
+        "--wg", "--allow-deletion", "--filter-msa", "--filter-min-enable", "--max-seq-id", "--qid", "--qsc", "--cov", "--diff", "--pseudo-cnt-mode",
+        "--profile-output-mode", "--min-length", "--max-length", "--max-gaps", "--contig-start-mode", "--contig-end-mode", "--orf-start-mode",
+        "--forward-frames", "--reverse-frames", "--translation-table", "--translate", "--use-all-table-starts", "--id-offset", "--create-lookup",
+        "--sequence-overlap", "--sequence-split-mode", "--headers-split-mode", "--translation-mode", "--strand", "--start-sens", "--sens-steps",
+        "--realign-score-bias", "--realign-max-seqs", "--corr-score-weight", "--chain-alignments", "--merge-query", "--db-output",
+        "--tar-include", "--tar-exclude", "--file-include", "--file-exclude", "--gff-type", "--dbtype", "--shuffle", "--write-lookup",
+        "--createdb-mode", "--stat", "--tsv", "--output-mode", "--mask-n-repeat", nullptr};
+    struct Only { const char *flag; const char *values[3]; };
+    static const Only only[] = {
+        {"--suboptimal-hits", {"0"}}, {"--simple-best-hit", {"1"}}, {"--profile-cluster-search", {"0"}},
+        {"--max-accept", {"2147483647"}}, {"--max-rejected", {"2147483647"}}, {"--seq-id-mode", {"0"}},
+        {"--alignment-output-mode", {"0"}}, {"--wrapped-scoring", {"0"}}, {"--exhaustive-search", {"0"}},
+        {"--exhaustive-search-filter", {"0"}}, {"--target-search-mode", {"0"}}, {"--k-score", {"seq:2147483647,prof:2147483647", "2147483647"}},
+        {"--alph-size", {"aa:21,nucl:5", "21"}}, {"--comp-bias-corr-scale", {"1", "1.0", "1.000"}}, {"--mask-lower-case", {"0"}},
+        {"--max-seq-len", {"65535"}}, {"--prefilter-mode", {"0"}}, {"--rescore-mode", {"0"}}, {"--filter-hits", {"0"}},
+        {"--sort-results", {"0"}}, {"--search-type", {"0"}}, {"--lca-search", {"0"}}, {"--taxon-list", {""}},
+    };
+    for (const auto &kv : a.flags) {
+        bool ok = false;
+        for (int i = 0; implemented[i] && !ok; i++) ok = kv.first == implemented[i];
+        for (int i = 0; inert[i] && !ok; i++) ok = kv.first == inert[i];
+        if (ok) continue;
+        bool known = false;
+        for (const Only &o : only) {
+            if (kv.first != o.flag) continue;
+            known = true;
+            for (const char *v : o.values) ok = ok || (v && kv.second == v);
+            if (!ok) die("%s %s is not implemented (only %s %s, the value the clustersearch workflow passes)", o.flag, kv.second.c_str(), o.flag, o.values[0]);
+        }
+        if (!known) die("unknown or unsupported flag %s (it would be ignored; refusing to run)", kv.first.c_str());
+    }
+}
+
 // Flags whose non-default values select code this path does not implement.
 void rejectUnsupported(const Args &a) {
+    checkKnownFlags(a);
     if (a.num("--search-mode", 0) != 0) die("--search-mode %s is not implemented (only 0: MMseqs2 protein search)", a.str("--search-mode", "").c_str());
     if (a.num("--num-iterations", 1) != 1) die("--num-iterations > 1 (profile search) is not implemented");
     if (a.num("-k", 0) != 0 && a.num("-k", 0) != 6) die("-k %s is not implemented (k = 6, as the reference selects for these DB sizes)", a.str("-k", "").c_str());

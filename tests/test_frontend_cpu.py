@@ -195,6 +195,14 @@ def test_iteration_glue_modules_vs_reference(synth_small):
         ref = helpers.read_db(os.path.join(d, "sub_ref"))
         assert helpers.read_db(os.path.join(d, "sub_mine")) == ref
         assert 0 < sum(len(v) for v in ref.values()) < sum(len(v) for v in helpers.read_db(os.path.join(d, "pref")).values())
+        # -e and --e-profile differ: the threshold is the smaller one (subtractdbs.cpp:17), in either order
+        helpers.run_ref(["align", db, db, os.path.join(d, "pref"), os.path.join(d, "aln10"), "-a", "1", "-e", "10", "--threads", "2", "-v", "1"])
+        for tag, e, ep in (("a", "1e-8", "0.1"), ("b", "1", "1e-8")):
+            helpers.run_ref(["subtractdbs", os.path.join(d, "aln10"), os.path.join(d, "aln"), os.path.join(d, "sub2_ref" + tag), "--e-profile", ep,
+                             "-e", e, "--threads", "2", "-v", "1"])
+            subprocess.run([SDB200, "subtractdbs", os.path.join(d, "aln10"), os.path.join(d, "aln"), os.path.join(d, "sub2_mine" + tag),
+                            "--e-profile", ep, "-e", e], check=True)
+            assert helpers.read_db(os.path.join(d, "sub2_mine" + tag)) == helpers.read_db(os.path.join(d, "sub2_ref" + tag)), tag
         helpers.run_ref(["mergedbs", db, os.path.join(d, "mrg_ref"), os.path.join(d, "aln"), os.path.join(d, "sub_ref"), "-v", "1"])
         subprocess.run([SDB200, "mergedbs", db, os.path.join(d, "mrg_mine"), os.path.join(d, "aln"), os.path.join(d, "sub_mine")], check=True)
         assert helpers.read_db(os.path.join(d, "mrg_mine")) == helpers.read_db(os.path.join(d, "mrg_ref"))
