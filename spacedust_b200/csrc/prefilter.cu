@@ -223,6 +223,7 @@ __global__ void kmerThresholds(const uint8_t *__restrict__ code, const uint32_t 
 }
 
 #include "prefilter_kernel.cuh"
+#include "prefilter_stream.cuh"
 
 // dense[offs[q] + i] = out[q*maxHits + i]; one warp per query
 __global__ void compactHits(const sd_prefilter_hit *__restrict__ out, const uint32_t *__restrict__ count,
@@ -530,13 +531,118 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     uint32_t maxLq = 1;
     for (uint32_t i = 0; i < nq; i++) maxLq = std::max(maxLq, hOff[i + 1] - hOff[i]);
 
+    // QueryMatcher.cpp:43 (SD_PF_MAXDBMATCHES: test hook, the oracle has the same knob)
+    unsigned long long maxDbMatches = 2ull * std::max<unsigned long long>(1000000ull, idx->nT);
+    if (getenv("SD_PF_MAXDBMATCHES")) maxDbMatches = strtoull(getenv("SD_PF_MAXDBMATCHES"), nullptr, 10);
+
+    ScratchBuf<sd_prefilter_hit> dOut(ctx, SL_PF_OUT);
+    DevBuf<uint32_t> dOutCount, dNext, dFail, dOrder2;
+    DevBuf<unsigned long long> dStats;
+    if ((rc = dOut.alloc((size_t)nq * maxHits)) || (rc = dOutCount.alloc(nq)) || (rc = dNext.alloc(4)) || (rc = dStats.alloc(ST_N)) || (rc = dFail.alloc(nq)) ||
+        (rc = dOrder2.alloc(nq)))
+        return rc;
+    SD_CUDA(cudaMemsetAsync(dOutCount.p, 0, nq * sizeof(uint32_t), st));
+    SD_CUDA(cudaMemsetAsync(dStats.p, 0, ST_N * sizeof(unsigned long long), st));
+    const uint32_t initNext[4] = {0u, 0xffffffffu, 0u, 0u};     // next query, first failing query, number of listed queries
+    SD_CUDA(cudaMemcpyAsync(dNext.p, initNext, sizeof initNext, cudaMemcpyHostToDevice, st));
+    SD_CUDA(cudaEventRecord(evk0, st));
+
+    // ---- kernel choice by the number of targets: the streaming kernel (one warp per query, per-warp last-diagonal table in
+    // global memory) has the lower cost per index entry while its tables stay small; the binned kernel (one CTA per query,
+    // shared-memory tables) does not depend on the table size and restates the reference's hit-buffer overflow, so it also
+    // takes the queries the streaming kernel hands over.  SD_PF_STREAM_MAX: largest target count for the streaming kernel.
+    const long streamMax = getenv("SD_PF_STREAM_MAX") ? atol(getenv("SD_PF_STREAM_MAX")) : 262144;
+    const bool useStream = (long)idx->nT <= streamMax;
+    const uint32_t *binnedOrder = dOrder.p;      // queries for the binned kernel (device list) ...
+    uint32_t binnedCount = nq;                   // ... and how many
+    if (useStream) {
+        const uint32_t nCtaS = std::max(1u, std::min<uint32_t>((uint32_t)(ctx->smCount * 4), (nq + PS_WARPS - 1) / PS_WARPS));
+        const uint32_t nWarpsS = nCtaS * PS_WARPS;
+        // first-pass capacity of the per-warp candidate lists (SD_PF_CANDCAP: test hook that forces the second pass)
+        uint32_t candCapS = 32768u;
+        while (candCapS < 262144u && (uint64_t)candCapS * 8u < idx->nT) candCapS *= 2;
+        if (getenv("SD_PF_CANDCAP")) candCapS = (uint32_t)std::max(32, atoi(getenv("SD_PF_CANDCAP")));
+        ScratchBuf<uint32_t> sTable(ctx, SL_PF_TABLE), sResT(ctx, SL_PF_REST);
+        ScratchBuf<uint64_t> sCand(ctx, SL_PF_CAND), sKeep(ctx, SL_PF_KEEP);
+        ScratchBuf<int32_t> sResScore(ctx, SL_PF_RESS);
+        ScratchBuf<uint16_t> sResDiag(ctx, SL_PF_RESD);
+        if ((rc = sTable.alloc((size_t)nWarpsS * idx->nT)) || (rc = sCand.alloc((size_t)nWarpsS * candCapS)) || (rc = sKeep.alloc((size_t)nWarpsS * candCapS)) ||
+            (rc = sResT.alloc((size_t)nWarpsS * maxHits)) || (rc = sResScore.alloc((size_t)nWarpsS * maxHits)) || (rc = sResDiag.alloc((size_t)nWarpsS * maxHits)))
+            return rc;
+        SD_CUDA(cudaMemsetAsync(sTable.p, 0, (size_t)nWarpsS * idx->nT * sizeof(uint32_t), st));
+        StreamArgs sa{};
+        sa.tRes = idx->res.p; sa.tOff = idx->off.p; sa.nT = idx->nT;
+        sa.bm = idx->bm.p; sa.rows = idx->rows.p; sa.ent = idx->ent.p;
+        sa.e3pair = ctx->e3pair.p; sa.e3cnt = ctx->e3cnt.p; sa.diagSub = dDiagSub.p;
+        sa.q.code = dCode.p; sa.q.off = dOff.p; sa.q.corr = dCorr.p; sa.q.thr = dThr.p;
+        sa.nQ = nq; sa.order = dOrder.p; sa.queryFirst = query_first; sa.sameDb = par->same_db;
+        sa.maxHits = maxHits; sa.minDiagScore = (uint32_t)std::max(par->min_ungapped_score, 0);
+        sa.covThr = par->cov_thr; sa.covMode = par->cov_mode; sa.binMask = (uint32_t)binSize - 1u;
+        sa.maxDbMatches = maxDbMatches;
+        sa.table = sTable.p; sa.candCap = candCapS; sa.cand = sCand.p; sa.keep = sKeep.p;
+        sa.resT = sResT.p; sa.resScore = sResScore.p; sa.resDiag = sResDiag.p;
+        sa.out = dOut.p; sa.outCount = dOutCount.p; sa.stats = dStats.p; sa.nextQuery = dNext.p; sa.errQuery = dNext.p + 1;
+        sa.failList = dFail.p; sa.nFail = dNext.p + 2;
+        sa.evictFirst = 0; sa.prefetch = 0; sa.debugSkip = 0;
+        SD_CUDA(cudaFuncSetAttribute(prefilterStreamKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_DYN_SMEM));
+        if (getenv("SD_PF_DEBUG")) fprintf(stderr, "[sd] prefilter: streaming kernel, %u CTAs x %d warps, candidate lists %u\n", nCtaS, PS_WARPS, candCapS);
+        prefilterStreamKernel<<<nCtaS, PS_WARPS * 32, PS_DYN_SMEM, st>>>(sa);
+        ctx->launches++;
+        SD_CUDA(cudaGetLastError());
+        // listed queries: bit 31 = reached the reference's hit-buffer limit (-> binned kernel); otherwise the candidate list
+        // did not fit (-> second streaming launch over just those, few warps with 4 M entry lists)
+        uint32_t hN[4];
+        SD_CUDA(cudaMemcpyAsync(hN, dNext.p, sizeof hN, cudaMemcpyDeviceToHost, st));
+        SD_CUDA(cudaStreamSynchronize(st));
+        std::vector<uint32_t> listed(hN[2]), big, over;
+        if (hN[2]) {
+            SD_CUDA(cudaMemcpyAsync(listed.data(), dFail.p, hN[2] * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            SD_CUDA(cudaStreamSynchronize(st));
+        }
+        for (uint32_t v : listed) (v >> 31 ? over : big).push_back(v & 0x7fffffffu);
+        if (getenv("SD_PF_DEBUG")) fprintf(stderr, "[sd] prefilter: %zu queries reach the hit-buffer limit, %zu overflow the candidate lists\n", over.size(), big.size());
+        if (!big.empty()) {
+            const uint32_t bigCap = 1u << 22;
+            const uint32_t nCta2 = std::max(1u, std::min<uint32_t>(((uint32_t)big.size() + PS_WARPS - 1) / PS_WARPS, 16u));
+            const uint32_t nWarps2 = nCta2 * PS_WARPS;
+            DevBuf<uint64_t> dCand2, dKeep2;
+            if ((rc = dCand2.alloc((size_t)nWarps2 * bigCap)) || (rc = dKeep2.alloc((size_t)nWarps2 * bigCap))) return rc;
+            SD_CUDA(cudaMemcpyAsync(dOrder2.p, big.data(), big.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            SD_CUDA(cudaMemsetAsync(sTable.p, 0, (size_t)nWarps2 * idx->nT * sizeof(uint32_t), st));      // epochs restart at 0
+            SD_CUDA(cudaMemsetAsync(dStats.p + ST_ERR_CAP, 0, sizeof(unsigned long long), st));
+            SD_CUDA(cudaMemcpyAsync(dNext.p, initNext, sizeof initNext, cudaMemcpyHostToDevice, st));
+            StreamArgs sb = sa;
+            sb.order = dOrder2.p; sb.nQ = (uint32_t)big.size(); sb.candCap = bigCap; sb.cand = dCand2.p; sb.keep = dKeep2.p;
+            prefilterStreamKernel<<<nCta2, PS_WARPS * 32, PS_DYN_SMEM, st>>>(sb);
+            ctx->launches++;
+            SD_CUDA(cudaGetLastError());
+            SD_CUDA(cudaMemcpyAsync(hN, dNext.p, sizeof hN, cudaMemcpyDeviceToHost, st));
+            SD_CUDA(cudaStreamSynchronize(st));     // the second-pass buffers go out of scope
+            if (hN[2]) {     // still listed: hit-buffer limit reached (cannot happen: same stream) or 4 M candidates exceeded
+                std::vector<uint32_t> l2(hN[2]);
+                SD_CUDA(cudaMemcpyAsync(l2.data(), dFail.p, hN[2] * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                SD_CUDA(cudaStreamSynchronize(st));
+                for (uint32_t v : l2) over.push_back(v & 0x7fffffffu);     // the binned kernel's scratch is sized per query length
+            }
+        }
+        binnedCount = (uint32_t)over.size();
+        if (binnedCount) {
+            SD_CUDA(cudaMemcpyAsync(dOrder2.p, over.data(), over.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            SD_CUDA(cudaMemsetAsync(dStats.p + ST_ERR_CAP, 0, sizeof(unsigned long long), st));
+            SD_CUDA(cudaStreamSynchronize(st));     // `over` goes out of scope
+            binnedOrder = dOrder2.p;
+        }
+    }
+
+  if (binnedCount) {
+    SD_CUDA(cudaMemcpyAsync(dNext.p, initNext, sizeof initNext, cudaMemcpyHostToDevice, st));
     // ---- launch geometry: two CTAs per SM when the shared-memory split allows it
     cudaFuncAttributes fa{};
     SD_CUDA(cudaFuncGetAttributes(&fa, prefilterKernel));
     int smemPerSm = 0, smemOptin = 0;
     SD_CUDA(cudaDeviceGetAttribute(&smemPerSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device));
     SD_CUDA(cudaDeviceGetAttribute(&smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-    static const int ctasPerSm = getenv("SD_PF_CTAS") ? std::max(1, atoi(getenv("SD_PF_CTAS"))) : 2;
+    static const int ctasPerSm = getenv("SD_PF_CTAS") ? std::max(1, atoi(getenv("SD_PF_CTAS"))) : 3;
     const size_t dynBudget = std::min<size_t>((size_t)smemOptin, (size_t)smemPerSm / ctasPerSm - 1024) - fa.sharedSizeBytes;
     // ---- target bins: id ranges whose table (2 bytes + 1 bit per target) fits a warp's share of the dynamic shared memory;
     // nBins is a multiple of the warps so that every round of P2 keeps all warps busy
@@ -557,7 +663,7 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     int occ = 0;
     SD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prefilterKernel, PF_THREADS, dynSmem));
     if (occ < 1) { setError("prefilter kernel does not fit an SM (%zu bytes of shared memory)", dynSmem + fa.sharedSizeBytes); return SD_ELIMIT; }
-    const uint32_t nCta = std::max(1u, std::min<uint32_t>((uint32_t)(ctx->smCount * std::min(occ, ctasPerSm)), nq));
+    const uint32_t nCta = std::max(1u, std::min<uint32_t>((uint32_t)(ctx->smCount * std::min(occ, ctasPerSm)), binnedCount));
 
     // ---- per-CTA scratch.  Expected index entries per query position: similar k-mers per position x entries per k-mer
     // (measured on the synthetic proteomes: 425 x nEntries / 20^6); the regions of (slice, bin) get 4x the share of the
@@ -570,26 +676,19 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     if (getenv("SD_PF_REGIONCAP")) regionCap = (uint32_t)std::max(32, atoi(getenv("SD_PF_REGIONCAP")));     // test hooks: force the second pass
     if (getenv("SD_PF_CANDCAP")) candCap = (uint32_t)std::max(32, atoi(getenv("SD_PF_CANDCAP")));
     candCap = std::min(candCap, 1u << 23);
-    // QueryMatcher.cpp:43 (SD_PF_MAXDBMATCHES: test hook, the oracle has the same knob)
-    unsigned long long maxDbMatches = 2ull * std::max<unsigned long long>(1000000ull, idx->nT);
-    if (getenv("SD_PF_MAXDBMATCHES")) maxDbMatches = strtoull(getenv("SD_PF_MAXDBMATCHES"), nullptr, 10);
-
     ScratchBuf<uint2> dPool(ctx, SL_PF_TABLE);
     ScratchBuf<uint64_t> dCand(ctx, SL_PF_CAND);
-    ScratchBuf<uint32_t> dCandSeq(ctx, SL_PF_CSEQ), dResT(ctx, SL_PF_REST), dResAux(ctx, SL_PF_RESD);
+    ScratchBuf<uint32_t> dCandSeq(ctx, SL_PF_CSEQ), dSortIdx(ctx, SL_PF_SORTIDX), dResT(ctx, SL_PF_REST), dResAux(ctx, SL_PF_RESD);
     ScratchBuf<uint4> dKeep(ctx, SL_PF_KEEP);
     ScratchBuf<int32_t> dResScore(ctx, SL_PF_RESS);
     ScratchBuf<uint16_t> dQpack(ctx, SL_PF_QPACK);
     ScratchBuf<uint4> dPosInfo(ctx, SL_PF_POSINFO);
     ScratchBuf<uint32_t> dPosPrefix(ctx, SL_PF_POSPREFIX);
-    ScratchBuf<sd_prefilter_hit> dOut(ctx, SL_PF_OUT);
-    DevBuf<uint32_t> dOutCount, dNext, dFail;
-    DevBuf<unsigned long long> dStats;
     auto allocScratch = [&](uint32_t ctas, uint32_t rCap, uint32_t cCap, uint32_t &kCap) -> int {
         int r;
         kCap = (uint32_t)std::min<uint64_t>(idx->nT, (uint64_t)PF_WARPS * cCap);
         if ((r = dPool.alloc((size_t)ctas * PF_WARPS * nBins * rCap)) || (r = dCand.alloc((size_t)ctas * PF_WARPS * cCap)) ||
-            (r = dCandSeq.alloc((size_t)ctas * PF_WARPS * cCap)) || (r = dKeep.alloc((size_t)ctas * kCap)) ||
+            (r = dCandSeq.alloc((size_t)ctas * PF_WARPS * cCap)) || (r = dSortIdx.alloc((size_t)ctas * PF_WARPS * cCap)) || (r = dKeep.alloc((size_t)ctas * kCap)) ||
             (r = dResT.alloc((size_t)ctas * maxHits)) || (r = dResScore.alloc((size_t)ctas * maxHits)) || (r = dResAux.alloc((size_t)ctas * maxHits)) ||
             (r = dQpack.alloc((size_t)ctas * (maxLq + 16))) || (r = dPosInfo.alloc((size_t)ctas * (maxLq + 16))) ||
             (r = dPosPrefix.alloc((size_t)ctas * (maxLq + 16))))
@@ -597,25 +696,19 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
         return SD_OK;
     };
     uint32_t keepCap = 0;
-    if ((rc = allocScratch(nCta, regionCap, candCap, keepCap)) || (rc = dOut.alloc((size_t)nq * maxHits)) || (rc = dOutCount.alloc(nq)) ||
-        (rc = dNext.alloc(4)) || (rc = dStats.alloc(ST_N)) || (rc = dFail.alloc(nq)))
-        return rc;
-    SD_CUDA(cudaMemsetAsync(dOutCount.p, 0, nq * sizeof(uint32_t), st));
-    SD_CUDA(cudaMemsetAsync(dStats.p, 0, ST_N * sizeof(unsigned long long), st));
-    const uint32_t initNext[4] = {0u, 0xffffffffu, 0u, 0u};     // next query, first failing query, number of overflowed queries
-    SD_CUDA(cudaMemcpyAsync(dNext.p, initNext, sizeof initNext, cudaMemcpyHostToDevice, st));
+    if ((rc = allocScratch(nCta, regionCap, candCap, keepCap))) return rc;
 
     PrefilterArgs a{};
     a.tRes = idx->res.p; a.tOff = idx->off.p; a.nT = idx->nT;
     a.bm = idx->bm.p; a.rows = idx->rows.p; a.ent = idx->ent.p;
     a.e3pair = ctx->e3pair.p; a.e3cnt = ctx->e3cnt.p; a.diagSub = dDiagSub.p;
     a.q.code = dCode.p; a.q.off = dOff.p; a.q.corr = dCorr.p; a.q.thr = dThr.p;
-    a.nQ = nq; a.order = dOrder.p; a.queryFirst = query_first; a.sameDb = par->same_db;
+    a.nQ = binnedCount; a.order = binnedOrder; a.queryFirst = query_first; a.sameDb = par->same_db;
     a.maxHits = maxHits; a.minDiagScore = (uint32_t)std::max(par->min_ungapped_score, 0);
     a.covThr = par->cov_thr; a.covMode = par->cov_mode; a.binMask = (uint32_t)binSize - 1u;
     a.maxDbMatches = maxDbMatches;
     a.nBins = nBins; a.binSize = tBinSize; a.binMagic = ((1ull << 40) + tBinSize - 1) / tBinSize; a.tabBytes = tabBytes;
-    a.regionCap = regionCap; a.pool = dPool.p; a.candCap = candCap; a.cand = dCand.p; a.candSeq = dCandSeq.p;
+    a.regionCap = regionCap; a.pool = dPool.p; a.candCap = candCap; a.cand = dCand.p; a.candSeq = dCandSeq.p; a.sortIdx = dSortIdx.p;
     a.keepCap = keepCap; a.keep = dKeep.p; a.resT = dResT.p; a.resScore = dResScore.p; a.resAux = dResAux.p;
     a.qpackG = dQpack.p; a.posInfo = dPosInfo.p; a.posPrefix = dPosPrefix.p; a.maxLq = maxLq + 16;
     a.out = dOut.p; a.outCount = dOutCount.p; a.stats = dStats.p; a.nextQuery = dNext.p; a.errQuery = dNext.p + 1;
@@ -625,7 +718,6 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
         fprintf(stderr, "[sd] prefilter: %u CTAs x %d threads, %zu B dynamic + %zu B static smem, %u bins of %u targets, region %u, cand %u, keep %u, maxDbMatches %llu\n",
                 nCta, PF_THREADS, dynSmem, (size_t)fa.sharedSizeBytes, nBins, tBinSize, regionCap, candCap, keepCap, maxDbMatches);
 
-    SD_CUDA(cudaEventRecord(evk0, st));
     static const int envPersist = getenv("SD_PF_PERSIST") ? atoi(getenv("SD_PF_PERSIST")) : 0;
     if (envPersist) {
         // the occupancy bitmap is probed once per similar k-mer: keep it in the persisting part of the L2
@@ -656,30 +748,31 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
         if (getenv("SD_PF_DEBUG")) fprintf(stderr, "[sd] prefilter: %u queries overflowed the first-pass scratch\n", nFail);
         if (nFail) {
             const uint32_t nCta2 = std::max(1u, std::min<uint32_t>(nFail, std::max(1u, nCta / 16)));
-            DevBuf<uint32_t> dOrder2;
-            if ((rc = dOrder2.alloc(nFail))) return rc;
-            SD_CUDA(cudaMemcpyAsync(dOrder2.p, dFail.p, nFail * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+            DevBuf<uint32_t> dOrder3;
+            if ((rc = dOrder3.alloc(nFail))) return rc;
+            SD_CUDA(cudaMemcpyAsync(dOrder3.p, dFail.p, nFail * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
             SD_CUDA(cudaMemsetAsync(dStats.p + ST_ERR_CAP, 0, sizeof(unsigned long long), st));
             const uint32_t init2[4] = {0u, hN[1], 0u, 0u};
             SD_CUDA(cudaMemcpyAsync(dNext.p, init2, sizeof init2, cudaMemcpyHostToDevice, st));
             PrefilterArgs b = a;
             b.regionCap = regionCap * 16; b.candCap = std::min(candCap * 16, 1u << 23);
             if ((rc = allocScratch(nCta2, b.regionCap, b.candCap, b.keepCap))) return rc;
-            b.pool = dPool.p; b.cand = dCand.p; b.candSeq = dCandSeq.p; b.keep = dKeep.p; b.resT = dResT.p; b.resScore = dResScore.p;
+            b.pool = dPool.p; b.cand = dCand.p; b.candSeq = dCandSeq.p; b.sortIdx = dSortIdx.p; b.keep = dKeep.p; b.resT = dResT.p; b.resScore = dResScore.p;
             b.resAux = dResAux.p; b.qpackG = dQpack.p; b.posInfo = dPosInfo.p; b.posPrefix = dPosPrefix.p;
-            b.order = dOrder2.p; b.nQ = nFail;
+            b.order = dOrder3.p; b.nQ = nFail;
             prefilterKernel<<<nCta2, PF_THREADS, dynSmem, st>>>(b);
             ctx->launches++;
             SD_CUDA(cudaGetLastError());
             SD_CUDA(cudaStreamSynchronize(st));     // init2 and the second-pass buffers go out of scope
         }
     }
-    SD_CUDA(cudaEventRecord(evk1, st));
     if (envPersist) {
         cudaStreamAttrValue av{};
         av.accessPolicyWindow.num_bytes = 0;
         cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
     }
+  }
+    SD_CUDA(cudaEventRecord(evk1, st));
 
     std::vector<uint32_t> hCount(nq);
     unsigned long long hStats[ST_N];
@@ -689,11 +782,11 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     SD_CUDA(cudaMemcpyAsync(hNext, dNext.p, sizeof hNext, cudaMemcpyDeviceToHost, st));
     SD_CUDA(cudaStreamSynchronize(st));
     if (hStats[ST_ERR_OVERFLOW]) {
-        setError("prefilter: %llu queries return at least twice maxDbMatches = %llu index entries (first: query %u): the reference's repeated "
-                 "hit-buffer overflow path (QueryMatcher.cpp:296-303) is not implemented", hStats[ST_ERR_OVERFLOW], maxDbMatches, hNext[1]);
+        setError("prefilter: %llu queries overflow the reference's hit buffer (maxDbMatches = %llu index entries) more than %u times (first: query %u): "
+                 "not followed", hStats[ST_ERR_OVERFLOW], maxDbMatches, PF_MAXBOUND, hNext[1]);
         return SD_ELIMIT;
     }
-    if (hStats[ST_ERR_CAP]) { setError("prefilter: %llu queries overflow the enlarged hit / candidate scratch (region %u, candidates %u)", hStats[ST_ERR_CAP], regionCap * 16, candCap * 16); return SD_ELIMIT; }
+    if (hStats[ST_ERR_CAP]) { setError("prefilter: %llu queries overflow the enlarged hit / candidate scratch of the second pass", hStats[ST_ERR_CAP]); return SD_ELIMIT; }
     uint64_t totalHits = 0;
     for (uint32_t i = 0; i < nq; i++) totalHits += hCount[i];
     if (hitOffsets)

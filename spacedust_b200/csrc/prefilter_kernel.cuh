@@ -40,6 +40,7 @@ constexpr uint32_t PF_HQCAP = 256;       // hit-row ring: non-empty buckets {buc
 constexpr uint32_t PF_HQDRAIN = 128;     // stage B runs when the ring holds this many: its rows were prefetched >= 96 pushes ago
 constexpr uint32_t PF_PROFLEN = 1168;    // query positions whose 21-column diagonal profile is staged in shared memory
 constexpr uint32_t PF_MAXBINSIZE = 8192; // 13 bits of target-in-bin in a pool entry
+constexpr uint32_t PF_MAXBOUND = 15;     // hit-buffer overflows per query that are followed exactly (16 chunks)
 constexpr uint32_t PF_SEQBITS = 28;      // running number inside a slice; slice index above
 static_assert(PF_WARPS <= 16, "slice index must fit above the running number");
 
@@ -82,6 +83,7 @@ struct PrefilterArgs {
     uint32_t *resT;            // [cta][maxHits]
     int32_t *resScore;
     uint32_t *resAux;          // diag | pass<<16 ...
+    uint32_t *sortIdx;         // [cta][PF_WARPS][candCap]: candidates of a bin grouped by target (repeated-overflow path only)
     uint16_t *qpackG;          // [cta][maxLq]: staged query rows of queries longer than PF_QCAP
     uint4 *posInfo;            // [cta][maxLq]: per k-mer position {i1 | i2<<16, thr | cutoff1<<16, cutMid | cutBig<<16, similar k-mers}
     uint32_t *posPrefix;       // [cta][maxLq]: inclusive prefix of the position weights (slice balancing)
@@ -97,7 +99,7 @@ struct PrefilterArgs {
     int debugSkip;             // profiling only (SD_PF_SKIP): 1 = drop stage B (index entries), 2 = drop the bitmap loads too; results are wrong
 };
 
-enum { ST_PROBES = 0, ST_MATCHES, ST_DIAGRES, ST_HITS, ST_CANDS, ST_TRUNC, ST_ERR_CAP, ST_ERR_OVERFLOW, ST_CHUNKED,
+enum { ST_PROBES = 0, ST_MATCHES, ST_DIAGRES, ST_HITS, ST_CANDS, ST_TRUNC, ST_ERR_CAP, ST_ERR_OVERFLOW, ST_CHUNKED, ST_MULTICHUNKED,
        ST_CYC_P1, ST_CYC_P24, ST_CYC_P5, ST_CYC_SEL, ST_CYC_P0B, ST_CYC_STAGEB, ST_CYC_DRAIN, ST_CYC_BIG, ST_CYC_TAIL, ST_N_STAGEB, ST_N_HITROWS, ST_N };   // ST_CYC_*: SM cycles per phase summed over queries (thread 0's view)
 
 __device__ __forceinline__ uint2 ldgU2(const uint2 *p) { return __ldg(p); }
@@ -254,6 +256,152 @@ __device__ __noinline__ uint32_t prefilterStageB(const uint2 *__restrict__ rows,
     return seqBase;
 }
 
+// Repeated hit-buffer overflow (QueryMatcher.cpp:296-303,322-333), per target.  With k >= 2 overflows the reference's candidate
+// lists D_0..D_k (one findDuplicates result per chunk) are folded like this:
+//   overflow j = 2..k:  S = F ++ D_{j-1}  (F = D_0 before the first fold, afterwards the single survivor of the previous fold);
+//                       walk S BACKWARDS, keep an element if it carries a score or its 8-bit diagonal differs from the element
+//                       after it (mergeDiagonalKeepScoredHitsDuplicates); score the unscored ones; the survivor is the first
+//                       maximum in that reversed order (keepMaxElement).  A score of 0 counts as "no score" again.
+//   end:                S = F ++ D_k forwards, keep an element if its 8-bit diagonal differs from the element before it
+//                       (mergeDiagonalDuplicates); score the unscored ones; first maximum wins.
+// The candidates of the bin (stream order, chunk in the low byte, capped score already in place) are grouped by target with a
+// counting sort on the idle table words, then one lane folds one target.  Winners go to the CTA's kept list with their arrival
+// order (block of the origin chunk, direction).  cands / residues: the reference's counters for this path.
+__device__ __noinline__ void prefilterMergeChunks(const uint64_t *candW, const uint32_t *candSeqW, uint32_t nC, uint32_t *sortIdx,
+                                                  uint32_t *tab32, uint32_t tabWords, uint32_t binBase, uint32_t binSize, uint32_t k,
+                                                  const uint32_t *blockRank, const uint32_t *blockDir, const uint32_t *__restrict__ tOff, int Lq,
+                                                  uint4 *keepC, uint32_t keepCap, uint32_t *nKeep, uint32_t *hist,
+                                                  unsigned long long *candsOut, unsigned long long *residuesOut) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    unsigned long long cands = 0, residues = 0;
+    for (uint32_t lo = 0; lo < binSize; lo += tabWords) {
+        for (uint32_t i = lane; i < tabWords; i += 32) tab32[i] = 0u;
+        __syncwarp();
+        for (uint32_t c = lane; c < nC; c += 32) {
+            const uint32_t tl = (uint32_t)(candW[c] >> 32) - binBase - lo;
+            if (tl < tabWords) atomicAdd(&tab32[tl], 1u);
+        }
+        __syncwarp();
+        uint32_t carry = 0;
+        for (uint32_t i0 = 0; i0 < tabWords; i0 += 32) {           // exclusive prefix: start of every target's run
+            const uint32_t v = (i0 + lane < tabWords) ? tab32[i0 + lane] : 0u;
+            uint32_t x = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= (uint32_t)d) x += y;
+            }
+            if (i0 + lane < tabWords) tab32[i0 + lane] = x - v + carry;
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+        __syncwarp();
+        for (uint32_t c0 = 0; c0 < nC; c0 += 32) {                 // stable scatter; afterwards tab32[tl] = END of the run
+            const uint32_t c = c0 + lane;
+            uint32_t tl = 0xffffffffu;
+            if (c < nC) tl = (uint32_t)(candW[c] >> 32) - binBase - lo;
+            const bool valid = tl < tabWords;
+            const uint32_t grp = __match_any_sync(0xffffffffu, valid ? tl : (0x80000000u | lane));
+            const uint32_t leader = (uint32_t)__ffs(grp) - 1u;
+            uint32_t base = 0;
+            if (valid && lane == leader) { base = tab32[tl]; tab32[tl] = base + (uint32_t)__popc(grp); }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (valid) sortIdx[base + (uint32_t)__popc(grp & ltMask)] = c;
+            __syncwarp();
+        }
+        const uint32_t nTargets = min(tabWords, binSize - lo);
+        for (uint32_t t0 = 0; t0 < nTargets; t0 += 32) {
+            const uint32_t tl = t0 + lane;
+            int best = -1;
+            uint32_t bestScore = 0;
+            if (tl < nTargets) {
+                const uint32_t b = tl ? tab32[tl - 1] : 0u, e = tab32[tl];
+                if (e > b) {
+                    const uint32_t t = binBase + lo + tl;
+                    const int Lt = (int)(__ldg(&tOff[t + 1]) - __ldg(&tOff[t]));
+                    auto elem = [&](uint32_t i) -> uint64_t { return candW[sortIdx[i]]; };
+                    auto diagLen = [&](uint64_t v) -> uint32_t {                  // residues the diagonal scorer reads
+                        const int diag = (int)(int16_t)(uint16_t)(v >> 16);
+                        if (diag >= 0) return diag >= Lq ? 0u : (uint32_t)min(Lt, Lq - diag);
+                        return -diag >= Lt ? 0u : (uint32_t)min(Lt + diag, Lq);
+                    };
+                    int f = -1;                        // survivor of the folds so far (position in the run)
+                    uint32_t fScore = 0;
+                    uint32_t p = b;
+                    for (uint32_t j = 2; j <= k; j++) {
+                        uint32_t s0b = p, s0e = p;
+                        if (j == 2) { while (s0e < e && (uint32_t)(elem(s0e) & 0xffu) == 0u) s0e++; p = s0e; }
+                        const uint32_t cb = p;
+                        uint32_t ce = p;
+                        while (ce < e && (uint32_t)(elem(ce) & 0xffu) == j - 1u) ce++;
+                        p = ce;
+                        bool first = true;
+                        uint32_t table = 0;
+                        int bst = -1;
+                        uint32_t bstScore = 0;
+                        auto visit = [&](uint32_t i, bool isF) {
+                            const uint64_t v = elem(i);
+                            const uint32_t d8 = (uint32_t)(v >> 16) & 0xffu;
+                            const bool scored = isF && fScore != 0;
+                            const bool keep = first || scored || d8 != table;
+                            table = d8;
+                            first = false;
+                            if (keep) {
+                                const uint32_t sc = scored ? fScore : ((uint32_t)(v >> 8) & 0xffu);
+                                if (!scored) residues += diagLen(v);
+                                if (bst < 0 || sc > bstScore) { bst = (int)i; bstScore = sc; }
+                            }
+                        };
+                        for (uint32_t x = ce; x-- > cb;) visit(x, false);
+                        if (j == 2) { for (uint32_t x = s0e; x-- > s0b;) visit(x, false); }
+                        else if (f >= 0) visit((uint32_t)f, true);
+                        if (bst >= 0) { f = bst; fScore = bstScore; }
+                    }
+                    {
+                        bool first = true;
+                        uint32_t prevD8 = 0;
+                        auto visit = [&](uint32_t i, bool isF) {
+                            const uint64_t v = elem(i);
+                            const uint32_t d8 = (uint32_t)(v >> 16) & 0xffu;
+                            const bool keep = first || d8 != prevD8;
+                            prevD8 = d8;
+                            first = false;
+                            if (keep) {
+                                cands++;
+                                const bool scored = isF && fScore != 0;
+                                const uint32_t sc = scored ? fScore : ((uint32_t)(v >> 8) & 0xffu);
+                                if (!scored) residues += diagLen(v);
+                                if (best < 0 || sc > bestScore) { best = (int)i; bestScore = sc; }
+                            }
+                        };
+                        if (f >= 0) visit((uint32_t)f, true);
+                        for (uint32_t x = p; x < e; x++) visit(x, false);
+                    }
+                }
+            }
+            const bool win = best >= 0;
+            const uint32_t wb = __ballot_sync(0xffffffffu, win);
+            uint32_t base = 0;
+            if (lane == 0 && wb) base = atomicAdd(nKeep, (uint32_t)__popc(wb));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (win) {
+                const uint32_t ci = sortIdx[best];
+                const uint64_t v = candW[ci];
+                const uint32_t chunk = (uint32_t)(v & 0xffu);
+                const uint32_t g = candSeqW[ci];
+                const uint32_t pos = base + (uint32_t)__popc(wb & ltMask);
+                if (pos < keepCap)
+                    keepC[pos] = make_uint4((uint32_t)(v >> 32), ((uint32_t)(v >> 16) & 0xffffu) | (bestScore << 16), blockDir[chunk] ? g : ~g, blockRank[chunk] << 8);
+                atomicAdd(&hist[bestScore], 1u);
+            }
+            __syncwarp();
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) cands += __shfl_xor_sync(0xffffffffu, cands, d);
+    if (lane == 0) *candsOut += cands;          // the caller keeps this counter on lane 0 and reduces the residues itself
+    *residuesOut += residues;
+}
+
 // Shared memory: static part below + dynamic [counters: PF_WARPS*nBins u32][tables: PF_WARPS * tabBytes]
 struct PfShared {
     int8_t sub32[AA * 32];
@@ -271,7 +419,9 @@ struct PfShared {
     unsigned long long stat[8];
     unsigned long long selPrefix;
     uint32_t q, fail, nKeep, nRes, nAt, thrScore, selCount, selNeed, nOut;
-    uint32_t boundSlice, boundSeq, nBound, boundSearch;
+    uint32_t nBound, boundSearch;
+    uint32_t boundSlice[PF_MAXBOUND], boundSeq[PF_MAXBOUND];     // chunk c+1 starts at (slice, running number)
+    uint32_t blockRank[PF_MAXBOUND + 1], blockDir[PF_MAXBOUND + 1];   // final arrival order of the surviving element by origin chunk
     int maxSelf;
 };
 
@@ -613,55 +763,79 @@ __global__ void __launch_bounds__(PF_THREADS, 3) prefilterKernel(PrefilterArgs a
                 S.u.prof[i] = (int8_t)((int)S.sub32[(uint32_t)a.q.code[qBase + p] * 32u + c] + (int)a.q.corr[qBase + p]);
             }
         }
-        // ---------------- chunk boundary of the reference's hit buffer (see the header comment)
+        // ---------------- chunk boundaries of the reference's hit buffer (see the header comment)
+        // Chunk c+1 opens with the bucket that holds hit number G_c + maxDbMatches - 1 (G_c = first hit of chunk c): the reference
+        // flushes when buffered + bucket size reaches the limit, and the bucket goes to the new chunk (QueryMatcher.cpp:280-314).
         if (tid == 0) {
             unsigned long long acc = 0;
             for (int s = 0; s < PF_WARPS; s++) { S.sliceBase[s] = acc; acc += S.sliceTotal[s]; }
             S.sliceBase[PF_WARPS] = acc;
             S.stat[ST_MATCHES] = acc;
-            S.boundSearch = 0;
-            if (acc >= a.maxDbMatches) {
-                if (acc >= 2ull * a.maxDbMatches - 1ull && !(a.debugSkip & 4)) S.fail |= 2u;      // at least two overflows for sure
-                else {
-                    const unsigned long long x = a.maxDbMatches - 1ull;     // the bucket holding hit x opens chunk 1
-                    int s = 0;
-                    while (S.sliceBase[s + 1] <= x) s++;
-                    S.boundSlice = (uint32_t)s;
-                    S.boundSeq = (uint32_t)(x - S.sliceBase[s]);            // turned into the bucket start below
-                    S.boundSearch = 1;
-                    S.selCount = 0;
-                }
-            }
+            S.nBound = 0;
+            S.boundSearch = (acc >= a.maxDbMatches) ? 1u : 0u;
+            S.selPrefix = 0ull;                                             // G of the current chunk
         }
         __syncthreads();
-        if (S.boundSearch && !S.fail) {
-            // largest bucket start (first-entry flag) <= boundSeq in slice boundSlice, over all bins
-            const uint32_t bs = S.boundSlice, bx = S.boundSeq;
-            uint32_t best = 0;
-            for (uint32_t bin = w; bin < nBins; bin += PF_WARPS) {
-                const uint32_t n = min(cntAll[bs * nBins + bin], a.regionCap);
-                const uint2 *reg = poolC + ((size_t)bs * nBins + bin) * a.regionCap;
-                for (uint32_t i = lane; i < n; i += 32) {
-                    const uint2 e = reg[i];
-                    if (((e.x >> 29) & 1u) && e.y <= bx) best = max(best, e.y);
-                }
+        while (S.boundSearch && !S.fail) {
+            if (tid == 0) {
+                const unsigned long long x = S.selPrefix + a.maxDbMatches - 1ull;
+                int s = 0;
+                while (S.sliceBase[s + 1] <= x) s++;
+                S.boundSlice[S.nBound] = (uint32_t)s;
+                S.boundSeq[S.nBound] = (uint32_t)(x - S.sliceBase[s]);      // turned into the bucket start below
+                S.selCount = 0;
             }
-            atomicMax(&S.selCount, best);
+            __syncthreads();
+            {   // largest bucket start (first-entry flag) <= that hit in its slice, over all bins
+                const uint32_t bs = S.boundSlice[S.nBound], bx = S.boundSeq[S.nBound];
+                uint32_t best = 0;
+                for (uint32_t bin = w; bin < nBins; bin += PF_WARPS) {
+                    const uint32_t n = min(cntAll[bs * nBins + bin], a.regionCap);
+                    const uint2 *reg = poolC + ((size_t)bs * nBins + bin) * a.regionCap;
+                    for (uint32_t i = lane; i < n; i += 32) {
+                        const uint2 e = reg[i];
+                        if (((e.x >> 29) & 1u) && e.y <= bx) best = max(best, e.y);
+                    }
+                }
+                for (int d = 16; d > 0; d >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, d));
+                if (lane == 0) atomicMax(&S.selCount, best);
+            }
             __syncthreads();
             if (tid == 0) {
-                S.boundSeq = S.selCount;
-                S.nBound = 1;
-                // a second overflow inside chunk 1?
-                const unsigned long long g = S.sliceBase[bs] + S.boundSeq;
-                if (S.sliceBase[PF_WARPS] - g >= a.maxDbMatches && !(a.debugSkip & 4)) S.fail |= 2u;
+                const uint32_t k = S.nBound;
+                S.boundSeq[k] = S.selCount;
+                S.selPrefix = S.sliceBase[S.boundSlice[k]] + S.selCount;
+                S.nBound = k + 1;
+                S.boundSearch = (S.sliceBase[PF_WARPS] - S.selPrefix >= a.maxDbMatches) ? 1u : 0u;
+                if (S.boundSearch && S.nBound >= PF_MAXBOUND) S.fail |= 2u;
             }
             __syncthreads();
         }
+        if (tid == 0 && S.nBound >= 2) {
+            // Arrival order of what survives the repeated merges (ties of the --max-seqs cut): every overflow from the second on
+            // REVERSES the merged list (mergeDiagonalKeepScoredHitsDuplicates walks backwards, CacheFriendlyOperations.cpp:132-142)
+            // before keepMax; the last chunk is appended in stream order.  blocks[] = origin chunks in final order.
+            const uint32_t k = S.nBound;                                    // overflows; chunks 0..k
+            uint32_t blk[PF_MAXBOUND + 1], dir[PF_MAXBOUND + 1], nb = 1;
+            blk[0] = 0; dir[0] = 1;                                         // F_1 = chunk 0, stream order
+            for (uint32_t j = 2; j <= k; j++) {                             // F_j = reversed(F_{j-1} ++ chunk j-1)
+                uint32_t nblk[PF_MAXBOUND + 1], ndir[PF_MAXBOUND + 1];
+                nblk[0] = j - 1; ndir[0] = 0;
+                for (uint32_t i = 0; i < nb; i++) { nblk[1 + i] = blk[nb - 1 - i]; ndir[1 + i] = dir[nb - 1 - i] ^ 1u; }
+                nb++;
+                for (uint32_t i = 0; i < nb; i++) { blk[i] = nblk[i]; dir[i] = ndir[i]; }
+            }
+            for (uint32_t i = 0; i < nb; i++) { S.blockRank[blk[i]] = i; S.blockDir[blk[i]] = dir[i]; }
+            S.blockRank[k] = nb; S.blockDir[k] = 1;
+        }
+        __syncthreads();
 
         const long long clk1 = clock64();
         // ---------------- P2-P4: per warp, bin by bin
         if (!S.fail) {
-            const uint32_t nBound = S.nBound, boundSlice = S.boundSlice, boundSeq = S.boundSeq;
+            const uint32_t nBound = S.nBound;
+            const bool multi = nBound >= 2;            // repeated overflow: chunk-local lists, folded per target below
+            uint32_t *sortIdxW = a.sortIdx + ((size_t)blockIdx.x * PF_WARPS + w) * a.candCap;
             bool overflow = false;
             unsigned long long stCands = 0;
             for (uint32_t bin = w; bin < nBins; bin += PF_WARPS) {
@@ -670,7 +844,7 @@ __global__ void __launch_bounds__(PF_THREADS, 3) prefilterKernel(PrefilterArgs a
                 __syncwarp();
                 uint32_t nC = 0;
                 // ---- P2: double-hit rule in stream order (CacheFriendlyOperations::findDuplicates restated per target)
-                auto rule = [&](const uint2 *reg, const uint32_t s, const uint32_t lo, const uint32_t hi) {
+                auto rule = [&](const uint2 *reg, const uint32_t s, const uint32_t lo, const uint32_t hi, const uint32_t chunk) {
                     uint2 nxt = make_uint2(0u, 0u);
                     if (lo + lane < hi) nxt = reg[lo + lane];
                     for (uint32_t e0 = lo; e0 < hi; e0 += 32) {
@@ -706,7 +880,7 @@ __global__ void __launch_bounds__(PF_THREADS, 3) prefilterKernel(PrefilterArgs a
                         if (isCand) {
                             const uint32_t pos = nC + __popc(candBallot & ltMask);
                             if (pos < a.candCap) {
-                                candW[pos] = ((uint64_t)(binBase + tl) << 32) | ((uint64_t)diag16 << 16);
+                                candW[pos] = ((uint64_t)(binBase + tl) << 32) | ((uint64_t)diag16 << 16) | chunk;
                                 candSeqW[pos] = (s << PF_SEQBITS) | ey;
                             }
                         }
@@ -714,35 +888,39 @@ __global__ void __launch_bounds__(PF_THREADS, 3) prefilterKernel(PrefilterArgs a
                         __syncwarp();
                     }
                 };
-                bool resetPending = nBound != 0;
+                uint32_t chunk = 0;                                     // chunk of the entries that come next
                 for (uint32_t s = 0; s < PF_WARPS; s++) {
                     const uint32_t n = cntAll[s * nBins + bin];
                     const uint2 *reg = poolC + ((size_t)s * nBins + bin) * a.regionCap;
-                    uint32_t split = n;
-                    const bool resetHere = resetPending && s >= boundSlice;
-                    if (resetHere) {
-                        split = 0;
-                        if (s == boundSlice) {
-                            // entries are ordered by running number: count those before the boundary
-                            uint32_t c = 0;
-                            for (uint32_t i = lane; i < n; i += 32) c += (reg[i].y < boundSeq) ? 1u : 0u;
-                            for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-                            split = c;
+                    uint32_t lo = 0;
+                    for (;;) {
+                        uint32_t hi = n;
+                        const bool boundaryHere = chunk < nBound && S.boundSlice[chunk] <= s;
+                        if (boundaryHere) {
+                            hi = lo;
+                            if (S.boundSlice[chunk] == s) {
+                                // entries are ordered by running number: count those before the boundary
+                                const uint32_t bseq = S.boundSeq[chunk];
+                                uint32_t c = 0;
+                                for (uint32_t i = lane; i < n; i += 32) c += (reg[i].y < bseq) ? 1u : 0u;
+                                for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+                                hi = max(c, lo);
+                            }
                         }
-                        resetPending = false;
-                    }
-                    for (int part = 0; part < 2; part++) {
-                        if (part == 1 && resetHere) {
-                            // chunk 1 starts: the reference runs findDuplicates on a cleared table; the collapse state (last
-                            // emitted diagonal) lives on through mergeDiagonalDuplicates
-                            for (uint32_t i = lane; i < a.binSize; i += 32) tab16[i] &= 0xff00u;
-                            __syncwarp();
-                        }
-                        rule(reg, s, part ? split : 0u, part ? n : split);
+                        rule(reg, s, lo, hi, multi ? chunk : 0u);
+                        lo = hi;
+                        if (!boundaryHere) break;
+                        // the next chunk starts: the reference runs findDuplicates on a cleared table.  One overflow: the collapse
+                        // state (last emitted diagonal) lives on through mergeDiagonalDuplicates, only the last-diagonal bytes
+                        // restart.  Repeated overflow: chunk-local lists, everything restarts.
+                        if (multi) { for (uint32_t i = lane; i < tabWords; i += 32) tab32[i] = 0u; }
+                        else { for (uint32_t i = lane; i < a.binSize; i += 32) tab16[i] &= 0xff00u; }
+                        __syncwarp();
+                        chunk++;
                     }
                 }
                 if (nC > a.candCap) { overflow = true; nC = a.candCap; }
-                stCands += (lane == 0) ? nC : 0;
+                if (!multi) stCands += (lane == 0) ? nC : 0;
                 __syncwarp();
                 // ---- P3: diagonal scores, one candidate per lane, capped at 255 (UngappedAlignment::align)
                 for (uint32_t c0 = 0; c0 < nC; c0 += 32) {
@@ -751,12 +929,19 @@ __global__ void __launch_bounds__(PF_THREADS, 3) prefilterKernel(PrefilterArgs a
                         const uint64_t v = candW[c];
                         const uint32_t ct = (uint32_t)(v >> 32);
                         const int cd = (int)(int16_t)(uint16_t)(v >> 16);
-                        const int sc = useProf ? diagonalScoreProf(a.tRes, a.tOff, S.u.prof, Lq, ct, cd, stDiagRes)
-                                               : diagonalScoreSlow(a.tRes, a.tOff, S.u.prof, S.sub32, qp, 0, 1, Lq, ct, cd, &stDiagRes);
+                        unsigned long long resHere = 0;
+                        const int sc = useProf ? diagonalScoreProf(a.tRes, a.tOff, S.u.prof, Lq, ct, cd, resHere)
+                                               : diagonalScoreSlow(a.tRes, a.tOff, S.u.prof, S.sub32, qp, 0, 1, Lq, ct, cd, &resHere);
+                        if (!multi) stDiagRes += resHere;     // repeated overflow: the fold below counts what the reference scores
                         candW[c] = v | ((uint64_t)min(sc, 255) << 8);
                     }
                 }
                 __syncwarp();
+                if (multi) {
+                    prefilterMergeChunks(candW, candSeqW, nC, sortIdxW, tab32, tabWords, binBase, a.binSize, nBound, S.blockRank, S.blockDir,
+                                         a.tOff, Lq, keepC, a.keepCap, &S.nKeep, S.hist, &stCands, &stDiagRes);
+                    continue;
+                }
                 // ---- P4: keepMaxScoreElementOnly: first candidate (stream order) carrying the target's maximum
                 for (uint32_t lo = 0; lo < a.binSize; lo += tabWords) {
                     for (uint32_t i = lane; i < tabWords; i += 32) tab32[i] = 0u;
@@ -857,7 +1042,7 @@ __global__ void __launch_bounds__(PF_THREADS, 3) prefilterKernel(PrefilterArgs a
                     const uint32_t newScore = full - 255u;
                     const float sc = (float)min(newScore, 65535u);
                     const float scaled = __fmul_rn(__fdiv_rn(sc, fltMaxSelf), 255.0f);
-                    v.w = (uint32_t)(int)__dadd_rn((double)scaled, 0.5) & 0xffu;
+                    v.w = (v.w & 0xff00u) | ((uint32_t)(int)__dadd_rn((double)scaled, 0.5) & 0xffu);
                     keepC[i] = v;
                 }
             }
@@ -893,7 +1078,8 @@ __global__ void __launch_bounds__(PF_THREADS, 3) prefilterKernel(PrefilterArgs a
         const uint32_t nAt = S.nAt;
         unsigned long long selLimit = ~0ull;             // keys <= selLimit are taken
         auto keyOf = [&](const uint4 &v) -> unsigned long long {
-            return ((unsigned long long)(255u - (needRescale ? v.w : 255u)) << 40) | ((unsigned long long)(v.x & a.binMask) << 32) | v.z;
+            return ((unsigned long long)(255u - (needRescale ? (v.w & 0xffu) : 255u)) << 47) | ((unsigned long long)(v.x & a.binMask) << 36) |
+                   ((unsigned long long)((v.w >> 8) & 0xfu) << 32) | v.z;
         };
         if (nAt > room) {
             clkSel = clock64();
@@ -902,7 +1088,7 @@ __global__ void __launch_bounds__(PF_THREADS, 3) prefilterKernel(PrefilterArgs a
             else {
                 if (tid == 0) { S.selPrefix = 0ull; S.selNeed = room; }
                 __syncthreads();
-                for (int bit = needRescale ? 47 : 43; bit >= 0; bit--) {
+                for (int bit = needRescale ? 54 : 46; bit >= 0; bit--) {
                     if (tid == 0) S.selCount = 0;
                     __syncthreads();
                     const unsigned long long prefix = S.selPrefix;
@@ -938,7 +1124,7 @@ __global__ void __launch_bounds__(PF_THREADS, 3) prefilterKernel(PrefilterArgs a
                 const uint32_t pos = atomicAdd(&S.nRes, 1u);
                 if (pos < a.maxHits) {
                     resT[pos] = v.x;
-                    resScore[pos] = needRescale ? (int)(255u + (v.w * (uint32_t)maxSelf) / 255u) : (int)(v.y >> 16);
+                    resScore[pos] = needRescale ? (int)(255u + ((v.w & 0xffu) * (uint32_t)maxSelf) / 255u) : (int)(v.y >> 16);
                     resAux[pos] = v.y & 0xffffu;
                 }
             }
@@ -1010,6 +1196,7 @@ __global__ void __launch_bounds__(PF_THREADS, 3) prefilterKernel(PrefilterArgs a
                 atomicAdd(&a.stats[ST_CANDS], S.stat[ST_CANDS]);
                 if (eligible + first > nRes) atomicAdd(&a.stats[ST_TRUNC], 1ull);
                 if (S.nBound) atomicAdd(&a.stats[ST_CHUNKED], 1ull);
+                if (S.nBound >= 2) atomicAdd(&a.stats[ST_MULTICHUNKED], 1ull);
                 const long long clk3 = clock64();
                 atomicAdd(&a.stats[ST_CYC_P1], (unsigned long long)(clk1 - clk0));
                 atomicAdd(&a.stats[ST_CYC_P24], (unsigned long long)(clk2 - clk1));

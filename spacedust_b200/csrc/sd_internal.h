@@ -81,7 +81,7 @@ struct DevBuf {
 };
 
 enum ScratchSlot {
-    SL_PF_TABLE = 0, SL_PF_CAND, SL_PF_KEEP, SL_PF_REST, SL_PF_RESS, SL_PF_RESD, SL_PF_OUT, SL_PF_DENSE, SL_PF_CSEQ, SL_PF_QPACK, SL_PF_POSINFO, SL_PF_POSPREFIX,
+    SL_PF_TABLE = 0, SL_PF_CAND, SL_PF_KEEP, SL_PF_REST, SL_PF_RESS, SL_PF_RESD, SL_PF_OUT, SL_PF_DENSE, SL_PF_CSEQ, SL_PF_QPACK, SL_PF_POSINFO, SL_PF_POSPREFIX, SL_PF_SORTIDX,
     SL_AL_FWD, SL_AL_WORD, SL_AL_BIG, SL_AL_REV, SL_AL_RES, SL_AL_HITS, SL_AL_TB, SL_AL_TBRES, SL_AL_IDENT, SL_AL_ORDER,
     SL_AL_PROFF, SL_AL_PROFR, SL_AL_PROFS, SL_AL_BOUND, SL_AL_PAIRQ, SL_AL_PAIRT,
     SL_TB_DIR, SL_TB_ROWS, SL_TB_REV, SL_TB_POOL, SL_SW_KEYA, SL_SW_KEYB, SL_SW_VALA, SL_SW_VALB, SL_SW_ORDER, SL_SW_TMP, SL_COUNT

@@ -1,4 +1,5 @@
 """GPU parity: CUDA prefilter (through the C ABI) vs the scalar oracle on the same seeded inputs."""
+import os
 import subprocess
 
 import numpy as np
@@ -11,8 +12,23 @@ from spacedust_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["stream", "binned"], autouse=True)
+def kernel_variant(request, monkeypatch):
+    """Both prefilter kernels must give the reference's result: the streaming kernel (small target sets; it hands queries that
+    reach the reference's hit-buffer limit to the binned kernel) and the binned kernel (SD_PF_STREAM_MAX=0 forces it)."""
+    if request.param == "binned":
+        monkeypatch.setenv("SD_PF_STREAM_MAX", "0")
+    else:
+        monkeypatch.delenv("SD_PF_STREAM_MAX", raising=False)
+    return request.param
+
+
 def _compare(gpu_ctx, tbuf, toff, qbuf, qoff, same_db, **kw):
     op = helpers.default_pref_params(sameDB=1 if same_db else 0, **kw)
+    if op.maxDbMatches:
+        os.environ["SD_PF_MAXDBMATCHES"] = str(op.maxDbMatches)       # test hook of the library, same knob as the oracle's
+    else:
+        os.environ.pop("SD_PF_MAXDBMATCHES", None)
     ohits, ost, omask = helpers.orc_prefilter(tbuf, toff, qbuf, qoff, op, want_masked=True)
     gp = sd.default_prefilter_params(same_db=1 if same_db else 0, bin_size=op.binSize, max_seqs=op.maxSeqs,
                                      min_ungapped_score=op.minDiagScore, cov_thr=op.covThr, cov_mode=op.covMode,
@@ -24,6 +40,7 @@ def _compare(gpu_ctx, tbuf, toff, qbuf, qoff, same_db, **kw):
         ghits, gst = sd.prefilter(gpu_ctx, idx, qbuf, qoff, gp)
     finally:
         idx.close()
+        os.environ.pop("SD_PF_MAXDBMATCHES", None)
     for k_o, k_g in (("probes", "probes"), ("matches", "matches"), ("candidates", "candidates"),
                      ("diagResidues", "diag_residues"), ("hits", "hits"), ("truncated", "truncated")):
         assert ost[k_o] == gst[k_g], "counter %s: oracle %d gpu %d" % (k_o, ost[k_o], gst[k_g])
@@ -68,10 +85,38 @@ def test_prefilter_truncation_tie_order(gpu_ctx):
     _compare(gpu_ctx, buf, off, buf, off, True, maxSeqs=12, minDiagScore=0, binSize=8)
 
 
+def test_prefilter_hit_buffer_overflow(gpu_ctx, synth_small):
+    """The reference buffers at most maxDbMatches index entries per query (QueryMatcher.cpp:43,280-333); beyond that the
+    double-hit table restarts and the candidate lists are merged, from the second overflow on through the reversed merge +
+    intermediate keepMax (:296-303).  The oracle restates that path (pinned on the reference binary by tests/test_oracle_cpu.py
+    with queries of > 2*10^6 and > 4*10^6 entries); here the limit is lowered in both (test hook) and the GPU path must follow,
+    hits and counters: once with single overflows only, once with up to a dozen overflows per query."""
+    buf, off, _ = synth.pack(synth_small)
+    single = multi = None
+    for limit in (3000, 2000, 1500, 1000, 700, 500, 350, 250, 150, 100, 60):
+        _, st = helpers.orc_prefilter(buf, off, buf, off, helpers.default_pref_params(maxDbMatches=limit))
+        if single is None and st["overflowQueries"] >= 10 and st["multiOverflowQueries"] == 0:
+            single = limit
+        if st["multiOverflowQueries"] >= 30:
+            multi = limit
+            break
+    assert single is not None and multi is not None, (single, multi)
+    _compare(gpu_ctx, buf, off, buf, off, True, maxDbMatches=single)
+    st = _compare(gpu_ctx, buf, off, buf, off, True, maxDbMatches=multi)
+    assert st["multiOverflowQueries"] >= 30
+    st = _compare(gpu_ctx, buf, off, buf, off, True, maxDbMatches=150)
+    assert st["multiOverflowQueries"] >= 200
+    # tie order of the --max-seqs cut after repeated overflows (reversed blocks), other radix
+    fbuf, foff = _weak_family_set()
+    _compare(gpu_ctx, fbuf, foff, fbuf, foff, True, maxSeqs=16, maxDbMatches=1500)
+    _compare(gpu_ctx, fbuf, foff, fbuf, foff, True, maxSeqs=16, binSize=4, maxDbMatches=700)
+
+
 def test_prefilter_candidate_overflow_second_pass(gpu_ctx, synth_small, monkeypatch):
     """Queries whose double-hit candidate list exceeds the first-pass capacity are re-run by a second launch with a
     larger list: hits AND the P/M/R/H counters must still equal the oracle's (SD_PF_CANDCAP forces the situation)."""
     monkeypatch.setenv("SD_PF_CANDCAP", "32")
+    monkeypatch.setenv("SD_PF_REGIONCAP", "64")
     buf, off, _ = synth.pack(synth_small)
     st = _compare(gpu_ctx, buf, off, buf, off, True)
     assert st["candidates"] > 32 * 10
