@@ -2,8 +2,10 @@
 """bench.py -- `spacedust clustersearch --search-mode 0` hot path on B200 vs the reference's AVX2 CPU path.
 
 Metric (BASELINE.json): query-genes/s of the clustersearch hot path (prefilter -> align -> besthitbyset/combinehits ->
-clusterhits) on synthetic proteomes.  Workload at N=1 is BASELINE config[1]: 20 synthetic 3k-gene prokaryote
-proteomes all-vs-all (60 000 query genes, 19.5 M residues), generator spacedust_b200/synth.py, seed 20261017.
+clusterhits) on synthetic proteomes.  Workload at N=1 (default, --workload c2) is BASELINE config[1]: 20 synthetic 3k-gene
+prokaryote proteomes all-vs-all (60 000 query genes, 19.5 M residues), generator spacedust_b200/synth.py, seed 20261017.
+--workload c3 = BASELINE config[2] (200 x 4000), --workload c5 = config[4] (500 x 4000, --max-gene-gap 10 --cluster-size 5);
+--proteomes / --genes give any other size (labelled "custom").
 
 One step = one pass of the hot path over the whole query batch.
   value  : target DB + k-mer index and the query batch already resident in HBM when the timed region starts
@@ -15,8 +17,9 @@ per-rank result lists (alignments, backtraces, clusters) per step so that every 
 result; total work fixed => "strong".
 
 `--impl reference` times the unmodified reference binary (oracle/_ref/spacedust, built by oracle/build_ref.py)
-on the host cores on a bounded sample of the same workload (S query proteomes against the same 20-proteome
-target setDB).
+on the host cores on a bounded sample of the same workload: S query proteomes against the full target setDB, S chosen so
+that the whole --steps/--warmup run stays within a few minutes (the line states S and an estimate for the full run, in which
+the reference's fixed start-up -- index table, extended 3-mer matrix -- is amortised over all queries instead of S proteomes).
 """
 import argparse
 import json
@@ -37,6 +40,12 @@ N_PROTEOMES = 20
 GENES = 3000
 SEED = 20261017
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "spacedust")
+# BASELINE.json configs that bench.py can run ("cluster": flags of clusterhits that differ from the defaults)
+WORKLOADS = {
+    "c2": {"proteomes": N_PROTEOMES, "genes": GENES, "cluster": {}, "label": "BASELINE config[1]"},
+    "c3": {"proteomes": 200, "genes": 4000, "cluster": {}, "label": "BASELINE config[2]"},
+    "c5": {"proteomes": 500, "genes": 4000, "cluster": {"max_gene_gap": 10, "cluster_size": 5}, "label": "BASELINE config[4]"},
+}
 
 
 def parse_args():
@@ -45,11 +54,19 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--proteomes", type=int, default=N_PROTEOMES)
-    ap.add_argument("--genes", type=int, default=GENES)
-    ap.add_argument("--ref-sample", type=int, default=2, help="query proteomes in the reference / cpu_baseline sample")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="BASELINE.json config (default c2 = config[1])")
+    ap.add_argument("--proteomes", type=int, default=0, help="override the workload's proteome count")
+    ap.add_argument("--genes", type=int, default=0, help="override the workload's genes per proteome")
+    ap.add_argument("--ref-sample", type=int, default=0,
+                    help="query proteomes in the reference / cpu_baseline sample (0: as many as fit the time budget)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    args.custom = bool(args.proteomes or args.genes)
+    args.proteomes = args.proteomes or w["proteomes"]
+    args.genes = args.genes or w["genes"]
+    args.cluster_flags = dict(w["cluster"])
+    return args
 
 
 def peaks():
@@ -137,42 +154,121 @@ def parse_stage_times(log):
     return stages
 
 
+def pick_ref_sample(args, runs, budget_s):
+    """Query proteomes per reference run such that `runs` runs stay within budget_s.  Cost model from the reference's own stage
+    times on this pool's hosts (16 cores): ~1.5 s fixed start-up (index table + 3-mer matrix) and ~0.75 ms per query gene and
+    per 60 k target genes; scaled by the core count."""
+    if args.ref_sample > 0:
+        return min(args.ref_sample, args.proteomes)
+    cores = os.cpu_count() or 1
+    per_proteome = 0.75e-3 * args.genes * (args.proteomes * args.genes / 60000.0) * (16.0 / cores)
+    fixed = 1.5 * (args.proteomes * args.genes / 60000.0)
+    s = int((budget_s / max(runs, 1) - fixed) / max(per_proteome, 1e-9))
+    return max(1, min(args.proteomes, max(s, 2 if args.proteomes >= 2 else 1)))
+
+
 class ReferenceRunner:
     """createsetdb once (excluded from the timing), then clustersearch per step."""
 
-    def __init__(self, proteomes, n_query_sets):
+    def __init__(self, args, proteomes, n_query_sets):
         from spacedust_b200 import synth
         if not (os.path.exists(REF_BIN) and os.access(REF_BIN, os.X_OK)):
             raise RuntimeError("oracle/_ref/spacedust is missing: run `python oracle/build_ref.py` in the build container")
         self.dir = tempfile.mkdtemp(prefix="sdbench_ref_")
         self.threads = os.cpu_count() or 1
         self.env = dict(os.environ, MMSEQS_FORCE_MERGE="1")
+        self.flags = []
+        for k, v in args.cluster_flags.items():
+            self.flags += ["--" + k.replace("_", "-"), str(v)]
+        self.keep = False
         paths = synth.write_fasta(proteomes, os.path.join(self.dir, "faa"))
-        self._run(["createsetdb"] + paths + [os.path.join(self.dir, "tDB"), os.path.join(self.dir, "tmp_t"), "-v", "1"])
-        self._run(["createsetdb"] + paths[:n_query_sets] + [os.path.join(self.dir, "qDB"), os.path.join(self.dir, "tmp_q"), "-v", "1"])
         self.n_queries = sum(len(p["seqs"]) for p in proteomes[:n_query_sets])
+        n_targets = sum(len(p["seqs"]) for p in proteomes)
+        for attempt in range(2):      # createsetdb runs awk/sort/join children: validate what they wrote, rebuild once if not
+            for db in ("tDB", "qDB"):
+                for f in os.listdir(self.dir):
+                    if f.startswith(db):
+                        os.remove(os.path.join(self.dir, f))
+            self._run(["createsetdb"] + paths + [os.path.join(self.dir, "tDB"), os.path.join(self.dir, "tmp_t%d" % attempt), "-v", "1"])
+            self._run(["createsetdb"] + paths[:n_query_sets] + [os.path.join(self.dir, "qDB"), os.path.join(self.dir, "tmp_q%d" % attempt), "-v", "1"])
+            bad = self._check_lookup("qDB", self.n_queries) or self._check_lookup("tDB", n_targets)
+            if not bad:
+                break
+            sys.stderr.write("[bench] reference createsetdb wrote an invalid lookup (%s), attempt %d\n" % (bad, attempt + 1))
+            if attempt == 1:
+                self.keep = True
+                raise RuntimeError("reference createsetdb: %s (files kept in %s)" % (bad, self.dir))
         self.step_no = 0
+
+    def _check_lookup(self, db, n_expected):
+        """<db>.lookup: key \t accession_geneIdx_start_end \t set; clusterhits parses the last three '_' fields
+        (src/util/ClusterHits.cpp:328-350) and dies with "Invalid query lookup record" otherwise."""
+        n = 0
+        try:
+            for line in open(os.path.join(self.dir, db + ".lookup")):
+                f = line.rstrip("\n").split("\t")
+                parts = f[1].split("_") if len(f) == 3 else []
+                if len(parts) < 4 or not (parts[-1].isdigit() and parts[-2].isdigit() and parts[-3].isdigit()):
+                    return "%s.lookup line %d: %r" % (db, n + 1, line[:80])
+                n += 1
+        except OSError as e:
+            return "%s.lookup: %s" % (db, e)
+        return None if n == n_expected else "%s.lookup has %d records, expected %d" % (db, n, n_expected)
 
     def _run(self, args):
         r = subprocess.run([REF_BIN] + args, env=self.env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
         if r.returncode != 0:
-            raise RuntimeError("reference failed: %s\n%s" % (" ".join(args[:3]), r.stdout.decode()[-1500:]))
-        return r.stdout.decode()
+            raise RuntimeError("reference failed (rc %d): %s\n%s" % (r.returncode, " ".join(args[:3]), r.stdout.decode(errors="replace")[-1500:]))
+        return r.stdout.decode(errors="replace")
 
     def step(self):
-        self.step_no += 1
-        tmp = os.path.join(self.dir, "tmp_cs%d" % self.step_no)
-        out = os.path.join(self.dir, "out%d.tsv" % self.step_no)
-        t0 = time.perf_counter()
-        log = self._run(["clustersearch", os.path.join(self.dir, "qDB"), os.path.join(self.dir, "tDB"), out, tmp,
-                         "--filter-self-match", "1", "--threads", str(self.threads), "-v", "3"])
-        dt = time.perf_counter() - t0
-        n_clusters = sum(1 for l in open(out) if l.startswith("#"))
-        shutil.rmtree(tmp, ignore_errors=True)
-        return dt, parse_stage_times(log), n_clusters
+        """One clustersearch run; a failed run is repeated once (the reference's clusterhits has died sporadically on these hosts),
+        the failing tmp dir and the lookup files are kept for inspection."""
+        last = None
+        for attempt in range(2):
+            self.step_no += 1
+            tmp = os.path.join(self.dir, "tmp_cs%d" % self.step_no)
+            out = os.path.join(self.dir, "out%d.tsv" % self.step_no)
+            t0 = time.perf_counter()
+            try:
+                log = self._run(["clustersearch", os.path.join(self.dir, "qDB"), os.path.join(self.dir, "tDB"), out, tmp,
+                                 "--filter-self-match", "1", "--threads", str(self.threads), "-v", "3"] + self.flags)
+            except RuntimeError as e:
+                last = e
+                self.keep = True
+                keep_dir = os.path.join(ROOT, "gpurun_out") if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else self.dir
+                try:
+                    with open(os.path.join(keep_dir, "ref_failure_step%d.log" % self.step_no), "w") as f:
+                        f.write(str(e))
+                    for db in ("qDB", "tDB"):
+                        shutil.copy(os.path.join(self.dir, db + ".lookup"), os.path.join(keep_dir, "ref_failure_%s.lookup" % db))
+                except OSError:
+                    pass
+                sys.stderr.write("[bench] reference clustersearch failed (attempt %d), evidence in %s and %s: %s\n"
+                                 % (attempt + 1, keep_dir, tmp, str(e)[:300]))
+                continue
+            dt = time.perf_counter() - t0
+            self.last_tsv = out
+            n_clusters = sum(1 for l in open(out) if l.startswith("#"))
+            shutil.rmtree(tmp, ignore_errors=True)
+            return dt, parse_stage_times(log), n_clusters
+        raise last
 
     def close(self):
-        shutil.rmtree(self.dir, ignore_errors=True)
+        if not self.keep:
+            shutil.rmtree(self.dir, ignore_errors=True)
+
+
+def full_run_estimate(args, n_sample_queries, dt, stages):
+    """The sample runs S query proteomes against the whole target setDB, so the reference's start-up that does not depend on the
+    number of queries (index table init, and the extended 3-mer matrix inside the prefilter) is amortised over S instead of all
+    proteomes.  Estimate for the full run: fixed part once + the per-query part scaled up."""
+    fixed = stages.get("index_table_init", 0.0) + 0.6      # 0.6 s: 3-mer matrix + DB open, measured on these hosts
+    fixed = min(fixed, 0.8 * dt)
+    n_all = args.proteomes * args.genes
+    t_full = fixed + (dt - fixed) * n_all / max(n_sample_queries, 1)
+    return {"query_genes_per_s": n_all / t_full, "seconds": t_full, "fixed_seconds_in_sample": fixed,
+            "note": "extrapolated from the sample; the sample's own value overstates the GPU/CPU ratio by value_full/value_sample"}
 
 
 def cpu_model():
@@ -188,7 +284,8 @@ def cpu_model():
 def run_reference(args, proteomes, rank, world):
     if rank != 0:
         return
-    runner = ReferenceRunner(proteomes, args.ref_sample)
+    n_sets = pick_ref_sample(args, args.steps + args.warmup, 200.0)
+    runner = ReferenceRunner(args, proteomes, n_sets)
     try:
         for _ in range(args.warmup):
             runner.step()
@@ -199,14 +296,16 @@ def run_reference(args, proteomes, rank, world):
         total = sum(times)
         value = runner.n_queries * args.steps / total
         sample = ("%d of %d query proteomes (%d query genes) against the full %d-proteome target setDB, "
-                  "clustersearch --filter-self-match 1 --threads %d; createsetdb excluded"
-                  % (args.ref_sample, args.proteomes, runner.n_queries, args.proteomes, runner.threads))
+                  "clustersearch --filter-self-match 1 --threads %d%s; createsetdb excluded"
+                  % (n_sets, args.proteomes, runner.n_queries, args.proteomes, runner.threads,
+                     "".join(" " + f for f in runner.flags)))
         line = {"impl": "reference", "metric": "clustersearch query-genes/s", "value": value, "unit": "query-genes/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32/f64", "data": "synthetic",
                 "config": workload_config(args),
                 "cpu_baseline": {"value": value, "unit": "query-genes/s", "cores": runner.threads, "kind": "reference",
-                                 "sample": sample, "cpu": cpu_model(), "stage_seconds": stages},
+                                 "sample": sample, "cpu": cpu_model(), "stage_seconds": stages,
+                                 "full_run_estimate": full_run_estimate(args, runner.n_queries, total / args.steps, stages)},
                 "e2e": {"value": value, "unit": "query-genes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line), flush=True)
@@ -215,11 +314,13 @@ def run_reference(args, proteomes, rank, world):
 
 
 def workload_config(args):
-    return {"workload": "%d synthetic %d-gene prokaryote proteomes all-vs-all (BASELINE config[1]), seed %d, "
-                        "clustersearch --search-mode 0 --filter-self-match 1, defaults -s 5.7 --max-seqs 300 -e 10 -c 0.8 --cov-mode 2"
-                        % (args.proteomes, args.genes, SEED),
+    label = "custom size" if args.custom else WORKLOADS[args.workload]["label"]
+    extra = "".join(" --%s %s" % (k.replace("_", "-"), v) for k, v in args.cluster_flags.items())
+    return {"workload": "%d synthetic %d-gene prokaryote proteomes all-vs-all (%s), seed %d, "
+                        "clustersearch --search-mode 0 --filter-self-match 1%s, defaults -s 5.7 --max-seqs 300 -e 10 -c 0.8 --cov-mode 2"
+                        % (args.proteomes, args.genes, label, SEED, extra),
             "query_genes": args.proteomes * args.genes, "proteomes": args.proteomes, "genes_per_proteome": args.genes,
-            "l2": "inputs larger than L2 (k-mer index + neighbour tables + per-warp state > 1 GB vs 126 MB L2)"}
+            "l2": "inputs larger than L2 (k-mer index + neighbour tables + per-query scratch > 1 GB vs 126 MB L2)"}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -260,7 +361,7 @@ def run_ours(args, proteomes, rank, world, local_rank):
     ctx = sd.Context(local_rank)
     pp = sd.default_prefilter_params(same_db=1)
     ap = sd.default_align_params(same_db=1)
-    cp = sd.default_cluster_params(filter_self_match=1)
+    cp = sd.default_cluster_params(filter_self_match=1, **args.cluster_flags)
 
     def barrier():
         torch.cuda.synchronize()
@@ -384,8 +485,11 @@ def run_ours(args, proteomes, rank, world, local_rank):
                                         "R_diag_residues": int(pst["diag_residues"]), "Lq_residues": int(pst["query_residues"]),
                                         "H_hits": int(pst["hits"]), "diag_candidates": int(pst["candidates"])}},
                 "sw": {"gcups": cells / 1e9 / (ast["sw_ms"] / 1e3) if ast["sw_ms"] > 0 else 0.0, "cells": int(cells),
-                       "kernel_ms": ast["sw_ms"], "pairs": int(ast["alignments"]), "hbm_gbs_algorithmic":
-                       (int(ast["alignments"]) * 380.0) / 1e9 / (ast["sw_ms"] / 1e3) if ast["sw_ms"] > 0 else 0.0},
+                       "kernel_ms": ast["sw_ms"], "pairs": int(ast["alignments"]),
+                       "algorithmic_bytes": int(ast["target_residues"]) + 64 * int(ast["alignments"]),
+                       "hbm_gbs_algorithmic": (int(ast["target_residues"]) + 64.0 * int(ast["alignments"])) / 1e9 / (ast["sw_ms"] / 1e3)
+                       if ast["sw_ms"] > 0 else 0.0,
+                       "bytes_formula": "sum over aligned pairs of (L_t + 64) (SURVEY.md 8d); the pass is integer-issue bound, not HBM bound"},
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
                 "results": {"aligned_pairs": int(counts[0]), "alignments": int(counts[1]), "clusters": int(counts[2]),
                             "query_genes": int(counts[3])},
@@ -408,14 +512,16 @@ def run_ours(args, proteomes, rank, world, local_rank):
 
 
 def cpu_baseline(args, proteomes):
-    """oracle/_ref (the unmodified reference, AVX2) on this box's host cores, one bounded sample of the workload."""
-    runner = ReferenceRunner(proteomes, args.ref_sample)
+    """oracle/_ref (the unmodified reference, AVX2) on this box's host cores, one bounded sample of the workload (about 25 s)."""
+    n_sets = pick_ref_sample(args, 1, 25.0)
+    runner = ReferenceRunner(args, proteomes, n_sets)
     try:
         dt, stages, n_clu = runner.step()
         return {"value": runner.n_queries / dt, "unit": "query-genes/s", "cores": runner.threads, "kind": "reference",
                 "sample": "%d of %d query proteomes (%d query genes) against the full %d-proteome target setDB, one clustersearch run, "
-                          "%.1f s wall; createsetdb excluded" % (args.ref_sample, args.proteomes, runner.n_queries, args.proteomes, dt),
-                "cpu": cpu_model(), "stage_seconds": stages, "clusters_in_sample": n_clu}
+                          "%.1f s wall; createsetdb excluded" % (n_sets, args.proteomes, runner.n_queries, args.proteomes, dt),
+                "cpu": cpu_model(), "stage_seconds": stages, "clusters_in_sample": n_clu,
+                "full_run_estimate": full_run_estimate(args, runner.n_queries, dt, stages)}
     finally:
         runner.close()
 

@@ -156,6 +156,7 @@ typedef struct {
     double sw_ms;             /* device time of the score/coordinate kernels, CUDA events */
     double traceback_ms;
     double total_ms;
+    uint64_t target_residues; /* sum of target lengths over the aligned pairs (algorithmic bytes: L_t + 64 per pair) */
 } sd_align_stats;
 
 /* Body of the query loop of Alignment::run (lib/mmseqs/src/alignment/Alignment.cpp:312-511) for the

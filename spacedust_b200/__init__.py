@@ -169,7 +169,7 @@ class AlignStats(ctypes.Structure):
     _fields_ = [("alignments", ctypes.c_uint64), ("passed", ctypes.c_uint64), ("word_mode", ctypes.c_uint64),
                 ("reverse_passes", ctypes.c_uint64), ("tracebacks", ctypes.c_uint64), ("cells_forward", ctypes.c_uint64),
                 ("cells_reverse", ctypes.c_uint64), ("cells_traceback", ctypes.c_uint64), ("sw_ms", ctypes.c_double),
-                ("traceback_ms", ctypes.c_double), ("total_ms", ctypes.c_double)]
+                ("traceback_ms", ctypes.c_double), ("total_ms", ctypes.c_double), ("target_residues", ctypes.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -508,6 +508,18 @@ inline unsigned gridOf(uint64_t n, unsigned b) { return (unsigned)std::max<uint6
 
 // Device pair arrays in, accepted alignments out.  dPairQ/dPairT live on the device (grouped or not: the order of
 // the output is defined by (query, Matcher::compareHits)).
+// sum of target lengths over the (query, target) pairs of a call (reporting: algorithmic bytes of the score pass)
+static __global__ void sumPairTargetResidues(const uint32_t *__restrict__ pairT, uint64_t n, const uint32_t *__restrict__ tOff,
+                                             unsigned long long *__restrict__ out) {
+    unsigned long long s = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t t = pairT[i];
+        s += tOff[t + 1] - tOff[t];
+    }
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xffffffffu, s, d);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
 int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
                           const uint32_t *dPairQ, const uint32_t *dPairT, uint64_t n_pairs, uint64_t db_residues,
                           const sd_align_params *par, std::vector<sd_alignment> &acc, sd::CharPool &pool,
@@ -611,6 +623,10 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     SD_CUDA(cudaMemcpyAsync(dSub.p, sub16, sizeof sub16, cudaMemcpyHostToDevice, st));
     SD_CUDA(cudaMemcpyAsync(dPBack.p, alnMat.pBack, AA * sizeof(double), cudaMemcpyHostToDevice, st));
     SD_CUDA(cudaMemsetAsync(dCells.p, 0, 4 * sizeof(unsigned long long), st));
+    if (n_pairs) {      // algorithmic bytes of the score pass: sum of target lengths over the pairs (L_t + 64 per pair)
+        sumPairTargetResidues<<<(unsigned)std::min<uint64_t>((n_pairs + 255) / 256, 4096), 256, 0, st>>>(dPairT, n_pairs, idx->off.p, dCells.p + 3);
+        ctx->launches++;
+    }
     SD_CUDA(cudaMemsetAsync(dProfF.p, 0x80, profBytes, st));
     SD_CUDA(cudaMemsetAsync(dProfR.p, 0x80, profBytes, st));
     compositionBias<<<(nPos + 127) / 128, 128, 0, st>>>(queries->code.p, queries->off.p, nq, nPos, dSub.p, dPBack.p, par->comp_bias_corr, dBias.p);
@@ -950,7 +966,7 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
         cudaEventElapsedTime(&ms, ev0, ev1);
         stats->alignments = hCounters[0]; stats->passed = acc.size(); stats->word_mode = nWord;
         stats->reverse_passes = nRev; stats->tracebacks = nTb;
-        stats->cells_forward = hc[0]; stats->cells_reverse = hc[1]; stats->cells_traceback = hc[2];
+        stats->cells_forward = hc[0]; stats->cells_reverse = hc[1]; stats->cells_traceback = hc[2]; stats->target_residues = hc[3];
         stats->sw_ms = swMs; stats->traceback_ms = tbMs; stats->total_ms = ms;
     }
     cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evA); cudaEventDestroy(evB);

@@ -18,6 +18,7 @@
 // which gives the same merge sequence in O(K^2).  Transcendentals (Lanczos log-gamma, log(1 - m/k), log 2,
 // log q0) are tabulated on the host with the same libm the reference links, the device only adds and
 // multiplies doubles (compiled with --fmad=false), so scores compare bit-for-bit.
+#include <mutex>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -490,6 +491,10 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
         A.matchOff = dOff.p; A.order = dOrder.p; A.nMatches = nDev; A.qPos = dQ.p; A.tPos = dT.p; A.sameStrand = dS.p;
         A.nodes = dNodes.p; A.dmin = dDmin.p; A.val = dVal.p; A.root = dRoot.p; A.next = dNext.p; A.stats = dStats.p;
         const uint32_t nCta = std::min<uint32_t>(nDev, (uint32_t)ctx->smCount * 4u);
+        // fused clustersearch: two host threads share the GPU; take the turn so that the event pair brackets this kernel and not
+        // the other chunk's Smith-Waterman launches queued before it (the kernel is a few ms)
+        std::unique_lock<std::mutex> gpuTurn;
+        if (ctx->gpuToken) gpuTurn = std::unique_lock<std::mutex>(*ctx->gpuToken);
         SD_CUDA(cudaEventRecord(evA, st));
         clusterKernel<<<nCta, CL_THREADS, 0, st>>>(A);
         ctx->launches++;
@@ -498,6 +503,7 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
         SD_CUDA(cudaMemcpyAsync(hRoot.data(), dRoot.p, nH * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         SD_CUDA(cudaMemcpyAsync(hStat, dStats.p, sizeof hStat, cudaMemcpyDeviceToHost, st));
         SD_CUDA(cudaStreamSynchronize(st));
+        if (gpuTurn.owns_lock()) gpuTurn.unlock();
         float ms = 0;
         cudaEventElapsedTime(&ms, evA, evB);
         kernelMs = ms;

@@ -132,7 +132,7 @@ extern "C" int sd_clustersearch_run(sd_context *ctx, const sd_target_index *idx,
         if (ast) {
             ast->alignments += cr.ast.alignments; ast->passed += cr.ast.passed; ast->word_mode += cr.ast.word_mode;
             ast->reverse_passes += cr.ast.reverse_passes; ast->tracebacks += cr.ast.tracebacks;
-            ast->cells_forward += cr.ast.cells_forward; ast->cells_reverse += cr.ast.cells_reverse; ast->cells_traceback += cr.ast.cells_traceback;
+            ast->cells_forward += cr.ast.cells_forward; ast->cells_reverse += cr.ast.cells_reverse; ast->cells_traceback += cr.ast.cells_traceback; ast->target_residues += cr.ast.target_residues;
             ast->sw_ms += cr.ast.sw_ms; ast->traceback_ms += cr.ast.traceback_ms; ast->total_ms += cr.ast.total_ms;
         }
         if (cst) {
