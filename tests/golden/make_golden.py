@@ -97,10 +97,36 @@ def createsetdb_fixture(n_proteomes=2, genes=5, seed=3):
     print("createsetdb fixture: %d files" % len(files))
 
 
+def examples_fixture():
+    """The reference's own example (examples/NC_000913.faa + NC_000915.faa, BASELINE config[0]): gzipped copies of the two input
+    proteomes (public NCBI data, not reference source) and the reference's final TSV in canonical form (cluster numbers dropped,
+    lines sorted) -- tests/test_scale_gpu.py::test_c1_reference_example_through_frontend runs the same input through sdb200."""
+    import gzip
+    ex = os.path.join(HERE, "examples")
+    os.makedirs(ex, exist_ok=True)
+    d = tempfile.mkdtemp(prefix="sdgold_")
+    paths = []
+    for n in ("NC_000913.faa", "NC_000915.faa"):
+        src = os.path.join("/root/reference/examples", n)
+        with open(src, "rb") as f, gzip.GzipFile(os.path.join(ex, n + ".gz"), "wb", 9, mtime=0) as g:
+            shutil.copyfileobj(f, g)
+        paths.append(src)
+    db = os.path.join(d, "setDB")
+    helpers.run_ref(["createsetdb"] + paths + [db, os.path.join(d, "tmp"), "-v", "1"])
+    out = os.path.join(d, "res.tsv")
+    helpers.run_ref(["clustersearch", db, db, out, os.path.join(d, "tmpcs"), "--filter-self-match", "1", "--threads", "8", "-v", "1"])
+    lines = [l for l in open(out).read().split("\n") if l]
+    canon = sorted("\t".join(l.split("\t")[1:]) if l.startswith("#") else l for l in lines)
+    open(os.path.join(ex, "result_canonical.tsv"), "w").write("\n".join(canon) + "\n")
+    print("examples fixture: %d clusters, %d hit lines" % (sum(1 for l in lines if l.startswith("#")), sum(1 for l in lines if l.startswith(">"))))
+    shutil.rmtree(d, ignore_errors=True)
+
+
 if __name__ == "__main__":
     if not helpers.have_ref():
         sys.exit("oracle/_ref/spacedust missing: run python oracle/build_ref.py")
     prefilter_fixture()
     align_fixture()
     clustersearch_fixture()
+    examples_fixture()
     createsetdb_fixture()

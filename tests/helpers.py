@@ -349,6 +349,21 @@ def oracle_clustersearch(proteomes, filter_self_match=True, max_gene_gap=3, clus
     return {"alns": alns, "bt": bt, "result": result, "matches": matches, "clusters": clusters, "meta": meta, "lookup": lookup}
 
 
+def gpu_clusters(res):
+    """Result of sd.clustersearch / sd.clustersearch_staged -> [(header, [lines])] in the clusterhits convention (query and target
+    by key = index, P-values as printed), comparable through canonical_clusters()."""
+    import spacedust_b200 as sd
+    out = []
+    for c in res["clusters"]:
+        lines = []
+        for m in res["members"][int(c["first"]):int(c["first"]) + int(c["n"])]:
+            al = res["alns"][int(m["aln"])]
+            line = sd.format_alignment(al, al["target"], res["pool"]).decode().rstrip("\n").split("\t")
+            lines.append("\t".join([str(int(al["query"])), line[0], "%.3E" % m["pval"]] + line[2:]))
+        out.append(("%d\t%d\t%.3E\t%.3E\t%d" % (c["q_set"], c["t_set"], c["p_co"], c["p_mh"], c["n"]), lines))
+    return out
+
+
 def canonical_clusters(clusters):
     """[(header, [lines])] -> sorted list of (qSet, tSet, pCO, pMH, n, tuple(lines)) (cluster keys/order are not deterministic)."""
     out = []

@@ -35,12 +35,5 @@ def test_fused_equals_staged_and_oracle(gpu_ctx, synth_small, monkeypatch, chunk
         assert np.array_equal(a["members"][f], b["members"][f]), f
     # and against the oracle's whole pipeline (cluster membership + printed P-values)
     o = helpers.oracle_clustersearch(synth_small, filter_self_match=True)
-    mine = []
-    for c in b["clusters"]:
-        lines = []
-        for m in b["members"][int(c["first"]):int(c["first"]) + int(c["n"])]:
-            al = b["alns"][int(m["aln"])]
-            line = sd.format_alignment(al, al["target"], b["pool"]).decode().rstrip("\n").split("\t")
-            lines.append("\t".join([str(int(al["query"])), line[0], "%.3E" % m["pval"]] + line[2:]))
-        mine.append(("%d\t%d\t%.3E\t%.3E\t%d" % (c["q_set"], c["t_set"], c["p_co"], c["p_mh"], c["n"]), lines))
+    mine = helpers.gpu_clusters(b)
     assert helpers.canonical_clusters(mine) == helpers.canonical_clusters(o["clusters"])
