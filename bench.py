@@ -344,7 +344,7 @@ def run_ours(args, proteomes, rank, world, local_rank):
     n_total = len(off) - 1
     # this rank's query sets: contiguous block of proteomes, balanced by residues
     set_res = np.array([sum(len(s) for s in p["seqs"]) for p in proteomes])
-    s_lo, s_hi = shard.partition_sets(set_res, world)[rank]
+    s_lo, s_hi = sd.shard_partition(set_res, world)[rank]      # sd_shard_partition (C ABI)
     sel = np.arange(*shard.query_block(meta["set_of"], s_lo, s_hi))
     q_first = int(sel[0]) if len(sel) else 0
     q_lo, q_hi = (int(off[sel[0]]), int(off[sel[-1] + 1])) if len(sel) else (0, 0)
@@ -359,6 +359,11 @@ def run_ours(args, proteomes, rank, world, local_rank):
     tbuf_h, qbuf_h = t_pin.numpy(), q_pin.numpy()
 
     ctx = sd.Context(local_rank)
+    if world > 1:
+        # the library's own NCCL communicator (csrc/shard.cu); torch.distributed only carries the 128-byte id and the timing reductions
+        box = [sd.shard_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        sd.shard_init(ctx, rank, world, box[0])
     pp = sd.default_prefilter_params(same_db=1)
     ap = sd.default_align_params(same_db=1)
     cp = sd.default_cluster_params(filter_self_match=1, **args.cluster_flags)
@@ -375,11 +380,9 @@ def run_ours(args, proteomes, rank, world, local_rank):
 
     def step(index, queries):
         """One pass of the hot path over this rank's query block, results into pinned host memory; N>1: + the one
-        all_gather of the result lists (every rank ends with all ranks' parts in host memory)."""
-        r = sd.clustersearch(ctx, index, queries, q_meta, meta, pp, ap, cp, q_first, out=exch)
-        if world > 1:
-            r["parts"] = exch.exchange(q_first)
-        return r
+        ncclAllGather of the result lists inside the library (sd_shard_allgather_result: every rank ends with the whole job's
+        lists in host memory, global query indices, single-GPU order)."""
+        return sd.clustersearch(ctx, index, queries, q_meta, meta, pp, ap, cp, q_first, out=exch, gather=world > 1)
 
     # ---------------- resident arm
     idx = sd.TargetIndex(ctx, tbuf_h, off, pp)
@@ -444,12 +447,11 @@ def run_ours(args, proteomes, rank, world, local_rank):
 
     # max over ranks
     t_all = torch.tensor([dt, dt_e2e], dtype=torch.float64, device="cuda")
-    counts = torch.tensor([int(res["align_stats"]["alignments"]), len(res["alns"]), len(res["clusters"]), nq_local], dtype=torch.int64, device="cuda")
+    counts = torch.tensor([int(res["align_stats"]["alignments"]), 0, 0, nq_local], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
-        gathered = [torch.zeros_like(counts) for _ in range(world)]
-        dist.all_gather(gathered, counts)          # reporting only (outside the timed region)
-        counts = torch.stack(gathered).sum(0)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)          # reporting only (outside the timed region)
+    counts[1], counts[2] = len(res["alns"]), len(res["clusters"])      # after the gather every rank holds the whole job's lists
     dt, dt_e2e = float(t_all[0]), float(t_all[1])
     if rank == 0:
         pst, ast, cst = res["prefilter_stats"], res["align_stats"], res["cluster_stats"]
@@ -495,11 +497,12 @@ def run_ours(args, proteomes, rank, world, local_rank):
                             "query_genes": int(counts[3])},
                 "clocks": clocks}
         if world > 1:
-            parts = res["parts"]
-            assert sum(len(x["alns"]) for x in parts) == int(counts[1]) and sum(len(x["clusters"]) for x in parts) == int(counts[2])
-            line["collective"] = {"op": "all_gather_into_tensor (sizes, then padded blocks) of per-rank alignment/backtrace/cluster lists, NCCL",
-                                  "bytes_gathered_per_step": int(sum(x[k].nbytes for x in parts for k in ("alns", "pool", "clusters", "members"))),
-                                  "sharding": "query sets in contiguous residue-balanced blocks; target index replicated"}
+            q_all = res["alns"]["query"]
+            assert len(q_all) == 0 or (int(q_all.max()) < n_total and bool(np.all(np.diff(q_all.astype(np.int64)) >= 0)))
+            line["collective"] = {"op": "ncclAllGather (sizes, then padded blocks) of per-rank alignment/backtrace/cluster lists, issued by "
+                                        "libsdgpu.so (sd_shard_allgather_result, csrc/shard.cu)",
+                                  "bytes_gathered_per_step": int(res["bytes_gathered"]),
+                                  "sharding": "query sets in contiguous residue-balanced blocks (sd_shard_partition); target index replicated"}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(args, proteomes)

@@ -245,6 +245,24 @@ void sd_search_result_sizes(const sd_search_result *r, uint64_t *n_alns, uint64_
 int sd_search_result_copy(const sd_search_result *r, sd_alignment *alns, char *pool, sd_cluster *clusters, sd_cluster_member *members);
 void sd_search_result_destroy(sd_search_result *r);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink (csrc/shard.cu) -------------------------------------------------
+ * The reference's counterpart is its MPI mode (Prefiltering.cpp:273-377 splits the target DB per node and merges the per-split
+ * lists, :662-723; Alignment/ClusterHits run per DB chunk): here the target index is replicated, the QUERY SETS are split into
+ * contiguous residue-balanced blocks (sd_shard_partition), every rank runs sd_clustersearch_run on its block with query_first =
+ * first gene of the block, and ONE all-gather leaves every rank with all ranks' result lists. */
+#define SD_NCCL_ID_BYTES 128
+int sd_shard_unique_id(uint8_t *id /* SD_NCCL_ID_BYTES, filled by rank 0 and sent to the other ranks by the caller */);
+int sd_shard_init(sd_context *ctx, int rank, int world, const uint8_t *id);
+void sd_shard_finalize(sd_context *ctx);
+int sd_shard_rank(const sd_context *ctx);
+int sd_shard_world(const sd_context *ctx);
+/* first_set[world + 1]: rank r owns query sets first_set[r] .. first_set[r+1]-1 */
+int sd_shard_partition(const uint64_t *set_residues, uint32_t n_sets, int world, uint32_t *first_set);
+/* mine: this rank's result (query indices relative to its block; query_first makes them global); *all: every rank's lists in
+ * rank order = ascending query sets, same layout a single-GPU run returns; bytes_gathered: payload bytes over NVLink. */
+int sd_shard_allgather_result(sd_context *ctx, const sd_search_result *mine, uint32_t query_first, sd_search_result **all,
+                              uint64_t *bytes_gathered);
+
 #ifdef __cplusplus
 }
 #endif

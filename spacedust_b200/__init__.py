@@ -349,12 +349,40 @@ def clustersearch_staged(ctx, index, batch, q_meta, t_meta, pref_params=None, al
             "prefilter_stats": pst, "align_stats": ast, "cluster_stats": cst}
 
 
+NCCL_ID_BYTES = 128
+
+
+def shard_unique_id():
+    """ncclGetUniqueId through the C ABI (rank 0; the caller sends the 128 bytes to the other ranks)."""
+    buf = (ctypes.c_uint8 * NCCL_ID_BYTES)()
+    _check(lib().sd_shard_unique_id(buf))
+    return bytes(buf)
+
+
+def shard_init(ctx, rank, world, unique_id):
+    """One process per GPU: NCCL communicator of this rank inside the context (sd_shard_init)."""
+    assert len(unique_id) == NCCL_ID_BYTES
+    buf = (ctypes.c_uint8 * NCCL_ID_BYTES).from_buffer_copy(unique_id)
+    _check(lib().sd_shard_init(ctx._h, ctypes.c_int(rank), ctypes.c_int(world), buf))
+
+
+def shard_partition(set_residues, world):
+    """sd_shard_partition: contiguous residue-balanced blocks of query sets -> [(lo, hi)] * world."""
+    w = np.ascontiguousarray(set_residues, dtype=np.uint64)
+    first = np.zeros(world + 1, dtype=np.uint32)
+    _check(lib().sd_shard_partition(w.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(len(w)), ctypes.c_int(world),
+                                    first.ctypes.data_as(ctypes.c_void_p)))
+    return [(int(first[i]), int(first[i + 1])) for i in range(world)]
+
+
 def clustersearch(ctx, index, batch, q_meta, t_meta, pref_params=None, aln_params=None, clu_params=None, query_first=0,
-                  db_residues=0, out=None):
+                  db_residues=0, out=None, gather=False):
     """The hot path of `spacedust clustersearch` after createsetdb for one query batch, fused (sd_clustersearch_run):
     prefilter -> align -> besthitbyset/combinehits -> clusterhits with the prefilter hit list kept in HBM.
     out: optional object with carve(n_alns, pool_bytes, n_clusters, n_members) -> (alns, pool, clusters, members) arrays to
-    receive the result (e.g. shard.ResultExchange: persistent pinned memory, no per-call allocation)."""
+    receive the result (e.g. shard.ResultExchange: persistent pinned memory, no per-call allocation).
+    gather=True (after shard_init): this rank's block of query sets is searched, then sd_shard_allgather_result (ONE ncclAllGather
+    over NVLink, inside the library) returns every rank's lists with global query indices, in the order of a single-GPU run."""
     pp = pref_params or default_prefilter_params(same_db=1)
     ap = aln_params or default_align_params(same_db=pp.same_db)
     cp = clu_params or default_cluster_params(filter_self_match=1)
@@ -373,6 +401,14 @@ def clustersearch(ctx, index, batch, q_meta, t_meta, pref_params=None, aln_param
                                   ts.ctypes.data_as(p), tp.ctypes.data_as(p), tst.ctypes.data_as(p), ctypes.c_uint32(len(ts)),
                                   qsz.ctypes.data_as(p), ctypes.c_uint32(len(qsz)), tsz.ctypes.data_as(p), ctypes.c_uint32(len(tsz)),
                                   ctypes.c_uint64(db_residues), ctypes.byref(res), ctypes.byref(pst), ctypes.byref(ast), ctypes.byref(cst)))
+    gathered = ctypes.c_uint64(0)
+    if gather:
+        merged = ctypes.c_void_p()
+        try:
+            _check(L.sd_shard_allgather_result(ctx._h, res, ctypes.c_uint32(query_first), ctypes.byref(merged), ctypes.byref(gathered)))
+        finally:
+            L.sd_search_result_destroy(res)
+        res = merged
     try:
         na, nb, nc, nm = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
         L.sd_search_result_sizes(res, ctypes.byref(na), ctypes.byref(nb), ctypes.byref(nc), ctypes.byref(nm))
@@ -389,4 +425,5 @@ def clustersearch(ctx, index, batch, q_meta, t_meta, pref_params=None, aln_param
         L.sd_search_result_destroy(res)
     pst_d = pst.as_dict()
     return {"alns": alns[:na.value], "pool": pool[:nb.value], "clusters": clusters[:nc.value], "members": members[:nm.value],
-            "n_prefilter_hits": None, "prefilter_stats": pst_d, "align_stats": ast.as_dict(), "cluster_stats": cst.as_dict()}
+            "n_prefilter_hits": None, "prefilter_stats": pst_d, "align_stats": ast.as_dict(), "cluster_stats": cst.as_dict(),
+            "bytes_gathered": int(gathered.value)}

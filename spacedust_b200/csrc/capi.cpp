@@ -76,6 +76,7 @@ extern "C" int sd_context_create(int device, sd_context **out) {
 extern "C" void sd_context_destroy(sd_context *ctx) {
     if (!ctx) return;
     if (ctx->helper) { sd_context_destroy(ctx->helper); ctx->helper = nullptr; }
+    sd_shard_finalize(ctx);
     cudaSetDevice(ctx->device);
     for (auto &sl : ctx->devSlot) if (sl.p) cudaFree(sl.p);
     for (auto &sl : ctx->pinSlot) if (sl.p) cudaFreeHost(sl.p);

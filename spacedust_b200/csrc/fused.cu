@@ -184,3 +184,27 @@ extern "C" int sd_search_result_copy(const sd_search_result *r, sd_alignment *al
 }
 
 extern "C" void sd_search_result_destroy(sd_search_result *r) { delete r; }
+
+int sd_search_result_from_blocks(const char *blocks, uint64_t stride, const uint64_t *sizes, int n, sd_search_result **out) {
+    std::unique_ptr<sd_search_result> r(new sd_search_result());
+    r->chunks.resize((size_t)n);
+    auto al = [](uint64_t x) { return (x + 15) & ~15ull; };
+    for (int k = 0; k < n; k++) {
+        const char *b = blocks + (uint64_t)k * stride;
+        uint64_t head[4];
+        memcpy(head, b, sizeof head);
+        const uint64_t na = head[0], np = head[1], nc = head[2], nm = head[3];
+        const uint64_t oA = 32, oP = al(oA + na * sizeof(sd_alignment)), oC = al(oP + np), oM = al(oC + nc * sizeof(sd_cluster));
+        if (al(oM + nm * sizeof(sd_cluster_member)) != sizes[k]) { sd::setError("result block of rank %d is inconsistent", k); return SD_EINVAL; }
+        ChunkResult &cr = r->chunks[(size_t)k];
+        memset(&cr.ast, 0, sizeof cr.ast);
+        memset(&cr.cst, 0, sizeof cr.cst);
+        cr.alns.resize(na); cr.pool.resize(np); cr.clusters.resize(nc); cr.members.resize(nm);
+        if (na) memcpy(cr.alns.data(), b + oA, na * sizeof(sd_alignment));
+        if (np) memcpy(cr.pool.data(), b + oP, np);
+        if (nc) memcpy(cr.clusters.data(), b + oC, nc * sizeof(sd_cluster));
+        if (nm) memcpy(cr.members.data(), b + oM, nm * sizeof(sd_cluster_member));
+    }
+    *out = r.release();
+    return SD_OK;
+}

@@ -84,7 +84,7 @@ enum ScratchSlot {
     SL_PF_TABLE = 0, SL_PF_CAND, SL_PF_KEEP, SL_PF_REST, SL_PF_RESS, SL_PF_RESD, SL_PF_OUT, SL_PF_DENSE, SL_PF_CSEQ, SL_PF_QPACK, SL_PF_POSINFO, SL_PF_POSPREFIX, SL_PF_SORTIDX,
     SL_AL_FWD, SL_AL_WORD, SL_AL_BIG, SL_AL_REV, SL_AL_RES, SL_AL_HITS, SL_AL_TB, SL_AL_TBRES, SL_AL_IDENT, SL_AL_ORDER,
     SL_AL_PROFF, SL_AL_PROFR, SL_AL_PROFS, SL_AL_BOUND, SL_AL_PAIRQ, SL_AL_PAIRT,
-    SL_TB_DIR, SL_TB_ROWS, SL_TB_REV, SL_TB_POOL, SL_SW_KEYA, SL_SW_KEYB, SL_SW_VALA, SL_SW_VALB, SL_SW_ORDER, SL_SW_TMP, SL_COUNT
+    SL_TB_DIR, SL_TB_ROWS, SL_TB_REV, SL_TB_POOL, SL_SW_KEYA, SL_SW_KEYB, SL_SW_VALA, SL_SW_VALB, SL_SW_ORDER, SL_SW_TMP, SL_SH_SIZES, SL_SH_SEND, SL_SH_RECV, SL_COUNT
 };
 static_assert(SL_COUNT <= 48, "sd_context::devSlot is too small");
 void *ctxDeviceScratch(sd_context *ctx, int slot, size_t bytes);     // nullptr + error message on failure
@@ -210,6 +210,9 @@ struct sd_context {
     // fused clustersearch: a second context (own stream + scratch) runs alternate query chunks on a helper thread; the token
     // serialises the GPU-heavy part of the align stage so that one chunk's host post-processing overlaps the other's kernels
     sd_context *helper = nullptr;
+    // multi-GPU (csrc/shard.cu): NCCL communicator of this rank (ncclComm_t), one process per GPU
+    void *comm = nullptr;
+    int rank = 0, world = 1;
     std::mutex *gpuToken = nullptr;
     // seed / diagonal matrices and the sorted 3-mer neighbour table are per context (device resident)
     sd::SubMat seedMat;       // VTML80 x8, bias -0.2   (Prefiltering.cpp:68)
@@ -236,6 +239,8 @@ struct sd_query_batch {
 int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
                       const sd_prefilter_params *par, sd_prefilter_hit *hits, uint64_t cap, uint64_t *n_hits,
                       sd_prefilter_stats *stats, sd::DevBuf<sd_prefilter_hit> *keepOnDevice, std::vector<uint64_t> *hitOffsets = nullptr);
+// merged result of an exchange: one chunk per rank block ([4 x u64 counts][alns][pool][clusters][members], 16-byte aligned parts)
+int sd_search_result_from_blocks(const char *blocks, uint64_t stride, const uint64_t *sizes, int n, sd_search_result **out);
 int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
                           const uint32_t *dPairQ, const uint32_t *dPairT, uint64_t n_pairs, uint64_t db_residues,
                           const sd_align_params *par, std::vector<sd_alignment> &acc, sd::CharPool &pool,

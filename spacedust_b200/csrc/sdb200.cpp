@@ -22,6 +22,8 @@
 #include <map>
 #include <string>
 #include <sys/stat.h>
+#include <sys/wait.h>
+#include <unistd.h>
 #include <vector>
 
 #include "../../include/sdgpu.h"
@@ -105,7 +107,7 @@ void checkKnownFlags(const Args &a) {
     static const char *implemented[] = {
         "-s", "-c", "-e", "-k", "-v", "-a", "--max-seqs", "--min-ungapped-score", "--cov-mode", "--mask", "--mask-prob", "--comp-bias-corr",
         "--min-seq-id", "--min-aln-len", "--score-bias", "--gap-open", "--gap-extend", "--alignment-mode", "--filter-self-match",
-        "--max-gene-gap", "--cluster-size", "--cluster-pval", "--multihit-pval", "--alpha", "--gpu", "--gpus", "--write-dbs", "--search-mode",
+        "--max-gene-gap", "--cluster-size", "--cluster-pval", "--multihit-pval", "--alpha", "--gpu", "--gpus", "--rank", "--nccl-id-file", "--write-dbs", "--search-mode",
         "--num-iterations", "--exact-kmer-matching", "--diag-score", "--spaced-kmer-mode", "--realign", "--alt-ali", "--compressed",
         "--split", "--add-self-matches", "--cluster-use-weight", "--aggregation-mode", "--sub-mat", "--seed-sub-mat", nullptr};
     static const char *inert[] = {
@@ -400,8 +402,84 @@ int modClustersearch(int argc, char **argv) {
     info("Read set DBs: %u query genes in %zu sets, %u target genes in %zu sets, %.0f ms\n", qdb.n(), qdb.setKey.size(), tdb.n(),
          tdb.setKey.size(), nowMs() - t0);
 
+    // ---- multi-GPU (--gpus N): one process per GPU.  The parent starts N copies of itself (--rank r); rank 0 creates the NCCL id and
+    // hands it over through a file in the tmp dir; every rank searches its block of query sets against the whole target index and
+    // ONE ncclAllGather inside libsdgpu.so (sd_shard_allgather_result) gives every rank the whole result; rank 0 writes it.
+    const int nGpus = std::max(1, (int)a.num("--gpus", 1));
+    const int rank = (int)a.num("--rank", -1);
+    if (nGpus > 1 && rank < 0) {
+        const std::string idFile = tmp + "/nccl_id." + std::to_string((long)getpid());
+        unlink(idFile.c_str());
+        std::vector<pid_t> kids;
+        for (int r = 0; r < nGpus; r++) {
+            pid_t pid = fork();
+            if (pid < 0) die("fork failed");
+            if (pid == 0) {
+                std::vector<std::string> args(argv, argv + argc);
+                args.push_back("--rank"); args.push_back(std::to_string(r));
+                args.push_back("--nccl-id-file"); args.push_back(idFile);
+                std::vector<char *> av;
+                for (std::string &x : args) av.push_back(&x[0]);
+                av.push_back(nullptr);
+                execv("/proc/self/exe", av.data());
+                _exit(127);
+            }
+            kids.push_back(pid);
+        }
+        int bad = 0;
+        for (pid_t pid : kids) {
+            int status = 0;
+            waitpid(pid, &status, 0);
+            if (!WIFEXITED(status) || WEXITSTATUS(status) != 0) bad++;
+        }
+        unlink(idFile.c_str());
+        if (bad) die("%d of %d ranks failed", bad, nGpus);
+        return EXIT_SUCCESS;
+    }
+    const int world = rank >= 0 ? nGpus : 1;
+    const int myRank = rank >= 0 ? rank : 0;
+    if (myRank != 0) g_verbosity = std::min(g_verbosity, 1);
+
     sd_context *ctx = nullptr;
-    sdCheck(sd_context_create((int)a.num("--gpu", -1), &ctx), "sd_context_create");
+    sdCheck(sd_context_create(world > 1 ? (int)std::max(0.0, a.num("--gpu", 0)) + myRank : (int)a.num("--gpu", -1), &ctx), "sd_context_create");
+    uint32_t qLo = 0, qHi = qdb.n();
+    if (world > 1) {
+        const std::string idFile = a.str("--nccl-id-file", "");
+        uint8_t id[SD_NCCL_ID_BYTES];
+        if (myRank == 0) {
+            sdCheck(sd_shard_unique_id(id), "sd_shard_unique_id");
+            const std::string part = idFile + ".part";
+            FILE *f = fopen(part.c_str(), "wb");
+            if (!f || fwrite(id, 1, sizeof id, f) != sizeof id) die("cannot write %s", part.c_str());
+            fclose(f);
+            if (rename(part.c_str(), idFile.c_str()) != 0) die("cannot publish %s", idFile.c_str());
+        } else {
+            const double tWait = nowMs();
+            for (;;) {
+                FILE *f = fopen(idFile.c_str(), "rb");
+                if (f) {
+                    const size_t got = fread(id, 1, sizeof id, f);
+                    fclose(f);
+                    if (got == sizeof id) break;
+                }
+                if (nowMs() - tWait > 300000.0) die("rank %d: no NCCL id from rank 0 after 300 s", myRank);
+                usleep(20000);
+            }
+        }
+        sdCheck(sd_shard_init(ctx, myRank, world, id), "sd_shard_init");
+        // this rank's block of query sets (sets are contiguous in the DB order createsetdb writes)
+        std::vector<uint64_t> setRes(qdb.setSize.size(), 0);
+        for (uint32_t g = 0; g < qdb.n(); g++) setRes[qdb.setOf[g]] += qdb.off[g + 1] - qdb.off[g];
+        std::vector<uint32_t> first((size_t)world + 1);
+        sdCheck(sd_shard_partition(setRes.data(), (uint32_t)setRes.size(), world, first.data()), "sd_shard_partition");
+        qLo = qdb.n(); qHi = 0;
+        for (uint32_t g = 0; g < qdb.n(); g++)
+            if (qdb.setOf[g] >= first[myRank] && qdb.setOf[g] < first[myRank + 1]) { qLo = std::min(qLo, g); qHi = std::max(qHi, g + 1); }
+        if (qHi < qLo) { qLo = 0; qHi = 0; }
+        for (uint32_t g = qLo; g < qHi; g++)
+            if (qdb.setOf[g] < first[myRank] || qdb.setOf[g] >= first[myRank + 1]) die("query sets are not contiguous in the set DB");
+        info("rank %d of %d: query sets %u..%u, genes %u..%u\n", myRank, world, first[myRank], first[myRank + 1], qLo, qHi);
+    }
     sd_prefilter_params pp = prefParams(a, same);
     sd_align_params ap = alignParams(a, same);
     sd_cluster_params cp = clusterParams(a);
@@ -409,17 +487,36 @@ int modClustersearch(int argc, char **argv) {
     sd_target_index *idx = nullptr;
     sdCheck(sd_target_index_build(ctx, tdb.residues.data(), tdb.off.data(), tdb.n(), &pp, &idx), "sd_target_index_build");
     sd_query_batch *batch = nullptr;
-    sdCheck(sd_query_batch_create(ctx, qdb.residues.data(), qdb.off.data(), qdb.n(), &batch), "sd_query_batch_create");
+    std::vector<uint64_t> qOffBlock(qdb.off.begin() + qLo, qdb.off.begin() + qHi + 1);
+    for (uint64_t &o : qOffBlock) o -= qdb.off[qLo];
+    sdCheck(sd_query_batch_create(ctx, qdb.residues.data() + qdb.off[qLo], qOffBlock.data(), qHi - qLo, &batch), "sd_query_batch_create");
     info("Index table: %llu entries, %.0f ms\n", (unsigned long long)sd_target_index_entries(idx), nowMs() - t0);
     t0 = nowMs();
     sd_search_result *res = nullptr;
     sd_prefilter_stats pst;
     sd_align_stats ast;
     sd_cluster_stats cst;
-    sdCheck(sd_clustersearch_run(ctx, idx, batch, 0, &pp, &ap, &cp, qdb.setOf.data(), qdb.genePos.data(), qdb.strand.data(),
+    memset(&pst, 0, sizeof pst);
+    // same DB: the identity hit of query gene g is target g = qLo + index in the block
+    sdCheck(sd_clustersearch_run(ctx, idx, batch, qLo, &pp, &ap, &cp, qdb.setOf.data() + qLo, qdb.genePos.data() + qLo, qdb.strand.data() + qLo,
                                  tdb.setOf.data(), tdb.genePos.data(), tdb.strand.data(), tdb.n(), qdb.setSize.data(),
                                  (uint32_t)qdb.setSize.size(), tdb.setSize.data(), (uint32_t)tdb.setSize.size(), 0, &res, &pst, &ast, &cst),
             "sd_clustersearch_run");
+    if (world > 1) {
+        sd_search_result *all = nullptr;
+        uint64_t gathered = 0;
+        sdCheck(sd_shard_allgather_result(ctx, res, qLo, &all, &gathered), "sd_shard_allgather_result");
+        sd_search_result_destroy(res);
+        res = all;
+        info("all-gather of the result lists: %.1f MB over NCCL\n", gathered / 1e6);
+        if (myRank != 0) {      // every rank holds the whole result now; rank 0 writes it
+            sd_search_result_destroy(res);
+            sd_query_batch_destroy(batch);
+            sd_target_index_destroy(idx);
+            sd_context_destroy(ctx);
+            return EXIT_SUCCESS;
+        }
+    }
     uint64_t nA = 0, nPool = 0, nC = 0, nM = 0;
     sd_search_result_sizes(res, &nA, &nPool, &nC, &nM);
     std::vector<sd_alignment> alns(nA + 1);

@@ -170,3 +170,16 @@ def test_exchange_with_an_empty_rank(tmp_path):
     s.close()
     mp.spawn(_worker_empty, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert all(os.path.exists(os.path.join(tmp_path, "ok_%d.npy" % r)) for r in range(2))
+
+
+def test_c_abi_partition_equals_python():
+    """sd_shard_partition (csrc/shard.cu, host code) == shard.partition_sets, including fewer sets than ranks and skewed weights."""
+    import spacedust_b200 as sd
+    from spacedust_b200 import shard
+    rng = np.random.default_rng(4)
+    for n, world in [(1, 1), (1, 4), (3, 8), (8, 8), (20, 8), (20, 3), (200, 8), (7, 2), (500, 8)]:
+        for _ in range(5):
+            w = rng.integers(1, 10 ** 6, size=n).astype(np.uint64)
+            if rng.random() < 0.3:
+                w[rng.integers(0, n)] *= 50
+            assert sd.shard_partition(w, world) == shard.partition_sets(w, world), (n, world, w[:8])

@@ -47,6 +47,19 @@ def _worker(rank, world, port, tmpdir):
                 if True:
                     assert np.array_equal(merged[k][f], merged2[k][f]), (k, f)
         assert np.array_equal(merged["pool"], merged2["pool"])
+        # the product path: communicator and all-gather inside libsdgpu.so (sd_shard_init / sd_shard_allgather_result)
+        box = [sd.shard_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        sd.shard_init(ctx, rank, world, box[0])
+        assert sd.shard_partition(set_res, world)[rank] == (lo, hi)
+        for _ in range(2):
+            r3 = sd.clustersearch(ctx, idx, batch, q_meta, meta, pp, query_first=q_lo, gather=True)
+        assert r3["bytes_gathered"] > 0
+        for k in ("alns", "clusters", "members"):
+            assert len(r3[k]) == len(merged[k]), k
+            for f in merged[k].dtype.names:
+                assert np.array_equal(r3[k][f], merged[k][f]), (k, f)
+        assert np.array_equal(r3["pool"], merged["pool"])
         np.savez(os.path.join(tmpdir, "merged_%d.npz" % rank), **merged)
         if rank == 0:      # the unsharded run on one GPU
             whole = sd.clustersearch(ctx, idx, sd.QueryBatch(ctx, buf, off), meta, meta, pp)
@@ -76,3 +89,28 @@ def test_two_ranks_equal_one(tmp_path):
                 if True:
                     assert np.array_equal(m[k][f], whole[k][f]), (k, f)
         assert np.array_equal(m["pool"], whole["pool"])
+
+
+def test_frontend_two_gpus_equal_one(tmp_path):
+    """`sdb200 clustersearch --gpus 2` (process per GPU started by the front-end, NCCL id through the tmp dir, one all-gather in
+    libsdgpu.so, rank 0 writes) gives the TSV of the single-GPU run."""
+    import subprocess
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import spacedust_b200 as sd
+    from spacedust_b200 import synth
+    sdb = os.path.join(os.path.dirname(sd.LIB_PATH), "sdb200")
+    prot = synth.generate(5, 120, seed=17)
+    paths = synth.write_fasta(prot, os.path.join(tmp_path, "faa"))
+    db = os.path.join(tmp_path, "setDB")
+    subprocess.run([sdb, "createsetdb"] + paths + [db, os.path.join(tmp_path, "tmp")], check=True)
+    outs = []
+    for n in (1, 2):
+        out = os.path.join(tmp_path, "res%d.tsv" % n)
+        subprocess.run([sdb, "clustersearch", db, db, out, os.path.join(tmp_path, "tmp%d" % n), "--filter-self-match", "1", "--gpus", str(n), "-v", "1"],
+                       check=True)
+        outs.append(open(out).read())
+    assert outs[0].count("#") > 5
+    assert outs[0] == outs[1]
