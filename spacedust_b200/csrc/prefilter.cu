@@ -558,6 +558,15 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     if (useStream) {
         const uint32_t nCtaS = std::max(1u, std::min<uint32_t>((uint32_t)(ctx->smCount * 4), (nq + PS_WARPS - 1) / PS_WARPS));
         const uint32_t nWarpsS = nCtaS * PS_WARPS;
+        // A warp works through its query alone: queries much longer than a warp's share of the batch set the kernel's tail (strong
+        // scaling of small batches).  They go to the binned kernel instead, where a whole CTA shares one query.
+        uint32_t nLong = 0;
+        {
+            const double share = (double)total / (double)nWarpsS;
+            const double longThr = std::max(512.0, share);
+            while (nLong < nq && (double)(hOff[order[nLong] + 1] - hOff[order[nLong]]) > longThr) nLong++;
+            if (getenv("SD_PF_NOLONG")) nLong = 0;
+        }
         // first-pass capacity of the per-warp candidate lists (SD_PF_CANDCAP: test hook that forces the second pass)
         uint32_t candCapS = 32768u;
         while (candCapS < 262144u && (uint64_t)candCapS * 8u < idx->nT) candCapS *= 2;
@@ -575,7 +584,7 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
         sa.bm = idx->bm.p; sa.rows = idx->rows.p; sa.ent = idx->ent.p;
         sa.e3pair = ctx->e3pair.p; sa.e3cnt = ctx->e3cnt.p; sa.diagSub = dDiagSub.p;
         sa.q.code = dCode.p; sa.q.off = dOff.p; sa.q.corr = dCorr.p; sa.q.thr = dThr.p;
-        sa.nQ = nq; sa.order = dOrder.p; sa.queryFirst = query_first; sa.sameDb = par->same_db;
+        sa.nQ = nq - nLong; sa.order = dOrder.p + nLong; sa.queryFirst = query_first; sa.sameDb = par->same_db;
         sa.maxHits = maxHits; sa.minDiagScore = (uint32_t)std::max(par->min_ungapped_score, 0);
         sa.covThr = par->cov_thr; sa.covMode = par->cov_mode; sa.binMask = (uint32_t)binSize - 1u;
         sa.maxDbMatches = maxDbMatches;
@@ -586,9 +595,11 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
         sa.evictFirst = 0; sa.prefetch = 0; sa.debugSkip = 0;
         SD_CUDA(cudaFuncSetAttribute(prefilterStreamKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_DYN_SMEM));
         if (getenv("SD_PF_DEBUG")) fprintf(stderr, "[sd] prefilter: streaming kernel, %u CTAs x %d warps, candidate lists %u\n", nCtaS, PS_WARPS, candCapS);
-        prefilterStreamKernel<<<nCtaS, PS_WARPS * 32, PS_DYN_SMEM, st>>>(sa);
-        ctx->launches++;
-        SD_CUDA(cudaGetLastError());
+        if (sa.nQ) {
+            prefilterStreamKernel<<<nCtaS, PS_WARPS * 32, PS_DYN_SMEM, st>>>(sa);
+            ctx->launches++;
+            SD_CUDA(cudaGetLastError());
+        }
         // listed queries: bit 31 = reached the reference's hit-buffer limit (-> binned kernel); otherwise the candidate list
         // did not fit (-> second streaming launch over just those, few warps with 4 M entry lists)
         uint32_t hN[4];
@@ -599,8 +610,11 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
             SD_CUDA(cudaMemcpyAsync(listed.data(), dFail.p, hN[2] * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             SD_CUDA(cudaStreamSynchronize(st));
         }
+        for (uint32_t i = 0; i < nLong; i++) over.push_back(order[i]);
         for (uint32_t v : listed) (v >> 31 ? over : big).push_back(v & 0x7fffffffu);
-        if (getenv("SD_PF_DEBUG")) fprintf(stderr, "[sd] prefilter: %zu queries reach the hit-buffer limit, %zu overflow the candidate lists\n", over.size(), big.size());
+        if (getenv("SD_PF_DEBUG"))
+            fprintf(stderr, "[sd] prefilter: %u long queries to the binned kernel, %zu queries reach the hit-buffer limit, %zu overflow the candidate lists\n",
+                    nLong, over.size() - nLong, big.size());
         if (!big.empty()) {
             const uint32_t bigCap = 1u << 22;
             const uint32_t nCta2 = std::max(1u, std::min<uint32_t>(((uint32_t)big.size() + PS_WARPS - 1) / PS_WARPS, 16u));

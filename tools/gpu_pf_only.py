@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Prefilter only on N x G synthetic proteomes all-vs-all (no oracle): kernel time, counters, algorithmic GB/s.
-usage: gpu_pf_only.py N G [reps]"""
+usage: gpu_pf_only.py N G [reps] [query_genes]   (query_genes: only the first so many genes are queries, e.g. one rank's block)"""
 import os
 import sys
 import time
@@ -21,7 +21,8 @@ def main():
     t0 = time.time()
     idx = sd.TargetIndex(ctx, buf, off, gp)
     print("index build %.3fs entries %d" % (time.time() - t0, idx.entries), flush=True)
-    batch = sd.QueryBatch(ctx, buf, off)
+    nqg = int(sys.argv[4]) if len(sys.argv) > 4 else len(off) - 1
+    batch = sd.QueryBatch(ctx, buf[:int(off[nqg])], off[:nqg + 1])
     for rep in range(reps):
         hits, st = sd.prefilter_batch(ctx, idx, batch, gp)
         algo = 8 * st["probes"] + 6 * st["matches"] + st["diag_residues"] + 21 * st["query_residues"] + 10 * st["hits"]
