@@ -98,6 +98,12 @@ void sd_target_index_destroy(sd_target_index *idx);
 /* Copy the masked numeric residues (sum of lengths bytes) back; test hook. */
 int sd_target_index_masked(const sd_target_index *idx, uint8_t *out, uint64_t cap);
 uint64_t sd_target_index_entries(const sd_target_index *idx);
+uint32_t sd_target_index_targets(const sd_target_index *idx);
+/* Persisted GPU-ready index (the reference's counterpart: `createindex` + PrefilteringIndexReader, lib/mmseqs/src/prefiltering/
+ * PrefilteringIndexReader.cpp): the device buffers of a built index in one file; loading is read + upload, nothing is recomputed.
+ * sd_target_index_load refuses a file built with another sensitivity / masking. */
+int sd_target_index_save(const sd_target_index *idx, const sd_prefilter_params *par, const char *path);
+int sd_target_index_load(sd_context *ctx, const char *path, const sd_prefilter_params *par, sd_target_index **out);
 
 /* Run the prefilter for nq queries against the index (body of the query loop of
  * Prefiltering::runSplit, Prefiltering.cpp:790-880).  Hits are grouped by query in query order;
@@ -259,7 +265,8 @@ int sd_shard_world(const sd_context *ctx);
 /* first_set[world + 1]: rank r owns query sets first_set[r] .. first_set[r+1]-1 */
 int sd_shard_partition(const uint64_t *set_residues, uint32_t n_sets, int world, uint32_t *first_set);
 /* mine: this rank's result (query indices relative to its block; query_first makes them global); *all: every rank's lists in
- * rank order = ascending query sets, same layout a single-GPU run returns; bytes_gathered: payload bytes over NVLink. */
+ * rank order = ascending query sets, same layout a single-GPU run returns (it refers to the context's receive buffer: copy it out with
+ * sd_search_result_copy before the next exchange on this context); bytes_gathered: payload bytes over NVLink. */
 int sd_shard_allgather_result(sd_context *ctx, const sd_search_result *mine, uint32_t query_first, sd_search_result **all,
                               uint64_t *bytes_gathered);
 

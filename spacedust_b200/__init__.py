@@ -62,6 +62,7 @@ def lib():
         L.sd_last_error.restype = ctypes.c_char_p
         L.sd_context_launches.restype = ctypes.c_uint64
         L.sd_target_index_entries.restype = ctypes.c_uint64
+        L.sd_target_index_targets.restype = ctypes.c_uint32
         L.sd_search_result_sizes.restype = None
         L.sd_search_result_destroy.restype = None
         _lib = L
@@ -119,6 +120,20 @@ class TargetIndex:
         _check(lib().sd_target_index_build(ctx._h, self.seqs.ctypes.data_as(ctypes.c_char_p),
                                            self.off.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(self.n),
                                            ctypes.byref(params), ctypes.byref(self._h)))
+
+    @classmethod
+    def load(cls, ctx, path, params):
+        """Persisted index (sd_target_index_load): read + upload, nothing is recomputed."""
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.seqs = self.off = None
+        self._h = ctypes.c_void_p()
+        _check(lib().sd_target_index_load(ctx._h, path.encode(), ctypes.byref(params), ctypes.byref(self._h)))
+        self.n = int(lib().sd_target_index_targets(self._h))
+        return self
+
+    def save(self, path, params):
+        _check(lib().sd_target_index_save(self._h, ctypes.byref(params), path.encode()))
 
     @property
     def entries(self):

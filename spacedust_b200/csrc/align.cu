@@ -546,8 +546,9 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
     std::unique_lock<std::mutex> gpuTurn;
     if (ctx->gpuToken) gpuTurn = std::unique_lock<std::mutex>(*ctx->gpuToken);
     int rc;
-    cudaEvent_t ev0, ev1, evA, evB;
-    SD_CUDA(cudaEventCreate(&ev0)); SD_CUDA(cudaEventCreate(&ev1)); SD_CUDA(cudaEventCreate(&evA)); SD_CUDA(cudaEventCreate(&evB));
+    sd::EventQuad events;
+    { const int erc = events.create(); if (erc) return erc; }
+    cudaEvent_t ev0 = events.e[0], ev1 = events.e[1], evA = events.e[2], evB = events.e[3];
     SD_CUDA(cudaEventRecord(ev0, st));
     const bool timing = getenv("SD_TIMING") != nullptr;
     auto tPrev = std::chrono::steady_clock::now();
@@ -969,7 +970,6 @@ int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_
         stats->cells_forward = hc[0]; stats->cells_reverse = hc[1]; stats->cells_traceback = hc[2]; stats->target_residues = hc[3];
         stats->sw_ms = swMs; stats->traceback_ms = tbMs; stats->total_ms = ms;
     }
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evA); cudaEventDestroy(evB);
     return SD_OK;
 }
 

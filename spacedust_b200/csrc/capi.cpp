@@ -1,4 +1,5 @@
 // C ABI plumbing of libsdgpu.so: error slot, context life cycle.
+#include <memory>
 #include "sd_internal.h"
 
 #include <cstring>
@@ -53,7 +54,8 @@ extern "C" int sd_context_create(int device, sd_context **out) {
     if (device < 0) SD_CUDA(cudaGetDevice(&device));
     if (device >= count) { sd::setError("device %d out of range (%d devices)", device, count); return SD_EINVAL; }
     SD_CUDA(cudaSetDevice(device));
-    sd_context *ctx = new sd_context();
+    std::unique_ptr<sd_context> holder(new sd_context());      // released to the caller at the end: no leak on an early return
+    sd_context *ctx = holder.get();
     ctx->device = device;
     cudaDeviceProp prop;
     SD_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -69,7 +71,7 @@ extern "C" int sd_context_create(int device, sd_context **out) {
     sd::buildSubMat(sd::VTML80, 8.0f, -0.2f, ctx->seedMat);
     sd::buildSubMat(sd::BLOSUM62, 2.0f, -0.2f, ctx->diagMat);
     sd::buildSubMat(sd::BLOSUM62, 2.0f, 0.0f, ctx->alnMat);
-    *out = ctx;
+    *out = holder.release();
     return SD_OK;
 }
 

@@ -294,8 +294,9 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
     SD_CUDA(cudaSetDevice(ctx->device));
     sd::StreamScope allocScope(ctx->stream);
     cudaStream_t st = ctx->stream;
-    cudaEvent_t ev0, ev1, evA, evB;
-    SD_CUDA(cudaEventCreate(&ev0)); SD_CUDA(cudaEventCreate(&ev1)); SD_CUDA(cudaEventCreate(&evA)); SD_CUDA(cudaEventCreate(&evB));
+    sd::EventQuad events;
+    { const int erc = events.create(); if (erc) return erc; }
+    cudaEvent_t ev0 = events.e[0], ev1 = events.e[1], evA = events.e[2], evB = events.e[3];
     SD_CUDA(cudaEventRecord(ev0, st));
 
     const bool timing = getenv("SD_TIMING") != nullptr;
@@ -597,6 +598,5 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
         stats->max_hits_per_pair = maxK; stats->merges = hStat[0]; stats->inexact_log = hStat[1];
         stats->kernel_ms = kernelMs; stats->total_ms = ms;
     }
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evA); cudaEventDestroy(evB);
     return SD_OK;
 }

@@ -70,6 +70,8 @@ bool Db::open(const std::string &path, std::string &err) {
         uint32_t v;
         memcpy(&v, t.data(), 4);
         dbtype = (int)(v & 0xffff);
+        // bit 31 = entries are zstd-compressed (Parameters.h:90-94, DBReader decompresses them): not read here
+        if (v & 0x80000000u) { err = path + " is a compressed DB (--compressed 1): not supported, re-create it with --compressed 0"; return false; }
     }
     return true;
 }

@@ -20,6 +20,22 @@ struct ChunkResult {
     sd::CharPool pool;
     std::vector<sd_cluster> clusters;
     std::vector<sd_cluster_member> members;
+    // merged result of an exchange: views into the context's pinned receive buffer instead of owned vectors (valid until the
+    // next exchange on that context; the caller copies the result out right away)
+    const sd_alignment *vAlns = nullptr;
+    const char *vPool = nullptr;
+    const sd_cluster *vClusters = nullptr;
+    const sd_cluster_member *vMembers = nullptr;
+    uint64_t vNa = 0, vNp = 0, vNc = 0, vNm = 0;
+    bool view = false;
+    uint64_t nAlns() const { return view ? vNa : alns.size(); }
+    uint64_t nPool() const { return view ? vNp : pool.size(); }
+    uint64_t nClusters() const { return view ? vNc : clusters.size(); }
+    uint64_t nMembers() const { return view ? vNm : members.size(); }
+    const sd_alignment *pAlns() const { return view ? vAlns : alns.data(); }
+    const char *pPool() const { return view ? vPool : pool.data(); }
+    const sd_cluster *pClusters() const { return view ? vClusters : clusters.data(); }
+    const sd_cluster_member *pMembers() const { return view ? vMembers : members.data(); }
     sd_align_stats ast;
     sd_cluster_stats cst;
     int rc = SD_OK;
@@ -149,7 +165,7 @@ extern "C" int sd_clustersearch_run(sd_context *ctx, const sd_target_index *idx,
 extern "C" void sd_search_result_sizes(const sd_search_result *r, uint64_t *n_alns, uint64_t *pool_bytes, uint64_t *n_clusters, uint64_t *n_members) {
     uint64_t a = 0, p = 0, c = 0, m = 0;
     if (r)
-        for (const ChunkResult &cr : r->chunks) { a += cr.alns.size(); p += cr.pool.size(); c += cr.clusters.size(); m += cr.members.size(); }
+        for (const ChunkResult &cr : r->chunks) { a += cr.nAlns(); p += cr.nPool(); c += cr.nClusters(); m += cr.nMembers(); }
     if (n_alns) *n_alns = a;
     if (pool_bytes) *pool_bytes = p;
     if (n_clusters) *n_clusters = c;
@@ -162,20 +178,25 @@ extern "C" int sd_search_result_copy(const sd_search_result *r, sd_alignment *al
     if (!r) { sd::setError("sd_search_result_copy: null result"); return SD_EINVAL; }
     uint64_t a0 = 0, p0 = 0, c0 = 0, m0 = 0;
     for (const ChunkResult &cr : r->chunks) {
-        const uint64_t na = cr.alns.size(), np = cr.pool.size(), nc = cr.clusters.size(), nm = cr.members.size();
+        const uint64_t na = cr.nAlns(), np = cr.nPool(), nc = cr.nClusters(), nm = cr.nMembers();
         if (alns && na) {
             sd_alignment *dst = alns + a0;
-            const sd_alignment *src = cr.alns.data();
+            const sd_alignment *src = cr.pAlns();
             sd::parallelFor(na, [&](uint64_t i) { dst[i] = src[i]; dst[i].bt_off += p0; });
         }
-        if (pool && np) memcpy(pool + p0, cr.pool.data(), np);
+        if (pool && np) {
+            const char *src = cr.pPool();
+            char *dst = pool + p0;
+            sd::parallelChunks(np, 64, [&](unsigned, uint64_t lo, uint64_t hi) { memcpy(dst + lo, src + lo, hi - lo); });
+        }
         if (clusters && nc) {
             sd_cluster *dst = clusters + c0;
-            for (uint64_t i = 0; i < nc; i++) { dst[i] = cr.clusters[i]; dst[i].first += (uint32_t)m0; }
+            const sd_cluster *src = cr.pClusters();
+            sd::parallelFor(nc, [&](uint64_t i) { dst[i] = src[i]; dst[i].first += (uint32_t)m0; });
         }
         if (members && nm) {
             sd_cluster_member *dst = members + m0;
-            const sd_cluster_member *src = cr.members.data();
+            const sd_cluster_member *src = cr.pMembers();
             sd::parallelFor(nm, [&](uint64_t i) { dst[i] = src[i]; dst[i].aln += (uint32_t)a0; });
         }
         a0 += na; p0 += np; c0 += nc; m0 += nm;
@@ -199,11 +220,11 @@ int sd_search_result_from_blocks(const char *blocks, uint64_t stride, const uint
         ChunkResult &cr = r->chunks[(size_t)k];
         memset(&cr.ast, 0, sizeof cr.ast);
         memset(&cr.cst, 0, sizeof cr.cst);
-        cr.alns.resize(na); cr.pool.resize(np); cr.clusters.resize(nc); cr.members.resize(nm);
-        if (na) memcpy(cr.alns.data(), b + oA, na * sizeof(sd_alignment));
-        if (np) memcpy(cr.pool.data(), b + oP, np);
-        if (nc) memcpy(cr.clusters.data(), b + oC, nc * sizeof(sd_cluster));
-        if (nm) memcpy(cr.members.data(), b + oM, nm * sizeof(sd_cluster_member));
+        cr.view = true;
+        cr.vAlns = reinterpret_cast<const sd_alignment *>(b + oA); cr.vNa = na;
+        cr.vPool = b + oP; cr.vNp = np;
+        cr.vClusters = reinterpret_cast<const sd_cluster *>(b + oC); cr.vNc = nc;
+        cr.vMembers = reinterpret_cast<const sd_cluster_member *>(b + oM); cr.vNm = nm;
     }
     *out = r.release();
     return SD_OK;

@@ -491,9 +491,9 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     sd::StreamScope allocScope(ctx->stream);
     cudaStream_t st = ctx->stream;
     int rc;
-    cudaEvent_t ev0, ev1, evk0, evk1;
-    SD_CUDA(cudaEventCreate(&ev0)); SD_CUDA(cudaEventCreate(&ev1));
-    SD_CUDA(cudaEventCreate(&evk0)); SD_CUDA(cudaEventCreate(&evk1));
+    sd::EventQuad events;
+    { const int erc = events.create(); if (erc) return erc; }
+    cudaEvent_t ev0 = events.e[0], ev1 = events.e[1], evk0 = events.e[2], evk1 = events.e[3];
     SD_CUDA(cudaEventRecord(ev0, st));
 
     const uint32_t nPos = (uint32_t)total;
@@ -841,7 +841,6 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
         stats->query_residues = total; stats->hits = hStats[ST_HITS]; stats->candidates = hStats[ST_CANDS];
         stats->truncated = hStats[ST_TRUNC]; stats->kernel_ms = msK; stats->total_ms = msT;
     }
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evk0); cudaEventDestroy(evk1);
     return SD_OK;
 }
 
@@ -850,3 +849,91 @@ extern "C" int sd_prefilter_run_batch(sd_context *ctx, const sd_target_index *id
                                       sd_prefilter_stats *stats) {
     return sd_prefilter_core(ctx, idx, queries, query_first, par, hits, cap, n_hits, stats, nullptr);
 }
+
+// ------------------------------------------------------------------------------------------------
+// persisted GPU-ready index (the reference's counterpart: createindex / PrefilteringIndexReader, which stores the CPU index table
+// next to the DB so that repeated searches skip IndexBuilder::fillDatabase).  One flat file: header, target offsets, then the
+// device buffers exactly as the kernels read them (masked + unmasked residue codes, occupancy bitmap {bits, rank}, bucket rows,
+// entries).  Loading is a read + upload; nothing is recomputed.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct IndexFileHeader {
+    char magic[8];             // "SDGPUIX2"
+    uint32_t version, nT;
+    uint64_t totalRes, nEntries, masked;
+    int32_t kmerThr;
+    uint32_t maxLen, nDistinct, bmWords;
+    float sensitivity, maskProb;
+    int32_t mask, pad;
+};
+}  // namespace
+
+extern "C" int sd_target_index_save(const sd_target_index *idx, const sd_prefilter_params *par, const char *path) {
+    if (!idx || !par || !path) { setError("sd_target_index_save: bad argument"); return SD_EINVAL; }
+    sd_context *ctx = idx->ctx;
+    SD_CUDA(cudaSetDevice(ctx->device));
+    FILE *f = fopen(path, "wb");
+    if (!f) { setError("cannot write %s", path); return SD_EINVAL; }
+    IndexFileHeader h{};
+    memcpy(h.magic, "SDGPUIX2", 8);
+    h.version = 2; h.nT = idx->nT; h.totalRes = idx->totalRes; h.nEntries = idx->nEntries; h.masked = idx->masked;
+    h.kmerThr = idx->kmerThr; h.maxLen = idx->maxLen; h.nDistinct = idx->nDistinct; h.bmWords = (uint32_t)idx->bm.n;
+    h.sensitivity = par->sensitivity; h.maskProb = par->mask_prob; h.mask = par->mask;
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(idx->hostOff.data(), sizeof(uint32_t), (size_t)idx->nT + 1, f) == (size_t)idx->nT + 1;
+    auto dump = [&](const void *dev, size_t bytes) {
+        std::vector<char> host(bytes);
+        if (cudaMemcpy(host.data(), dev, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+        return bytes == 0 || fwrite(host.data(), 1, bytes, f) == bytes;
+    };
+    ok = ok && dump(idx->res.p, idx->totalRes + 32) && dump(idx->raw.p, idx->totalRes + 32) && dump(idx->bm.p, idx->bm.n * sizeof(uint2)) &&
+         dump(idx->rows.p, ((size_t)idx->nDistinct + 1) * sizeof(uint2)) && dump(idx->ent.p, (size_t)idx->nEntries * sizeof(uint2));
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { setError("writing %s failed", path); return SD_EINVAL; }
+    return SD_OK;
+}
+
+extern "C" int sd_target_index_load(sd_context *ctx, const char *path, const sd_prefilter_params *par, sd_target_index **out) {
+    if (!ctx || !path || !par || !out) { setError("sd_target_index_load: bad argument"); return SD_EINVAL; }
+    *out = nullptr;
+    SD_CUDA(cudaSetDevice(ctx->device));
+    sd::StreamScope allocScope(ctx->stream);
+    FILE *f = fopen(path, "rb");
+    if (!f) { setError("cannot read %s", path); return SD_EINVAL; }
+    std::unique_ptr<FILE, int (*)(FILE *)> closer(f, fclose);
+    IndexFileHeader h;
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "SDGPUIX2", 8) != 0 || h.version != 2) { setError("%s is not a libsdgpu index file (version 2)", path); return SD_EINVAL; }
+    // the index depends on the sensitivity (k-mer threshold) and on the masking parameters: refuse a file built with others
+    if (h.kmerThr != kmerThreshold(par->sensitivity, KMER) || h.mask != par->mask || (par->mask && h.maskProb != par->mask_prob)) {
+        setError("%s was built with -s %g --mask %d --mask-prob %g; the search asks for -s %g --mask %d --mask-prob %g", path, h.sensitivity, h.mask,
+                 h.maskProb, par->sensitivity, par->mask, par->mask_prob);
+        return SD_EINVAL;
+    }
+    std::unique_ptr<sd_target_index> idx(new sd_target_index());
+    idx->ctx = ctx; idx->nT = h.nT; idx->totalRes = h.totalRes; idx->nEntries = h.nEntries; idx->masked = h.masked;
+    idx->kmerThr = h.kmerThr; idx->maxLen = h.maxLen; idx->nDistinct = h.nDistinct;
+    idx->hostOff.resize((size_t)h.nT + 1);
+    if (fread(idx->hostOff.data(), sizeof(uint32_t), (size_t)h.nT + 1, f) != (size_t)h.nT + 1) { setError("%s is truncated", path); return SD_EINVAL; }
+    int rc;
+    if ((rc = idx->res.alloc(h.totalRes + 32)) || (rc = idx->raw.alloc(h.totalRes + 32)) || (rc = idx->off.alloc((size_t)h.nT + 1)) ||
+        (rc = idx->bm.alloc(h.bmWords)) || (rc = idx->rows.alloc((size_t)h.nDistinct + 1)) || (rc = idx->ent.alloc(h.nEntries)))
+        return rc;
+    std::vector<char> host;
+    auto load = [&](void *dev, size_t bytes) {
+        host.resize(bytes);
+        if (bytes && fread(host.data(), 1, bytes, f) != bytes) return false;
+        return cudaMemcpyAsync(dev, host.data(), bytes, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+               cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    };
+    if (!load(idx->res.p, h.totalRes + 32) || !load(idx->raw.p, h.totalRes + 32) || !load(idx->bm.p, (size_t)h.bmWords * sizeof(uint2)) ||
+        !load(idx->rows.p, ((size_t)h.nDistinct + 1) * sizeof(uint2)) || !load(idx->ent.p, (size_t)h.nEntries * sizeof(uint2))) {
+        setError("%s is truncated or the upload failed", path);
+        return SD_EINVAL;
+    }
+    SD_CUDA(cudaMemcpyAsync(idx->off.p, idx->hostOff.data(), ((size_t)h.nT + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(cudaStreamSynchronize(ctx->stream));
+    if ((rc = ensureExt3(ctx)) != SD_OK) return rc;
+    *out = idx.release();
+    return SD_OK;
+}
+
+extern "C" uint32_t sd_target_index_targets(const sd_target_index *idx) { return idx ? idx->nT : 0; }

@@ -90,6 +90,20 @@ static_assert(SL_COUNT <= 48, "sd_context::devSlot is too small");
 void *ctxDeviceScratch(sd_context *ctx, int slot, size_t bytes);     // nullptr + error message on failure
 void *ctxPinnedScratch(sd_context *ctx, int slot, size_t bytes);
 
+// four timing events that are destroyed on every return path
+struct EventQuad {
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    int create() {
+        for (auto &x : e)
+            if (cudaEventCreate(&x) != cudaSuccess) { setError("cudaEventCreate failed"); return SD_ENODEV; }
+        return SD_OK;
+    }
+    ~EventQuad() { for (auto &x : e) if (x) cudaEventDestroy(x); }
+    EventQuad() = default;
+    EventQuad(const EventQuad &) = delete;
+    EventQuad &operator=(const EventQuad &) = delete;
+};
+
 // DevBuf look-alike backed by a context slot (not freed when it goes out of scope)
 template <typename T>
 struct ScratchBuf {
@@ -239,7 +253,8 @@ struct sd_query_batch {
 int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
                       const sd_prefilter_params *par, sd_prefilter_hit *hits, uint64_t cap, uint64_t *n_hits,
                       sd_prefilter_stats *stats, sd::DevBuf<sd_prefilter_hit> *keepOnDevice, std::vector<uint64_t> *hitOffsets = nullptr);
-// merged result of an exchange: one chunk per rank block ([4 x u64 counts][alns][pool][clusters][members], 16-byte aligned parts)
+// merged result of an exchange: one chunk per rank block ([4 x u64 counts][alns][pool][clusters][members], 16-byte aligned parts);
+// the chunks are VIEWS into `blocks` (the context's pinned receive buffer), valid until the next exchange on that context
 int sd_search_result_from_blocks(const char *blocks, uint64_t stride, const uint64_t *sizes, int n, sd_search_result **out);
 int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
                           const uint32_t *dPairQ, const uint32_t *dPairT, uint64_t n_pairs, uint64_t db_residues,

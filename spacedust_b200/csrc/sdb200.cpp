@@ -107,7 +107,7 @@ void checkKnownFlags(const Args &a) {
     static const char *implemented[] = {
         "-s", "-c", "-e", "-k", "-v", "-a", "--max-seqs", "--min-ungapped-score", "--cov-mode", "--mask", "--mask-prob", "--comp-bias-corr",
         "--min-seq-id", "--min-aln-len", "--score-bias", "--gap-open", "--gap-extend", "--alignment-mode", "--filter-self-match",
-        "--max-gene-gap", "--cluster-size", "--cluster-pval", "--multihit-pval", "--alpha", "--gpu", "--gpus", "--rank", "--nccl-id-file", "--write-dbs", "--search-mode",
+        "--max-gene-gap", "--cluster-size", "--cluster-pval", "--multihit-pval", "--alpha", "--gpu", "--gpus", "--rank", "--nccl-id-file", "--write-dbs", "--ignore-index", "--search-mode",
         "--num-iterations", "--exact-kmer-matching", "--diag-score", "--spaced-kmer-mode", "--realign", "--alt-ali", "--compressed",
         "--split", "--add-self-matches", "--cluster-use-weight", "--aggregation-mode", "--sub-mat", "--seed-sub-mat", nullptr};
     static const char *inert[] = {
@@ -174,9 +174,13 @@ std::string realPath(const std::string &p) {
     return p;
 }
 
-sd_prefilter_params prefParams(const Args &a, bool sameDb) {
+// workflow = true: defaults of `clustersearch` (data/clustersearch.sh passes -s 5.7 -c 0.8 --cov-mode 2 -e 10 --min-aln-len 30);
+// workflow = false: the stand-alone `prefilter` / `align` modules start from the reference's module defaults
+// (Parameters.cpp:2364-2425: -s 4, -c 0, --cov-mode 0, -e 0.001, --min-aln-len 0), so that the same command line gives the same DB.
+sd_prefilter_params prefParams(const Args &a, bool sameDb, bool workflow = true) {
     sd_prefilter_params p;
     sd_prefilter_params_default(&p);
+    if (!workflow) { p.sensitivity = 4.0f; p.cov_thr = 0.0f; p.cov_mode = 0; }
     p.sensitivity = (float)a.num("-s", p.sensitivity);
     p.max_seqs = (int)a.num("--max-seqs", p.max_seqs);
     p.min_ungapped_score = (int)a.num("--min-ungapped-score", p.min_ungapped_score);
@@ -189,9 +193,10 @@ sd_prefilter_params prefParams(const Args &a, bool sameDb) {
     return p;
 }
 
-sd_align_params alignParams(const Args &a, bool sameDb) {
+sd_align_params alignParams(const Args &a, bool sameDb, bool workflow = true) {
     sd_align_params p;
     sd_align_params_default(&p);
+    if (!workflow) { p.evalue_thr = 0.001; p.cov_thr = 0.0f; p.cov_mode = 0; p.min_aln_len = 0; }
     p.evalue_thr = a.num("-e", p.evalue_thr);
     p.min_seq_id = a.num("--min-seq-id", p.min_seq_id);
     p.cov_thr = (float)a.num("-c", p.cov_thr);
@@ -272,7 +277,9 @@ int modPrefilter(int argc, char **argv) {
     SeqView &q = same ? t : qv;
     sd_context *ctx = nullptr;
     sdCheck(sd_context_create(-1, &ctx), "sd_context_create");
-    sd_prefilter_params p = prefParams(a, same);
+    sd_prefilter_params p = prefParams(a, same, false);
+    info("prefilter: -s %g --max-seqs %d -c %g --cov-mode %d --min-ungapped-score %d (reference module defaults unless given)\n", p.sensitivity,
+         p.max_seqs, p.cov_thr, p.cov_mode, p.min_ungapped_score);
     sd_target_index *idx = nullptr;
     double t0 = nowMs();
     sdCheck(sd_target_index_build(ctx, t.residues.data(), t.off.data(), (uint32_t)t.keys.size(), &p, &idx), "sd_target_index_build");
@@ -346,7 +353,9 @@ int modAlign(int argc, char **argv) {
     sdCheck(sd_context_create(-1, &ctx), "sd_context_create");
     sd_prefilter_params pp = prefParams(a, same);
     pp.mask = 0;       // the alignment reads unmasked residues; no k-mer index is probed here
-    sd_align_params ap = alignParams(a, same);
+    sd_align_params ap = alignParams(a, same, false);
+    info("align: -e %g -c %g --cov-mode %d --min-aln-len %d --min-seq-id %g (reference module defaults unless given)\n", ap.evalue_thr, ap.cov_thr,
+         ap.cov_mode, ap.min_aln_len, ap.min_seq_id);
     sd_target_index *idx = nullptr;
     sdCheck(sd_target_index_build(ctx, t.residues.data(), t.off.data(), (uint32_t)t.keys.size(), &pp, &idx), "sd_target_index_build");
     uint64_t cap = std::max<uint64_t>(1024, pq.size() / 4), btCap = cap * 512, n = 0, used = 0;
@@ -385,6 +394,31 @@ int modAlign(int argc, char **argv) {
 }
 
 // ------------------------------------------------------------------------------------------------------ clustersearch
+// `createindex <setDB> <tmpDir>`: build the target index once and keep it next to the DB (<setDB>.sdidx) -- the reference's
+// createindex writes <db>.idx, which later searches pick up instead of rebuilding the table (PrefilteringIndexReader).
+int modCreateindex(int argc, char **argv) {
+    Args a = parseArgs(argc, argv, 2);
+    if (a.pos.size() < 1 || a.pos.size() > 2) die("usage: sdb200 createindex <setDB> [tmpDir] [-s 5.7] [--mask 1] [--mask-prob 0.9]");
+    g_verbosity = (int)a.num("-v", 3);
+    rejectUnsupported(a);
+    sddb::SetDb tdb;
+    std::string err;
+    if (!tdb.open(a.pos[0], err)) die("%s", err.c_str());
+    sd_context *ctx = nullptr;
+    sdCheck(sd_context_create((int)a.num("--gpu", -1), &ctx), "sd_context_create");
+    sd_prefilter_params pp = prefParams(a, true);
+    sd_target_index *idx = nullptr;
+    double t0 = nowMs();
+    sdCheck(sd_target_index_build(ctx, tdb.residues.data(), tdb.off.data(), tdb.n(), &pp, &idx), "sd_target_index_build");
+    const std::string idxFile = a.pos[0] + ".sdidx";
+    sdCheck(sd_target_index_save(idx, &pp, idxFile.c_str()), "sd_target_index_save");
+    info("Index table: %llu entries for %u targets (-s %g), %.0f ms -> %s\n", (unsigned long long)sd_target_index_entries(idx), tdb.n(), pp.sensitivity,
+         nowMs() - t0, idxFile.c_str());
+    sd_target_index_destroy(idx);
+    sd_context_destroy(ctx);
+    return EXIT_SUCCESS;
+}
+
 int modClustersearch(int argc, char **argv) {
     Args a = parseArgs(argc, argv, 2);
     if (a.pos.size() != 4) die("usage: sdb200 clustersearch <querySetDB> <targetSetDB> <output.tsv> <tmpDir> [flags]");
@@ -485,7 +519,20 @@ int modClustersearch(int argc, char **argv) {
     sd_cluster_params cp = clusterParams(a);
     t0 = nowMs();
     sd_target_index *idx = nullptr;
-    sdCheck(sd_target_index_build(ctx, tdb.residues.data(), tdb.off.data(), tdb.n(), &pp, &idx), "sd_target_index_build");
+    {   // a persisted index next to the target DB (`sdb200 createindex`, the counterpart of the reference's <db>.idx) is used when it
+        // was built with the same sensitivity / masking; otherwise the index is built now
+        const std::string idxFile = a.pos[1] + ".sdidx";
+        struct stat stIdx;
+        if ((int)a.num("--ignore-index", 0) == 0 && stat(idxFile.c_str(), &stIdx) == 0) {
+            if (sd_target_index_load(ctx, idxFile.c_str(), &pp, &idx) == SD_OK && sd_target_index_targets(idx) == tdb.n())
+                info("Loaded the persisted index %s\n", idxFile.c_str());
+            else {
+                info("Not using %s: %s\n", idxFile.c_str(), idx ? "it indexes another DB" : sd_last_error());
+                if (idx) { sd_target_index_destroy(idx); idx = nullptr; }
+            }
+        }
+    }
+    if (!idx) sdCheck(sd_target_index_build(ctx, tdb.residues.data(), tdb.off.data(), tdb.n(), &pp, &idx), "sd_target_index_build");
     sd_query_batch *batch = nullptr;
     std::vector<uint64_t> qOffBlock(qdb.off.begin() + qLo, qdb.off.begin() + qHi + 1);
     for (uint64_t &o : qOffBlock) o -= qdb.off[qLo];
@@ -608,11 +655,12 @@ int modMergedbs(int argc, char **argv);
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "sdb200 (libsdgpu %d): createsetdb | prefilter | align | clustersearch | summarizeresults | filterdb | swapdb | subtractdbs | mergedbs\n", sd_version());
+        fprintf(stderr, "sdb200 (libsdgpu %d): createsetdb | createindex | prefilter | align | clustersearch | summarizeresults | filterdb | swapdb | subtractdbs | mergedbs\n", sd_version());
         return EXIT_FAILURE;
     }
     const std::string mod = argv[1];
     if (mod == "createsetdb") return modCreatesetdb(argc, argv);
+    if (mod == "createindex") return modCreateindex(argc, argv);
     if (mod == "prefilter") return modPrefilter(argc, argv);
     if (mod == "align") return modAlign(argc, argv);
     if (mod == "clustersearch") return modClustersearch(argc, argv);

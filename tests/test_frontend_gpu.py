@@ -9,6 +9,7 @@ import shutil
 import subprocess
 import tempfile
 
+import numpy as np
 import pytest
 
 import helpers
@@ -97,3 +98,58 @@ def test_clustersearch_tsv_matches_reference_run():
         assert len(ref) > 20
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def test_modules_default_flags_match_reference(workdir):
+    """`prefilter` / `align` WITHOUT flags: the stand-alone modules start from the reference's module defaults (-s 4, -c 0, -e 0.001,
+    Parameters.cpp:2364-2425), not from the clustersearch workflow's (-s 5.7, -c 0.8 --cov-mode 2, -e 10)."""
+    if not helpers.have_ref():
+        pytest.skip("oracle/_ref/spacedust not built")
+    d = workdir
+    db = os.path.join(d, "setDB")
+    helpers.run_ref(["prefilter", db, db, os.path.join(d, "pref_ref_def"), "--threads", "2", "-v", "1"])
+    helpers.run_ref(["align", db, db, os.path.join(d, "pref_ref_def"), os.path.join(d, "res_ref_def"), "-a", "1", "--threads", "2", "-v", "1"])
+    _run(["prefilter", db, db, os.path.join(d, "pref_mine_def")])
+    _run(["align", db, db, os.path.join(d, "pref_mine_def"), os.path.join(d, "res_mine_def"), "-a", "1"])
+    assert helpers.read_db(os.path.join(d, "pref_mine_def")) == helpers.read_db(os.path.join(d, "pref_ref_def"))
+    ref = helpers.read_db(os.path.join(d, "res_ref_def"))
+    assert helpers.read_db(os.path.join(d, "res_mine_def")) == ref
+    assert sum(len(v) for v in ref.values()) > 300
+
+
+def test_persisted_index(gpu_ctx, synth_small, workdir):
+    """sd_target_index_save / _load (and `sdb200 createindex` + clustersearch picking <db>.sdidx up): same hits, same final TSV; a
+    file built with another sensitivity is refused."""
+    import spacedust_b200 as sd
+    buf, off, _ = synth.pack(synth_small)
+    pp = sd.default_prefilter_params(same_db=1, bin_size=2)
+    idx = sd.TargetIndex(gpu_ctx, buf, off, pp)
+    path = os.path.join(workdir, "index.bin")
+    try:
+        hits, st = sd.prefilter(gpu_ctx, idx, buf, off, pp)
+        idx.save(path, pp)
+    finally:
+        idx.close()
+    idx2 = sd.TargetIndex.load(gpu_ctx, path, pp)
+    try:
+        assert idx2.n == len(off) - 1 and idx2.entries > 0
+        hits2, st2 = sd.prefilter(gpu_ctx, idx2, buf, off, pp)
+    finally:
+        idx2.close()
+    assert len(hits) == len(hits2) > 0
+    for f in ("query", "target", "score", "diag"):
+        assert np.array_equal(hits[f], hits2[f]), f
+    for k in ("probes", "matches", "diag_residues", "hits"):
+        assert st[k] == st2[k], k
+    with pytest.raises(sd.SdError):
+        sd.TargetIndex.load(gpu_ctx, path, sd.default_prefilter_params(same_db=1, sensitivity=7.5))
+    # front-end: createindex, then clustersearch with and without the persisted index
+    d = workdir
+    db = os.path.join(d, "setDB")
+    _run(["createindex", db, os.path.join(d, "tmp_ix")])
+    assert os.path.exists(db + ".sdidx")
+    out_a, out_b = os.path.join(d, "ix_a.tsv"), os.path.join(d, "ix_b.tsv")
+    _run(["clustersearch", db, db, out_a, os.path.join(d, "tmp_ixa"), "--filter-self-match", "1"])
+    _run(["clustersearch", db, db, out_b, os.path.join(d, "tmp_ixb"), "--filter-self-match", "1", "--ignore-index", "1"])
+    assert open(out_a).read() == open(out_b).read() and open(out_a).read().count("#") > 5
+    os.remove(db + ".sdidx")
