@@ -11,9 +11,9 @@ One step = one pass of the hot path over the whole query batch.
   value  : target DB + k-mer index and the query batch already resident in HBM when the timed region starts
   e2e    : same step through the C ABI from pinned HOST buffers: target index build (upload, masking, index),
            query upload, all stages, results read back -- what `clustersearch` does after `createsetdb`
-Multi-GPU (--gpus N via torchrun): the target index is replicated, query SETS are split across ranks in contiguous
-residue-balanced blocks (spacedust_b200/shard.py); no collective inside the data path, ONE NCCL all_gather of the
-per-rank result lists (alignments, backtraces, clusters) per step so that every rank ends with the whole job's
+Multi-GPU (--gpus N via torchrun): the target index is replicated, query GENES are split across ranks in contiguous
+residue-balanced blocks for prefilter + align, an ncclAllGather inside libsdgpu.so merges the alignment lists, every rank
+clusters its block of query SETS, a second ncclAllGather merges the cluster lists, so that every rank ends with the whole job's
 result; total work fixed => "strong".
 
 `--impl reference` times the unmodified reference binary (oracle/_ref/spacedust, built by oracle/build_ref.py)
@@ -340,21 +340,17 @@ def run_ours(args, proteomes, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    if args.proteomes < world:
-        raise SystemExit("bench.py: %d query proteomes cannot be sharded over %d ranks (query sets are the sharding unit)" % (args.proteomes, world))
     buf, off, _ = synth.pack(proteomes)
     meta = synth.set_metadata(proteomes)
     n_total = len(off) - 1
-    # this rank's query sets: contiguous block of proteomes, balanced by residues
-    set_res = np.array([sum(len(s) for s in p["seqs"]) for p in proteomes])
-    s_lo, s_hi = sd.shard_partition(set_res, world)[rank]      # sd_shard_partition (C ABI)
-    sel = np.arange(*shard.query_block(meta["set_of"], s_lo, s_hi))
-    q_first = int(sel[0]) if len(sel) else 0
-    q_lo, q_hi = (int(off[sel[0]]), int(off[sel[-1] + 1])) if len(sel) else (0, 0)
-    qbuf = buf[q_lo:q_hi]
-    qoff = (off[sel[0]:sel[-1] + 2] - off[sel[0]]).astype(np.uint64) if len(sel) else np.zeros(1, dtype=np.uint64)
-    q_meta = {"set_of": meta["set_of"][sel], "pos": meta["pos"][sel], "strand": meta["strand"][sel], "set_size": meta["set_size"]}
-    nq_local = len(sel)
+    # this rank's query GENES: contiguous residue-balanced block (sd_shard_partition_genes, C ABI); the cluster stages, which need
+    # whole query sets, are re-partitioned inside the library after the first exchange (sd_shard_clustersearch_run)
+    g_lo, g_hi = sd.shard_partition_genes(off, world)[rank]
+    q_first = g_lo
+    qbuf = buf[int(off[g_lo]):int(off[g_hi])]
+    qoff = (off[g_lo:g_hi + 1] - off[g_lo]).astype(np.uint64)
+    q_meta = meta if world > 1 else {k: meta[k] for k in ("set_of", "pos", "strand", "set_size")}
+    nq_local = g_hi - g_lo
 
     # pinned host staging for the end-to-end arm
     t_pin = torch.from_numpy(buf.copy()).pin_memory()
@@ -385,7 +381,7 @@ def run_ours(args, proteomes, rank, world, local_rank):
         """One pass of the hot path over this rank's query block, results into pinned host memory; N>1: + the one
         ncclAllGather of the result lists inside the library (sd_shard_allgather_result: every rank ends with the whole job's
         lists in host memory, global query indices, single-GPU order)."""
-        return sd.clustersearch(ctx, index, queries, q_meta, meta, pp, ap, cp, q_first, out=exch, gather=world > 1)
+        return sd.clustersearch(ctx, index, queries, q_meta, meta, pp, ap, cp, q_first, out=exch, shard_genes=world > 1)
 
     # ---------------- resident arm
     idx = sd.TargetIndex(ctx, tbuf_h, off, pp)
@@ -502,10 +498,11 @@ def run_ours(args, proteomes, rank, world, local_rank):
         if world > 1:
             q_all = res["alns"]["query"]
             assert len(q_all) == 0 or (int(q_all.max()) < n_total and bool(np.all(np.diff(q_all.astype(np.int64)) >= 0)))
-            line["collective"] = {"op": "ncclAllGather (sizes, then padded blocks) of per-rank alignment/backtrace/cluster lists, issued by "
-                                        "libsdgpu.so (sd_shard_allgather_result, csrc/shard.cu)",
+            line["collective"] = {"op": "two ncclAllGather exchanges (sizes, then padded blocks) issued by libsdgpu.so (sd_shard_clustersearch_run, "
+                                        "csrc/fused.cu + csrc/shard.cu): alignment/backtrace lists after the align stage, cluster lists after clusterhits",
                                   "bytes_gathered_per_step": int(res["bytes_gathered"]),
-                                  "sharding": "query sets in contiguous residue-balanced blocks (sd_shard_partition); target index replicated"}
+                                  "sharding": "query genes in contiguous residue-balanced blocks for prefilter + align (sd_shard_partition_genes), "
+                                              "query sets balanced by alignments for besthitbyset/combinehits/clusterhits; target index replicated"}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(args, proteomes)

@@ -270,6 +270,27 @@ int sd_shard_partition(const uint64_t *set_residues, uint32_t n_sets, int world,
 int sd_shard_allgather_result(sd_context *ctx, const sd_search_result *mine, uint32_t query_first, sd_search_result **all,
                               uint64_t *bytes_gathered);
 
+
+/* Gene-granular sharding (the layout `sdb200 clustersearch --gpus N` and bench.py use): query GENES, not query sets, are the
+ * unit of the expensive stages, so a job with few large sets (20 proteomes over 8 GPUs) is still balanced.
+ * sd_shard_partition_genes: first_gene[world + 1], contiguous residue-balanced gene blocks (gene_off: n_genes + 1 offsets).
+ * sd_shard_clustersearch_run (after sd_shard_init; with world == 1 it equals sd_clustersearch_run):
+ *   1. prefilter + align of this rank's genes (`queries` = genes query_first .. query_first + nq - 1 of the job),
+ *   2. ncclAllGather of the alignment lists (every rank then holds all alignments in ascending gene order),
+ *   3. besthitbyset / combinehits / clusterhits for this rank's block of query SETS (blocks balanced by alignments; these stages
+ *      need all genes of a set: src/util/besthitbyset.cpp:41-144, ClusterHits.cpp:359-454),
+ *   4. ncclAllGather of the cluster lists.
+ * q_set_of / q_pos / q_strand describe ALL nq_total query genes of the job (sets in ascending contiguous blocks); the result is
+ * the whole job's, identical to a single-GPU run, and refers to the context's receive buffers like sd_shard_allgather_result. */
+int sd_shard_partition_genes(const uint64_t *gene_off, uint32_t n_genes, int world, uint32_t *first_gene);
+int sd_shard_clustersearch_run(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                               const sd_prefilter_params *ppar, const sd_align_params *apar, const sd_cluster_params *cpar,
+                               const uint32_t *q_set_of, const uint32_t *q_pos, const uint8_t *q_strand, uint32_t nq_total,
+                               const uint32_t *t_set_of, const uint32_t *t_pos, const uint8_t *t_strand, uint32_t nt,
+                               const uint32_t *q_set_size, uint32_t n_q_sets, const uint32_t *t_set_size, uint32_t n_t_sets,
+                               uint64_t db_residues, sd_search_result **out, sd_prefilter_stats *pst, sd_align_stats *ast,
+                               sd_cluster_stats *cst, uint64_t *bytes_gathered);
+
 #ifdef __cplusplus
 }
 #endif

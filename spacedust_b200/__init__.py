@@ -12,7 +12,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsdgpu.so")
+# SD_LIB_PATH: another build of the same library (variant builds for A/B measurements, csrc/Makefile)
+LIB_PATH = os.environ.get("SD_LIB_PATH") or os.path.join(_HERE, "libsdgpu.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 
@@ -390,8 +391,17 @@ def shard_partition(set_residues, world):
     return [(int(first[i]), int(first[i + 1])) for i in range(world)]
 
 
+def shard_partition_genes(gene_off, world):
+    """sd_shard_partition_genes: contiguous residue-balanced blocks of query genes -> [(lo, hi)] * world."""
+    o = np.ascontiguousarray(gene_off, dtype=np.uint64)
+    first = np.zeros(world + 1, dtype=np.uint32)
+    _check(lib().sd_shard_partition_genes(o.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint32(len(o) - 1), ctypes.c_int(world),
+                                          first.ctypes.data_as(ctypes.c_void_p)))
+    return [(int(first[i]), int(first[i + 1])) for i in range(world)]
+
+
 def clustersearch(ctx, index, batch, q_meta, t_meta, pref_params=None, aln_params=None, clu_params=None, query_first=0,
-                  db_residues=0, out=None, gather=False):
+                  db_residues=0, out=None, gather=False, shard_genes=False):
     """The hot path of `spacedust clustersearch` after createsetdb for one query batch, fused (sd_clustersearch_run):
     prefilter -> align -> besthitbyset/combinehits -> clusterhits with the prefilter hit list kept in HBM.
     out: optional object with carve(n_alns, pool_bytes, n_clusters, n_members) -> (alns, pool, clusters, members) arrays to
@@ -406,17 +416,29 @@ def clustersearch(ctx, index, batch, q_meta, t_meta, pref_params=None, aln_param
         return np.ascontiguousarray(x, dtype=dt)
     qs, qp, qst, qsz = arr(q_meta["set_of"], np.uint32), arr(q_meta["pos"], np.uint32), arr(q_meta["strand"], np.uint8), arr(q_meta["set_size"], np.uint32)
     ts, tp, tst, tsz = arr(t_meta["set_of"], np.uint32), arr(t_meta["pos"], np.uint32), arr(t_meta["strand"], np.uint8), arr(t_meta["set_size"], np.uint32)
-    assert len(qs) == batch.n and len(ts) == index.n
+    assert (shard_genes or len(qs) == batch.n) and len(ts) == index.n
     res = ctypes.c_void_p()
     pst, ast, cst = PrefilterStats(), AlignStats(), ClusterStats()
     p = ctypes.c_void_p
     L = lib()
-    _check(L.sd_clustersearch_run(ctx._h, index._h, batch._h, ctypes.c_uint32(query_first), ctypes.byref(pp), ctypes.byref(ap),
-                                  ctypes.byref(cp), qs.ctypes.data_as(p), qp.ctypes.data_as(p), qst.ctypes.data_as(p),
-                                  ts.ctypes.data_as(p), tp.ctypes.data_as(p), tst.ctypes.data_as(p), ctypes.c_uint32(len(ts)),
-                                  qsz.ctypes.data_as(p), ctypes.c_uint32(len(qsz)), tsz.ctypes.data_as(p), ctypes.c_uint32(len(tsz)),
-                                  ctypes.c_uint64(db_residues), ctypes.byref(res), ctypes.byref(pst), ctypes.byref(ast), ctypes.byref(cst)))
     gathered = ctypes.c_uint64(0)
+    if shard_genes:
+        # gene-sharded multi-GPU step (after shard_init): batch = this rank's genes query_first.., q_meta describes ALL query genes;
+        # both exchanges happen inside the library (sd_shard_clustersearch_run)
+        assert query_first + batch.n <= len(qs)
+        _check(L.sd_shard_clustersearch_run(ctx._h, index._h, batch._h, ctypes.c_uint32(query_first), ctypes.byref(pp), ctypes.byref(ap),
+                                            ctypes.byref(cp), qs.ctypes.data_as(p), qp.ctypes.data_as(p), qst.ctypes.data_as(p),
+                                            ctypes.c_uint32(len(qs)), ts.ctypes.data_as(p), tp.ctypes.data_as(p), tst.ctypes.data_as(p),
+                                            ctypes.c_uint32(len(ts)), qsz.ctypes.data_as(p), ctypes.c_uint32(len(qsz)),
+                                            tsz.ctypes.data_as(p), ctypes.c_uint32(len(tsz)), ctypes.c_uint64(db_residues),
+                                            ctypes.byref(res), ctypes.byref(pst), ctypes.byref(ast), ctypes.byref(cst), ctypes.byref(gathered)))
+        gather = False
+    else:
+        _check(L.sd_clustersearch_run(ctx._h, index._h, batch._h, ctypes.c_uint32(query_first), ctypes.byref(pp), ctypes.byref(ap),
+                                      ctypes.byref(cp), qs.ctypes.data_as(p), qp.ctypes.data_as(p), qst.ctypes.data_as(p),
+                                      ts.ctypes.data_as(p), tp.ctypes.data_as(p), tst.ctypes.data_as(p), ctypes.c_uint32(len(ts)),
+                                      qsz.ctypes.data_as(p), ctypes.c_uint32(len(qsz)), tsz.ctypes.data_as(p), ctypes.c_uint32(len(tsz)),
+                                      ctypes.c_uint64(db_residues), ctypes.byref(res), ctypes.byref(pst), ctypes.byref(ast), ctypes.byref(cst)))
     if gather:
         merged = ctypes.c_void_p()
         try:

@@ -1,4 +1,5 @@
 // C ABI plumbing of libsdgpu.so: error slot, context life cycle.
+#include <cstdlib>
 #include <memory>
 #include "sd_internal.h"
 

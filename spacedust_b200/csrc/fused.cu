@@ -28,6 +28,7 @@ struct ChunkResult {
     const sd_cluster_member *vMembers = nullptr;
     uint64_t vNa = 0, vNp = 0, vNc = 0, vNm = 0;
     bool view = false;
+    bool membersGlobal = false;          // member.aln already indexes the merged alignment array (gene-sharded step)
     uint64_t nAlns() const { return view ? vNa : alns.size(); }
     uint64_t nPool() const { return view ? vNp : pool.size(); }
     uint64_t nClusters() const { return view ? vNc : clusters.size(); }
@@ -48,14 +49,17 @@ struct sd_search_result {
     std::vector<ChunkResult> chunks;     // ascending query sets
 };
 
-extern "C" int sd_clustersearch_run(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
-                                    const sd_prefilter_params *ppar, const sd_align_params *apar, const sd_cluster_params *cpar,
-                                    const uint32_t *q_set_of, const uint32_t *q_pos, const uint8_t *q_strand,
-                                    const uint32_t *t_set_of, const uint32_t *t_pos, const uint8_t *t_strand, uint32_t nt,
-                                    const uint32_t *q_set_size, uint32_t n_q_sets, const uint32_t *t_set_size, uint32_t n_t_sets,
-                                    uint64_t db_residues, sd_search_result **out, sd_prefilter_stats *pst, sd_align_stats *ast,
-                                    sd_cluster_stats *cst) {
-    if (!ctx || !idx || !queries || !ppar || !apar || !cpar || !out || !q_set_of) { sd::setError("sd_clustersearch_run: bad argument"); return SD_EINVAL; }
+// cpar == nullptr: prefilter + align only (the gene-sharded multi-GPU step clusters after its first exchange); chunks are then cut
+// at any query, not at set boundaries, and q_* / *_set_size are not read.
+static int searchCore(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                      const sd_prefilter_params *ppar, const sd_align_params *apar, const sd_cluster_params *cpar,
+                      const uint32_t *q_set_of, const uint32_t *q_pos, const uint8_t *q_strand,
+                      const uint32_t *t_set_of, const uint32_t *t_pos, const uint8_t *t_strand, uint32_t nt,
+                      const uint32_t *q_set_size, uint32_t n_q_sets, const uint32_t *t_set_size, uint32_t n_t_sets,
+                      uint64_t db_residues, sd_search_result **out, sd_prefilter_stats *pst, sd_align_stats *ast,
+                      sd_cluster_stats *cst) {
+    const bool doCluster = cpar != nullptr;
+    if (!ctx || !idx || !queries || !ppar || !apar || !out || (doCluster && !q_set_of)) { sd::setError("sd_clustersearch_run: bad argument"); return SD_EINVAL; }
     *out = nullptr;
     if (ast) memset(ast, 0, sizeof *ast);
     if (cst) memset(cst, 0, sizeof *cst);
@@ -74,7 +78,9 @@ extern "C" int sd_clustersearch_run(sd_context *ctx, const sd_target_index *idx,
         bool contiguous = true;
         std::vector<uint32_t> setStart;                     // first query of every run of equal set ids
         for (uint32_t q = 0; q < nq; q++)
-            if (q == 0 || q_set_of[q] != q_set_of[q - 1]) {
+            if (!doCluster) {
+                if ((q & 63u) == 0) setStart.push_back(q);                       // align only: any query may open a chunk
+            } else if (q == 0 || q_set_of[q] != q_set_of[q - 1]) {
                 if (q > 0 && q_set_of[q] < q_set_of[q - 1]) contiguous = false;   // sets must come in ascending blocks
                 setStart.push_back(q);
             }
@@ -115,7 +121,7 @@ extern "C" int sd_clustersearch_run(sd_context *ctx, const sd_target_index *idx,
             memset(&cr.cst, 0, sizeof cr.cst);
             const uint64_t lo = hitOff[cut[k]], hi = hitOff[cut[k + 1]];
             int rc2 = sd_align_device_hits(c, idx, queries, query_first, dHits.p + lo, hi - lo, db_residues, apar, cr.alns, cr.pool, &cr.ast);
-            if (rc2 == SD_OK) {
+            if (rc2 == SD_OK && doCluster) {
                 uint64_t nC = 0, nM = 0;
                 cr.clusters.resize(cr.alns.size() / 2 + 1);
                 cr.members.resize(cr.alns.size() + 1);
@@ -162,6 +168,117 @@ extern "C" int sd_clustersearch_run(sd_context *ctx, const sd_target_index *idx,
     return SD_OK;
 }
 
+extern "C" int sd_clustersearch_run(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                                    const sd_prefilter_params *ppar, const sd_align_params *apar, const sd_cluster_params *cpar,
+                                    const uint32_t *q_set_of, const uint32_t *q_pos, const uint8_t *q_strand,
+                                    const uint32_t *t_set_of, const uint32_t *t_pos, const uint8_t *t_strand, uint32_t nt,
+                                    const uint32_t *q_set_size, uint32_t n_q_sets, const uint32_t *t_set_size, uint32_t n_t_sets,
+                                    uint64_t db_residues, sd_search_result **out, sd_prefilter_stats *pst, sd_align_stats *ast,
+                                    sd_cluster_stats *cst) {
+    if (!cpar) { sd::setError("sd_clustersearch_run: bad argument"); return SD_EINVAL; }
+    return searchCore(ctx, idx, queries, query_first, ppar, apar, cpar, q_set_of, q_pos, q_strand, t_set_of, t_pos, t_strand, nt,
+                      q_set_size, n_q_sets, t_set_size, n_t_sets, db_residues, out, pst, ast, cst);
+}
+
+// Multi-GPU step with gene-granular sharding (see include/sdgpu.h).  Query genes, not query sets, are the unit of the expensive
+// stages: with few large sets (20 proteomes over 8 GPUs) whole-set blocks leave a 3-vs-2 imbalance, gene blocks do not.
+//   1. prefilter + align of this rank's genes [query_first, query_first + nq)           (searchCore without the cluster stage)
+//   2. ncclAllGather #1: alignments + CIGAR pools -> every rank holds all alignments, ascending genes
+//   3. besthitbyset / combinehits / clusterhits for this rank's block of query SETS (blocks balanced by alignment count;
+//      those stages need every gene of a set and every alignment of it, src/util/besthitbyset.cpp:41-144)
+//   4. ncclAllGather #2: clusters + members (member.aln already indexes the merged alignment array)
+extern "C" int sd_shard_clustersearch_run(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
+                                          const sd_prefilter_params *ppar, const sd_align_params *apar, const sd_cluster_params *cpar,
+                                          const uint32_t *q_set_of, const uint32_t *q_pos, const uint8_t *q_strand, uint32_t nq_total,
+                                          const uint32_t *t_set_of, const uint32_t *t_pos, const uint8_t *t_strand, uint32_t nt,
+                                          const uint32_t *q_set_size, uint32_t n_q_sets, const uint32_t *t_set_size, uint32_t n_t_sets,
+                                          uint64_t db_residues, sd_search_result **out, sd_prefilter_stats *pst, sd_align_stats *ast,
+                                          sd_cluster_stats *cst, uint64_t *bytes_gathered) {
+    if (!ctx || !queries || !cpar || !q_set_of || !out) { sd::setError("sd_shard_clustersearch_run: bad argument"); return SD_EINVAL; }
+    *out = nullptr;
+    if (bytes_gathered) *bytes_gathered = 0;
+    if (cst) memset(cst, 0, sizeof *cst);
+    if ((uint64_t)query_first + queries->nq > nq_total) { sd::setError("sd_shard_clustersearch_run: gene block %u + %u exceeds %u query genes", query_first, queries->nq, nq_total); return SD_EINVAL; }
+    const int world = ctx->world, rank = ctx->rank;
+    // 1
+    sd_search_result *mineRaw = nullptr;
+    int rc = searchCore(ctx, idx, queries, query_first, ppar, apar, nullptr, nullptr, nullptr, nullptr, t_set_of, t_pos, t_strand, nt,
+                        nullptr, 0, t_set_size, n_t_sets, db_residues, &mineRaw, pst, ast, nullptr);
+    if (rc) return rc;
+    std::unique_ptr<sd_search_result> mine(mineRaw);
+    // 2
+    sd_search_result *allRaw = nullptr;
+    uint64_t bytes1 = 0, bytes2 = 0;
+    if ((rc = sd::shardAllgather(ctx, mine.get(), query_first, 1, &allRaw, &bytes1))) return rc;
+    std::unique_ptr<sd_search_result> all(allRaw);
+    mine.reset();
+    // 3: alignments per query set (every rank computes the same partition from the same merged list)
+    std::vector<uint64_t> setAlns(n_q_sets, 0), chunkBase(all->chunks.size() + 1, 0);
+    for (size_t k = 0; k < all->chunks.size(); k++) chunkBase[k + 1] = chunkBase[k] + all->chunks[k].nAlns();
+    const uint64_t nAll = chunkBase.back();
+    {
+        const unsigned nPart = 32;
+        std::vector<std::vector<uint64_t>> part(nPart, std::vector<uint64_t>(n_q_sets, 0));
+        for (const ChunkResult &cr : all->chunks) {
+            const sd_alignment *a = cr.pAlns();
+            sd::parallelChunks(cr.nAlns(), nPart, [&](unsigned c, uint64_t lo, uint64_t hi) {
+                for (uint64_t i = lo; i < hi; i++) {
+                    if (a[i].query < nq_total) part[c][q_set_of[a[i].query]]++;
+                }
+            });
+        }
+        for (unsigned c = 0; c < nPart; c++)
+            for (uint32_t sIdx = 0; sIdx < n_q_sets; sIdx++) setAlns[sIdx] += part[c][sIdx];
+    }
+    std::vector<uint64_t> weight(n_q_sets);
+    for (uint32_t sIdx = 0; sIdx < n_q_sets; sIdx++) weight[sIdx] = setAlns[sIdx] + 1;
+    std::vector<uint32_t> firstSet((size_t)world + 1);
+    if ((rc = sd_shard_partition(weight.data(), n_q_sets, world, firstSet.data()))) return rc;
+    uint64_t a0 = 0, a1 = 0;
+    for (uint32_t sIdx = 0; sIdx < firstSet[rank]; sIdx++) a0 += setAlns[sIdx];
+    a1 = a0;
+    for (uint32_t sIdx = firstSet[rank]; sIdx < firstSet[rank + 1]; sIdx++) a1 += setAlns[sIdx];
+    if (a1 > nAll) { sd::setError("sd_shard_clustersearch_run: query sets are not contiguous ascending blocks of genes"); return SD_EINVAL; }
+    std::unique_ptr<sd_search_result> mineC(new sd_search_result());
+    mineC->chunks.resize(1);
+    ChunkResult &cc = mineC->chunks[0];
+    memset(&cc.ast, 0, sizeof cc.ast);
+    memset(&cc.cst, 0, sizeof cc.cst);
+    {
+        std::vector<sd_alignment> myAlns(a1 - a0);
+        for (size_t k = 0; k < all->chunks.size(); k++) {       // the range may span several rank blocks
+            const uint64_t lo = std::max(a0, chunkBase[k]), hi = std::min(a1, chunkBase[k + 1]);
+            if (lo >= hi) continue;
+            const sd_alignment *src = all->chunks[k].pAlns() + (lo - chunkBase[k]);
+            sd_alignment *dst = myAlns.data() + (lo - a0);
+            sd::parallelChunks(hi - lo, 32, [&](unsigned, uint64_t l, uint64_t h) { memcpy(dst + l, src + l, (h - l) * sizeof(sd_alignment)); });
+        }
+        for (uint64_t i = 0; i < myAlns.size(); i += std::max<uint64_t>(1, myAlns.size() - 1)) {     // first and last belong to this rank's sets
+            const uint32_t sIdx = q_set_of[myAlns[i].query];
+            if (sIdx < firstSet[rank] || sIdx >= firstSet[rank + 1]) { sd::setError("sd_shard_clustersearch_run: query sets are not contiguous ascending blocks of genes"); return SD_EINVAL; }
+        }
+        uint64_t nC = 0, nM = 0;
+        cc.clusters.resize(myAlns.size() / 2 + 1);
+        cc.members.resize(myAlns.size() + 1);
+        rc = sd_cluster_run(ctx, myAlns.data(), myAlns.size(), q_set_of, q_pos, q_strand, nq_total, t_set_of, t_pos, t_strand, nt, q_set_size, n_q_sets,
+                            t_set_size, n_t_sets, cpar, cc.clusters.data(), cc.clusters.size(), &nC, cc.members.data(), cc.members.size(), &nM, &cc.cst);
+        if (rc) return rc;
+        cc.clusters.resize(nC);
+        cc.members.resize(nM);
+        sd_cluster_member *m = cc.members.data();
+        sd::parallelFor(nM, [&](uint64_t i) { m[i].aln += (uint32_t)a0; });
+        if (cst) *cst = cc.cst;
+    }
+    // 4
+    sd_search_result *allCRaw = nullptr;
+    if ((rc = sd::shardAllgather(ctx, mineC.get(), 0, 3, &allCRaw, &bytes2))) return rc;
+    std::unique_ptr<sd_search_result> allC(allCRaw);
+    for (ChunkResult &cr : allC->chunks) { cr.membersGlobal = true; all->chunks.push_back(std::move(cr)); }
+    if (bytes_gathered) *bytes_gathered = bytes1 + bytes2;
+    *out = all.release();
+    return SD_OK;
+}
+
 extern "C" void sd_search_result_sizes(const sd_search_result *r, uint64_t *n_alns, uint64_t *pool_bytes, uint64_t *n_clusters, uint64_t *n_members) {
     uint64_t a = 0, p = 0, c = 0, m = 0;
     if (r)
@@ -197,7 +314,8 @@ extern "C" int sd_search_result_copy(const sd_search_result *r, sd_alignment *al
         if (members && nm) {
             sd_cluster_member *dst = members + m0;
             const sd_cluster_member *src = cr.pMembers();
-            sd::parallelFor(nm, [&](uint64_t i) { dst[i] = src[i]; dst[i].aln += (uint32_t)a0; });
+            const uint32_t rebase = cr.membersGlobal ? 0u : (uint32_t)a0;
+            sd::parallelFor(nm, [&](uint64_t i) { dst[i] = src[i]; dst[i].aln += rebase; });
         }
         a0 += na; p0 += np; c0 += nc; m0 += nm;
     }

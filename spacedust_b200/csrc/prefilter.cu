@@ -89,7 +89,7 @@ __global__ void extractTargetKmers(const uint8_t *__restrict__ res, const uint32
     uint32_t L = off[s + 1] - off[s];
     uint64_t key = ~0ull;
     if (p + SPAN <= L && p < 65536u) {
-        uint32_t idx = 0, mul = 1;
+        uint32_t half[2] = {0, 0}, mul = 1;
         int self = 0;
         bool ok = true;
 #pragma unroll
@@ -97,9 +97,10 @@ __global__ void extractTargetKmers(const uint8_t *__restrict__ res, const uint32
             uint8_t c = res[gp + c_seedPos[k]];
             ok = ok && (c < 20);
             self += selfScore[c];
-            idx += (uint32_t)c * mul;
-            mul *= 20;
+            half[k / 3] += (uint32_t)c * mul;
+            mul = (k == 2) ? 1 : mul * 20;
         }
+        const uint32_t idx = kmerSlot(half[0], half[1]);
         if (ok && !(kmerThr > 0 && self < kmerThr)) key = ((uint64_t)s << 42) | ((uint64_t)idx << 16) | p;
     }
     keys[gp] = key;
@@ -592,7 +593,28 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
         sa.resT = sResT.p; sa.resScore = sResScore.p; sa.resDiag = sResDiag.p;
         sa.out = dOut.p; sa.outCount = dOutCount.p; sa.stats = dStats.p; sa.nextQuery = dNext.p; sa.errQuery = dNext.p + 1;
         sa.failList = dFail.p; sa.nFail = dNext.p + 2;
-        sa.evictFirst = 0; sa.prefetch = 0; sa.debugSkip = 0;
+        // profiling switches (results with SD_PF_SKIP are wrong): L2 policy of the streamed data, prefetches, dropped stages
+        sa.evictFirst = getenv("SD_PS_EVICT") ? atoi(getenv("SD_PS_EVICT")) : 0;
+        sa.prefetch = getenv("SD_PS_PREFETCH") ? atoi(getenv("SD_PS_PREFETCH")) : 0;
+        sa.debugSkip = getenv("SD_PF_SKIP") ? atoi(getenv("SD_PF_SKIP")) : 0;
+        const int persistS = getenv("SD_PS_PERSIST") ? atoi(getenv("SD_PS_PERSIST")) : 0;
+        if (persistS) {
+            int maxPersist = 0, maxWin = 0;
+            cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+            cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+            const size_t bmBytes = idx->bm.n * sizeof(uint2);
+            if (getenv("SD_PF_DEBUG")) fprintf(stderr, "[sd] persisting L2: max %d bytes, window max %d bytes, bitmap %zu bytes\n", maxPersist, maxWin, bmBytes);
+            if (maxPersist > 0 && maxWin > 0) {
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>((size_t)maxPersist, (size_t)persistS << 20));
+                cudaStreamAttrValue av{};
+                av.accessPolicyWindow.base_ptr = (void *)idx->bm.p;
+                av.accessPolicyWindow.num_bytes = std::min<size_t>(bmBytes, (size_t)maxWin);
+                av.accessPolicyWindow.hitRatio = 1.0f;
+                av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+                cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+            }
+        }
         SD_CUDA(cudaFuncSetAttribute(prefilterStreamKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_DYN_SMEM));
         if (getenv("SD_PF_DEBUG")) fprintf(stderr, "[sd] prefilter: streaming kernel, %u CTAs x %d warps, candidate lists %u\n", nCtaS, PS_WARPS, candCapS);
         if (sa.nQ) {
@@ -858,7 +880,7 @@ extern "C" int sd_prefilter_run_batch(sd_context *ctx, const sd_target_index *id
 // ------------------------------------------------------------------------------------------------
 namespace {
 struct IndexFileHeader {
-    char magic[8];             // "SDGPUIX2"
+    char magic[8];             // "SDGPUIX3"
     uint32_t version, nT;
     uint64_t totalRes, nEntries, masked;
     int32_t kmerThr;
@@ -875,8 +897,8 @@ extern "C" int sd_target_index_save(const sd_target_index *idx, const sd_prefilt
     FILE *f = fopen(path, "wb");
     if (!f) { setError("cannot write %s", path); return SD_EINVAL; }
     IndexFileHeader h{};
-    memcpy(h.magic, "SDGPUIX2", 8);
-    h.version = 2; h.nT = idx->nT; h.totalRes = idx->totalRes; h.nEntries = idx->nEntries; h.masked = idx->masked;
+    memcpy(h.magic, "SDGPUIX3", 8);
+    h.version = 3 + SD_KMER_LAYOUT; h.nT = idx->nT; h.totalRes = idx->totalRes; h.nEntries = idx->nEntries; h.masked = idx->masked;
     h.kmerThr = idx->kmerThr; h.maxLen = idx->maxLen; h.nDistinct = idx->nDistinct; h.bmWords = (uint32_t)idx->bm.n;
     h.sensitivity = par->sensitivity; h.maskProb = par->mask_prob; h.mask = par->mask;
     bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(idx->hostOff.data(), sizeof(uint32_t), (size_t)idx->nT + 1, f) == (size_t)idx->nT + 1;
@@ -901,7 +923,7 @@ extern "C" int sd_target_index_load(sd_context *ctx, const char *path, const sd_
     if (!f) { setError("cannot read %s", path); return SD_EINVAL; }
     std::unique_ptr<FILE, int (*)(FILE *)> closer(f, fclose);
     IndexFileHeader h;
-    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "SDGPUIX2", 8) != 0 || h.version != 2) { setError("%s is not a libsdgpu index file (version 2)", path); return SD_EINVAL; }
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "SDGPUIX3", 8) != 0 || h.version != 3 + SD_KMER_LAYOUT) { setError("%s is not a libsdgpu index file (version 3)", path); return SD_EINVAL; }
     // the index depends on the sensitivity (k-mer threshold) and on the masking parameters: refuse a file built with others
     if (h.kmerThr != kmerThreshold(par->sensitivity, KMER) || h.mask != par->mask || (par->mask && h.maskProb != par->mask_prob)) {
         setError("%s was built with -s %g --mask %d --mask-prob %g; the search asks for -s %g --mask %d --mask-prob %g", path, h.sensitivity, h.mask,

@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(PF_THREADS, 3) prefilterKernel(PrefilterArgs a
                     nRows = info.y >> 16; nBig = info.z & 0xffffu; nHead = info.z >> 16;
                     row1 = a.e3pair + (size_t)(info.x & 0xffffu) * N3;
                     row2 = a.e3pair + (size_t)i2 * N3;
-                    x2top = N3 * (top2w >> 16);
+                    x2top = top2w >> 16;
                     a0 = 0;
                     mode = nHead ? M_HEAD : M_TAIL;
                     continue;
@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(PF_THREADS, 3) prefilterKernel(PrefilterArgs a
 #pragma unroll
                     for (int j = 0; j < PF_UNROLL; j++) {
                         const uint32_t c = c0 + 32u * j + lane;
-                        if (c < nbb) kmerW[j] = xb + N3 * (__ldg(&row2[c]) >> 16);
+                        if (c < nbb) kmerW[j] = kmerSlot(xb, __ldg(&row2[c]) >> 16);
                     }
                     nSteps = (min(nbb - c0, 32u * PF_UNROLL) + 31u) / 32u;
                     c0 += 32 * PF_UNROLL;
@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(PF_THREADS, 3) prefilterKernel(PrefilterArgs a
                             const uint32_t owner = warpOwnerOfSlot(dExcl, nb != 0, base, lane);
                             const uint32_t oExcl = __shfl_sync(0xffffffffu, dExcl, owner);
                             const uint32_t oRow = __shfl_sync(0xffffffffu, dRow, owner);
-                            if (base + lane < dTotal) kmerW[j] = (oRow & 0xffffu) + N3 * (__ldg(&row2[base + lane - oExcl]) >> 16);   // KmerGenerator.cpp:207
+                            if (base + lane < dTotal) kmerW[j] = kmerSlot(oRow & 0xffffu, __ldg(&row2[base + lane - oExcl]) >> 16);   // KmerGenerator.cpp:207
                         }
                     }
                     nSteps = (min(dTotal - pc, 32u * PF_UNROLL) + 31u) / 32u;
@@ -698,7 +698,7 @@ __global__ void __launch_bounds__(PF_THREADS, 3) prefilterKernel(PrefilterArgs a
 #pragma unroll
                     for (int j = 0; j < PF_UNROLL; j++) {
                         const uint32_t ai = a0 + 32u * j + lane;
-                        if (ai < nRows) kmerW[j] = (__ldg(&row1[ai]) >> 16) + x2top;
+                        if (ai < nRows) kmerW[j] = kmerSlot(__ldg(&row1[ai]) >> 16, x2top);
                     }
                     nSteps = (min(nRows - a0, 32u * PF_UNROLL) + 31u) / 32u;
                     a0 += 32 * PF_UNROLL;

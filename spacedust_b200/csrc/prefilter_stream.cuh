@@ -97,7 +97,7 @@ struct StreamArgs {
     uint32_t *nFail;
     int evictFirst;            // L2 evict-first policy for the streamed data
     int prefetch;              // bit 0: table words, bit 1: bucket rows
-    int debugSkip;             // profiling only (SD_PF_SKIP): bit 0 drops stage C, bit 1 drops stage B -- results are then wrong
+    int debugSkip;             // profiling only (SD_PF_SKIP): bit 0 drops stage C, bit 1 drops stage B, bit 2 drops the bitmap loads -- results are then wrong
 };
 
 
@@ -393,8 +393,8 @@ __global__ void __launch_bounds__(PS_WARPS * 32, 4) prefilterStreamKernel(Stream
                                 if (base + lane < totalProbes) {
                                     const uint32_t c = base + lane - ownerExcl;
                                     const uint32_t xc = (c < (uint32_t)PS_CAP2) ? (uint32_t)X2[c] : (__ldg(&x2[c]) >> 16);
-                                    kmerW[j] = ownerX + N3 * xc;            // KmerGenerator.cpp:207
-                                    const uint2 wv = __ldg(&a.bm[kmerW[j] >> 5]);
+                                    kmerW[j] = kmerSlot(ownerX, xc);            // KmerGenerator.cpp:207
+                                    const uint2 wv = (a.debugSkip & 4) ? make_uint2(kmerW[j] * 2654435761u & 0x11111111u, 0u) : __ldg(&a.bm[kmerW[j] >> 5]);
                                     w[j] = wv.x;
                                     rk[j] = wv.y;
                                 }

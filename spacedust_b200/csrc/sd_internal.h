@@ -38,6 +38,21 @@ constexpr int SPAN = 10;                 // spaced seed 1101010011 (Sequence.h:2
 constexpr uint32_t N3 = 8000;            // 20^3
 constexpr uint32_t NKMER = 64000000;     // 20^6
 
+// Place of a k-mer in the occupancy bitmap and the row table.  The reference numbers a k-mer first3 + 8000 * second3
+// (Indexer.h); the similar-k-mer stream varies the SECOND 3-mer fastest (KmerGenerator.cpp:201-207), so with the reference
+// numbering successive probes of a query position land 1000 bytes apart in the bitmap.  Layout 1 stores k-mer
+// (first3, second3) at first3 * 8000 + second3: all partners of one first-row neighbour fall into one 1000-byte window of
+// the bitmap (8 cache lines), so a probe step of 32 lanes touches a few lines instead of 32 sectors.  Only the storage
+// order of the buckets changes (stream order is the probe order), results are identical.
+#ifndef SD_KMER_LAYOUT
+#define SD_KMER_LAYOUT 1
+#endif
+#ifdef __CUDACC__
+__host__ __device__ __forceinline__ uint32_t kmerSlot(uint32_t first3, uint32_t second3) {
+    return SD_KMER_LAYOUT ? first3 * N3 + second3 : first3 + N3 * second3;
+}
+#endif
+
 // Stream-ordered allocations: entry points set the calling context's stream (StreamScope); buffers then come from
 // the device's default memory pool (cudaMallocAsync), which keeps freed blocks for reuse -- no cudaMalloc/cudaFree
 // round trips in steady state.
@@ -255,6 +270,9 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
                       sd_prefilter_stats *stats, sd::DevBuf<sd_prefilter_hit> *keepOnDevice, std::vector<uint64_t> *hitOffsets = nullptr);
 // merged result of an exchange: one chunk per rank block ([4 x u64 counts][alns][pool][clusters][members], 16-byte aligned parts);
 // the chunks are VIEWS into `blocks` (the context's pinned receive buffer), valid until the next exchange on that context
+namespace sd {
+int shardAllgather(sd_context *ctx, const sd_search_result *mine, uint32_t query_first, int pinSlot, sd_search_result **all, uint64_t *bytes_gathered);
+}
 int sd_search_result_from_blocks(const char *blocks, uint64_t stride, const uint64_t *sizes, int n, sd_search_result **out);
 int sd_align_device_pairs(sd_context *ctx, const sd_target_index *idx, const sd_query_batch *queries, uint32_t query_first,
                           const uint32_t *dPairQ, const uint32_t *dPairT, uint64_t n_pairs, uint64_t db_residues,

@@ -437,8 +437,8 @@ int modClustersearch(int argc, char **argv) {
          tdb.setKey.size(), nowMs() - t0);
 
     // ---- multi-GPU (--gpus N): one process per GPU.  The parent starts N copies of itself (--rank r); rank 0 creates the NCCL id and
-    // hands it over through a file in the tmp dir; every rank searches its block of query sets against the whole target index and
-    // ONE ncclAllGather inside libsdgpu.so (sd_shard_allgather_result) gives every rank the whole result; rank 0 writes it.
+    // hands it over through a file in the tmp dir; every rank searches its block of query genes against the whole target index, the
+    // ncclAllGather exchanges inside libsdgpu.so (sd_shard_clustersearch_run) give every rank the whole result; rank 0 writes it.
     const int nGpus = std::max(1, (int)a.num("--gpus", 1));
     const int rank = (int)a.num("--rank", -1);
     if (nGpus > 1 && rank < 0) {
@@ -501,18 +501,14 @@ int modClustersearch(int argc, char **argv) {
             }
         }
         sdCheck(sd_shard_init(ctx, myRank, world, id), "sd_shard_init");
-        // this rank's block of query sets (sets are contiguous in the DB order createsetdb writes)
-        std::vector<uint64_t> setRes(qdb.setSize.size(), 0);
-        for (uint32_t g = 0; g < qdb.n(); g++) setRes[qdb.setOf[g]] += qdb.off[g + 1] - qdb.off[g];
+        // this rank's block of query genes (prefilter + align); the set-wise stages are re-partitioned inside the library after the
+        // first exchange (sd_shard_clustersearch_run)
+        for (uint32_t g = 1; g < qdb.n(); g++)
+            if (qdb.setOf[g] < qdb.setOf[g - 1]) die("query sets are not contiguous ascending blocks in the set DB");
         std::vector<uint32_t> first((size_t)world + 1);
-        sdCheck(sd_shard_partition(setRes.data(), (uint32_t)setRes.size(), world, first.data()), "sd_shard_partition");
-        qLo = qdb.n(); qHi = 0;
-        for (uint32_t g = 0; g < qdb.n(); g++)
-            if (qdb.setOf[g] >= first[myRank] && qdb.setOf[g] < first[myRank + 1]) { qLo = std::min(qLo, g); qHi = std::max(qHi, g + 1); }
-        if (qHi < qLo) { qLo = 0; qHi = 0; }
-        for (uint32_t g = qLo; g < qHi; g++)
-            if (qdb.setOf[g] < first[myRank] || qdb.setOf[g] >= first[myRank + 1]) die("query sets are not contiguous in the set DB");
-        info("rank %d of %d: query sets %u..%u, genes %u..%u\n", myRank, world, first[myRank], first[myRank + 1], qLo, qHi);
+        sdCheck(sd_shard_partition_genes(qdb.off.data(), qdb.n(), world, first.data()), "sd_shard_partition_genes");
+        qLo = first[myRank]; qHi = first[myRank + 1];
+        info("rank %d of %d: query genes %u..%u\n", myRank, world, qLo, qHi);
     }
     sd_prefilter_params pp = prefParams(a, same);
     sd_align_params ap = alignParams(a, same);
@@ -545,17 +541,14 @@ int modClustersearch(int argc, char **argv) {
     sd_cluster_stats cst;
     memset(&pst, 0, sizeof pst);
     // same DB: the identity hit of query gene g is target g = qLo + index in the block
-    sdCheck(sd_clustersearch_run(ctx, idx, batch, qLo, &pp, &ap, &cp, qdb.setOf.data() + qLo, qdb.genePos.data() + qLo, qdb.strand.data() + qLo,
-                                 tdb.setOf.data(), tdb.genePos.data(), tdb.strand.data(), tdb.n(), qdb.setSize.data(),
-                                 (uint32_t)qdb.setSize.size(), tdb.setSize.data(), (uint32_t)tdb.setSize.size(), 0, &res, &pst, &ast, &cst),
-            "sd_clustersearch_run");
     if (world > 1) {
-        sd_search_result *all = nullptr;
         uint64_t gathered = 0;
-        sdCheck(sd_shard_allgather_result(ctx, res, qLo, &all, &gathered), "sd_shard_allgather_result");
-        sd_search_result_destroy(res);
-        res = all;
-        info("all-gather of the result lists: %.1f MB over NCCL\n", gathered / 1e6);
+        sdCheck(sd_shard_clustersearch_run(ctx, idx, batch, qLo, &pp, &ap, &cp, qdb.setOf.data(), qdb.genePos.data(), qdb.strand.data(), qdb.n(),
+                                           tdb.setOf.data(), tdb.genePos.data(), tdb.strand.data(), tdb.n(), qdb.setSize.data(),
+                                           (uint32_t)qdb.setSize.size(), tdb.setSize.data(), (uint32_t)tdb.setSize.size(), 0, &res, &pst, &ast, &cst,
+                                           &gathered),
+                "sd_shard_clustersearch_run");
+        info("all-gathers of the alignment and cluster lists: %.1f MB over NCCL\n", gathered / 1e6);
         if (myRank != 0) {      // every rank holds the whole result now; rank 0 writes it
             sd_search_result_destroy(res);
             sd_query_batch_destroy(batch);
@@ -563,6 +556,11 @@ int modClustersearch(int argc, char **argv) {
             sd_context_destroy(ctx);
             return EXIT_SUCCESS;
         }
+    } else {
+        sdCheck(sd_clustersearch_run(ctx, idx, batch, qLo, &pp, &ap, &cp, qdb.setOf.data() + qLo, qdb.genePos.data() + qLo, qdb.strand.data() + qLo,
+                                     tdb.setOf.data(), tdb.genePos.data(), tdb.strand.data(), tdb.n(), qdb.setSize.data(),
+                                     (uint32_t)qdb.setSize.size(), tdb.setSize.data(), (uint32_t)tdb.setSize.size(), 0, &res, &pst, &ast, &cst),
+                "sd_clustersearch_run");
     }
     uint64_t nA = 0, nPool = 0, nC = 0, nM = 0;
     sd_search_result_sizes(res, &nA, &nPool, &nC, &nM);

@@ -133,11 +133,34 @@ extern "C" int sd_shard_partition(const uint64_t *set_residues, uint32_t n_sets,
     return SD_OK;
 }
 
+// Contiguous blocks of query GENES with about equal residues (gene_off: n_genes + 1 residue offsets): rank r owns genes
+// first_gene[r] .. first_gene[r+1]-1.  The unit of the prefilter and align stages of sd_shard_clustersearch_run.
+extern "C" int sd_shard_partition_genes(const uint64_t *gene_off, uint32_t n_genes, int world, uint32_t *first_gene) {
+    if (!gene_off || !first_gene || world < 1) { sd::setError("sd_shard_partition_genes: bad argument"); return SD_EINVAL; }
+    const uint64_t base = gene_off[0], total = gene_off[n_genes] - base;
+    first_gene[0] = 0;
+    for (int r = 1; r < world; r++) {
+        const uint64_t target = base + (uint64_t)((double)total * r / world);
+        uint32_t c = (uint32_t)(std::lower_bound(gene_off, gene_off + n_genes + 1, target) - gene_off);
+        c = std::min(c, n_genes);
+        first_gene[r] = std::max(first_gene[r - 1], c);
+    }
+    first_gene[world] = n_genes;
+    return SD_OK;
+}
+
 // Block layout: [4 x u64 counts][alignments][backtrace pool][clusters][members], every part on a 16-byte boundary.
 // ONE exchange: ncclAllGather of the block sizes, then ncclAllGather of the blocks padded to the largest one
 // (pinned host -> HBM -> NVLink -> HBM -> pinned host); the merged result has one chunk per rank, in rank (= query set) order.
 extern "C" int sd_shard_allgather_result(sd_context *ctx, const sd_search_result *mine, uint32_t query_first, sd_search_result **all,
                                          uint64_t *bytes_gathered) {
+    return sd::shardAllgather(ctx, mine, query_first, 1, all, bytes_gathered);
+}
+
+// pinSlot, pinSlot + 1: pinned send / receive blocks of this exchange (the merged result is a view of the receive block, so a step
+// with two exchanges uses two pairs)
+int sd::shardAllgather(sd_context *ctx, const sd_search_result *mine, uint32_t query_first, int pinSlot, sd_search_result **all,
+                       uint64_t *bytes_gathered) {
     if (!ctx || !mine || !all) { sd::setError("sd_shard_allgather_result: bad argument"); return SD_EINVAL; }
     *all = nullptr;
     if (!ctx->comm) { sd::setError("sd_shard_allgather_result: call sd_shard_init first"); return SD_EINVAL; }
@@ -163,8 +186,8 @@ extern "C" int sd_shard_allgather_result(sd_context *ctx, const sd_search_result
     cap = (cap + 4095) & ~4095ull;
 
     // local block in pinned memory (cross references stay block-relative; the query index becomes global)
-    char *hSend = static_cast<char *>(sd::ctxPinnedScratch(ctx, 1, cap));
-    char *hRecv = static_cast<char *>(sd::ctxPinnedScratch(ctx, 2, cap * (uint64_t)world));
+    char *hSend = static_cast<char *>(sd::ctxPinnedScratch(ctx, pinSlot, cap));
+    char *hRecv = static_cast<char *>(sd::ctxPinnedScratch(ctx, pinSlot + 1, cap * (uint64_t)world));
     char *dSend = static_cast<char *>(sd::ctxDeviceScratch(ctx, sd::SL_SH_SEND, cap));
     char *dRecv = static_cast<char *>(sd::ctxDeviceScratch(ctx, sd::SL_SH_RECV, cap * (uint64_t)world));
     if (!hSend || !hRecv || !dSend || !dRecv) return SD_ENOMEM;

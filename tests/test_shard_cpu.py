@@ -183,3 +183,19 @@ def test_c_abi_partition_equals_python():
             if rng.random() < 0.3:
                 w[rng.integers(0, n)] *= 50
             assert sd.shard_partition(w, world) == shard.partition_sets(w, world), (n, world, w[:8])
+
+
+def test_c_abi_partition_genes():
+    """sd_shard_partition_genes (csrc/shard.cu, host code): contiguous blocks that cover all genes, in order, balanced by residues to
+    within the longest gene; more ranks than genes leaves empty blocks."""
+    import spacedust_b200 as sd
+    rng = np.random.default_rng(5)
+    for n, world in [(1, 1), (1, 4), (3, 8), (60, 8), (1000, 3), (60000, 8)]:
+        lens = rng.integers(30, 2500, size=n).astype(np.uint64)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64) + 7      # offsets need not start at 0
+        blocks = sd.shard_partition_genes(off, world)
+        assert len(blocks) == world and blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1)) and all(lo <= hi for lo, hi in blocks)
+        share = float(lens.sum()) / world
+        for lo, hi in blocks:
+            assert float(lens[lo:hi].sum()) <= share + 2 * float(lens.max())

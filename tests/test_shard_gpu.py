@@ -1,5 +1,5 @@
-"""GPU, 2 ranks (skipped on a 1-GPU box): one process per GPU over NCCL, query sets sharded (spacedust_b200/shard.py),
-the libsdgpu path per rank, one all_gather of the result lists -> identical to the single-GPU result."""
+"""GPU, 2 ranks (skipped on a 1-GPU box): one process per GPU over NCCL; query sets sharded with one all-gather of the result
+lists, and query genes sharded with the two exchanges of sd_shard_clustersearch_run -> both identical to the single-GPU result."""
 import os
 import socket
 import sys
@@ -61,6 +61,15 @@ def _worker(rank, world, port, tmpdir):
                 assert np.array_equal(r3[k][f], merged[k][f]), (k, f)
         assert np.array_equal(r3["pool"], merged["pool"])
         np.savez(os.path.join(tmpdir, "merged_%d.npz" % rank), **merged)
+        # gene-granular sharding (what bench.py and `sdb200 --gpus N` use): this rank's genes for prefilter + align, both exchanges
+        # and the set-wise cluster stages inside the library (sd_shard_clustersearch_run)
+        g_lo, g_hi = sd.shard_partition_genes(off, world)[rank]
+        gbatch = sd.QueryBatch(ctx, buf[int(off[g_lo]):int(off[g_hi])], (off[g_lo:g_hi + 1] - off[g_lo]).astype(np.uint64))
+        for _ in range(2):
+            r4 = sd.clustersearch(ctx, idx, gbatch, meta, meta, pp, query_first=g_lo, shard_genes=True)
+        assert r4["bytes_gathered"] > 0
+        np.savez(os.path.join(tmpdir, "genes_%d.npz" % rank), **{k: r4[k] for k in ("alns", "pool", "clusters", "members")})
+        gbatch.close()
         if rank == 0:      # the unsharded run on one GPU
             whole = sd.clustersearch(ctx, idx, sd.QueryBatch(ctx, buf, off), meta, meta, pp)
             np.savez(os.path.join(tmpdir, "whole.npz"), **{k: whole[k] for k in ("alns", "pool", "clusters", "members")})
@@ -81,8 +90,8 @@ def test_two_ranks_equal_one(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     whole = np.load(os.path.join(tmp_path, "whole.npz"))
     assert len(whole["clusters"]) > 10
-    for rank in range(2):
-        m = np.load(os.path.join(tmp_path, "merged_%d.npz" % rank))
+    for name in ("merged_0", "merged_1", "genes_0", "genes_1"):
+        m = np.load(os.path.join(tmp_path, name + ".npz"))
         for k in ("alns", "clusters", "members"):
             assert len(m[k]) == len(whole[k]), k
             for f in whole[k].dtype.names:
