@@ -7,6 +7,7 @@
 // (query set, target set)).  Two host threads, each with its own context (stream + scratch), take the chunks in turn; a
 // token serialises the GPU-heavy part of the align stage, so one chunk's host post-processing (E-values, sorting,
 // aggregation, clustering bookkeeping) runs under the other chunk's Smith-Waterman kernels.
+#include <chrono>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -85,7 +86,11 @@ static int searchCore(sd_context *ctx, const sd_target_index *idx, const sd_quer
                 setStart.push_back(q);
             }
         const int envChunks = getenv("SD_CHUNKS") ? atoi(getenv("SD_CHUNKS")) : 0;      // test / tuning hook
-        uint64_t want = envChunks > 0 ? (uint64_t)envChunks : std::max<uint64_t>(4, (nHits + (20ull << 20) - 1) / (20ull << 20));
+        // Every chunk pays the critical paths of its small passes (16-bit re-runs, reverse pass, traceback: a few ms each, set by
+        // the longest pair), so small batches (one rank's share of a multi-GPU step) get fewer chunks: about 2.5 M pairs each up to
+        // the four that let the host post-processing of one chunk hide under the kernels of the next
+        uint64_t want = envChunks > 0 ? (uint64_t)envChunks
+                                      : std::max<uint64_t>(std::min<uint64_t>(4, std::max<uint64_t>(1, (nHits + 1250000) / 2500000)), (nHits + (20ull << 20) - 1) / (20ull << 20));
         if (!contiguous || setStart.size() < 2 || (envChunks <= 0 && nHits < 4096)) want = 1;
         want = std::min<uint64_t>(want, setStart.size());
         cut.push_back(0);
@@ -200,18 +205,31 @@ extern "C" int sd_shard_clustersearch_run(sd_context *ctx, const sd_target_index
     if (cst) memset(cst, 0, sizeof *cst);
     if ((uint64_t)query_first + queries->nq > nq_total) { sd::setError("sd_shard_clustersearch_run: gene block %u + %u exceeds %u query genes", query_first, queries->nq, nq_total); return SD_EINVAL; }
     const int world = ctx->world, rank = ctx->rank;
+    const bool timing = getenv("SD_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    std::string tLog;
+    auto tick = [&](const char *what) {
+        if (!timing) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        char b[64];
+        snprintf(b, sizeof b, " %s %.1f", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        tLog += b;
+        t0 = t1;
+    };
     // 1
     sd_search_result *mineRaw = nullptr;
     int rc = searchCore(ctx, idx, queries, query_first, ppar, apar, nullptr, nullptr, nullptr, nullptr, t_set_of, t_pos, t_strand, nt,
                         nullptr, 0, t_set_size, n_t_sets, db_residues, &mineRaw, pst, ast, nullptr);
     if (rc) return rc;
     std::unique_ptr<sd_search_result> mine(mineRaw);
+    tick("search");
     // 2
     sd_search_result *allRaw = nullptr;
     uint64_t bytes1 = 0, bytes2 = 0;
     if ((rc = sd::shardAllgather(ctx, mine.get(), query_first, 1, &allRaw, &bytes1))) return rc;
     std::unique_ptr<sd_search_result> all(allRaw);
     mine.reset();
+    tick("gather1");
     // 3: alignments per query set (every rank computes the same partition from the same merged list)
     std::vector<uint64_t> setAlns(n_q_sets, 0), chunkBase(all->chunks.size() + 1, 0);
     for (size_t k = 0; k < all->chunks.size(); k++) chunkBase[k + 1] = chunkBase[k] + all->chunks[k].nAlns();
@@ -239,6 +257,7 @@ extern "C" int sd_shard_clustersearch_run(sd_context *ctx, const sd_target_index
     a1 = a0;
     for (uint32_t sIdx = firstSet[rank]; sIdx < firstSet[rank + 1]; sIdx++) a1 += setAlns[sIdx];
     if (a1 > nAll) { sd::setError("sd_shard_clustersearch_run: query sets are not contiguous ascending blocks of genes"); return SD_EINVAL; }
+    tick("partition");
     std::unique_ptr<sd_search_result> mineC(new sd_search_result());
     mineC->chunks.resize(1);
     ChunkResult &cc = mineC->chunks[0];
@@ -269,11 +288,14 @@ extern "C" int sd_shard_clustersearch_run(sd_context *ctx, const sd_target_index
         sd::parallelFor(nM, [&](uint64_t i) { m[i].aln += (uint32_t)a0; });
         if (cst) *cst = cc.cst;
     }
+    tick("cluster");
     // 4
     sd_search_result *allCRaw = nullptr;
     if ((rc = sd::shardAllgather(ctx, mineC.get(), 0, 3, &allCRaw, &bytes2))) return rc;
     std::unique_ptr<sd_search_result> allC(allCRaw);
     for (ChunkResult &cr : allC->chunks) { cr.membersGlobal = true; all->chunks.push_back(std::move(cr)); }
+    tick("gather2");
+    if (timing) fprintf(stderr, "[sd_shard rank %d]%s (ms; prefilter %.1f align %.1f)\n", rank, tLog.c_str(), pst ? pst->total_ms : 0.0, ast ? ast->total_ms : 0.0);
     if (bytes_gathered) *bytes_gathered = bytes1 + bytes2;
     *out = all.release();
     return SD_OK;

@@ -89,7 +89,7 @@ void buildExt3(const SubMat &seedMat, std::vector<int16_t> &score, std::vector<u
     score.resize(static_cast<size_t>(N3) * N3);
     index.resize(static_cast<size_t>(N3) * N3);
     // pair tables first: s2[x0,x1][y0,y1] would be 160k entries; the triple loop below is cheap enough
-    unsigned nThreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    unsigned nThreads = hostThreads();
     std::atomic<int> nextRow{0};
     auto work = [&]() {
         std::vector<int16_t> rowScore(N3);

@@ -3,10 +3,20 @@
 // reference also runs once per process; they stay on the host in the reference's operation order
 // (hard part 4).
 #pragma once
+#include <algorithm>
 #include <cstdint>
+#include <thread>
 #include <vector>
 
 namespace sd {
+
+// Host threads of the post-processing helpers: all hardware threads (at most 64) for a single process; with one process per GPU
+// (sd_shard_init) every rank takes its share of the node, otherwise N ranks x 64 threads fight for the same cores.
+inline unsigned &hostThreadLimit() { static unsigned limit = 0; return limit; }
+inline unsigned hostThreads() {
+    const unsigned hc = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    return hostThreadLimit() ? std::min(hc, hostThreadLimit()) : hc;
+}
 
 constexpr int AA = 21;     // alphabet incl. X
 constexpr int XCODE = 20;

@@ -139,7 +139,7 @@ struct ScratchBuf {
 // run fn(i) for i in [0,n) on a pool of host threads (small per-item work, chunked)
 template <typename F>
 inline void parallelFor(uint64_t n, F fn) {
-    unsigned nThreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    unsigned nThreads = hostThreads();
     if (n < 4096) nThreads = 1;
     std::atomic<uint64_t> next{0};
     const uint64_t chunk = 2048;
@@ -161,7 +161,7 @@ inline void parallelFor(uint64_t n, F fn) {
 // few heavy items (genome pairs, ...): one item per grab, always threaded
 template <typename F>
 inline void parallelItems(uint64_t n, F fn) {
-    unsigned nThreads = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(std::min(std::thread::hardware_concurrency(), 64u), n));
+    unsigned nThreads = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(hostThreads(), n));
     std::atomic<uint64_t> next{0};
     auto work = [&]() {
         for (;;) {
@@ -194,7 +194,7 @@ using CharPool = std::vector<char, NoInitAlloc<char>>;
 template <typename F>
 inline void parallelChunks(uint64_t n, unsigned nChunks, F fn) {
     if (nChunks == 0) nChunks = 1;
-    unsigned nThreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+    unsigned nThreads = hostThreads();
     if (n < 4096) nThreads = 1;
     std::atomic<unsigned> next{0};
     auto work = [&]() {

@@ -95,6 +95,9 @@ extern "C" int sd_shard_init(sd_context *ctx, int rank, int world, const uint8_t
     ctx->comm = comm;
     ctx->rank = rank;
     ctx->world = world;
+    // one process per GPU of one node: this rank's share of the host threads (SD_HOST_THREADS overrides)
+    sd::hostThreadLimit() = getenv("SD_HOST_THREADS") ? (unsigned)std::max(1, atoi(getenv("SD_HOST_THREADS")))
+                                                      : std::max(4u, std::thread::hardware_concurrency() / (unsigned)world);
     return SD_OK;
 }
 
