@@ -458,13 +458,15 @@ def run_ours(args, proteomes, rank, world, local_rank):
         algo = 8 * pst["probes"] + 6 * pst["matches"] + pst["diag_residues"] + 21 * pst["query_residues"] + 10 * pst["hits"]
         k_ms = pst["kernel_ms"]
         achieved = algo / 1e9 / (k_ms / 1e3) if k_ms > 0 else 0.0
-        # DRAM bytes of this launch from ncu (dram__bytes_read.sum + dram__bytes_write.sum, profiles/prof_prefilter_traffic_c2_r01.csv);
+        # DRAM bytes of this launch from ncu --set full (dram__bytes_read.sum + dram__bytes_write.sum, profiles/prof_pf_stream_c2_r02.raw.csv);
         # known only for the default workload on one GPU
         traffic, traffic_src = None, None
         if world == 1 and args.proteomes == N_PROTEOMES and args.genes == GENES:
-            traffic = 495320312064 + 70822895104
-            traffic_src = ("ncu dram__bytes_read.sum + dram__bytes_write.sum of the C2 prefilterKernel launch (157.5 ms under ncu): 566 GB = "
-                           "6.65 x algorithmic, 3.6 TB/s; profiles/prof_prefilter_traffic_c2_r01.csv")
+            traffic = 504474968000 + 70755082000
+            traffic_src = ("ncu dram__bytes_read.sum + dram__bytes_write.sum of the C2 prefilterStreamKernel launch (154.8 ms under ncu): 575 GB = "
+                           "6.76 x algorithmic, 3.71 TB/s = 0.57 of the measured HBM peak; profiles/prof_pf_stream_c2_r02.raw.csv")
+        # which of the two prefilter kernels took this index (csrc/prefilter.cu: streaming kernel up to 262144 targets, else binned)
+        pf_kernel = "prefilterStreamKernel" if n_total <= 262144 else "prefilterKernel"
         cells = ast["cells_forward"] + ast["cells_reverse"]
         line = {"metric": "clustersearch query-genes/s", "value": n_total * args.steps / dt, "unit": "query-genes/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -476,8 +478,9 @@ def run_ours(args, proteomes, rank, world, local_rank):
                         "includes": "target index build from host residues (upload, tantan masking and k-mer index on the device), query upload, "
                                     "prefilter, align, besthitbyset/combinehits, clusterhits, results to host"},
                 "gpu_launches": int(launches),
-                "roofline": {"kernel": "prefilterKernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "roofline": {"kernel": pf_kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                             "dram_frac_of_peak": (traffic / 1e9 / (k_ms / 1e3) / peak) if (traffic and k_ms > 0) else None,
                              "algorithmic_bytes_per_launch": int(algo),
                              "bytes_formula": "8*P + 6*M + R + 21*Lq + 10*H (SURVEY.md 8d), P/M/R/H counted by the kernel and "
                                               "equal to the oracle's counts (tests/test_prefilter_gpu.py)",

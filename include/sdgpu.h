@@ -234,6 +234,15 @@ int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_t n_alns,
                    const sd_cluster_params *par, sd_cluster *clusters, uint64_t cap, uint64_t *n_clusters,
                    sd_cluster_member *members, uint64_t mcap, uint64_t *n_members, sd_cluster_stats *stats);
 
+/* The clusterhits module body alone (src/util/ClusterHits.cpp:294-485), for matches read from a `matches` / `matches_h` DB pair
+ * (`sdb200 clusterhits`): match i owns hits first[i] .. first[i+1]-1; per hit the gene index of the query / target gene in its set,
+ * whether both genes lie on the same strand, and the P-value column; nq[i] = number of genes of the match's query set (header
+ * column 3); q_set / t_set are passed through to the clusters (set KEYS here).  members[].aln = index of the hit. */
+int sd_clusterhits_run(sd_context *ctx, uint32_t n_matches, const uint64_t *first, const uint32_t *q_set, const uint32_t *t_set,
+                       const uint32_t *nq, const uint32_t *hit_q_pos, const uint32_t *hit_t_pos, const uint8_t *hit_same_strand,
+                       const double *hit_pval, uint32_t max_set_size, const sd_cluster_params *par, sd_cluster *clusters, uint64_t cap,
+                       uint64_t *n_clusters, sd_cluster_member *members, uint64_t mcap, uint64_t *n_members, sd_cluster_stats *stats);
+
 /* ---- fused hot path: prefilter -> align -> besthitbyset/combinehits -> clusterhits (data/clustersearch.sh:112-146) ----
  * Same results as calling the three stages one after the other, but the prefilter hit list stays in HBM.  The result
  * object owns host copies of the accepted alignments (+ CIGAR strings) and the clusters.  Internally the query batch is cut

@@ -270,6 +270,192 @@ struct BestHit {
 
 using namespace sd;
 
+// ClusterHits.cpp:359-485 for a list of matches (genome pairs): pairs with at least two hits go to the device, clusters come back in
+// match order, then node order; member.aln = index of the hit in the caller's hit arrays.  Shared by sd_cluster_run (hits = kept best
+// hits of the fused path) and sd_clusterhits_run (hits = lines of a `matches` DB).
+struct Match { uint32_t qSet, tSet; uint64_t first; uint32_t n, nq; };
+struct ClusterCoreOut {
+    std::vector<sd_cluster> clusters;
+    std::vector<sd_cluster_member> members;
+    uint64_t maxK = 0;
+    uint32_t nDev = 0;
+    unsigned long long hStat[2] = {0, 0};
+    double kernelMs = 0;
+};
+
+template <typename Tick>
+static int clusterMatchesCore(sd_context *ctx, cudaStream_t st, cudaEvent_t evA, cudaEvent_t evB, const std::vector<Match> &matches,
+                              const uint32_t *hitQPos, const uint32_t *hitTPos, const uint8_t *hitSame, const double *mPval, uint32_t maxOrf,
+                              const sd_cluster_params *par, ClusterCoreOut &out, Tick tick) {
+    // ---- clusterhits: genome pairs with at least two hits go to the device
+    std::vector<double> lgam(maxOrf + 2);
+    lgam[0] = INFINITY;
+    for (uint32_t i = 1; i < maxOrf + 2; i++) lgam[i] = lanczosLogGamma((double)i);
+    const unsigned d = (unsigned)par->max_gene_gap;
+    auto hostScore = [&](int k, int span, int m) {
+        const double logpClu = 2 * lgam[span + 1] - 2 * lgam[span - k + 1] - lgam[k + 1] + k * std::log(0.001);
+        const double logpOrd = std::log(1 - 1.0 * m / k) - m * std::log(2) - lgam[m + 1];
+        return -0.5 * logpClu - 0.5 * logpOrd;
+    };
+    if (d + 2 >= lgam.size()) { setError("sd_cluster_run: --max-gene-gap larger than the biggest set"); return SD_EINVAL; }
+    const double sMin = hostScore(2, (int)d + 1, 1);
+
+    std::vector<uint32_t> dMatchOff(1, 0), hQ, hT, devMatch;
+    std::vector<uint8_t> hS;
+    uint64_t maxK = 0;
+    for (size_t mi = 0; mi < matches.size(); mi++) {
+        const Match &m = matches[mi];
+        maxK = std::max<uint64_t>(maxK, m.n);
+        if (m.n < 2) continue;
+        std::vector<uint32_t> seen;
+        seen.reserve(m.n);
+        for (uint32_t h = 0; h < m.n; h++) {
+            const uint64_t g = m.first + h;
+            if (hitQPos[g] + 1 >= lgam.size() || hitTPos[g] + 1 >= lgam.size()) { setError("sd_cluster_run: gene position beyond the set size"); return SD_EINVAL; }
+            hQ.push_back(hitQPos[g]);
+            hT.push_back(hitTPos[g]);
+            hS.push_back(hitSame[g] ? 1 : 0);
+            seen.push_back(hitQPos[g]);
+        }
+        std::sort(seen.begin(), seen.end());
+        if (std::adjacent_find(seen.begin(), seen.end()) != seen.end()) {
+            setError("sd_cluster_run: query positions repeat inside genome pair (%u,%u): --suboptimal-hits > 0 style input is not supported", m.qSet, m.tSet);
+            return SD_ELIMIT;
+        }
+        devMatch.push_back((uint32_t)mi);
+        dMatchOff.push_back((uint32_t)hQ.size());
+    }
+    tick("matches");
+    const uint32_t nDev = (uint32_t)devMatch.size();
+    std::vector<uint32_t> hRoot(hQ.size());
+    unsigned long long hStat[2] = {0, 0};
+    double kernelMs = 0;
+    if (nDev) {
+        std::vector<uint32_t> order(nDev);
+        for (uint32_t i = 0; i < nDev; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return dMatchOff[a + 1] - dMatchOff[a] > dMatchOff[b + 1] - dMatchOff[b]; });
+        std::vector<double> log1m((size_t)CL_LOGTAB * CL_LOGTAB, 0.0);
+        for (int k = 1; k < CL_LOGTAB; k++)
+            for (int m = 0; m < k; m++) log1m[(size_t)k * CL_LOGTAB + m] = std::log(1 - 1.0 * m / k);
+        DevBuf<double> dLgam, dLog1m, dVal;
+        DevBuf<uint32_t> dOff, dOrder, dQ, dT, dRoot, dNext;
+        DevBuf<uint8_t> dS;
+        DevBuf<Node> dNodes;
+        DevBuf<int> dDmin;
+        DevBuf<unsigned long long> dStats;
+        int rc;
+        const size_t nH = hQ.size();
+        if ((rc = dLgam.alloc(lgam.size())) || (rc = dLog1m.alloc(log1m.size())) || (rc = dVal.alloc(nH)) || (rc = dOff.alloc(nDev + 1)) ||
+            (rc = dOrder.alloc(nDev)) || (rc = dQ.alloc(nH)) || (rc = dT.alloc(nH)) || (rc = dRoot.alloc(nH)) || (rc = dNext.alloc(1)) ||
+            (rc = dS.alloc(nH)) || (rc = dNodes.alloc(nH)) || (rc = dDmin.alloc(nH)) || (rc = dStats.alloc(2)))
+            return rc;
+        SD_CUDA(cudaMemcpyAsync(dLgam.p, lgam.data(), lgam.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        SD_CUDA(cudaMemcpyAsync(dLog1m.p, log1m.data(), log1m.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        SD_CUDA(cudaMemcpyAsync(dOff.p, dMatchOff.data(), (nDev + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        SD_CUDA(cudaMemcpyAsync(dOrder.p, order.data(), nDev * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        SD_CUDA(cudaMemcpyAsync(dQ.p, hQ.data(), nH * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        SD_CUDA(cudaMemcpyAsync(dT.p, hT.data(), nH * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        SD_CUDA(cudaMemcpyAsync(dS.p, hS.data(), nH, cudaMemcpyHostToDevice, st));
+        SD_CUDA(cudaMemsetAsync(dNext.p, 0, sizeof(uint32_t), st));
+        SD_CUDA(cudaMemsetAsync(dStats.p, 0, 2 * sizeof(unsigned long long), st));
+        ClusterArgs A;
+        A.tab.lgam = dLgam.p; A.tab.log1m = dLog1m.p; A.tab.logQ0 = std::log(0.001); A.tab.log2v = std::log(2); A.tab.sMin = sMin; A.tab.d = d;
+        A.matchOff = dOff.p; A.order = dOrder.p; A.nMatches = nDev; A.qPos = dQ.p; A.tPos = dT.p; A.sameStrand = dS.p;
+        A.nodes = dNodes.p; A.dmin = dDmin.p; A.val = dVal.p; A.root = dRoot.p; A.next = dNext.p; A.stats = dStats.p;
+        const uint32_t nCta = std::min<uint32_t>(nDev, (uint32_t)ctx->smCount * 4u);
+        // fused clustersearch: two host threads share the GPU; take the turn so that the event pair brackets this kernel and not
+        // the other chunk's Smith-Waterman launches queued before it (the kernel is a few ms)
+        std::unique_lock<std::mutex> gpuTurn;
+        if (ctx->gpuToken) gpuTurn = std::unique_lock<std::mutex>(*ctx->gpuToken);
+        SD_CUDA(cudaEventRecord(evA, st));
+        clusterKernel<<<nCta, CL_THREADS, 0, st>>>(A);
+        ctx->launches++;
+        SD_CUDA(cudaGetLastError());
+        SD_CUDA(cudaEventRecord(evB, st));
+        SD_CUDA(cudaMemcpyAsync(hRoot.data(), dRoot.p, nH * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        SD_CUDA(cudaMemcpyAsync(hStat, dStats.p, sizeof hStat, cudaMemcpyDeviceToHost, st));
+        SD_CUDA(cudaStreamSynchronize(st));
+        if (gpuTurn.owns_lock()) gpuTurn.unlock();
+        float ms = 0;
+        cudaEventElapsedTime(&ms, evA, evB);
+        kernelMs = ms;
+    }
+    tick("kernel");
+    // ---- clusters of each genome pair in node order; thresholds (ClusterHits.cpp:456-485)
+    const uint32_t cls = (uint32_t)std::max(par->cluster_size, 0);
+    std::vector<std::vector<sd_cluster>> partC(nDev);
+    std::vector<std::vector<sd_cluster_member>> partM(nDev);
+    parallelItems(nDev, [&](uint64_t di64) {
+        const uint32_t di = (uint32_t)di64;
+        std::vector<sd_cluster> &outC = partC[di];
+        std::vector<sd_cluster_member> &outM = partM[di];
+        const Match &m = matches[devMatch[di]];
+        const uint32_t base = dMatchOff[di];
+        std::map<uint32_t, std::vector<uint32_t>> byRoot;
+        for (uint32_t h = 0; h < m.n; h++) byRoot[hRoot[base + h]].push_back(h);
+        for (auto &kv : byRoot) {
+            std::vector<uint32_t> &mem = kv.second;
+            if (mem.size() < cls) continue;
+            std::sort(mem.begin(), mem.end(), [&](uint32_t a, uint32_t b) { return hQ[base + a] < hQ[base + b]; });   // findConservedPairs sorts by qPos
+            unsigned iMin = UINT_MAX, iMax = 0, jMin = UINT_MAX, jMax = 0;
+            for (uint32_t h : mem) {
+                iMin = std::min(iMin, hQ[base + h]); iMax = std::max(iMax, hQ[base + h]);
+                jMin = std::min(jMin, hT[base + h]); jMax = std::max(jMax, hT[base + h]);
+            }
+            const int span = std::max((int)(iMax - iMin + 1), (int)(jMax - jMin + 1));
+            int cons = 0;
+            for (size_t l = 0; l + 1 < mem.size(); l++) {
+                const bool sameOrder = hT[base + mem[l + 1]] > hT[base + mem[l]];
+                if ((hS[base + mem[l]] != 0) == sameOrder && (hS[base + mem[l + 1]] != 0) == sameOrder) cons++;
+            }
+            const int k = (int)mem.size();
+            const double pCO = std::exp(-hostScore(k, span, cons));
+            // multihitPval (ClusterHits.cpp:184-213)
+            const uint32_t Nq = m.nq;
+            double pMH;
+            {
+                size_t kk = 0;
+                double r = 0;
+                const double thr = std::log((double)par->alpha / (Nq + 1));
+                for (uint32_t h : mem) {
+                    const double lp = std::log(mPval[m.first + h]);
+                    if (lp < thr) { kk++; r -= lp - thr; }
+                }
+                if (r == 0) pMH = 1.0;
+                else if (std::isinf(r)) pMH = 0.0;
+                else {
+                    const double emr = std::exp(-r);
+                    if (emr == 0) pMH = 0.0;
+                    else {
+                        double sum = 0;
+                        for (size_t i = 0; i + 1 < kk; i++) sum += std::pow(r, (double)i) / std::exp(lgam[i + 1]);
+                        pMH = emr * sum;
+                    }
+                }
+            }
+            if (!(pCO <= par->cluster_pval && pMH <= par->multihit_pval)) continue;
+            sd_cluster c;
+            c.q_set = m.qSet; c.t_set = m.tSet; c.p_co = pCO; c.p_mh = pMH; c.n = (uint32_t)k; c.first = (uint32_t)outM.size();
+            for (uint32_t h : mem) {
+                sd_cluster_member mm;
+                mm.aln = (uint32_t)(m.first + h); mm.pad = 0; mm.pval = mPval[m.first + h];
+                outM.push_back(mm);
+            }
+            outC.push_back(c);
+        }
+    });
+    std::vector<sd_cluster> outC;
+    std::vector<sd_cluster_member> outM;
+    for (uint32_t di = 0; di < nDev; di++) {
+        for (sd_cluster c : partC[di]) { c.first += (uint32_t)outM.size(); outC.push_back(c); }
+        outM.insert(outM.end(), partM[di].begin(), partM[di].end());
+    }
+    out.clusters.swap(outC);
+    out.members.swap(outM);
+    out.maxK = maxK; out.nDev = nDev; out.hStat[0] = hStat[0]; out.hStat[1] = hStat[1]; out.kernelMs = kernelMs;
+    return SD_OK;
+}
+
 extern "C" void sd_cluster_params_default(sd_cluster_params *p) {
     p->alpha = 1.0f;
     p->filter_self_match = 0;
@@ -383,7 +569,6 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
         });
     }
     tick("pairsort");
-    struct Match { uint32_t qSet, tSet, first, n; };
     std::vector<Match> matches;
     std::vector<uint32_t> mAln;       // alignment index per kept hit
     std::vector<double> mPval;        // P-value column as combinehits prints it
@@ -406,179 +591,37 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
                     }
                 }
                 if (r == 0 || k == 0) { mAln.resize(first); mPval.resize(first); }
-                else matches.push_back(Match{best[i].qSet, best[i].tSet, first, (uint32_t)k});
+                else matches.push_back(Match{best[i].qSet, best[i].tSet, first, (uint32_t)k, q_set_size[best[i].qSet]});
             }
             i = j;
         }
     }
     parallelFor(mPval.size(), [&](uint64_t i) { mPval[i] = roundTrip3E(std::exp(mPval[i])); });
     tick("combine");
-    // ---- clusterhits: genome pairs with at least two hits go to the device
+    // ---- clusterhits on the kept hits (clusterMatchesCore): positions / strands / printed P-values per kept hit
     uint32_t maxOrf = 0;
     for (uint32_t s = 0; s < n_q_sets; s++) maxOrf = std::max(maxOrf, q_set_size[s]);
     for (uint32_t s = 0; s < n_t_sets; s++) maxOrf = std::max(maxOrf, t_set_size[s]);
-    std::vector<double> lgam(maxOrf + 2);
-    lgam[0] = INFINITY;
-    for (uint32_t i = 1; i < maxOrf + 2; i++) lgam[i] = lanczosLogGamma((double)i);
-    const unsigned d = (unsigned)par->max_gene_gap;
-    auto hostScore = [&](int k, int span, int m) {
-        const double logpClu = 2 * lgam[span + 1] - 2 * lgam[span - k + 1] - lgam[k + 1] + k * std::log(0.001);
-        const double logpOrd = std::log(1 - 1.0 * m / k) - m * std::log(2) - lgam[m + 1];
-        return -0.5 * logpClu - 0.5 * logpOrd;
-    };
-    if (d + 2 >= lgam.size()) { setError("sd_cluster_run: --max-gene-gap larger than the biggest set"); return SD_EINVAL; }
-    const double sMin = hostScore(2, (int)d + 1, 1);
-
-    std::vector<uint32_t> dMatchOff(1, 0), hQ, hT, devMatch;
-    std::vector<uint8_t> hS;
-    uint64_t maxK = 0;
-    for (size_t mi = 0; mi < matches.size(); mi++) {
-        const Match &m = matches[mi];
-        maxK = std::max<uint64_t>(maxK, m.n);
-        if (m.n < 2) continue;
-        std::vector<uint32_t> seen;
-        seen.reserve(m.n);
-        for (uint32_t h = 0; h < m.n; h++) {
-            const sd_alignment &a = alns[mAln[m.first + h]];
-            if (q_pos[a.query] + 1 >= lgam.size() || t_pos[a.target] + 1 >= lgam.size()) { setError("sd_cluster_run: gene position beyond the set size"); return SD_EINVAL; }
-            hQ.push_back(q_pos[a.query]);
-            hT.push_back(t_pos[a.target]);
-            hS.push_back((q_strand[a.query] != 0) == (t_strand[a.target] != 0) ? 1 : 0);
-            seen.push_back(q_pos[a.query]);
-        }
-        std::sort(seen.begin(), seen.end());
-        if (std::adjacent_find(seen.begin(), seen.end()) != seen.end()) {
-            setError("sd_cluster_run: query positions repeat inside genome pair (%u,%u): --suboptimal-hits > 0 style input is not supported", m.qSet, m.tSet);
-            return SD_ELIMIT;
-        }
-        devMatch.push_back((uint32_t)mi);
-        dMatchOff.push_back((uint32_t)hQ.size());
-    }
-    tick("matches");
-    const uint32_t nDev = (uint32_t)devMatch.size();
-    std::vector<uint32_t> hRoot(hQ.size());
-    unsigned long long hStat[2] = {0, 0};
-    double kernelMs = 0;
-    if (nDev) {
-        std::vector<uint32_t> order(nDev);
-        for (uint32_t i = 0; i < nDev; i++) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return dMatchOff[a + 1] - dMatchOff[a] > dMatchOff[b + 1] - dMatchOff[b]; });
-        std::vector<double> log1m((size_t)CL_LOGTAB * CL_LOGTAB, 0.0);
-        for (int k = 1; k < CL_LOGTAB; k++)
-            for (int m = 0; m < k; m++) log1m[(size_t)k * CL_LOGTAB + m] = std::log(1 - 1.0 * m / k);
-        DevBuf<double> dLgam, dLog1m, dVal;
-        DevBuf<uint32_t> dOff, dOrder, dQ, dT, dRoot, dNext;
-        DevBuf<uint8_t> dS;
-        DevBuf<Node> dNodes;
-        DevBuf<int> dDmin;
-        DevBuf<unsigned long long> dStats;
-        int rc;
-        const size_t nH = hQ.size();
-        if ((rc = dLgam.alloc(lgam.size())) || (rc = dLog1m.alloc(log1m.size())) || (rc = dVal.alloc(nH)) || (rc = dOff.alloc(nDev + 1)) ||
-            (rc = dOrder.alloc(nDev)) || (rc = dQ.alloc(nH)) || (rc = dT.alloc(nH)) || (rc = dRoot.alloc(nH)) || (rc = dNext.alloc(1)) ||
-            (rc = dS.alloc(nH)) || (rc = dNodes.alloc(nH)) || (rc = dDmin.alloc(nH)) || (rc = dStats.alloc(2)))
-            return rc;
-        SD_CUDA(cudaMemcpyAsync(dLgam.p, lgam.data(), lgam.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-        SD_CUDA(cudaMemcpyAsync(dLog1m.p, log1m.data(), log1m.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-        SD_CUDA(cudaMemcpyAsync(dOff.p, dMatchOff.data(), (nDev + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        SD_CUDA(cudaMemcpyAsync(dOrder.p, order.data(), nDev * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        SD_CUDA(cudaMemcpyAsync(dQ.p, hQ.data(), nH * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        SD_CUDA(cudaMemcpyAsync(dT.p, hT.data(), nH * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        SD_CUDA(cudaMemcpyAsync(dS.p, hS.data(), nH, cudaMemcpyHostToDevice, st));
-        SD_CUDA(cudaMemsetAsync(dNext.p, 0, sizeof(uint32_t), st));
-        SD_CUDA(cudaMemsetAsync(dStats.p, 0, 2 * sizeof(unsigned long long), st));
-        ClusterArgs A;
-        A.tab.lgam = dLgam.p; A.tab.log1m = dLog1m.p; A.tab.logQ0 = std::log(0.001); A.tab.log2v = std::log(2); A.tab.sMin = sMin; A.tab.d = d;
-        A.matchOff = dOff.p; A.order = dOrder.p; A.nMatches = nDev; A.qPos = dQ.p; A.tPos = dT.p; A.sameStrand = dS.p;
-        A.nodes = dNodes.p; A.dmin = dDmin.p; A.val = dVal.p; A.root = dRoot.p; A.next = dNext.p; A.stats = dStats.p;
-        const uint32_t nCta = std::min<uint32_t>(nDev, (uint32_t)ctx->smCount * 4u);
-        // fused clustersearch: two host threads share the GPU; take the turn so that the event pair brackets this kernel and not
-        // the other chunk's Smith-Waterman launches queued before it (the kernel is a few ms)
-        std::unique_lock<std::mutex> gpuTurn;
-        if (ctx->gpuToken) gpuTurn = std::unique_lock<std::mutex>(*ctx->gpuToken);
-        SD_CUDA(cudaEventRecord(evA, st));
-        clusterKernel<<<nCta, CL_THREADS, 0, st>>>(A);
-        ctx->launches++;
-        SD_CUDA(cudaGetLastError());
-        SD_CUDA(cudaEventRecord(evB, st));
-        SD_CUDA(cudaMemcpyAsync(hRoot.data(), dRoot.p, nH * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        SD_CUDA(cudaMemcpyAsync(hStat, dStats.p, sizeof hStat, cudaMemcpyDeviceToHost, st));
-        SD_CUDA(cudaStreamSynchronize(st));
-        if (gpuTurn.owns_lock()) gpuTurn.unlock();
-        float ms = 0;
-        cudaEventElapsedTime(&ms, evA, evB);
-        kernelMs = ms;
-    }
-    tick("kernel");
-    // ---- clusters of each genome pair in node order; thresholds (ClusterHits.cpp:456-485)
-    const uint32_t cls = (uint32_t)std::max(par->cluster_size, 0);
-    std::vector<std::vector<sd_cluster>> partC(nDev);
-    std::vector<std::vector<sd_cluster_member>> partM(nDev);
-    parallelItems(nDev, [&](uint64_t di64) {
-        const uint32_t di = (uint32_t)di64;
-        std::vector<sd_cluster> &outC = partC[di];
-        std::vector<sd_cluster_member> &outM = partM[di];
-        const Match &m = matches[devMatch[di]];
-        const uint32_t base = dMatchOff[di];
-        std::map<uint32_t, std::vector<uint32_t>> byRoot;
-        for (uint32_t h = 0; h < m.n; h++) byRoot[hRoot[base + h]].push_back(h);
-        for (auto &kv : byRoot) {
-            std::vector<uint32_t> &mem = kv.second;
-            if (mem.size() < cls) continue;
-            std::sort(mem.begin(), mem.end(), [&](uint32_t a, uint32_t b) { return hQ[base + a] < hQ[base + b]; });   // findConservedPairs sorts by qPos
-            unsigned iMin = UINT_MAX, iMax = 0, jMin = UINT_MAX, jMax = 0;
-            for (uint32_t h : mem) {
-                iMin = std::min(iMin, hQ[base + h]); iMax = std::max(iMax, hQ[base + h]);
-                jMin = std::min(jMin, hT[base + h]); jMax = std::max(jMax, hT[base + h]);
-            }
-            const int span = std::max((int)(iMax - iMin + 1), (int)(jMax - jMin + 1));
-            int cons = 0;
-            for (size_t l = 0; l + 1 < mem.size(); l++) {
-                const bool sameOrder = hT[base + mem[l + 1]] > hT[base + mem[l]];
-                if ((hS[base + mem[l]] != 0) == sameOrder && (hS[base + mem[l + 1]] != 0) == sameOrder) cons++;
-            }
-            const int k = (int)mem.size();
-            const double pCO = std::exp(-hostScore(k, span, cons));
-            // multihitPval (ClusterHits.cpp:184-213)
-            const uint32_t Nq = q_set_size[m.qSet];
-            double pMH;
-            {
-                size_t kk = 0;
-                double r = 0;
-                const double thr = std::log((double)par->alpha / (Nq + 1));
-                for (uint32_t h : mem) {
-                    const double lp = std::log(mPval[m.first + h]);
-                    if (lp < thr) { kk++; r -= lp - thr; }
-                }
-                if (r == 0) pMH = 1.0;
-                else if (std::isinf(r)) pMH = 0.0;
-                else {
-                    const double emr = std::exp(-r);
-                    if (emr == 0) pMH = 0.0;
-                    else {
-                        double sum = 0;
-                        for (size_t i = 0; i + 1 < kk; i++) sum += std::pow(r, (double)i) / std::exp(lgam[i + 1]);
-                        pMH = emr * sum;
-                    }
-                }
-            }
-            if (!(pCO <= par->cluster_pval && pMH <= par->multihit_pval)) continue;
-            sd_cluster c;
-            c.q_set = m.qSet; c.t_set = m.tSet; c.p_co = pCO; c.p_mh = pMH; c.n = (uint32_t)k; c.first = (uint32_t)outM.size();
-            for (uint32_t h : mem) {
-                sd_cluster_member mm;
-                mm.aln = mAln[m.first + h]; mm.pad = 0; mm.pval = mPval[m.first + h];
-                outM.push_back(mm);
-            }
-            outC.push_back(c);
-        }
+    std::vector<uint32_t> hitQPos(mAln.size()), hitTPos(mAln.size());
+    std::vector<uint8_t> hitSame(mAln.size());
+    parallelFor(mAln.size(), [&](uint64_t i) {
+        const sd_alignment &a = alns[mAln[i]];
+        hitQPos[i] = q_pos[a.query];
+        hitTPos[i] = t_pos[a.target];
+        hitSame[i] = (q_strand[a.query] != 0) == (t_strand[a.target] != 0) ? 1 : 0;
     });
-    std::vector<sd_cluster> outC;
-    std::vector<sd_cluster_member> outM;
-    for (uint32_t di = 0; di < nDev; di++) {
-        for (sd_cluster c : partC[di]) { c.first += (uint32_t)outM.size(); outC.push_back(c); }
-        outM.insert(outM.end(), partM[di].begin(), partM[di].end());
+    ClusterCoreOut core;
+    {
+        const int crc = clusterMatchesCore(ctx, st, evA, evB, matches, hitQPos.data(), hitTPos.data(), hitSame.data(), mPval.data(), maxOrf, par, core, tick);
+        if (crc) return crc;
     }
+    std::vector<sd_cluster> &outC = core.clusters;
+    std::vector<sd_cluster_member> &outM = core.members;
+    parallelFor(outM.size(), [&](uint64_t i) { outM[i].aln = mAln[outM[i].aln]; });
+    const uint64_t maxK = core.maxK;
+    const uint32_t nDev = core.nDev;
+    const unsigned long long *hStat = core.hStat;
+    const double kernelMs = core.kernelMs;
     *n_clusters = outC.size();
     *n_members = outM.size();
     if (outC.size() > cap || outM.size() > mcap || (outC.size() && (!clusters || !members))) {
@@ -597,6 +640,53 @@ extern "C" int sd_cluster_run(sd_context *ctx, const sd_alignment *alns, uint64_
         stats->best_hits = best.size(); stats->genome_pairs = matches.size(); stats->pairs_clustered = nDev;
         stats->max_hits_per_pair = maxK; stats->merges = hStat[0]; stats->inexact_log = hStat[1];
         stats->kernel_ms = kernelMs; stats->total_ms = ms;
+    }
+    return SD_OK;
+}
+
+// The clusterhits module body on its own (src/util/ClusterHits.cpp:294-485) for matches that come from a `matches` DB instead of
+// the fused path: match i owns hits first[i] .. first[i+1]-1 (query-gene position, target-gene position, same-strand flag and the
+// P-value column of every hit), nq[i] = genes of its query set (header column 3).  members[].aln = index of the hit.
+extern "C" int sd_clusterhits_run(sd_context *ctx, uint32_t n_matches, const uint64_t *first, const uint32_t *q_set, const uint32_t *t_set,
+                                  const uint32_t *nq, const uint32_t *hit_q_pos, const uint32_t *hit_t_pos, const uint8_t *hit_same_strand,
+                                  const double *hit_pval, uint32_t max_set_size, const sd_cluster_params *par, sd_cluster *clusters, uint64_t cap,
+                                  uint64_t *n_clusters, sd_cluster_member *members, uint64_t mcap, uint64_t *n_members, sd_cluster_stats *stats) {
+    if (!ctx || !par || !n_clusters || !n_members || !first || (n_matches && (!q_set || !t_set || !nq))) { setError("sd_clusterhits_run: bad argument"); return SD_EINVAL; }
+    *n_clusters = 0; *n_members = 0;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (n_matches == 0) return SD_OK;
+    if (first[n_matches] >= 0xffffffffull) { setError("sd_clusterhits_run: too many hits in one call"); return SD_ELIMIT; }
+    if (first[n_matches] && (!hit_q_pos || !hit_t_pos || !hit_same_strand || !hit_pval)) { setError("sd_clusterhits_run: bad argument"); return SD_EINVAL; }
+    SD_CUDA(cudaSetDevice(ctx->device));
+    sd::StreamScope allocScope(ctx->stream);
+    cudaStream_t st = ctx->stream;
+    sd::EventQuad events;
+    { const int erc = events.create(); if (erc) return erc; }
+    SD_CUDA(cudaEventRecord(events.e[0], st));
+    std::vector<Match> matches(n_matches);
+    for (uint32_t i = 0; i < n_matches; i++) {
+        if (first[i + 1] < first[i]) { setError("sd_clusterhits_run: match offsets must ascend"); return SD_EINVAL; }
+        matches[i] = Match{q_set[i], t_set[i], first[i], (uint32_t)(first[i + 1] - first[i]), nq[i]};
+    }
+    ClusterCoreOut core;
+    const int crc = clusterMatchesCore(ctx, st, events.e[2], events.e[3], matches, hit_q_pos, hit_t_pos, hit_same_strand, hit_pval, max_set_size, par, core,
+                                       [](const char *) {});
+    if (crc) return crc;
+    *n_clusters = core.clusters.size();
+    *n_members = core.members.size();
+    if (core.clusters.size() > cap || core.members.size() > mcap || (core.clusters.size() && (!clusters || !members))) {
+        setError("sd_clusterhits_run: needs room for %zu clusters / %zu members", core.clusters.size(), core.members.size());
+        return SD_ESMALL;
+    }
+    if (!core.clusters.empty()) memcpy(clusters, core.clusters.data(), core.clusters.size() * sizeof(sd_cluster));
+    if (!core.members.empty()) memcpy(members, core.members.data(), core.members.size() * sizeof(sd_cluster_member));
+    SD_CUDA(cudaEventRecord(events.e[1], st));
+    SD_CUDA(cudaStreamSynchronize(st));
+    if (stats) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, events.e[0], events.e[1]);
+        stats->genome_pairs = n_matches; stats->pairs_clustered = core.nDev; stats->max_hits_per_pair = core.maxK;
+        stats->merges = core.hStat[0]; stats->inexact_log = core.hStat[1]; stats->kernel_ms = core.kernelMs; stats->total_ms = ms;
     }
     return SD_OK;
 }

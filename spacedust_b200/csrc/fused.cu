@@ -86,16 +86,18 @@ static int searchCore(sd_context *ctx, const sd_target_index *idx, const sd_quer
                 setStart.push_back(q);
             }
         const int envChunks = getenv("SD_CHUNKS") ? atoi(getenv("SD_CHUNKS")) : 0;      // test / tuning hook
-        // Every chunk pays the critical paths of its small passes (16-bit re-runs, reverse pass, traceback: a few ms each, set by
-        // the longest pair), so small batches (one rank's share of a multi-GPU step) get fewer chunks: about 2.5 M pairs each up to
-        // the four that let the host post-processing of one chunk hide under the kernels of the next
-        uint64_t want = envChunks > 0 ? (uint64_t)envChunks
-                                      : std::max<uint64_t>(std::min<uint64_t>(4, std::max<uint64_t>(1, (nHits + 1250000) / 2500000)), (nHits + (20ull << 20) - 1) / (20ull << 20));
+        // Every chunk pays the critical paths of its small launches (16-bit re-runs, reverse pass, traceback: ~10 ms each on C2, set
+        // by the longest pairs), a second chunk lets the host post-processing of the first hide under its kernels: one chunk for small
+        // batches (a rank's share of a multi-GPU step), two otherwise (measured on C2: 4 chunks 997 ms, 3 chunks 981, 2 chunks 962),
+        // more only to bound the scratch of very large batches (~20 M prefilter hits per chunk)
+        uint64_t want = envChunks > 0 ? (uint64_t)envChunks : std::max<uint64_t>(nHits >= 2000000 ? 2 : 1, (nHits + (20ull << 20) - 1) / (20ull << 20));
         if (!contiguous || setStart.size() < 2 || (envChunks <= 0 && nHits < 4096)) want = 1;
         want = std::min<uint64_t>(want, setStart.size());
         cut.push_back(0);
+        // the host post-processing of the LAST chunk is not hidden under any kernel: it gets 40 % of an even share
+        const double evenShare = 1.0 / ((double)want - 0.6);
         for (uint64_t c = 1; c < want; c++) {
-            const uint64_t target = nHits * c / want;
+            const uint64_t target = want > 1 ? (uint64_t)((double)nHits * evenShare * (double)c) : 0;
             // first set boundary whose hit offset reaches the target
             uint32_t best = nq;
             for (uint32_t sIdx = 0; sIdx < setStart.size(); sIdx++)

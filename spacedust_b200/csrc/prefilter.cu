@@ -557,7 +557,8 @@ int sd_prefilter_core(sd_context *ctx, const sd_target_index *idx, const sd_quer
     const uint32_t *binnedOrder = dOrder.p;      // queries for the binned kernel (device list) ...
     uint32_t binnedCount = nq;                   // ... and how many
     if (useStream) {
-        const uint32_t nCtaS = std::max(1u, std::min<uint32_t>((uint32_t)(ctx->smCount * 4), (nq + PS_WARPS - 1) / PS_WARPS));
+        static const int ctasPerSmS = getenv("SD_PS_CTAS") ? std::max(1, std::min(4, atoi(getenv("SD_PS_CTAS")))) : 4;      // tuning hook
+        const uint32_t nCtaS = std::max(1u, std::min<uint32_t>((uint32_t)(ctx->smCount * ctasPerSmS), (nq + PS_WARPS - 1) / PS_WARPS));
         const uint32_t nWarpsS = nCtaS * PS_WARPS;
         // A warp works through its query alone: queries much longer than a warp's share of the batch set the kernel's tail (strong
         // scaling of small batches).  They go to the binned kernel instead, where a whole CTA shares one query.

@@ -6,7 +6,7 @@
 //   sdb200 prefilter     <qDB> <tDB> <prefDB>            [prefilter flags]   Prefiltering::runSplit   -> sd_prefilter_run
 //   sdb200 align         <qDB> <tDB> <prefDB> <resultDB> [align flags]       Alignment::run           -> sd_align_run
 //   sdb200 clustersearch <qSetDB> <tSetDB> <out.tsv> <tmp> [all flags]       clustersearch.sh:112-151 -> sd_clustersearch_run
-//                        (writes <tmp>/clusters, <tmp>/clusters_h and, with --write-dbs 1, <tmp>/result; then the TSV of
+//                        (writes <tmp>/clusters, <tmp>/clusters_h and, with --write-dbs 1, <tmp>/result, result_prefixed, aggregate, aggregate_merged, matches(_h); then the TSV of
 //                         summarizeresults, src/util/SummarizeResults.cpp:77-114, <tmp>/clu_to_seq and <out>_seq_to_clu)
 //   sdb200 summarizeresults / filterdb --trim-to-one-column / swapdb      host-only text modules (postmods.cpp)
 // Flags keep the reference's names and meaning; reference flags that do not change the result of this path are
@@ -32,6 +32,18 @@
 // postmods.cpp
 int filterdbTrimToOneColumn(const std::string &in, const std::string &out);
 int swapOneColumnDb(const std::string &in, const std::string &out);
+
+int modCreatesetdb(int argc, char **argv);
+int modSummarizeresults(int argc, char **argv);
+int modFilterdb(int argc, char **argv);
+int modSwapdb(int argc, char **argv);
+int modSubtractdbs(int argc, char **argv);
+int modMergedbs(int argc, char **argv);
+int modPrefixid(int argc, char **argv);
+int modBesthitbyset(int argc, char **argv);
+int modMergeresultsbyset(int argc, char **argv);
+int modCombinehits(int argc, char **argv);
+int modClusterhits(int argc, char **argv);
 
 namespace {
 
@@ -591,6 +603,19 @@ int modClustersearch(int argc, char **argv) {
             w.add(qdb.keys[qi], buf);
         }
         if (!w.close(err)) die("%s", err.c_str());
+        // ... and the intermediates of data/clustersearch.sh:119-141 under the reference's names, written by the stand-alone text
+        // modules (csrc/aggmods.cpp) from that result DB, so that the reference (or sdb200 clusterhits) can resume from any of them
+        auto runMod = [&](int (*fn)(int, char **), std::vector<std::string> args) {
+            std::vector<char *> av;
+            args.insert(args.begin(), {"sdb200", "module"});
+            for (std::string &x : args) av.push_back(&x[0]);
+            fn((int)av.size(), av.data());
+        };
+        runMod(modPrefixid, {tmp + "/result", tmp + "/result_prefixed"});
+        runMod(modBesthitbyset, {a.pos[0], a.pos[1], tmp + "/result_prefixed", tmp + "/aggregate"});
+        runMod(modMergeresultsbyset, {a.pos[0] + "_set_to_member", tmp + "/aggregate", tmp + "/aggregate_merged"});
+        runMod(modCombinehits, {a.pos[0], a.pos[1], tmp + "/aggregate_merged", tmp + "/matches", tmp, "--alpha", a.str("--alpha", "1"),
+                                "--filter-self-match", a.str("--filter-self-match", "0")});
     }
     // clusters / clusters_h (src/util/ClusterHits.cpp:455-483) and the TSV of summarizeresults (SummarizeResults.cpp:77-114)
     sddb::DbWriter wc(tmp + "/clusters", sddb::DBTYPE_ALIGNMENT_RES), wh(tmp + "/clusters_h", sddb::DBTYPE_GENERIC_DB);
@@ -644,16 +669,10 @@ int modClustersearch(int argc, char **argv) {
 
 }  // namespace
 
-int modCreatesetdb(int argc, char **argv);
-int modSummarizeresults(int argc, char **argv);
-int modFilterdb(int argc, char **argv);
-int modSwapdb(int argc, char **argv);
-int modSubtractdbs(int argc, char **argv);
-int modMergedbs(int argc, char **argv);
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "sdb200 (libsdgpu %d): createsetdb | createindex | prefilter | align | clustersearch | summarizeresults | filterdb | swapdb | subtractdbs | mergedbs\n", sd_version());
+        fprintf(stderr, "sdb200 (libsdgpu %d): createsetdb | createindex | prefilter | align | clustersearch | prefixid | besthitbyset | mergeresultsbyset | combinehits | clusterhits | summarizeresults | filterdb | swapdb | subtractdbs | mergedbs\n", sd_version());
         return EXIT_FAILURE;
     }
     const std::string mod = argv[1];
@@ -667,5 +686,10 @@ int main(int argc, char **argv) {
     if (mod == "swapdb") return modSwapdb(argc, argv);
     if (mod == "subtractdbs") return modSubtractdbs(argc, argv);
     if (mod == "mergedbs") return modMergedbs(argc, argv);
+    if (mod == "prefixid") return modPrefixid(argc, argv);
+    if (mod == "besthitbyset") return modBesthitbyset(argc, argv);
+    if (mod == "mergeresultsbyset") return modMergeresultsbyset(argc, argv);
+    if (mod == "combinehits") return modCombinehits(argc, argv);
+    if (mod == "clusterhits") return modClusterhits(argc, argv);
     die("unknown module '%s'", mod.c_str());
 }

@@ -470,7 +470,10 @@ __device__ void swGroupPass(const SwKernelArgs &A, uint32_t round, int *bnd, uns
 
 // packed pass: one round = up to four pairs of the same scheduling class (order[] is laid out in rounds of 4 slots)
 template <bool KEYED>
-__global__ void __launch_bounds__(SW_WARPS * 32, 5) swKernel16(SwKernelArgs A) {
+#ifndef SD_SW_LB
+#define SD_SW_LB 5      // resident CTAs per SM the packed kernel is compiled for (align.cu sizes the grid with the same number)
+#endif
+__global__ void __launch_bounds__(SW_WARPS * 32, SD_SW_LB) swKernel16(SwKernelArgs A) {
     const uint32_t lane = swLane();
     const uint32_t warp = blockIdx.x * SW_WARPS + (threadIdx.x >> 5);
     int *bnd = A.boundary + (size_t)warp * 6 * A.boundaryStride;
@@ -516,12 +519,19 @@ __global__ void __launch_bounds__(SW_WARPS * 32, 5) swKernel16(SwKernelArgs A) {
 
 // ---- scheduling: sort tasks by (class desc, columns), lay them out in class-pure rounds of 4 slots
 __global__ void swScheduleKeys(const SwTask *tasks, uint32_t n, uint32_t *keys, uint32_t *vals, uint32_t *classCount) {
+    __shared__ uint32_t sCount[SW_NCLASS];      // per-block histogram: one global atomic per class and block
+    for (int c = threadIdx.x; c < SW_NCLASS; c += blockDim.x) sCount[c] = 0;
+    __syncthreads();
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int cls = swClassOf(tasks[i].nRows);
-    keys[i] = ((uint32_t)(SW_NCLASS - 1 - cls) << 16) | (uint32_t)min(tasks[i].nCols, 65535);
-    vals[i] = i;
-    atomicAdd(&classCount[SW_NCLASS - 1 - cls], 1u);
+    if (i < n) {
+        const int cls = swClassOf(tasks[i].nRows);
+        keys[i] = ((uint32_t)(SW_NCLASS - 1 - cls) << 16) | (uint32_t)min(tasks[i].nCols, 65535);
+        vals[i] = i;
+        atomicAdd(&sCount[SW_NCLASS - 1 - cls], 1u);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < SW_NCLASS; c += blockDim.x)
+        if (sCount[c]) atomicAdd(&classCount[c], sCount[c]);
 }
 
 // classInfo: [0..20] counts (in), -> [0..20] first sorted position, [32..52] first round, [64] number of rounds

@@ -209,3 +209,78 @@ def test_iteration_glue_modules_vs_reference(synth_small):
         assert open(os.path.join(d, "mrg_mine.dbtype"), "rb").read() == open(os.path.join(d, "mrg_ref.dbtype"), "rb").read()
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def _write_db(path, entries, dbtype_bytes):
+    off = 0
+    with open(path, "wb") as f, open(path + ".index", "w") as ix:
+        for k, data in entries:
+            f.write(data + b"\0")
+            ix.write("%d\t%d\t%d\n" % (k, off, len(data) + 1))
+            off += len(data) + 1
+    open(path + ".dbtype", "wb").write(dbtype_bytes)
+
+
+def test_aggregation_modules_vs_reference(synth_small):
+    """The stand-alone text modules between align and clusterhits (data/clustersearch.sh:119-141, csrc/aggmods.cpp) on the
+    REFERENCE's own intermediates: prefixid, besthitbyset, mergeresultsbyset give the reference's DBs entry for entry (and the
+    same dbtype files); combinehits gives the reference's (header, lines) records -- compared as sorted pairs against the
+    2-thread reference run (its entry keys are per-thread counters), key for key against a 1-thread run on weakened hits
+    (non-zero combined E-values in the headers)."""
+    if not helpers.have_ref():
+        pytest.skip("oracle/_ref/spacedust not built")
+    import random
+    d = tempfile.mkdtemp(prefix="sdfe_")
+    try:
+        paths = synth.write_fasta(synth_small, os.path.join(d, "faa"))
+        db = os.path.join(d, "setDB")
+        helpers.run_ref(["createsetdb"] + paths + [db, os.path.join(d, "tmp"), "-v", "1"])
+        helpers.run_ref(["clustersearch", db, db, os.path.join(d, "ref.tsv"), os.path.join(d, "tmpcs"), "--filter-self-match", "1",
+                         "--threads", "2", "-v", "1"])
+        L = os.path.join(d, "tmpcs", "latest")
+
+        def mine(*args):
+            subprocess.run([SDB200] + list(args), check=True)
+        mine("prefixid", os.path.join(L, "result"), os.path.join(d, "m_prefixed"))
+        mine("besthitbyset", db, db, os.path.join(L, "result_prefixed"), os.path.join(d, "m_aggregate"))
+        mine("mergeresultsbyset", db + "_set_to_member", os.path.join(L, "aggregate"), os.path.join(d, "m_merged"))
+        mine("combinehits", db, db, os.path.join(L, "aggregate_merged"), os.path.join(d, "m_matches"), os.path.join(d, "tmpm"),
+             "--filter-self-match", "1", "--alpha", "1", "--threads", "2")
+        for m, r in (("m_prefixed", "result_prefixed"), ("m_aggregate", "aggregate"), ("m_merged", "aggregate_merged")):
+            a, b = helpers.read_db(os.path.join(d, m)), helpers.read_db(os.path.join(L, r))
+            assert a == b and len(a) > 0, m
+            assert open(os.path.join(d, m + ".dbtype"), "rb").read() == open(os.path.join(L, r + ".dbtype"), "rb").read(), m
+
+        def pairs(p):
+            h, e = helpers.read_db_entries(p + "_h"), helpers.read_db_entries(p)
+            assert len(h) == len(e)
+            return list(zip(h, e))
+        a, b = pairs(os.path.join(d, "m_matches")), pairs(os.path.join(L, "matches"))
+        assert sorted((x[0][1], x[1][1]) for x in a) == sorted((x[0][1], x[1][1]) for x in b) and len(a) > 3
+        for suffix in ("", "_h"):
+            assert open(os.path.join(d, "m_matches" + suffix + ".dbtype"), "rb").read() == open(os.path.join(L, "matches" + suffix + ".dbtype"), "rb").read()
+
+        # few, weak hits per genome pair: the truncated-Fisher sum of the header is no longer 0
+        rnd = random.Random(5)
+        weak = []
+        for k, data in helpers.read_db_entries(os.path.join(L, "aggregate_merged")):
+            lines = []
+            for ln in data.decode().split("\n"):
+                if ln and rnd.random() < 0.07:
+                    c = ln.split("\t")
+                    c[2] = "%.3E" % (-rnd.uniform(10, 22))
+                    lines.append("\t".join(c))
+            weak.append((k, ("\n".join(lines) + "\n").encode()))
+        _write_db(os.path.join(d, "weak"), weak, open(os.path.join(L, "aggregate_merged.dbtype"), "rb").read())
+        helpers.run_ref(["combinehits", db, db, os.path.join(d, "weak"), os.path.join(d, "r_weak"), os.path.join(d, "tmpr"), "--filter-self-match", "1",
+                         "--threads", "1", "-v", "1"])
+        mine("combinehits", db, db, os.path.join(d, "weak"), os.path.join(d, "m_weak"), os.path.join(d, "tmpw"), "--filter-self-match", "1")
+        a, b = pairs(os.path.join(d, "m_weak")), pairs(os.path.join(d, "r_weak"))
+        assert a == b and len(a) > 2
+        assert any(not h[1].rstrip().endswith(b"0.000E+00") for h, _ in a)
+        # flags that select code these modules do not have stop them
+        r = subprocess.run([SDB200, "besthitbyset", db, db, os.path.join(L, "result_prefixed"), os.path.join(d, "x"), "--simple-best-hit", "0"],
+                           stderr=subprocess.PIPE)
+        assert r.returncode != 0 and b"not implemented" in r.stderr
+    finally:
+        shutil.rmtree(d, ignore_errors=True)

@@ -153,3 +153,43 @@ def test_persisted_index(gpu_ctx, synth_small, workdir):
     _run(["clustersearch", db, db, out_b, os.path.join(d, "tmp_ixb"), "--filter-self-match", "1", "--ignore-index", "1"])
     assert open(out_a).read() == open(out_b).read() and open(out_a).read().count("#") > 5
     os.remove(db + ".sdidx")
+
+
+def test_clusterhits_module_and_intermediate_dbs(tmp_path):
+    """Module-level drop-in of the last steps (data/clustersearch.sh:119-146): `sdb200 clusterhits` on the REFERENCE's matches DB
+    gives the reference's clusters / clusters_h records; `sdb200 clustersearch --write-dbs 1` leaves result_prefixed, aggregate,
+    aggregate_merged and matches(_h) equal to the reference's, and the reference's own clusterhits + summarizeresults resumed from
+    OUR matches DB give the same TSV."""
+    if not helpers.have_ref():
+        pytest.skip("oracle/_ref/spacedust not built")
+    from spacedust_b200 import synth
+    d = str(tmp_path)
+    prot = synth.generate(3, 120, seed=11)
+    paths = synth.write_fasta(prot, os.path.join(d, "faa"))
+    db = os.path.join(d, "setDB")
+    helpers.run_ref(["createsetdb"] + paths + [db, os.path.join(d, "tmp"), "-v", "1"])
+    helpers.run_ref(["clustersearch", db, db, os.path.join(d, "ref.tsv"), os.path.join(d, "tmpcs"), "--filter-self-match", "1", "--threads", "2", "-v", "1"])
+    L = os.path.join(d, "tmpcs", "latest")
+
+    def pairs(p):
+        h, e = helpers.read_db_entries(p + "_h"), helpers.read_db_entries(p)
+        assert len(h) == len(e)
+        return sorted((x[1], y[1]) for x, y in zip(h, e))
+    _run(["clusterhits", db, db, os.path.join(L, "matches"), os.path.join(d, "m_clusters")])
+    ref_clusters = pairs(os.path.join(L, "clusters"))
+    assert pairs(os.path.join(d, "m_clusters")) == ref_clusters and len(ref_clusters) > 5
+    # non-default thresholds reach the module
+    _run(["clusterhits", db, db, os.path.join(L, "matches"), os.path.join(d, "m_clusters5"), "--cluster-size", "5", "--max-gene-gap", "10"])
+    helpers.run_ref(["clusterhits", db, db, os.path.join(L, "matches"), os.path.join(d, "r_clusters5"), "--cluster-size", "5", "--max-gene-gap", "10",
+                     "--threads", "2", "-v", "1"])
+    assert pairs(os.path.join(d, "m_clusters5")) == pairs(os.path.join(d, "r_clusters5"))
+
+    out = os.path.join(d, "mine.tsv")
+    mt = os.path.join(d, "tmpmine")
+    _run(["clustersearch", db, db, out, mt, "--filter-self-match", "1", "--write-dbs", "1", "-v", "1"])
+    for name in ("result_prefixed", "aggregate", "aggregate_merged"):
+        assert helpers.read_db(os.path.join(mt, name)) == helpers.read_db(os.path.join(L, name)), name
+    assert pairs(os.path.join(mt, "matches")) == pairs(os.path.join(L, "matches"))
+    # the reference resumes from our matches DB
+    helpers.run_ref(["clusterhits", db, db, os.path.join(mt, "matches"), os.path.join(d, "r_from_mine"), "--threads", "2", "-v", "1"])
+    assert pairs(os.path.join(d, "r_from_mine")) == ref_clusters
