@@ -179,9 +179,9 @@ def test_clusterhits_module_and_intermediate_dbs(tmp_path):
     ref_clusters = pairs(os.path.join(L, "clusters"))
     assert pairs(os.path.join(d, "m_clusters")) == ref_clusters and len(ref_clusters) > 5
     # non-default thresholds reach the module
-    _run(["clusterhits", db, db, os.path.join(L, "matches"), os.path.join(d, "m_clusters5"), "--cluster-size", "5", "--max-gene-gap", "10"])
+    _run(["clusterhits", db, db, os.path.join(L, "matches"), os.path.join(d, "m_clusters5"), "--cluster-size", "5", "--max-gene-gap", "10", "--db-output", "1"])
     helpers.run_ref(["clusterhits", db, db, os.path.join(L, "matches"), os.path.join(d, "r_clusters5"), "--cluster-size", "5", "--max-gene-gap", "10",
-                     "--threads", "2", "-v", "1"])
+                     "--db-output", "1", "--threads", "2", "-v", "1"])
     assert pairs(os.path.join(d, "m_clusters5")) == pairs(os.path.join(d, "r_clusters5"))
 
     out = os.path.join(d, "mine.tsv")
@@ -191,5 +191,5 @@ def test_clusterhits_module_and_intermediate_dbs(tmp_path):
         assert helpers.read_db(os.path.join(mt, name)) == helpers.read_db(os.path.join(L, name)), name
     assert pairs(os.path.join(mt, "matches")) == pairs(os.path.join(L, "matches"))
     # the reference resumes from our matches DB
-    helpers.run_ref(["clusterhits", db, db, os.path.join(mt, "matches"), os.path.join(d, "r_from_mine"), "--threads", "2", "-v", "1"])
+    helpers.run_ref(["clusterhits", db, db, os.path.join(mt, "matches"), os.path.join(d, "r_from_mine"), "--db-output", "1", "--threads", "2", "-v", "1"])
     assert pairs(os.path.join(d, "r_from_mine")) == ref_clusters
