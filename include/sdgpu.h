@@ -168,7 +168,9 @@ typedef struct {
 /* Body of the query loop of Alignment::run (lib/mmseqs/src/alignment/Alignment.cpp:312-511) for the
  * (query, target) pairs of a prefilter result: pairs must be grouped by query.  Accepted alignments come
  * back grouped by query (ascending query index) and, inside a query, in Matcher::compareHits order
- * (Matcher.h:157-168).  db_residues is the E-value search-space size (0: residues of the index).
+ * (Matcher.h:157-168; its last tie-break, the target's DB key, is the target INDEX here: index the targets in ascending key order,
+ * as createdb / createsetdb number them -- sdb200 refuses DBs where that does not hold).  db_residues is the E-value
+ * search-space size (0: residues of the index).
  * Returns SD_ESMALL with *n_out / *bt_used = required sizes when a buffer is too small. */
 int sd_align_run(sd_context *ctx, const sd_target_index *idx, const char *qseqs, const uint64_t *qoff, uint32_t nq,
                  uint32_t query_first, const uint32_t *pair_q, const uint32_t *pair_t, uint64_t n_pairs,

@@ -111,6 +111,7 @@ bool SetDb::open(const std::string &p, std::string &err) {
     posOfKey.reserve(n * 2);
     for (size_t i = 0; i < n; i++) {
         keys[i] = ord[i].key;
+        if (i && keys[i] <= keys[i - 1]) keysAscend = false;
         posOfKey[ord[i].key] = (uint32_t)i;
         const uint64_t l = ord[i].len - 2;
         memcpy(&residues[off[i]], db.data.data() + ord[i].off, l);

@@ -36,6 +36,7 @@ struct Db {
 struct SetDb {
     std::string path;
     std::vector<uint32_t> keys;             // position -> DB key
+    bool keysAscend = true;                 // keys ascend with the data offset (what createsetdb / createdb write)
     std::unordered_map<uint32_t, uint32_t> posOfKey;
     std::string residues;
     std::vector<uint64_t> off;              // n+1

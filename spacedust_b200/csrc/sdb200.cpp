@@ -240,6 +240,7 @@ struct SeqView {
     std::unordered_map<uint32_t, uint32_t> posOfKey;
     std::string residues;
     std::vector<uint64_t> off;
+    bool keysAscend = true;
     void open(const std::string &path) {
         sddb::Db db;
         std::string err;
@@ -256,6 +257,7 @@ struct SeqView {
         residues.resize(total);
         for (size_t i = 0; i < ord.size(); i++) {
             keys[i] = ord[i].key;
+            if (i && keys[i] <= keys[i - 1]) keysAscend = false;
             posOfKey[ord[i].key] = (uint32_t)i;
             memcpy(&residues[off[i]], db.data.data() + ord[i].off, ord[i].len - 2);
             off[i + 1] = off[i] + ord[i].len - 2;
@@ -340,6 +342,9 @@ int modAlign(int argc, char **argv) {
     t.open(a.pos[1]);
     if (!same) qv.open(a.pos[0]);
     SeqView &q = same ? t : qv;
+    if (!t.keysAscend)
+        die("%s: the DB keys do not ascend with the data offset; Matcher::compareHits breaks ties of equal (E-value, score, target length) by "
+            "the target KEY, this implementation by the target's position -- rewrite the DB with createdb / createsetdb", a.pos[1].c_str());
     sddb::Db pref;
     std::string err;
     if (!pref.open(a.pos[2], err)) die("%s", err.c_str());
@@ -445,6 +450,9 @@ int modClustersearch(int argc, char **argv) {
     if (!tdb.open(a.pos[1], err)) die("%s", err.c_str());
     if (!same && !qdbOwn.open(a.pos[0], err)) die("%s", err.c_str());
     sddb::SetDb &qdb = same ? tdb : qdbOwn;
+    if (!tdb.keysAscend)
+        die("%s: the DB keys do not ascend with the data offset; Matcher::compareHits breaks ties of equal (E-value, score, target length) by "
+            "the target KEY, this implementation by the target's position -- rewrite the DB with createdb / createsetdb", a.pos[1].c_str());
     info("Read set DBs: %u query genes in %zu sets, %u target genes in %zu sets, %.0f ms\n", qdb.n(), qdb.setKey.size(), tdb.n(),
          tdb.setKey.size(), nowMs() - t0);
 
