@@ -207,6 +207,11 @@ extern "C" int sd_shard_clustersearch_run(sd_context *ctx, const sd_target_index
     if (cst) memset(cst, 0, sizeof *cst);
     if ((uint64_t)query_first + queries->nq > nq_total) { sd::setError("sd_shard_clustersearch_run: gene block %u + %u exceeds %u query genes", query_first, queries->nq, nq_total); return SD_EINVAL; }
     const int world = ctx->world, rank = ctx->rank;
+    if (!ctx->comm || world == 1) {      // no communicator: the block is the whole job
+        if (query_first != 0 || queries->nq != nq_total) { sd::setError("sd_shard_clustersearch_run: call sd_shard_init first (the gene block is not the whole job)"); return SD_EINVAL; }
+        return searchCore(ctx, idx, queries, 0, ppar, apar, cpar, q_set_of, q_pos, q_strand, t_set_of, t_pos, t_strand, nt, q_set_size, n_q_sets,
+                          t_set_size, n_t_sets, db_residues, out, pst, ast, cst);
+    }
     const bool timing = getenv("SD_TIMING") != nullptr;
     auto t0 = std::chrono::steady_clock::now();
     std::string tLog;
