@@ -90,7 +90,13 @@ static int searchCore(sd_context *ctx, const sd_target_index *idx, const sd_quer
         // by the longest pairs), a second chunk lets the host post-processing of the first hide under its kernels: one chunk for small
         // batches (a rank's share of a multi-GPU step), two otherwise (measured on C2: 4 chunks 997 ms, 3 chunks 981, 2 chunks 962),
         // more only to bound the scratch of very large batches (~20 M prefilter hits per chunk)
-        uint64_t want = envChunks > 0 ? (uint64_t)envChunks : std::max<uint64_t>(nHits >= 2000000 ? 2 : 1, (nHits + (20ull << 20) - 1) / (20ull << 20));
+        // (without the cluster stages -- the gene-sharded multi-GPU step -- a chunk's host part is only E-values, sorting and the CIGAR
+        // pool, so the second chunk pays off later -- C2 at 4 GPUs, 2.5 M hits per rank: 330 ms with two chunks, 306 ms with one; SD_CHUNK2_MIN /
+        // SD_CHUNK2_MIN_ALIGN override the two thresholds)
+        static const uint64_t twoFrom = getenv("SD_CHUNK2_MIN") ? strtoull(getenv("SD_CHUNK2_MIN"), nullptr, 10) : 2000000ull;
+        static const uint64_t twoFromAlign = getenv("SD_CHUNK2_MIN_ALIGN") ? strtoull(getenv("SD_CHUNK2_MIN_ALIGN"), nullptr, 10) : 4000000ull;
+        uint64_t want = envChunks > 0 ? (uint64_t)envChunks
+                                      : std::max<uint64_t>(nHits >= (doCluster ? twoFrom : twoFromAlign) ? 2 : 1, (nHits + (20ull << 20) - 1) / (20ull << 20));
         if (!contiguous || setStart.size() < 2 || (envChunks <= 0 && nHits < 4096)) want = 1;
         want = std::min<uint64_t>(want, setStart.size());
         cut.push_back(0);
