@@ -284,3 +284,42 @@ def test_aggregation_modules_vs_reference(synth_small):
         assert r.returncode != 0 and b"not implemented" in r.stderr
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def test_aggregation_modules_edge_cases_vs_reference():
+    """Empty entries, an entry whose last line lacks its newline, genes without hits: the four text modules give the reference's
+    entries (1-thread reference run: its running keys are then the same as ours)."""
+    if not helpers.have_ref():
+        pytest.skip("oracle/_ref/spacedust not built")
+    d = tempfile.mkdtemp(prefix="sdfe_")
+    try:
+        prot = synth.generate(2, 8, seed=3)
+        paths = synth.write_fasta(prot, os.path.join(d, "faa"))
+        db = os.path.join(d, "setDB")
+        helpers.run_ref(["createsetdb"] + paths + [db, os.path.join(d, "tmp"), "-v", "1"])
+        keys = [k for k, _, _ in helpers.read_index(db)]
+        rec = "%d\t%d\t0.9\t%s\t0\t9\t10\t0\t9\t10\t10M"
+        ents = []
+        for k in keys:
+            if k == keys[1]:
+                ents.append((k, (rec % (keys[9], 50, "1E-20") + "\n").encode()))
+            elif k == keys[2]:
+                ents.append((k, (rec % (keys[10], 50, "1E-12") + "\n" + rec % (keys[11], 40, "1E-30")).encode()))
+            else:
+                ents.append((k, b""))
+        _write_db(os.path.join(d, "result"), ents, b"\x05\0\0\0")
+        for tool, pre in (("ref", "r_"), ("mine", "m_")):
+            def run(args):
+                if tool == "ref":
+                    helpers.run_ref(args + ["--threads", "1", "-v", "1"], cwd=d)
+                else:
+                    subprocess.run([SDB200] + args, check=True, cwd=d)
+            run(["prefixid", "result", pre + "prefixed"])
+            run(["besthitbyset", db, db, pre + "prefixed", pre + "aggregate"])
+            run(["mergeresultsbyset", db + "_set_to_member", pre + "aggregate", pre + "merged"])
+            run(["combinehits", db, db, pre + "merged", pre + "matches", "tmpc_" + tool, "--filter-self-match", "1"])
+        for n in ("prefixed", "aggregate", "merged", "matches", "matches_h"):
+            a, b = helpers.read_db_entries(os.path.join(d, "m_" + n)), helpers.read_db_entries(os.path.join(d, "r_" + n))
+            assert a == b and len(a) > 0, n
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
