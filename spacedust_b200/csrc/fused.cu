@@ -65,6 +65,11 @@ static int searchCore(sd_context *ctx, const sd_target_index *idx, const sd_quer
     if (ast) memset(ast, 0, sizeof *ast);
     if (cst) memset(cst, 0, sizeof *cst);
     std::unique_ptr<sd_search_result> r(new sd_search_result());
+    if (queries->nq == 0) {      // a rank without query genes (more GPUs than genes): an empty result takes part in the exchanges
+        if (pst) memset(pst, 0, sizeof *pst);
+        *out = r.release();
+        return SD_OK;
+    }
     sd::DevBuf<sd_prefilter_hit> dHits;
     uint64_t nHits = 0;
     std::vector<uint64_t> hitOff;
