@@ -985,20 +985,52 @@ extern "C" int sd_align_run_batch(sd_context *ctx, const sd_target_index *idx, c
         if (pair_q[k] >= queries->nq || pair_t[k] >= idx->nT) { setError("sd_align_run: pair %llu out of range", (unsigned long long)k); return SD_EINVAL; }
     SD_CUDA(cudaSetDevice(ctx->device));
     sd::StreamScope allocScope(ctx->stream);
-    ScratchBuf<uint32_t> dQ(ctx, SL_AL_PAIRQ), dT(ctx, SL_AL_PAIRT);
-    int rc;
-    if ((rc = dQ.alloc(n_pairs)) || (rc = dT.alloc(n_pairs))) return rc;
-    SD_CUDA(cudaMemcpyAsync(dQ.p, pair_q, n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    SD_CUDA(cudaMemcpyAsync(dT.p, pair_t, n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    // identity of a call (FNV-1a over the arguments, the sizes and a sample of the pairs and query residues), computed only when an
+    // SD_ESMALL result is pending or has to be parked: the retry with larger buffers finds its result in the context
+    auto callKey = [&]() -> uint64_t {
+        uint64_t k = 1469598103934665603ull;
+        auto mix = [&](const void *p, size_t n) { const unsigned char *b = static_cast<const unsigned char *>(p); for (size_t i = 0; i < n; i++) { k ^= b[i]; k *= 1099511628211ull; } };
+        const void *ptrs[1] = {idx};          // (the query batch is identified by its content: sd_align_run builds a new one per call)
+        mix(ptrs, sizeof ptrs); mix(&query_first, sizeof query_first); mix(&n_pairs, sizeof n_pairs); mix(&db_residues, sizeof db_residues);
+        mix(par, sizeof *par); mix(&queries->nq, sizeof queries->nq); mix(&queries->total, sizeof queries->total);
+        const uint64_t sample = std::min<uint64_t>(n_pairs, 4096);
+        mix(pair_q, sample * sizeof(uint32_t)); mix(pair_t, sample * sizeof(uint32_t));
+        mix(pair_q + (n_pairs - sample), sample * sizeof(uint32_t)); mix(pair_t + (n_pairs - sample), sample * sizeof(uint32_t));
+        const size_t rs = std::min<size_t>(queries->hostCode.size(), 4096);
+        mix(queries->hostCode.data(), rs); mix(queries->hostCode.data() + (queries->hostCode.size() - rs), rs);
+        return k ? k : 1;
+    };
+    const uint64_t key = ctx->esmallKey ? callKey() : 0;
     std::vector<sd_alignment> acc;
     sd::CharPool pool;
-    if ((rc = sd_align_device_pairs(ctx, idx, queries, query_first, dQ.p, dT.p, n_pairs, db_residues, par, acc, pool, stats))) return rc;
+    int rc;
+    if (ctx->esmallKey && ctx->esmallKey == key) {
+        acc.swap(ctx->esmallAlns);
+        pool.swap(ctx->esmallPool);
+        if (stats) *stats = ctx->esmallStats;
+        ctx->esmallKey = 0;
+    } else {
+        ctx->esmallKey = 0;
+        ctx->esmallAlns.clear(); ctx->esmallAlns.shrink_to_fit();
+        ctx->esmallPool.clear(); ctx->esmallPool.shrink_to_fit();
+        ScratchBuf<uint32_t> dQ(ctx, SL_AL_PAIRQ), dT(ctx, SL_AL_PAIRT);
+        if ((rc = dQ.alloc(n_pairs)) || (rc = dT.alloc(n_pairs))) return rc;
+        SD_CUDA(cudaMemcpyAsync(dQ.p, pair_q, n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        SD_CUDA(cudaMemcpyAsync(dT.p, pair_t, n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        sd_align_stats localStats;
+        if ((rc = sd_align_device_pairs(ctx, idx, queries, query_first, dQ.p, dT.p, n_pairs, db_residues, par, acc, pool, &localStats))) return rc;
+        if (stats) *stats = localStats;
+        ctx->esmallStats = localStats;
+    }
     uint64_t used = 0;
     for (const sd_alignment &a : acc) used += a.bt_len;
     *n_out = acc.size();
     *bt_used = used;
     if (acc.size() > cap || used > bt_cap || (acc.size() && (!out || !bt_pool))) {
         setError("sd_align_run: needs %zu alignments / %llu backtrace bytes", acc.size(), (unsigned long long)used);
+        ctx->esmallAlns.swap(acc);       // kept for the retry with the same arguments
+        ctx->esmallPool.swap(pool);
+        ctx->esmallKey = callKey();
         return SD_ESMALL;
     }
     if (!acc.empty()) memcpy(out, acc.data(), acc.size() * sizeof(sd_alignment));

@@ -253,6 +253,12 @@ struct sd_context {
     // align: smallest passing raw score per query length for (database residues, -e)
     double minScoreDb = -1, minScoreThr = -1;
     std::vector<int32_t> minScoreByLen;
+    // sd_align_run[_batch]: a call that ends with SD_ESMALL keeps its result here, so that the caller's retry with larger buffers
+    // (same arguments) copies it out instead of aligning everything again
+    std::vector<sd_alignment> esmallAlns;
+    sd::CharPool esmallPool;
+    sd_align_stats esmallStats;
+    uint64_t esmallKey = 0;
 };
 
 struct sd_query_batch {
