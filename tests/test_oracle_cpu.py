@@ -95,6 +95,24 @@ def test_oracle_clustersearch_vs_reference(ref_setdb, synth_small):
     assert len(ref) > 5
 
 
+def test_oracle_clustersearch_c5_flags_vs_reference(ref_setdb, synth_small):
+    """BASELINE config 5's clustering flags (--max-gene-gap 10 --cluster-size 5): reference TSV == oracle pipeline."""
+    d = ref_setdb
+    db = os.path.join(d, "setDB")
+    out = os.path.join(d, "res_c5.tsv")
+    helpers.run_ref(["clustersearch", db, db, out, os.path.join(d, "tmpcs_c5"), "--filter-self-match", "1", "--max-gene-gap", "10",
+                     "--cluster-size", "5", "--threads", "2", "-v", "1"])
+    o = helpers.oracle_clustersearch(synth_small, filter_self_match=True, max_gene_gap=10, cluster_size=5)
+    src = {}
+    for line in open(db + ".source"):
+        a = line.rstrip("\n").split("\t")
+        src[a[1]] = int(a[0])
+    name_to_key = {v: k for k, v in o["lookup"].items()}
+    ref = helpers.parse_result_tsv(out, src, name_to_key)
+    assert ref == helpers.canonical_clusters(o["clusters"])
+    assert len(ref) > 2 and all(len(c[-1]) >= 5 for c in ref)
+
+
 def _saturated_family(n_copies=60, n_unrelated=20, length=300, seed=9):
     """One ancestral protein in many close copies (88-97 % identity: every pair's diagonal score is far above the 8-bit
     cap) plus unrelated proteins, as ONE proteome in Prodigal form."""
