@@ -1,6 +1,8 @@
 // MMseqs2 flat-file DB access (see dbio.h).
 #include "dbio.h"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -34,6 +36,76 @@ static inline uint64_t parseU64(const char *&p) {
     return v;
 }
 
+// zstd is resolved at run time (libzstd.so.1; no header in this image): only compressed DBs need it
+namespace {
+struct ZstdApi {
+    void *h = nullptr;
+    size_t (*decompress)(void *, size_t, const void *, size_t) = nullptr;
+    unsigned (*isError)(size_t) = nullptr;
+    const char *(*errorName)(size_t) = nullptr;
+};
+ZstdApi &zstd() {
+    static ZstdApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        for (const char *name : {"libzstd.so.1", "libzstd.so"}) {
+            api.h = dlopen(name, RTLD_NOW);
+            if (api.h) break;
+        }
+        if (api.h) {
+            api.decompress = reinterpret_cast<decltype(api.decompress)>(dlsym(api.h, "ZSTD_decompress"));
+            api.isError = reinterpret_cast<decltype(api.isError)>(dlsym(api.h, "ZSTD_isError"));
+            api.errorName = reinterpret_cast<decltype(api.errorName)>(dlsym(api.h, "ZSTD_getErrorName"));
+        }
+    }
+    return api;
+}
+}  // namespace
+
+// A DB written with --compressed 1 (DBWriter::writeEnd, DBWriter.cpp:326-395): every entry is [u32 n][n bytes][marker]; marker 0 = the
+// n bytes are one zstd frame, 0xFF = stored as they are; the index keeps the ORIGINAL length (+ terminator).  The entries are
+// expanded once into the layout of a plain DB (what DBReader::getDataCompressed does per access, DBReader.cpp:560-587).
+bool Db::inflate(const std::string &path, std::string &err) {
+    ZstdApi &z = zstd();
+    std::string plain;
+    uint64_t total = 0;
+    for (const Entry &e : index) total += e.len;
+    plain.reserve(total);
+    // in ascending offset, so that the expanded entries keep their relative order (DBReader ids of LINEAR_ACCCESS follow the offsets)
+    std::vector<size_t> order(index.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return index[a].off < index[b].off; });
+    for (size_t oi : order) {
+        Entry &e = index[oi];
+        if (e.off + 5 > data.size()) { err = "index entry beyond the data file in " + path; return false; }
+        uint32_t n;
+        memcpy(&n, data.data() + e.off, 4);
+        const char *payload = data.data() + e.off + 4;
+        if (e.off + 4 + (uint64_t)n + 1 > data.size()) { err = "compressed entry beyond the data file in " + path; return false; }
+        const bool isFrame = payload[n] == 0;
+        const uint64_t newOff = plain.size();
+        if (isFrame) {
+            if (!z.decompress || !z.isError) { err = path + " is a compressed DB (--compressed 1) and libzstd.so.1 could not be loaded"; return false; }
+            const size_t want = e.len ? (size_t)e.len - 1 : 0;
+            plain.resize(newOff + want + 1);
+            const size_t got = z.decompress(&plain[newOff], want, payload, n);
+            if (z.isError(got) || got != want) {
+                err = path + ": zstd entry " + std::to_string(e.key) + " does not decompress to its indexed length (" + (z.isError(got) && z.errorName ? z.errorName(got) : "size mismatch") + ")";
+                return false;
+            }
+            plain[newOff + want] = '\0';
+        } else {
+            plain.append(payload, n);
+            plain.push_back('\0');
+            e.len = (uint64_t)n + 1;
+        }
+        e.off = newOff;
+    }
+    data.swap(plain);
+    return true;
+}
+
 bool Db::open(const std::string &path, std::string &err) {
     data.clear();
     index.clear();
@@ -46,6 +118,15 @@ bool Db::open(const std::string &path, std::string &err) {
             i++;
         }
         if (i == 0 && !fileExists(path + ".index")) { err = "database " + path + " does not exist"; return false; }
+    }
+    std::string t;
+    dbtype = -1;
+    bool compressed = false;
+    if (readFile(path + ".dbtype", t) && t.size() >= 4) {
+        uint32_t v;
+        memcpy(&v, t.data(), 4);
+        dbtype = (int)(v & 0xffff);
+        compressed = (v & 0x80000000u) != 0;      // bit 31: entries are zstd frames (Parameters.h:90-94, DBWriter.cpp:326-395)
     }
     std::string idx;
     if (!readFile(path + ".index", idx)) { err = "cannot read " + path + ".index"; return false; }
@@ -61,18 +142,10 @@ bool Db::open(const std::string &path, std::string &err) {
         e.len = parseU64(p);
         while (*p && *p != '\n') p++;
         if (*p == '\n') p++;
-        if (e.off + e.len > data.size()) { err = "index entry beyond the data file in " + path; return false; }
+        if (!compressed && e.off + e.len > data.size()) { err = "index entry beyond the data file in " + path; return false; }
         index.push_back(e);
     }
-    std::string t;
-    dbtype = -1;
-    if (readFile(path + ".dbtype", t) && t.size() >= 4) {
-        uint32_t v;
-        memcpy(&v, t.data(), 4);
-        dbtype = (int)(v & 0xffff);
-        // bit 31 = entries are zstd-compressed (Parameters.h:90-94, DBReader decompresses them): not read here
-        if (v & 0x80000000u) { err = path + " is a compressed DB (--compressed 1): not supported, re-create it with --compressed 0"; return false; }
-    }
+    if (compressed && !inflate(path, err)) return false;
     return true;
 }
 

@@ -26,6 +26,7 @@ struct Db {
     std::vector<Entry> index;   // file order of <db>.index
     int dbtype = -1;
     bool open(const std::string &path, std::string &err);
+    bool inflate(const std::string &path, std::string &err);     // compressed DB -> plain layout (called by open)
     // entry payload without the trailing '\0'
     const char *ptr(const Entry &e) const { return data.data() + e.off; }
     size_t size(const Entry &e) const { return e.len ? (size_t)e.len - 1 : 0; }

@@ -323,3 +323,33 @@ def test_aggregation_modules_edge_cases_vs_reference():
             assert a == b and len(a) > 0, n
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def test_compressed_dbs_are_read():
+    """DBs written by the reference with --compressed 1 (zstd frames per entry, DBWriter.cpp:326-395) are expanded on open: a text
+    module gives the same output on the compressed and on the plain set DB, and the compressed _set_size / _member_to_set side DBs
+    feed besthitbyset like the plain ones."""
+    if not helpers.have_ref():
+        pytest.skip("oracle/_ref/spacedust not built")
+    d = tempfile.mkdtemp(prefix="sdfe_")
+    try:
+        prot = synth.generate(2, 30, seed=4)
+        paths = synth.write_fasta(prot, os.path.join(d, "faa"))
+        for c in ("0", "1"):
+            helpers.run_ref(["createsetdb"] + paths + [os.path.join(d, "set" + c), os.path.join(d, "tmp" + c), "--compressed", c, "-v", "1"])
+        assert open(os.path.join(d, "set1.dbtype"), "rb").read()[3] & 0x80 and not open(os.path.join(d, "set0.dbtype"), "rb").read()[3] & 0x80
+        for c in ("0", "1"):
+            subprocess.run([SDB200, "prefixid", os.path.join(d, "set" + c), os.path.join(d, "p" + c)], check=True)
+        a, b = helpers.read_db(os.path.join(d, "p0")), helpers.read_db(os.path.join(d, "p1"))
+        assert a == b and len(a) == 60
+        keys = sorted(a)
+        rec = "%d\t%d\t0.9\t%s\t0\t9\t10\t0\t9\t10\t10M\n"
+        ents = [(k, ((str(k) + "\t" + rec % (keys[40], 50, "1E-20")) if k == keys[1] else "").encode()) for k in keys]
+        _write_db(os.path.join(d, "prefixed"), ents, b"\x05\0\0\0")
+        for c in ("0", "1"):
+            subprocess.run([SDB200, "besthitbyset", os.path.join(d, "set" + c), os.path.join(d, "set" + c), os.path.join(d, "prefixed"),
+                            os.path.join(d, "agg" + c)], check=True)
+        a, b = helpers.read_db(os.path.join(d, "agg0")), helpers.read_db(os.path.join(d, "agg1"))
+        assert a == b and any(v for v in a.values())
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
