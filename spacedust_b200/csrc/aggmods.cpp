@@ -59,7 +59,7 @@ void checkFlags(const Cli &c, std::initializer_list<const char *> implemented) {
         bool ok = false;
         for (const char *f : implemented) ok = ok || kv.first == f;
         for (int i = 0; inert[i] && !ok; i++) ok = kv.first == inert[i];
-        if (kv.first == "--compressed" && kv.second != "0") fail("--compressed 1 is not implemented");
+        if (kv.first == "--compressed") sddb::setCompressedOutput(kv.second != "0");
         if (kv.first == "--tsv" && kv.second != "0") fail("--tsv 1 is not implemented");
         if (kv.first == "--simple-best-hit" && kv.second != "1") fail("--simple-best-hit 0 is not implemented (only 1, the value the clustersearch workflow passes)");
         if (kv.first == "--suboptimal-hits" && kv.second != "0") fail("--suboptimal-hits > 0 is not implemented");

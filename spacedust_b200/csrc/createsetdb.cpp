@@ -65,6 +65,7 @@ int modCreatesetdb(int argc, char **argv) {
         if (s[0] == '-' && s[1] != '\0') {
             if (!strcmp(s, "--gff-dir") || !strcmp(s, "--gff-type")) fail("nucleotide input with --gff-dir is not implemented (protein FASTA only)");
             if (i + 1 >= argc) fail(std::string("flag ") + s + " needs a value");
+            if (!strcmp(s, "--compressed") && atoi(argv[i + 1]) != 0) sddb::setCompressedOutput(true);      // zstd frames, like DBWriter
             i++;        // reference flags (--threads, -v, --remove-tmp-files ...) do not change the files written here
         } else pos.push_back(s);
     }

@@ -43,7 +43,10 @@ struct ZstdApi {
     size_t (*decompress)(void *, size_t, const void *, size_t) = nullptr;
     unsigned (*isError)(size_t) = nullptr;
     const char *(*errorName)(size_t) = nullptr;
+    size_t (*compress)(void *, size_t, const void *, size_t, int) = nullptr;
+    size_t (*compressBound)(size_t) = nullptr;
 };
+bool g_compressOutput = false;
 ZstdApi &zstd() {
     static ZstdApi api;
     static bool tried = false;
@@ -57,6 +60,8 @@ ZstdApi &zstd() {
             api.decompress = reinterpret_cast<decltype(api.decompress)>(dlsym(api.h, "ZSTD_decompress"));
             api.isError = reinterpret_cast<decltype(api.isError)>(dlsym(api.h, "ZSTD_isError"));
             api.errorName = reinterpret_cast<decltype(api.errorName)>(dlsym(api.h, "ZSTD_getErrorName"));
+            api.compress = reinterpret_cast<decltype(api.compress)>(dlsym(api.h, "ZSTD_compress"));
+            api.compressBound = reinterpret_cast<decltype(api.compressBound)>(dlsym(api.h, "ZSTD_compressBound"));
         }
     }
     return api;
@@ -274,7 +279,29 @@ void DbWriter::add(uint32_t key, const char *p, size_t n) {
     index_.push_back(e);
 }
 
+void setCompressedOutput(bool on) { g_compressOutput = on; }
+
 bool DbWriter::close(std::string &err) {
+    if (g_compressOutput) {
+        // every entry becomes [u32 n][zstd frame of n bytes][0]; the index keeps the data offset of the record and the ORIGINAL length
+        ZstdApi &z = zstd();
+        if (!z.compress || !z.compressBound || !z.isError) { err = "--compressed 1: libzstd.so.1 could not be loaded"; return false; }
+        std::string packed;
+        std::string frame;
+        for (Entry &e : index_) {
+            const size_t n = (size_t)e.len - 1;
+            frame.resize(z.compressBound(n));
+            const size_t got = z.compress(&frame[0], frame.size(), data_.data() + e.off, n, 3);      // level 3 (Parameters: --compress-level... default)
+            if (z.isError(got)) { err = "zstd compression failed for " + path_; return false; }
+            const uint32_t n32 = (uint32_t)got;
+            e.off = packed.size();
+            packed.append(reinterpret_cast<const char *>(&n32), 4);
+            packed.append(frame.data(), got);
+            packed.push_back('\0');
+        }
+        data_.swap(packed);
+        dbtype_ = (int)((uint32_t)dbtype_ | 0x80000000u);
+    }
     FILE *f = fopen(path_.c_str(), "wb");
     if (!f) { err = "cannot write " + path_; return false; }
     if (!data_.empty() && fwrite(data_.data(), 1, data_.size(), f) != data_.size()) { fclose(f); err = "short write on " + path_; return false; }

@@ -51,6 +51,10 @@ struct SetDb {
     bool open(const std::string &path, std::string &err);
 };
 
+// --compressed 1 of the calling module: every DbWriter closed afterwards writes zstd frames ([u32 n][frame][0], index lengths =
+// original sizes, dbtype bit 31: DBWriter.cpp:326-395).  The frames need not equal the reference's byte for byte, only expand to the same.
+void setCompressedOutput(bool on);
+
 // Collects entries and writes <path>, <path>.index (sorted by key, stable) and <path>.dbtype like a merged DBWriter result.
 class DbWriter {
 public:

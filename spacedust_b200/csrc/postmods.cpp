@@ -232,7 +232,7 @@ int modSubtractdbs(int argc, char **argv) {
     const double evalThr = flags.count("-e") ? strtod(flags["-e"].c_str(), nullptr) : 0.001;
     const double evalProfile = flags.count("--e-profile") ? strtod(flags["--e-profile"].c_str(), nullptr) : 0.001;
     const double thr = std::min(evalThr, evalProfile);
-    if (flags.count("--compressed") && atoi(flags["--compressed"].c_str()) != 0) fail("--compressed 1 is not implemented");
+    sddb::setCompressedOutput(flags.count("--compressed") && atoi(flags["--compressed"].c_str()) != 0);
     sddb::Db left, right;
     std::string err;
     if (!left.open(pos[0], err)) fail(err);

@@ -171,7 +171,7 @@ void rejectUnsupported(const Args &a) {
     if (a.num("--spaced-kmer-mode", 1) != 1) die("--spaced-kmer-mode 0 is not implemented");
     if (a.num("--realign", 0) != 0) die("--realign 1 is not implemented");
     if (a.num("--alt-ali", 0) != 0) die("--alt-ali > 0 is not implemented");
-    if (a.num("--compressed", 0) != 0) die("--compressed 1 is not implemented");
+    sddb::setCompressedOutput(a.num("--compressed", 0) != 0);      // result DBs as zstd frames, like DBWriter in compressed mode
     if (a.num("--split", 0) > 1) die("--split > 1 is not implemented (the whole target index fits one B200)");
     if (a.num("--add-self-matches", 0) != 0) die("--add-self-matches 1 is not implemented");
     if (a.num("--cluster-use-weight", 0) != 0) die("--cluster-use-weight 1 is not implemented");

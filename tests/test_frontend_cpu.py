@@ -62,7 +62,7 @@ def test_frontend_rejects_unimplemented_modes():
         paths = synth.write_fasta(synth.generate(2, 5, seed=3), os.path.join(d, "faa"))
         db = os.path.join(d, "setDB")
         subprocess.run([SDB200, "createsetdb"] + paths + [db, os.path.join(d, "tmp")], check=True)
-        for flags in (["--search-mode", "1"], ["--num-iterations", "3"], ["--compressed", "1"]):
+        for flags in (["--search-mode", "1"], ["--num-iterations", "3"], ["--realign", "1"]):
             r = subprocess.run([SDB200, "clustersearch", db, db, os.path.join(d, "o.tsv"), os.path.join(d, "tmp")] + flags,
                                stdout=subprocess.PIPE, stderr=subprocess.PIPE)
             assert r.returncode != 0 and b"not implemented" in r.stderr, flags
@@ -351,5 +351,36 @@ def test_compressed_dbs_are_read():
                             os.path.join(d, "agg" + c)], check=True)
         a, b = helpers.read_db(os.path.join(d, "agg0")), helpers.read_db(os.path.join(d, "agg1"))
         assert a == b and any(v for v in a.values())
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def test_compressed_output_is_read_by_the_reference():
+    """--compressed 1 on our side: the reference reads the zstd DBs we write -- an aggregation module's compressed output expands to
+    the plain one, and the reference's clustersearch on OUR compressed set DB gives the TSV it gives on its own plain set DB."""
+    if not helpers.have_ref():
+        pytest.skip("oracle/_ref/spacedust not built")
+    d = tempfile.mkdtemp(prefix="sdfe_")
+    try:
+        prot = synth.generate(2, 30, seed=4)
+        paths = synth.write_fasta(prot, os.path.join(d, "faa"))
+        helpers.run_ref(["createsetdb"] + paths + [os.path.join(d, "rset"), os.path.join(d, "tmpr"), "-v", "1"])
+        subprocess.run([SDB200, "createsetdb"] + paths + [os.path.join(d, "mset"), os.path.join(d, "tmpm"), "--compressed", "1"], check=True,
+                       stdout=subprocess.DEVNULL)
+        assert open(os.path.join(d, "mset.dbtype"), "rb").read()[3] & 0x80
+        outs = []
+        for db in ("rset", "mset"):
+            out = os.path.join(d, db + ".tsv")
+            helpers.run_ref(["clustersearch", os.path.join(d, db), os.path.join(d, db), out, os.path.join(d, "tmpcs_" + db), "--filter-self-match", "1",
+                             "--threads", "2", "-v", "1"])
+            outs.append(sorted(l for l in open(out) if not l.startswith("#")))
+        assert outs[0] == outs[1] and len(outs[0]) > 3
+        L = os.path.join(d, "tmpcs_rset", "latest")
+        subprocess.run([SDB200, "prefixid", os.path.join(L, "result"), os.path.join(d, "c_prefixed"), "--compressed", "1"], check=True)
+        assert open(os.path.join(d, "c_prefixed.dbtype"), "rb").read()[3] & 0x80
+        assert os.path.getsize(os.path.join(d, "c_prefixed")) < os.path.getsize(os.path.join(L, "result_prefixed"))
+        helpers.run_ref(["besthitbyset", os.path.join(d, "rset"), os.path.join(d, "rset"), os.path.join(d, "c_prefixed"), os.path.join(d, "r_agg"),
+                         "--threads", "1", "-v", "1"])
+        assert helpers.read_db(os.path.join(d, "r_agg")) == helpers.read_db(os.path.join(L, "aggregate"))
     finally:
         shutil.rmtree(d, ignore_errors=True)
