@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "dbio.h"
 
 namespace {
@@ -81,7 +83,25 @@ int modCreatesetdb(int argc, char **argv) {
     for (size_t fi = 0; fi < inputs.size(); fi++) {
         std::string text;
         if (!sddb::readFile(inputs[fi], text)) fail("cannot read " + inputs[fi]);
-        if (text.size() >= 2 && (unsigned char)text[0] == 0x1f && (unsigned char)text[1] == 0x8b) fail(inputs[fi] + ": compressed input is not implemented");
+        if (text.size() >= 2 && (unsigned char)text[0] == 0x1f && (unsigned char)text[1] == 0x8b) {
+            // gzip input (createdb reads it through kseq + zlib, createdb.cpp): zlib resolved at run time
+            static void *hz = dlopen("libz.so.1", RTLD_NOW);
+            using GzOpen = void *(*)(const char *, const char *);
+            using GzRead = int (*)(void *, void *, unsigned);
+            using GzClose = int (*)(void *);
+            GzOpen gzopenFn = hz ? reinterpret_cast<GzOpen>(dlsym(hz, "gzopen")) : nullptr;
+            GzRead gzreadFn = hz ? reinterpret_cast<GzRead>(dlsym(hz, "gzread")) : nullptr;
+            GzClose gzcloseFn = hz ? reinterpret_cast<GzClose>(dlsym(hz, "gzclose")) : nullptr;
+            if (!gzopenFn || !gzreadFn || !gzcloseFn) fail(inputs[fi] + ": gzip input needs libz.so.1, which could not be loaded");
+            void *gz = gzopenFn(inputs[fi].c_str(), "rb");
+            if (!gz) fail("cannot read " + inputs[fi]);
+            text.clear();
+            std::vector<char> chunk(1 << 20);
+            int got;
+            while ((got = gzreadFn(gz, chunk.data(), (unsigned)chunk.size())) > 0) text.append(chunk.data(), (size_t)got);
+            gzcloseFn(gz);
+            if (got < 0) fail(inputs[fi] + ": corrupt gzip stream");
+        }
         source += std::to_string(fi) + "\t" + baseName(inputs[fi]) + "\n";
         std::string members;
         uint32_t geneIdx = 0;

@@ -384,3 +384,26 @@ def test_compressed_output_is_read_by_the_reference():
         assert helpers.read_db(os.path.join(d, "r_agg")) == helpers.read_db(os.path.join(L, "aggregate"))
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def test_createsetdb_gzip_input_vs_reference():
+    """gzip-compressed protein FASTA (createdb reads it through zlib): the same 19 files as the reference's createsetdb, byte for byte."""
+    if not helpers.have_ref():
+        pytest.skip("oracle/_ref/spacedust not built")
+    import gzip
+    d = tempfile.mkdtemp(prefix="sdfe_")
+    try:
+        paths = synth.write_fasta(synth.generate(2, 20, seed=6), os.path.join(d, "faa"))
+        gz = []
+        for p in paths:
+            with open(p, "rb") as f, gzip.open(p + ".gz", "wb") as g:
+                g.write(f.read())
+            gz.append(p + ".gz")
+        os.makedirs(os.path.join(d, "a"))
+        os.makedirs(os.path.join(d, "b"))
+        helpers.run_ref(["createsetdb"] + gz + [os.path.join(d, "a", "setDB"), os.path.join(d, "a", "tmp"), "-v", "1"])
+        subprocess.run([SDB200, "createsetdb"] + gz + [os.path.join(d, "b", "setDB"), os.path.join(d, "b", "tmp")], check=True, stdout=subprocess.DEVNULL)
+        assert _sha(os.path.join(d, "a")) == _sha(os.path.join(d, "b"))
+        assert len(_sha(os.path.join(d, "a"))) == 19
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
