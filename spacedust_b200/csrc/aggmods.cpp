@@ -64,6 +64,8 @@ void checkFlags(const Cli &c, std::initializer_list<const char *> implemented) {
         if (kv.first == "--simple-best-hit" && kv.second != "1") fail("--simple-best-hit 0 is not implemented (only 1, the value the clustersearch workflow passes)");
         if (kv.first == "--suboptimal-hits" && kv.second != "0") fail("--suboptimal-hits > 0 is not implemented");
         if (kv.first == "--aggregation-mode" && kv.second != "0") fail("--aggregation-mode != 0 is not implemented");
+        if (kv.first == "--cluster-use-weight" && kv.second != "0") fail("--cluster-use-weight 1 is not implemented");
+        if (kv.first == "--cluster-use-weight") ok = true;
         if (kv.first == "--db-output" && kv.second != "1") fail("--db-output 0 is not implemented (the modules write DBs, as the clustersearch workflow asks)");
         if (kv.first == "--simple-best-hit" || kv.first == "--suboptimal-hits" || kv.first == "--aggregation-mode" || kv.first == "--db-output") ok = true;
         if (!ok) fail("unknown or unsupported flag " + kv.first + " (it would be ignored; refusing to run)");

@@ -407,3 +407,55 @@ def test_createsetdb_gzip_input_vs_reference():
         assert len(_sha(os.path.join(d, "a"))) == 19
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+def test_reference_child_command_lines_are_accepted(synth_small):
+    """the exact child command lines of the reference's clustersearch workflow (printed with -v 3) replayed through
+    sdb200, flag for flag.  The host-only modules must reproduce the reference's DBs; the modules that need the GPU must get past
+    their flag checks (without a device they stop at sd_context_create, never at an unknown flag)."""
+    if not helpers.have_ref():
+        pytest.skip("oracle/_ref/spacedust not built")
+    import shlex
+    d = tempfile.mkdtemp(prefix="sdfe_")
+    try:
+        paths = synth.write_fasta(synth_small, os.path.join(d, "faa"))
+        helpers.run_ref(["createsetdb"] + paths + ["setDB", "tmp", "-v", "1"], cwd=d)
+        log = helpers.run_ref(["clustersearch", "setDB", "setDB", "ref.tsv", "tmpcs", "--filter-self-match", "1", "--threads", "2", "-v", "3"], cwd=d)
+        mods = ("prefilter", "align", "prefixid", "besthitbyset", "mergeresultsbyset", "combinehits", "clusterhits", "summarizeresults", "filterdb", "swapdb")
+        lines = [l for l in log.splitlines() if l.split(" ")[0] in mods and " setDB" in l or l.startswith(("prefixid ", "filterdb ", "swapdb "))]
+        seen = set()
+        for line in lines:
+            args = shlex.split(line)
+            mod = args[0]
+            if mod in seen:
+                continue
+            seen.add(mod)
+            L = os.path.dirname([a for a in args[1:] if "/" in a][0])
+            # outputs go next to the reference's (suffix _m); inputs are the reference's own files
+            out_pos = {"prefilter": 3, "align": 4, "prefixid": 2, "besthitbyset": 4, "mergeresultsbyset": 3, "combinehits": 4, "clusterhits": 4,
+                       "summarizeresults": 4, "filterdb": 2, "swapdb": 2}[mod]
+            ref_out = args[out_pos]
+            args[out_pos] = ref_out + "_m"
+            r = subprocess.run([SDB200] + args, cwd=d, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            if mod in ("prefilter", "align", "clusterhits"):
+                assert r.returncode == 0 or b"no CUDA device" in r.stderr, (mod, r.stderr[-300:])
+                continue
+            assert r.returncode == 0, (mod, r.stderr[-300:])
+            if mod == "summarizeresults":
+                a = sorted(l for l in open(os.path.join(d, ref_out)) if not l.startswith("#"))
+                b = sorted(l for l in open(os.path.join(d, ref_out + "_m")) if not l.startswith("#"))
+                assert a == b and len(a) > 5
+            elif mod == "combinehits":
+                def pairs(p):
+                    return sorted(zip([x[1] for x in helpers.read_db_entries(p + "_h")], [x[1] for x in helpers.read_db_entries(p)]))
+                assert pairs(os.path.join(d, ref_out)) == pairs(os.path.join(d, ref_out + "_m"))
+            elif mod == "swapdb":
+                a = {k: sorted(v.split()) for k, v in helpers.read_db(os.path.join(d, ref_out)).items()}
+                b = {k: sorted(v.split()) for k, v in helpers.read_db(os.path.join(d, ref_out + "_m")).items()}
+                assert a == b
+            else:
+                assert helpers.read_db(os.path.join(d, ref_out)) == helpers.read_db(os.path.join(d, ref_out + "_m")), mod
+            assert L
+        assert seen == set(mods), seen
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
