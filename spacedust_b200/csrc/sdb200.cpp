@@ -413,6 +413,53 @@ int modAlign(int argc, char **argv) {
 // ------------------------------------------------------------------------------------------------------ clustersearch
 // `createindex <setDB> <tmpDir>`: build the target index once and keep it next to the DB (<setDB>.sdidx) -- the reference's
 // createindex writes <db>.idx, which later searches pick up instead of rebuilding the table (PrefilteringIndexReader).
+// `search <queryDB> <targetDB> <resultDB> <tmpDir> [flags]`: the sequence search of lib/mmseqs/data/workflow/blastp.sh:70-95 (one
+// sensitivity step, --num-iterations 1): prefilter into <tmpDir>/pref_0, then align.  With it, and the aggregation modules, the
+// reference's own data/clustersearch.sh runs with MMSEQS pointing at this binary.
+int modSearch(int argc, char **argv) {
+    Args a = parseArgs(argc, argv, 2);
+    if (a.pos.size() != 4) die("usage: sdb200 search <queryDB> <targetDB> <resultDB> <tmpDir> [flags]");
+    if (a.num("--start-sens", 4) != 4 && a.has("--sens-steps") && a.num("--sens-steps", 1) > 1) die("--sens-steps > 1 is not implemented");
+    for (size_t i = 1; i <= a.pos[3].size(); i++)      // mkdir -p: the search workflow creates its tmp directory itself
+        if (i == a.pos[3].size() || a.pos[3][i] == '/') mkdir(a.pos[3].substr(0, i).c_str(), 0777);
+    const std::string pref = a.pos[3] + "/pref_0";
+    std::vector<std::string> flagTokens;          // every flag with its value, in the order given
+    {
+        size_t seenPos = 0;
+        for (int i = 2; i < argc; i++) {
+            if (argv[i][0] == '-' && argv[i][1] != '\0' && !(argv[i][1] >= '0' && argv[i][1] <= '9')) {
+                flagTokens.push_back(argv[i]);
+                if (i + 1 < argc) flagTokens.push_back(argv[++i]);
+            } else seenPos++;
+        }
+        (void)seenPos;
+    }
+    auto run = [&](int (*fn)(int, char **), std::vector<std::string> args) {
+        args.insert(args.end(), flagTokens.begin(), flagTokens.end());
+        std::vector<char *> av;
+        for (std::string &x : args) av.push_back(&x[0]);
+        return fn((int)av.size(), av.data());
+    };
+    int rc = run(modPrefilter, {argv[0], "prefilter", a.pos[0], a.pos[1], pref});
+    if (rc != EXIT_SUCCESS) return rc;
+    return run(modAlign, {argv[0], "align", a.pos[0], a.pos[1], pref, a.pos[2]});
+}
+
+// `rmdb <db>`: remove a DB and its side files (lib/mmseqs/src/util/rmdb.cpp -> DBReader::removeDb)
+int modRmdb(int argc, char **argv) {
+    Args a = parseArgs(argc, argv, 2);
+    if (a.pos.size() != 1) die("usage: sdb200 rmdb <DB>");
+    const std::string &db = a.pos[0];
+    for (const char *suffix : {"", ".index", ".dbtype", ".lookup", ".source", "_h", "_h.index", "_h.dbtype"}) remove((db + suffix).c_str());
+    for (int i = 0;; i++) {
+        const std::string part = db + "." + std::to_string(i);
+        struct stat stPart;
+        if (stat(part.c_str(), &stPart) != 0) break;
+        remove(part.c_str());
+    }
+    return EXIT_SUCCESS;
+}
+
 int modCreateindex(int argc, char **argv) {
     Args a = parseArgs(argc, argv, 2);
     if (a.pos.size() < 1 || a.pos.size() > 2) die("usage: sdb200 createindex <setDB> [tmpDir] [-s 5.7] [--mask 1] [--mask-prob 0.9]");
@@ -680,13 +727,15 @@ int modClustersearch(int argc, char **argv) {
 
 int main(int argc, char **argv) {
     if (argc < 2) {
-        fprintf(stderr, "sdb200 (libsdgpu %d): createsetdb | createindex | prefilter | align | clustersearch | prefixid | besthitbyset | mergeresultsbyset | combinehits | clusterhits | summarizeresults | filterdb | swapdb | subtractdbs | mergedbs\n", sd_version());
+        fprintf(stderr, "sdb200 (libsdgpu %d): createsetdb | createindex | prefilter | align | search | clustersearch | prefixid | besthitbyset | mergeresultsbyset | combinehits | clusterhits | summarizeresults | filterdb | swapdb | subtractdbs | mergedbs\n", sd_version());
         return EXIT_FAILURE;
     }
     const std::string mod = argv[1];
     if (mod == "createsetdb") return modCreatesetdb(argc, argv);
     if (mod == "createindex") return modCreateindex(argc, argv);
     if (mod == "prefilter") return modPrefilter(argc, argv);
+    if (mod == "search") return modSearch(argc, argv);
+    if (mod == "rmdb") return modRmdb(argc, argv);
     if (mod == "align") return modAlign(argc, argv);
     if (mod == "clustersearch") return modClustersearch(argc, argv);
     if (mod == "summarizeresults") return modSummarizeresults(argc, argv);

@@ -193,3 +193,43 @@ def test_clusterhits_module_and_intermediate_dbs(tmp_path):
     # the reference resumes from our matches DB
     helpers.run_ref(["clusterhits", db, db, os.path.join(mt, "matches"), os.path.join(d, "r_from_mine"), "--db-output", "1", "--threads", "2", "-v", "1"])
     assert pairs(os.path.join(d, "r_from_mine")) == ref_clusters
+
+
+def test_reference_workflow_script_drives_sdb200(tmp_path):
+    """Script-level drop-in: the reference's OWN data/clustersearch.sh (the copy its binary leaves in the tmp dir), with the parameter
+    strings of a real reference run, executed with MMSEQS pointing at sdb200 -- search (prefilter + align), prefixid, besthitbyset,
+    mergeresultsbyset, combinehits, clusterhits, summarizeresults, filterdb, swapdb as separate processes -- gives the reference's TSV."""
+    if not helpers.have_ref():
+        pytest.skip("oracle/_ref/spacedust not built")
+    from spacedust_b200 import synth
+    d = str(tmp_path)
+    prot = synth.generate(3, 120, seed=11)
+    synth.write_fasta(prot, os.path.join(d, "faa"))
+    faa = sorted(os.path.join("faa", f) for f in os.listdir(os.path.join(d, "faa")))
+    helpers.run_ref(["createsetdb"] + faa + ["setDB", "tmp", "-v", "1"], cwd=d)
+    log = helpers.run_ref(["clustersearch", "setDB", "setDB", "ref.tsv", "tmpcs", "--filter-self-match", "1", "--threads", "2", "-v", "3"], cwd=d)
+
+    def par(module, n_pos):
+        line = [l for l in log.splitlines() if l.startswith(module + " ")][0]
+        return " ".join(line.split(" ")[1 + n_pos:]).strip()      # verbatim, as the workflow puts it into the environment
+    env = dict(os.environ)
+    env.update({"MMSEQS": SDB200, "SEARCH_PAR": par("search", 4), "BESTHITBYSET_PAR": par("besthitbyset", 4), "COMBINEHITS_PAR": par("combinehits", 5),
+                "CLUSTERHITS_PAR": par("clusterhits", 4), "THREADS_PAR": par("prefixid", 2), "VERBOSITY": "-v 3"})
+    script = os.path.join(d, "tmpcs", "latest", "clustersearch.sh")
+    os.makedirs(os.path.join(d, "tmpmine"))          # the workflow binary creates the tmp directory before it runs the script
+    r = subprocess.run(["sh", script, "setDB", "setDB", "mine.tsv", "tmpmine"], cwd=d, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout.decode()[-3000:]
+
+    def blocks(path):
+        out, cur = [], None
+        for line in open(path):
+            if line.startswith("#"):
+                cur = [line.split("\t", 1)[1], []]
+                out.append(cur)
+            else:
+                cur[1].append(line)
+        return sorted((a, tuple(b)) for a, b in out)
+    ref = blocks(os.path.join(d, "ref.tsv"))
+    assert blocks(os.path.join(d, "mine.tsv")) == ref and len(ref) > 5
+    for name in ("result", "result_prefixed", "aggregate", "aggregate_merged", "matches", "clusters", "clu_to_seq"):
+        assert os.path.exists(os.path.join(d, "tmpmine", name + ".index")), name
